@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- JPEG pixel-reconstruction throughput (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg4|cfg5]
+
+One "step" = one pass of the hot path (dequant + IDCT + upsample + colour) over
+one batch of synthetic coefficient planes.  Default workload = BASELINE.json
+configs[1]: 4096x4096 baseline 4:4:4 frames (one frame per step per GPU).
+
+Printed JSON (one line, rank 0):
+  value        whole-job MP/s with the planes already resident in HBM (CUDA events,
+               max over ranks)
+  e2e          the same metric through the C-ABI job API with HOST buffers: pinned
+               H2D + kernel + D2H inside the timed region
+  roofline     algorithmic bytes / kernel time against the measured HBM peak
+  cpu_baseline the oracle's reconstruction (GID restated in C; GNAT is not
+               available, so the Ada benchmark cannot be built) on the host cores
+
+`--impl reference` times that CPU restatement alone, with all host threads, on
+the same workload definition, and prints the same line with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "jpeg_reconstruction_throughput"
+UNIT = "MP/s"
+
+WORKLOADS = {
+    # name: (width, height, sampling, frames per step per GPU, description)
+    "cfg2": (4096, 4096, "444", 1, "4096x4096 baseline 4:4:4 frame (BASELINE.json configs[1], kernel roofline case)"),
+    "cfg3": (1920, 1080, "420", 128, "batch of 1920x1080 baseline 4:2:0 frames (configs[2]), 128 frames per step per GPU"),
+    "cfg4": (8192, 8192, "grey", 1, "8192x8192 grey baseline frame (configs[3])"),
+    "cfg5": (2048, 2048, "422", 32, "batch of 2048x2048 4:2:2 frames, full coefficient planes after all scans (configs[4]), 32 per step per GPU"),
+}
+
+
+def env_int(name: str, default: int) -> int:
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def make_frames(workload: str, count: int, seed0: int):
+    """`count` distinct synthetic frames (quantised coefficient planes) of the workload."""
+    from tests.harness import Synth
+    w, h, samp, _, _ = WORKLOADS[workload]
+    S = Synth()
+    frames = []
+    for i in range(count):
+        img = S.image(seed0 + i, w, h)
+        pix = img[:, :, 1].copy() if samp == "grey" else img
+        frames.append(S.planes_only(pix, samp))
+    return frames
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        self.rows: list[str] = []
+        self.proc = None
+        self.index = index
+
+    def start(self) -> None:
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self) -> None:
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[4 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak() -> tuple[float, str]:
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
+
+
+def ncu_traffic(workload: str):
+    """DRAM bytes per launch from the committed ncu capture, if there is one."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[workload]
+    except Exception:
+        return None
+
+
+# --------------------------------------------------------------------------- CPU reference arm
+
+
+def cpu_reconstruct_rate(frames, seconds_target: float, threads: int) -> tuple[float, str]:
+    """Oracle reconstruction (dequant + IDCT + upsample + colour into a top-down RGB
+    buffer, the client of test/benchmark.adb) on `threads` host threads; each thread
+    runs its own copy of the work, as `one process per host core` would."""
+    from tests.harness import Oracle
+    O = Oracle()
+    fr = frames[0]
+    mp = fr.width * fr.height / 1e6
+    t0 = time.perf_counter()
+    O.reconstruct(fr)
+    one = time.perf_counter() - t0
+    reps = max(1, int(round(seconds_target / max(one, 1e-3))))
+    done = [0] * threads
+
+    def work(k: int) -> None:
+        for _ in range(reps):
+            O.reconstruct(frames[k % len(frames)])
+            done[k] += 1
+
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(threads)]
+    t0 = time.perf_counter()
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    dt = time.perf_counter() - t0
+    total_mp = mp * sum(done)
+    sample = f"{reps} x {fr.width}x{fr.height} frame(s) per thread on {threads} thread(s), {dt:.1f} s wall"
+    return total_mp / dt, sample
+
+
+def run_reference(args) -> None:
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    w, h, samp, per_step, desc = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    frames = make_frames(args.workload, 1, 0)
+    # each "step" = a bounded sample of the workload; keep the whole run within a few minutes
+    per_step_seconds = max(0.5, min(4.0, 60.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_reconstruct_rate(frames, per_step_seconds / 4, cores)
+    rates, sample = [], ""
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r, sample = cpu_reconstruct_rate(frames, per_step_seconds, cores)
+        rates.append(r)
+    dt = time.perf_counter() - t0
+    value = float(np.mean(rates))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+        "data": "synthetic", "gpu_launches": 0,
+        "config": {"workload": f"{args.workload}: {desc}", "sampling": samp, "width": w, "height": h},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "per step: " + sample,
+                         "note": "GID's reconstruction restated in C (oracle/gidref.c, gcc -O2); "
+                                 "GNAT is not installed so test/benchmark.adb cannot be built"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- our arm
+
+
+def run_ours(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    from gid_b200 import GidCuda, build, capi
+    from tests.harness import frame_desc
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the reconstruction path has no CPU fallback)")
+    if not os.path.exists(capi.library_path()):
+        build.build_cuda()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    w, h, samp, per_step, desc = WORKLOADS[args.workload]
+    ctx = GidCuda(local)
+
+    # ---- synthetic inputs: a ring of distinct step-batches so that consecutive steps never
+    # reuse L2-resident data (every step-batch is also larger than the 126 MB L2) ---------
+    distinct = 2 if per_step > 1 else 4          # distinct source frames
+    frames = make_frames(args.workload, distinct, 1000 * rank)
+    alg_bytes_frame = frames[0].algorithmic_bytes()
+    ring = max(2, min(4, int(2.5e9 // max(1, alg_bytes_frame * per_step))))
+    descs_one = [frame_desc(f) for f in frames]
+    stride, nbytes = ctx.output_geometry(descs_one[0])
+    keep, plans = [], []
+    for r in range(ring):
+        descs, d_planes, d_pixels = [], [], []
+        for i in range(per_step):
+            fr = frames[(r + i) % distinct]
+            descs.append(descs_one[(r + i) % distinct])
+            for c in range(3):
+                if c < fr.ncomp:
+                    t = torch.from_numpy(fr.planes[c].reshape(-1)).to(dev)
+                    keep.append(t)
+                    d_planes.append(t.data_ptr())
+                else:
+                    d_planes.append(0)
+            out = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            keep.append(out)
+            d_pixels.append(out.data_ptr())
+        plans.append(ctx.plan_create(descs, d_planes, d_pixels))
+    launches_per_step = ctx.plan_launch_count(plans[0])
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier() -> None:
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing --------------------------------------------------------
+    for s in range(args.warmup):
+        ctx.plan_launch(plans[s % ring], stream)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(args.steps):
+        ctx.plan_launch(plans[s % ring], stream)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    # keep the clocks under observation for at least ~0.5 s of the same work
+    t_end = time.perf_counter() + 0.5
+    s = 0
+    while time.perf_counter() < t_end:
+        ctx.plan_launch(plans[s % ring], stream)
+        s += 1
+        if s % 64 == 0:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max = float(t_ms.item())
+    mp_step = w * h * per_step / 1e6
+    value = mp_step * args.steps * world / (ms_max * 1e-3)
+
+    # ---- end to end through the job API: host planes -> host pixels -----------------------
+    L = ctx.lib
+    depth = 2
+    jobs = []
+    for k in range(depth):
+        job = ctypes.c_void_p()
+        fr = frames[k % distinct]
+        d = descs_one[k % distinct]
+        ctx._check(L.gidcuda_job_begin(ctx.ctx, ctypes.byref(d), ctypes.byref(job)), ctx.ctx)
+        for c in range(fr.ncomp):
+            p = L.gidcuda_job_plane(job, c, None, None)
+            ctypes.memmove(p, fr.planes[c].ctypes.data, fr.planes[c].nbytes)
+        jobs.append(job)
+    e2e_frames = max(1, min(per_step, 8))  # frames per e2e step (bounded: host-link limited)
+    pix, st = ctypes.c_void_p(), ctypes.c_size_t()
+    checksum = 0
+
+    def e2e_steps(n: int) -> None:
+        nonlocal checksum
+        total = n * e2e_frames
+        for i in range(total + 1):
+            if i < total:
+                ctx._check(L.gidcuda_job_submit(jobs[i % depth]), ctx.ctx)
+            if i >= 1:
+                ctx._check(L.gidcuda_job_wait(jobs[(i - 1) % depth], ctypes.byref(pix), ctypes.byref(st)), ctx.ctx)
+                # device->host read of the step's result: first and last byte of the host pixel buffer
+                row = (ctypes.c_uint8 * 1).from_address(pix.value)
+                checksum += row[0]
+
+    e2e_steps(max(1, min(args.warmup, 3)))
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps(args.steps)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_value = (w * h * e2e_frames / 1e6) * args.steps * world / float(t_e.item())
+    coef_bytes = sum(p.nbytes for p in frames[0].planes)
+    for job in jobs:
+        L.gidcuda_job_release(job)
+
+    # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        v, sample = cpu_reconstruct_rate(frames[:1], 3.0, cores)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+               "note": "oracle/gidref.c reconstruction only (GID restated in C, gcc -O2); GNAT unavailable"}
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        achieved = alg_bytes_frame * per_step * args.steps / (ms_max * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "sampling": samp, "width": w, "height": h,
+                       "frames_per_step_per_gpu": per_step, "parallelism": f"images sharded over {world} GPU(s), no collective",
+                       "l2": f"inputs larger than L2: ring of {ring} step-batches of {alg_bytes_frame * per_step / 1e6:.0f} MB each"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": coef_bytes * e2e_frames,
+                    "d2h_bytes_per_step": nbytes * e2e_frames, "frames_per_step": e2e_frames,
+                    "api": "gidcuda_job_submit/wait, pinned host planes -> pinned host pixels, 2 jobs in flight"},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": ncu_traffic(args.workload), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes_frame * per_step},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    for p in plans:
+        ctx.plan_destroy(p)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg2")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

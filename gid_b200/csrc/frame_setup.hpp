@@ -1,0 +1,148 @@
+// frame_setup.hpp -- frame geometry and device descriptor set-up, plain C++
+// (no CUDA runtime dependency) so that tests can drive the host-compiled
+// kernel body with exactly the descriptors the shim builds.
+#pragma once
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/gidcuda.h"
+#include "recon_body.cuh"
+
+namespace gidk {
+
+constexpr int kTileMcusSetup = 128;  // = kTileMcus of recon_launch.h
+
+inline int geo_fail(std::string *err, int code, const char *fmt, ...) {
+  if (err) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    *err = buf;
+  }
+  return code;
+}
+
+struct Geometry {
+  int ncomp = 0, hmax = 1, vmax = 1, mcux = 0, mcuy = 0;
+  int bx[3] = {0, 0, 0}, by[3] = {0, 0, 0};
+  size_t plane_bytes[3] = {0, 0, 0};
+  size_t plane_off[3] = {0, 0, 0};  // offsets inside one contiguous coefficient buffer
+  size_t coef_bytes = 0;
+  size_t stride = 0, pixel_bytes = 0;
+  size_t sample_off[3] = {0, 0, 0}, sample_bytes = 0;  // generic layout scratch
+  Layout layout = LAYOUT_GENERIC;
+  bool q8 = true;
+  int out_format = 0;
+  uint32_t ntiles = 0;
+};
+
+inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Validates a frame descriptor and derives everything the launch needs.
+// Mirrors Read_SOF / Read_SOS geometry (gid-decoding_jpg.adb:244-276, :1945-1951).
+inline int make_geometry(std::string *err, const gidcuda_frame_desc *d, Geometry *g) {
+  if (!d) return geo_fail(err, GIDCUDA_ERR_BAD_ARGUMENT, "null frame descriptor");
+  if (d->width < 1 || d->width > 65535 || d->height < 1 || d->height > 65535)
+    return geo_fail(err, GIDCUDA_ERR_BAD_ARGUMENT, "frame size %d x %d out of range 1..65535",
+                d->width, d->height);
+  if (d->ncomp != 1 && d->ncomp != 3)
+    return geo_fail(err, GIDCUDA_ERR_UNSUPPORTED,
+                "%d components: only Y and YCbCr frames are decoded (gid-decoding_jpg.adb:298-317)",
+                d->ncomp);
+  g->ncomp = d->ncomp;
+  g->hmax = g->vmax = 1;
+  for (int c = 0; c < d->ncomp; c++) {
+    if (d->samp_h[c] < 1 || d->samp_h[c] > 4 || d->samp_v[c] < 1 || d->samp_v[c] > 4)
+      return geo_fail(err, GIDCUDA_ERR_BAD_ARGUMENT, "component %d: sampling factors %d x %d", c,
+                  d->samp_h[c], d->samp_v[c]);
+    if (d->samp_h[c] > g->hmax) g->hmax = d->samp_h[c];
+    if (d->samp_v[c] > g->vmax) g->vmax = d->samp_v[c];
+  }
+  for (int c = 0; c < d->ncomp; c++)
+    if (g->hmax % d->samp_h[c] != 0 || g->vmax % d->samp_v[c] != 0)
+      return geo_fail(err, GIDCUDA_ERR_UNSUPPORTED,
+                  "component %d: non-integer upsampling factor (GID needs max_samples / samples "
+                  "to be exact, gid-decoding_jpg.adb:274-275)", c);
+  if (d->ncomp == 1 && (d->samp_h[0] != 1 || d->samp_v[0] != 1))
+    return geo_fail(err, GIDCUDA_ERR_UNSUPPORTED,
+                "grey frame with sampling factors other than 1x1 (single-component scans are "
+                "8x8 MCUs, gid-decoding_jpg.adb:1952-1971)");
+  g->mcux = (d->width + 8 * g->hmax - 1) / (8 * g->hmax);
+  g->mcuy = (d->height + 8 * g->vmax - 1) / (8 * g->vmax);
+  size_t off = 0, soff = 0;
+  g->q8 = true;
+  for (int c = 0; c < d->ncomp; c++) {
+    g->bx[c] = g->mcux * d->samp_h[c];
+    g->by[c] = g->mcuy * d->samp_v[c];
+    g->plane_bytes[c] = (size_t)g->bx[c] * g->by[c] * 128;
+    g->plane_off[c] = off;
+    off += round_up(g->plane_bytes[c], 256);
+    g->sample_off[c] = soff;
+    soff += round_up((size_t)g->bx[c] * g->by[c] * 64, 256);
+    for (int i = 0; i < 64; i++)
+      if (d->qt[c][i] > 255) g->q8 = false;
+  }
+  g->coef_bytes = off;
+  g->sample_bytes = soff;
+  g->out_format = (int)(d->flags & GIDCUDA_OUT_MASK);
+  if (g->out_format != (int)GIDCUDA_OUT_RGB8 && g->out_format != (int)GIDCUDA_OUT_BGR8_BOTTOM_UP)
+    return geo_fail(err, GIDCUDA_ERR_BAD_ARGUMENT, "unknown output format %d", g->out_format);
+  const size_t packed = (size_t)3 * d->width;
+  if (d->out_stride != 0) {
+    if ((size_t)d->out_stride < packed)
+      return geo_fail(err, GIDCUDA_ERR_BAD_ARGUMENT, "out_stride %d < 3 * width", d->out_stride);
+    g->stride = (size_t)d->out_stride;
+  } else if (g->out_format == (int)GIDCUDA_OUT_BGR8_BOTTOM_UP) {
+    g->stride = round_up(packed, 4);  // BMP rows, test/to_bmp.adb:94-102
+  } else if (d->flags & GIDCUDA_FLAG_PACKED_ROWS) {
+    g->stride = packed;
+  } else {
+    g->stride = round_up(packed, 16);
+  }
+  g->pixel_bytes = g->stride * (size_t)d->height;
+  if (d->ncomp == 1) {
+    g->layout = LAYOUT_GREY;
+  } else if (d->samp_h[1] == 1 && d->samp_v[1] == 1 && d->samp_h[2] == 1 && d->samp_v[2] == 1) {
+    if (d->samp_h[0] == 1 && d->samp_v[0] == 1) g->layout = LAYOUT_444;
+    else if (d->samp_h[0] == 2 && d->samp_v[0] == 1) g->layout = LAYOUT_422;
+    else if (d->samp_h[0] == 2 && d->samp_v[0] == 2) g->layout = LAYOUT_420;
+    else g->layout = LAYOUT_GENERIC;
+  } else {
+    g->layout = LAYOUT_GENERIC;
+  }
+  g->ntiles = (uint32_t)(((size_t)g->mcux * g->mcuy + kTileMcusSetup - 1) / kTileMcusSetup);
+  return GIDCUDA_OK;
+}
+
+inline void fill_frame_dev(const gidcuda_frame_desc *d, const Geometry &g, const int16_t *const planes[3],
+                    uint8_t *pixels, uint8_t *samples, uint32_t tile_base, FrameDev *f) {
+  memset(f, 0, sizeof *f);
+  for (int c = 0; c < g.ncomp; c++) {
+    f->plane[c] = planes[c];
+    f->bx[c] = g.bx[c];
+    f->by[c] = g.by[c];
+    f->samp_h[c] = d->samp_h[c];
+    f->samp_v[c] = d->samp_v[c];
+    f->samples[c] = samples ? samples + g.sample_off[c] : nullptr;
+    for (int k = 0; k < 32; k++) {
+      const uint32_t lo = d->qt[c][2 * k], hi = d->qt[c][2 * k + 1];
+      f->qw[c][k] = g.q8 ? (lo | (hi << 24)) : (lo | (hi << 16));
+    }
+  }
+  f->pixels = pixels;
+  f->stride = (uint32_t)g.stride;
+  f->width = d->width;
+  f->height = d->height;
+  f->mcux = g.mcux;
+  f->mcuy = g.mcuy;
+  f->out_format = g.out_format;
+  f->tile_base = tile_base;
+  f->q8 = g.q8 ? 1 : 0;
+}
+
+}  // namespace gidk

@@ -1,0 +1,804 @@
+// gidcuda.cu -- C-ABI shim of the B200 reconstruction path (include/gidcuda.h).
+//
+// Owns pinned host buffers, device buffers, streams and launches; the Ada
+// binding GID.CUDA and the C++ host mirror only see plain pointers and sizes.
+// No CPU fallback: every compute entry point needs a CUDA device.
+#include "../../include/gidcuda.h"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "frame_setup.hpp"
+#include "recon_launch.h"
+
+using gidk::FrameDev;
+using gidk::Layout;
+
+// ---------------------------------------------------------------------------
+// errors
+
+static thread_local std::string t_last_error;
+
+struct gidcuda_ctx {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  std::string last_error;
+  std::vector<gidcuda_job *> free_jobs;  // recycled jobs (buffers kept)
+  int live_jobs = 0;
+};
+
+static int fail(gidcuda_ctx *ctx, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  t_last_error = buf;
+  if (ctx) ctx->last_error = buf;
+  return code;
+}
+
+#define CU_TRY(ctx, call)                                                                  \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess)                                                                 \
+      return fail((ctx), e_ == cudaErrorMemoryAllocation ? GIDCUDA_ERR_OUT_OF_MEMORY       \
+                                                         : GIDCUDA_ERR_CUDA,               \
+                  "%s failed: %s", #call, cudaGetErrorString(e_));                         \
+  } while (0)
+
+// ---------------------------------------------------------------------------
+// geometry (frame_setup.hpp)
+
+using gidk::Geometry;
+using gidk::fill_frame_dev;
+using gidk::round_up;
+
+static int geometry_or_fail(gidcuda_ctx *ctx, const gidcuda_frame_desc *d, Geometry *g) {
+  std::string err;
+  const int rc = gidk::make_geometry(&err, d, g);
+  if (rc != GIDCUDA_OK) return fail(ctx, rc, "%s", err.c_str());
+  return rc;
+}
+
+// ---------------------------------------------------------------------------
+// library / device
+
+extern "C" int gidcuda_abi_version(void) { return GIDCUDA_ABI_VERSION; }
+
+extern "C" int gidcuda_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+extern "C" const char *gidcuda_last_error(const gidcuda_ctx *ctx) {
+  return ctx ? ctx->last_error.c_str() : t_last_error.c_str();
+}
+
+extern "C" int gidcuda_create(int device, gidcuda_ctx **out) {
+  if (!out) return fail(nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "null ctx pointer");
+  *out = nullptr;
+  const int n = gidcuda_device_count();
+  if (n == 0)
+    return fail(nullptr, GIDCUDA_ERR_NO_DEVICE,
+                "no CUDA device: the reconstruction path has no CPU fallback");
+  if (device < 0 || device >= n)
+    return fail(nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "device %d out of range 0..%d", device, n - 1);
+  gidcuda_ctx *ctx = new (std::nothrow) gidcuda_ctx();
+  if (!ctx) return fail(nullptr, GIDCUDA_ERR_OUT_OF_MEMORY, "out of host memory");
+  ctx->device = device;
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete ctx;
+    return fail(nullptr, GIDCUDA_ERR_CUDA, "cannot initialise device %d: %s", device,
+                cudaGetErrorString(e));
+  }
+  *out = ctx;
+  return GIDCUDA_OK;
+}
+
+extern "C" int gidcuda_plane_geometry(const gidcuda_frame_desc *desc, int comp, int32_t *blocks_x,
+                                      int32_t *blocks_y) {
+  Geometry g;
+  int rc = geometry_or_fail(nullptr, desc, &g);
+  if (rc != GIDCUDA_OK) return rc;
+  if (comp < 0 || comp >= g.ncomp) return fail(nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "component %d", comp);
+  if (blocks_x) *blocks_x = g.bx[comp];
+  if (blocks_y) *blocks_y = g.by[comp];
+  return GIDCUDA_OK;
+}
+
+extern "C" int gidcuda_output_geometry(const gidcuda_frame_desc *desc, size_t *stride, size_t *bytes) {
+  Geometry g;
+  int rc = geometry_or_fail(nullptr, desc, &g);
+  if (rc != GIDCUDA_OK) return rc;
+  if (stride) *stride = g.stride;
+  if (bytes) *bytes = g.pixel_bytes;
+  return GIDCUDA_OK;
+}
+
+extern "C" int gidcuda_host_alloc(size_t bytes, void **ptr) {
+  if (!ptr) return fail(nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "null pointer");
+  *ptr = nullptr;
+  if (gidcuda_device_count() == 0) return fail(nullptr, GIDCUDA_ERR_NO_DEVICE, "no CUDA device");
+  CU_TRY(nullptr, cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable));
+  return GIDCUDA_OK;
+}
+
+extern "C" int gidcuda_host_free(void *ptr) {
+  if (ptr) CU_TRY(nullptr, cudaFreeHost(ptr));
+  return GIDCUDA_OK;
+}
+
+// ---------------------------------------------------------------------------
+// jobs
+
+struct gidcuda_job {
+  gidcuda_ctx *ctx = nullptr;
+  gidcuda_frame_desc desc;
+  Geometry geo;
+  // capacities of the recycled buffers
+  size_t cap_coef = 0, cap_pixels = 0, cap_samples = 0;
+  uint8_t *h_coef = nullptr;    // pinned: planes, contiguous
+  uint8_t *h_pixels = nullptr;  // pinned
+  uint8_t *d_coef = nullptr, *d_pixels = nullptr, *d_samples = nullptr;
+  FrameDev *d_frame = nullptr;
+  FrameDev *h_frame = nullptr;  // pinned staging of the descriptor
+  cudaEvent_t done = nullptr;
+  cudaStream_t stream = nullptr;  // one stream per job: two jobs in flight overlap H2D and D2H
+  enum { IDLE, BEGUN, SUBMITTED } state = IDLE;
+};
+
+static void job_free_buffers(gidcuda_job *j) {
+  if (j->h_coef) cudaFreeHost(j->h_coef);
+  if (j->h_pixels) cudaFreeHost(j->h_pixels);
+  if (j->h_frame) cudaFreeHost(j->h_frame);
+  if (j->d_coef) cudaFree(j->d_coef);
+  if (j->d_pixels) cudaFree(j->d_pixels);
+  if (j->d_samples) cudaFree(j->d_samples);
+  if (j->d_frame) cudaFree(j->d_frame);
+  if (j->done) cudaEventDestroy(j->done);
+  if (j->stream) cudaStreamDestroy(j->stream);
+  j->stream = nullptr;
+  j->h_coef = j->h_pixels = j->d_coef = j->d_pixels = j->d_samples = nullptr;
+  j->h_frame = nullptr;
+  j->d_frame = nullptr;
+  j->done = nullptr;
+  j->cap_coef = j->cap_pixels = j->cap_samples = 0;
+}
+
+static int job_reserve(gidcuda_job *j) {
+  gidcuda_ctx *ctx = j->ctx;
+  const Geometry &g = j->geo;
+  if (!j->done) CU_TRY(ctx, cudaEventCreateWithFlags(&j->done, cudaEventDisableTiming));
+  if (!j->stream) CU_TRY(ctx, cudaStreamCreateWithFlags(&j->stream, cudaStreamNonBlocking));
+  if (!j->d_frame) CU_TRY(ctx, cudaMalloc(&j->d_frame, sizeof(FrameDev)));
+  if (!j->h_frame) CU_TRY(ctx, cudaHostAlloc((void **)&j->h_frame, sizeof(FrameDev), cudaHostAllocDefault));
+  if (j->cap_coef < g.coef_bytes) {
+    if (j->h_coef) cudaFreeHost(j->h_coef);
+    if (j->d_coef) cudaFree(j->d_coef);
+    j->h_coef = j->d_coef = nullptr;
+    j->cap_coef = 0;
+    CU_TRY(ctx, cudaHostAlloc((void **)&j->h_coef, g.coef_bytes, cudaHostAllocDefault));
+    CU_TRY(ctx, cudaMalloc((void **)&j->d_coef, g.coef_bytes));
+    j->cap_coef = g.coef_bytes;
+  }
+  if (j->cap_pixels < g.pixel_bytes) {
+    if (j->h_pixels) cudaFreeHost(j->h_pixels);
+    if (j->d_pixels) cudaFree(j->d_pixels);
+    j->h_pixels = j->d_pixels = nullptr;
+    j->cap_pixels = 0;
+    CU_TRY(ctx, cudaHostAlloc((void **)&j->h_pixels, g.pixel_bytes, cudaHostAllocDefault));
+    CU_TRY(ctx, cudaMalloc((void **)&j->d_pixels, g.pixel_bytes));
+    j->cap_pixels = g.pixel_bytes;
+  }
+  if (g.layout == gidk::LAYOUT_GENERIC && j->cap_samples < g.sample_bytes) {
+    if (j->d_samples) cudaFree(j->d_samples);
+    j->d_samples = nullptr;
+    j->cap_samples = 0;
+    CU_TRY(ctx, cudaMalloc((void **)&j->d_samples, g.sample_bytes));
+    j->cap_samples = g.sample_bytes;
+  }
+  return GIDCUDA_OK;
+}
+
+extern "C" int gidcuda_job_begin(gidcuda_ctx *ctx, const gidcuda_frame_desc *desc, gidcuda_job **out) {
+  if (!ctx || !out) return fail(ctx, GIDCUDA_ERR_BAD_ARGUMENT, "null argument");
+  *out = nullptr;
+  Geometry g;
+  int rc = geometry_or_fail(ctx, desc, &g);
+  if (rc != GIDCUDA_OK) return rc;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  gidcuda_job *j = nullptr;
+  // recycle the free job whose buffers fit best
+  for (size_t i = 0; i < ctx->free_jobs.size(); i++) {
+    gidcuda_job *c = ctx->free_jobs[i];
+    if (c->cap_coef >= g.coef_bytes && c->cap_pixels >= g.pixel_bytes) {
+      j = c;
+      ctx->free_jobs.erase(ctx->free_jobs.begin() + (long)i);
+      break;
+    }
+  }
+  if (!j && !ctx->free_jobs.empty()) {
+    j = ctx->free_jobs.back();
+    ctx->free_jobs.pop_back();
+  }
+  if (!j) {
+    j = new (std::nothrow) gidcuda_job();
+    if (!j) return fail(ctx, GIDCUDA_ERR_OUT_OF_MEMORY, "out of host memory");
+  }
+  j->ctx = ctx;
+  j->desc = *desc;
+  j->geo = g;
+  rc = job_reserve(j);
+  if (rc != GIDCUDA_OK) {
+    job_free_buffers(j);
+    delete j;
+    return rc;
+  }
+  // planes must be zero before entropy decode (:771, :1876-1882)
+  memset(j->h_coef, 0, g.coef_bytes);
+  j->state = gidcuda_job::BEGUN;
+  ctx->live_jobs++;
+  *out = j;
+  return GIDCUDA_OK;
+}
+
+extern "C" int16_t *gidcuda_job_plane(gidcuda_job *job, int comp, int32_t *blocks_x, int32_t *blocks_y) {
+  if (!job || comp < 0 || comp >= job->geo.ncomp || job->state == gidcuda_job::IDLE) {
+    fail(job ? job->ctx : nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_job_plane: bad job or component");
+    return nullptr;
+  }
+  if (blocks_x) *blocks_x = job->geo.bx[comp];
+  if (blocks_y) *blocks_y = job->geo.by[comp];
+  return reinterpret_cast<int16_t *>(job->h_coef + job->geo.plane_off[comp]);
+}
+
+extern "C" int gidcuda_job_submit(gidcuda_job *job) {
+  if (!job) return fail(nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "null job");
+  gidcuda_ctx *ctx = job->ctx;
+  // A job may be submitted again after a wait (same planes, or planes the caller
+  // has updated in place): the work is stream-ordered behind the previous run.
+  if (job->state == gidcuda_job::IDLE)
+    return fail(ctx, GIDCUDA_ERR_STATE, "gidcuda_job_submit: job was released");
+  const Geometry &g = job->geo;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  const int16_t *planes[3] = {nullptr, nullptr, nullptr};
+  for (int c = 0; c < g.ncomp; c++)
+    planes[c] = reinterpret_cast<const int16_t *>(job->d_coef + g.plane_off[c]);
+  fill_frame_dev(&job->desc, g, planes, job->d_pixels, job->d_samples, 0, job->h_frame);
+  cudaStream_t s = job->stream;
+  CU_TRY(ctx, cudaMemcpyAsync(job->d_frame, job->h_frame, sizeof(FrameDev), cudaMemcpyHostToDevice, s));
+  CU_TRY(ctx, cudaMemcpyAsync(job->d_coef, job->h_coef, g.coef_bytes, cudaMemcpyHostToDevice, s));
+  if (g.layout == gidk::LAYOUT_GENERIC)
+    CU_TRY(ctx, gidk::launch_generic(*job->h_frame, job->d_frame, s));
+  else
+    CU_TRY(ctx, gidk::launch_fused(g.layout, g.q8, job->d_frame, nullptr, g.ntiles, s));
+  CU_TRY(ctx, cudaMemcpyAsync(job->h_pixels, job->d_pixels, g.pixel_bytes, cudaMemcpyDeviceToHost, s));
+  CU_TRY(ctx, cudaEventRecord(job->done, s));
+  job->state = gidcuda_job::SUBMITTED;
+  return GIDCUDA_OK;
+}
+
+extern "C" int gidcuda_job_wait(gidcuda_job *job, const uint8_t **pixels, size_t *stride) {
+  if (!job) return fail(nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "null job");
+  gidcuda_ctx *ctx = job->ctx;
+  if (job->state != gidcuda_job::SUBMITTED)
+    return fail(ctx, GIDCUDA_ERR_STATE, "gidcuda_job_wait: job was not submitted");
+  CU_TRY(ctx, cudaEventSynchronize(job->done));
+  if (pixels) *pixels = job->h_pixels;
+  if (stride) *stride = job->geo.stride;
+  return GIDCUDA_OK;
+}
+
+extern "C" int gidcuda_job_release(gidcuda_job *job) {
+  if (!job) return GIDCUDA_OK;
+  gidcuda_ctx *ctx = job->ctx;
+  if (job->state == gidcuda_job::IDLE) return fail(ctx, GIDCUDA_ERR_STATE, "job released twice");
+  if (job->state == gidcuda_job::SUBMITTED) (void)cudaEventSynchronize(job->done);
+  job->state = gidcuda_job::IDLE;
+  ctx->live_jobs--;
+  ctx->free_jobs.push_back(job);
+  return GIDCUDA_OK;
+}
+
+extern "C" int gidcuda_synchronize(gidcuda_ctx *ctx) {
+  if (!ctx) return fail(nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "null ctx");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return GIDCUDA_OK;
+}
+
+extern "C" int gidcuda_destroy(gidcuda_ctx *ctx) {
+  if (!ctx) return GIDCUDA_OK;
+  if (ctx->live_jobs != 0)
+    return fail(ctx, GIDCUDA_ERR_STATE, "gidcuda_destroy: %d job(s) not released", ctx->live_jobs);
+  (void)cudaSetDevice(ctx->device);
+  (void)cudaStreamSynchronize(ctx->stream);
+  for (gidcuda_job *j : ctx->free_jobs) {
+    job_free_buffers(j);
+    delete j;
+  }
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return GIDCUDA_OK;
+}
+
+// ---------------------------------------------------------------------------
+// plans: prepared launches over device-resident frames
+
+namespace {
+struct PlanGroup {
+  Layout layout;
+  bool q8;
+  std::vector<FrameDev> frames;
+  std::vector<uint32_t> tile_frame;
+  FrameDev *d_frames = nullptr;
+  uint32_t *d_tile_frame = nullptr;
+};
+}  // namespace
+
+struct gidcuda_plan {
+  gidcuda_ctx *ctx = nullptr;
+  std::vector<PlanGroup> groups;       // fused layouts, one launch each
+  std::vector<FrameDev> generic;       // generic frames, two launches each
+  FrameDev *d_generic = nullptr;
+  std::vector<uint8_t *> d_samples;    // scratch of generic frames
+  int launches = 0;
+};
+
+extern "C" int gidcuda_plan_destroy(gidcuda_plan *plan) {
+  if (!plan) return GIDCUDA_OK;
+  (void)cudaSetDevice(plan->ctx->device);
+  for (PlanGroup &g : plan->groups) {
+    if (g.d_frames) cudaFree(g.d_frames);
+    if (g.d_tile_frame) cudaFree(g.d_tile_frame);
+  }
+  if (plan->d_generic) cudaFree(plan->d_generic);
+  for (uint8_t *p : plan->d_samples) cudaFree(p);
+  delete plan;
+  return GIDCUDA_OK;
+}
+
+extern "C" int gidcuda_plan_create(gidcuda_ctx *ctx, int32_t n, const gidcuda_frame_desc *descs,
+                                   const int16_t *const *d_planes, uint8_t *const *d_pixels,
+                                   gidcuda_plan **out) {
+  if (!ctx || !out || n < 0 || (n > 0 && (!descs || !d_planes || !d_pixels)))
+    return fail(ctx, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_plan_create: bad argument");
+  *out = nullptr;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  gidcuda_plan *plan = new (std::nothrow) gidcuda_plan();
+  if (!plan) return fail(ctx, GIDCUDA_ERR_OUT_OF_MEMORY, "out of host memory");
+  plan->ctx = ctx;
+  int rc = GIDCUDA_OK;
+  for (int32_t i = 0; i < n && rc == GIDCUDA_OK; i++) {
+    Geometry g;
+    rc = geometry_or_fail(ctx, &descs[i], &g);
+    if (rc != GIDCUDA_OK) break;
+    const int16_t *planes[3] = {d_planes[3 * i], d_planes[3 * i + 1], d_planes[3 * i + 2]};
+    for (int c = 0; c < g.ncomp; c++)
+      if (!planes[c] || (reinterpret_cast<uintptr_t>(planes[c]) & 15u)) {
+        rc = fail(ctx, GIDCUDA_ERR_BAD_ARGUMENT, "frame %d plane %d: null or not 16-byte aligned", i, c);
+        break;
+      }
+    if (rc != GIDCUDA_OK) break;
+    if (!d_pixels[i]) { rc = fail(ctx, GIDCUDA_ERR_BAD_ARGUMENT, "frame %d: null pixel buffer", i); break; }
+    if (g.layout == gidk::LAYOUT_GENERIC) {
+      uint8_t *scratch = nullptr;
+      cudaError_t e = cudaMalloc((void **)&scratch, g.sample_bytes);
+      if (e != cudaSuccess) { rc = fail(ctx, GIDCUDA_ERR_OUT_OF_MEMORY, "cudaMalloc: %s", cudaGetErrorString(e)); break; }
+      plan->d_samples.push_back(scratch);
+      FrameDev f;
+      fill_frame_dev(&descs[i], g, planes, d_pixels[i], scratch, 0, &f);
+      plan->generic.push_back(f);
+      continue;
+    }
+    PlanGroup *grp = nullptr;
+    for (PlanGroup &pg : plan->groups)
+      if (pg.layout == g.layout && pg.q8 == g.q8) grp = &pg;
+    if (!grp) {
+      plan->groups.emplace_back();
+      grp = &plan->groups.back();
+      grp->layout = g.layout;
+      grp->q8 = g.q8;
+    }
+    FrameDev f;
+    fill_frame_dev(&descs[i], g, planes, d_pixels[i], nullptr, (uint32_t)grp->tile_frame.size(), &f);
+    const uint32_t fi = (uint32_t)grp->frames.size();
+    grp->frames.push_back(f);
+    grp->tile_frame.insert(grp->tile_frame.end(), g.ntiles, fi);
+  }
+  if (rc == GIDCUDA_OK) {
+    for (PlanGroup &pg : plan->groups) {
+      cudaError_t e = cudaMalloc((void **)&pg.d_frames, pg.frames.size() * sizeof(FrameDev));
+      if (e == cudaSuccess) e = cudaMalloc((void **)&pg.d_tile_frame, pg.tile_frame.size() * sizeof(uint32_t));
+      if (e == cudaSuccess)
+        e = cudaMemcpy(pg.d_frames, pg.frames.data(), pg.frames.size() * sizeof(FrameDev), cudaMemcpyHostToDevice);
+      if (e == cudaSuccess)
+        e = cudaMemcpy(pg.d_tile_frame, pg.tile_frame.data(), pg.tile_frame.size() * sizeof(uint32_t),
+                       cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) { rc = fail(ctx, GIDCUDA_ERR_CUDA, "plan upload: %s", cudaGetErrorString(e)); break; }
+      plan->launches += gidk::launches_fused();
+    }
+  }
+  if (rc == GIDCUDA_OK && !plan->generic.empty()) {
+    cudaError_t e = cudaMalloc((void **)&plan->d_generic, plan->generic.size() * sizeof(FrameDev));
+    if (e == cudaSuccess)
+      e = cudaMemcpy(plan->d_generic, plan->generic.data(), plan->generic.size() * sizeof(FrameDev),
+                     cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) rc = fail(ctx, GIDCUDA_ERR_CUDA, "plan upload: %s", cudaGetErrorString(e));
+    plan->launches += gidk::launches_generic() * (int)plan->generic.size();
+  }
+  if (rc != GIDCUDA_OK) {
+    gidcuda_plan_destroy(plan);
+    return rc;
+  }
+  *out = plan;
+  return GIDCUDA_OK;
+}
+
+extern "C" int gidcuda_plan_launch(gidcuda_plan *plan, void *cuda_stream) {
+  if (!plan) return fail(nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "null plan");
+  gidcuda_ctx *ctx = plan->ctx;
+  cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  for (PlanGroup &pg : plan->groups)
+    CU_TRY(ctx, gidk::launch_fused(pg.layout, pg.q8, pg.d_frames,
+                                   pg.frames.size() > 1 ? pg.d_tile_frame : nullptr,
+                                   (uint32_t)pg.tile_frame.size(), s));
+  for (size_t i = 0; i < plan->generic.size(); i++)
+    CU_TRY(ctx, gidk::launch_generic(plan->generic[i], plan->d_generic + i, s));
+  return GIDCUDA_OK;
+}
+
+extern "C" int gidcuda_plan_launch_count(const gidcuda_plan *plan) { return plan ? plan->launches : 0; }
+
+// ---------------------------------------------------------------------------
+// batch driver: per-GPU worker thread + work queue + ring of in-flight chunks
+
+namespace {
+
+struct BatchRun {
+  int32_t n = 0;
+  const gidcuda_frame_desc *descs = nullptr;
+  const int16_t *const *planes = nullptr;
+  uint8_t *const *pixels = nullptr;
+  int32_t *status = nullptr;
+  std::atomic<int32_t> next{0};  // shared work queue: next image index (dynamic sharding)
+  std::atomic<int64_t> h2d{0}, d2h{0};
+  std::atomic<int32_t> launches{0}, failed{0};
+  int32_t per_device[16] = {0};
+};
+
+// A chunk in flight on one device: staging buffers + plan-like launch state.
+struct ChunkSlot {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+  uint8_t *h_in = nullptr, *d_in = nullptr, *h_out = nullptr, *d_out = nullptr;
+  size_t cap_in = 0, cap_out = 0;
+  FrameDev *h_frames = nullptr, *d_frames = nullptr;
+  uint32_t *h_tiles = nullptr, *d_tiles = nullptr;
+  size_t cap_frames = 0, cap_tiles = 0;
+  uint8_t *d_samples = nullptr;
+  size_t cap_samples = 0;
+  // contents
+  std::vector<int32_t> images;
+  std::vector<Geometry> geos;
+  std::vector<size_t> out_off;
+  bool busy = false;
+};
+
+struct Worker {
+  int device = 0;
+  int index = 0;
+  std::thread thread;
+  std::vector<ChunkSlot> slots;
+};
+
+}  // namespace
+
+struct gidcuda_batch {
+  std::vector<Worker> workers;
+  int chunk_images = 8;
+  std::mutex mu;
+  std::condition_variable cv_start, cv_done;
+  BatchRun *run = nullptr;
+  uint64_t generation = 0;
+  int pending = 0;
+  bool quit = false;
+  std::string error;
+};
+
+namespace {
+
+bool cu_ok(gidcuda_batch *b, cudaError_t e, const char *what) {
+  if (e == cudaSuccess) return true;
+  std::lock_guard<std::mutex> lk(b->mu);
+  if (b->error.empty()) b->error = std::string(what) + ": " + cudaGetErrorString(e);
+  return false;
+}
+
+template <typename T>
+bool grow_pair(gidcuda_batch *b, T **h, T **d, size_t *cap, size_t need, bool host_too) {
+  if (*cap >= need) return true;
+  if (host_too && *h) cudaFreeHost(*h);
+  if (*d) cudaFree(*d);
+  *h = nullptr;
+  *d = nullptr;
+  *cap = 0;
+  const size_t bytes = need * sizeof(T);
+  if (host_too && !cu_ok(b, cudaHostAlloc((void **)h, bytes, cudaHostAllocDefault), "cudaHostAlloc")) return false;
+  if (!cu_ok(b, cudaMalloc((void **)d, bytes), "cudaMalloc")) return false;
+  *cap = need;
+  return true;
+}
+
+// Finish a slot: wait for its stream, copy pixels to the caller's buffers.
+void slot_finish(gidcuda_batch *b, BatchRun *run, ChunkSlot &s) {
+  if (!s.busy) return;
+  const bool ok = cu_ok(b, cudaEventSynchronize(s.done), "cudaEventSynchronize");
+  for (size_t k = 0; k < s.images.size(); k++) {
+    const int32_t i = s.images[k];
+    if (ok) {
+      memcpy(run->pixels[i], s.h_out + s.out_off[k], s.geos[k].pixel_bytes);
+      if (run->status) run->status[i] = GIDCUDA_OK;
+    } else {
+      if (run->status) run->status[i] = GIDCUDA_ERR_CUDA;
+      run->failed++;
+    }
+  }
+  s.busy = false;
+}
+
+// Fill a slot with up to chunk_images images from the shared queue and submit.
+bool slot_submit(gidcuda_batch *b, BatchRun *run, Worker &w, ChunkSlot &s) {
+  s.images.clear();
+  s.geos.clear();
+  s.out_off.clear();
+  size_t in_bytes = 0, out_bytes = 0, ntiles = 0, samples = 0;
+  std::vector<size_t> in_off;
+  for (int k = 0; k < b->chunk_images; k++) {
+    const int32_t i = run->next.fetch_add(1);
+    if (i >= run->n) break;
+    Geometry g;
+    const int rc = geometry_or_fail(nullptr, &run->descs[i], &g);
+    bool good = rc == GIDCUDA_OK && run->pixels[i] != nullptr;
+    for (int c = 0; good && c < g.ncomp; c++) good = run->planes[3 * i + c] != nullptr;
+    if (!good) {
+      // a failed image is reported and skipped; the others are unaffected
+      if (run->status) run->status[i] = rc != GIDCUDA_OK ? rc : GIDCUDA_ERR_BAD_ARGUMENT;
+      run->failed++;
+      continue;
+    }
+    s.images.push_back(i);
+    s.geos.push_back(g);
+    in_off.push_back(in_bytes);
+    s.out_off.push_back(out_bytes);
+    in_bytes += g.coef_bytes;
+    out_bytes += round_up(g.pixel_bytes, 256);
+    ntiles += g.ntiles;
+    if (g.layout == gidk::LAYOUT_GENERIC) samples += g.sample_bytes;
+  }
+  if (s.images.empty()) return false;
+  const size_t nf = s.images.size();
+  if (!grow_pair(b, &s.h_in, &s.d_in, &s.cap_in, in_bytes, true)) return false;
+  if (!grow_pair(b, &s.h_out, &s.d_out, &s.cap_out, out_bytes, true)) return false;
+  if (!grow_pair(b, &s.h_frames, &s.d_frames, &s.cap_frames, nf, true)) return false;
+  if (!grow_pair(b, &s.h_tiles, &s.d_tiles, &s.cap_tiles, ntiles + 1, true)) return false;
+  if (samples) {
+    uint8_t *dummy = nullptr;
+    if (!grow_pair(b, &dummy, &s.d_samples, &s.cap_samples, samples, false)) return false;
+  }
+  // stage coefficients into pinned memory, then one H2D copy per chunk
+  for (size_t k = 0; k < nf; k++) {
+    const int32_t i = s.images[k];
+    const Geometry &g = s.geos[k];
+    for (int c = 0; c < g.ncomp; c++)
+      memcpy(s.h_in + in_off[k] + g.plane_off[c], run->planes[3 * i + c], g.plane_bytes[c]);
+  }
+  // frames grouped by (layout, q8): fused groups first, generic frames after
+  struct Launch { Layout layout; bool q8; size_t first_frame, nframes, first_tile, ntiles; };
+  std::vector<Launch> launches;
+  std::vector<size_t> order;
+  for (int lay = 0; lay < 4; lay++)
+    for (int q = 0; q < 2; q++) {
+      Launch L{(Layout)lay, q == 1, order.size(), 0, 0, 0};
+      for (size_t k = 0; k < nf; k++)
+        if ((int)s.geos[k].layout == lay && s.geos[k].q8 == (q == 1)) { order.push_back(k); L.nframes++; }
+      if (L.nframes) launches.push_back(L);
+    }
+  const size_t nfused = order.size();
+  for (size_t k = 0; k < nf; k++)
+    if (s.geos[k].layout == gidk::LAYOUT_GENERIC) order.push_back(k);
+  size_t tile_cursor = 0, sample_cursor = 0;
+  size_t li = 0;
+  for (size_t pos = 0; pos < order.size(); pos++) {
+    const size_t k = order[pos];
+    const int32_t i = s.images[k];
+    const Geometry &g = s.geos[k];
+    const int16_t *planes[3] = {nullptr, nullptr, nullptr};
+    for (int c = 0; c < g.ncomp; c++)
+      planes[c] = reinterpret_cast<const int16_t *>(s.d_in + in_off[k] + g.plane_off[c]);
+    if (pos < nfused) {
+      while (pos >= launches[li].first_frame + launches[li].nframes) li++;
+      Launch &L = launches[li];
+      if (pos == L.first_frame) L.first_tile = tile_cursor;
+      fill_frame_dev(&run->descs[i], g, planes, s.d_out + s.out_off[k], nullptr,
+                     (uint32_t)(tile_cursor - L.first_tile), &s.h_frames[pos]);
+      for (uint32_t t = 0; t < g.ntiles; t++) s.h_tiles[tile_cursor + t] = (uint32_t)(pos - L.first_frame);
+      tile_cursor += g.ntiles;
+      L.ntiles += g.ntiles;
+    } else {
+      fill_frame_dev(&run->descs[i], g, planes, s.d_out + s.out_off[k], s.d_samples + sample_cursor, 0,
+                     &s.h_frames[pos]);
+      sample_cursor += g.sample_bytes;
+    }
+  }
+  cudaStream_t st = s.stream;
+  bool ok = cu_ok(b, cudaMemcpyAsync(s.d_in, s.h_in, in_bytes, cudaMemcpyHostToDevice, st), "H2D coefficients");
+  ok = ok && cu_ok(b, cudaMemcpyAsync(s.d_frames, s.h_frames, nf * sizeof(FrameDev), cudaMemcpyHostToDevice, st), "H2D frames");
+  ok = ok && cu_ok(b, cudaMemcpyAsync(s.d_tiles, s.h_tiles, (ntiles + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st), "H2D tiles");
+  int nl = 0;
+  for (const Launch &L : launches) {
+    ok = ok && cu_ok(b, gidk::launch_fused(L.layout, L.q8, s.d_frames + L.first_frame, s.d_tiles + L.first_tile,
+                                          (uint32_t)L.ntiles, st), "launch_fused");
+    nl += gidk::launches_fused();
+  }
+  for (size_t pos = nfused; pos < order.size(); pos++) {
+    ok = ok && cu_ok(b, gidk::launch_generic(s.h_frames[pos], s.d_frames + pos, st), "launch_generic");
+    nl += gidk::launches_generic();
+  }
+  ok = ok && cu_ok(b, cudaMemcpyAsync(s.h_out, s.d_out, out_bytes, cudaMemcpyDeviceToHost, st), "D2H pixels");
+  ok = ok && cu_ok(b, cudaEventRecord(s.done, st), "cudaEventRecord");
+  if (!ok) {
+    for (int32_t i : s.images) {
+      if (run->status) run->status[i] = GIDCUDA_ERR_CUDA;
+      run->failed++;
+    }
+    return true;  // keep draining the queue so that every image gets a status
+  }
+  run->h2d += (int64_t)(in_bytes + nf * sizeof(FrameDev) + (ntiles + 1) * sizeof(uint32_t));
+  run->d2h += (int64_t)out_bytes;
+  run->launches += nl;
+  run->per_device[w.index] += (int32_t)nf;
+  s.busy = true;
+  return true;
+}
+
+void worker_main(gidcuda_batch *b, Worker *w) {
+  uint64_t seen = 0;
+  if (!cu_ok(b, cudaSetDevice(w->device), "cudaSetDevice")) { /* reported on first run */ }
+  for (ChunkSlot &s : w->slots) {
+    cu_ok(b, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    cu_ok(b, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming), "cudaEventCreate");
+  }
+  for (;;) {
+    BatchRun *run;
+    {
+      std::unique_lock<std::mutex> lk(b->mu);
+      b->cv_start.wait(lk, [&] { return b->quit || b->generation != seen; });
+      if (b->quit) break;
+      seen = b->generation;
+      run = b->run;
+    }
+    // ring of slots: submit into the oldest free slot, finish it when it comes round again
+    size_t cur = 0;
+    bool more = true;
+    while (more) {
+      ChunkSlot &s = w->slots[cur];
+      slot_finish(b, run, s);
+      more = slot_submit(b, run, *w, s);
+      cur = (cur + 1) % w->slots.size();
+    }
+    for (size_t k = 0; k < w->slots.size(); k++) slot_finish(b, run, w->slots[(cur + k) % w->slots.size()]);
+    {
+      std::lock_guard<std::mutex> lk(b->mu);
+      if (--b->pending == 0) b->cv_done.notify_all();
+    }
+  }
+  for (ChunkSlot &s : w->slots) {
+    if (s.h_in) cudaFreeHost(s.h_in);
+    if (s.h_out) cudaFreeHost(s.h_out);
+    if (s.h_frames) cudaFreeHost(s.h_frames);
+    if (s.h_tiles) cudaFreeHost(s.h_tiles);
+    if (s.d_in) cudaFree(s.d_in);
+    if (s.d_out) cudaFree(s.d_out);
+    if (s.d_frames) cudaFree(s.d_frames);
+    if (s.d_tiles) cudaFree(s.d_tiles);
+    if (s.d_samples) cudaFree(s.d_samples);
+    if (s.done) cudaEventDestroy(s.done);
+    if (s.stream) cudaStreamDestroy(s.stream);
+  }
+}
+
+}  // namespace
+
+extern "C" int gidcuda_batch_create(const int32_t *devices, int32_t ndevices, int32_t chunk_images,
+                                    gidcuda_batch **out) {
+  if (!out || ndevices < 1 || ndevices > 16 || !devices)
+    return fail(nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_batch_create: bad argument");
+  *out = nullptr;
+  const int n = gidcuda_device_count();
+  if (n == 0) return fail(nullptr, GIDCUDA_ERR_NO_DEVICE, "no CUDA device: no CPU fallback");
+  for (int i = 0; i < ndevices; i++)
+    if (devices[i] < 0 || devices[i] >= n)
+      return fail(nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "device %d out of range", devices[i]);
+  gidcuda_batch *b = new (std::nothrow) gidcuda_batch();
+  if (!b) return fail(nullptr, GIDCUDA_ERR_OUT_OF_MEMORY, "out of host memory");
+  b->chunk_images = chunk_images > 0 ? chunk_images : 8;
+  b->workers.resize((size_t)ndevices);
+  for (int i = 0; i < ndevices; i++) {
+    b->workers[(size_t)i].device = devices[i];
+    b->workers[(size_t)i].index = i;
+    b->workers[(size_t)i].slots.resize(3);
+  }
+  for (Worker &w : b->workers) w.thread = std::thread(worker_main, b, &w);
+  *out = b;
+  return GIDCUDA_OK;
+}
+
+extern "C" int gidcuda_batch_run(gidcuda_batch *b, int32_t n, const gidcuda_frame_desc *descs,
+                                 const int16_t *const *planes, uint8_t *const *pixels, int32_t *status,
+                                 gidcuda_batch_stats *stats) {
+  if (!b || n < 0 || (n > 0 && (!descs || !planes || !pixels)))
+    return fail(nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_batch_run: bad argument");
+  BatchRun run;
+  run.n = n;
+  run.descs = descs;
+  run.planes = planes;
+  run.pixels = pixels;
+  run.status = status;
+  const auto t0 = std::chrono::steady_clock::now();
+  {
+    std::unique_lock<std::mutex> lk(b->mu);
+    b->error.clear();
+    b->run = &run;
+    b->pending = (int)b->workers.size();
+    b->generation++;
+    b->cv_start.notify_all();
+    b->cv_done.wait(lk, [&] { return b->pending == 0; });
+    b->run = nullptr;
+  }
+  const auto t1 = std::chrono::steady_clock::now();
+  if (stats) {
+    memset(stats, 0, sizeof *stats);
+    stats->seconds = std::chrono::duration<double>(t1 - t0).count();
+    for (int32_t i = 0; i < n; i++) stats->megapixels += (double)descs[i].width * descs[i].height / 1e6;
+    stats->h2d_bytes = run.h2d;
+    stats->d2h_bytes = run.d2h;
+    stats->kernel_launches = run.launches;
+    stats->images_failed = run.failed;
+    for (int i = 0; i < 16; i++) stats->images_per_device[i] = run.per_device[i];
+  }
+  if (!b->error.empty()) return fail(nullptr, GIDCUDA_ERR_CUDA, "batch: %s", b->error.c_str());
+  return GIDCUDA_OK;
+}
+
+extern "C" int gidcuda_batch_destroy(gidcuda_batch *b) {
+  if (!b) return GIDCUDA_OK;
+  {
+    std::lock_guard<std::mutex> lk(b->mu);
+    b->quit = true;
+    b->cv_start.notify_all();
+  }
+  for (Worker &w : b->workers)
+    if (w.thread.joinable()) w.thread.join();
+  delete b;
+  return GIDCUDA_OK;
+}

@@ -1,0 +1,169 @@
+/*
+ * gidcuda.h -- C ABI of the B200 JPEG pixel-reconstruction path for GID.
+ *
+ * This is the drop-in boundary.  The Ada package
+ * GID.CUDA (gid_b200/ada/gid-cuda.ads) binds exactly these entry points with
+ * pragma Import (C, ...); the patched GID.Decoding_JPG calls them where the
+ * reference ran the reconstruction inline:
+ *
+ *   reference (file:line, relative to the GID tree)        replaced by
+ *   ------------------------------------------------------  ------------------
+ *   Decode_8x8_Block dequant, gid-decoding_jpg.adb:771,785  kernel (dequant)
+ *   Inverse_DCT_8x8_Block, :790-907                         kernel (IDCT)
+ *   Upsampling_and_Output*, :957-1124                       kernel (upsample)
+ *   Color_Transformation_and_Output, :1018-1054             kernel (colour)
+ *   call sites Baseline_DCT_Decoding_Scan :1199, :1206      gidcuda_job_*
+ *   Finalize_Progressive_DCT_Decoding :1789-1850            gidcuda_job_*
+ *
+ * Conventions: plain C types only; every function returns an int status
+ * (0 = ok, < 0 = error class below) and never throws; the message of the last
+ * error is available from gidcuda_last_error.  A context belongs to one host
+ * thread (GID is "task safe": one descriptor per task, doc/gid.txt:20).
+ *
+ * There is NO CPU fallback: without a CUDA device every compute entry point
+ * fails with GIDCUDA_ERR_NO_DEVICE.
+ */
+#ifndef GIDCUDA_H
+#define GIDCUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GIDCUDA_ABI_VERSION 1
+
+/* Status codes.  The Ada binding maps DATA -> GID.error_in_image_data,
+ * UNSUPPORTED -> GID.unsupported_image_subformat, the others ->
+ * GID.CUDA.Device_Error. */
+enum {
+  GIDCUDA_OK = 0,
+  GIDCUDA_ERR_BAD_ARGUMENT = -1,
+  GIDCUDA_ERR_UNSUPPORTED = -2, /* geometry the path does not cover */
+  GIDCUDA_ERR_NO_DEVICE = -3,
+  GIDCUDA_ERR_CUDA = -4,        /* a CUDA runtime call failed */
+  GIDCUDA_ERR_OUT_OF_MEMORY = -5,
+  GIDCUDA_ERR_STATE = -6        /* call sequence violated (e.g. wait before submit) */
+};
+
+/* Output pixel formats (flags, low byte).  RGB8 top-down is what
+ * test/benchmark.adb:67-81 and test/mini.adb:55-69 build with Put_Pixel. */
+#define GIDCUDA_OUT_RGB8 0u      /* top-down, 3 bytes per pixel: R, G, B */
+#define GIDCUDA_OUT_BGR8_BOTTOM_UP 1u /* test/to_bmp.adb:94-146: bottom-up B, G, R, rows padded to 4 bytes */
+#define GIDCUDA_OUT_MASK 0xFFu
+/* Force stride = 3 * width (no row padding) for RGB8 even when that makes rows
+ * unaligned; the default stride is 3 * width rounded up to 16 bytes. */
+#define GIDCUDA_FLAG_PACKED_ROWS 0x100u
+
+/* One JPEG frame, as the entropy decoder knows it after SOF/DQT/SOS
+ * (Read_SOF gid-decoding_jpg.adb:184-318, Read_DQT :393-422). */
+typedef struct gidcuda_frame_desc {
+  int32_t width;        /* 1 .. 65535 (:206-215) */
+  int32_t height;       /* 1 .. 65535 */
+  int32_t ncomp;        /* 1 = Y (grey), 3 = Y, Cb, Cr (:298-317) */
+  int32_t samp_h[3];    /* samples_hor per component, 1 .. 4 (:246) */
+  int32_t samp_v[3];    /* samples_ver per component, 1 .. 4 (:247) */
+  uint16_t qt[3][64];   /* quantisation table per component in NATURAL order:
+                           qt[c][i] = qt_list(qt_assoc(c))(undo_zig_zag(i)), :1771-1775 */
+  uint32_t flags;       /* GIDCUDA_OUT_* | GIDCUDA_FLAG_* */
+  int32_t out_stride;   /* bytes per output row; 0 = library default */
+} gidcuda_frame_desc;
+
+typedef struct gidcuda_ctx gidcuda_ctx;
+typedef struct gidcuda_job gidcuda_job;
+typedef struct gidcuda_plan gidcuda_plan;
+typedef struct gidcuda_batch gidcuda_batch;
+
+/* ---- library / device ---------------------------------------------------- */
+
+int gidcuda_abi_version(void);
+/* Number of usable CUDA devices (0 when there is none; never fails). */
+int gidcuda_device_count(void);
+/* Message of the last error raised on this thread (ctx may be NULL). */
+const char *gidcuda_last_error(const gidcuda_ctx *ctx);
+
+/* One context per host thread / Ada task.  Owns a device, streams and a pool
+ * of pinned host + device buffers that jobs recycle. */
+int gidcuda_create(int device, gidcuda_ctx **ctx);
+int gidcuda_destroy(gidcuda_ctx *ctx);
+
+/* Geometry helper: MCU-padded block grid of a component, = what GID computes
+ * in Read_SOS (:1945-1951) times the sampling factors. */
+int gidcuda_plane_geometry(const gidcuda_frame_desc *desc, int comp, int32_t *blocks_x,
+                           int32_t *blocks_y);
+/* Output geometry: stride in bytes and total size of the pixel buffer. */
+int gidcuda_output_geometry(const gidcuda_frame_desc *desc, size_t *stride, size_t *bytes);
+
+/* ---- one frame: the path GID.Decoding_JPG calls --------------------------- */
+
+/* Begin a frame.  Allocates (or recycles) pinned, ZEROED coefficient planes
+ * (baseline zeroes each block, :771; progressive zero-fills, :1876-1882). */
+int gidcuda_job_begin(gidcuda_ctx *ctx, const gidcuda_frame_desc *desc, gidcuda_job **job);
+/* Pinned host plane of component comp: int16, block-major
+ * [block_row][block_col][64], natural order (index = 8 * row + col), NOT
+ * de-quantised.  The entropy decoder stores dc_predictor / value at
+ * zig_zag(k) (:771, :785) or the progressive accumulators (:1339, :1615). */
+int16_t *gidcuda_job_plane(gidcuda_job *job, int comp, int32_t *blocks_x, int32_t *blocks_y);
+/* Asynchronous: host-to-device copies, reconstruction kernel, device-to-host
+ * copy of the pixels, all on the job's own stream (two jobs in flight overlap
+ * their transfers).  A job may be submitted again after gidcuda_job_wait. */
+int gidcuda_job_submit(gidcuda_job *job);
+/* Block until the frame is done.  *pixels points to pinned host memory owned
+ * by the job (valid until release): rows top-down, *stride bytes apart. */
+int gidcuda_job_wait(gidcuda_job *job, const uint8_t **pixels, size_t *stride);
+/* Return the job's buffers to the context pool. */
+int gidcuda_job_release(gidcuda_job *job);
+
+/* ---- device-resident path (planes already in HBM) ------------------------- */
+
+/* A plan is a prepared launch over n frames whose coefficient planes and
+ * output buffers live in device memory (one kernel launch per sampling
+ * layout present in the batch, all frames of a layout in the same launch). */
+int gidcuda_plan_create(gidcuda_ctx *ctx, int32_t n, const gidcuda_frame_desc *descs,
+                        const int16_t *const *d_planes /* [n][3] device pointers */,
+                        uint8_t *const *d_pixels /* [n] device pointers */,
+                        gidcuda_plan **plan);
+/* Launch on the given CUDA stream (cudaStream_t as void*; NULL = context stream).
+ * Asynchronous. */
+int gidcuda_plan_launch(gidcuda_plan *plan, void *cuda_stream);
+/* Number of kernel launches one gidcuda_plan_launch performs. */
+int gidcuda_plan_launch_count(const gidcuda_plan *plan);
+int gidcuda_plan_destroy(gidcuda_plan *plan);
+/* Wait for everything queued on the context stream. */
+int gidcuda_synchronize(gidcuda_ctx *ctx);
+
+/* ---- batch driver: independent images sharded over the GPUs of one box ---- */
+
+typedef struct gidcuda_batch_stats {
+  double seconds;            /* wall time of the whole run */
+  double megapixels;         /* sum of width * height / 1e6 */
+  int64_t h2d_bytes;
+  int64_t d2h_bytes;
+  int32_t kernel_launches;
+  int32_t images_failed;
+  int32_t images_per_device[16];
+} gidcuda_batch_stats;
+
+/* One worker thread, one work queue and a ring of in-flight chunks per device;
+ * no inter-GPU communication (images carry no cross-GPU data). */
+int gidcuda_batch_create(const int32_t *devices, int32_t ndevices, int32_t chunk_images,
+                         gidcuda_batch **batch);
+/* planes[i*3 + c]: HOST pointer to plane c of image i (any memory; pinned is
+ * faster); pixels[i]: HOST output buffer of gidcuda_output_geometry bytes.
+ * status[i] (optional) receives the per-image status: a failed image is
+ * reported and skipped, the others are unaffected. */
+int gidcuda_batch_run(gidcuda_batch *batch, int32_t n, const gidcuda_frame_desc *descs,
+                      const int16_t *const *planes, uint8_t *const *pixels, int32_t *status,
+                      gidcuda_batch_stats *stats);
+int gidcuda_batch_destroy(gidcuda_batch *batch);
+
+/* Pinned host memory for callers that want the fast copy path. */
+int gidcuda_host_alloc(size_t bytes, void **ptr);
+int gidcuda_host_free(void *ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GIDCUDA_H */

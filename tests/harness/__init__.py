@@ -28,9 +28,24 @@ def _build(target_dir: str, lib: str, sources: list[str], flags: list[str]) -> s
     return out
 
 
+def _build_emu() -> str:
+    """Host build of the kernel body (test-only; see emu_recon.cpp)."""
+    out = os.path.join(_HERE, "libemurecon.so")
+    csrc = os.path.join(_ROOT, "gid_b200", "csrc")
+    deps = [os.path.join(_HERE, "emu_recon.cpp")] + [
+        os.path.join(csrc, f) for f in ("recon_math.cuh", "recon_body.cuh", "frame_setup.hpp")
+    ] + [os.path.join(_ROOT, "include", "gidcuda.h")]
+    if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
+        return out
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
+                    "-o", out, deps[0]], check=True, cwd=_HERE)
+    return out
+
+
 def build_all() -> None:
     _build(_ORACLE_DIR, "libgidref.so", ["gidref.c", "gidref_load.inc", "gidref.h"], ["-fwrapv"])
     _build(_HERE, "libsynthjpeg.so", ["synth_jpeg.c"], [])
+    _build_emu()
 
 
 # --------------------------------------------------------------------------- oracle
@@ -387,3 +402,43 @@ class Synth:
         mx = -(-width // (8 * hmax))
         my = -(-height // (8 * vmax))
         return [mx * h for h in sh], [my * v for v in sv]
+
+
+# --------------------------------------------------------------------------- kernel body on the host
+
+
+class Emu:
+    """The kernel's per-thread body compiled for the host (tests only)."""
+
+    def __init__(self) -> None:
+        build_all()
+        self.lib = ctypes.CDLL(os.path.join(_HERE, "libemurecon.so"))
+        self.lib.emu_reconstruct.restype = ctypes.c_int
+
+    def reconstruct(self, desc, planes, stride: int, height: int) -> np.ndarray:
+        """desc: gid_b200.FrameDesc; returns (H, stride) uint8 rows."""
+        keep = [np.ascontiguousarray(p, dtype=np.int16) for p in planes]
+        ptrs = (ctypes.c_void_p * 3)()
+        for c in range(desc.ncomp):
+            ptrs[c] = keep[c].ctypes.data
+        out = np.zeros((height, stride), dtype=np.uint8)
+        err = ctypes.create_string_buffer(512)
+        rc = self.lib.emu_reconstruct(ctypes.byref(desc), ptrs, out.ctypes.data_as(ctypes.c_void_p),
+                                      err, ctypes.c_size_t(512))
+        if rc != 0:
+            raise RuntimeError(f"emu_reconstruct {rc}: {err.value.decode()}")
+        return out
+
+    def idct(self, block) -> np.ndarray:
+        b = (ctypes.c_int32 * 64)(*[int(v) for v in block])
+        self.lib.emu_idct_block(b)
+        return np.array(b[:], dtype=np.int32)
+
+    def chroma_exhaustive(self) -> int:
+        return self.lib.emu_chroma_exhaustive()
+
+
+def frame_desc(fr: Frame, flags: int = 0, out_stride: int = 0):
+    """gid_b200.FrameDesc for a harness Frame."""
+    from gid_b200 import FrameDesc
+    return FrameDesc.make(fr.width, fr.height, fr.samp_h, fr.samp_v, fr.qt, flags, out_stride)

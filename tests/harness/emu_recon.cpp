@@ -1,0 +1,111 @@
+// emu_recon.cpp -- TEST HARNESS.  Compiles the per-thread kernel body
+// (gid_b200/csrc/recon_body.cuh) for the host and runs it for every
+// (tile, thread) of a launch, with the frame descriptors the shim builds
+// (frame_setup.hpp).  Lets the CPU test-suite check the kernel's arithmetic
+// and indexing against the oracle without a GPU.  Never shipped: the product
+// library contains device code only and has no CPU path.
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../gid_b200/csrc/frame_setup.hpp"
+
+using namespace gidk;
+
+extern "C" int emu_reconstruct(const gidcuda_frame_desc *desc, const int16_t *const planes[3],
+                               uint8_t *pixels, char *err, size_t errlen) {
+  Geometry g;
+  std::string e;
+  int rc = make_geometry(&e, desc, &g);
+  if (rc != 0) {
+    if (err && errlen) snprintf(err, errlen, "%s", e.c_str());
+    return rc;
+  }
+  std::vector<uint8_t> samples(g.sample_bytes + 16);
+  FrameDev f;
+  fill_frame_dev(desc, g, planes, pixels, samples.data(), 0, &f);
+  const uint32_t *qw = &f.qw[0][0];
+  if (g.layout == LAYOUT_GENERIC) {
+    // pass 1 (generic_idct_kernel)
+    for (int c = 0; c < g.ncomp; c++)
+      for (int by = 0; by < f.by[c]; by++)
+        for (int bx = 0; bx < f.bx[c]; bx++) {
+          int b[64];
+          const size_t idx = (size_t)by * f.bx[c] + bx;
+          if (f.q8) load_idct_block<true>(f.plane[c] + idx * 64, &f.qw[c][0], b);
+          else load_idct_block<false>(f.plane[c] + idx * 64, &f.qw[c][0], b);
+          uint32_t p[16];
+          pack_block(b, p);
+          const size_t pitch = (size_t)f.bx[c] * 8;
+          uint8_t *dst = f.samples[c] + (size_t)by * 8 * pitch + (size_t)bx * 8;
+          for (int r = 0; r < 8; r++) memcpy(dst + r * pitch, &p[2 * r], 8);
+        }
+    // pass 2 (generic_color_kernel)
+    for (int y = 0; y < f.height; y++)
+      for (int x = 0; x < f.width; x++) {
+        int s[3] = {0, 0, 0};
+        for (int c = 0; c < g.ncomp; c++) {
+          const int ux = g.hmax / f.samp_h[c], uy = g.vmax / f.samp_v[c];
+          s[c] = f.samples[c][(size_t)(y / uy) * ((size_t)f.bx[c] * 8) + (size_t)(x / ux)];
+        }
+        int r, gg, b;
+        if (g.ncomp == 3) {
+          const ChromaTerms t = chroma_terms(s[1], s[2]);
+          r = clip255(s[0] + t.r); gg = clip255(s[0] + t.g); b = clip255(s[0] + t.b);
+        } else {
+          r = gg = b = s[0];
+        }
+        int yy = y;
+        if (f.out_format == OUT_BGR8_BOTTOM_UP) { yy = f.height - 1 - y; int t = r; r = b; b = t; }
+        uint8_t *dst = f.pixels + (size_t)yy * f.stride + (size_t)x * 3;
+        dst[0] = (uint8_t)r; dst[1] = (uint8_t)gg; dst[2] = (uint8_t)b;
+      }
+    return 0;
+  }
+  for (uint32_t tile = 0; tile < g.ntiles; tile++)
+    for (int t = 0; t < kTileMcusSetup; t++) {
+      const uint32_t m = (tile - f.tile_base) * kTileMcusSetup + t;
+      if (m >= (uint32_t)(f.mcux * f.mcuy)) continue;
+      const int my = (int)(m / (uint32_t)f.mcux), mx = (int)(m - (uint32_t)my * f.mcux);
+      switch (g.layout) {
+        case LAYOUT_GREY: f.q8 ? mcu_grey<true>(f, qw, mx, my) : mcu_grey<false>(f, qw, mx, my); break;
+        case LAYOUT_444: f.q8 ? mcu_ycc<1, 1, true>(f, qw, mx, my) : mcu_ycc<1, 1, false>(f, qw, mx, my); break;
+        case LAYOUT_422: f.q8 ? mcu_ycc<2, 1, true>(f, qw, mx, my) : mcu_ycc<2, 1, false>(f, qw, mx, my); break;
+        default: f.q8 ? mcu_ycc<2, 2, true>(f, qw, mx, my) : mcu_ycc<2, 2, false>(f, qw, mx, my); break;
+      }
+    }
+  return 0;
+}
+
+// idct on one de-quantised block with the kernel arithmetic; clipped samples out
+extern "C" void emu_idct_block(int32_t blk[64]) {
+  int b[64];
+  for (int i = 0; i < 64; i++) b[i] = blk[i];
+  idct_8x8(b);
+  for (int i = 0; i < 64; i++) blk[i] = clip255(b[i]);
+}
+
+extern "C" void emu_chroma_rgb(int y, int cb, int cr, uint8_t out[3]) {
+  const ChromaTerms t = chroma_terms(cb, cr);
+  out[0] = (uint8_t)clip255(y + t.r);
+  out[1] = (uint8_t)clip255(y + t.g);
+  out[2] = (uint8_t)clip255(y + t.b);
+}
+
+// exhaustive check of the colour identity against the reference formula
+// (gid-decoding_jpg.adb:1028-1035), written out here with truncating "/"
+extern "C" int emu_chroma_exhaustive(void) {
+  int bad = 0;
+  for (int y = 0; y < 256; y++)
+    for (int cb = 0; cb < 256; cb++)
+      for (int cr = 0; cr < 256; cr++) {
+        const int yv = y * 256, cbv = cb - 128, crv = cr - 128;
+        const int r = clip255((yv + 359 * crv + 128) / 256);
+        const int g = clip255((yv - 88 * cbv - 183 * crv + 128) / 256);
+        const int b = clip255((yv + 454 * cbv + 128) / 256);
+        const ChromaTerms t = chroma_terms(cb, cr);
+        if (clip255(y + t.r) != r || clip255(y + t.g) != g || clip255(y + t.b) != b) bad++;
+      }
+  return bad;
+}

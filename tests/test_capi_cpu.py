@@ -1,0 +1,98 @@
+"""The C-ABI library without a GPU: it loads, exports every symbol
+include/gidcuda.h declares, answers geometry questions, and refuses to compute
+without a device (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "gidcuda.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gidcuda_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported(gidcuda_lib):
+    from gid_b200 import capi
+    syms = _declared_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(gidcuda_lib, s), s
+    assert sorted(capi.EXPORTS) == syms
+    assert gidcuda_lib.gidcuda_abi_version() == 1
+
+
+def test_geometry_matches_gid(gidcuda_lib, synth):
+    """Block grids = what GID's Read_SOS computes, for the five configs + odd sizes."""
+    from gid_b200 import FrameDesc
+    from tests.harness import SAMPLING
+    q = np.ones((3, 64), dtype=np.uint16)
+    table = [(512, 512, "420", [(64, 64), (32, 32), (32, 32)], 1536),
+             (4096, 4096, "444", [(512, 512)] * 3, 12288),
+             (1920, 1080, "420", [(240, 136), (120, 68), (120, 68)], 5760),
+             (8192, 8192, "grey", [(1024, 1024)], 24576),
+             (2048, 2048, "422", [(256, 256), (128, 256), (128, 256)], 6144),
+             (17, 9, "420", [(4, 2), (2, 1), (2, 1)], 64),
+             (1, 1, "444", [(1, 1)] * 3, 16)]
+    for w, h, samp, grids, stride in table:
+        sh, sv = SAMPLING[samp]
+        d = FrameDesc.make(w, h, sh, sv, q[:len(sh)])
+        for c, (ex, ey) in enumerate(grids):
+            bx, by = ctypes.c_int32(), ctypes.c_int32()
+            assert gidcuda_lib.gidcuda_plane_geometry(ctypes.byref(d), c, ctypes.byref(bx), ctypes.byref(by)) == 0
+            assert (bx.value, by.value) == (ex, ey)
+            assert [bx.value, by.value] == [synth.grid(w, h, samp)[0][c], synth.grid(w, h, samp)[1][c]]
+        st, nb = ctypes.c_size_t(), ctypes.c_size_t()
+        assert gidcuda_lib.gidcuda_output_geometry(ctypes.byref(d), ctypes.byref(st), ctypes.byref(nb)) == 0
+        assert st.value == stride and nb.value == stride * h
+
+
+def test_bad_descriptors_are_rejected(gidcuda_lib):
+    from gid_b200 import FrameDesc
+    q = np.ones((3, 64), dtype=np.uint16)
+    st = ctypes.c_size_t()
+
+    def rc(d):
+        return gidcuda_lib.gidcuda_output_geometry(ctypes.byref(d), ctypes.byref(st), None)
+
+    assert rc(FrameDesc.make(0, 10, [1], [1], q[:1])) == -1
+    assert rc(FrameDesc.make(70000, 10, [1], [1], q[:1])) == -1
+    assert rc(FrameDesc.make(10, 10, [1, 1], [1, 1], q[:2])) == -2          # 2 components
+    assert rc(FrameDesc.make(10, 10, [5, 1, 1], [1, 1, 1], q)) == -1        # sampling factor 5
+    assert rc(FrameDesc.make(10, 10, [3, 2, 1], [1, 1, 1], q)) == -2        # 3/2 not integer
+    assert rc(FrameDesc.make(10, 10, [2], [2], q[:1])) == -2                # grey with 2x2
+    assert rc(FrameDesc.make(10, 10, [1], [1], q[:1], out_stride=29)) == -1 # stride < 3*W
+    assert b"stride" in gidcuda_lib.gidcuda_last_error(None)
+
+
+def test_no_cpu_fallback(gidcuda_lib):
+    """On a machine without a CUDA device every compute entry point fails loudly."""
+    if gidcuda_lib.gidcuda_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    from gid_b200 import GidCuda, GidCudaError, capi
+    with pytest.raises(GidCudaError) as e:
+        GidCuda(0)
+    assert e.value.code == -3 and "no CPU fallback" in e.value.msg
+    with pytest.raises(GidCudaError):
+        capi.Batch([0])
+    with pytest.raises(GidCudaError):
+        capi.pinned_empty(16)
+
+
+def test_product_does_not_touch_the_oracle():
+    """Nothing under gid_b200/ or include/ may reference oracle/ or the test harness."""
+    bad = []
+    for base in ("gid_b200", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith((".so", ".o", ".pyc")):
+                    continue
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                if re.search(r"gidref|oracle/|tests[./]harness|libemurecon", text):
+                    bad.append(os.path.join(dirpath, f))
+    assert not bad, bad

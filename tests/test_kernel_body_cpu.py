@@ -1,0 +1,98 @@
+"""The kernel's per-thread body, compiled for the host (tests/harness/emu_recon.cpp),
+against the oracle.  Same source as the device code (gid_b200/csrc/recon_*.cuh),
+same frame descriptors as the shim builds; bit-exact bar.  No GPU needed.
+"""
+import ctypes
+import zlib
+
+import numpy as np
+import pytest
+
+from tests.cases import GEOMETRIES, pixels_for, random_planes
+from tests.harness import Frame, SAMPLING, frame_desc
+
+
+def _stride(lib, d):
+    st, nb = ctypes.c_size_t(), ctypes.c_size_t()
+    assert lib.gidcuda_output_geometry(ctypes.byref(d), ctypes.byref(st), ctypes.byref(nb)) == 0
+    return st.value
+
+
+def _check(emu, oracle, lib, fr, flags=0, out_stride=0):
+    from gid_b200 import capi
+    ref = oracle.reconstruct(fr)
+    d = frame_desc(fr, flags, out_stride)
+    rows = emu.reconstruct(d, fr.planes, _stride(lib, d), fr.height)
+    got = rows[:, :3 * fr.width].reshape(fr.height, fr.width, 3)
+    if (flags & 0xFF) == capi.OUT_BGR8_BOTTOM_UP:
+        got = got[::-1, :, ::-1]
+    assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("w,h,samp", GEOMETRIES)
+def test_geometries(emu, oracle, synth, gidcuda_lib, w, h, samp):
+    fr = synth.planes_only(pixels_for(synth, 11, w, h, samp), samp)
+    _check(emu, oracle, gidcuda_lib, fr)
+
+
+@pytest.mark.parametrize("kind", ["dense", "sparse", "dc_only", "rows", "extreme"])
+@pytest.mark.parametrize("samp", ["grey", "444", "422", "420", "440"])
+def test_random_coefficients(emu, oracle, synth, gidcuda_lib, kind, samp):
+    rng = np.random.default_rng(zlib.crc32(f"{kind}-{samp}".encode()))
+    w, h = 200, 136
+    bx, by = synth.grid(w, h, samp)
+    sh, sv = SAMPLING[samp]
+    qt = rng.integers(1, 256, size=(len(sh), 64)).astype(np.uint16)
+    fr = Frame(w, h, len(sh), list(sh), list(sv), bx, by, qt)
+    fr.planes = random_planes(rng, bx, by, kind)
+    _check(emu, oracle, gidcuda_lib, fr)
+
+
+def test_16bit_quant_tables(emu, oracle, synth, gidcuda_lib):
+    rng = np.random.default_rng(7)
+    for samp in ("grey", "420", "444"):
+        w, h = 120, 72
+        bx, by = synth.grid(w, h, samp)
+        sh, sv = SAMPLING[samp]
+        qt = rng.integers(1, 2000, size=(len(sh), 64)).astype(np.uint16)
+        fr = Frame(w, h, len(sh), list(sh), list(sv), bx, by, qt)
+        fr.planes = [np.clip(p, -400, 400) for p in random_planes(rng, bx, by, "sparse")]
+        _check(emu, oracle, gidcuda_lib, fr)
+
+
+@pytest.mark.parametrize("samp", ["grey", "444", "422", "420", "411"])
+def test_output_formats_and_strides(emu, oracle, synth, gidcuda_lib, samp):
+    from gid_b200 import capi
+    fr = synth.planes_only(pixels_for(synth, 3, 211, 77, samp), samp)
+    _check(emu, oracle, gidcuda_lib, fr, flags=capi.FLAG_PACKED_ROWS)
+    _check(emu, oracle, gidcuda_lib, fr, flags=capi.OUT_BGR8_BOTTOM_UP)
+    _check(emu, oracle, gidcuda_lib, fr, out_stride=3 * 211 + 29)
+
+
+def test_idct_blocks_match_oracle(emu, oracle):
+    """Block-level: the kernel IDCT (shortcut folded into the rounding constant,
+    column shortcut dropped, re-associated rotations) == GID's, on blocks built
+    to hit every special case."""
+    rng = np.random.default_rng(99)
+    for k in range(3000):
+        blk = np.zeros(64, dtype=np.int64)
+        mode = k % 6
+        if mode == 0:
+            blk[:] = rng.integers(-2000, 2001, size=64)
+        elif mode == 1:
+            blk[0] = rng.integers(-500000, 500001)           # DC only, large
+        elif mode == 2:
+            blk[::8] = rng.integers(-3000, 3001, size=8)     # first column only: all rows shortcut
+        elif mode == 3:
+            blk[:8] = rng.integers(-3000, 3001, size=8)      # first row only: column shortcut territory
+        elif mode == 4:
+            idx = rng.choice(64, size=3, replace=False)
+            blk[idx] = rng.integers(-30000, 30001, size=3)
+        else:
+            blk[:] = rng.integers(-3, 4, size=64)            # tiny values around the truncation points
+        assert np.array_equal(emu.idct(blk), oracle.idct(blk)), (k, blk.tolist())
+
+
+def test_colour_identity_exhaustive(emu):
+    """Clip(Y + (T >> 8)) == Clip((Y*256 + T) / 256) for all 2**24 (Y, Cb, Cr)."""
+    assert emu.chroma_exhaustive() == 0
