@@ -248,7 +248,13 @@ def run_ours(args) -> None:
         plans.append(ctx.plan_create(descs, d_planes, d_pixels))
     launches_per_step = ctx.plan_launch_count(plans[0])
     torch.cuda.synchronize()
-    stream = torch.cuda.current_stream().cuda_stream
+    # an explicit stream: the events below and the kernels must be on the SAME stream
+    # (torch.cuda.Event only sees torch's current stream; a NULL handle would mean the
+    # context's own stream in the C ABI)
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     def barrier() -> None:
         if world > 1:
@@ -262,10 +268,10 @@ def run_ours(args) -> None:
     barrier()
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    e0.record(tstream)
     for s in range(args.steps):
         ctx.plan_launch(plans[s % ring], stream)
-    e1.record()
+    e1.record(tstream)
     barrier()
     ms = e0.elapsed_time(e1)
     # keep the clocks under observation for at least ~0.5 s of the same work

@@ -25,10 +25,10 @@ FLAG_PACKED_ROWS = 0x100
 
 # every symbol include/gidcuda.h declares
 EXPORTS = [
-    "gidcuda_abi_version", "gidcuda_device_count", "gidcuda_last_error", "gidcuda_create",
+    "gidcuda_abi_version", "gidcuda_device_count", "gidcuda_last_error", "gidcuda_set_option", "gidcuda_create",
     "gidcuda_destroy", "gidcuda_plane_geometry", "gidcuda_output_geometry", "gidcuda_job_begin",
     "gidcuda_job_plane", "gidcuda_job_submit", "gidcuda_job_wait", "gidcuda_job_release",
-    "gidcuda_plan_create", "gidcuda_plan_launch", "gidcuda_plan_launch_count",
+    "gidcuda_plan_create", "gidcuda_plan_launch", "gidcuda_plan_launch_count", "gidcuda_plan_uses_tma",
     "gidcuda_plan_destroy", "gidcuda_synchronize", "gidcuda_batch_create", "gidcuda_batch_run",
     "gidcuda_batch_destroy", "gidcuda_host_alloc", "gidcuda_host_free",
 ]
@@ -96,6 +96,7 @@ def load_library() -> ctypes.CDLL:
     L.gidcuda_last_error.restype = ctypes.c_char_p
     L.gidcuda_last_error.argtypes = [vp]
     L.gidcuda_create.argtypes = [ctypes.c_int, ctypes.POINTER(vp)]
+    L.gidcuda_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int]
     L.gidcuda_destroy.argtypes = [vp]
     L.gidcuda_plane_geometry.argtypes = [ctypes.POINTER(FrameDesc), ctypes.c_int, i32p, i32p]
     L.gidcuda_output_geometry.argtypes = [ctypes.POINTER(FrameDesc), ctypes.POINTER(ctypes.c_size_t),
@@ -110,6 +111,7 @@ def load_library() -> ctypes.CDLL:
                                       ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp)]
     L.gidcuda_plan_launch.argtypes = [vp, vp]
     L.gidcuda_plan_launch_count.argtypes = [vp]
+    L.gidcuda_plan_uses_tma.argtypes = [vp]
     L.gidcuda_plan_destroy.argtypes = [vp]
     L.gidcuda_synchronize.argtypes = [vp]
     L.gidcuda_batch_create.argtypes = [i32p, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(vp)]
@@ -123,6 +125,13 @@ def load_library() -> ctypes.CDLL:
             getattr(L, name).restype = ctypes.c_int
     _lib = L
     return L
+
+
+def set_option(name: str, value: int) -> None:
+    L = load_library()
+    rc = L.gidcuda_set_option(name.encode(), value)
+    if rc != GIDCUDA_OK:
+        raise GidCudaError(rc, (L.gidcuda_last_error(None) or b"").decode())
 
 
 class GidCuda:
@@ -209,6 +218,9 @@ class GidCuda:
 
     def plan_launch_count(self, plan) -> int:
         return self.lib.gidcuda_plan_launch_count(plan)
+
+    def plan_uses_tma(self, plan) -> int:
+        return self.lib.gidcuda_plan_uses_tma(plan)
 
     def plan_destroy(self, plan) -> None:
         self._check(self.lib.gidcuda_plan_destroy(plan), self.ctx)

@@ -143,6 +143,8 @@ inline void fill_frame_dev(const gidcuda_frame_desc *d, const Geometry &g, const
   f->out_format = g.out_format;
   f->tile_base = tile_base;
   f->q8 = g.q8 ? 1 : 0;
+  f->flags = 0;
+  if (g.stride % 8 == 0 && (reinterpret_cast<uintptr_t>(pixels) & 7u) == 0) f->flags |= FRAME_ALIGNED8;
 }
 
 }  // namespace gidk

@@ -19,8 +19,7 @@
 #include <thread>
 #include <vector>
 
-#include "frame_setup.hpp"
-#include "recon_launch.h"
+#include "launch_set.hpp"
 
 using gidk::FrameDev;
 using gidk::Layout;
@@ -32,6 +31,7 @@ static thread_local std::string t_last_error;
 
 struct gidcuda_ctx {
   int device = -1;
+  int num_sms = 148;
   cudaStream_t stream = nullptr;
   std::string last_error;
   std::vector<gidcuda_job *> free_jobs;  // recycled jobs (buffers kept)
@@ -104,6 +104,8 @@ extern "C" int gidcuda_create(int device, gidcuda_ctx **out) {
   ctx->device = device;
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
+  if (e == cudaSuccess) e = gidk::init_kernels();
   if (e != cudaSuccess) {
     delete ctx;
     return fail(nullptr, GIDCUDA_ERR_CUDA, "cannot initialise device %d: %s", device,
@@ -158,8 +160,7 @@ struct gidcuda_job {
   uint8_t *h_coef = nullptr;    // pinned: planes, contiguous
   uint8_t *h_pixels = nullptr;  // pinned
   uint8_t *d_coef = nullptr, *d_pixels = nullptr, *d_samples = nullptr;
-  FrameDev *d_frame = nullptr;
-  FrameDev *h_frame = nullptr;  // pinned staging of the descriptor
+  gidk::LaunchSet set;
   cudaEvent_t done = nullptr;
   cudaStream_t stream = nullptr;  // one stream per job: two jobs in flight overlap H2D and D2H
   enum { IDLE, BEGUN, SUBMITTED } state = IDLE;
@@ -168,17 +169,14 @@ struct gidcuda_job {
 static void job_free_buffers(gidcuda_job *j) {
   if (j->h_coef) cudaFreeHost(j->h_coef);
   if (j->h_pixels) cudaFreeHost(j->h_pixels);
-  if (j->h_frame) cudaFreeHost(j->h_frame);
   if (j->d_coef) cudaFree(j->d_coef);
   if (j->d_pixels) cudaFree(j->d_pixels);
   if (j->d_samples) cudaFree(j->d_samples);
-  if (j->d_frame) cudaFree(j->d_frame);
   if (j->done) cudaEventDestroy(j->done);
   if (j->stream) cudaStreamDestroy(j->stream);
+  j->set.destroy();
   j->stream = nullptr;
   j->h_coef = j->h_pixels = j->d_coef = j->d_pixels = j->d_samples = nullptr;
-  j->h_frame = nullptr;
-  j->d_frame = nullptr;
   j->done = nullptr;
   j->cap_coef = j->cap_pixels = j->cap_samples = 0;
 }
@@ -188,8 +186,6 @@ static int job_reserve(gidcuda_job *j) {
   const Geometry &g = j->geo;
   if (!j->done) CU_TRY(ctx, cudaEventCreateWithFlags(&j->done, cudaEventDisableTiming));
   if (!j->stream) CU_TRY(ctx, cudaStreamCreateWithFlags(&j->stream, cudaStreamNonBlocking));
-  if (!j->d_frame) CU_TRY(ctx, cudaMalloc(&j->d_frame, sizeof(FrameDev)));
-  if (!j->h_frame) CU_TRY(ctx, cudaHostAlloc((void **)&j->h_frame, sizeof(FrameDev), cudaHostAllocDefault));
   if (j->cap_coef < g.coef_bytes) {
     if (j->h_coef) cudaFreeHost(j->h_coef);
     if (j->d_coef) cudaFree(j->d_coef);
@@ -226,7 +222,7 @@ extern "C" int gidcuda_job_begin(gidcuda_ctx *ctx, const gidcuda_frame_desc *des
   if (rc != GIDCUDA_OK) return rc;
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   gidcuda_job *j = nullptr;
-  // recycle the free job whose buffers fit best
+  // recycle the free job whose buffers fit
   for (size_t i = 0; i < ctx->free_jobs.size(); i++) {
     gidcuda_job *c = ctx->free_jobs[i];
     if (c->cap_coef >= g.coef_bytes && c->cap_pixels >= g.pixel_bytes) {
@@ -252,6 +248,15 @@ extern "C" int gidcuda_job_begin(gidcuda_ctx *ctx, const gidcuda_frame_desc *des
     delete j;
     return rc;
   }
+  // launch tables for this frame (device addresses are fixed from here on)
+  gidk::FrameItem it;
+  it.desc = &j->desc;
+  it.geo = g;
+  for (int c = 0; c < 3; c++)
+    it.planes[c] = c < g.ncomp ? reinterpret_cast<const int16_t *>(j->d_coef + g.plane_off[c]) : nullptr;
+  it.pixels = j->d_pixels;
+  it.samples = j->d_samples;
+  j->set.build(std::vector<gidk::FrameItem>(1, it));
   // planes must be zero before entropy decode (:771, :1876-1882)
   memset(j->h_coef, 0, g.coef_bytes);
   j->state = gidcuda_job::BEGUN;
@@ -279,17 +284,10 @@ extern "C" int gidcuda_job_submit(gidcuda_job *job) {
     return fail(ctx, GIDCUDA_ERR_STATE, "gidcuda_job_submit: job was released");
   const Geometry &g = job->geo;
   CU_TRY(ctx, cudaSetDevice(ctx->device));
-  const int16_t *planes[3] = {nullptr, nullptr, nullptr};
-  for (int c = 0; c < g.ncomp; c++)
-    planes[c] = reinterpret_cast<const int16_t *>(job->d_coef + g.plane_off[c]);
-  fill_frame_dev(&job->desc, g, planes, job->d_pixels, job->d_samples, 0, job->h_frame);
   cudaStream_t s = job->stream;
-  CU_TRY(ctx, cudaMemcpyAsync(job->d_frame, job->h_frame, sizeof(FrameDev), cudaMemcpyHostToDevice, s));
+  if (job->state == gidcuda_job::BEGUN) CU_TRY(ctx, job->set.upload(s));  // tables: once per begin
   CU_TRY(ctx, cudaMemcpyAsync(job->d_coef, job->h_coef, g.coef_bytes, cudaMemcpyHostToDevice, s));
-  if (g.layout == gidk::LAYOUT_GENERIC)
-    CU_TRY(ctx, gidk::launch_generic(*job->h_frame, job->d_frame, s));
-  else
-    CU_TRY(ctx, gidk::launch_fused(g.layout, g.q8, job->d_frame, nullptr, g.ntiles, s));
+  CU_TRY(ctx, job->set.launch(ctx->num_sms, s));
   CU_TRY(ctx, cudaMemcpyAsync(job->h_pixels, job->d_pixels, g.pixel_bytes, cudaMemcpyDeviceToHost, s));
   CU_TRY(ctx, cudaEventRecord(job->done, s));
   job->state = gidcuda_job::SUBMITTED;
@@ -343,34 +341,16 @@ extern "C" int gidcuda_destroy(gidcuda_ctx *ctx) {
 // ---------------------------------------------------------------------------
 // plans: prepared launches over device-resident frames
 
-namespace {
-struct PlanGroup {
-  Layout layout;
-  bool q8;
-  std::vector<FrameDev> frames;
-  std::vector<uint32_t> tile_frame;
-  FrameDev *d_frames = nullptr;
-  uint32_t *d_tile_frame = nullptr;
-};
-}  // namespace
-
 struct gidcuda_plan {
   gidcuda_ctx *ctx = nullptr;
-  std::vector<PlanGroup> groups;       // fused layouts, one launch each
-  std::vector<FrameDev> generic;       // generic frames, two launches each
-  FrameDev *d_generic = nullptr;
-  std::vector<uint8_t *> d_samples;    // scratch of generic frames
-  int launches = 0;
+  std::vector<gidcuda_frame_desc> descs;
+  gidk::LaunchSet set;
+  std::vector<uint8_t *> d_samples;  // scratch of generic frames
 };
 
 extern "C" int gidcuda_plan_destroy(gidcuda_plan *plan) {
   if (!plan) return GIDCUDA_OK;
   (void)cudaSetDevice(plan->ctx->device);
-  for (PlanGroup &g : plan->groups) {
-    if (g.d_frames) cudaFree(g.d_frames);
-    if (g.d_tile_frame) cudaFree(g.d_tile_frame);
-  }
-  if (plan->d_generic) cudaFree(plan->d_generic);
   for (uint8_t *p : plan->d_samples) cudaFree(p);
   delete plan;
   return GIDCUDA_OK;
@@ -386,64 +366,37 @@ extern "C" int gidcuda_plan_create(gidcuda_ctx *ctx, int32_t n, const gidcuda_fr
   gidcuda_plan *plan = new (std::nothrow) gidcuda_plan();
   if (!plan) return fail(ctx, GIDCUDA_ERR_OUT_OF_MEMORY, "out of host memory");
   plan->ctx = ctx;
+  plan->descs.assign(descs, descs + n);
+  std::vector<gidk::FrameItem> items;
   int rc = GIDCUDA_OK;
   for (int32_t i = 0; i < n && rc == GIDCUDA_OK; i++) {
-    Geometry g;
-    rc = geometry_or_fail(ctx, &descs[i], &g);
+    gidk::FrameItem it;
+    it.desc = &plan->descs[(size_t)i];
+    rc = geometry_or_fail(ctx, it.desc, &it.geo);
     if (rc != GIDCUDA_OK) break;
-    const int16_t *planes[3] = {d_planes[3 * i], d_planes[3 * i + 1], d_planes[3 * i + 2]};
-    for (int c = 0; c < g.ncomp; c++)
-      if (!planes[c] || (reinterpret_cast<uintptr_t>(planes[c]) & 15u)) {
+    for (int c = 0; c < 3; c++) {
+      it.planes[c] = c < it.geo.ncomp ? d_planes[3 * i + c] : nullptr;
+      if (c < it.geo.ncomp && (!it.planes[c] || (reinterpret_cast<uintptr_t>(it.planes[c]) & 15u))) {
         rc = fail(ctx, GIDCUDA_ERR_BAD_ARGUMENT, "frame %d plane %d: null or not 16-byte aligned", i, c);
         break;
       }
+    }
     if (rc != GIDCUDA_OK) break;
     if (!d_pixels[i]) { rc = fail(ctx, GIDCUDA_ERR_BAD_ARGUMENT, "frame %d: null pixel buffer", i); break; }
-    if (g.layout == gidk::LAYOUT_GENERIC) {
-      uint8_t *scratch = nullptr;
-      cudaError_t e = cudaMalloc((void **)&scratch, g.sample_bytes);
+    it.pixels = d_pixels[i];
+    it.samples = nullptr;
+    if (it.geo.layout == gidk::LAYOUT_GENERIC) {
+      cudaError_t e = cudaMalloc((void **)&it.samples, it.geo.sample_bytes);
       if (e != cudaSuccess) { rc = fail(ctx, GIDCUDA_ERR_OUT_OF_MEMORY, "cudaMalloc: %s", cudaGetErrorString(e)); break; }
-      plan->d_samples.push_back(scratch);
-      FrameDev f;
-      fill_frame_dev(&descs[i], g, planes, d_pixels[i], scratch, 0, &f);
-      plan->generic.push_back(f);
-      continue;
+      plan->d_samples.push_back(it.samples);
     }
-    PlanGroup *grp = nullptr;
-    for (PlanGroup &pg : plan->groups)
-      if (pg.layout == g.layout && pg.q8 == g.q8) grp = &pg;
-    if (!grp) {
-      plan->groups.emplace_back();
-      grp = &plan->groups.back();
-      grp->layout = g.layout;
-      grp->q8 = g.q8;
-    }
-    FrameDev f;
-    fill_frame_dev(&descs[i], g, planes, d_pixels[i], nullptr, (uint32_t)grp->tile_frame.size(), &f);
-    const uint32_t fi = (uint32_t)grp->frames.size();
-    grp->frames.push_back(f);
-    grp->tile_frame.insert(grp->tile_frame.end(), g.ntiles, fi);
+    items.push_back(it);
   }
   if (rc == GIDCUDA_OK) {
-    for (PlanGroup &pg : plan->groups) {
-      cudaError_t e = cudaMalloc((void **)&pg.d_frames, pg.frames.size() * sizeof(FrameDev));
-      if (e == cudaSuccess) e = cudaMalloc((void **)&pg.d_tile_frame, pg.tile_frame.size() * sizeof(uint32_t));
-      if (e == cudaSuccess)
-        e = cudaMemcpy(pg.d_frames, pg.frames.data(), pg.frames.size() * sizeof(FrameDev), cudaMemcpyHostToDevice);
-      if (e == cudaSuccess)
-        e = cudaMemcpy(pg.d_tile_frame, pg.tile_frame.data(), pg.tile_frame.size() * sizeof(uint32_t),
-                       cudaMemcpyHostToDevice);
-      if (e != cudaSuccess) { rc = fail(ctx, GIDCUDA_ERR_CUDA, "plan upload: %s", cudaGetErrorString(e)); break; }
-      plan->launches += gidk::launches_fused();
-    }
-  }
-  if (rc == GIDCUDA_OK && !plan->generic.empty()) {
-    cudaError_t e = cudaMalloc((void **)&plan->d_generic, plan->generic.size() * sizeof(FrameDev));
-    if (e == cudaSuccess)
-      e = cudaMemcpy(plan->d_generic, plan->generic.data(), plan->generic.size() * sizeof(FrameDev),
-                     cudaMemcpyHostToDevice);
+    plan->set.build(items);
+    cudaError_t e = plan->set.upload(ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) rc = fail(ctx, GIDCUDA_ERR_CUDA, "plan upload: %s", cudaGetErrorString(e));
-    plan->launches += gidk::launches_generic() * (int)plan->generic.size();
   }
   if (rc != GIDCUDA_OK) {
     gidcuda_plan_destroy(plan);
@@ -458,16 +411,22 @@ extern "C" int gidcuda_plan_launch(gidcuda_plan *plan, void *cuda_stream) {
   gidcuda_ctx *ctx = plan->ctx;
   cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
   CU_TRY(ctx, cudaSetDevice(ctx->device));
-  for (PlanGroup &pg : plan->groups)
-    CU_TRY(ctx, gidk::launch_fused(pg.layout, pg.q8, pg.d_frames,
-                                   pg.frames.size() > 1 ? pg.d_tile_frame : nullptr,
-                                   (uint32_t)pg.tile_frame.size(), s));
-  for (size_t i = 0; i < plan->generic.size(); i++)
-    CU_TRY(ctx, gidk::launch_generic(plan->generic[i], plan->d_generic + i, s));
+  CU_TRY(ctx, plan->set.launch(ctx->num_sms, s));
   return GIDCUDA_OK;
 }
 
-extern "C" int gidcuda_plan_launch_count(const gidcuda_plan *plan) { return plan ? plan->launches : 0; }
+extern "C" int gidcuda_plan_launch_count(const gidcuda_plan *plan) { return plan ? plan->set.launch_count() : 0; }
+
+extern "C" int gidcuda_set_option(const char *name, int value) {
+  if (!name) return fail(nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "null option name");
+  if (strcmp(name, "tma") == 0) {
+    gidk::tma_option() = value ? 1 : 0;
+    return GIDCUDA_OK;
+  }
+  return fail(nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "unknown option '%s'", name);
+}
+
+extern "C" int gidcuda_plan_uses_tma(const gidcuda_plan *plan) { return plan ? plan->set.tma_groups : 0; }
 
 // ---------------------------------------------------------------------------
 // batch driver: per-GPU worker thread + work queue + ring of in-flight chunks
@@ -486,17 +445,15 @@ struct BatchRun {
   int32_t per_device[16] = {0};
 };
 
-// A chunk in flight on one device: staging buffers + plan-like launch state.
+// A chunk in flight on one device: staging buffers + launch tables.
 struct ChunkSlot {
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
   uint8_t *h_in = nullptr, *d_in = nullptr, *h_out = nullptr, *d_out = nullptr;
   size_t cap_in = 0, cap_out = 0;
-  FrameDev *h_frames = nullptr, *d_frames = nullptr;
-  uint32_t *h_tiles = nullptr, *d_tiles = nullptr;
-  size_t cap_frames = 0, cap_tiles = 0;
   uint8_t *d_samples = nullptr;
   size_t cap_samples = 0;
+  gidk::LaunchSet set;
   // contents
   std::vector<int32_t> images;
   std::vector<Geometry> geos;
@@ -507,6 +464,7 @@ struct ChunkSlot {
 struct Worker {
   int device = 0;
   int index = 0;
+  int num_sms = 148;
   std::thread thread;
   std::vector<ChunkSlot> slots;
 };
@@ -534,17 +492,16 @@ bool cu_ok(gidcuda_batch *b, cudaError_t e, const char *what) {
   return false;
 }
 
-template <typename T>
-bool grow_pair(gidcuda_batch *b, T **h, T **d, size_t *cap, size_t need, bool host_too) {
+bool grow_pair(gidcuda_batch *b, uint8_t **h, uint8_t **d, size_t *cap, size_t need, bool host_too) {
   if (*cap >= need) return true;
   if (host_too && *h) cudaFreeHost(*h);
   if (*d) cudaFree(*d);
-  *h = nullptr;
+  if (host_too) *h = nullptr;
   *d = nullptr;
   *cap = 0;
-  const size_t bytes = need * sizeof(T);
-  if (host_too && !cu_ok(b, cudaHostAlloc((void **)h, bytes, cudaHostAllocDefault), "cudaHostAlloc")) return false;
-  if (!cu_ok(b, cudaMalloc((void **)d, bytes), "cudaMalloc")) return false;
+  need += need / 4;
+  if (host_too && !cu_ok(b, cudaHostAlloc((void **)h, need, cudaHostAllocDefault), "cudaHostAlloc")) return false;
+  if (!cu_ok(b, cudaMalloc((void **)d, need), "cudaMalloc")) return false;
   *cap = need;
   return true;
 }
@@ -567,15 +524,17 @@ void slot_finish(gidcuda_batch *b, BatchRun *run, ChunkSlot &s) {
 }
 
 // Fill a slot with up to chunk_images images from the shared queue and submit.
+// Returns false when the queue is empty.
 bool slot_submit(gidcuda_batch *b, BatchRun *run, Worker &w, ChunkSlot &s) {
   s.images.clear();
   s.geos.clear();
   s.out_off.clear();
-  size_t in_bytes = 0, out_bytes = 0, ntiles = 0, samples = 0;
-  std::vector<size_t> in_off;
-  for (int k = 0; k < b->chunk_images; k++) {
+  size_t in_bytes = 0, out_bytes = 0, samples = 0;
+  std::vector<size_t> in_off, sample_off;
+  bool drained = false;
+  while ((int)s.images.size() < b->chunk_images) {
     const int32_t i = run->next.fetch_add(1);
-    if (i >= run->n) break;
+    if (i >= run->n) { drained = true; break; }
     Geometry g;
     const int rc = geometry_or_fail(nullptr, &run->descs[i], &g);
     bool good = rc == GIDCUDA_OK && run->pixels[i] != nullptr;
@@ -590,80 +549,39 @@ bool slot_submit(gidcuda_batch *b, BatchRun *run, Worker &w, ChunkSlot &s) {
     s.geos.push_back(g);
     in_off.push_back(in_bytes);
     s.out_off.push_back(out_bytes);
+    sample_off.push_back(samples);
     in_bytes += g.coef_bytes;
     out_bytes += round_up(g.pixel_bytes, 256);
-    ntiles += g.ntiles;
-    if (g.layout == gidk::LAYOUT_GENERIC) samples += g.sample_bytes;
+    if (g.layout == gidk::LAYOUT_GENERIC) samples += round_up(g.sample_bytes, 256);
   }
-  if (s.images.empty()) return false;
+  if (s.images.empty()) return !drained;
   const size_t nf = s.images.size();
-  if (!grow_pair(b, &s.h_in, &s.d_in, &s.cap_in, in_bytes, true)) return false;
-  if (!grow_pair(b, &s.h_out, &s.d_out, &s.cap_out, out_bytes, true)) return false;
-  if (!grow_pair(b, &s.h_frames, &s.d_frames, &s.cap_frames, nf, true)) return false;
-  if (!grow_pair(b, &s.h_tiles, &s.d_tiles, &s.cap_tiles, ntiles + 1, true)) return false;
-  if (samples) {
-    uint8_t *dummy = nullptr;
-    if (!grow_pair(b, &dummy, &s.d_samples, &s.cap_samples, samples, false)) return false;
-  }
+  uint8_t *none = nullptr;
+  if (!grow_pair(b, &s.h_in, &s.d_in, &s.cap_in, in_bytes, true)) return true;
+  if (!grow_pair(b, &s.h_out, &s.d_out, &s.cap_out, out_bytes, true)) return true;
+  if (samples && !grow_pair(b, &none, &s.d_samples, &s.cap_samples, samples, false)) return true;
   // stage coefficients into pinned memory, then one H2D copy per chunk
+  std::vector<gidk::FrameItem> items(nf);
   for (size_t k = 0; k < nf; k++) {
     const int32_t i = s.images[k];
     const Geometry &g = s.geos[k];
-    for (int c = 0; c < g.ncomp; c++)
+    gidk::FrameItem &it = items[k];
+    it.desc = &run->descs[i];
+    it.geo = g;
+    for (int c = 0; c < 3; c++) {
+      it.planes[c] = nullptr;
+      if (c >= g.ncomp) continue;
       memcpy(s.h_in + in_off[k] + g.plane_off[c], run->planes[3 * i + c], g.plane_bytes[c]);
-  }
-  // frames grouped by (layout, q8): fused groups first, generic frames after
-  struct Launch { Layout layout; bool q8; size_t first_frame, nframes, first_tile, ntiles; };
-  std::vector<Launch> launches;
-  std::vector<size_t> order;
-  for (int lay = 0; lay < 4; lay++)
-    for (int q = 0; q < 2; q++) {
-      Launch L{(Layout)lay, q == 1, order.size(), 0, 0, 0};
-      for (size_t k = 0; k < nf; k++)
-        if ((int)s.geos[k].layout == lay && s.geos[k].q8 == (q == 1)) { order.push_back(k); L.nframes++; }
-      if (L.nframes) launches.push_back(L);
+      it.planes[c] = reinterpret_cast<const int16_t *>(s.d_in + in_off[k] + g.plane_off[c]);
     }
-  const size_t nfused = order.size();
-  for (size_t k = 0; k < nf; k++)
-    if (s.geos[k].layout == gidk::LAYOUT_GENERIC) order.push_back(k);
-  size_t tile_cursor = 0, sample_cursor = 0;
-  size_t li = 0;
-  for (size_t pos = 0; pos < order.size(); pos++) {
-    const size_t k = order[pos];
-    const int32_t i = s.images[k];
-    const Geometry &g = s.geos[k];
-    const int16_t *planes[3] = {nullptr, nullptr, nullptr};
-    for (int c = 0; c < g.ncomp; c++)
-      planes[c] = reinterpret_cast<const int16_t *>(s.d_in + in_off[k] + g.plane_off[c]);
-    if (pos < nfused) {
-      while (pos >= launches[li].first_frame + launches[li].nframes) li++;
-      Launch &L = launches[li];
-      if (pos == L.first_frame) L.first_tile = tile_cursor;
-      fill_frame_dev(&run->descs[i], g, planes, s.d_out + s.out_off[k], nullptr,
-                     (uint32_t)(tile_cursor - L.first_tile), &s.h_frames[pos]);
-      for (uint32_t t = 0; t < g.ntiles; t++) s.h_tiles[tile_cursor + t] = (uint32_t)(pos - L.first_frame);
-      tile_cursor += g.ntiles;
-      L.ntiles += g.ntiles;
-    } else {
-      fill_frame_dev(&run->descs[i], g, planes, s.d_out + s.out_off[k], s.d_samples + sample_cursor, 0,
-                     &s.h_frames[pos]);
-      sample_cursor += g.sample_bytes;
-    }
+    it.pixels = s.d_out + s.out_off[k];
+    it.samples = g.layout == gidk::LAYOUT_GENERIC ? s.d_samples + sample_off[k] : nullptr;
   }
+  s.set.build(items);
   cudaStream_t st = s.stream;
   bool ok = cu_ok(b, cudaMemcpyAsync(s.d_in, s.h_in, in_bytes, cudaMemcpyHostToDevice, st), "H2D coefficients");
-  ok = ok && cu_ok(b, cudaMemcpyAsync(s.d_frames, s.h_frames, nf * sizeof(FrameDev), cudaMemcpyHostToDevice, st), "H2D frames");
-  ok = ok && cu_ok(b, cudaMemcpyAsync(s.d_tiles, s.h_tiles, (ntiles + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st), "H2D tiles");
-  int nl = 0;
-  for (const Launch &L : launches) {
-    ok = ok && cu_ok(b, gidk::launch_fused(L.layout, L.q8, s.d_frames + L.first_frame, s.d_tiles + L.first_tile,
-                                          (uint32_t)L.ntiles, st), "launch_fused");
-    nl += gidk::launches_fused();
-  }
-  for (size_t pos = nfused; pos < order.size(); pos++) {
-    ok = ok && cu_ok(b, gidk::launch_generic(s.h_frames[pos], s.d_frames + pos, st), "launch_generic");
-    nl += gidk::launches_generic();
-  }
+  ok = ok && cu_ok(b, s.set.upload(st), "H2D launch tables");
+  ok = ok && cu_ok(b, s.set.launch(w.num_sms, st), "kernel launch");
   ok = ok && cu_ok(b, cudaMemcpyAsync(s.h_out, s.d_out, out_bytes, cudaMemcpyDeviceToHost, st), "D2H pixels");
   ok = ok && cu_ok(b, cudaEventRecord(s.done, st), "cudaEventRecord");
   if (!ok) {
@@ -671,19 +589,21 @@ bool slot_submit(gidcuda_batch *b, BatchRun *run, Worker &w, ChunkSlot &s) {
       if (run->status) run->status[i] = GIDCUDA_ERR_CUDA;
       run->failed++;
     }
-    return true;  // keep draining the queue so that every image gets a status
+    return !drained;  // keep draining the queue so that every image gets a status
   }
-  run->h2d += (int64_t)(in_bytes + nf * sizeof(FrameDev) + (ntiles + 1) * sizeof(uint32_t));
+  run->h2d += (int64_t)(in_bytes + s.set.upload_bytes);
   run->d2h += (int64_t)out_bytes;
-  run->launches += nl;
+  run->launches += s.set.launch_count();
   run->per_device[w.index] += (int32_t)nf;
   s.busy = true;
-  return true;
+  return !drained;
 }
 
 void worker_main(gidcuda_batch *b, Worker *w) {
   uint64_t seen = 0;
-  if (!cu_ok(b, cudaSetDevice(w->device), "cudaSetDevice")) { /* reported on first run */ }
+  cu_ok(b, cudaSetDevice(w->device), "cudaSetDevice");
+  cu_ok(b, cudaDeviceGetAttribute(&w->num_sms, cudaDevAttrMultiProcessorCount, w->device), "device attribute");
+  cu_ok(b, gidk::init_kernels(), "kernel set-up");
   for (ChunkSlot &s : w->slots) {
     cu_ok(b, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), "cudaStreamCreate");
     cu_ok(b, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming), "cudaEventCreate");
@@ -697,7 +617,7 @@ void worker_main(gidcuda_batch *b, Worker *w) {
       seen = b->generation;
       run = b->run;
     }
-    // ring of slots: submit into the oldest free slot, finish it when it comes round again
+    // ring of slots: finish the oldest slot, refill it, move on
     size_t cur = 0;
     bool more = true;
     while (more) {
@@ -715,13 +635,10 @@ void worker_main(gidcuda_batch *b, Worker *w) {
   for (ChunkSlot &s : w->slots) {
     if (s.h_in) cudaFreeHost(s.h_in);
     if (s.h_out) cudaFreeHost(s.h_out);
-    if (s.h_frames) cudaFreeHost(s.h_frames);
-    if (s.h_tiles) cudaFreeHost(s.h_tiles);
     if (s.d_in) cudaFree(s.d_in);
     if (s.d_out) cudaFree(s.d_out);
-    if (s.d_frames) cudaFree(s.d_frames);
-    if (s.d_tiles) cudaFree(s.d_tiles);
     if (s.d_samples) cudaFree(s.d_samples);
+    s.set.destroy();
     if (s.done) cudaEventDestroy(s.done);
     if (s.stream) cudaStreamDestroy(s.stream);
   }

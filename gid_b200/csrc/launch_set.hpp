@@ -1,0 +1,271 @@
+// launch_set.hpp -- turns a list of frames into kernel launches: groups frames
+// by (sampling layout, table width), builds the tile table with the TMA
+// coordinates, encodes the coefficient tensor maps, uploads and launches.
+// Used by jobs (one frame), plans (device-resident batches) and the batch
+// driver's chunks.  Internal to the shim.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "frame_setup.hpp"
+#include "recon_launch.h"
+
+namespace gidk {
+
+struct FrameItem {
+  const gidcuda_frame_desc *desc;
+  Geometry geo;
+  const int16_t *planes[3];  // device pointers
+  uint8_t *pixels;           // device pointer
+  uint8_t *samples;          // device scratch (generic layouts only)
+};
+
+struct LaunchGroup {
+  Layout layout;
+  bool q8;
+  bool tma;
+  uint32_t first_frame, nframes, first_tile, ntiles;
+  CUtensorMap map2, map3;
+};
+
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                      CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                      CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library
+// links cudart statically and does not link libcuda).
+inline TensorMapEncodeFn tensor_map_encoder() {
+  static TensorMapEncodeFn fn = [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess) {
+      (void)cudaGetLastError();
+      p = nullptr;
+    }
+    return reinterpret_cast<TensorMapEncodeFn>(p);
+  }();
+  return fn;
+}
+
+// TMA staging can be switched off (environment GIDCUDA_DISABLE_TMA=1 or
+// gidcuda_set_option("tma", 0)); the plain-load kernel is then used.
+inline int &tma_option() {
+  static int enabled = [] {
+    const char *e = getenv("GIDCUDA_DISABLE_TMA");
+    return (e && *e && *e != '0') ? 0 : 1;
+  }();
+  return enabled;
+}
+inline bool tma_disabled_by_env() { return tma_option() == 0; }
+
+class LaunchSet {
+ public:
+  std::vector<FrameDev> frames;  // fused frames (group by group), then generic frames
+  std::vector<TileDesc> tiles;
+  std::vector<LaunchGroup> groups;
+  uint32_t n_fused = 0;
+  int tma_groups = 0;
+
+  ~LaunchSet() { destroy(); }
+
+  void destroy() {
+    if (d_frames_) cudaFree(d_frames_);
+    if (d_tiles_) cudaFree(d_tiles_);
+    if (h_frames_) cudaFreeHost(h_frames_);
+    if (h_tiles_) cudaFreeHost(h_tiles_);
+    d_frames_ = nullptr;
+    d_tiles_ = nullptr;
+    h_frames_ = nullptr;
+    h_tiles_ = nullptr;
+    cap_frames_ = cap_tiles_ = 0;
+  }
+
+  // Host-side preparation.  Every item must have passed make_geometry.
+  void build(const std::vector<FrameItem> &items) {
+    frames.clear();
+    tiles.clear();
+    groups.clear();
+    tma_groups = 0;
+    for (int lay = 0; lay < 4; lay++)
+      for (int q = 1; q >= 0; q--) {
+        LaunchGroup g;
+        memset(&g, 0, sizeof g);
+        g.layout = (Layout)lay;
+        g.q8 = q == 1;
+        g.first_frame = (uint32_t)frames.size();
+        g.first_tile = (uint32_t)tiles.size();
+        uintptr_t lo = ~(uintptr_t)0, hi = 0;
+        for (const FrameItem &it : items) {
+          if ((int)it.geo.layout != lay || it.geo.q8 != g.q8) continue;
+          for (int c = 0; c < it.geo.ncomp; c++) {
+            const uintptr_t p = reinterpret_cast<uintptr_t>(it.planes[c]);
+            if (p < lo) lo = p;
+            if (p + it.geo.plane_bytes[c] > hi) hi = p + it.geo.plane_bytes[c];
+          }
+        }
+        if (hi == 0) continue;
+        const uintptr_t base = lo & ~(uintptr_t)255;
+        bool aligned = true;
+        for (const FrameItem &it : items) {
+          if ((int)it.geo.layout != lay || it.geo.q8 != g.q8) continue;
+          for (int c = 0; c < it.geo.ncomp; c++)
+            if ((reinterpret_cast<uintptr_t>(it.planes[c]) - base) % 256 != 0) aligned = false;
+        }
+        g.tma = aligned && !tma_disabled_by_env() && encode_maps(&g, base, hi);
+        for (const FrameItem &it : items) {
+          if ((int)it.geo.layout != lay || it.geo.q8 != g.q8) continue;
+          FrameDev f;
+          fill_frame_dev(it.desc, it.geo, it.planes, it.pixels, nullptr, 0, &f);
+          const uint32_t fi = (uint32_t)frames.size() - g.first_frame;
+          frames.push_back(f);
+          append_tiles(it, fi, base);
+        }
+        g.nframes = (uint32_t)frames.size() - g.first_frame;
+        g.ntiles = (uint32_t)tiles.size() - g.first_tile;
+        if (g.tma) tma_groups++;
+        groups.push_back(g);
+      }
+    n_fused = (uint32_t)frames.size();
+    for (const FrameItem &it : items) {
+      if (it.geo.layout != LAYOUT_GENERIC) continue;
+      FrameDev f;
+      fill_frame_dev(it.desc, it.geo, it.planes, it.pixels, it.samples, 0, &f);
+      frames.push_back(f);
+    }
+  }
+
+  int launch_count() const { return (int)groups.size() * launches_fused() + (int)(frames.size() - n_fused) * launches_generic(); }
+
+  // Copies the tables to the device (asynchronously, from pinned staging).
+  cudaError_t upload(cudaStream_t s) {
+    cudaError_t e;
+    if (cap_frames_ < frames.size()) {
+      if (d_frames_) cudaFree(d_frames_);
+      if (h_frames_) cudaFreeHost(h_frames_);
+      d_frames_ = nullptr;
+      h_frames_ = nullptr;
+      cap_frames_ = 0;
+      const size_t n = frames.size() + frames.size() / 2 + 1;
+      if ((e = cudaMalloc((void **)&d_frames_, n * sizeof(FrameDev))) != cudaSuccess) return e;
+      if ((e = cudaHostAlloc((void **)&h_frames_, n * sizeof(FrameDev), cudaHostAllocDefault)) != cudaSuccess) return e;
+      cap_frames_ = n;
+    }
+    if (cap_tiles_ < tiles.size() + 1) {
+      if (d_tiles_) cudaFree(d_tiles_);
+      if (h_tiles_) cudaFreeHost(h_tiles_);
+      d_tiles_ = nullptr;
+      h_tiles_ = nullptr;
+      cap_tiles_ = 0;
+      const size_t n = tiles.size() + tiles.size() / 2 + 1;
+      if ((e = cudaMalloc((void **)&d_tiles_, n * sizeof(TileDesc))) != cudaSuccess) return e;
+      if ((e = cudaHostAlloc((void **)&h_tiles_, n * sizeof(TileDesc), cudaHostAllocDefault)) != cudaSuccess) return e;
+      cap_tiles_ = n;
+    }
+    memcpy(h_frames_, frames.data(), frames.size() * sizeof(FrameDev));
+    if (!tiles.empty()) memcpy(h_tiles_, tiles.data(), tiles.size() * sizeof(TileDesc));
+    if ((e = cudaMemcpyAsync(d_frames_, h_frames_, frames.size() * sizeof(FrameDev), cudaMemcpyHostToDevice, s)) != cudaSuccess)
+      return e;
+    if (!tiles.empty())
+      if ((e = cudaMemcpyAsync(d_tiles_, h_tiles_, tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, s)) != cudaSuccess)
+        return e;
+    upload_bytes = frames.size() * sizeof(FrameDev) + tiles.size() * sizeof(TileDesc);
+    return cudaSuccess;
+  }
+
+  cudaError_t launch(int num_sms, cudaStream_t s) const {
+    cudaError_t e;
+    for (const LaunchGroup &g : groups)
+      if ((e = launch_fused(g.layout, g.q8, g.tma, &g.map2, &g.map3, d_frames_ + g.first_frame,
+                            d_tiles_ + g.first_tile, g.ntiles, num_sms, s)) != cudaSuccess)
+        return e;
+    for (size_t i = n_fused; i < frames.size(); i++)
+      if ((e = launch_generic(frames[i], d_frames_ + i, s)) != cudaSuccess) return e;
+    return cudaSuccess;
+  }
+
+  size_t upload_bytes = 0;
+
+ private:
+  FrameDev *d_frames_ = nullptr, *h_frames_ = nullptr;
+  TileDesc *d_tiles_ = nullptr, *h_tiles_ = nullptr;
+  size_t cap_frames_ = 0, cap_tiles_ = 0;
+
+  static bool encode_maps(LaunchGroup *g, uintptr_t base, uintptr_t hi) {
+    TensorMapEncodeFn enc = tensor_map_encoder();
+    if (!enc) return false;
+    uint64_t rows = (uint64_t)((hi - base + 127) / 128);
+    rows = (rows + 1) & ~(uint64_t)1;
+    if (rows >= ((uint64_t)1 << 32)) return false;
+    {
+      const cuuint64_t dims[2] = {64, rows};
+      const cuuint64_t strides[1] = {128};
+      const cuuint32_t box[2] = {64, (cuuint32_t)kTileMcus};
+      const cuuint32_t estr[2] = {1, 1};
+      if (enc(&g->map2, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, reinterpret_cast<void *>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    }
+    {
+      const cuuint64_t dims[3] = {64, 2, rows / 2};
+      const cuuint64_t strides[2] = {128, 256};
+      const cuuint32_t box[3] = {64, 1, (cuuint32_t)kTileMcus};
+      const cuuint32_t estr[3] = {1, 1, 1};
+      if (enc(&g->map3, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, reinterpret_cast<void *>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    }
+    return true;
+  }
+
+  // Tiles of one frame.  coord[] = box row of each item relative to `base`:
+  // blocks for the 2-D map, block pairs for the 3-D (even/odd) luma map.
+  void append_tiles(const FrameItem &it, uint32_t frame_index, uintptr_t base) {
+    const Geometry &g = it.geo;
+    uint64_t row0[3] = {0, 0, 0};
+    for (int c = 0; c < g.ncomp; c++) row0[c] = (reinterpret_cast<uintptr_t>(it.planes[c]) - base) / 128;
+    const uint32_t nmcu = (uint32_t)g.mcux * (uint32_t)g.mcuy;
+    TileDesc t;
+    memset(&t, 0, sizeof t);
+    t.frame = frame_index;
+    if (g.layout == LAYOUT_GREY || g.layout == LAYOUT_444) {
+      for (uint32_t m0 = 0; m0 < nmcu; m0 += kTileMcus) {
+        t.m0 = m0;
+        if (g.layout == LAYOUT_GREY) {
+          t.coord[0] = (uint32_t)(row0[0] + m0);
+        } else {
+          t.coord[0] = (uint32_t)(row0[1] + m0);
+          t.coord[1] = (uint32_t)(row0[2] + m0);
+          t.coord[2] = (uint32_t)(row0[0] + m0);
+        }
+        tiles.push_back(t);
+      }
+      return;
+    }
+    const int V = g.layout == LAYOUT_420 ? 2 : 1;
+    for (int my = 0; my < g.mcuy; my++)
+      for (int mx0 = 0; mx0 < g.mcux; mx0 += kTileMcus) {
+        const uint32_t m0 = (uint32_t)my * (uint32_t)g.mcux + (uint32_t)mx0;
+        t.m0 = m0;
+        t.coord[0] = (uint32_t)(row0[1] + m0);
+        t.coord[1] = (uint32_t)(row0[2] + m0);
+        for (int sy = 0; sy < V; sy++)
+          for (int sx = 0; sx < 2; sx++) {
+            const uint64_t blk = row0[0] + (uint64_t)(my * V + sy) * (uint64_t)g.bx[0] + 2u * (uint64_t)mx0;
+            t.coord[2 + sy * 2 + sx] = (uint32_t)(blk / 2);  // row0 and bx are even: exact
+          }
+        tiles.push_back(t);
+      }
+  }
+};
+
+}  // namespace gidk

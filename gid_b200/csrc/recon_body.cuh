@@ -10,6 +10,11 @@
 //   colour + clipping to W x H       :1018-1054 (rows/cols beyond the image are
 //                                    skipped, :1023, :1026)
 //   output layout                    test/benchmark.adb:67-81: top-down RGB8
+//
+// The body is parameterised by a "block source": where the 8 rows of 8 int16
+// coefficients of a block come from -- global memory (LdgSource, also the host
+// build used by the CPU tests) or the TMA-filled shared-memory ring of
+// recon_kernels.cu (TmaSource).
 #pragma once
 
 #include "recon_math.cuh"
@@ -23,6 +28,11 @@ enum Layout : int { LAYOUT_GREY = 0, LAYOUT_444 = 1, LAYOUT_422 = 2, LAYOUT_420 
 
 // Output pixel formats, = GIDCUDA_OUT_* of include/gidcuda.h
 enum OutFormat : int { OUT_RGB8 = 0, OUT_BGR8_BOTTOM_UP = 1 };
+
+// FrameDev::flags
+enum FrameFlags : uint32_t {
+  FRAME_ALIGNED8 = 1u,  // pixel base and stride are multiples of 8: rows of a block go out as 3 x 8 bytes
+};
 
 // Per-frame descriptor in device memory (one per image of a launch).
 struct FrameDev {
@@ -40,6 +50,7 @@ struct FrameDev {
   //   q8 == 0:                      word k = q[2k] | q[2k+1] << 16
   uint32_t qw[3][32];
   int32_t q8;
+  uint32_t flags;
   // generic layouts only: 8-bit sample planes written by the IDCT pass
   uint8_t *samples[3];
 };
@@ -53,9 +64,6 @@ struct alignas(8) u32x2 { uint32_t x, y; };
 #endif
 
 #if defined(__CUDA_ARCH__)
-__device__ __forceinline__ u32x4 ld_block_row(const int16_t *p) {
-  return __ldg(reinterpret_cast<const uint4 *>(p));
-}
 // a = two signed 16-bit lanes, b = four unsigned bytes: a.lo*b0 + a.hi*b1 + c
 __device__ __forceinline__ int dp2a_lo_su(uint32_t a, uint32_t b, int c) {
   int d;
@@ -69,12 +77,6 @@ __device__ __forceinline__ int dp2a_hi_su(uint32_t a, uint32_t b, int c) {
   return d;
 }
 #else
-inline u32x4 ld_block_row(const int16_t *p) {
-  u32x4 v;
-  const uint32_t *q = reinterpret_cast<const uint32_t *>(p);
-  v.x = q[0]; v.y = q[1]; v.z = q[2]; v.w = q[3];
-  return v;
-}
 inline int dp2a_lo_su(uint32_t a, uint32_t b, int c) {
   return (int)(int16_t)(a & 0xFFFF) * (int)(b & 0xFF) + (int)(int16_t)(a >> 16) * (int)((b >> 8) & 0xFF) + c;
 }
@@ -82,6 +84,24 @@ inline int dp2a_hi_su(uint32_t a, uint32_t b, int c) {
   return (int)(int16_t)(a & 0xFFFF) * (int)((b >> 16) & 0xFF) + (int)(int16_t)(a >> 16) * (int)(b >> 24) + c;
 }
 #endif
+
+// Block source reading global memory directly (fallback kernel, generic pass 1,
+// and the host build).
+struct LdgSource {
+  const FrameDev *f;
+  GID_HD void load(int comp, int bx, int by, u32x4 (&raw)[8]) const {
+    const int16_t *p = f->plane[comp] + ((size_t)by * (size_t)f->bx[comp] + (size_t)bx) * 64;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+#if defined(__CUDA_ARCH__)
+      raw[r] = __ldg(reinterpret_cast<const uint4 *>(p + 8 * r));
+#else
+      const uint32_t *q = reinterpret_cast<const uint32_t *>(p + 8 * r);
+      raw[r].x = q[0]; raw[r].y = q[1]; raw[r].z = q[2]; raw[r].w = q[3];
+#endif
+    }
+  }
+};
 
 // De-quantise one coefficient pair (two int16 in w) with table word q.
 template <bool Q8>
@@ -95,13 +115,10 @@ GID_HD void dequant_pair(uint32_t w, uint32_t q, int &lo, int &hi) {
   }
 }
 
-// Load + de-quantise + inverse DCT of one block.  qw: the component's 32
-// table words (in shared memory on the device).  Result: un-clipped samples.
+// De-quantise + inverse DCT of one block held as 8 raw rows.  qw: the
+// component's 32 table words.  Result: un-clipped samples.
 template <bool Q8>
-GID_HD void load_idct_block(const int16_t *src, const uint32_t *qw, int (&b)[64]) {
-  u32x4 raw[8];
-#pragma unroll
-  for (int r = 0; r < 8; r++) raw[r] = ld_block_row(src + 8 * r);
+GID_HD void dequant_idct(const u32x4 (&raw)[8], const uint32_t *qw, int (&b)[64]) {
 #pragma unroll
   for (int r = 0; r < 8; r++) {
     dequant_pair<Q8>(raw[r].x, qw[4 * r + 0], b[8 * r + 0], b[8 * r + 1]);
@@ -112,127 +129,184 @@ GID_HD void load_idct_block(const int16_t *src, const uint32_t *qw, int (&b)[64]
   idct_8x8(b);
 }
 
-GID_HD uint32_t pack4(int a, int b, int c, int d) {
-  return (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16) | ((uint32_t)d << 24);
-}
-
 // Clip + pack the 64 samples of a block into 16 words (row r -> words 2r, 2r+1).
 GID_HD void pack_block(const int (&b)[64], uint32_t (&p)[16]) {
 #pragma unroll
-  for (int i = 0; i < 16; i++)
-    p[i] = pack4(clip255(b[4 * i]), clip255(b[4 * i + 1]), clip255(b[4 * i + 2]), clip255(b[4 * i + 3]));
+  for (int i = 0; i < 16; i++) p[i] = pack_sat4(b[4 * i], b[4 * i + 1], b[4 * i + 2], b[4 * i + 3]);
 }
 
-GID_HD int byte_of(uint32_t w, int k) { return (int)((w >> (8 * k)) & 0xFFu); }
+// Destination of pixel (x0, y): rows are flipped for the bottom-up format.
+GID_HD uint8_t *row_ptr(const FrameDev &f, int x0, int y) {
+  const int yy = f.out_format == OUT_BGR8_BOTTOM_UP ? f.height - 1 - y : y;
+  return f.pixels + (size_t)yy * f.stride + (size_t)x0 * 3;
+}
 
-// Write one row of 8 pixels (r/g/b un-clipped ints) of a block whose left edge
-// is pixel column x0, on image row y.  Fast path: the 24 bytes are stored as
-// three 8-byte words when the row lies fully inside the image and is 8-byte
-// aligned; otherwise byte by byte with clipping to the image (:1023, :1026).
-GID_HD void store_row8(const FrameDev &f, int x0, int y, const int (&r)[8], const int (&g)[8],
-                       const int (&bl)[8]) {
-  if (y >= f.height || x0 >= f.width) return;
-  int c0[8], c2[8];
-  int yy = y;
-  if (f.out_format == OUT_BGR8_BOTTOM_UP) {
-    // test/to_bmp.adb:94-146: bottom-up rows, B G R byte order
-    yy = f.height - 1 - y;
-#pragma unroll
-    for (int i = 0; i < 8; i++) { c0[i] = bl[i]; c2[i] = r[i]; }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 8; i++) { c0[i] = r[i]; c2[i] = bl[i]; }
-  }
-  uint8_t *dst = f.pixels + (size_t)yy * f.stride + (size_t)x0 * 3;
-  if (x0 + 8 <= f.width && (((uintptr_t)dst) & 7u) == 0) {
-    uint32_t w[6];
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const int i = 4 * h;
-      w[3 * h + 0] = pack4(clip255(c0[i]), clip255(g[i]), clip255(c2[i]), clip255(c0[i + 1]));
-      w[3 * h + 1] = pack4(clip255(g[i + 1]), clip255(c2[i + 1]), clip255(c0[i + 2]), clip255(g[i + 2]));
-      w[3 * h + 2] = pack4(clip255(c2[i + 2]), clip255(c0[i + 3]), clip255(g[i + 3]), clip255(c2[i + 3]));
+// Slow path: byte stores with clipping to the image (:1023, :1026); used for
+// partial blocks at the right edge and for frames whose rows are not 8-byte
+// aligned.  c0/c1/c2 = the three output channels in memory order.
+#if defined(__CUDACC__)
+static __host__ __device__ __noinline__
+#else
+inline
+#endif
+void store_row8_bytes(const FrameDev &f, int x0, int y, const int *c0, const int *c1, const int *c2) {
+  uint8_t *dst = row_ptr(f, x0, y);
+  for (int i = 0; i < 8; i++) {
+    if (x0 + i < f.width) {
+      dst[3 * i + 0] = (uint8_t)clip255(c0[i]);
+      dst[3 * i + 1] = (uint8_t)clip255(c1[i]);
+      dst[3 * i + 2] = (uint8_t)clip255(c2[i]);
     }
-    u32x2 *d2 = reinterpret_cast<u32x2 *>(dst);
+  }
+}
+
+// One row of 8 pixels of the block whose left edge is pixel column x0.
+// c0/c1/c2 un-clipped, in memory order.  `fast` = whole block inside the image
+// and FRAME_ALIGNED8: 24 bytes leave as three 8-byte stores.
+GID_HD void store_row8(const FrameDev &f, bool fast, int x0, int y, const int (&c0)[8], const int (&c1)[8],
+                       const int (&c2)[8]) {
+  if (y >= f.height) return;
+  if (fast) {
+    u32x2 *d2 = reinterpret_cast<u32x2 *>(row_ptr(f, x0, y));
     u32x2 v;
-    v.x = w[0]; v.y = w[1]; d2[0] = v;
-    v.x = w[2]; v.y = w[3]; d2[1] = v;
-    v.x = w[4]; v.y = w[5]; d2[2] = v;
-  } else {
+    v.x = pack_sat4(c0[0], c1[0], c2[0], c0[1]);
+    v.y = pack_sat4(c1[1], c2[1], c0[2], c1[2]);
+    d2[0] = v;
+    v.x = pack_sat4(c2[2], c0[3], c1[3], c2[3]);
+    v.y = pack_sat4(c0[4], c1[4], c2[4], c0[5]);
+    d2[1] = v;
+    v.x = pack_sat4(c1[5], c2[5], c0[6], c1[6]);
+    v.y = pack_sat4(c2[6], c0[7], c1[7], c2[7]);
+    d2[2] = v;
+  } else if (x0 < f.width) {
+    store_row8_bytes(f, x0, y, c0, c1, c2);
+  }
+}
+
+GID_HD bool block_is_fast(const FrameDev &f, int x0) {
+  return (f.flags & FRAME_ALIGNED8) != 0 && x0 + 8 <= f.width;
+}
+
+// Per-thread scratch for the packed 8-bit samples of the current MCU: 8 rows of
+// 8 bytes for Cb, Cr and the luma block being emitted.  On the device it lives
+// in shared memory as [row][thread] (row r of thread t at base[r * stride + t],
+// conflict-free 8-byte accesses); the host build uses plain arrays (stride 1).
+// Keeping these bytes out of registers lets the kernel LOOP over the blocks of
+// an MCU and over pixel rows, so that one copy of the IDCT (~20 KiB of code)
+// and one copy of the row emitter serve every block: a fully unrolled MCU body
+// (~100 KiB) thrashes the instruction cache (measured: no_instructions was the
+// top stall reason, icc hit rate 76 %).
+struct Scratch {
+  u32x2 *cb, *cr, *y;
+  int stride;
+};
+
+// Emit the pixel rows of one luma block from the scratch (Step 4-6 of GID:
+// upsampling by replication, colour transformation, output).
+//   H, V   luma sampling (1 or 2); GREY = no chroma
+//   sx, sy position of the block inside the MCU
+template <int H, int V, bool GREY>
+GID_HD void emit_block_rows(const FrameDev &f, const Scratch &sc, int x0, int y0, int sx, int sy) {
+  const bool fast = (f.flags & FRAME_ALIGNED8) != 0 && x0 + 8 <= f.width;
+  const bool bgr = f.out_format == OUT_BGR8_BOTTOM_UP;
+  if (x0 >= f.width) return;
+#pragma unroll 1
+  for (int i = 0; i < 8 / V; i++) {
+    ChromaTerms t[8 / H];
+    if (!GREY) {
+      const int crow = sy * (8 / V) + i;  // row inside the chroma block
+      const u32x2 cbw = sc.cb[crow * sc.stride], crw = sc.cr[crow * sc.stride];
+      if (H == 1) {
+        t[0] = chroma_terms_packed<0>(cbw.x, crw.x); t[1] = chroma_terms_packed<1>(cbw.x, crw.x);
+        t[2] = chroma_terms_packed<2>(cbw.x, crw.x); t[3] = chroma_terms_packed<3>(cbw.x, crw.x);
+        t[4 / H] = chroma_terms_packed<0>(cbw.y, crw.y); t[5 / H] = chroma_terms_packed<1>(cbw.y, crw.y);
+        t[6 / H] = chroma_terms_packed<2>(cbw.y, crw.y); t[7 / H] = chroma_terms_packed<3>(cbw.y, crw.y);
+      } else {
+        // block sx covers chroma columns 4*sx .. 4*sx+3, i.e. word sx of the row
+        const uint32_t wb = sx ? cbw.y : cbw.x, wr = sx ? crw.y : crw.x;
+        t[0] = chroma_terms_packed<0>(wb, wr); t[1] = chroma_terms_packed<1>(wb, wr);
+        t[2] = chroma_terms_packed<2>(wb, wr); t[3] = chroma_terms_packed<3>(wb, wr);
+      }
+      if (bgr) {
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-      if (x0 + i < f.width) {
-        dst[3 * i + 0] = (uint8_t)clip255(c0[i]);
-        dst[3 * i + 1] = (uint8_t)clip255(g[i]);
-        dst[3 * i + 2] = (uint8_t)clip255(c2[i]);
+        for (int k = 0; k < 8 / H; k++) { const int s = t[k].r; t[k].r = t[k].b; t[k].b = s; }
+      }
+    }
+#pragma unroll
+    for (int ry = 0; ry < V; ry++) {
+      const int row = i * V + ry;  // row inside the luma block
+      const int y = y0 + row;
+      if (y >= f.height) continue;
+      const u32x2 yw = sc.y[row * sc.stride];
+      if (GREY) {
+        // R = G = B = Y (:1036-1038)
+        if (fast) {
+          u32x2 *d2 = reinterpret_cast<u32x2 *>(row_ptr(f, x0, y));
+          u32x2 v;
+          v.x = prmt(yw.x, 0u, 0x1000u);  // Y0 Y0 Y0 Y1
+          v.y = prmt(yw.x, 0u, 0x2211u);  // Y1 Y1 Y2 Y2
+          d2[0] = v;
+          v.x = prmt(yw.x, 0u, 0x3332u);  // Y2 Y3 Y3 Y3
+          v.y = prmt(yw.y, 0u, 0x1000u);
+          d2[1] = v;
+          v.x = prmt(yw.y, 0u, 0x2211u);
+          v.y = prmt(yw.y, 0u, 0x3332u);
+          d2[2] = v;
+        } else {
+          int v[8];
+#pragma unroll
+          for (int c = 0; c < 8; c++) v[c] = (int)(((c < 4 ? yw.x : yw.y) >> (8 * (c & 3))) & 0xFFu);
+          store_row8_bytes(f, x0, y, v, v, v);
+        }
+      } else {
+        int c0[8], c1[8], c2[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          const int yv = (int)(((c < 4 ? yw.x : yw.y) >> (8 * (c & 3))) & 0xFFu);
+          const ChromaTerms &tt = t[c / H];
+          c0[c] = yv + tt.r;
+          c1[c] = yv + tt.g;
+          c2[c] = yv + tt.b;
+        }
+        store_row8(f, fast, x0, y, c0, c1, c2);
       }
     }
   }
 }
 
-// One MCU of a grey frame: a single block (single-component scans use 8x8
-// MCUs, :1952-1971).  R = G = B = Y (:1036-1038).
-template <bool Q8>
-GID_HD void mcu_grey(const FrameDev &f, const uint32_t *qw, int mx, int my) {
-  int b[64];
-  load_idct_block<Q8>(f.plane[0] + ((size_t)my * f.bx[0] + mx) * 64, qw, b);
-#pragma unroll
-  for (int r = 0; r < 8; r++) {
-    int v[8];
-#pragma unroll
-    for (int c = 0; c < 8; c++) v[c] = b[8 * r + c];
-    store_row8(f, mx * 8, my * 8 + r, v, v, v);
-  }
-}
-
-// One MCU of a YCbCr frame with luma sampling H x V in {1x1, 2x1, 2x2} and
-// 1x1 chroma: 4:4:4, 4:2:2 (h2v1), 4:2:0.  Chroma blocks first (kept as packed
-// bytes), then each luma block is transformed and turned into pixels.
-template <int H, int V, bool Q8>
-GID_HD void mcu_ycc(const FrameDev &f, const uint32_t *qw /* [3][32] */, int mx, int my) {
-  uint32_t cbp[16], crp[16];
-  {
+// One MCU: loop over its items (Cb, Cr, then the luma blocks in raster order; a
+// single luma block for grey).  Each item: fetch 8 raw rows from the block
+// source, de-quantise, inverse DCT, clip + pack to bytes into the scratch; luma
+// blocks are then turned into pixels.
+template <int H, int V, bool GREY, bool Q8, class Src>
+GID_HD void mcu_run(const FrameDev &f, const uint32_t *qw /* [3][32] */, Src &src, const Scratch &sc, int mx,
+                    int my) {
+  constexpr int NI = GREY ? 1 : 2 + H * V;
+#pragma unroll 1
+  for (int it = 0; it < NI; it++) {
+    int comp = 0, sx = 0, sy = 0;
+    if (!GREY) {
+      if (it < 2) {
+        comp = it + 1;
+      } else {
+        sx = (it - 2) % H;
+        sy = (it - 2) / H;
+      }
+    }
+    const int bxi = comp == 0 ? mx * H + sx : mx, byi = comp == 0 ? my * V + sy : my;
+    u32x4 raw[8];
+    src.load(comp, bxi, byi, raw);
     int b[64];
-    load_idct_block<Q8>(f.plane[1] + ((size_t)my * f.bx[1] + mx) * 64, qw + 32, b);
-    pack_block(b, cbp);
-    load_idct_block<Q8>(f.plane[2] + ((size_t)my * f.bx[2] + mx) * 64, qw + 64, b);
-    pack_block(b, crp);
-  }
+    dequant_idct<Q8>(raw, qw + 32 * comp, b);
+    u32x2 *dst = comp == 0 ? sc.y : (comp == 1 ? sc.cb : sc.cr);
 #pragma unroll
-  for (int sy = 0; sy < V; sy++) {
-#pragma unroll
-    for (int sx = 0; sx < H; sx++) {
-      const int bxi = mx * H + sx, byi = my * V + sy;
-      int b[64];
-      load_idct_block<Q8>(f.plane[0] + ((size_t)byi * f.bx[0] + bxi) * 64, qw, b);
-      // chroma rows covering this luma block: V == 1 -> 8 rows, V == 2 -> 4 rows
-#pragma unroll
-      for (int cr = 0; cr < 8 / V; cr++) {
-        const int crow = sy * (8 / V) + cr;  // row inside the chroma block
-        // chroma samples under the 8 pixel columns: H == 1 -> 8 samples, H == 2 -> 4
-        ChromaTerms t[8 / H];
-#pragma unroll
-        for (int k = 0; k < 8 / H; k++) {
-          const int ccol = sx * (8 / H) + k;  // column inside the chroma block
-          const uint32_t wb = cbp[crow * 2 + (ccol >> 2)], wr = crp[crow * 2 + (ccol >> 2)];
-          t[k] = chroma_terms(byte_of(wb, ccol & 3), byte_of(wr, ccol & 3));
-        }
-#pragma unroll
-        for (int ry = 0; ry < V; ry++) {
-          const int row = cr * V + ry;  // row inside the luma block
-          int r[8], g[8], bl[8];
-#pragma unroll
-          for (int c = 0; c < 8; c++) {
-            const int yv = clip255(b[8 * row + c]);
-            const ChromaTerms &tt = t[c / H];
-            r[c] = yv + tt.r;
-            g[c] = yv + tt.g;
-            bl[c] = yv + tt.b;
-          }
-          store_row8(f, bxi * 8, byi * 8 + row, r, g, bl);
-        }
-      }
+    for (int r = 0; r < 8; r++) {
+      u32x2 v;
+      v.x = pack_sat4(b[8 * r + 0], b[8 * r + 1], b[8 * r + 2], b[8 * r + 3]);
+      v.y = pack_sat4(b[8 * r + 4], b[8 * r + 5], b[8 * r + 6], b[8 * r + 7]);
+      dst[r * sc.stride] = v;
     }
+    if (comp == 0) emit_block_rows<H, V, GREY>(f, sc, bxi * 8, byi * 8, sx, sy);
   }
 }
 

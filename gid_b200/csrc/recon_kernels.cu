@@ -1,9 +1,23 @@
 // recon_kernels.cu -- sm_100a kernels of the JPEG reconstruction path.
 //
-// v0 layout: one thread = one MCU, 128 MCUs per CTA ("tile"); a tile is a run
-// of consecutive MCUs of one frame in raster order, so neighbouring threads
-// read neighbouring coefficient blocks and write neighbouring 24-byte pixel
-// runs of the same image rows.
+// Mapping: one thread = one MCU, 128 MCUs per tile (recon_launch.h).  A thread
+// does, entirely in registers, dequant + IDCT of its chroma blocks (kept as
+// packed bytes), then dequant + IDCT + upsample + colour of each luma block and
+// writes 24-byte pixel runs; neighbouring threads write neighbouring runs of
+// the same image rows.
+//
+// recon_tma_kernel (main path): persistent CTAs (3 per SM), each walking a
+//   contiguous chunk of the tile list.  Coefficients reach the threads through
+//   a 4-slot ring of 16 KiB shared-memory slots filled by TMA
+//   (cp.async.bulk.tensor with a 128-byte swizzle, so that thread t reading row
+//   t of a slot in 16-byte pieces is bank-conflict free); full/empty mbarriers
+//   per slot; a slot is released as soon as the four warps have pulled their
+//   blocks into registers, so the ring stays 3 items ahead of the arithmetic.
+//   The kernel is bound by integer issue (see recon_math.cuh), not by HBM, for
+//   4:4:4; the ring keeps the issue slots busy while HBM streams.
+// recon_ldg_kernel (fallback): same body, 128-bit global loads; used when the
+//   coefficient planes cannot be described by one tensor map (alignment).
+// generic_*: two-pass path for sampling layouts without a fused kernel.
 #include "recon_launch.h"
 
 namespace gidk {
@@ -13,29 +27,238 @@ namespace {
 constexpr int kFrameWords = (int)(sizeof(FrameDev) / sizeof(uint32_t));
 static_assert(sizeof(FrameDev) % sizeof(uint32_t) == 0, "FrameDev must be word sized");
 
+constexpr int kNumSlots = 2;
+constexpr int kSlotBytes = kTileMcus * 128;  // one block (64 x int16) per thread
+constexpr int kCtasPerSm = 3;
+
+template <int LAYOUT> struct LayoutInfo;
+template <> struct LayoutInfo<LAYOUT_GREY> { static constexpr int H = 1, V = 1, NI = 1; static constexpr bool linear = true; };
+template <> struct LayoutInfo<LAYOUT_444> { static constexpr int H = 1, V = 1, NI = 3; static constexpr bool linear = true; };
+template <> struct LayoutInfo<LAYOUT_422> { static constexpr int H = 2, V = 1, NI = 4; static constexpr bool linear = false; };
+template <> struct LayoutInfo<LAYOUT_420> { static constexpr int H = 2, V = 2, NI = 6; static constexpr bool linear = false; };
+
+// ---- PTX wrappers -------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
+// ---- block source: the TMA ring -------------------------------------------------
+
+// Items flow through the ring in a fixed order: for every tile of the CTA's
+// chunk, items 0 .. NI-1.  Consumer item k lives in slot k % 4 and completes
+// phase (k / 4) & 1 of full[slot].  After pulling item k into registers every
+// warp arrives on empty[slot]; thread 0 then issues item k + 3 (into the slot
+// item k - 1 used, whose empty barrier has normally completed long ago).
+template <int LAYOUT>
+struct TmaSource {
+  using LI = LayoutInfo<LAYOUT>;
+  uint32_t slots, full, empty;  // shared-window addresses
+  uint32_t lane_off;            // t * 128 + ((t & 7) << 4): row t, chunk index pre-xored
+  uint32_t k;                   // consumer item counter
+  // producer cursor (meaningful in thread 0 only)
+  const TileDesc *tiles;
+  const CUtensorMap *map2, *map3;
+  uint32_t p_tile, p_end, p_item, kp;
+
+  __device__ __forceinline__ void produce_one() {
+    if (p_tile >= p_end) return;
+    const uint32_t s = kp & (kNumSlots - 1);
+    if (kp >= (uint32_t)kNumSlots) mbar_wait(empty + 8 * s, ((kp / kNumSlots) - 1) & 1);
+    const uint32_t coord = __ldg(&tiles[p_tile].coord[p_item]);
+    const uint32_t bar = full + 8 * s;
+    mbar_arrive_expect_tx(bar, kSlotBytes);
+    const uint32_t dst = slots + s * kSlotBytes;
+    if (LI::H == 2 && p_item >= 2) tma_load_3d(dst, map3, 0, (int)((p_item - 2) & 1), (int)coord, bar);
+    else tma_load_2d(dst, map2, 0, (int)coord, bar);
+    kp++;
+    if (++p_item == (uint32_t)LI::NI) { p_item = 0; p_tile++; }
+  }
+
+  // consume the next item: this thread's block (row t of the slot) -> raw[8]
+  __device__ __forceinline__ void load(int, int, int, u32x4 (&raw)[8]) {
+    const uint32_t s = k & (kNumSlots - 1);
+    mbar_wait(full + 8 * s, (k / kNumSlots) & 1);
+    const uint32_t base = slots + s * kSlotBytes + lane_off;
+#pragma unroll
+    for (int j = 0; j < 8; j++) raw[j] = lds128(base ^ (uint32_t)(j << 4));
+    release(s);
+  }
+  // threads without an MCU in this tile still take part in the protocol
+  __device__ __forceinline__ void skip() {
+    const uint32_t s = k & (kNumSlots - 1);
+    mbar_wait(full + 8 * s, (k / kNumSlots) & 1);
+    release(s);
+  }
+  __device__ __forceinline__ void release(uint32_t s) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(empty + 8 * s);
+    if (threadIdx.x == 0) produce_one();
+    k++;
+  }
+};
+
+// scratch for the packed samples: [3 planes][8 rows][128 threads] x 8 bytes
+constexpr int kScratchBytes = 3 * 8 * kTileMcus * 8;
+
+__device__ __forceinline__ Scratch make_scratch(uint8_t *base, uint32_t t) {
+  Scratch sc;
+  u32x2 *p = reinterpret_cast<u32x2 *>(base) + t;
+  sc.cb = p;
+  sc.cr = p + 8 * kTileMcus;
+  sc.y = p + 16 * kTileMcus;
+  sc.stride = kTileMcus;
+  return sc;
+}
+
+template <int LAYOUT, bool Q8, class Src>
+__device__ __forceinline__ void run_mcu(const FrameDev &f, Src &src, const Scratch &sc, int mx, int my) {
+  using LI = LayoutInfo<LAYOUT>;
+  mcu_run<LI::H, LI::V, LAYOUT == LAYOUT_GREY, Q8>(f, &f.qw[0][0], src, sc, mx, my);
+}
+
+// MCU (mx, my) of thread t in a tile starting at m0, or false when the thread
+// has no MCU (tail of the frame / of the MCU row).
+template <int LAYOUT>
+__device__ __forceinline__ bool tile_mcu(const FrameDev &f, uint32_t m0, uint32_t t, int &mx, int &my) {
+  if (LayoutInfo<LAYOUT>::linear) {
+    const uint32_t m = m0 + t;
+    if (m >= (uint32_t)(f.mcux * f.mcuy)) return false;
+    my = (int)(m / (uint32_t)f.mcux);
+    mx = (int)(m - (uint32_t)my * (uint32_t)f.mcux);
+    return true;
+  }
+  my = (int)(m0 / (uint32_t)f.mcux);
+  mx = (int)(m0 - (uint32_t)my * (uint32_t)f.mcux + t);
+  return mx < f.mcux;
+}
+
+constexpr int kDynSmem = kNumSlots * kSlotBytes + kScratchBytes + 1024;  // + slack for 1024-byte alignment
+
+template <int LAYOUT, bool Q8>
+__global__ void __launch_bounds__(kTileMcus, kCtasPerSm)
+recon_tma_kernel(const __grid_constant__ CUtensorMap map2, const __grid_constant__ CUtensorMap map3,
+                 const FrameDev *__restrict__ frames, const TileDesc *__restrict__ tiles, uint32_t ntiles) {
+  using LI = LayoutInfo<LAYOUT>;
+  extern __shared__ uint8_t dyn_smem[];
+  __shared__ __align__(16) uint32_t s_frame_words[kFrameWords];
+  __shared__ __align__(8) uint64_t s_full[kNumSlots], s_empty[kNumSlots];
+
+  // contiguous chunk of the tile list per CTA
+  const uint32_t per = (ntiles + gridDim.x - 1) / gridDim.x;
+  const uint32_t t_begin = blockIdx.x * per;
+  const uint32_t t_end = min(ntiles, t_begin + per);
+  if (t_begin >= t_end) return;
+
+  const uint32_t t = threadIdx.x;
+  TmaSource<LAYOUT> src;
+  src.slots = (smem_u32(dyn_smem) + 1023u) & ~1023u;
+  src.full = smem_u32(s_full);
+  src.empty = smem_u32(s_empty);
+  src.lane_off = t * 128u + ((t & 7u) << 4);
+  src.k = 0;
+  src.tiles = tiles;
+  src.map2 = &map2;
+  src.map3 = &map3;
+  src.p_tile = t_begin;
+  src.p_end = t_end;
+  src.p_item = 0;
+  src.kp = 0;
+  if (t == 0) {
+    for (int s = 0; s < kNumSlots; s++) {
+      mbar_init(src.full + 8 * s, 1);
+      mbar_init(src.empty + 8 * s, kTileMcus / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (t == 0)
+    for (int i = 0; i < kNumSlots - 1; i++) src.produce_one();
+
+  const Scratch scratch =
+      make_scratch(dyn_smem + (src.slots - smem_u32(dyn_smem)) + kNumSlots * kSlotBytes, t);
+  uint32_t cur_frame = 0xFFFFFFFFu;
+#pragma unroll 1
+  for (uint32_t tile = t_begin; tile < t_end; tile++) {
+    const uint32_t fi = __ldg(&tiles[tile].frame);
+    const uint32_t m0 = __ldg(&tiles[tile].m0);
+    if (fi != cur_frame) {  // uniform over the CTA
+      __syncthreads();
+      const uint32_t *g = reinterpret_cast<const uint32_t *>(frames + fi);
+      for (int i = t; i < kFrameWords; i += kTileMcus) s_frame_words[i] = __ldg(g + i);
+      __syncthreads();
+      cur_frame = fi;
+    }
+    const FrameDev &f = *reinterpret_cast<const FrameDev *>(s_frame_words);
+    int mx, my;
+    if (tile_mcu<LAYOUT>(f, m0, t, mx, my)) {
+      run_mcu<LAYOUT, Q8>(f, src, scratch, mx, my);
+    } else {
+#pragma unroll
+      for (int i = 0; i < LI::NI; i++) src.skip();
+    }
+  }
+}
+
 template <int LAYOUT, bool Q8>
 __global__ void __launch_bounds__(kTileMcus)
-recon_fused_kernel(const FrameDev *__restrict__ frames, const uint32_t *__restrict__ tile_frame,
-                   uint32_t ntiles) {
+recon_ldg_kernel(const FrameDev *__restrict__ frames, const TileDesc *__restrict__ tiles, uint32_t ntiles) {
   __shared__ __align__(16) uint32_t s_frame_words[kFrameWords];
+  __shared__ __align__(16) uint8_t s_scratch[kScratchBytes];
   const uint32_t tile = blockIdx.x;
   if (tile >= ntiles) return;
-  const uint32_t fi = tile_frame ? tile_frame[tile] : 0u;
+  const uint32_t fi = __ldg(&tiles[tile].frame);
+  const uint32_t m0 = __ldg(&tiles[tile].m0);
   {
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(frames + fi);
-    for (int i = threadIdx.x; i < kFrameWords; i += kTileMcus) s_frame_words[i] = src[i];
+    const uint32_t *g = reinterpret_cast<const uint32_t *>(frames + fi);
+    for (int i = threadIdx.x; i < kFrameWords; i += kTileMcus) s_frame_words[i] = __ldg(g + i);
   }
   __syncthreads();
   const FrameDev &f = *reinterpret_cast<const FrameDev *>(s_frame_words);
-  const uint32_t m = (tile - f.tile_base) * kTileMcus + threadIdx.x;
-  if (m >= (uint32_t)(f.mcux * f.mcuy)) return;
-  const int my = (int)(m / (uint32_t)f.mcux);
-  const int mx = (int)(m - (uint32_t)my * (uint32_t)f.mcux);
-  const uint32_t *qw = &f.qw[0][0];
-  if (LAYOUT == LAYOUT_GREY) mcu_grey<Q8>(f, qw, mx, my);
-  else if (LAYOUT == LAYOUT_444) mcu_ycc<1, 1, Q8>(f, qw, mx, my);
-  else if (LAYOUT == LAYOUT_422) mcu_ycc<2, 1, Q8>(f, qw, mx, my);
-  else mcu_ycc<2, 2, Q8>(f, qw, mx, my);
+  int mx, my;
+  if (!tile_mcu<LAYOUT>(f, m0, threadIdx.x, mx, my)) return;
+  LdgSource src{&f};
+  run_mcu<LAYOUT, Q8>(f, src, make_scratch(s_scratch, threadIdx.x), mx, my);
 }
 
 // ---- generic path -----------------------------------------------------------
@@ -62,7 +285,12 @@ generic_idct_kernel(const FrameDev *__restrict__ frame, int ncomp) {
   const int by = (int)(idx / (uint32_t)f.bx[c]);
   const int bx = (int)(idx - (uint32_t)by * (uint32_t)f.bx[c]);
   int b[64];
-  load_idct_block<Q8>(f.plane[c] + (size_t)idx * 64, &f.qw[c][0], b);
+  {
+    LdgSource src{&f};
+    u32x4 raw[8];
+    src.load(c, bx, by, raw);
+    dequant_idct<Q8>(raw, &f.qw[c][0], b);
+  }
   uint32_t p[16];
   pack_block(b, p);
   const size_t pitch = (size_t)f.bx[c] * 8;
@@ -109,26 +337,56 @@ generic_color_kernel(const FrameDev *__restrict__ frame, int ncomp, int hmax, in
   dst[2] = (uint8_t)b;
 }
 
-template <int LAYOUT>
-cudaError_t launch_fused_q(bool q8, const FrameDev *d_frames, const uint32_t *d_tile_frame,
-                           uint32_t ntiles, cudaStream_t stream) {
-  if (q8)
-    recon_fused_kernel<LAYOUT, true><<<ntiles, kTileMcus, 0, stream>>>(d_frames, d_tile_frame, ntiles);
-  else
-    recon_fused_kernel<LAYOUT, false><<<ntiles, kTileMcus, 0, stream>>>(d_frames, d_tile_frame, ntiles);
+template <int LAYOUT, bool Q8>
+cudaError_t launch_one(bool use_tma, const CUtensorMap *map2, const CUtensorMap *map3, const FrameDev *d_frames,
+                       const TileDesc *d_tiles, uint32_t ntiles, int num_sms, cudaStream_t stream) {
+  if (use_tma) {
+    uint32_t grid = (uint32_t)(num_sms * kCtasPerSm);
+    if (grid > ntiles) grid = ntiles;
+    recon_tma_kernel<LAYOUT, Q8><<<grid, kTileMcus, kDynSmem, stream>>>(*map2, *map3, d_frames, d_tiles, ntiles);
+  } else {
+    recon_ldg_kernel<LAYOUT, Q8><<<ntiles, kTileMcus, 0, stream>>>(d_frames, d_tiles, ntiles);
+  }
   return cudaGetLastError();
+}
+
+template <int LAYOUT>
+cudaError_t launch_q(bool q8, bool use_tma, const CUtensorMap *map2, const CUtensorMap *map3,
+                     const FrameDev *d_frames, const TileDesc *d_tiles, uint32_t ntiles, int num_sms,
+                     cudaStream_t stream) {
+  return q8 ? launch_one<LAYOUT, true>(use_tma, map2, map3, d_frames, d_tiles, ntiles, num_sms, stream)
+            : launch_one<LAYOUT, false>(use_tma, map2, map3, d_frames, d_tiles, ntiles, num_sms, stream);
+}
+
+template <int LAYOUT, bool Q8>
+cudaError_t set_attr() {
+  return cudaFuncSetAttribute(recon_tma_kernel<LAYOUT, Q8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem);
 }
 
 }  // namespace
 
-cudaError_t launch_fused(Layout layout, bool q8, const FrameDev *d_frames,
-                         const uint32_t *d_tile_frame, uint32_t ntiles, cudaStream_t stream) {
+cudaError_t init_kernels() {
+  cudaError_t e;
+  if ((e = set_attr<LAYOUT_GREY, true>()) != cudaSuccess) return e;
+  if ((e = set_attr<LAYOUT_GREY, false>()) != cudaSuccess) return e;
+  if ((e = set_attr<LAYOUT_444, true>()) != cudaSuccess) return e;
+  if ((e = set_attr<LAYOUT_444, false>()) != cudaSuccess) return e;
+  if ((e = set_attr<LAYOUT_422, true>()) != cudaSuccess) return e;
+  if ((e = set_attr<LAYOUT_422, false>()) != cudaSuccess) return e;
+  if ((e = set_attr<LAYOUT_420, true>()) != cudaSuccess) return e;
+  if ((e = set_attr<LAYOUT_420, false>()) != cudaSuccess) return e;
+  return cudaSuccess;
+}
+
+cudaError_t launch_fused(Layout layout, bool q8, bool use_tma, const CUtensorMap *map2, const CUtensorMap *map3,
+                         const FrameDev *d_frames, const TileDesc *d_tiles, uint32_t ntiles, int num_sms,
+                         cudaStream_t stream) {
   if (ntiles == 0) return cudaSuccess;
   switch (layout) {
-    case LAYOUT_GREY: return launch_fused_q<LAYOUT_GREY>(q8, d_frames, d_tile_frame, ntiles, stream);
-    case LAYOUT_444: return launch_fused_q<LAYOUT_444>(q8, d_frames, d_tile_frame, ntiles, stream);
-    case LAYOUT_422: return launch_fused_q<LAYOUT_422>(q8, d_frames, d_tile_frame, ntiles, stream);
-    case LAYOUT_420: return launch_fused_q<LAYOUT_420>(q8, d_frames, d_tile_frame, ntiles, stream);
+    case LAYOUT_GREY: return launch_q<LAYOUT_GREY>(q8, use_tma, map2, map3, d_frames, d_tiles, ntiles, num_sms, stream);
+    case LAYOUT_444: return launch_q<LAYOUT_444>(q8, use_tma, map2, map3, d_frames, d_tiles, ntiles, num_sms, stream);
+    case LAYOUT_422: return launch_q<LAYOUT_422>(q8, use_tma, map2, map3, d_frames, d_tiles, ntiles, num_sms, stream);
+    case LAYOUT_420: return launch_q<LAYOUT_420>(q8, use_tma, map2, map3, d_frames, d_tiles, ntiles, num_sms, stream);
     default: return cudaErrorInvalidValue;
   }
 }

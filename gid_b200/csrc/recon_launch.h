@@ -2,6 +2,7 @@
 // the kernels (recon_kernels.cu).  Not installed.
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -11,20 +12,37 @@ namespace gidk {
 
 constexpr int kTileMcus = 128;  // MCUs (= threads) per tile of the fused kernels
 
-// Fused dequant + IDCT + upsample + colour kernel over `ntiles` tiles.
-//   d_frames     array of frame descriptors (device)
-//   d_tile_frame frame index of every tile (device), or nullptr when the launch
-//                covers a single frame (index 0)
-// Tile t of frame f covers MCUs (t - f.tile_base) * kTileMcus .. + kTileMcus - 1.
-cudaError_t launch_fused(Layout layout, bool q8, const FrameDev *d_frames,
-                         const uint32_t *d_tile_frame, uint32_t ntiles, cudaStream_t stream);
+// One tile = up to kTileMcus consecutive MCUs of one frame, starting at linear
+// MCU index m0.  Layouts whose components all have one block per MCU (grey,
+// 4:4:4) use linear runs that may wrap over MCU rows; 4:2:2 / 4:2:0 tiles stay
+// inside one MCU row, so that every item of the tile is ONE box of the
+// coefficient tensor map.  coord[i] = row coordinate of item i for the TMA
+// kernel (items: grey {Y}; YCbCr {Cb, Cr, Y(sy, sx) in raster order}).
+struct TileDesc {
+  uint32_t frame;
+  uint32_t m0;
+  uint32_t coord[6];
+};
+static_assert(sizeof(TileDesc) == 32, "TileDesc is 32 bytes");
+
+// Fused dequant + IDCT + upsample + colour over `ntiles` tiles of one layout.
+//   use_tma: coefficients are staged through a shared-memory ring by TMA
+//            (cp.async.bulk.tensor, 128-byte swizzle); needs map2/map3.
+//            Otherwise every thread reads its blocks with 128-bit global loads.
+//   map2: [rows][64] int16 view of the coefficient arena, box 128 x 64
+//   map3: [rows/2][2][64] view (even/odd blocks) for the luma plane of 4:2:x
+cudaError_t launch_fused(Layout layout, bool q8, bool use_tma, const CUtensorMap *map2,
+                         const CUtensorMap *map3, const FrameDev *d_frames, const TileDesc *d_tiles,
+                         uint32_t ntiles, int num_sms, cudaStream_t stream);
 
 // Generic path for one frame (any integer up-factors): pass 1 writes 8-bit
 // sample planes (f.samples), pass 2 upsamples + colour-converts.  `h_frame` is
 // the host copy of d_frame[0] (for grid sizing).
 cudaError_t launch_generic(const FrameDev &h_frame, const FrameDev *d_frame, cudaStream_t stream);
 
-// How many kernel launches each of the above performs.
+// One-time kernel attribute set-up (dynamic shared memory opt-in).
+cudaError_t init_kernels();
+
 inline int launches_fused() { return 1; }
 inline int launches_generic() { return 2; }
 

@@ -6,8 +6,16 @@
 //   Inverse_DCT_8x8_Block               gid-decoding_jpg.adb:790-907
 //   Color_Transformation_and_Output     gid-decoding_jpg.adb:1018-1054
 // The arithmetic is 32-bit two's-complement with wrap-around (GNAT Integer in
-// the Fast_unchecked build) and Ada's "/" truncates toward zero, so every
-// division below is a C "/" on a signed int, never a shift.
+// the Fast_unchecked build) and Ada's "/" truncates toward zero.
+//
+// Instruction budget (B200, measured with tools/ubench.cu): every integer
+// instruction class issues at 2 warp-instructions / clock / SM; IMAD (FMA pipe)
+// and ALU-pipe instructions (SHF, LOP3, IADD3, LEA, VIMNMX, PRMT, I2IP) overlap
+// up to the issue limit of 4 / clock / SM.  The code below is therefore written
+// to (a) minimise the instruction count and (b) split it evenly over the two
+// pipes: multiplications are re-associated into 2-term IMAD chains, sums feeding
+// a division are 3-input adds, and the truncating division puts its sign
+// correction on the FMA pipe (tdiv).
 //
 // The functions are __host__ __device__ so that tests/ can compile the same
 // code for the CPU and compare it with the oracle without a GPU (test-only
@@ -31,10 +39,26 @@ constexpr int W1 = 2841, W2 = 2676, W3 = 2408, W5 = 1609, W6 = 1108, W7 = 565;
 GID_HD int wadd(int a, int b) { return (int)((unsigned)a + (unsigned)b); }
 GID_HD int wsub(int a, int b) { return (int)((unsigned)a - (unsigned)b); }
 GID_HD int wmul(int a, int b) { return (int)((unsigned)a * (unsigned)b); }
-// a * b + c
 GID_HD int wmad(int a, int b, int c) { return (int)((unsigned)a * (unsigned)b + (unsigned)c); }
+GID_HD int wadd3(int a, int b, int c) { return (int)((unsigned)a + (unsigned)b + (unsigned)c); }
+GID_HD int wneg(int a) { return (int)(0u - (unsigned)a); }
 
 GID_HD int clip255(int x) { return x < 0 ? 0 : (x > 255 ? 255 : x); }
+
+// Truncating division by 2**K (Ada "/"):  x / 2**K = (x + (x < 0 ? 2**K - 1 : 0)) >> K.
+// Device: sign bit (SHF, ALU pipe), bias by IMAD sign * (2**K - 1) + x (FMA pipe),
+// arithmetic shift (ALU pipe).
+template <int K>
+GID_HD int tdiv(int x) {
+#if defined(__CUDA_ARCH__)
+  const unsigned s = (unsigned)x >> 31;
+  int t;
+  asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(t) : "r"(s), "r"((1 << K) - 1), "r"(x));
+  return t >> K;
+#else
+  return x / (1 << K);
+#endif
+}
 
 // Row_IDCT, gid-decoding_jpg.adb:799-845.
 // The "all AC zero" shortcut (:810-812) returns blk(0)*8 for the 8 outputs.
@@ -43,45 +67,32 @@ GID_HD int clip255(int x) { return x < 0 ? 0 : (x > 255 ? 255 : x); }
 // shortcut is reproduced by selecting the constant: 0 instead of 128.
 // (Exact while |blk(0)| < 2**20, which every 8-bit JPEG stream satisfies:
 // |DC| <= 2047 * 255.)
+//
+// Re-association (all exact modulo 2**32):
+//   x8 = W7*(x4+x5); x4' = x8 + (W1-W7)*x4 = W1*x4 + W7*x5;  x5' = x8 - (W1+W7)*x5 = W7*x4 - W1*x5
+//   x8 = W3*(x6+x7); x6' = x8 - (W3-W5)*x6 = W5*x6 + W3*x7;  x7' = x8 - (W3+W5)*x7 = W3*x6 - W5*x7
+//   x1 = W6*(x3+x2); x2' = x1 - (W2+W6)*x2 = W6*x3 - W2*x2;  x3' = x1 + (W2-W6)*x3 = W2*x3 + W6*x2
+//   181*(x4+x5)+128 = 181*x4 + (181*x5 + 128), and each output is one 3-input sum.
 GID_HD void row_idct(int &b0, int &b1, int &b2, int &b3, int &b4, int &b5, int &b6, int &b7) {
-  int x0, x1, x2, x3, x4, x5, x6, x7, x8;
-  x1 = wmul(b4, 2048);
-  x2 = b6;
-  x3 = b2;
-  x4 = b1;
-  x5 = b7;
-  x6 = b5;
-  x7 = b3;
-  const int any_ac = x1 | x2 | x3 | x4 | x5 | x6 | x7;
-  x0 = wmad(b0, 2048, any_ac != 0 ? 128 : 0);
-  // odd part: x4' = x8 + (W1-W7)*x4 with x8 = W7*(x4+x5)  ==  W1*x4 + W7*x5 (mod 2**32), etc.
-  const int o4 = wmad(W1, x4, wmul(W7, x5));
-  const int o5 = wsub(wmul(W7, x4), wmul(W1, x5));
-  const int o6 = wmad(W5, x6, wmul(W3, x7));
-  const int o7 = wsub(wmul(W3, x6), wmul(W5, x7));
-  x8 = wadd(x0, x1);
-  x0 = wsub(x0, x1);
-  // even part: x2' = W6*(x3+x2) - (W2+W6)*x2 == W6*x3 - W2*x2 ; x3' = W6*x2 + W2*x3
-  const int e2 = wsub(wmul(W6, x3), wmul(W2, x2));
-  const int e3 = wmad(W2, x3, wmul(W6, x2));
-  x1 = wadd(o4, o6);
-  x4 = wsub(o4, o6);
-  x6 = wadd(o5, o7);
-  x5 = wsub(o5, o7);
-  x7 = wadd(x8, e3);
-  x8 = wsub(x8, e3);
-  x3 = wadd(x0, e2);
-  x0 = wsub(x0, e2);
-  x2 = wmad(181, wadd(x4, x5), 128) / 256;
-  x4 = wmad(181, wsub(x4, x5), 128) / 256;
-  b0 = wadd(x7, x1) / 256;
-  b1 = wadd(x3, x2) / 256;
-  b2 = wadd(x0, x4) / 256;
-  b3 = wadd(x8, x6) / 256;
-  b4 = wsub(x8, x6) / 256;
-  b5 = wsub(x0, x4) / 256;
-  b6 = wsub(x3, x2) / 256;
-  b7 = wsub(x7, x1) / 256;
+  const int x1 = wmul(b4, 2048);
+  const int any_ac = x1 | b1 | b2 | b3 | b5 | b6 | b7;
+  const int x0 = wmad(b0, 2048, any_ac != 0 ? 128 : 0);
+  const int o4 = wmad(W1, b1, wmul(W7, b7)), o5 = wsub(wmul(W7, b1), wmul(W1, b7));
+  const int o6 = wmad(W5, b5, wmul(W3, b3)), o7 = wsub(wmul(W3, b5), wmul(W5, b3));
+  const int e2 = wsub(wmul(W6, b2), wmul(W2, b6)), e3 = wmad(W2, b2, wmul(W6, b6));
+  const int A = wadd(x0, x1), B = wsub(x0, x1);
+  const int p1 = wadd(o4, o6), q4 = wsub(o4, o6), p6 = wadd(o5, o7), q5 = wsub(o5, o7);
+  const int h = wmad(181, q4, 128);
+  const int x2 = tdiv<8>(wmad(181, q5, h));
+  const int x4 = tdiv<8>(wmad(-181, q5, h));
+  b0 = tdiv<8>(wadd3(A, e3, p1));
+  b7 = tdiv<8>(wadd3(A, e3, wneg(p1)));
+  b3 = tdiv<8>(wadd3(A, wneg(e3), p6));
+  b4 = tdiv<8>(wadd3(A, wneg(e3), wneg(p6)));
+  b1 = tdiv<8>(wadd3(B, e2, x2));
+  b6 = tdiv<8>(wadd3(B, e2, wneg(x2)));
+  b2 = tdiv<8>(wadd3(B, wneg(e2), x4));
+  b5 = tdiv<8>(wadd3(B, wneg(e2), wneg(x4)));
 }
 
 // Col_IDCT, gid-decoding_jpg.adb:847-895, general path only: the shortcut at
@@ -89,42 +100,24 @@ GID_HD void row_idct(int &b0, int &b1, int &b2, int &b3, int &b4, int &b5, int &
 // ((b0*256+8192)/16384 is the same rational number).  Outputs are NOT clipped
 // here: v = s / 2**14 + 128; the caller saturates to 0..255 (Clip, :755-756).
 GID_HD void col_idct(int &b0, int &b1, int &b2, int &b3, int &b4, int &b5, int &b6, int &b7) {
-  int x0, x1, x2, x3, x4, x5, x6, x7, x8;
-  x1 = wmul(b4, 256);
-  x2 = b6;
-  x3 = b2;
-  x4 = b1;
-  x5 = b7;
-  x6 = b5;
-  x7 = b3;
-  x0 = wmad(b0, 256, 8192);
-  // x4' = (W7*(x4+x5) + 4 + (W1-W7)*x4) / 8 == (W1*x4 + W7*x5 + 4) / 8, etc.
-  const int o4 = wmad(W1, x4, wmad(W7, x5, 4)) / 8;
-  const int o5 = wsub(wmad(W7, x4, 4), wmul(W1, x5)) / 8;
-  const int o6 = wmad(W5, x6, wmad(W3, x7, 4)) / 8;
-  const int o7 = wsub(wmad(W3, x6, 4), wmul(W5, x7)) / 8;
-  x8 = wadd(x0, x1);
-  x0 = wsub(x0, x1);
-  const int e2 = wsub(wmad(W6, x3, 4), wmul(W2, x2)) / 8;
-  const int e3 = wmad(W2, x3, wmad(W6, x2, 4)) / 8;
-  x1 = wadd(o4, o6);
-  x4 = wsub(o4, o6);
-  x6 = wadd(o5, o7);
-  x5 = wsub(o5, o7);
-  x7 = wadd(x8, e3);
-  x8 = wsub(x8, e3);
-  x3 = wadd(x0, e2);
-  x0 = wsub(x0, e2);
-  x2 = wmad(181, wadd(x4, x5), 128) / 256;
-  x4 = wmad(181, wsub(x4, x5), 128) / 256;
-  b0 = wadd(wadd(x7, x1) / 16384, 128);
-  b1 = wadd(wadd(x3, x2) / 16384, 128);
-  b2 = wadd(wadd(x0, x4) / 16384, 128);
-  b3 = wadd(wadd(x8, x6) / 16384, 128);
-  b4 = wadd(wsub(x8, x6) / 16384, 128);
-  b5 = wadd(wsub(x0, x4) / 16384, 128);
-  b6 = wadd(wsub(x3, x2) / 16384, 128);
-  b7 = wadd(wsub(x7, x1) / 16384, 128);
+  const int x1 = wmul(b4, 256);
+  const int x0 = wmad(b0, 256, 8192);
+  const int o4 = tdiv<3>(wmad(W1, b1, wmad(W7, b7, 4))), o5 = tdiv<3>(wsub(wmad(W7, b1, 4), wmul(W1, b7)));
+  const int o6 = tdiv<3>(wmad(W5, b5, wmad(W3, b3, 4))), o7 = tdiv<3>(wsub(wmad(W3, b5, 4), wmul(W5, b3)));
+  const int e2 = tdiv<3>(wsub(wmad(W6, b2, 4), wmul(W2, b6))), e3 = tdiv<3>(wmad(W2, b2, wmad(W6, b6, 4)));
+  const int A = wadd(x0, x1), B = wsub(x0, x1);
+  const int p1 = wadd(o4, o6), q4 = wsub(o4, o6), p6 = wadd(o5, o7), q5 = wsub(o5, o7);
+  const int h = wmad(181, q4, 128);
+  const int x2 = tdiv<8>(wmad(181, q5, h));
+  const int x4 = tdiv<8>(wmad(-181, q5, h));
+  b0 = wadd(tdiv<14>(wadd3(A, e3, p1)), 128);
+  b7 = wadd(tdiv<14>(wadd3(A, e3, wneg(p1))), 128);
+  b3 = wadd(tdiv<14>(wadd3(A, wneg(e3), p6)), 128);
+  b4 = wadd(tdiv<14>(wadd3(A, wneg(e3), wneg(p6))), 128);
+  b1 = wadd(tdiv<14>(wadd3(B, e2, x2)), 128);
+  b6 = wadd(tdiv<14>(wadd3(B, e2, wneg(x2))), 128);
+  b2 = wadd(tdiv<14>(wadd3(B, wneg(e2), x4)), 128);
+  b5 = wadd(tdiv<14>(wadd3(B, wneg(e2), wneg(x4))), 128);
 }
 
 // Inverse_DCT_8x8_Block on 64 registers (natural order, index = 8*row + col).
@@ -137,6 +130,31 @@ GID_HD void idct_8x8(int (&b)[64]) {
 #pragma unroll
   for (int c = 0; c < 8; c++)
     col_idct(b[c], b[8 + c], b[16 + c], b[24 + c], b[32 + c], b[40 + c], b[48 + c], b[56 + c]);
+}
+
+// Four samples -> four saturated bytes (Clip, :755-756, then packing), v0 in the
+// low byte.  Device: two I2IP (cvt.pack.sat.u8.s32), which saturate and merge.
+GID_HD uint32_t pack_sat4(int v0, int v1, int v2, int v3) {
+#if defined(__CUDA_ARCH__)
+  uint32_t t, w;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(v3), "r"(v2), "r"(0));
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(v1), "r"(v0), "r"(t));
+  return w;
+#else
+  return (uint32_t)clip255(v0) | ((uint32_t)clip255(v1) << 8) | ((uint32_t)clip255(v2) << 16) |
+         ((uint32_t)clip255(v3) << 24);
+#endif
+}
+
+// Clip to 0..255 in one instruction on the device (VIMNMX.RELU).
+GID_HD int clip255_fast(int x) {
+#if defined(__CUDA_ARCH__)
+  int r;
+  asm("min.relu.s32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(255));
+  return r;
+#else
+  return clip255(x);
+#endif
 }
 
 // Chroma terms of the YCbCr arm, gid-decoding_jpg.adb:1028-1035.
@@ -153,6 +171,55 @@ GID_HD ChromaTerms chroma_terms(int cb, int cr) {
   t.r = (359 * cr - 45824) >> 8;              // 359*(cr-128) + 128
   t.g = (-88 * cb - 183 * cr + 34816) >> 8;   // -88*(cb-128) - 183*(cr-128) + 128
   t.b = (454 * cb - 57984) >> 8;              // 454*(cb-128) + 128
+  return t;
+}
+
+// Byte permute and 4-way byte dot products (PRMT, IDP.4A); the host versions
+// restate the PTX semantics so that the CPU suite exercises the same formulas.
+GID_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+#if defined(__CUDA_ARCH__)
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+#else
+  const uint64_t src = ((uint64_t)b << 32) | a;
+  uint32_t d = 0;
+  for (int i = 0; i < 4; i++) d |= (uint32_t)((src >> (8 * ((sel >> (4 * i)) & 7))) & 0xFF) << (8 * i);
+  return d;
+#endif
+}
+GID_HD int dp4a_uu(uint32_t a, uint32_t b, int c) {  // unsigned bytes x unsigned bytes
+#if defined(__CUDA_ARCH__)
+  int d;
+  asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+#else
+  unsigned acc = (unsigned)c;
+  for (int i = 0; i < 4; i++) acc += ((a >> (8 * i)) & 0xFF) * ((b >> (8 * i)) & 0xFF);
+  return (int)acc;
+#endif
+}
+GID_HD int dp4a_us(uint32_t a, uint32_t b, int c) {  // unsigned bytes x signed bytes
+#if defined(__CUDA_ARCH__)
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+#else
+  int acc = c;
+  for (int i = 0; i < 4; i++) acc += (int)((a >> (8 * i)) & 0xFF) * (int)(int8_t)((b >> (8 * i)) & 0xFF);
+  return acc;
+#endif
+}
+
+// The same terms from packed sample words: sample K (0..3) of cbw / crw.
+//   v = [cb, cr, cb, cr];  359 = 255 + 104,  454 = 255 + 199,  -183 = -128 - 55
+template <int K>
+GID_HD ChromaTerms chroma_terms_packed(uint32_t cbw, uint32_t crw) {
+  const uint32_t v = prmt(cbw, crw, (uint32_t)(((4 + K) << 12) | (K << 8) | ((4 + K) << 4) | K));
+  ChromaTerms t;
+  t.r = dp4a_uu(v, 0x6800FF00u, -45824) >> 8;   // (0, 255, 0, 104)
+  t.g = dp4a_us(v, 0xC90080A8u, 34816) >> 8;    // (-88, -128, 0, -55)
+  t.b = dp4a_uu(v, 0x00C700FFu, -57984) >> 8;   // (255, 0, 199, 0)
   return t;
 }
 

@@ -84,6 +84,10 @@ int gidcuda_device_count(void);
 /* Message of the last error raised on this thread (ctx may be NULL). */
 const char *gidcuda_last_error(const gidcuda_ctx *ctx);
 
+/* Library options (process-wide; set before creating jobs / plans):
+ *   "tma"  1 (default) = stage coefficients through TMA, 0 = plain 128-bit loads. */
+int gidcuda_set_option(const char *name, int value);
+
 /* One context per host thread / Ada task.  Owns a device, streams and a pool
  * of pinned host + device buffers that jobs recycle. */
 int gidcuda_create(int device, gidcuda_ctx **ctx);
@@ -130,6 +134,9 @@ int gidcuda_plan_create(gidcuda_ctx *ctx, int32_t n, const gidcuda_frame_desc *d
 int gidcuda_plan_launch(gidcuda_plan *plan, void *cuda_stream);
 /* Number of kernel launches one gidcuda_plan_launch performs. */
 int gidcuda_plan_launch_count(const gidcuda_plan *plan);
+/* Number of those launches that stage coefficients through TMA (0 when the
+ * planes' alignment forced the plain-load kernel). */
+int gidcuda_plan_uses_tma(const gidcuda_plan *plan);
 int gidcuda_plan_destroy(gidcuda_plan *plan);
 /* Wait for everything queued on the context stream. */
 int gidcuda_synchronize(gidcuda_ctx *ctx);

@@ -32,9 +32,11 @@ extern "C" int emu_reconstruct(const gidcuda_frame_desc *desc, const int16_t *co
       for (int by = 0; by < f.by[c]; by++)
         for (int bx = 0; bx < f.bx[c]; bx++) {
           int b[64];
-          const size_t idx = (size_t)by * f.bx[c] + bx;
-          if (f.q8) load_idct_block<true>(f.plane[c] + idx * 64, &f.qw[c][0], b);
-          else load_idct_block<false>(f.plane[c] + idx * 64, &f.qw[c][0], b);
+          LdgSource src{&f};
+          u32x4 raw[8];
+          src.load(c, bx, by, raw);
+          if (f.q8) dequant_idct<true>(raw, &f.qw[c][0], b);
+          else dequant_idct<false>(raw, &f.qw[c][0], b);
           uint32_t p[16];
           pack_block(b, p);
           const size_t pitch = (size_t)f.bx[c] * 8;
@@ -63,16 +65,19 @@ extern "C" int emu_reconstruct(const gidcuda_frame_desc *desc, const int16_t *co
       }
     return 0;
   }
+  LdgSource src{&f};
+  u32x2 s_cb[8], s_cr[8], s_y[8];
+  Scratch sc{s_cb, s_cr, s_y, 1};
   for (uint32_t tile = 0; tile < g.ntiles; tile++)
     for (int t = 0; t < kTileMcusSetup; t++) {
       const uint32_t m = (tile - f.tile_base) * kTileMcusSetup + t;
       if (m >= (uint32_t)(f.mcux * f.mcuy)) continue;
       const int my = (int)(m / (uint32_t)f.mcux), mx = (int)(m - (uint32_t)my * f.mcux);
       switch (g.layout) {
-        case LAYOUT_GREY: f.q8 ? mcu_grey<true>(f, qw, mx, my) : mcu_grey<false>(f, qw, mx, my); break;
-        case LAYOUT_444: f.q8 ? mcu_ycc<1, 1, true>(f, qw, mx, my) : mcu_ycc<1, 1, false>(f, qw, mx, my); break;
-        case LAYOUT_422: f.q8 ? mcu_ycc<2, 1, true>(f, qw, mx, my) : mcu_ycc<2, 1, false>(f, qw, mx, my); break;
-        default: f.q8 ? mcu_ycc<2, 2, true>(f, qw, mx, my) : mcu_ycc<2, 2, false>(f, qw, mx, my); break;
+        case LAYOUT_GREY: f.q8 ? mcu_run<1, 1, true, true>(f, qw, src, sc, mx, my) : mcu_run<1, 1, true, false>(f, qw, src, sc, mx, my); break;
+        case LAYOUT_444: f.q8 ? mcu_run<1, 1, false, true>(f, qw, src, sc, mx, my) : mcu_run<1, 1, false, false>(f, qw, src, sc, mx, my); break;
+        case LAYOUT_422: f.q8 ? mcu_run<2, 1, false, true>(f, qw, src, sc, mx, my) : mcu_run<2, 1, false, false>(f, qw, src, sc, mx, my); break;
+        default: f.q8 ? mcu_run<2, 2, false, true>(f, qw, src, sc, mx, my) : mcu_run<2, 2, false, false>(f, qw, src, sc, mx, my); break;
       }
     }
   return 0;

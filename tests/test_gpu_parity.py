@@ -27,8 +27,17 @@ def _check(gpu, oracle, fr, flags=0, out_stride=0):
                              f"gpu {got[tuple(bad[0])]} oracle {ref[tuple(bad[0])]}")
 
 
+@pytest.fixture(params=["tma", "ldg"])
+def path(request):
+    """Both coefficient paths: TMA-staged ring (default) and plain 128-bit loads."""
+    from gid_b200 import capi
+    capi.set_option("tma", 1 if request.param == "tma" else 0)
+    yield request.param
+    capi.set_option("tma", 1)
+
+
 @pytest.mark.parametrize("w,h,samp", GEOMETRIES)
-def test_geometries_match_oracle(gpu, oracle, synth, w, h, samp):
+def test_geometries_match_oracle(gpu, oracle, synth, path, w, h, samp):
     fr = synth.planes_only(pixels_for(synth, 11, w, h, samp), samp)
     _check(gpu, oracle, fr)
 
@@ -48,7 +57,7 @@ def test_configs_through_jpeg_files(gpu, oracle, synth, cfg):
 
 @pytest.mark.parametrize("kind", ["dense", "sparse", "dc_only", "rows", "extreme"])
 @pytest.mark.parametrize("samp", ["grey", "444", "422", "420", "440"])
-def test_random_coefficients(gpu, oracle, synth, kind, samp):
+def test_random_coefficients(gpu, oracle, synth, path, kind, samp):
     from tests.harness import Frame, SAMPLING
     import zlib
     rng = np.random.default_rng(zlib.crc32(f"{kind}-{samp}".encode()))
@@ -132,6 +141,7 @@ def test_plan_device_resident_batch(gpu, oracle, synth):
     torch.cuda.synchronize()
     plan = gpu.plan_create(descs, d_planes, d_pixels)
     assert gpu.plan_launch_count(plan) == 4 + 2  # grey, 444, 422, 420 fused + generic (2 passes)
+    assert gpu.plan_uses_tma(plan) == 4          # torch allocations are 512-byte aligned
     gpu.plan_launch(plan, torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     k = 0
@@ -179,3 +189,55 @@ def test_batch_driver(oracle, synth, gidcuda_lib):
         assert status[i] == 0
         got = o.reshape(fr.height, stride)[:, :3 * fr.width].reshape(fr.height, fr.width, 3)
         assert np.array_equal(got, oracle.reconstruct(fr)), i
+
+
+FULL_SIZE = [
+    ("cfg1", 512, 512, "420", False, 0),
+    ("cfg2", 4096, 4096, "444", False, 0),
+    ("cfg3", 1920, 1080, "420", False, 0),
+    ("cfg4", 8192, 8192, "grey", False, 64),
+    ("cfg5", 2048, 2048, "422", True, 0),
+]
+
+
+@pytest.mark.parametrize("name,w,h,samp,prog,ri", FULL_SIZE, ids=[c[0] for c in FULL_SIZE])
+def test_baseline_configs_full_size(gpu, oracle, synth, name, w, h, samp, prog, ri):
+    """The five BASELINE.json configs at their full frame size: synthetic .jpg ->
+    GID front end (oracle) -> planes -> GPU, against the oracle's own decode."""
+    jpg, enc = synth.encode(pixels_for(synth, 77, w, h, samp), samp, progressive=prog, restart_interval=ri)
+    fr, rgb, fb = oracle.decode(jpg)
+    for c in range(fr.ncomp):
+        assert np.array_equal(fr.planes[c], enc.planes[c])
+    got = gpu.reconstruct_rgb(frame_desc(fr), fr.planes)
+    assert np.array_equal(got, rgb)
+    assert fb == sorted(fb) and fb[-1] == 100
+
+
+def test_batch_properties_full_size(oracle, synth, gidcuda_lib):
+    """Batch configs (3 and 5) at scale through the batch driver: the batch is built
+    from a small pool of distinct frames in a shuffled order, so every output must
+    equal the (oracle-checked) output of its pool member -- a size-independent
+    check of sharding and indexing."""
+    from gid_b200 import capi
+    n_dev = gidcuda_lib.gidcuda_device_count()
+    for (w, h, samp, count) in ((1920, 1080, "420", 96), (2048, 2048, "422", 24)):
+        pool = [synth.planes_only(pixels_for(synth, 300 + i, w, h, samp), samp) for i in range(3)]
+        refs = [oracle.reconstruct(fr) for fr in pool]
+        rng = np.random.default_rng(5)
+        order = rng.integers(0, len(pool), size=count)
+        ctx = capi.GidCuda(0)
+        descs = [frame_desc(pool[k]) for k in order]
+        stride, nbytes = ctx.output_geometry(descs[0])
+        ctx.close()
+        outs = [np.zeros(nbytes, dtype=np.uint8) for _ in order]
+        planes = []
+        for k in order:
+            planes += [pool[k].planes[c].ctypes.data for c in range(3)]
+        batch = capi.Batch(list(range(n_dev)), chunk_images=8)
+        status, stats = batch.run(descs, planes, [o.ctypes.data for o in outs])
+        batch.close()
+        assert all(s == 0 for s in status) and stats.images_failed == 0
+        assert sum(stats.images_per_device[:n_dev]) == count
+        for k, o in zip(order, outs):
+            got = o.reshape(h, stride)[:, :3 * w].reshape(h, w, 3)
+            assert np.array_equal(got, refs[k])
