@@ -143,43 +143,34 @@ GID_HD uint8_t *row_ptr(const FrameDev &f, int x0, int y) {
 
 // Slow path: byte stores with clipping to the image (:1023, :1026); used for
 // partial blocks at the right edge and for frames whose rows are not 8-byte
-// aligned.  c0/c1/c2 = the three output channels in memory order.
+// aligned.  w[0..5] = the 24 output bytes of the row, already packed.
 #if defined(__CUDACC__)
 static __host__ __device__ __noinline__
 #else
 inline
 #endif
-void store_row8_bytes(const FrameDev &f, int x0, int y, const int *c0, const int *c1, const int *c2) {
+void store_row8_bytes(const FrameDev &f, int x0, int y, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3,
+                      uint32_t w4, uint32_t w5) {
   uint8_t *dst = row_ptr(f, x0, y);
-  for (int i = 0; i < 8; i++) {
-    if (x0 + i < f.width) {
-      dst[3 * i + 0] = (uint8_t)clip255(c0[i]);
-      dst[3 * i + 1] = (uint8_t)clip255(c1[i]);
-      dst[3 * i + 2] = (uint8_t)clip255(c2[i]);
-    }
-  }
+  const uint32_t w[6] = {w0, w1, w2, w3, w4, w5};
+  int n = (f.width - x0) * 3;
+  if (n > 24) n = 24;
+  for (int i = 0; i < n; i++) dst[i] = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
 }
 
-// One row of 8 pixels of the block whose left edge is pixel column x0.
-// c0/c1/c2 un-clipped, in memory order.  `fast` = whole block inside the image
-// and FRAME_ALIGNED8: 24 bytes leave as three 8-byte stores.
-GID_HD void store_row8(const FrameDev &f, bool fast, int x0, int y, const int (&c0)[8], const int (&c1)[8],
-                       const int (&c2)[8]) {
-  if (y >= f.height) return;
+// One row of 8 pixels (24 packed bytes in w0..w5) of the block whose left edge
+// is pixel column x0.  `fast` = whole block inside the image and
+// FRAME_ALIGNED8: the row leaves as three 8-byte stores.
+GID_HD void store_row8(const FrameDev &f, bool fast, int x0, int y, uint32_t w0, uint32_t w1, uint32_t w2,
+                       uint32_t w3, uint32_t w4, uint32_t w5) {
   if (fast) {
     u32x2 *d2 = reinterpret_cast<u32x2 *>(row_ptr(f, x0, y));
     u32x2 v;
-    v.x = pack_sat4(c0[0], c1[0], c2[0], c0[1]);
-    v.y = pack_sat4(c1[1], c2[1], c0[2], c1[2]);
-    d2[0] = v;
-    v.x = pack_sat4(c2[2], c0[3], c1[3], c2[3]);
-    v.y = pack_sat4(c0[4], c1[4], c2[4], c0[5]);
-    d2[1] = v;
-    v.x = pack_sat4(c1[5], c2[5], c0[6], c1[6]);
-    v.y = pack_sat4(c2[6], c0[7], c1[7], c2[7]);
-    d2[2] = v;
-  } else if (x0 < f.width) {
-    store_row8_bytes(f, x0, y, c0, c1, c2);
+    v.x = w0; v.y = w1; d2[0] = v;
+    v.x = w2; v.y = w3; d2[1] = v;
+    v.x = w4; v.y = w5; d2[2] = v;
+  } else {
+    store_row8_bytes(f, x0, y, w0, w1, w2, w3, w4, w5);
   }
 }
 
@@ -205,25 +196,41 @@ struct Scratch {
 // upsampling by replication, colour transformation, output).
 //   H, V   luma sampling (1 or 2); GREY = no chroma
 //   sx, sy position of the block inside the MCU
+// The loop is rolled (one copy of the row code); the scratch words of the next
+// iteration are loaded before the current one is computed, to hide the
+// shared-memory latency.
 template <int H, int V, bool GREY>
 GID_HD void emit_block_rows(const FrameDev &f, const Scratch &sc, int x0, int y0, int sx, int sy) {
+  if (x0 >= f.width) return;
   const bool fast = (f.flags & FRAME_ALIGNED8) != 0 && x0 + 8 <= f.width;
   const bool bgr = f.out_format == OUT_BGR8_BOTTOM_UP;
-  if (x0 >= f.width) return;
+  const int crow0 = sy * (8 / V);  // first row inside the chroma block
+  u32x2 yw[V], cbw, crw;
+#pragma unroll
+  for (int ry = 0; ry < V; ry++) yw[ry] = sc.y[ry * sc.stride];
+  if (!GREY) { cbw = sc.cb[crow0 * sc.stride]; crw = sc.cr[crow0 * sc.stride]; }
 #pragma unroll 1
   for (int i = 0; i < 8 / V; i++) {
+    // current words -> locals, then prefetch the next iteration (clamped index)
+    u32x2 ycur[V];
+#pragma unroll
+    for (int ry = 0; ry < V; ry++) ycur[ry] = yw[ry];
+    const u32x2 cbc = cbw, crc = crw;
+    const int nx = i + 1 < 8 / V ? i + 1 : i;
+#pragma unroll
+    for (int ry = 0; ry < V; ry++) yw[ry] = sc.y[(nx * V + ry) * sc.stride];
+    if (!GREY) { cbw = sc.cb[(crow0 + nx) * sc.stride]; crw = sc.cr[(crow0 + nx) * sc.stride]; }
+
     ChromaTerms t[8 / H];
     if (!GREY) {
-      const int crow = sy * (8 / V) + i;  // row inside the chroma block
-      const u32x2 cbw = sc.cb[crow * sc.stride], crw = sc.cr[crow * sc.stride];
       if (H == 1) {
-        t[0] = chroma_terms_packed<0>(cbw.x, crw.x); t[1] = chroma_terms_packed<1>(cbw.x, crw.x);
-        t[2] = chroma_terms_packed<2>(cbw.x, crw.x); t[3] = chroma_terms_packed<3>(cbw.x, crw.x);
-        t[4 / H] = chroma_terms_packed<0>(cbw.y, crw.y); t[5 / H] = chroma_terms_packed<1>(cbw.y, crw.y);
-        t[6 / H] = chroma_terms_packed<2>(cbw.y, crw.y); t[7 / H] = chroma_terms_packed<3>(cbw.y, crw.y);
+        t[0] = chroma_terms_packed<0>(cbc.x, crc.x); t[1] = chroma_terms_packed<1>(cbc.x, crc.x);
+        t[2] = chroma_terms_packed<2>(cbc.x, crc.x); t[3] = chroma_terms_packed<3>(cbc.x, crc.x);
+        t[4 / H] = chroma_terms_packed<0>(cbc.y, crc.y); t[5 / H] = chroma_terms_packed<1>(cbc.y, crc.y);
+        t[6 / H] = chroma_terms_packed<2>(cbc.y, crc.y); t[7 / H] = chroma_terms_packed<3>(cbc.y, crc.y);
       } else {
         // block sx covers chroma columns 4*sx .. 4*sx+3, i.e. word sx of the row
-        const uint32_t wb = sx ? cbw.y : cbw.x, wr = sx ? crw.y : crw.x;
+        const uint32_t wb = sx ? cbc.y : cbc.x, wr = sx ? crc.y : crc.x;
         t[0] = chroma_terms_packed<0>(wb, wr); t[1] = chroma_terms_packed<1>(wb, wr);
         t[2] = chroma_terms_packed<2>(wb, wr); t[3] = chroma_terms_packed<3>(wb, wr);
       }
@@ -234,41 +241,26 @@ GID_HD void emit_block_rows(const FrameDev &f, const Scratch &sc, int x0, int y0
     }
 #pragma unroll
     for (int ry = 0; ry < V; ry++) {
-      const int row = i * V + ry;  // row inside the luma block
-      const int y = y0 + row;
+      const int y = y0 + i * V + ry;
       if (y >= f.height) continue;
-      const u32x2 yw = sc.y[row * sc.stride];
+      const u32x2 yv = ycur[ry];
       if (GREY) {
         // R = G = B = Y (:1036-1038)
-        if (fast) {
-          u32x2 *d2 = reinterpret_cast<u32x2 *>(row_ptr(f, x0, y));
-          u32x2 v;
-          v.x = prmt(yw.x, 0u, 0x1000u);  // Y0 Y0 Y0 Y1
-          v.y = prmt(yw.x, 0u, 0x2211u);  // Y1 Y1 Y2 Y2
-          d2[0] = v;
-          v.x = prmt(yw.x, 0u, 0x3332u);  // Y2 Y3 Y3 Y3
-          v.y = prmt(yw.y, 0u, 0x1000u);
-          d2[1] = v;
-          v.x = prmt(yw.y, 0u, 0x2211u);
-          v.y = prmt(yw.y, 0u, 0x3332u);
-          d2[2] = v;
-        } else {
-          int v[8];
-#pragma unroll
-          for (int c = 0; c < 8; c++) v[c] = (int)(((c < 4 ? yw.x : yw.y) >> (8 * (c & 3))) & 0xFFu);
-          store_row8_bytes(f, x0, y, v, v, v);
-        }
+        store_row8(f, fast, x0, y, prmt(yv.x, 0u, 0x1000u), prmt(yv.x, 0u, 0x2211u), prmt(yv.x, 0u, 0x3332u),
+                   prmt(yv.y, 0u, 0x1000u), prmt(yv.y, 0u, 0x2211u), prmt(yv.y, 0u, 0x3332u));
       } else {
         int c0[8], c1[8], c2[8];
 #pragma unroll
         for (int c = 0; c < 8; c++) {
-          const int yv = (int)(((c < 4 ? yw.x : yw.y) >> (8 * (c & 3))) & 0xFFu);
+          const int ys = (int)(((c < 4 ? yv.x : yv.y) >> (8 * (c & 3))) & 0xFFu);
           const ChromaTerms &tt = t[c / H];
-          c0[c] = yv + tt.r;
-          c1[c] = yv + tt.g;
-          c2[c] = yv + tt.b;
+          c0[c] = ys + tt.r;
+          c1[c] = ys + tt.g;
+          c2[c] = ys + tt.b;
         }
-        store_row8(f, fast, x0, y, c0, c1, c2);
+        store_row8(f, fast, x0, y, pack_sat4(c0[0], c1[0], c2[0], c0[1]), pack_sat4(c1[1], c2[1], c0[2], c1[2]),
+                   pack_sat4(c2[2], c0[3], c1[3], c2[3]), pack_sat4(c0[4], c1[4], c2[4], c0[5]),
+                   pack_sat4(c1[5], c2[5], c0[6], c1[6]), pack_sat4(c2[6], c0[7], c1[7], c2[7]));
       }
     }
   }

@@ -7,12 +7,13 @@
 // the same image rows.
 //
 // recon_tma_kernel (main path): persistent CTAs (3 per SM), each walking a
-//   contiguous chunk of the tile list.  Coefficients reach the threads through
-//   a 4-slot ring of 16 KiB shared-memory slots filled by TMA
-//   (cp.async.bulk.tensor with a 128-byte swizzle, so that thread t reading row
-//   t of a slot in 16-byte pieces is bank-conflict free); full/empty mbarriers
-//   per slot; a slot is released as soon as the four warps have pulled their
-//   blocks into registers, so the ring stays 3 items ahead of the arithmetic.
+//   contiguous chunk of the tile list.  Four consumer warps (128 MCUs) plus one
+//   producer warp.  Coefficients reach the consumers through a 3-slot ring of
+//   16 KiB shared-memory slots filled by TMA (cp.async.bulk.tensor with a
+//   128-byte swizzle, so that thread t reading row t of a slot in 16-byte
+//   pieces is bank-conflict free); full/empty mbarriers per slot; a slot is
+//   released as soon as the four warps have pulled their blocks into registers,
+//   so the producer keeps the ring full while the arithmetic runs.
 //   The kernel is bound by integer issue (see recon_math.cuh), not by HBM, for
 //   4:4:4; the ring keeps the issue slots busy while HBM streams.
 // recon_ldg_kernel (fallback): same body, 128-bit global loads; used when the
@@ -27,9 +28,10 @@ namespace {
 constexpr int kFrameWords = (int)(sizeof(FrameDev) / sizeof(uint32_t));
 static_assert(sizeof(FrameDev) % sizeof(uint32_t) == 0, "FrameDev must be word sized");
 
-constexpr int kNumSlots = 2;
+constexpr int kNumSlots = 3;
 constexpr int kSlotBytes = kTileMcus * 128;  // one block (64 x int16) per thread
 constexpr int kCtasPerSm = 3;
+constexpr int kTmaThreads = kTileMcus + 32;  // consumers + the producer warp
 
 template <int LAYOUT> struct LayoutInfo;
 template <> struct LayoutInfo<LAYOUT_GREY> { static constexpr int H = 1, V = 1, NI = 1; static constexpr bool linear = true; };
@@ -85,57 +87,65 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 // ---- block source: the TMA ring -------------------------------------------------
 
 // Items flow through the ring in a fixed order: for every tile of the CTA's
-// chunk, items 0 .. NI-1.  Consumer item k lives in slot k % 4 and completes
-// phase (k / 4) & 1 of full[slot].  After pulling item k into registers every
-// warp arrives on empty[slot]; thread 0 then issues item k + 3 (into the slot
-// item k - 1 used, whose empty barrier has normally completed long ago).
+// chunk, items 0 .. NI-1.  Item k lives in slot k % 3; the n-th use of a slot
+// completes phase n & 1 of its full barrier (producer: arrive.expect_tx + TMA
+// complete_tx) and, once the four consumer warps have pulled their blocks into
+// registers, of its empty barrier.
+struct RingCursor {
+  uint32_t slot = 0, phase = 0;
+  __device__ __forceinline__ void advance() {
+    if (++slot == (uint32_t)kNumSlots) { slot = 0; phase ^= 1u; }
+  }
+};
+
 template <int LAYOUT>
 struct TmaSource {
-  using LI = LayoutInfo<LAYOUT>;
   uint32_t slots, full, empty;  // shared-window addresses
   uint32_t lane_off;            // t * 128 + ((t & 7) << 4): row t, chunk index pre-xored
-  uint32_t k;                   // consumer item counter
-  // producer cursor (meaningful in thread 0 only)
-  const TileDesc *tiles;
-  const CUtensorMap *map2, *map3;
-  uint32_t p_tile, p_end, p_item, kp;
-
-  __device__ __forceinline__ void produce_one() {
-    if (p_tile >= p_end) return;
-    const uint32_t s = kp & (kNumSlots - 1);
-    if (kp >= (uint32_t)kNumSlots) mbar_wait(empty + 8 * s, ((kp / kNumSlots) - 1) & 1);
-    const uint32_t coord = __ldg(&tiles[p_tile].coord[p_item]);
-    const uint32_t bar = full + 8 * s;
-    mbar_arrive_expect_tx(bar, kSlotBytes);
-    const uint32_t dst = slots + s * kSlotBytes;
-    if (LI::H == 2 && p_item >= 2) tma_load_3d(dst, map3, 0, (int)((p_item - 2) & 1), (int)coord, bar);
-    else tma_load_2d(dst, map2, 0, (int)coord, bar);
-    kp++;
-    if (++p_item == (uint32_t)LI::NI) { p_item = 0; p_tile++; }
-  }
+  RingCursor cur;
 
   // consume the next item: this thread's block (row t of the slot) -> raw[8]
   __device__ __forceinline__ void load(int, int, int, u32x4 (&raw)[8]) {
-    const uint32_t s = k & (kNumSlots - 1);
-    mbar_wait(full + 8 * s, (k / kNumSlots) & 1);
-    const uint32_t base = slots + s * kSlotBytes + lane_off;
+    mbar_wait(full + 8 * cur.slot, cur.phase);
+    const uint32_t base = slots + cur.slot * kSlotBytes + lane_off;
 #pragma unroll
     for (int j = 0; j < 8; j++) raw[j] = lds128(base ^ (uint32_t)(j << 4));
-    release(s);
+    release();
   }
   // threads without an MCU in this tile still take part in the protocol
   __device__ __forceinline__ void skip() {
-    const uint32_t s = k & (kNumSlots - 1);
-    mbar_wait(full + 8 * s, (k / kNumSlots) & 1);
-    release(s);
+    mbar_wait(full + 8 * cur.slot, cur.phase);
+    release();
   }
-  __device__ __forceinline__ void release(uint32_t s) {
+  __device__ __forceinline__ void release() {
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) mbar_arrive(empty + 8 * s);
-    if (threadIdx.x == 0) produce_one();
-    k++;
+    if ((threadIdx.x & 31) == 0) mbar_arrive(empty + 8 * cur.slot);
+    cur.advance();
   }
 };
+
+// The producer: one thread streams every item of the CTA's tile chunk.
+template <int LAYOUT>
+__device__ __forceinline__ void produce_all(uint32_t slots, uint32_t full, uint32_t empty, const TileDesc *tiles,
+                                            const CUtensorMap *map2, const CUtensorMap *map3, uint32_t t_begin,
+                                            uint32_t t_end) {
+  using LI = LayoutInfo<LAYOUT>;
+  RingCursor cur;
+  uint32_t k = 0;
+  for (uint32_t tile = t_begin; tile < t_end; tile++) {
+#pragma unroll
+    for (int item = 0; item < LI::NI; item++, k++) {
+      const uint32_t coord = __ldg(&tiles[tile].coord[item]);
+      if (k >= (uint32_t)kNumSlots) mbar_wait(empty + 8 * cur.slot, cur.phase ^ 1u);
+      const uint32_t bar = full + 8 * cur.slot;
+      mbar_arrive_expect_tx(bar, kSlotBytes);
+      const uint32_t dst = slots + cur.slot * kSlotBytes;
+      if (LI::H == 2 && item >= 2) tma_load_3d(dst, map3, 0, (item - 2) & 1, (int)coord, bar);
+      else tma_load_2d(dst, map2, 0, (int)coord, bar);
+      cur.advance();
+    }
+  }
+}
 
 // scratch for the packed samples: [3 planes][8 rows][128 threads] x 8 bytes
 constexpr int kScratchBytes = 3 * 8 * kTileMcus * 8;
@@ -175,7 +185,7 @@ __device__ __forceinline__ bool tile_mcu(const FrameDev &f, uint32_t m0, uint32_
 constexpr int kDynSmem = kNumSlots * kSlotBytes + kScratchBytes + 1024;  // + slack for 1024-byte alignment
 
 template <int LAYOUT, bool Q8>
-__global__ void __launch_bounds__(kTileMcus, kCtasPerSm)
+__global__ void __launch_bounds__(kTmaThreads, kCtasPerSm)
 recon_tma_kernel(const __grid_constant__ CUtensorMap map2, const __grid_constant__ CUtensorMap map3,
                  const FrameDev *__restrict__ frames, const TileDesc *__restrict__ tiles, uint32_t ntiles) {
   using LI = LayoutInfo<LAYOUT>;
@@ -190,43 +200,39 @@ recon_tma_kernel(const __grid_constant__ CUtensorMap map2, const __grid_constant
   if (t_begin >= t_end) return;
 
   const uint32_t t = threadIdx.x;
-  TmaSource<LAYOUT> src;
-  src.slots = (smem_u32(dyn_smem) + 1023u) & ~1023u;
-  src.full = smem_u32(s_full);
-  src.empty = smem_u32(s_empty);
-  src.lane_off = t * 128u + ((t & 7u) << 4);
-  src.k = 0;
-  src.tiles = tiles;
-  src.map2 = &map2;
-  src.map3 = &map3;
-  src.p_tile = t_begin;
-  src.p_end = t_end;
-  src.p_item = 0;
-  src.kp = 0;
+  const uint32_t slots = (smem_u32(dyn_smem) + 1023u) & ~1023u;
+  const uint32_t full = smem_u32(s_full), empty = smem_u32(s_empty);
   if (t == 0) {
     for (int s = 0; s < kNumSlots; s++) {
-      mbar_init(src.full + 8 * s, 1);
-      mbar_init(src.empty + 8 * s, kTileMcus / 32);
+      mbar_init(full + 8 * s, 1);
+      mbar_init(empty + 8 * s, kTileMcus / 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
-  if (t == 0)
-    for (int i = 0; i < kNumSlots - 1; i++) src.produce_one();
 
-  const Scratch scratch =
-      make_scratch(dyn_smem + (src.slots - smem_u32(dyn_smem)) + kNumSlots * kSlotBytes, t);
+  if (t >= (uint32_t)kTileMcus) {  // producer warp
+    if (t == (uint32_t)kTileMcus) produce_all<LAYOUT>(slots, full, empty, tiles, &map2, &map3, t_begin, t_end);
+    return;
+  }
+
+  TmaSource<LAYOUT> src;
+  src.slots = slots;
+  src.full = full;
+  src.empty = empty;
+  src.lane_off = t * 128u + ((t & 7u) << 4);
+  const Scratch scratch = make_scratch(dyn_smem + (slots - smem_u32(dyn_smem)) + kNumSlots * kSlotBytes, t);
   uint32_t cur_frame = 0xFFFFFFFFu;
 #pragma unroll 1
   for (uint32_t tile = t_begin; tile < t_end; tile++) {
     const uint32_t fi = __ldg(&tiles[tile].frame);
     const uint32_t m0 = __ldg(&tiles[tile].m0);
-    if (fi != cur_frame) {  // uniform over the CTA
-      __syncthreads();
+    if (fi != cur_frame) {  // uniform over the consumer warps
+      asm volatile("bar.sync 1, %0;" ::"n"(kTileMcus) : "memory");
       const uint32_t *g = reinterpret_cast<const uint32_t *>(frames + fi);
       for (int i = t; i < kFrameWords; i += kTileMcus) s_frame_words[i] = __ldg(g + i);
-      __syncthreads();
+      asm volatile("bar.sync 1, %0;" ::"n"(kTileMcus) : "memory");
       cur_frame = fi;
     }
     const FrameDev &f = *reinterpret_cast<const FrameDev *>(s_frame_words);
@@ -343,7 +349,7 @@ cudaError_t launch_one(bool use_tma, const CUtensorMap *map2, const CUtensorMap 
   if (use_tma) {
     uint32_t grid = (uint32_t)(num_sms * kCtasPerSm);
     if (grid > ntiles) grid = ntiles;
-    recon_tma_kernel<LAYOUT, Q8><<<grid, kTileMcus, kDynSmem, stream>>>(*map2, *map3, d_frames, d_tiles, ntiles);
+    recon_tma_kernel<LAYOUT, Q8><<<grid, kTmaThreads, kDynSmem, stream>>>(*map2, *map3, d_frames, d_tiles, ntiles);
   } else {
     recon_ldg_kernel<LAYOUT, Q8><<<ntiles, kTileMcus, 0, stream>>>(d_frames, d_tiles, ntiles);
   }
