@@ -1,0 +1,107 @@
+--  Body of GID.CUDA: status checking and type conversions only.
+--  (Reviewed, not compiled: no Ada toolchain in this repository's image.)
+
+package body GID.CUDA is
+
+  use type C.int;
+
+  --  Status codes of include/gidcuda.h
+  ERR_BAD_ARGUMENT  : constant := -1;
+  ERR_UNSUPPORTED   : constant := -2;
+  ERR_NO_DEVICE     : constant := -3;
+  ERR_CUDA          : constant := -4;
+  ERR_OUT_OF_MEMORY : constant := -5;
+  ERR_STATE         : constant := -6;
+
+  procedure Check (status : C.int; ctx : Context) is
+    function Message return String is
+      p : constant C.Strings.chars_ptr := gidcuda_last_error (ctx);
+      use type C.Strings.chars_ptr;
+    begin
+      if p = C.Strings.Null_Ptr then
+        return "";
+      end if;
+      return C.Strings.Value (p);
+    end Message;
+  begin
+    case status is
+      when 0 =>
+        null;
+      when ERR_UNSUPPORTED =>
+        raise unsupported_image_subformat with "JPEG (CUDA): " & Message;
+      when ERR_BAD_ARGUMENT =>
+        raise error_in_image_data with "JPEG (CUDA): " & Message;
+      when others =>
+        --  ERR_NO_DEVICE, ERR_CUDA, ERR_OUT_OF_MEMORY, ERR_STATE:
+        --  there is deliberately no CPU fallback.
+        raise Device_Error with "JPEG (CUDA):" & C.int'Image (status) & " " & Message;
+    end case;
+  end Check;
+
+  function Device_Count return Natural is
+  begin
+    return Natural (gidcuda_device_count);
+  end Device_Count;
+
+  procedure Create (device : Natural; ctx : out Context) is
+    c_ctx : aliased Context := Null_Context;
+  begin
+    Check (gidcuda_create (C.int (device), c_ctx'Access), Null_Context);
+    ctx := c_ctx;
+  end Create;
+
+  procedure Destroy (ctx : in out Context) is
+  begin
+    if ctx /= Null_Context then
+      Check (gidcuda_destroy (ctx), ctx);
+      ctx := Null_Context;
+    end if;
+  end Destroy;
+
+  procedure Job_Begin (ctx : Context; desc : Frame_Desc; j : out Job) is
+    c_desc : aliased constant Frame_Desc := desc;
+    c_job  : aliased Job := Null_Job;
+  begin
+    Check (gidcuda_job_begin (ctx, c_desc'Access, c_job'Access), ctx);
+    j := c_job;
+  end Job_Begin;
+
+  function Plane
+    (j : Job; comp : Natural; blocks_x, blocks_y : out Natural) return System.Address
+  is
+    bx, by : aliased Interfaces.Integer_32 := 0;
+    use type System.Address;
+    a : constant System.Address :=
+      gidcuda_job_plane (j, C.int (comp), bx'Access, by'Access);
+  begin
+    if a = System.Null_Address then
+      raise Device_Error with "JPEG (CUDA): no plane for component" & comp'Image;
+    end if;
+    blocks_x := Natural (bx);
+    blocks_y := Natural (by);
+    return a;
+  end Plane;
+
+  procedure Submit (j : Job) is
+  begin
+    Check (gidcuda_job_submit (j), Null_Context);
+  end Submit;
+
+  procedure Wait (j : Job; pixels : out System.Address; stride : out Natural) is
+    p : aliased System.Address := System.Null_Address;
+    s : aliased C.size_t := 0;
+  begin
+    Check (gidcuda_job_wait (j, p'Access, s'Access), Null_Context);
+    pixels := p;
+    stride := Natural (s);
+  end Wait;
+
+  procedure Release (j : in out Job) is
+  begin
+    if j /= Null_Job then
+      Check (gidcuda_job_release (j), Null_Context);
+      j := Null_Job;
+    end if;
+  end Release;
+
+end GID.CUDA;

@@ -1,0 +1,118 @@
+--  GID.CUDA -- thin binding of GID to the B200 JPEG pixel-reconstruction
+--  library (libgidcuda.so, C ABI declared in include/gidcuda.h).
+--
+--  This package replaces, for JPEG images only, the work that
+--  GID.Decoding_JPG did inline per MCU (gid-decoding_jpg.adb):
+--     de-quantisation            :771, :785, :1820-1822
+--     Inverse_DCT_8x8_Block      :790-907
+--     Upsampling_and_Output*     :957-1124
+--     Color_Transformation_...   :1018-1054
+--  The entropy decoder keeps running on the host and stores its
+--  coefficients, NOT de-quantised, into the planes lent by Plane.
+--
+--  One Context per Ada task (GID is "task safe", doc/gid.txt:20).
+--  Every imported function returns an int status; Check turns a
+--  failure into an exception, so nothing unwinds through C frames.
+--
+--  NOTE: written for GNAT, but no Ada compiler exists in the build
+--  image of this repository: this unit has been reviewed, not compiled.
+--  The tested stand-in is the C++ host mirror (gid_b200/host).
+
+with Interfaces.C;
+with Interfaces.C.Strings;
+with System;
+
+private package GID.CUDA is
+
+  package C renames Interfaces.C;
+
+  Device_Error : exception;
+  --  GIDCUDA_ERR_DATA-like classes map to GID.error_in_image_data and
+  --  GIDCUDA_ERR_UNSUPPORTED to GID.unsupported_image_subformat (see Check).
+
+  type Context is private;
+  type Job is private;
+  Null_Context : constant Context;
+  Null_Job     : constant Job;
+
+  type Sampling_Array is array (0 .. 2) of aliased Interfaces.Integer_32;
+  pragma Convention (C, Sampling_Array);
+  type Natural_Order_Table is array (0 .. 63) of aliased Interfaces.Unsigned_16;
+  pragma Convention (C, Natural_Order_Table);
+  type Table_Array is array (0 .. 2) of aliased Natural_Order_Table;
+  pragma Convention (C, Table_Array);
+
+  Out_RGB8           : constant := 0;
+  Out_BGR8_Bottom_Up : constant := 1;
+  Flag_Packed_Rows   : constant := 16#100#;
+
+  --  = struct gidcuda_frame_desc
+  type Frame_Desc is record
+    width, height : Interfaces.Integer_32;
+    ncomp         : Interfaces.Integer_32;   --  1 = Y, 3 = Y, Cb, Cr
+    samp_h        : Sampling_Array;          --  samples_hor, :246
+    samp_v        : Sampling_Array;          --  samples_ver, :247
+    qt            : Table_Array;             --  natural order, :1771-1775
+    flags         : Interfaces.Unsigned_32;
+    out_stride    : Interfaces.Integer_32;   --  0 = library default
+  end record;
+  pragma Convention (C, Frame_Desc);
+
+  function Device_Count return Natural;
+
+  procedure Create  (device : Natural; ctx : out Context);
+  procedure Destroy (ctx : in out Context);
+
+  --  Begin a frame: pinned, zeroed coefficient planes are reserved.
+  procedure Job_Begin (ctx : Context; desc : Frame_Desc; j : out Job);
+
+  --  Address of the int16 plane of component comp (0 = Y, 1 = Cb, 2 = Cr):
+  --  block-major (block_row, block_col, 0 .. 63), natural order.
+  function Plane
+    (j : Job; comp : Natural; blocks_x, blocks_y : out Natural) return System.Address;
+
+  procedure Submit (j : Job);   --  asynchronous: H2D, kernel, D2H
+  procedure Wait   (j : Job; pixels : out System.Address; stride : out Natural);
+  procedure Release (j : in out Job);
+
+private
+
+  type Context is new System.Address;
+  type Job     is new System.Address;
+  Null_Context : constant Context := Context (System.Null_Address);
+  Null_Job     : constant Job     := Job (System.Null_Address);
+
+  --  Raw imports (names = include/gidcuda.h)
+
+  function gidcuda_device_count return C.int;
+  pragma Import (C, gidcuda_device_count, "gidcuda_device_count");
+
+  function gidcuda_last_error (ctx : Context) return C.Strings.chars_ptr;
+  pragma Import (C, gidcuda_last_error, "gidcuda_last_error");
+
+  function gidcuda_create (device : C.int; ctx : access Context) return C.int;
+  pragma Import (C, gidcuda_create, "gidcuda_create");
+
+  function gidcuda_destroy (ctx : Context) return C.int;
+  pragma Import (C, gidcuda_destroy, "gidcuda_destroy");
+
+  function gidcuda_job_begin
+    (ctx : Context; desc : access constant Frame_Desc; j : access Job) return C.int;
+  pragma Import (C, gidcuda_job_begin, "gidcuda_job_begin");
+
+  function gidcuda_job_plane
+    (j : Job; comp : C.int;
+     blocks_x, blocks_y : access Interfaces.Integer_32) return System.Address;
+  pragma Import (C, gidcuda_job_plane, "gidcuda_job_plane");
+
+  function gidcuda_job_submit (j : Job) return C.int;
+  pragma Import (C, gidcuda_job_submit, "gidcuda_job_submit");
+
+  function gidcuda_job_wait
+    (j : Job; pixels : access System.Address; stride : access C.size_t) return C.int;
+  pragma Import (C, gidcuda_job_wait, "gidcuda_job_wait");
+
+  function gidcuda_job_release (j : Job) return C.int;
+  pragma Import (C, gidcuda_job_release, "gidcuda_job_release");
+
+end GID.CUDA;

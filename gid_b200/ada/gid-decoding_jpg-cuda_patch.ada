@@ -1,0 +1,188 @@
+--  Patch to GID.Decoding_JPG.Load (gid-decoding_jpg.adb, GID 013) that routes the
+--  pixel reconstruction through GID.CUDA.  These are the NEW nested declarations and
+--  the replacement bodies; everything not shown (segment readers, bit buffer,
+--  Get_VLC, Check_Restart, the progressive scan decoder, Read_SOS) is unchanged.
+--  Line numbers refer to the unpatched file.
+--
+--  Reviewed, not compiled (no Ada toolchain in this repository's build image); the
+--  C++ host mirror gid_b200/host/gid_jpeg_host.cpp performs the identical call
+--  sequence and is what the tests exercise.
+--
+--  with GID.CUDA;  with System.Storage_Elements;   --  added to the context clause
+
+    ------------------------------------------------------------------
+    --  New state, declared next to info_A / info_B (around :550)
+    ------------------------------------------------------------------
+
+    type Coefficient_Plane is array (Natural_32 range <>) of Interfaces.Integer_16;
+    pragma Convention (C, Coefficient_Plane);
+
+    type Plane_Info is record
+      base     : System.Address := System.Null_Address;  --  pinned, owned by the library
+      blocks_x : Natural := 0;                            --  MCU-padded block grid
+      blocks_y : Natural := 0;
+    end record;
+
+    cuda_ctx   : GID.CUDA.Context := GID.CUDA.Null_Context;
+    cuda_job   : GID.CUDA.Job     := GID.CUDA.Null_Job;
+    plane      : array (Component) of Plane_Info;
+    comp_index : array (Component) of Natural := (others => 0);  --  Y -> 0, Cb -> 1, Cr -> 2
+
+    --  Called once from Read_SOS, after the MCU geometry is known (:1974) and before
+    --  the first scan is decoded.  Replaces Create_Image_Array (:1857-1883) too: the
+    --  progressive accumulators now ARE the int16 planes.
+    procedure Begin_Device_Frame is
+      desc : GID.CUDA.Frame_Desc;
+      idx  : Natural := 0;
+    begin
+      desc.width      := Interfaces.Integer_32 (image.width);
+      desc.height     := Interfaces.Integer_32 (image.height);
+      desc.flags      := GID.CUDA.Out_RGB8 + GID.CUDA.Flag_Packed_Rows;
+      desc.out_stride := 0;
+      for c in Component loop
+        if image.JPEG_stuff.compo_set (c) then
+          comp_index (c) := idx;
+          desc.samp_h (idx) := Interfaces.Integer_32 (info_A (c).ups.samples_hor);
+          desc.samp_v (idx) := Interfaces.Integer_32 (info_A (c).ups.samples_ver);
+          --  Natural-order table, as Finalize_Progressive_DCT_Decoding builds qt_zz (:1771-1775)
+          for i in 0 .. 63 loop
+            desc.qt (idx)(i) :=
+              Interfaces.Unsigned_16
+                (image.JPEG_stuff.qt_list (info_A (c).qt_assoc)(undo_zig_zag (i)));
+          end loop;
+          idx := idx + 1;
+        end if;
+      end loop;
+      desc.ncomp := Interfaces.Integer_32 (idx);
+      GID.CUDA.Create (device => 0, ctx => cuda_ctx);
+      GID.CUDA.Job_Begin (cuda_ctx, desc, cuda_job);
+      for c in Component loop
+        if image.JPEG_stuff.compo_set (c) then
+          plane (c).base :=
+            GID.CUDA.Plane (cuda_job, comp_index (c), plane (c).blocks_x, plane (c).blocks_y);
+        end if;
+      end loop;
+    end Begin_Device_Frame;
+
+    --  Address of coefficient `nat` (natural order 0 .. 63) of block (bx, by) of c.
+    function Coefficient_Address (c : Component; bx, by, nat : Natural) return System.Address is
+      use System.Storage_Elements;
+    begin
+      return plane (c).base +
+        Storage_Offset (2 * (64 * (by * plane (c).blocks_x + bx) + nat));
+    end Coefficient_Address;
+
+    ------------------------------------------------------------------
+    --  Decode_8x8_Block (:758-788): same entropy decoding, but the value is
+    --  stored UN-dequantised at zig_zag (coef); the multiplication by
+    --  qt_local (coef) (:771, :785) moves to the device.
+    ------------------------------------------------------------------
+    procedure Decode_8x8_Block (c : Component; bx, by : Natural) is
+      value, coef : Integer;
+      code : U8;
+      procedure Store (nat : Natural; v : Integer) is
+        cell : Interfaces.Integer_16;
+        for cell'Address use Coefficient_Address (c, bx, by, nat);
+        pragma Import (Ada, cell);
+      begin
+        cell := Interfaces.Integer_16 (v);  --  planes were zeroed by Job_Begin
+      end Store;
+    begin
+      Get_VLC (image.JPEG_stuff.vlc_defs (DC, info_B (c).ht_idx_DC).all, code, value);
+      info_B (c).dc_predictor := info_B (c).dc_predictor + value;
+      Store (0, info_B (c).dc_predictor);
+      coef := 0;
+      loop
+        Get_VLC (image.JPEG_stuff.vlc_defs (AC, info_B (c).ht_idx_AC).all, code, value);
+        exit when code = 0;
+        if (code and 16#0F#) = 0 and code /= 16#F0# then
+          raise error_in_image_data with "JPEG: error in VLC AC code for de-quantization";
+        end if;
+        coef := coef + Integer (Shift_Right (code, 4)) + 1;
+        if coef > 63 then
+          raise error_in_image_data with "JPEG: coefficient for de-quantization is > 63";
+        end if;
+        Store (zig_zag (coef), value);
+        exit when coef = 63;
+      end loop;
+    end Decode_8x8_Block;
+
+    ------------------------------------------------------------------
+    --  Steps 3-6 for the whole frame: replaces Inverse_DCT_8x8_Block (:1199),
+    --  Upsampling_and_Output (:1206) and, for progressive files, the body of
+    --  Finalize_Progressive_DCT_Decoding (:1789-1850).
+    ------------------------------------------------------------------
+    procedure Reconstruct_On_Device_And_Output (feedback_base, feedback_span : Natural) is
+      pixels : System.Address;
+      stride : Natural;
+    begin
+      GID.CUDA.Submit (cuda_job);
+      GID.CUDA.Wait (cuda_job, pixels, stride);
+      declare
+        type Byte_Array is array (0 .. stride * Natural (image.height) - 1) of Interfaces.Unsigned_8;
+        rgb : Byte_Array;
+        for rgb'Address use pixels;
+        pragma Import (Ada, rgb);
+        idx : Natural;
+      begin
+        --  Top-down rows; GID's y axis counts from the bottom (:1024).
+        for row in 0 .. Natural (image.height) - 1 loop
+          Set_X_Y (0, Natural (image.height) - 1 - row);
+          idx := row * stride;
+          for x in 0 .. Natural (image.width) - 1 loop
+            Out_Pixel_8 (rgb (idx), rgb (idx + 1), rgb (idx + 2));  --  :909-938 (8 / 16-bit ranges)
+            idx := idx + 3;
+          end loop;
+          Feedback (feedback_base + (feedback_span * (row + 1)) / Natural (image.height));
+        end loop;
+      end;
+      GID.CUDA.Release (cuda_job);
+      GID.CUDA.Destroy (cuda_ctx);
+    end Reconstruct_On_Device_And_Output;
+
+    ------------------------------------------------------------------
+    --  Baseline_DCT_Decoding_Scan (:1179-1220): the MCU loop keeps only the
+    --  entropy decoding; Feedback runs 0 .. 50 here and 50 .. 100 during output.
+    ------------------------------------------------------------------
+    procedure Baseline_DCT_Decoding_Scan is
+      mb_x, mb_y : Natural := 0;
+    begin
+      rst_count := image.JPEG_stuff.restart_interval;
+      next_rst := 0;
+      macro_blocks_loop :
+      loop
+        for c in Component loop
+          if image.JPEG_stuff.compo_set (c) then
+            for sby in 1 .. info_A (c).ups.samples_ver loop
+              for sbx in 1 .. info_A (c).ups.samples_hor loop
+                Decode_8x8_Block
+                  (c,
+                   bx => mb_x * info_A (c).ups.samples_hor + sbx - 1,
+                   by => mb_y * info_A (c).ups.samples_ver + sby - 1);
+              end loop;
+            end loop;
+          end if;
+        end loop;
+        mb_x := mb_x + 1;
+        if mb_x >= mcu_count_image_h then
+          mb_x := 0;
+          mb_y := mb_y + 1;
+          Feedback ((50 * mb_y) / mcu_count_image_v);
+          exit macro_blocks_loop when mb_y >= mcu_count_image_v;
+        end if;
+        Check_Restart (do_reset_predictors => True);
+      end loop macro_blocks_loop;
+      Reconstruct_On_Device_And_Output (feedback_base => 50, feedback_span => 50);
+    end Baseline_DCT_Decoding_Scan;
+
+    ------------------------------------------------------------------
+    --  Progressive files: every image_array (x, y, c_idx) access in
+    --  Progressive_DCT_Decoding_Scan (:1263-1690) becomes an access to the int16
+    --  plane cell  Coefficient_Address (c, x / 8, y / 8, 8 * (y mod 8) + x mod 8)
+    --  (same values: the scans accumulate un-dequantised coefficients at
+    --  pixel-positioned natural order, :580-588), and
+    ------------------------------------------------------------------
+    procedure Finalize_Progressive_DCT_Decoding is
+    begin
+      Reconstruct_On_Device_And_Output (feedback_base => 50, feedback_span => 50);
+    end Finalize_Progressive_DCT_Decoding;
