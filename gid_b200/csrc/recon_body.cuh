@@ -129,6 +129,71 @@ GID_HD void dequant_idct(const u32x4 (&raw)[8], const uint32_t *qw, int (&b)[64]
   idct_8x8(b);
 }
 
+// "Does any lane of the warp see p?"  `lanes` = the lanes that take part (all
+// lanes that own an MCU in this tile).  The host build runs one thread at a
+// time, so there the answer is p itself and every block picks its own variant.
+GID_HD bool warp_any(uint32_t lanes, bool p) {
+#if defined(__CUDA_ARCH__)
+  return __any_sync(lanes, p) != 0;
+#else
+  (void)lanes;
+  return p;
+#endif
+}
+
+// De-quantise one row (8 coefficients in 4 words) with table words q[0..3].
+template <bool Q8>
+GID_HD void dequant_row(const u32x4 &w, const uint32_t *q, int &c0, int &c1, int &c2, int &c3, int &c4, int &c5,
+                        int &c6, int &c7) {
+  dequant_pair<Q8>(w.x, q[0], c0, c1);
+  dequant_pair<Q8>(w.y, q[1], c2, c3);
+  dequant_pair<Q8>(w.z, q[2], c4, c5);
+  dequant_pair<Q8>(w.w, q[3], c6, c7);
+}
+
+// De-quantise + inverse DCT with the work that real streams do not need left
+// out.  All decisions are WARP-UNIFORM (a vote over the 32 blocks the warp holds)
+// so that no lane idles in a branch it does not need, and all of them are exact:
+//   * a row with no AC term in any lane: every output is 8 * dc (GID's own
+//     shortcut, :810-812) -- one multiply instead of the 65-instruction row pass;
+//   * rows 3 .. 7 zero in every lane (chroma at ordinary qualities, flat luma):
+//     those rows are not touched and the column pass runs its 3-input form
+//     (col_idct_lo3), otherwise the general column pass.
+// Dense data takes the general path everywhere; the result is the same either way.
+template <bool Q8>
+GID_HD void dequant_idct_sparse(uint32_t lanes, const u32x4 (&raw)[8], const uint32_t *qw, int (&b)[64]) {
+  uint32_t ac[8];
+#pragma unroll
+  for (int r = 0; r < 8; r++) ac[r] = (raw[r].x & 0xFFFF0000u) | raw[r].y | raw[r].z | raw[r].w;
+  const uint32_t low = (raw[3].x | raw[4].x) | (raw[5].x | raw[6].x) | raw[7].x;
+  const uint32_t tail = (ac[3] | ac[4]) | (ac[5] | ac[6]) | (ac[7] | low);
+  const bool tall = warp_any(lanes, tail != 0);
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    if (r >= 3 && !tall) break;
+    int *row = &b[8 * r];
+    if (warp_any(lanes, ac[r] != 0)) {
+      dequant_row<Q8>(raw[r], qw + 4 * r, row[0], row[1], row[2], row[3], row[4], row[5], row[6], row[7]);
+      row_idct_rnd(ac[r] != 0 ? 128 : 0, row[0], row[1], row[2], row[3], row[4], row[5], row[6], row[7]);
+    } else {
+      int dc, unused;
+      dequant_pair<Q8>(raw[r].x, qw[4 * r], dc, unused);
+      dc = wmul(dc, 8);
+#pragma unroll
+      for (int c = 0; c < 8; c++) row[c] = dc;
+    }
+  }
+  if (tall) {
+#pragma unroll
+    for (int c = 0; c < 8; c++)
+      col_idct(b[c], b[8 + c], b[16 + c], b[24 + c], b[32 + c], b[40 + c], b[48 + c], b[56 + c]);
+  } else {
+#pragma unroll
+    for (int c = 0; c < 8; c++)
+      col_idct_lo3(b[c], b[8 + c], b[16 + c], b[24 + c], b[32 + c], b[40 + c], b[48 + c], b[56 + c]);
+  }
+}
+
 // Clip + pack the 64 samples of a block into 16 words (row r -> words 2r, 2r+1).
 GID_HD void pack_block(const int (&b)[64], uint32_t (&p)[16]) {
 #pragma unroll
@@ -203,7 +268,7 @@ template <int H, int V, bool GREY>
 GID_HD void emit_block_rows(const FrameDev &f, const Scratch &sc, int x0, int y0, int sx, int sy) {
   if (x0 >= f.width) return;
   const bool fast = (f.flags & FRAME_ALIGNED8) != 0 && x0 + 8 <= f.width;
-  const bool bgr = f.out_format == OUT_BGR8_BOTTOM_UP;
+  const ColourOrder co = colour_order(f.out_format == OUT_BGR8_BOTTOM_UP);
   const int crow0 = sy * (8 / V);  // first row inside the chroma block
   u32x2 yw[V], cbw, crw;
 #pragma unroll
@@ -224,19 +289,15 @@ GID_HD void emit_block_rows(const FrameDev &f, const Scratch &sc, int x0, int y0
     ChromaTerms t[8 / H];
     if (!GREY) {
       if (H == 1) {
-        t[0] = chroma_terms_packed<0>(cbc.x, crc.x); t[1] = chroma_terms_packed<1>(cbc.x, crc.x);
-        t[2] = chroma_terms_packed<2>(cbc.x, crc.x); t[3] = chroma_terms_packed<3>(cbc.x, crc.x);
-        t[4 / H] = chroma_terms_packed<0>(cbc.y, crc.y); t[5 / H] = chroma_terms_packed<1>(cbc.y, crc.y);
-        t[6 / H] = chroma_terms_packed<2>(cbc.y, crc.y); t[7 / H] = chroma_terms_packed<3>(cbc.y, crc.y);
+        t[0] = chroma_terms_packed<0>(co, cbc.x, crc.x); t[1] = chroma_terms_packed<1>(co, cbc.x, crc.x);
+        t[2] = chroma_terms_packed<2>(co, cbc.x, crc.x); t[3] = chroma_terms_packed<3>(co, cbc.x, crc.x);
+        t[4 / H] = chroma_terms_packed<0>(co, cbc.y, crc.y); t[5 / H] = chroma_terms_packed<1>(co, cbc.y, crc.y);
+        t[6 / H] = chroma_terms_packed<2>(co, cbc.y, crc.y); t[7 / H] = chroma_terms_packed<3>(co, cbc.y, crc.y);
       } else {
         // block sx covers chroma columns 4*sx .. 4*sx+3, i.e. word sx of the row
         const uint32_t wb = sx ? cbc.y : cbc.x, wr = sx ? crc.y : crc.x;
-        t[0] = chroma_terms_packed<0>(wb, wr); t[1] = chroma_terms_packed<1>(wb, wr);
-        t[2] = chroma_terms_packed<2>(wb, wr); t[3] = chroma_terms_packed<3>(wb, wr);
-      }
-      if (bgr) {
-#pragma unroll
-        for (int k = 0; k < 8 / H; k++) { const int s = t[k].r; t[k].r = t[k].b; t[k].b = s; }
+        t[0] = chroma_terms_packed<0>(co, wb, wr); t[1] = chroma_terms_packed<1>(co, wb, wr);
+        t[2] = chroma_terms_packed<2>(co, wb, wr); t[3] = chroma_terms_packed<3>(co, wb, wr);
       }
     }
 #pragma unroll
@@ -271,8 +332,8 @@ GID_HD void emit_block_rows(const FrameDev &f, const Scratch &sc, int x0, int y0
 // source, de-quantise, inverse DCT, clip + pack to bytes into the scratch; luma
 // blocks are then turned into pixels.
 template <int H, int V, bool GREY, bool Q8, class Src>
-GID_HD void mcu_run(const FrameDev &f, const uint32_t *qw /* [3][32] */, Src &src, const Scratch &sc, int mx,
-                    int my) {
+GID_HD void mcu_run(uint32_t lanes, const FrameDev &f, const uint32_t *qw /* [3][32] */, Src &src,
+                    const Scratch &sc, int mx, int my) {
   constexpr int NI = GREY ? 1 : 2 + H * V;
 #pragma unroll 1
   for (int it = 0; it < NI; it++) {
@@ -289,7 +350,7 @@ GID_HD void mcu_run(const FrameDev &f, const uint32_t *qw /* [3][32] */, Src &sr
     u32x4 raw[8];
     src.load(comp, bxi, byi, raw);
     int b[64];
-    dequant_idct<Q8>(raw, qw + 32 * comp, b);
+    dequant_idct_sparse<Q8>(lanes, raw, qw + 32 * comp, b);
     u32x2 *dst = comp == 0 ? sc.y : (comp == 1 ? sc.cb : sc.cr);
 #pragma unroll
     for (int r = 0; r < 8; r++) {

@@ -161,9 +161,10 @@ __device__ __forceinline__ Scratch make_scratch(uint8_t *base, uint32_t t) {
 }
 
 template <int LAYOUT, bool Q8, class Src>
-__device__ __forceinline__ void run_mcu(const FrameDev &f, Src &src, const Scratch &sc, int mx, int my) {
+__device__ __forceinline__ void run_mcu(uint32_t lanes, const FrameDev &f, Src &src, const Scratch &sc, int mx,
+                                        int my) {
   using LI = LayoutInfo<LAYOUT>;
-  mcu_run<LI::H, LI::V, LAYOUT == LAYOUT_GREY, Q8>(f, &f.qw[0][0], src, sc, mx, my);
+  mcu_run<LI::H, LI::V, LAYOUT == LAYOUT_GREY, Q8>(lanes, f, &f.qw[0][0], src, sc, mx, my);
 }
 
 // MCU (mx, my) of thread t in a tile starting at m0, or false when the thread
@@ -237,8 +238,10 @@ recon_tma_kernel(const __grid_constant__ CUtensorMap map2, const __grid_constant
     }
     const FrameDev &f = *reinterpret_cast<const FrameDev *>(s_frame_words);
     int mx, my;
-    if (tile_mcu<LAYOUT>(f, m0, t, mx, my)) {
-      run_mcu<LAYOUT, Q8>(f, src, scratch, mx, my);
+    const bool has_mcu = tile_mcu<LAYOUT>(f, m0, t, mx, my);
+    const uint32_t lanes = __ballot_sync(0xFFFFFFFFu, has_mcu);  // the lanes that vote in the sparse IDCT
+    if (has_mcu) {
+      run_mcu<LAYOUT, Q8>(lanes, f, src, scratch, mx, my);
     } else {
 #pragma unroll
       for (int i = 0; i < LI::NI; i++) src.skip();
@@ -262,9 +265,11 @@ recon_ldg_kernel(const FrameDev *__restrict__ frames, const TileDesc *__restrict
   __syncthreads();
   const FrameDev &f = *reinterpret_cast<const FrameDev *>(s_frame_words);
   int mx, my;
-  if (!tile_mcu<LAYOUT>(f, m0, threadIdx.x, mx, my)) return;
+  const bool has_mcu = tile_mcu<LAYOUT>(f, m0, threadIdx.x, mx, my);
+  const uint32_t lanes = __ballot_sync(0xFFFFFFFFu, has_mcu);
+  if (!has_mcu) return;
   LdgSource src{&f};
-  run_mcu<LAYOUT, Q8>(f, src, make_scratch(s_scratch, threadIdx.x), mx, my);
+  run_mcu<LAYOUT, Q8>(lanes, f, src, make_scratch(s_scratch, threadIdx.x), mx, my);
 }
 
 // ---- generic path -----------------------------------------------------------

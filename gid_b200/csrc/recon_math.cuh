@@ -120,6 +120,54 @@ GID_HD void col_idct(int &b0, int &b1, int &b2, int &b3, int &b4, int &b5, int &
   b5 = wadd(tdiv<14>(wadd3(B, wneg(e2), wneg(x4))), 128);
 }
 
+// Row_IDCT with the rounding constant supplied by the caller: `rnd` = 128 when
+// the row has a non-zero AC term, 0 when it has none (the shortcut of :810-812,
+// see row_idct above).  The caller already knows which (it classifies rows to
+// skip work warp-wide), so the 7-term OR is not repeated here.
+GID_HD void row_idct_rnd(int rnd, int &b0, int &b1, int &b2, int &b3, int &b4, int &b5, int &b6, int &b7) {
+  const int x1 = wmul(b4, 2048);
+  const int x0 = wmad(b0, 2048, rnd);
+  const int o4 = wmad(W1, b1, wmul(W7, b7)), o5 = wsub(wmul(W7, b1), wmul(W1, b7));
+  const int o6 = wmad(W5, b5, wmul(W3, b3)), o7 = wsub(wmul(W3, b5), wmul(W5, b3));
+  const int e2 = wsub(wmul(W6, b2), wmul(W2, b6)), e3 = wmad(W2, b2, wmul(W6, b6));
+  const int A = wadd(x0, x1), B = wsub(x0, x1);
+  const int p1 = wadd(o4, o6), q4 = wsub(o4, o6), p6 = wadd(o5, o7), q5 = wsub(o5, o7);
+  const int h = wmad(181, q4, 128);
+  const int x2 = tdiv<8>(wmad(181, q5, h));
+  const int x4 = tdiv<8>(wmad(-181, q5, h));
+  b0 = tdiv<8>(wadd3(A, e3, p1));
+  b7 = tdiv<8>(wadd3(A, e3, wneg(p1)));
+  b3 = tdiv<8>(wadd3(A, wneg(e3), p6));
+  b4 = tdiv<8>(wadd3(A, wneg(e3), wneg(p6)));
+  b1 = tdiv<8>(wadd3(B, e2, x2));
+  b6 = tdiv<8>(wadd3(B, e2, wneg(x2)));
+  b2 = tdiv<8>(wadd3(B, wneg(e2), x4));
+  b5 = tdiv<8>(wadd3(B, wneg(e2), wneg(x4)));
+}
+
+// Col_IDCT for a column whose inputs b3 .. b7 are zero (rows 3 .. 7 of the
+// block are zero rows after the row pass).  col_idct with those zeros folded:
+//   x1 = 0;  o6 = tdiv3(4) = 0;  o7 = tdiv3(4) = 0;  e2 = tdiv3(W6*b2 + 4);  e3 = tdiv3(W2*b2 + 4)
+//   p1 = q4 = o4 = tdiv3(W1*b1 + 4);  p6 = q5 = o5 = tdiv3(W7*b1 + 4);  A = B = x0
+// Writes all 8 outputs (un-clipped samples).
+GID_HD void col_idct_lo3(int &b0, int &b1, int &b2, int &b3, int &b4, int &b5, int &b6, int &b7) {
+  const int x0 = wmad(b0, 256, 8192);
+  const int o4 = tdiv<3>(wmad(W1, b1, 4)), o5 = tdiv<3>(wmad(W7, b1, 4));
+  const int e2 = tdiv<3>(wmad(W6, b2, 4)), e3 = tdiv<3>(wmad(W2, b2, 4));
+  const int h = wmad(181, o4, 128);
+  const int x2 = tdiv<8>(wmad(181, o5, h));
+  const int x4 = tdiv<8>(wmad(-181, o5, h));
+  const int Ap = wadd(x0, e3), Am = wsub(x0, e3), Bp = wadd(x0, e2), Bm = wsub(x0, e2);
+  b0 = wadd(tdiv<14>(wadd(Ap, o4)), 128);
+  b7 = wadd(tdiv<14>(wsub(Ap, o4)), 128);
+  b3 = wadd(tdiv<14>(wadd(Am, o5)), 128);
+  b4 = wadd(tdiv<14>(wsub(Am, o5)), 128);
+  b1 = wadd(tdiv<14>(wadd(Bp, x2)), 128);
+  b6 = wadd(tdiv<14>(wsub(Bp, x2)), 128);
+  b2 = wadd(tdiv<14>(wadd(Bm, x4)), 128);
+  b5 = wadd(tdiv<14>(wsub(Bm, x4)), 128);
+}
+
 // Inverse_DCT_8x8_Block on 64 registers (natural order, index = 8*row + col).
 // On return b[] holds the un-clipped samples.
 GID_HD void idct_8x8(int (&b)[64]) {
@@ -213,13 +261,25 @@ GID_HD int dp4a_us(uint32_t a, uint32_t b, int c) {  // unsigned bytes x signed 
 
 // The same terms from packed sample words: sample K (0..3) of cbw / crw.
 //   v = [cb, cr, cb, cr];  359 = 255 + 104,  454 = 255 + 199,  -183 = -128 - 55
+// The constants of the first and third output byte come from the caller
+// (ColourOrder), so that B, G, R output costs nothing extra: .r is the term of
+// the FIRST byte of the pixel and .b the term of the THIRD.
+struct ColourOrder { uint32_t k_first; int bias_first; uint32_t k_third; int bias_third; };
+GID_HD ColourOrder colour_order(bool bgr) {
+  ColourOrder o;
+  o.k_first = bgr ? 0x00C700FFu : 0x6800FF00u;   // (255, 0, 199, 0) : (0, 255, 0, 104)
+  o.bias_first = bgr ? -57984 : -45824;
+  o.k_third = bgr ? 0x6800FF00u : 0x00C700FFu;
+  o.bias_third = bgr ? -45824 : -57984;
+  return o;
+}
 template <int K>
-GID_HD ChromaTerms chroma_terms_packed(uint32_t cbw, uint32_t crw) {
+GID_HD ChromaTerms chroma_terms_packed(const ColourOrder &o, uint32_t cbw, uint32_t crw) {
   const uint32_t v = prmt(cbw, crw, (uint32_t)(((4 + K) << 12) | (K << 8) | ((4 + K) << 4) | K));
   ChromaTerms t;
-  t.r = dp4a_uu(v, 0x6800FF00u, -45824) >> 8;   // (0, 255, 0, 104)
+  t.r = dp4a_uu(v, o.k_first, o.bias_first) >> 8;
   t.g = dp4a_us(v, 0xC90080A8u, 34816) >> 8;    // (-88, -128, 0, -55)
-  t.b = dp4a_uu(v, 0x00C700FFu, -57984) >> 8;   // (255, 0, 199, 0)
+  t.b = dp4a_uu(v, o.k_third, o.bias_third) >> 8;
   return t;
 }
 
