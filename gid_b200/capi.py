@@ -73,7 +73,8 @@ class GidCudaError(RuntimeError):
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "lib", "libgidcuda.so")
+    """In-tree library; GIDCUDA_LIB selects another in-tree build (kernel tuning experiments)."""
+    return os.environ.get("GIDCUDA_LIB") or os.path.join(_HERE, "lib", "libgidcuda.so")
 
 
 _lib = None

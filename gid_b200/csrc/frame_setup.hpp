@@ -13,7 +13,7 @@
 
 namespace gidk {
 
-constexpr int kTileMcusSetup = 128;  // = kTileMcus of recon_launch.h
+constexpr int kTileMcusSetup = 32;  // = kTileMcus of recon_launch.h
 
 inline int geo_fail(std::string *err, int code, const char *fmt, ...) {
   if (err) {

@@ -89,7 +89,12 @@ inline int dp2a_hi_su(uint32_t a, uint32_t b, int c) {
 // and the host build).
 struct LdgSource {
   const FrameDev *f;
-  GID_HD void load(int comp, int bx, int by, u32x4 (&raw)[8]) const {
+  GID_HD void load(bool active, int comp, int bx, int by, u32x4 (&raw)[8]) const {
+    if (!active) {  // lane without an MCU: nothing to read, contributes zeros
+#pragma unroll
+      for (int r = 0; r < 8; r++) { raw[r].x = 0; raw[r].y = 0; raw[r].z = 0; raw[r].w = 0; }
+      return;
+    }
     const int16_t *p = f->plane[comp] + ((size_t)by * (size_t)f->bx[comp] + (size_t)bx) * 64;
 #pragma unroll
     for (int r = 0; r < 8; r++) {
@@ -129,14 +134,25 @@ GID_HD void dequant_idct(const u32x4 (&raw)[8], const uint32_t *qw, int (&b)[64]
   idct_8x8(b);
 }
 
-// "Does any lane of the warp see p?"  `lanes` = the lanes that take part (all
-// lanes that own an MCU in this tile).  The host build runs one thread at a
-// time, so there the answer is p itself and every block picks its own variant.
-GID_HD bool warp_any(uint32_t lanes, bool p) {
+// Clip (:755-756) + pack the 64 samples of a block to bytes and store them as 8
+// rows of 8 bytes, `stride` u32x2 apart (the per-lane scratch plane).
+GID_HD void store_block_packed(const int (&b)[64], u32x2 *dst, int stride) {
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    u32x2 v;
+    v.x = pack_sat4(b[8 * r + 0], b[8 * r + 1], b[8 * r + 2], b[8 * r + 3]);
+    v.y = pack_sat4(b[8 * r + 4], b[8 * r + 5], b[8 * r + 6], b[8 * r + 7]);
+    dst[r * stride] = v;
+  }
+}
+
+// "Does any lane of the warp see p?"  Every lane of the warp votes; lanes that
+// own no MCU in this tile vote false.  The host build runs one thread at a time,
+// so there the answer is p itself and every block picks its own variant.
+GID_HD bool warp_any(bool p) {
 #if defined(__CUDA_ARCH__)
-  return __any_sync(lanes, p) != 0;
+  return __any_sync(0xFFFFFFFFu, p) != 0;
 #else
-  (void)lanes;
   return p;
 #endif
 }
@@ -161,18 +177,19 @@ GID_HD void dequant_row(const u32x4 &w, const uint32_t *q, int &c0, int &c1, int
 //     (col_idct_lo3), otherwise the general column pass.
 // Dense data takes the general path everywhere; the result is the same either way.
 template <bool Q8>
-GID_HD void dequant_idct_sparse(uint32_t lanes, const u32x4 (&raw)[8], const uint32_t *qw, int (&b)[64]) {
+GID_HD void dequant_idct_sparse(bool active, const u32x4 (&raw)[8], const uint32_t *qw, u32x2 *dst, int dst_stride) {
+  int b[64];
   uint32_t ac[8];
 #pragma unroll
   for (int r = 0; r < 8; r++) ac[r] = (raw[r].x & 0xFFFF0000u) | raw[r].y | raw[r].z | raw[r].w;
   const uint32_t low = (raw[3].x | raw[4].x) | (raw[5].x | raw[6].x) | raw[7].x;
   const uint32_t tail = (ac[3] | ac[4]) | (ac[5] | ac[6]) | (ac[7] | low);
-  const bool tall = warp_any(lanes, tail != 0);
+  const bool tall = warp_any(active && tail != 0);
 #pragma unroll
   for (int r = 0; r < 8; r++) {
     if (r >= 3 && !tall) break;
     int *row = &b[8 * r];
-    if (warp_any(lanes, ac[r] != 0)) {
+    if (warp_any(active && ac[r] != 0)) {
       dequant_row<Q8>(raw[r], qw + 4 * r, row[0], row[1], row[2], row[3], row[4], row[5], row[6], row[7]);
       row_idct_rnd(ac[r] != 0 ? 128 : 0, row[0], row[1], row[2], row[3], row[4], row[5], row[6], row[7]);
     } else {
@@ -183,14 +200,18 @@ GID_HD void dequant_idct_sparse(uint32_t lanes, const u32x4 (&raw)[8], const uin
       for (int c = 0; c < 8; c++) row[c] = dc;
     }
   }
+  // Clip + pack + store inside each variant: joining the two register sets first
+  // would cost a move per sample.
   if (tall) {
 #pragma unroll
     for (int c = 0; c < 8; c++)
       col_idct(b[c], b[8 + c], b[16 + c], b[24 + c], b[32 + c], b[40 + c], b[48 + c], b[56 + c]);
+    store_block_packed(b, dst, dst_stride);
   } else {
 #pragma unroll
     for (int c = 0; c < 8; c++)
       col_idct_lo3(b[c], b[8 + c], b[16 + c], b[24 + c], b[32 + c], b[40 + c], b[48 + c], b[56 + c]);
+    store_block_packed(b, dst, dst_stride);
   }
 }
 
@@ -208,44 +229,37 @@ GID_HD uint8_t *row_ptr(const FrameDev &f, int x0, int y) {
 
 // Slow path: byte stores with clipping to the image (:1023, :1026); used for
 // partial blocks at the right edge and for frames whose rows are not 8-byte
-// aligned.  w[0..5] = the 24 output bytes of the row, already packed.
+// aligned.  w[0..5] = the 24 output bytes of the row, already packed; n = how
+// many of them lie inside the image.
 #if defined(__CUDACC__)
 static __host__ __device__ __noinline__
 #else
 inline
 #endif
-void store_row8_bytes(const FrameDev &f, int x0, int y, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3,
-                      uint32_t w4, uint32_t w5) {
-  uint8_t *dst = row_ptr(f, x0, y);
+void store_row8_bytes(uint8_t *dst, int n, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4,
+                      uint32_t w5) {
   const uint32_t w[6] = {w0, w1, w2, w3, w4, w5};
-  int n = (f.width - x0) * 3;
-  if (n > 24) n = 24;
   for (int i = 0; i < n; i++) dst[i] = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
 }
 
-// One row of 8 pixels (24 packed bytes in w0..w5) of the block whose left edge
-// is pixel column x0.  `fast` = whole block inside the image and
-// FRAME_ALIGNED8: the row leaves as three 8-byte stores.
-GID_HD void store_row8(const FrameDev &f, bool fast, int x0, int y, uint32_t w0, uint32_t w1, uint32_t w2,
-                       uint32_t w3, uint32_t w4, uint32_t w5) {
+// One row of 8 pixels (24 packed bytes in w0..w5) at dst.  nbytes == 24 and an
+// 8-byte aligned dst (`fast`): the row leaves as three 8-byte stores.
+GID_HD void store_row8(uint8_t *dst, bool fast, int nbytes, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3,
+                       uint32_t w4, uint32_t w5) {
   if (fast) {
-    u32x2 *d2 = reinterpret_cast<u32x2 *>(row_ptr(f, x0, y));
+    u32x2 *d2 = reinterpret_cast<u32x2 *>(dst);
     u32x2 v;
     v.x = w0; v.y = w1; d2[0] = v;
     v.x = w2; v.y = w3; d2[1] = v;
     v.x = w4; v.y = w5; d2[2] = v;
   } else {
-    store_row8_bytes(f, x0, y, w0, w1, w2, w3, w4, w5);
+    store_row8_bytes(dst, nbytes, w0, w1, w2, w3, w4, w5);
   }
-}
-
-GID_HD bool block_is_fast(const FrameDev &f, int x0) {
-  return (f.flags & FRAME_ALIGNED8) != 0 && x0 + 8 <= f.width;
 }
 
 // Per-thread scratch for the packed 8-bit samples of the current MCU: 8 rows of
 // 8 bytes for Cb, Cr and the luma block being emitted.  On the device it lives
-// in shared memory as [row][thread] (row r of thread t at base[r * stride + t],
+// in shared memory as [row][lane] (row r of lane t at base[r * stride + t],
 // conflict-free 8-byte accesses); the host build uses plain arrays (stride 1).
 // Keeping these bytes out of registers lets the kernel LOOP over the blocks of
 // an MCU and over pixel rows, so that one copy of the IDCT (~20 KiB of code)
@@ -257,37 +271,36 @@ struct Scratch {
   int stride;
 };
 
+// byte k (0..3) of w, zero-extended: one PRMT
+template <int K>
+GID_HD int byte_of(uint32_t w) { return (int)prmt(w, 0u, 0x4440u + K); }
+
 // Emit the pixel rows of one luma block from the scratch (Step 4-6 of GID:
 // upsampling by replication, colour transformation, output).
 //   H, V   luma sampling (1 or 2); GREY = no chroma
 //   sx, sy position of the block inside the MCU
-// The loop is rolled (one copy of the row code); the scratch words of the next
-// iteration are loaded before the current one is computed, to hide the
-// shared-memory latency.
+// The destination pointer walks down the image one row per step (up for the
+// bottom-up format); rows below the image (:1023) are skipped by count.
 template <int H, int V, bool GREY>
 GID_HD void emit_block_rows(const FrameDev &f, const Scratch &sc, int x0, int y0, int sx, int sy) {
   if (x0 >= f.width) return;
-  const bool fast = (f.flags & FRAME_ALIGNED8) != 0 && x0 + 8 <= f.width;
-  const ColourOrder co = colour_order(f.out_format == OUT_BGR8_BOTTOM_UP);
-  const int crow0 = sy * (8 / V);  // first row inside the chroma block
-  u32x2 yw[V], cbw, crw;
-#pragma unroll
-  for (int ry = 0; ry < V; ry++) yw[ry] = sc.y[ry * sc.stride];
-  if (!GREY) { cbw = sc.cb[crow0 * sc.stride]; crw = sc.cr[crow0 * sc.stride]; }
-#pragma unroll 1
+  int nbytes = (f.width - x0) * 3;
+  if (nbytes > 24) nbytes = 24;
+  const bool fast = (f.flags & FRAME_ALIGNED8) != 0 && nbytes == 24;
+  const bool bottom_up = f.out_format == OUT_BGR8_BOTTOM_UP;
+  const ColourOrder co = colour_order(bottom_up);
+  uint8_t *dst = row_ptr(f, x0, y0);
+  const long long step = bottom_up ? -(long long)f.stride : (long long)f.stride;
+  const int rows_left = f.height - y0;  // >= 1
+  const int crow0 = sy * (8 / V);       // first row inside the chroma block
+#pragma unroll 2
   for (int i = 0; i < 8 / V; i++) {
-    // current words -> locals, then prefetch the next iteration (clamped index)
-    u32x2 ycur[V];
-#pragma unroll
-    for (int ry = 0; ry < V; ry++) ycur[ry] = yw[ry];
-    const u32x2 cbc = cbw, crc = crw;
-    const int nx = i + 1 < 8 / V ? i + 1 : i;
-#pragma unroll
-    for (int ry = 0; ry < V; ry++) yw[ry] = sc.y[(nx * V + ry) * sc.stride];
-    if (!GREY) { cbw = sc.cb[(crow0 + nx) * sc.stride]; crw = sc.cr[(crow0 + nx) * sc.stride]; }
-
+    if (i * V >= rows_left) break;
+    u32x2 cbc, crc;
     ChromaTerms t[8 / H];
     if (!GREY) {
+      cbc = sc.cb[(crow0 + i) * sc.stride];
+      crc = sc.cr[(crow0 + i) * sc.stride];
       if (H == 1) {
         t[0] = chroma_terms_packed<0>(co, cbc.x, crc.x); t[1] = chroma_terms_packed<1>(co, cbc.x, crc.x);
         t[2] = chroma_terms_packed<2>(co, cbc.x, crc.x); t[3] = chroma_terms_packed<3>(co, cbc.x, crc.x);
@@ -302,27 +315,28 @@ GID_HD void emit_block_rows(const FrameDev &f, const Scratch &sc, int x0, int y0
     }
 #pragma unroll
     for (int ry = 0; ry < V; ry++) {
-      const int y = y0 + i * V + ry;
-      if (y >= f.height) continue;
-      const u32x2 yv = ycur[ry];
+      if (V > 1 && i * V + ry >= rows_left) break;
+      const u32x2 yv = sc.y[(i * V + ry) * sc.stride];
       if (GREY) {
         // R = G = B = Y (:1036-1038)
-        store_row8(f, fast, x0, y, prmt(yv.x, 0u, 0x1000u), prmt(yv.x, 0u, 0x2211u), prmt(yv.x, 0u, 0x3332u),
+        store_row8(dst, fast, nbytes, prmt(yv.x, 0u, 0x1000u), prmt(yv.x, 0u, 0x2211u), prmt(yv.x, 0u, 0x3332u),
                    prmt(yv.y, 0u, 0x1000u), prmt(yv.y, 0u, 0x2211u), prmt(yv.y, 0u, 0x3332u));
       } else {
+        const int ys[8] = {byte_of<0>(yv.x), byte_of<1>(yv.x), byte_of<2>(yv.x), byte_of<3>(yv.x),
+                           byte_of<0>(yv.y), byte_of<1>(yv.y), byte_of<2>(yv.y), byte_of<3>(yv.y)};
         int c0[8], c1[8], c2[8];
 #pragma unroll
         for (int c = 0; c < 8; c++) {
-          const int ys = (int)(((c < 4 ? yv.x : yv.y) >> (8 * (c & 3))) & 0xFFu);
           const ChromaTerms &tt = t[c / H];
-          c0[c] = ys + tt.r;
-          c1[c] = ys + tt.g;
-          c2[c] = ys + tt.b;
+          c0[c] = ys[c] + tt.r;
+          c1[c] = ys[c] + tt.g;
+          c2[c] = ys[c] + tt.b;
         }
-        store_row8(f, fast, x0, y, pack_sat4(c0[0], c1[0], c2[0], c0[1]), pack_sat4(c1[1], c2[1], c0[2], c1[2]),
+        store_row8(dst, fast, nbytes, pack_sat4(c0[0], c1[0], c2[0], c0[1]), pack_sat4(c1[1], c2[1], c0[2], c1[2]),
                    pack_sat4(c2[2], c0[3], c1[3], c2[3]), pack_sat4(c0[4], c1[4], c2[4], c0[5]),
                    pack_sat4(c1[5], c2[5], c0[6], c1[6]), pack_sat4(c2[6], c0[7], c1[7], c2[7]));
       }
+      dst += step;
     }
   }
 }
@@ -332,7 +346,7 @@ GID_HD void emit_block_rows(const FrameDev &f, const Scratch &sc, int x0, int y0
 // source, de-quantise, inverse DCT, clip + pack to bytes into the scratch; luma
 // blocks are then turned into pixels.
 template <int H, int V, bool GREY, bool Q8, class Src>
-GID_HD void mcu_run(uint32_t lanes, const FrameDev &f, const uint32_t *qw /* [3][32] */, Src &src,
+GID_HD void mcu_run(bool active, const FrameDev &f, const uint32_t *qw /* [3][32] */, Src &src,
                     const Scratch &sc, int mx, int my) {
   constexpr int NI = GREY ? 1 : 2 + H * V;
 #pragma unroll 1
@@ -348,18 +362,10 @@ GID_HD void mcu_run(uint32_t lanes, const FrameDev &f, const uint32_t *qw /* [3]
     }
     const int bxi = comp == 0 ? mx * H + sx : mx, byi = comp == 0 ? my * V + sy : my;
     u32x4 raw[8];
-    src.load(comp, bxi, byi, raw);
-    int b[64];
-    dequant_idct_sparse<Q8>(lanes, raw, qw + 32 * comp, b);
+    src.load(active, comp, bxi, byi, raw);
     u32x2 *dst = comp == 0 ? sc.y : (comp == 1 ? sc.cb : sc.cr);
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-      u32x2 v;
-      v.x = pack_sat4(b[8 * r + 0], b[8 * r + 1], b[8 * r + 2], b[8 * r + 3]);
-      v.y = pack_sat4(b[8 * r + 4], b[8 * r + 5], b[8 * r + 6], b[8 * r + 7]);
-      dst[r * sc.stride] = v;
-    }
-    if (comp == 0) emit_block_rows<H, V, GREY>(f, sc, bxi * 8, byi * 8, sx, sy);
+    dequant_idct_sparse<Q8>(active, raw, qw + 32 * comp, dst, sc.stride);
+    if (comp == 0 && active) emit_block_rows<H, V, GREY>(f, sc, bxi * 8, byi * 8, sx, sy);
   }
 }
 

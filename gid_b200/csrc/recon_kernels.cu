@@ -1,21 +1,23 @@
 // recon_kernels.cu -- sm_100a kernels of the JPEG reconstruction path.
 //
-// Mapping: one thread = one MCU, 128 MCUs per tile (recon_launch.h).  A thread
-// does, entirely in registers, dequant + IDCT of its chroma blocks (kept as
-// packed bytes), then dequant + IDCT + upsample + colour of each luma block and
-// writes 24-byte pixel runs; neighbouring threads write neighbouring runs of
-// the same image rows.
+// Mapping: one thread = one MCU, one WARP = one tile of 32 consecutive MCUs
+// (recon_launch.h).  A thread does, entirely in registers, dequant + IDCT of its
+// chroma blocks (kept as packed bytes in a shared-memory scratch), then dequant +
+// IDCT + upsample + colour of each luma block and writes 24-byte pixel runs;
+// neighbouring lanes write neighbouring runs of the same image rows.
 //
-// recon_tma_kernel (main path): persistent CTAs (3 per SM), each walking a
-//   contiguous chunk of the tile list.  Four consumer warps (128 MCUs) plus one
-//   producer warp.  Coefficients reach the consumers through a 3-slot ring of
-//   16 KiB shared-memory slots filled by TMA (cp.async.bulk.tensor with a
-//   128-byte swizzle, so that thread t reading row t of a slot in 16-byte
-//   pieces is bank-conflict free); full/empty mbarriers per slot; a slot is
-//   released as soon as the four warps have pulled their blocks into registers,
-//   so the producer keeps the ring full while the arithmetic runs.
-//   The kernel is bound by integer issue (see recon_math.cuh), not by HBM, for
-//   4:4:4; the ring keeps the issue slots busy while HBM streams.
+// recon_tma_kernel (main path): every warp is an autonomous pipeline -- no
+//   CTA-wide barrier after set-up.  Warp w of the grid owns tiles w, w + W,
+//   w + 2W, ... (W = warps in the grid), so that the warps resident at any moment
+//   stream neighbouring 4 KiB pieces of the planes.  Coefficients reach the lanes
+//   through a private 2-slot ring of 4 KiB shared-memory slots filled by TMA
+//   (cp.async.bulk.tensor, box = 32 blocks x 64 coefficients, 128-byte swizzle so
+//   that lane t reading row t in 16-byte pieces is bank-conflict free), one
+//   mbarrier per slot.  As soon as the warp has pulled an item into registers,
+//   lane 0 re-arms the slot with the item two steps ahead; the arithmetic of one
+//   item (about a thousand instructions per lane) covers the fetch of the next.
+//   Small tiles + interleaved ownership keep the tail of single-frame launches
+//   short; 15 warps per SM (3 CTAs x 5) are resident, bounded by shared memory.
 // recon_ldg_kernel (fallback): same body, 128-bit global loads; used when the
 //   coefficient planes cannot be described by one tensor map (alignment).
 // generic_*: two-pass path for sampling layouts without a fused kernel.
@@ -26,12 +28,29 @@ namespace gidk {
 namespace {
 
 constexpr int kFrameWords = (int)(sizeof(FrameDev) / sizeof(uint32_t));
-static_assert(sizeof(FrameDev) % sizeof(uint32_t) == 0, "FrameDev must be word sized");
+static_assert(sizeof(FrameDev) % 16 == 0, "FrameDev is copied in 16-byte pieces");
 
-constexpr int kNumSlots = 3;
-constexpr int kSlotBytes = kTileMcus * 128;  // one block (64 x int16) per thread
-constexpr int kCtasPerSm = 3;
-constexpr int kTmaThreads = kTileMcus + 32;  // consumers + the producer warp
+// Warps are assigned to the four SM sub-partitions round-robin inside a CTA, so
+// the warp count per CTA must spread evenly over them (5 warps per CTA put 6 of
+// 15 warps on one scheduler and cost 20 %: measured, profiles/r01c).
+#ifndef GIDK_WARPS_PER_CTA
+#define GIDK_WARPS_PER_CTA 15
+#define GIDK_CTAS_PER_SM 1
+#endif
+constexpr int kWarpsPerCta = GIDK_WARPS_PER_CTA;
+constexpr int kCtasPerSm = GIDK_CTAS_PER_SM;
+constexpr int kCtaThreads = kWarpsPerCta * 32;
+constexpr int kNumSlots = 2;
+constexpr int kSlotBytes = kTileMcus * 128;            // one block (64 x int16) per lane
+constexpr int kRingBytes = kNumSlots * kSlotBytes;
+constexpr int kScratchBytes = 3 * 8 * kTileMcus * 8;   // per warp: [3 planes][8 rows][32 lanes] x 8 bytes
+constexpr int kFrameBytes = (int)((sizeof(FrameDev) + 127) / 128 * 128);
+// dynamic shared memory of one CTA: rings (1024-byte aligned), scratches, frame caches, barriers
+constexpr int kOffScratch = kWarpsPerCta * kRingBytes;
+constexpr int kOffFrame = kOffScratch + kWarpsPerCta * kScratchBytes;
+constexpr int kOffBars = kOffFrame + kWarpsPerCta * kFrameBytes;
+constexpr int kDynSmem = kOffBars + kWarpsPerCta * kNumSlots * 8 + 1024;  // + slack for the alignment
+static_assert(kTileMcus == 32, "one tile per warp");
 
 template <int LAYOUT> struct LayoutInfo;
 template <> struct LayoutInfo<LAYOUT_GREY> { static constexpr int H = 1, V = 1, NI = 1; static constexpr bool linear = true; };
@@ -46,9 +65,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) {
 }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -84,75 +100,66 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   return v;
 }
 
-// ---- block source: the TMA ring -------------------------------------------------
+// ---- block source: the warp's private TMA ring -------------------------------------
 
-// Items flow through the ring in a fixed order: for every tile of the CTA's
-// chunk, items 0 .. NI-1.  Item k lives in slot k % 3; the n-th use of a slot
-// completes phase n & 1 of its full barrier (producer: arrive.expect_tx + TMA
-// complete_tx) and, once the four consumer warps have pulled their blocks into
-// registers, of its empty barrier.
-struct RingCursor {
-  uint32_t slot = 0, phase = 0;
-  __device__ __forceinline__ void advance() {
-    if (++slot == (uint32_t)kNumSlots) { slot = 0; phase ^= 1u; }
-  }
-};
-
+// Items flow through the ring in a fixed order: for every tile the warp owns,
+// items 0 .. NI-1.  Item k lives in slot k & 1; the n-th use of a slot completes
+// phase n & 1 of its barrier.  The fetch cursor runs kNumSlots items ahead of the
+// consumer; the coordinate of the next box is loaded one step early so that its
+// latency hides behind the arithmetic.
 template <int LAYOUT>
 struct TmaSource {
-  uint32_t slots, full, empty;  // shared-window addresses
-  uint32_t lane_off;            // t * 128 + ((t & 7) << 4): row t, chunk index pre-xored
-  RingCursor cur;
+  using LI = LayoutInfo<LAYOUT>;
+  uint32_t slots, full;   // shared-window addresses (this warp)
+  uint32_t lane_off;      // lane * 128 + ((lane & 7) << 4): row `lane`, chunk index pre-xored
+  uint32_t slot, phase;   // consume cursor
+  const TileDesc *tiles;
+  const CUtensorMap *map2, *map3;
+  uint32_t ntiles, stride;      // stride = warps in the grid
+  uint32_t f_tile, f_item, f_coord;  // fetch cursor
 
-  // consume the next item: this thread's block (row t of the slot) -> raw[8]
-  __device__ __forceinline__ void load(int, int, int, u32x4 (&raw)[8]) {
-    mbar_wait(full + 8 * cur.slot, cur.phase);
-    const uint32_t base = slots + cur.slot * kSlotBytes + lane_off;
+  __device__ __forceinline__ void start(uint32_t first_tile) {
+    slot = 0;
+    phase = 0;
+    f_tile = first_tile;
+    f_item = 0;
+    f_coord = __ldg(&tiles[f_tile].coord[0]);
+#pragma unroll
+    for (int s = 0; s < kNumSlots; s++) refill((uint32_t)s);
+  }
+  // lane 0 arms slot s with the item under the fetch cursor; every lane advances the cursor
+  __device__ __forceinline__ void refill(uint32_t s) {
+    if (f_tile >= ntiles) return;
+    if ((threadIdx.x & 31) == 0) {
+      const uint32_t bar = full + 8 * s, dst = slots + s * kSlotBytes;
+      mbar_arrive_expect_tx(bar, kSlotBytes);
+      if (LI::H == 2 && f_item >= 2) tma_load_3d(dst, map3, 0, (int)((f_item - 2) & 1), (int)f_coord, bar);
+      else tma_load_2d(dst, map2, 0, (int)f_coord, bar);
+    }
+    if (++f_item == (uint32_t)LI::NI) {
+      f_item = 0;
+      f_tile += stride;
+    }
+    if (f_tile < ntiles) f_coord = __ldg(&tiles[f_tile].coord[f_item]);
+  }
+  // consume the next item: this lane's block (row `lane` of the slot) -> raw[8]
+  __device__ __forceinline__ void load(bool, int, int, int, u32x4 (&raw)[8]) {
+    mbar_wait(full + 8 * slot, phase);
+    const uint32_t base = slots + slot * kSlotBytes + lane_off;
 #pragma unroll
     for (int j = 0; j < 8; j++) raw[j] = lds128(base ^ (uint32_t)(j << 4));
-    release();
-  }
-  // threads without an MCU in this tile still take part in the protocol
-  __device__ __forceinline__ void skip() {
-    mbar_wait(full + 8 * cur.slot, cur.phase);
-    release();
-  }
-  __device__ __forceinline__ void release() {
+    // every lane has its block in registers: hand the slot back to the async proxy
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) mbar_arrive(empty + 8 * cur.slot);
-    cur.advance();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    refill(slot);
+    slot ^= 1u;
+    if (slot == 0) phase ^= 1u;
   }
 };
 
-// The producer: one thread streams every item of the CTA's tile chunk.
-template <int LAYOUT>
-__device__ __forceinline__ void produce_all(uint32_t slots, uint32_t full, uint32_t empty, const TileDesc *tiles,
-                                            const CUtensorMap *map2, const CUtensorMap *map3, uint32_t t_begin,
-                                            uint32_t t_end) {
-  using LI = LayoutInfo<LAYOUT>;
-  RingCursor cur;
-  uint32_t k = 0;
-  for (uint32_t tile = t_begin; tile < t_end; tile++) {
-#pragma unroll
-    for (int item = 0; item < LI::NI; item++, k++) {
-      const uint32_t coord = __ldg(&tiles[tile].coord[item]);
-      if (k >= (uint32_t)kNumSlots) mbar_wait(empty + 8 * cur.slot, cur.phase ^ 1u);
-      const uint32_t bar = full + 8 * cur.slot;
-      mbar_arrive_expect_tx(bar, kSlotBytes);
-      const uint32_t dst = slots + cur.slot * kSlotBytes;
-      if (LI::H == 2 && item >= 2) tma_load_3d(dst, map3, 0, (item - 2) & 1, (int)coord, bar);
-      else tma_load_2d(dst, map2, 0, (int)coord, bar);
-      cur.advance();
-    }
-  }
-}
-
-// scratch for the packed samples: [3 planes][8 rows][128 threads] x 8 bytes
-constexpr int kScratchBytes = 3 * 8 * kTileMcus * 8;
-
-__device__ __forceinline__ Scratch make_scratch(uint8_t *base, uint32_t t) {
+__device__ __forceinline__ Scratch make_scratch(uint8_t *base, uint32_t lane) {
   Scratch sc;
-  u32x2 *p = reinterpret_cast<u32x2 *>(base) + t;
+  u32x2 *p = reinterpret_cast<u32x2 *>(base) + lane;
   sc.cb = p;
   sc.cr = p + 8 * kTileMcus;
   sc.y = p + 16 * kTileMcus;
@@ -161,115 +168,105 @@ __device__ __forceinline__ Scratch make_scratch(uint8_t *base, uint32_t t) {
 }
 
 template <int LAYOUT, bool Q8, class Src>
-__device__ __forceinline__ void run_mcu(uint32_t lanes, const FrameDev &f, Src &src, const Scratch &sc, int mx,
-                                        int my) {
+__device__ __forceinline__ void run_mcu(bool active, const FrameDev &f, Src &src, const Scratch &sc, int mx, int my) {
   using LI = LayoutInfo<LAYOUT>;
-  mcu_run<LI::H, LI::V, LAYOUT == LAYOUT_GREY, Q8>(lanes, f, &f.qw[0][0], src, sc, mx, my);
+  mcu_run<LI::H, LI::V, LAYOUT == LAYOUT_GREY, Q8>(active, f, &f.qw[0][0], src, sc, mx, my);
 }
 
-// MCU (mx, my) of thread t in a tile starting at m0, or false when the thread
-// has no MCU (tail of the frame / of the MCU row).
+// MCU (mx, my) of lane t in a tile starting at m0, or false when the lane has
+// no MCU (tail of the frame / of the MCU row).
 template <int LAYOUT>
 __device__ __forceinline__ bool tile_mcu(const FrameDev &f, uint32_t m0, uint32_t t, int &mx, int &my) {
   if (LayoutInfo<LAYOUT>::linear) {
     const uint32_t m = m0 + t;
-    if (m >= (uint32_t)(f.mcux * f.mcuy)) return false;
     my = (int)(m / (uint32_t)f.mcux);
     mx = (int)(m - (uint32_t)my * (uint32_t)f.mcux);
-    return true;
+    return m < (uint32_t)(f.mcux * f.mcuy);
   }
   my = (int)(m0 / (uint32_t)f.mcux);
   mx = (int)(m0 - (uint32_t)my * (uint32_t)f.mcux + t);
   return mx < f.mcux;
 }
 
-constexpr int kDynSmem = kNumSlots * kSlotBytes + kScratchBytes + 1024;  // + slack for 1024-byte alignment
-
-template <int LAYOUT, bool Q8>
-__global__ void __launch_bounds__(kTmaThreads, kCtasPerSm)
-recon_tma_kernel(const __grid_constant__ CUtensorMap map2, const __grid_constant__ CUtensorMap map3,
-                 const FrameDev *__restrict__ frames, const TileDesc *__restrict__ tiles, uint32_t ntiles) {
-  using LI = LayoutInfo<LAYOUT>;
-  extern __shared__ uint8_t dyn_smem[];
-  __shared__ __align__(16) uint32_t s_frame_words[kFrameWords];
-  __shared__ __align__(8) uint64_t s_full[kNumSlots], s_empty[kNumSlots];
-
-  // contiguous chunk of the tile list per CTA
-  const uint32_t per = (ntiles + gridDim.x - 1) / gridDim.x;
-  const uint32_t t_begin = blockIdx.x * per;
-  const uint32_t t_end = min(ntiles, t_begin + per);
-  if (t_begin >= t_end) return;
-
-  const uint32_t t = threadIdx.x;
-  const uint32_t slots = (smem_u32(dyn_smem) + 1023u) & ~1023u;
-  const uint32_t full = smem_u32(s_full), empty = smem_u32(s_empty);
-  if (t == 0) {
-    for (int s = 0; s < kNumSlots; s++) {
-      mbar_init(full + 8 * s, 1);
-      mbar_init(empty + 8 * s, kTileMcus / 32);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  __syncthreads();
-
-  if (t >= (uint32_t)kTileMcus) {  // producer warp
-    if (t == (uint32_t)kTileMcus) produce_all<LAYOUT>(slots, full, empty, tiles, &map2, &map3, t_begin, t_end);
-    return;
-  }
-
-  TmaSource<LAYOUT> src;
-  src.slots = slots;
-  src.full = full;
-  src.empty = empty;
-  src.lane_off = t * 128u + ((t & 7u) << 4);
-  const Scratch scratch = make_scratch(dyn_smem + (slots - smem_u32(dyn_smem)) + kNumSlots * kSlotBytes, t);
-  uint32_t cur_frame = 0xFFFFFFFFu;
-#pragma unroll 1
-  for (uint32_t tile = t_begin; tile < t_end; tile++) {
-    const uint32_t fi = __ldg(&tiles[tile].frame);
-    const uint32_t m0 = __ldg(&tiles[tile].m0);
-    if (fi != cur_frame) {  // uniform over the consumer warps
-      asm volatile("bar.sync 1, %0;" ::"n"(kTileMcus) : "memory");
-      const uint32_t *g = reinterpret_cast<const uint32_t *>(frames + fi);
-      for (int i = t; i < kFrameWords; i += kTileMcus) s_frame_words[i] = __ldg(g + i);
-      asm volatile("bar.sync 1, %0;" ::"n"(kTileMcus) : "memory");
-      cur_frame = fi;
-    }
-    const FrameDev &f = *reinterpret_cast<const FrameDev *>(s_frame_words);
-    int mx, my;
-    const bool has_mcu = tile_mcu<LAYOUT>(f, m0, t, mx, my);
-    const uint32_t lanes = __ballot_sync(0xFFFFFFFFu, has_mcu);  // the lanes that vote in the sparse IDCT
-    if (has_mcu) {
-      run_mcu<LAYOUT, Q8>(lanes, f, src, scratch, mx, my);
-    } else {
-#pragma unroll
-      for (int i = 0; i < LI::NI; i++) src.skip();
-    }
-  }
+// warp-level copy of a frame descriptor into the warp's shared-memory cache
+__device__ __forceinline__ void cache_frame(uint8_t *dst, const FrameDev *src, uint32_t lane) {
+  const uint4 *g = reinterpret_cast<const uint4 *>(src);
+  uint4 *d = reinterpret_cast<uint4 *>(dst);
+  __syncwarp();
+  for (uint32_t i = lane; i < sizeof(FrameDev) / 16; i += 32) d[i] = __ldg(g + i);
+  __syncwarp();
 }
 
 template <int LAYOUT, bool Q8>
-__global__ void __launch_bounds__(kTileMcus)
+__global__ void __launch_bounds__(kCtaThreads, kCtasPerSm)
+recon_tma_kernel(const __grid_constant__ CUtensorMap map2, const __grid_constant__ CUtensorMap map3,
+                 const FrameDev *__restrict__ frames, const TileDesc *__restrict__ tiles, uint32_t ntiles) {
+  extern __shared__ uint8_t dyn_smem[];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t nwarps = gridDim.x * kWarpsPerCta;
+  const uint32_t first = blockIdx.x * kWarpsPerCta + warp;
+  if (first >= ntiles) return;  // warp-uniform; the warps never meet at a CTA barrier
+
+  const uint32_t base = (smem_u32(dyn_smem) + 1023u) & ~1023u;
+  uint8_t *gen = dyn_smem + (base - smem_u32(dyn_smem));
+  TmaSource<LAYOUT> src;
+  src.slots = base + warp * kRingBytes;
+  src.full = base + kOffBars + warp * (kNumSlots * 8);
+  src.lane_off = lane * 128u + ((lane & 7u) << 4);
+  src.tiles = tiles;
+  src.map2 = &map2;
+  src.map3 = &map3;
+  src.ntiles = ntiles;
+  src.stride = nwarps;
+  if (lane == 0) {
+    for (int s = 0; s < kNumSlots; s++) mbar_init(src.full + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+  src.start(first);
+
+  const Scratch scratch = make_scratch(gen + kOffScratch + warp * kScratchBytes, lane);
+  uint8_t *frame_cache = gen + kOffFrame + warp * kFrameBytes;
+  const FrameDev &f = *reinterpret_cast<const FrameDev *>(frame_cache);
+  uint32_t cur_frame = 0xFFFFFFFFu;
+  uint32_t fi = __ldg(&tiles[first].frame), m0 = __ldg(&tiles[first].m0);
+#pragma unroll 1
+  for (uint32_t tile = first; tile < ntiles; tile += nwarps) {
+    const uint32_t this_frame = fi, this_m0 = m0;
+    const uint32_t nxt = tile + nwarps;
+    if (nxt < ntiles) {  // header of the next tile: in flight while this one is computed
+      fi = __ldg(&tiles[nxt].frame);
+      m0 = __ldg(&tiles[nxt].m0);
+    }
+    if (this_frame != cur_frame) {
+      cache_frame(frame_cache, frames + this_frame, lane);
+      cur_frame = this_frame;
+    }
+    int mx, my;
+    const bool active = tile_mcu<LAYOUT>(f, this_m0, lane, mx, my);
+    run_mcu<LAYOUT, Q8>(active, f, src, scratch, mx, my);
+  }
+}
+
+constexpr int kLdgWarps = 4;
+
+template <int LAYOUT, bool Q8>
+__global__ void __launch_bounds__(kLdgWarps * 32)
 recon_ldg_kernel(const FrameDev *__restrict__ frames, const TileDesc *__restrict__ tiles, uint32_t ntiles) {
-  __shared__ __align__(16) uint32_t s_frame_words[kFrameWords];
-  __shared__ __align__(16) uint8_t s_scratch[kScratchBytes];
-  const uint32_t tile = blockIdx.x;
+  __shared__ __align__(16) uint8_t s_frame[kLdgWarps][kFrameBytes];
+  __shared__ __align__(16) uint8_t s_scratch[kLdgWarps][kScratchBytes];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tile = blockIdx.x * kLdgWarps + warp;
   if (tile >= ntiles) return;
   const uint32_t fi = __ldg(&tiles[tile].frame);
   const uint32_t m0 = __ldg(&tiles[tile].m0);
-  {
-    const uint32_t *g = reinterpret_cast<const uint32_t *>(frames + fi);
-    for (int i = threadIdx.x; i < kFrameWords; i += kTileMcus) s_frame_words[i] = __ldg(g + i);
-  }
-  __syncthreads();
-  const FrameDev &f = *reinterpret_cast<const FrameDev *>(s_frame_words);
+  cache_frame(s_frame[warp], frames + fi, lane);
+  const FrameDev &f = *reinterpret_cast<const FrameDev *>(s_frame[warp]);
   int mx, my;
-  const bool has_mcu = tile_mcu<LAYOUT>(f, m0, threadIdx.x, mx, my);
-  const uint32_t lanes = __ballot_sync(0xFFFFFFFFu, has_mcu);
-  if (!has_mcu) return;
+  const bool active = tile_mcu<LAYOUT>(f, m0, lane, mx, my);
   LdgSource src{&f};
-  run_mcu<LAYOUT, Q8>(lanes, f, src, make_scratch(s_scratch, threadIdx.x), mx, my);
+  run_mcu<LAYOUT, Q8>(active, f, src, make_scratch(s_scratch[warp], lane), mx, my);
 }
 
 // ---- generic path -----------------------------------------------------------
@@ -299,7 +296,7 @@ generic_idct_kernel(const FrameDev *__restrict__ frame, int ncomp) {
   {
     LdgSource src{&f};
     u32x4 raw[8];
-    src.load(c, bx, by, raw);
+    src.load(true, c, bx, by, raw);
     dequant_idct<Q8>(raw, &f.qw[c][0], b);
   }
   uint32_t p[16];
@@ -353,10 +350,11 @@ cudaError_t launch_one(bool use_tma, const CUtensorMap *map2, const CUtensorMap 
                        const TileDesc *d_tiles, uint32_t ntiles, int num_sms, cudaStream_t stream) {
   if (use_tma) {
     uint32_t grid = (uint32_t)(num_sms * kCtasPerSm);
-    if (grid > ntiles) grid = ntiles;
-    recon_tma_kernel<LAYOUT, Q8><<<grid, kTmaThreads, kDynSmem, stream>>>(*map2, *map3, d_frames, d_tiles, ntiles);
+    const uint32_t need = (ntiles + kWarpsPerCta - 1) / kWarpsPerCta;
+    if (grid > need) grid = need;
+    recon_tma_kernel<LAYOUT, Q8><<<grid, kCtaThreads, kDynSmem, stream>>>(*map2, *map3, d_frames, d_tiles, ntiles);
   } else {
-    recon_ldg_kernel<LAYOUT, Q8><<<ntiles, kTileMcus, 0, stream>>>(d_frames, d_tiles, ntiles);
+    recon_ldg_kernel<LAYOUT, Q8><<<(ntiles + kLdgWarps - 1) / kLdgWarps, kLdgWarps * 32, 0, stream>>>(d_frames, d_tiles, ntiles);
   }
   return cudaGetLastError();
 }

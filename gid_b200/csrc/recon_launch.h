@@ -10,7 +10,7 @@
 
 namespace gidk {
 
-constexpr int kTileMcus = 128;  // MCUs (= threads) per tile of the fused kernels
+constexpr int kTileMcus = 32;  // MCUs (= lanes of one warp) per tile of the fused kernels
 
 // One tile = up to kTileMcus consecutive MCUs of one frame, starting at linear
 // MCU index m0.  Layouts whose components all have one block per MCU (grey,

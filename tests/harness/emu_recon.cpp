@@ -34,7 +34,7 @@ extern "C" int emu_reconstruct(const gidcuda_frame_desc *desc, const int16_t *co
           int b[64];
           LdgSource src{&f};
           u32x4 raw[8];
-          src.load(c, bx, by, raw);
+          src.load(true, c, bx, by, raw);
           if (f.q8) dequant_idct<true>(raw, &f.qw[c][0], b);
           else dequant_idct<false>(raw, &f.qw[c][0], b);
           uint32_t p[16];
@@ -74,10 +74,10 @@ extern "C" int emu_reconstruct(const gidcuda_frame_desc *desc, const int16_t *co
       if (m >= (uint32_t)(f.mcux * f.mcuy)) continue;
       const int my = (int)(m / (uint32_t)f.mcux), mx = (int)(m - (uint32_t)my * f.mcux);
       switch (g.layout) {
-        case LAYOUT_GREY: f.q8 ? mcu_run<1, 1, true, true>(1u, f, qw, src, sc, mx, my) : mcu_run<1, 1, true, false>(1u, f, qw, src, sc, mx, my); break;
-        case LAYOUT_444: f.q8 ? mcu_run<1, 1, false, true>(1u, f, qw, src, sc, mx, my) : mcu_run<1, 1, false, false>(1u, f, qw, src, sc, mx, my); break;
-        case LAYOUT_422: f.q8 ? mcu_run<2, 1, false, true>(1u, f, qw, src, sc, mx, my) : mcu_run<2, 1, false, false>(1u, f, qw, src, sc, mx, my); break;
-        default: f.q8 ? mcu_run<2, 2, false, true>(1u, f, qw, src, sc, mx, my) : mcu_run<2, 2, false, false>(1u, f, qw, src, sc, mx, my); break;
+        case LAYOUT_GREY: f.q8 ? mcu_run<1, 1, true, true>(true, f, qw, src, sc, mx, my) : mcu_run<1, 1, true, false>(true, f, qw, src, sc, mx, my); break;
+        case LAYOUT_444: f.q8 ? mcu_run<1, 1, false, true>(true, f, qw, src, sc, mx, my) : mcu_run<1, 1, false, false>(true, f, qw, src, sc, mx, my); break;
+        case LAYOUT_422: f.q8 ? mcu_run<2, 1, false, true>(true, f, qw, src, sc, mx, my) : mcu_run<2, 1, false, false>(true, f, qw, src, sc, mx, my); break;
+        default: f.q8 ? mcu_run<2, 2, false, true>(true, f, qw, src, sc, mx, my) : mcu_run<2, 2, false, false>(true, f, qw, src, sc, mx, my); break;
       }
     }
   return 0;
