@@ -65,7 +65,8 @@ def build_host(force: bool = False) -> str | None:
     deps = _sources(HOST, (".cpp", ".hpp", ".h")) + [os.path.join(ROOT, "include", "gidcuda.h")]
     if force or _stale(out, deps):
         cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wextra",
-               "-I", os.path.join(ROOT, "include")] + srcs + ["-o", out, "-ldl", "-lpthread"]
+               "-I", os.path.join(ROOT, "include")] + srcs + ["-o", out, "-L", LIB, "-lgidcuda",
+               "-Wl,-rpath,$ORIGIN", "-lpthread"]
         subprocess.run(cmd, check=True, cwd=HOST)
     return out
 
