@@ -40,6 +40,7 @@ UNIT = "MP/s"
 
 WORKLOADS = {
     # name: (width, height, sampling, frames per step per GPU, description)
+    "cfg1": (512, 512, "420", 64, "batch of 512x512 baseline 4:2:0 frames (configs[0], the reference's CPU-runnable case), 64 per step per GPU"),
     "cfg2": (4096, 4096, "444", 1, "4096x4096 baseline 4:4:4 frame (BASELINE.json configs[1], kernel roofline case)"),
     "cfg3": (1920, 1080, "420", 128, "batch of 1920x1080 baseline 4:2:0 frames (configs[2]), 128 frames per step per GPU"),
     "cfg4": (8192, 8192, "grey", 1, "8192x8192 grey baseline frame (configs[3])"),
@@ -173,6 +174,8 @@ def run_reference(args) -> None:
     frames = make_frames(args.workload, 1, 0)
     # each "step" = a bounded sample of the workload; keep the whole run within a few minutes
     per_step_seconds = max(0.5, min(4.0, 60.0 / max(1, args.steps + args.warmup)))
+    if os.environ.get("GIDBENCH_REFERENCE_SECONDS"):  # tests: a shorter sample
+        per_step_seconds = float(os.environ["GIDBENCH_REFERENCE_SECONDS"])
     for _ in range(args.warmup):
         cpu_reconstruct_rate(frames, per_step_seconds / 4, cores)
     rates, sample = [], ""
@@ -204,7 +207,7 @@ def run_ours(args) -> None:
     import torch
     import torch.distributed as dist
 
-    from gid_b200 import GidCuda, build, capi
+    from gid_b200 import GidCuda, build, capi, sharding
     from tests.harness import frame_desc
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
@@ -284,12 +287,9 @@ def run_ours(args) -> None:
             torch.cuda.synchronize()
     torch.cuda.synchronize()
     clocks = sampler.stop()
-    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_max = float(t_ms.item())
+    ms_max = sharding.max_over_ranks(ms, dev)  # the job is as slow as its slowest rank
     mp_step = w * h * per_step / 1e6
-    value = mp_step * args.steps * world / (ms_max * 1e-3)
+    value = sharding.whole_job_rate(mp_step * args.steps, world, ms_max * 1e-3)
 
     # ---- end to end through the job API: host planes -> host pixels -----------------------
     L = ctx.lib
@@ -326,10 +326,8 @@ def run_ours(args) -> None:
     e2e_steps(args.steps)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e_value = (w * h * e2e_frames / 1e6) * args.steps * world / float(t_e.item())
+    e2e_value = sharding.whole_job_rate((w * h * e2e_frames / 1e6) * args.steps, world,
+                                        sharding.max_over_ranks(e2e_s, dev))
     coef_bytes = sum(p.nbytes for p in frames[0].planes)
     for job in jobs:
         L.gidcuda_job_release(job)
