@@ -79,10 +79,12 @@ class LaunchSet {
   void destroy() {
     if (d_frames_) cudaFree(d_frames_);
     if (d_tiles_) cudaFree(d_tiles_);
+    if (d_counters_) cudaFree(d_counters_);
     if (h_frames_) cudaFreeHost(h_frames_);
     if (h_tiles_) cudaFreeHost(h_tiles_);
     d_frames_ = nullptr;
     d_tiles_ = nullptr;
+    d_counters_ = nullptr;
     h_frames_ = nullptr;
     h_tiles_ = nullptr;
     cap_frames_ = cap_tiles_ = 0;
@@ -147,6 +149,10 @@ class LaunchSet {
   // Copies the tables to the device (asynchronously, from pinned staging).
   cudaError_t upload(cudaStream_t s) {
     cudaError_t e;
+    if (!d_counters_) {  // tile-claim counters, two words per possible launch group; kernels leave them zero
+      if ((e = cudaMalloc((void **)&d_counters_, kMaxGroups * 2 * sizeof(uint32_t))) != cudaSuccess) return e;
+      if ((e = cudaMemsetAsync(d_counters_, 0, kMaxGroups * 2 * sizeof(uint32_t), s)) != cudaSuccess) return e;
+    }
     if (cap_frames_ < frames.size()) {
       if (d_frames_) cudaFree(d_frames_);
       if (h_frames_) cudaFreeHost(h_frames_);
@@ -182,10 +188,13 @@ class LaunchSet {
 
   cudaError_t launch(int num_sms, cudaStream_t s) const {
     cudaError_t e;
-    for (const LaunchGroup &g : groups)
+    uint32_t gi = 0;
+    for (const LaunchGroup &g : groups) {
       if ((e = launch_fused(g.layout, g.q8, g.tma, &g.map2, &g.map3, d_frames_ + g.first_frame,
-                            d_tiles_ + g.first_tile, g.ntiles, num_sms, s)) != cudaSuccess)
+                            d_tiles_ + g.first_tile, g.ntiles, d_counters_ + 2 * gi, num_sms, s)) != cudaSuccess)
         return e;
+      gi++;
+    }
     for (size_t i = n_fused; i < frames.size(); i++)
       if ((e = launch_generic(frames[i], d_frames_ + i, s)) != cudaSuccess) return e;
     return cudaSuccess;
@@ -194,6 +203,8 @@ class LaunchSet {
   size_t upload_bytes = 0;
 
  private:
+  static constexpr int kMaxGroups = 8;  // 4 layouts x 2 table widths
+  uint32_t *d_counters_ = nullptr;
   FrameDev *d_frames_ = nullptr, *h_frames_ = nullptr;
   TileDesc *d_tiles_ = nullptr, *h_tiles_ = nullptr;
   size_t cap_frames_ = 0, cap_tiles_ = 0;

@@ -49,7 +49,8 @@ constexpr int kFrameBytes = (int)((sizeof(FrameDev) + 127) / 128 * 128);
 constexpr int kOffScratch = kWarpsPerCta * kRingBytes;
 constexpr int kOffFrame = kOffScratch + kWarpsPerCta * kScratchBytes;
 constexpr int kOffBars = kOffFrame + kWarpsPerCta * kFrameBytes;
-constexpr int kDynSmem = kOffBars + kWarpsPerCta * kNumSlots * 8 + 1024;  // + slack for the alignment
+constexpr int kBarBytes = kNumSlots * 8 + 64;  // per warp: the slot barriers + the ring of claimed tiles (4 x uint4)
+constexpr int kDynSmem = kOffBars + kWarpsPerCta * kBarBytes + 1024;  // + slack for the alignment
 static_assert(kTileMcus == 32, "one tile per warp");
 
 template <int LAYOUT> struct LayoutInfo;
@@ -102,11 +103,60 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 
 // ---- block source: the warp's private TMA ring -------------------------------------
 
-// Items flow through the ring in a fixed order: for every tile the warp owns,
+// Tiles are handed out dynamically: a warp claims its next tile with an atomic
+// on a launch-wide counter, so warps on a lightly loaded scheduler (or a faster
+// SM) simply take more of them and nobody waits at the end of the launch (static
+// ownership left the SMs idle 14-22 % of the time: profiles/r01e).  The claim for
+// the tile AFTER the next one is issued early, so the atomic's latency hides
+// behind a whole tile of arithmetic.  The last warp to finish resets the
+// counters for the next launch of the same plan.
+struct TileClaims {
+  uint32_t *counters;  // [0] next dynamic tile - 2 * nwarps, [1] warps finished
+  uint32_t pending;    // lane 0: result of the claim in flight
+  uint32_t gw, nwarps; // this warp's index in the grid, warps in the grid
+  uint32_t taken;
+  // The first two tiles of a warp are fixed (gw, gw + nwarps): 2 220 warps hitting
+  // one counter at the same instant at kernel start serialise in L2 for microseconds.
+  // Later claims are spread in time and hidden behind a tile of work.
+  // Plain atom (not atomicAdd: the compiler's warp-aggregated form reads the result
+  // back at once, which would expose the latency this scheme exists to hide).
+  __device__ __forceinline__ void issue() {
+    if ((threadIdx.x & 31) == 0)
+      asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(pending) : "l"(counters) : "memory");
+  }
+  __device__ __forceinline__ uint32_t take() {  // the next tile, to every lane
+    const uint32_t n = taken++;
+    if (n < 2u) return gw + n * nwarps;
+    const uint32_t t = 2u * nwarps + __shfl_sync(0xFFFFFFFFu, pending, 0);
+    issue();
+    return t;
+  }
+  // The last warp to finish leaves the counters zero for the next launch.  Reading
+  // `pending` first makes sure this warp's last claim has been performed (its value
+  // has come back) before the warp counts itself as finished, so no claim can land
+  // after the reset; no fence needed.
+  __device__ __forceinline__ void finish() {
+    if ((threadIdx.x & 31) == 0) {
+      uint32_t old;
+      asm volatile(
+          "{ .reg .u32 t;\n\tand.b32 t, %2, 0;\n\tadd.u32 t, t, 1;\n\tatom.global.add.u32 %0, [%1], t; }"
+          : "=r"(old)
+          : "l"(counters + 1), "r"(pending)
+          : "memory");
+      if (old == nwarps - 1u) {
+        counters[0] = 0u;
+        counters[1] = 0u;
+      }
+    }
+  }
+};
+
+// Items flow through the ring in a fixed order: for every tile the warp claims,
 // items 0 .. NI-1.  Item k lives in slot k & 1; the n-th use of a slot completes
 // phase n & 1 of its barrier.  The fetch cursor runs kNumSlots items ahead of the
 // consumer; the coordinate of the next box is loaded one step early so that its
-// latency hides behind the arithmetic.
+// latency hides behind the arithmetic.  Claimed tiles travel from the fetch
+// cursor to the consumer through a 4-entry ring in shared memory.
 template <int LAYOUT>
 struct TmaSource {
   using LI = LayoutInfo<LAYOUT>;
@@ -115,20 +165,60 @@ struct TmaSource {
   uint32_t slot, phase;   // consume cursor
   const TileDesc *tiles;
   const CUtensorMap *map2, *map3;
-  uint32_t ntiles, stride;      // stride = warps in the grid
+  uint32_t ntiles;
+  TileClaims claims;
+  volatile uint4 *claimed;  // shared: ring of claimed tiles {tile, frame, m0, -}
+  uint32_t n_claimed, n_consumed;
   uint32_t f_tile, f_item, f_coord;  // fetch cursor
+  uint32_t h_frame, h_m0;            // header of the tile claimed last (lane 0), stored one step later
+  bool h_pending;
 
-  __device__ __forceinline__ void start(uint32_t first_tile) {
+  __device__ __forceinline__ void next_fetch_tile() {
+    f_tile = claims.take();
+    n_claimed++;
+    h_pending = true;
+    h_frame = h_m0 = 0;
+    if (f_tile < ntiles) {
+      f_coord = __ldg(&tiles[f_tile].coord[0]);
+      h_frame = __ldg(&tiles[f_tile].frame);
+      h_m0 = __ldg(&tiles[f_tile].m0);
+    }
+  }
+  // the header loads were issued a whole item ago: publishing them costs no wait
+  __device__ __forceinline__ void publish_header() {
+    if (h_pending) {
+      if ((threadIdx.x & 31) == 0) {
+        uint4 e;
+        e.x = f_tile; e.y = h_frame; e.z = h_m0; e.w = 0;
+        const_cast<uint4 *>(claimed)[(n_claimed - 1u) & 3u] = e;
+      }
+      h_pending = false;
+    }
+  }
+  __device__ __forceinline__ void start() {
     slot = 0;
     phase = 0;
-    f_tile = first_tile;
+    n_claimed = n_consumed = 0;
     f_item = 0;
-    f_coord = __ldg(&tiles[f_tile].coord[0]);
+    h_pending = false;
+    claims.issue();
+    next_fetch_tile();
 #pragma unroll
     for (int s = 0; s < kNumSlots; s++) refill((uint32_t)s);
+    publish_header();
+  }
+  // the next tile of this warp (tile >= ntiles: none left).  Its ring entry was
+  // published at least one refill ago (the fetch cursor is kNumSlots items ahead).
+  __device__ __forceinline__ uint4 next_tile() {
+    __syncwarp();
+    const volatile uint4 *e = &claimed[(n_consumed++) & 3u];
+    uint4 v;
+    v.x = e->x; v.y = e->y; v.z = e->z; v.w = 0;
+    return v;
   }
   // lane 0 arms slot s with the item under the fetch cursor; every lane advances the cursor
   __device__ __forceinline__ void refill(uint32_t s) {
+    publish_header();
     if (f_tile >= ntiles) return;
     if ((threadIdx.x & 31) == 0) {
       const uint32_t bar = full + 8 * s, dst = slots + s * kSlotBytes;
@@ -138,9 +228,10 @@ struct TmaSource {
     }
     if (++f_item == (uint32_t)LI::NI) {
       f_item = 0;
-      f_tile += stride;
+      next_fetch_tile();
+    } else {
+      f_coord = __ldg(&tiles[f_tile].coord[f_item]);
     }
-    if (f_tile < ntiles) f_coord = __ldg(&tiles[f_tile].coord[f_item]);
   }
   // consume the next item: this lane's block (row `lane` of the slot) -> raw[8]
   __device__ __forceinline__ void load(bool, int, int, int, u32x4 (&raw)[8]) {
@@ -200,45 +291,43 @@ __device__ __forceinline__ void cache_frame(uint8_t *dst, const FrameDev *src, u
 template <int LAYOUT, bool Q8>
 __global__ void __launch_bounds__(kCtaThreads, kCtasPerSm)
 recon_tma_kernel(const __grid_constant__ CUtensorMap map2, const __grid_constant__ CUtensorMap map3,
-                 const FrameDev *__restrict__ frames, const TileDesc *__restrict__ tiles, uint32_t ntiles) {
+                 const FrameDev *__restrict__ frames, const TileDesc *__restrict__ tiles, uint32_t ntiles,
+                 uint32_t *__restrict__ counters) {
   extern __shared__ uint8_t dyn_smem[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t nwarps = gridDim.x * kWarpsPerCta;
-  const uint32_t first = blockIdx.x * kWarpsPerCta + warp;
-  if (first >= ntiles) return;  // warp-uniform; the warps never meet at a CTA barrier
 
   const uint32_t base = (smem_u32(dyn_smem) + 1023u) & ~1023u;
   uint8_t *gen = dyn_smem + (base - smem_u32(dyn_smem));
   TmaSource<LAYOUT> src;
   src.slots = base + warp * kRingBytes;
-  src.full = base + kOffBars + warp * (kNumSlots * 8);
+  src.full = base + kOffBars + warp * kBarBytes;
+  src.claimed = reinterpret_cast<volatile uint4 *>(gen + kOffBars + warp * kBarBytes + kNumSlots * 8);
   src.lane_off = lane * 128u + ((lane & 7u) << 4);
   src.tiles = tiles;
   src.map2 = &map2;
   src.map3 = &map3;
   src.ntiles = ntiles;
-  src.stride = nwarps;
+  src.claims.counters = counters;
+  src.claims.pending = 0;
+  src.claims.gw = blockIdx.x * kWarpsPerCta + warp;
+  src.claims.nwarps = nwarps;
+  src.claims.taken = 0;
   if (lane == 0) {
     for (int s = 0; s < kNumSlots; s++) mbar_init(src.full + 8 * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncwarp();
-  src.start(first);
+  src.start();
 
   const Scratch scratch = make_scratch(gen + kOffScratch + warp * kScratchBytes, lane);
   uint8_t *frame_cache = gen + kOffFrame + warp * kFrameBytes;
   const FrameDev &f = *reinterpret_cast<const FrameDev *>(frame_cache);
   uint32_t cur_frame = 0xFFFFFFFFu;
-  uint32_t fi = __ldg(&tiles[first].frame), m0 = __ldg(&tiles[first].m0);
 #pragma unroll 1
-  for (uint32_t tile = first; tile < ntiles; tile += nwarps) {
-    const uint32_t this_frame = fi, this_m0 = m0;
-    const uint32_t nxt = tile + nwarps;
-    if (nxt < ntiles) {  // header of the next tile: in flight while this one is computed
-      fi = __ldg(&tiles[nxt].frame);
-      m0 = __ldg(&tiles[nxt].m0);
-    }
+  for (uint4 t = src.next_tile(); t.x < ntiles; t = src.next_tile()) {
+    const uint32_t this_frame = t.y, this_m0 = t.z;
     if (this_frame != cur_frame) {
       cache_frame(frame_cache, frames + this_frame, lane);
       cur_frame = this_frame;
@@ -247,6 +336,7 @@ recon_tma_kernel(const __grid_constant__ CUtensorMap map2, const __grid_constant
     const bool active = tile_mcu<LAYOUT>(f, this_m0, lane, mx, my);
     run_mcu<LAYOUT, Q8>(active, f, src, scratch, mx, my);
   }
+  src.claims.finish();
 }
 
 constexpr int kLdgWarps = 4;
@@ -347,12 +437,14 @@ generic_color_kernel(const FrameDev *__restrict__ frame, int ncomp, int hmax, in
 
 template <int LAYOUT, bool Q8>
 cudaError_t launch_one(bool use_tma, const CUtensorMap *map2, const CUtensorMap *map3, const FrameDev *d_frames,
-                       const TileDesc *d_tiles, uint32_t ntiles, int num_sms, cudaStream_t stream) {
+                       const TileDesc *d_tiles, uint32_t ntiles, uint32_t *d_counters, int num_sms,
+                       cudaStream_t stream) {
   if (use_tma) {
     uint32_t grid = (uint32_t)(num_sms * kCtasPerSm);
     const uint32_t need = (ntiles + kWarpsPerCta - 1) / kWarpsPerCta;
     if (grid > need) grid = need;
-    recon_tma_kernel<LAYOUT, Q8><<<grid, kCtaThreads, kDynSmem, stream>>>(*map2, *map3, d_frames, d_tiles, ntiles);
+    recon_tma_kernel<LAYOUT, Q8><<<grid, kCtaThreads, kDynSmem, stream>>>(*map2, *map3, d_frames, d_tiles, ntiles,
+                                                                          d_counters);
   } else {
     recon_ldg_kernel<LAYOUT, Q8><<<(ntiles + kLdgWarps - 1) / kLdgWarps, kLdgWarps * 32, 0, stream>>>(d_frames, d_tiles, ntiles);
   }
@@ -361,10 +453,10 @@ cudaError_t launch_one(bool use_tma, const CUtensorMap *map2, const CUtensorMap 
 
 template <int LAYOUT>
 cudaError_t launch_q(bool q8, bool use_tma, const CUtensorMap *map2, const CUtensorMap *map3,
-                     const FrameDev *d_frames, const TileDesc *d_tiles, uint32_t ntiles, int num_sms,
-                     cudaStream_t stream) {
-  return q8 ? launch_one<LAYOUT, true>(use_tma, map2, map3, d_frames, d_tiles, ntiles, num_sms, stream)
-            : launch_one<LAYOUT, false>(use_tma, map2, map3, d_frames, d_tiles, ntiles, num_sms, stream);
+                     const FrameDev *d_frames, const TileDesc *d_tiles, uint32_t ntiles, uint32_t *d_counters,
+                     int num_sms, cudaStream_t stream) {
+  return q8 ? launch_one<LAYOUT, true>(use_tma, map2, map3, d_frames, d_tiles, ntiles, d_counters, num_sms, stream)
+            : launch_one<LAYOUT, false>(use_tma, map2, map3, d_frames, d_tiles, ntiles, d_counters, num_sms, stream);
 }
 
 template <int LAYOUT, bool Q8>
@@ -388,14 +480,14 @@ cudaError_t init_kernels() {
 }
 
 cudaError_t launch_fused(Layout layout, bool q8, bool use_tma, const CUtensorMap *map2, const CUtensorMap *map3,
-                         const FrameDev *d_frames, const TileDesc *d_tiles, uint32_t ntiles, int num_sms,
-                         cudaStream_t stream) {
+                         const FrameDev *d_frames, const TileDesc *d_tiles, uint32_t ntiles, uint32_t *d_counters,
+                         int num_sms, cudaStream_t stream) {
   if (ntiles == 0) return cudaSuccess;
   switch (layout) {
-    case LAYOUT_GREY: return launch_q<LAYOUT_GREY>(q8, use_tma, map2, map3, d_frames, d_tiles, ntiles, num_sms, stream);
-    case LAYOUT_444: return launch_q<LAYOUT_444>(q8, use_tma, map2, map3, d_frames, d_tiles, ntiles, num_sms, stream);
-    case LAYOUT_422: return launch_q<LAYOUT_422>(q8, use_tma, map2, map3, d_frames, d_tiles, ntiles, num_sms, stream);
-    case LAYOUT_420: return launch_q<LAYOUT_420>(q8, use_tma, map2, map3, d_frames, d_tiles, ntiles, num_sms, stream);
+    case LAYOUT_GREY: return launch_q<LAYOUT_GREY>(q8, use_tma, map2, map3, d_frames, d_tiles, ntiles, d_counters, num_sms, stream);
+    case LAYOUT_444: return launch_q<LAYOUT_444>(q8, use_tma, map2, map3, d_frames, d_tiles, ntiles, d_counters, num_sms, stream);
+    case LAYOUT_422: return launch_q<LAYOUT_422>(q8, use_tma, map2, map3, d_frames, d_tiles, ntiles, d_counters, num_sms, stream);
+    case LAYOUT_420: return launch_q<LAYOUT_420>(q8, use_tma, map2, map3, d_frames, d_tiles, ntiles, d_counters, num_sms, stream);
     default: return cudaErrorInvalidValue;
   }
 }

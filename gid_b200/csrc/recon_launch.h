@@ -31,9 +31,12 @@ static_assert(sizeof(TileDesc) == 32, "TileDesc is 32 bytes");
 //            Otherwise every thread reads its blocks with 128-bit global loads.
 //   map2: [rows][64] int16 view of the coefficient arena, box 128 x 64
 //   map3: [rows/2][2][64] view (even/odd blocks) for the luma plane of 4:2:x
+//   d_counters: two zero-initialised words of device memory private to this launch
+//            group (dynamic tile claims; the kernel leaves them zero again), so one
+//            group must not run concurrently with itself.
 cudaError_t launch_fused(Layout layout, bool q8, bool use_tma, const CUtensorMap *map2,
                          const CUtensorMap *map3, const FrameDev *d_frames, const TileDesc *d_tiles,
-                         uint32_t ntiles, int num_sms, cudaStream_t stream);
+                         uint32_t ntiles, uint32_t *d_counters, int num_sms, cudaStream_t stream);
 
 // Generic path for one frame (any integer up-factors): pass 1 writes 8-bit
 // sample planes (f.samples), pass 2 upsamples + colour-converts.  `h_frame` is
