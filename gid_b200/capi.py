@@ -21,6 +21,7 @@ ERR_NAMES = {
 }
 OUT_RGB8 = 0
 OUT_BGR8_BOTTOM_UP = 1
+OUT_RGBA8 = 2
 FLAG_PACKED_ROWS = 0x100
 
 # every symbol include/gidcuda.h declares
@@ -199,9 +200,10 @@ class GidCuda:
         return out
 
     def reconstruct_rgb(self, desc: FrameDesc, planes: Sequence[np.ndarray]) -> np.ndarray:
-        """Same, cropped to (H, W, 3)."""
+        """Same, cropped to (H, W, 3) -- (H, W, 4) for the RGBA format."""
         rows = self.reconstruct(desc, planes)
-        return rows[:, :3 * desc.width].reshape(desc.height, desc.width, 3)
+        bpp = 4 if (desc.flags & 0xFF) == OUT_RGBA8 else 3
+        return rows[:, :bpp * desc.width].reshape(desc.height, desc.width, bpp)
 
     # -- device-resident plans ----------------------------------------------------
     def plan_create(self, descs: Sequence[FrameDesc], d_planes: Sequence[int],

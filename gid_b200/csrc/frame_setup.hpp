@@ -90,12 +90,13 @@ inline int make_geometry(std::string *err, const gidcuda_frame_desc *d, Geometry
   g->coef_bytes = off;
   g->sample_bytes = soff;
   g->out_format = (int)(d->flags & GIDCUDA_OUT_MASK);
-  if (g->out_format != (int)GIDCUDA_OUT_RGB8 && g->out_format != (int)GIDCUDA_OUT_BGR8_BOTTOM_UP)
+  if (g->out_format != (int)GIDCUDA_OUT_RGB8 && g->out_format != (int)GIDCUDA_OUT_BGR8_BOTTOM_UP &&
+      g->out_format != (int)GIDCUDA_OUT_RGBA8)
     return geo_fail(err, GIDCUDA_ERR_BAD_ARGUMENT, "unknown output format %d", g->out_format);
-  const size_t packed = (size_t)3 * d->width;
+  const size_t packed = (size_t)(g->out_format == (int)GIDCUDA_OUT_RGBA8 ? 4 : 3) * d->width;
   if (d->out_stride != 0) {
     if ((size_t)d->out_stride < packed)
-      return geo_fail(err, GIDCUDA_ERR_BAD_ARGUMENT, "out_stride %d < 3 * width", d->out_stride);
+      return geo_fail(err, GIDCUDA_ERR_BAD_ARGUMENT, "out_stride %d is smaller than a packed row", d->out_stride);
     g->stride = (size_t)d->out_stride;
   } else if (g->out_format == (int)GIDCUDA_OUT_BGR8_BOTTOM_UP) {
     g->stride = round_up(packed, 4);  // BMP rows, test/to_bmp.adb:94-102
@@ -145,6 +146,7 @@ inline void fill_frame_dev(const gidcuda_frame_desc *d, const Geometry &g, const
   f->q8 = g.q8 ? 1 : 0;
   f->flags = 0;
   if (g.stride % 8 == 0 && (reinterpret_cast<uintptr_t>(pixels) & 7u) == 0) f->flags |= FRAME_ALIGNED8;
+  if (g.stride % 16 == 0 && (reinterpret_cast<uintptr_t>(pixels) & 15u) == 0) f->flags |= FRAME_ALIGNED16;
 }
 
 }  // namespace gidk

@@ -27,11 +27,12 @@ namespace gidk {
 enum Layout : int { LAYOUT_GREY = 0, LAYOUT_444 = 1, LAYOUT_422 = 2, LAYOUT_420 = 3, LAYOUT_GENERIC = 4 };
 
 // Output pixel formats, = GIDCUDA_OUT_* of include/gidcuda.h
-enum OutFormat : int { OUT_RGB8 = 0, OUT_BGR8_BOTTOM_UP = 1 };
+enum OutFormat : int { OUT_RGB8 = 0, OUT_BGR8_BOTTOM_UP = 1, OUT_RGBA8 = 2 };
 
 // FrameDev::flags
 enum FrameFlags : uint32_t {
-  FRAME_ALIGNED8 = 1u,  // pixel base and stride are multiples of 8: rows of a block go out as 3 x 8 bytes
+  FRAME_ALIGNED8 = 1u,   // pixel base and stride are multiples of 8: rows of a block go out as 3 x 8 bytes
+  FRAME_ALIGNED16 = 2u,  // ... multiples of 16: RGBA rows of a block go out as 2 x 16 bytes
 };
 
 // Per-frame descriptor in device memory (one per image of a launch).
@@ -176,7 +177,7 @@ GID_HD void dequant_row(const u32x4 &w, const uint32_t *q, int &c0, int &c1, int
 //     those rows are not touched and the column pass runs its 3-input form
 //     (col_idct_lo3), otherwise the general column pass.
 // Dense data takes the general path everywhere; the result is the same either way.
-template <bool Q8>
+template <bool Q8, bool LO3>
 GID_HD void dequant_idct_sparse(bool active, const u32x4 (&raw)[8], const uint32_t *qw, u32x2 *dst, int dst_stride) {
   int b[64];
   uint32_t ac[8];
@@ -201,8 +202,14 @@ GID_HD void dequant_idct_sparse(bool active, const u32x4 (&raw)[8], const uint32
     }
   }
   // Clip + pack + store inside each variant: joining the two register sets first
-  // would cost a move per sample.
-  if (tall) {
+  // would cost a move per sample.  LO3 = false (4:2:x kernels, where chroma is a third
+  // of the blocks or less): the 3-input column pass is left out -- there its code
+  // costs more instruction-cache misses than it saves instructions (measured).
+  if (tall || !LO3) {
+    if (!LO3 && !tall) {
+#pragma unroll
+      for (int i = 24; i < 64; i++) b[i] = 0;
+    }
 #pragma unroll
     for (int c = 0; c < 8; c++)
       col_idct(b[c], b[8 + c], b[16 + c], b[24 + c], b[32 + c], b[40 + c], b[48 + c], b[56 + c]);
@@ -224,7 +231,7 @@ GID_HD void pack_block(const int (&b)[64], uint32_t (&p)[16]) {
 // Destination of pixel (x0, y): rows are flipped for the bottom-up format.
 GID_HD uint8_t *row_ptr(const FrameDev &f, int x0, int y) {
   const int yy = f.out_format == OUT_BGR8_BOTTOM_UP ? f.height - 1 - y : y;
-  return f.pixels + (size_t)yy * f.stride + (size_t)x0 * 3;
+  return f.pixels + (size_t)yy * f.stride + (size_t)x0 * (f.out_format == OUT_RGBA8 ? 4 : 3);
 }
 
 // Slow path: byte stores with clipping to the image (:1023, :1026); used for
@@ -257,6 +264,30 @@ GID_HD void store_row8(uint8_t *dst, bool fast, int nbytes, uint32_t w0, uint32_
   }
 }
 
+// RGBA: one row of 8 pixels = 8 words [R, G, B, 255].  Partial blocks write whole pixels.
+#if defined(__CUDACC__)
+static __host__ __device__ __noinline__
+#else
+inline
+#endif
+void store_row8_rgba_words(uint8_t *dst, int npix, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4,
+                           uint32_t w5, uint32_t w6, uint32_t w7) {
+  const uint32_t w[8] = {w0, w1, w2, w3, w4, w5, w6, w7};
+  for (int i = 0; i < npix; i++)
+    for (int k = 0; k < 4; k++) dst[4 * i + k] = (uint8_t)(w[i] >> (8 * k));
+}
+GID_HD void store_row8_rgba(uint8_t *dst, bool fast, int npix, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3,
+                            uint32_t w4, uint32_t w5, uint32_t w6, uint32_t w7) {
+  if (fast) {
+    u32x4 *d4 = reinterpret_cast<u32x4 *>(dst);
+    u32x4 v;
+    v.x = w0; v.y = w1; v.z = w2; v.w = w3; d4[0] = v;
+    v.x = w4; v.y = w5; v.z = w6; v.w = w7; d4[1] = v;
+  } else {
+    store_row8_rgba_words(dst, npix, w0, w1, w2, w3, w4, w5, w6, w7);
+  }
+}
+
 // Per-thread scratch for the packed 8-bit samples of the current MCU: 8 rows of
 // 8 bytes for Cb, Cr and the luma block being emitted.  On the device it lives
 // in shared memory as [row][lane] (row r of lane t at base[r * stride + t],
@@ -281,19 +312,24 @@ GID_HD int byte_of(uint32_t w) { return (int)prmt(w, 0u, 0x4440u + K); }
 //   sx, sy position of the block inside the MCU
 // The destination pointer walks down the image one row per step (up for the
 // bottom-up format); rows below the image (:1023) are skipped by count.
-template <int H, int V, bool GREY>
+//   RGBA   4 bytes per pixel (a separate instance, so that the 3-byte loop stays lean)
+template <int H, int V, bool GREY, bool RGBA>
 GID_HD void emit_block_rows(const FrameDev &f, const Scratch &sc, int x0, int y0, int sx, int sy) {
   if (x0 >= f.width) return;
-  int nbytes = (f.width - x0) * 3;
-  if (nbytes > 24) nbytes = 24;
-  const bool fast = (f.flags & FRAME_ALIGNED8) != 0 && nbytes == 24;
+  constexpr bool rgba = RGBA;
+  int npix = f.width - x0;
+  if (npix > 8) npix = 8;
+  const int nbytes = npix * 3;
+  const bool fast = (f.flags & (rgba ? FRAME_ALIGNED16 : FRAME_ALIGNED8)) != 0 && npix == 8;
   const bool bottom_up = f.out_format == OUT_BGR8_BOTTOM_UP;
   const ColourOrder co = colour_order(bottom_up);
   uint8_t *dst = row_ptr(f, x0, y0);
   const long long step = bottom_up ? -(long long)f.stride : (long long)f.stride;
   const int rows_left = f.height - y0;  // >= 1
   const int crow0 = sy * (8 / V);       // first row inside the chroma block
-#pragma unroll 2
+  // colour kernels: rolled (their hot loop is at the edge of the 32 KiB instruction cache; measured +3 %);
+  // grey: two rows per trip
+#pragma unroll(GREY ? 2 : 1)
   for (int i = 0; i < 8 / V; i++) {
     if (i * V >= rows_left) break;
     u32x2 cbc, crc;
@@ -317,7 +353,11 @@ GID_HD void emit_block_rows(const FrameDev &f, const Scratch &sc, int x0, int y0
     for (int ry = 0; ry < V; ry++) {
       if (V > 1 && i * V + ry >= rows_left) break;
       const u32x2 yv = sc.y[(i * V + ry) * sc.stride];
-      if (GREY) {
+      if (GREY && rgba) {
+        store_row8_rgba(dst, fast, npix, prmt(yv.x, 255u, 0x4000u), prmt(yv.x, 255u, 0x4111u), prmt(yv.x, 255u, 0x4222u),
+                        prmt(yv.x, 255u, 0x4333u), prmt(yv.y, 255u, 0x4000u), prmt(yv.y, 255u, 0x4111u),
+                        prmt(yv.y, 255u, 0x4222u), prmt(yv.y, 255u, 0x4333u));
+      } else if (GREY) {
         // R = G = B = Y (:1036-1038)
         store_row8(dst, fast, nbytes, prmt(yv.x, 0u, 0x1000u), prmt(yv.x, 0u, 0x2211u), prmt(yv.x, 0u, 0x3332u),
                    prmt(yv.y, 0u, 0x1000u), prmt(yv.y, 0u, 0x2211u), prmt(yv.y, 0u, 0x3332u));
@@ -332,9 +372,15 @@ GID_HD void emit_block_rows(const FrameDev &f, const Scratch &sc, int x0, int y0
           c1[c] = ys[c] + tt.g;
           c2[c] = ys[c] + tt.b;
         }
-        store_row8(dst, fast, nbytes, pack_sat4(c0[0], c1[0], c2[0], c0[1]), pack_sat4(c1[1], c2[1], c0[2], c1[2]),
-                   pack_sat4(c2[2], c0[3], c1[3], c2[3]), pack_sat4(c0[4], c1[4], c2[4], c0[5]),
-                   pack_sat4(c1[5], c2[5], c0[6], c1[6]), pack_sat4(c2[6], c0[7], c1[7], c2[7]));
+        if (rgba)
+          store_row8_rgba(dst, fast, npix, pack_sat4(c0[0], c1[0], c2[0], 255), pack_sat4(c0[1], c1[1], c2[1], 255),
+                          pack_sat4(c0[2], c1[2], c2[2], 255), pack_sat4(c0[3], c1[3], c2[3], 255),
+                          pack_sat4(c0[4], c1[4], c2[4], 255), pack_sat4(c0[5], c1[5], c2[5], 255),
+                          pack_sat4(c0[6], c1[6], c2[6], 255), pack_sat4(c0[7], c1[7], c2[7], 255));
+        else
+          store_row8(dst, fast, nbytes, pack_sat4(c0[0], c1[0], c2[0], c0[1]), pack_sat4(c1[1], c2[1], c0[2], c1[2]),
+                     pack_sat4(c2[2], c0[3], c1[3], c2[3]), pack_sat4(c0[4], c1[4], c2[4], c0[5]),
+                     pack_sat4(c1[5], c2[5], c0[6], c1[6]), pack_sat4(c2[6], c0[7], c1[7], c2[7]));
       }
       dst += step;
     }
@@ -345,7 +391,7 @@ GID_HD void emit_block_rows(const FrameDev &f, const Scratch &sc, int x0, int y0
 // single luma block for grey).  Each item: fetch 8 raw rows from the block
 // source, de-quantise, inverse DCT, clip + pack to bytes into the scratch; luma
 // blocks are then turned into pixels.
-template <int H, int V, bool GREY, bool Q8, class Src>
+template <int H, int V, bool GREY, bool Q8, bool RGBA, class Src>
 GID_HD void mcu_run(bool active, const FrameDev &f, const uint32_t *qw /* [3][32] */, Src &src,
                     const Scratch &sc, int mx, int my) {
   constexpr int NI = GREY ? 1 : 2 + H * V;
@@ -364,8 +410,8 @@ GID_HD void mcu_run(bool active, const FrameDev &f, const uint32_t *qw /* [3][32
     u32x4 raw[8];
     src.load(active, comp, bxi, byi, raw);
     u32x2 *dst = comp == 0 ? sc.y : (comp == 1 ? sc.cb : sc.cr);
-    dequant_idct_sparse<Q8>(active, raw, qw + 32 * comp, dst, sc.stride);
-    if (comp == 0 && active) emit_block_rows<H, V, GREY>(f, sc, bxi * 8, byi * 8, sx, sy);
+    dequant_idct_sparse<Q8, H * V == 1>(active, raw, qw + 32 * comp, dst, sc.stride);
+    if (comp == 0 && active) emit_block_rows<H, V, GREY, RGBA>(f, sc, bxi * 8, byi * 8, sx, sy);
   }
 }
 

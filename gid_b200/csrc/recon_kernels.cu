@@ -258,10 +258,10 @@ __device__ __forceinline__ Scratch make_scratch(uint8_t *base, uint32_t lane) {
   return sc;
 }
 
-template <int LAYOUT, bool Q8, class Src>
+template <int LAYOUT, bool Q8, bool RGBA, class Src>
 __device__ __forceinline__ void run_mcu(bool active, const FrameDev &f, Src &src, const Scratch &sc, int mx, int my) {
   using LI = LayoutInfo<LAYOUT>;
-  mcu_run<LI::H, LI::V, LAYOUT == LAYOUT_GREY, Q8>(active, f, &f.qw[0][0], src, sc, mx, my);
+  mcu_run<LI::H, LI::V, LAYOUT == LAYOUT_GREY, Q8, RGBA>(active, f, &f.qw[0][0], src, sc, mx, my);
 }
 
 // MCU (mx, my) of lane t in a tile starting at m0, or false when the lane has
@@ -288,7 +288,7 @@ __device__ __forceinline__ void cache_frame(uint8_t *dst, const FrameDev *src, u
   __syncwarp();
 }
 
-template <int LAYOUT, bool Q8>
+template <int LAYOUT, bool Q8, bool RGBA>
 __global__ void __launch_bounds__(kCtaThreads, kCtasPerSm)
 recon_tma_kernel(const __grid_constant__ CUtensorMap map2, const __grid_constant__ CUtensorMap map3,
                  const FrameDev *__restrict__ frames, const TileDesc *__restrict__ tiles, uint32_t ntiles,
@@ -334,14 +334,14 @@ recon_tma_kernel(const __grid_constant__ CUtensorMap map2, const __grid_constant
     }
     int mx, my;
     const bool active = tile_mcu<LAYOUT>(f, this_m0, lane, mx, my);
-    run_mcu<LAYOUT, Q8>(active, f, src, scratch, mx, my);
+    run_mcu<LAYOUT, Q8, RGBA>(active, f, src, scratch, mx, my);
   }
   src.claims.finish();
 }
 
 constexpr int kLdgWarps = 4;
 
-template <int LAYOUT, bool Q8>
+template <int LAYOUT, bool Q8, bool RGBA>
 __global__ void __launch_bounds__(kLdgWarps * 32)
 recon_ldg_kernel(const FrameDev *__restrict__ frames, const TileDesc *__restrict__ tiles, uint32_t ntiles) {
   __shared__ __align__(16) uint8_t s_frame[kLdgWarps][kFrameBytes];
@@ -356,7 +356,7 @@ recon_ldg_kernel(const FrameDev *__restrict__ frames, const TileDesc *__restrict
   int mx, my;
   const bool active = tile_mcu<LAYOUT>(f, m0, lane, mx, my);
   LdgSource src{&f};
-  run_mcu<LAYOUT, Q8>(active, f, src, make_scratch(s_scratch[warp], lane), mx, my);
+  run_mcu<LAYOUT, Q8, RGBA>(active, f, src, make_scratch(s_scratch[warp], lane), mx, my);
 }
 
 // ---- generic path -----------------------------------------------------------
@@ -429,13 +429,15 @@ generic_color_kernel(const FrameDev *__restrict__ frame, int ncomp, int hmax, in
     yy = f.height - 1 - y;
     const int t = r; r = b; b = t;
   }
-  uint8_t *dst = f.pixels + (size_t)yy * f.stride + (size_t)x * 3;
+  const bool rgba = f.out_format == OUT_RGBA8;
+  uint8_t *dst = f.pixels + (size_t)yy * f.stride + (size_t)x * (rgba ? 4 : 3);
   dst[0] = (uint8_t)r;
   dst[1] = (uint8_t)g;
   dst[2] = (uint8_t)b;
+  if (rgba) dst[3] = 255;
 }
 
-template <int LAYOUT, bool Q8>
+template <int LAYOUT, bool Q8, bool RGBA>
 cudaError_t launch_one(bool use_tma, const CUtensorMap *map2, const CUtensorMap *map3, const FrameDev *d_frames,
                        const TileDesc *d_tiles, uint32_t ntiles, uint32_t *d_counters, int num_sms,
                        cudaStream_t stream) {
@@ -443,53 +445,62 @@ cudaError_t launch_one(bool use_tma, const CUtensorMap *map2, const CUtensorMap 
     uint32_t grid = (uint32_t)(num_sms * kCtasPerSm);
     const uint32_t need = (ntiles + kWarpsPerCta - 1) / kWarpsPerCta;
     if (grid > need) grid = need;
-    recon_tma_kernel<LAYOUT, Q8><<<grid, kCtaThreads, kDynSmem, stream>>>(*map2, *map3, d_frames, d_tiles, ntiles,
-                                                                          d_counters);
+    recon_tma_kernel<LAYOUT, Q8, RGBA><<<grid, kCtaThreads, kDynSmem, stream>>>(*map2, *map3, d_frames, d_tiles,
+                                                                                ntiles, d_counters);
   } else {
-    recon_ldg_kernel<LAYOUT, Q8><<<(ntiles + kLdgWarps - 1) / kLdgWarps, kLdgWarps * 32, 0, stream>>>(d_frames, d_tiles, ntiles);
+    recon_ldg_kernel<LAYOUT, Q8, RGBA><<<(ntiles + kLdgWarps - 1) / kLdgWarps, kLdgWarps * 32, 0, stream>>>(
+        d_frames, d_tiles, ntiles);
   }
   return cudaGetLastError();
 }
 
 template <int LAYOUT>
-cudaError_t launch_q(bool q8, bool use_tma, const CUtensorMap *map2, const CUtensorMap *map3,
+cudaError_t launch_q(bool q8, bool rgba, bool use_tma, const CUtensorMap *map2, const CUtensorMap *map3,
                      const FrameDev *d_frames, const TileDesc *d_tiles, uint32_t ntiles, uint32_t *d_counters,
                      int num_sms, cudaStream_t stream) {
-  return q8 ? launch_one<LAYOUT, true>(use_tma, map2, map3, d_frames, d_tiles, ntiles, d_counters, num_sms, stream)
-            : launch_one<LAYOUT, false>(use_tma, map2, map3, d_frames, d_tiles, ntiles, d_counters, num_sms, stream);
+#define GIDK_ARGS use_tma, map2, map3, d_frames, d_tiles, ntiles, d_counters, num_sms, stream
+  if (q8) return rgba ? launch_one<LAYOUT, true, true>(GIDK_ARGS) : launch_one<LAYOUT, true, false>(GIDK_ARGS);
+  return rgba ? launch_one<LAYOUT, false, true>(GIDK_ARGS) : launch_one<LAYOUT, false, false>(GIDK_ARGS);
+#undef GIDK_ARGS
 }
 
-template <int LAYOUT, bool Q8>
+template <int LAYOUT, bool Q8, bool RGBA>
 cudaError_t set_attr() {
-  return cudaFuncSetAttribute(recon_tma_kernel<LAYOUT, Q8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem);
+  return cudaFuncSetAttribute(recon_tma_kernel<LAYOUT, Q8, RGBA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              kDynSmem);
+}
+template <int LAYOUT>
+cudaError_t set_attr_all() {
+  cudaError_t e;
+  if ((e = set_attr<LAYOUT, true, false>()) != cudaSuccess) return e;
+  if ((e = set_attr<LAYOUT, false, false>()) != cudaSuccess) return e;
+  if ((e = set_attr<LAYOUT, true, true>()) != cudaSuccess) return e;
+  return set_attr<LAYOUT, false, true>();
 }
 
 }  // namespace
 
 cudaError_t init_kernels() {
   cudaError_t e;
-  if ((e = set_attr<LAYOUT_GREY, true>()) != cudaSuccess) return e;
-  if ((e = set_attr<LAYOUT_GREY, false>()) != cudaSuccess) return e;
-  if ((e = set_attr<LAYOUT_444, true>()) != cudaSuccess) return e;
-  if ((e = set_attr<LAYOUT_444, false>()) != cudaSuccess) return e;
-  if ((e = set_attr<LAYOUT_422, true>()) != cudaSuccess) return e;
-  if ((e = set_attr<LAYOUT_422, false>()) != cudaSuccess) return e;
-  if ((e = set_attr<LAYOUT_420, true>()) != cudaSuccess) return e;
-  if ((e = set_attr<LAYOUT_420, false>()) != cudaSuccess) return e;
-  return cudaSuccess;
+  if ((e = set_attr_all<LAYOUT_GREY>()) != cudaSuccess) return e;
+  if ((e = set_attr_all<LAYOUT_444>()) != cudaSuccess) return e;
+  if ((e = set_attr_all<LAYOUT_422>()) != cudaSuccess) return e;
+  return set_attr_all<LAYOUT_420>();
 }
 
-cudaError_t launch_fused(Layout layout, bool q8, bool use_tma, const CUtensorMap *map2, const CUtensorMap *map3,
-                         const FrameDev *d_frames, const TileDesc *d_tiles, uint32_t ntiles, uint32_t *d_counters,
-                         int num_sms, cudaStream_t stream) {
+cudaError_t launch_fused(Layout layout, bool q8, bool rgba, bool use_tma, const CUtensorMap *map2,
+                         const CUtensorMap *map3, const FrameDev *d_frames, const TileDesc *d_tiles, uint32_t ntiles,
+                         uint32_t *d_counters, int num_sms, cudaStream_t stream) {
   if (ntiles == 0) return cudaSuccess;
+#define GIDK_ARGS q8, rgba, use_tma, map2, map3, d_frames, d_tiles, ntiles, d_counters, num_sms, stream
   switch (layout) {
-    case LAYOUT_GREY: return launch_q<LAYOUT_GREY>(q8, use_tma, map2, map3, d_frames, d_tiles, ntiles, d_counters, num_sms, stream);
-    case LAYOUT_444: return launch_q<LAYOUT_444>(q8, use_tma, map2, map3, d_frames, d_tiles, ntiles, d_counters, num_sms, stream);
-    case LAYOUT_422: return launch_q<LAYOUT_422>(q8, use_tma, map2, map3, d_frames, d_tiles, ntiles, d_counters, num_sms, stream);
-    case LAYOUT_420: return launch_q<LAYOUT_420>(q8, use_tma, map2, map3, d_frames, d_tiles, ntiles, d_counters, num_sms, stream);
+    case LAYOUT_GREY: return launch_q<LAYOUT_GREY>(GIDK_ARGS);
+    case LAYOUT_444: return launch_q<LAYOUT_444>(GIDK_ARGS);
+    case LAYOUT_422: return launch_q<LAYOUT_422>(GIDK_ARGS);
+    case LAYOUT_420: return launch_q<LAYOUT_420>(GIDK_ARGS);
     default: return cudaErrorInvalidValue;
   }
+#undef GIDK_ARGS
 }
 
 cudaError_t launch_generic(const FrameDev &h, const FrameDev *d_frame, cudaStream_t stream) {

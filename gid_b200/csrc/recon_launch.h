@@ -34,7 +34,8 @@ static_assert(sizeof(TileDesc) == 32, "TileDesc is 32 bytes");
 //   d_counters: two zero-initialised words of device memory private to this launch
 //            group (dynamic tile claims; the kernel leaves them zero again), so one
 //            group must not run concurrently with itself.
-cudaError_t launch_fused(Layout layout, bool q8, bool use_tma, const CUtensorMap *map2,
+//   rgba:    4-byte pixels (a separate kernel instance: the 3-byte kernels do not carry its code)
+cudaError_t launch_fused(Layout layout, bool q8, bool rgba, bool use_tma, const CUtensorMap *map2,
                          const CUtensorMap *map3, const FrameDev *d_frames, const TileDesc *d_tiles,
                          uint32_t ntiles, uint32_t *d_counters, int num_sms, cudaStream_t stream);
 

@@ -52,9 +52,11 @@ enum {
  * test/benchmark.adb:67-81 and test/mini.adb:55-69 build with Put_Pixel. */
 #define GIDCUDA_OUT_RGB8 0u      /* top-down, 3 bytes per pixel: R, G, B */
 #define GIDCUDA_OUT_BGR8_BOTTOM_UP 1u /* test/to_bmp.adb:94-146: bottom-up B, G, R, rows padded to 4 bytes */
+#define GIDCUDA_OUT_RGBA8 2u     /* top-down R, G, B, A; A = 255 = the alpha GID passes to Put_Pixel
+                                    (Primary_Color_Range'Last, gid-decoding_jpg.adb:909-938) */
 #define GIDCUDA_OUT_MASK 0xFFu
 /* Force stride = 3 * width (no row padding) for RGB8 even when that makes rows
- * unaligned; the default stride is 3 * width rounded up to 16 bytes. */
+ * unaligned; the default stride is the packed row (3 or 4 bytes per pixel) rounded up to 16 bytes. */
 #define GIDCUDA_FLAG_PACKED_ROWS 0x100u
 
 /* One JPEG frame, as the entropy decoder knows it after SOF/DQT/SOS
@@ -130,7 +132,9 @@ int gidcuda_plan_create(gidcuda_ctx *ctx, int32_t n, const gidcuda_frame_desc *d
                         uint8_t *const *d_pixels /* [n] device pointers */,
                         gidcuda_plan **plan);
 /* Launch on the given CUDA stream (cudaStream_t as void*; NULL = context stream).
- * Asynchronous. */
+ * Asynchronous.  Launches of one plan are ordered one after the other: do not
+ * run a plan concurrently with itself on two streams (its kernels share the
+ * plan's tile counters). */
 int gidcuda_plan_launch(gidcuda_plan *plan, void *cuda_stream);
 /* Number of kernel launches one gidcuda_plan_launch performs. */
 int gidcuda_plan_launch_count(const gidcuda_plan *plan);

@@ -60,8 +60,10 @@ extern "C" int emu_reconstruct(const gidcuda_frame_desc *desc, const int16_t *co
         }
         int yy = y;
         if (f.out_format == OUT_BGR8_BOTTOM_UP) { yy = f.height - 1 - y; int t = r; r = b; b = t; }
-        uint8_t *dst = f.pixels + (size_t)yy * f.stride + (size_t)x * 3;
+        const bool rgba = f.out_format == OUT_RGBA8;
+        uint8_t *dst = f.pixels + (size_t)yy * f.stride + (size_t)x * (rgba ? 4 : 3);
         dst[0] = (uint8_t)r; dst[1] = (uint8_t)gg; dst[2] = (uint8_t)b;
+        if (rgba) dst[3] = 255;
       }
     return 0;
   }
@@ -73,12 +75,21 @@ extern "C" int emu_reconstruct(const gidcuda_frame_desc *desc, const int16_t *co
       const uint32_t m = (tile - f.tile_base) * kTileMcusSetup + t;
       if (m >= (uint32_t)(f.mcux * f.mcuy)) continue;
       const int my = (int)(m / (uint32_t)f.mcux), mx = (int)(m - (uint32_t)my * f.mcux);
+      const bool rgba = f.out_format == OUT_RGBA8;
+#define EMU_RUN(H, V, GREY)                                                                      \
+  do {                                                                                           \
+    if (f.q8) { if (rgba) mcu_run<H, V, GREY, true, true>(true, f, qw, src, sc, mx, my);          \
+                else mcu_run<H, V, GREY, true, false>(true, f, qw, src, sc, mx, my); }            \
+    else { if (rgba) mcu_run<H, V, GREY, false, true>(true, f, qw, src, sc, mx, my);              \
+           else mcu_run<H, V, GREY, false, false>(true, f, qw, src, sc, mx, my); }                \
+  } while (0)
       switch (g.layout) {
-        case LAYOUT_GREY: f.q8 ? mcu_run<1, 1, true, true>(true, f, qw, src, sc, mx, my) : mcu_run<1, 1, true, false>(true, f, qw, src, sc, mx, my); break;
-        case LAYOUT_444: f.q8 ? mcu_run<1, 1, false, true>(true, f, qw, src, sc, mx, my) : mcu_run<1, 1, false, false>(true, f, qw, src, sc, mx, my); break;
-        case LAYOUT_422: f.q8 ? mcu_run<2, 1, false, true>(true, f, qw, src, sc, mx, my) : mcu_run<2, 1, false, false>(true, f, qw, src, sc, mx, my); break;
-        default: f.q8 ? mcu_run<2, 2, false, true>(true, f, qw, src, sc, mx, my) : mcu_run<2, 2, false, false>(true, f, qw, src, sc, mx, my); break;
+        case LAYOUT_GREY: EMU_RUN(1, 1, true); break;
+        case LAYOUT_444: EMU_RUN(1, 1, false); break;
+        case LAYOUT_422: EMU_RUN(2, 1, false); break;
+        default: EMU_RUN(2, 2, false); break;
       }
+#undef EMU_RUN
     }
   return 0;
 }

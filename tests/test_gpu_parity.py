@@ -20,6 +20,9 @@ def _check(gpu, oracle, fr, flags=0, out_stride=0):
     got = gpu.reconstruct_rgb(d, fr.planes)
     if (flags & 0xFF) == capi.OUT_BGR8_BOTTOM_UP:
         got = got[::-1, :, ::-1]
+    if (flags & 0xFF) == capi.OUT_RGBA8:
+        assert (got[:, :, 3] == 255).all()
+        got = got[:, :, :3]
     assert got.shape == ref.shape
     if not np.array_equal(got, ref):
         bad = np.argwhere(got != ref)
@@ -92,6 +95,9 @@ def test_output_formats_and_strides(gpu, oracle, synth, samp):
     _check(gpu, oracle, fr, flags=capi.OUT_BGR8_BOTTOM_UP)       # to_bmp layout
     _check(gpu, oracle, fr, out_stride=3 * 211 + 29)             # odd caller-chosen stride
     _check(gpu, oracle, fr, out_stride=1024)
+    _check(gpu, oracle, fr, flags=capi.OUT_RGBA8)                # R, G, B, 255
+    _check(gpu, oracle, fr, flags=capi.OUT_RGBA8 | capi.FLAG_PACKED_ROWS)
+    _check(gpu, oracle, fr, flags=capi.OUT_RGBA8, out_stride=4 * 211 + 4)
 
 
 def test_job_recycling_and_state_errors(gpu, oracle, synth):
@@ -142,18 +148,49 @@ def test_plan_device_resident_batch(gpu, oracle, synth):
     plan = gpu.plan_create(descs, d_planes, d_pixels)
     assert gpu.plan_launch_count(plan) == 4 + 2  # grey, 444, 422, 420 fused + generic (2 passes)
     assert gpu.plan_uses_tma(plan) == 4          # torch allocations are 512-byte aligned
-    gpu.plan_launch(plan, torch.cuda.current_stream().cuda_stream)
-    torch.cuda.synchronize()
-    k = 0
-    for fr, d in zip(frames, descs):
-        stride, _ = gpu.output_geometry(d)
-        while keep[k].dtype != torch.uint8:
+    refs = [oracle.reconstruct(fr) for fr in frames]
+    # the same plan launched several times back to back: the kernels hand out tiles through
+    # launch-wide counters that the last warp resets, so every launch must be complete
+    for rep in range(4):
+        for t in keep:
+            if t.dtype == torch.uint8:
+                t.zero_()
+        gpu.plan_launch(plan, torch.cuda.current_stream().cuda_stream)
+        if rep == 2:  # and once without any host synchronisation in between
+            gpu.plan_launch(plan, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        k = 0
+        for fr, d, ref in zip(frames, descs, refs):
+            stride, _ = gpu.output_geometry(d)
+            while keep[k].dtype != torch.uint8:
+                k += 1
+            rows = keep[k].cpu().numpy().reshape(fr.height, stride)
             k += 1
-        rows = keep[k].cpu().numpy().reshape(fr.height, stride)
-        k += 1
-        got = rows[:, :3 * fr.width].reshape(fr.height, fr.width, 3)
-        assert np.array_equal(got, oracle.reconstruct(fr))
+            got = rows[:, :3 * fr.width].reshape(fr.height, fr.width, 3)
+            assert np.array_equal(got, ref), rep
     gpu.plan_destroy(plan)
+
+
+def test_job_resubmission(gpu, oracle, synth):
+    """A job submitted again after wait (what bench.py's e2e leg does) reconstructs again, also
+    after its planes were rewritten in place."""
+    a = synth.planes_only(pixels_for(synth, 61, 1000, 700, "420"), "420")
+    b = synth.planes_only(pixels_for(synth, 62, 1000, 700, "420"), "420")
+    L = gpu.lib
+    job = ctypes.c_void_p()
+    d = frame_desc(a)
+    assert L.gidcuda_job_begin(gpu.ctx, ctypes.byref(d), ctypes.byref(job)) == 0
+    pix, st = ctypes.c_void_p(), ctypes.c_size_t()
+    for rep, fr in enumerate((a, a, b, a)):
+        for c in range(fr.ncomp):
+            p = L.gidcuda_job_plane(job, c, None, None)
+            ctypes.memmove(p, fr.planes[c].ctypes.data, fr.planes[c].nbytes)
+        assert L.gidcuda_job_submit(job) == 0
+        assert L.gidcuda_job_wait(job, ctypes.byref(pix), ctypes.byref(st)) == 0
+        rows = np.frombuffer((ctypes.c_uint8 * (st.value * fr.height)).from_address(pix.value), dtype=np.uint8)
+        got = rows.reshape(fr.height, st.value)[:, :3 * fr.width].reshape(fr.height, fr.width, 3)
+        assert np.array_equal(got, oracle.reconstruct(fr)), rep
+    assert L.gidcuda_job_release(job) == 0
 
 
 def test_batch_driver(oracle, synth, gidcuda_lib):

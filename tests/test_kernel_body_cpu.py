@@ -23,7 +23,12 @@ def _check(emu, oracle, lib, fr, flags=0, out_stride=0):
     ref = oracle.reconstruct(fr)
     d = frame_desc(fr, flags, out_stride)
     rows = emu.reconstruct(d, fr.planes, _stride(lib, d), fr.height)
-    got = rows[:, :3 * fr.width].reshape(fr.height, fr.width, 3)
+    if (flags & 0xFF) == capi.OUT_RGBA8:
+        got = rows[:, :4 * fr.width].reshape(fr.height, fr.width, 4)
+        assert (got[:, :, 3] == 255).all()
+        got = got[:, :, :3]
+    else:
+        got = rows[:, :3 * fr.width].reshape(fr.height, fr.width, 3)
     if (flags & 0xFF) == capi.OUT_BGR8_BOTTOM_UP:
         got = got[::-1, :, ::-1]
     assert np.array_equal(got, ref)
@@ -67,6 +72,8 @@ def test_output_formats_and_strides(emu, oracle, synth, gidcuda_lib, samp):
     _check(emu, oracle, gidcuda_lib, fr, flags=capi.FLAG_PACKED_ROWS)
     _check(emu, oracle, gidcuda_lib, fr, flags=capi.OUT_BGR8_BOTTOM_UP)
     _check(emu, oracle, gidcuda_lib, fr, out_stride=3 * 211 + 29)
+    _check(emu, oracle, gidcuda_lib, fr, flags=capi.OUT_RGBA8)
+    _check(emu, oracle, gidcuda_lib, fr, flags=capi.OUT_RGBA8, out_stride=4 * 211 + 4)
 
 
 def test_idct_blocks_match_oracle(emu, oracle):
