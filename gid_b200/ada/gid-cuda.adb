@@ -82,6 +82,11 @@ package body GID.CUDA is
     return a;
   end Plane;
 
+  procedure Hint_Rows (j : Job; comp : Natural; rows_used : Positive) is
+  begin
+    Check (gidcuda_job_hint_rows (j, C.int (comp), C.int (rows_used)), Null_Context);
+  end Hint_Rows;
+
   procedure Submit (j : Job) is
   begin
     Check (gidcuda_job_submit (j), Null_Context);

@@ -71,6 +71,9 @@ private package GID.CUDA is
   function Plane
     (j : Job; comp : Natural; blocks_x, blocks_y : out Natural) return System.Address;
 
+  --  Promise that rows >= rows_used of every block of the plane are zero (1 .. 8).
+  procedure Hint_Rows (j : Job; comp : Natural; rows_used : Positive);
+
   procedure Submit (j : Job);   --  asynchronous: H2D, kernel, D2H
   procedure Wait   (j : Job; pixels : out System.Address; stride : out Natural);
   procedure Release (j : in out Job);
@@ -104,6 +107,9 @@ private
     (j : Job; comp : C.int;
      blocks_x, blocks_y : access Interfaces.Integer_32) return System.Address;
   pragma Import (C, gidcuda_job_plane, "gidcuda_job_plane");
+
+  function gidcuda_job_hint_rows (j : Job; comp, rows_used : C.int) return C.int;
+  pragma Import (C, gidcuda_job_hint_rows, "gidcuda_job_hint_rows");
 
   function gidcuda_job_submit (j : Job) return C.int;
   pragma Import (C, gidcuda_job_submit, "gidcuda_job_submit");

@@ -27,6 +27,7 @@
     cuda_job   : GID.CUDA.Job     := GID.CUDA.Null_Job;
     plane      : array (Component) of Plane_Info;
     comp_index : array (Component) of Natural := (others => 0);  --  Y -> 0, Cb -> 1, Cr -> 2
+    last_row   : array (Component) of Natural := (others => 0);  --  last block row a coefficient was stored in
 
     --  Called once from Read_SOS, after the MCU geometry is known (:1974) and before
     --  the first scan is decoded.  Replaces Create_Image_Array (:1857-1883) too: the
@@ -86,6 +87,7 @@
         pragma Import (Ada, cell);
       begin
         cell := Interfaces.Integer_16 (v);  --  planes were zeroed by Job_Begin
+        last_row (c) := Natural'Max (last_row (c), nat / 8);
       end Store;
     begin
       Get_VLC (image.JPEG_stuff.vlc_defs (DC, info_B (c).ht_idx_DC).all, code, value);
@@ -116,6 +118,11 @@
       pixels : System.Address;
       stride : Natural;
     begin
+      for c in Component loop
+        if image.JPEG_stuff.compo_set (c) then
+          GID.CUDA.Hint_Rows (cuda_job, comp_index (c), last_row (c) + 1);
+        end if;
+      end loop;
       GID.CUDA.Submit (cuda_job);
       GID.CUDA.Wait (cuda_job, pixels, stride);
       declare

@@ -28,7 +28,7 @@ FLAG_PACKED_ROWS = 0x100
 EXPORTS = [
     "gidcuda_abi_version", "gidcuda_device_count", "gidcuda_last_error", "gidcuda_set_option", "gidcuda_create",
     "gidcuda_destroy", "gidcuda_plane_geometry", "gidcuda_output_geometry", "gidcuda_job_begin",
-    "gidcuda_job_plane", "gidcuda_job_submit", "gidcuda_job_wait", "gidcuda_job_release",
+    "gidcuda_job_plane", "gidcuda_job_hint_rows", "gidcuda_job_submit", "gidcuda_job_wait", "gidcuda_job_release",
     "gidcuda_plan_create", "gidcuda_plan_launch", "gidcuda_plan_launch_count", "gidcuda_plan_uses_tma",
     "gidcuda_plan_destroy", "gidcuda_synchronize", "gidcuda_batch_create", "gidcuda_batch_run",
     "gidcuda_batch_destroy", "gidcuda_host_alloc", "gidcuda_host_free",
@@ -106,6 +106,7 @@ def load_library() -> ctypes.CDLL:
     L.gidcuda_job_begin.argtypes = [vp, ctypes.POINTER(FrameDesc), ctypes.POINTER(vp)]
     L.gidcuda_job_plane.restype = vp
     L.gidcuda_job_plane.argtypes = [vp, ctypes.c_int, i32p, i32p]
+    L.gidcuda_job_hint_rows.argtypes = [vp, ctypes.c_int, ctypes.c_int]
     L.gidcuda_job_submit.argtypes = [vp]
     L.gidcuda_job_wait.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t)]
     L.gidcuda_job_release.argtypes = [vp]
@@ -134,6 +135,12 @@ def set_option(name: str, value: int) -> None:
     rc = L.gidcuda_set_option(name.encode(), value)
     if rc != GIDCUDA_OK:
         raise GidCudaError(rc, (L.gidcuda_last_error(None) or b"").decode())
+
+
+def rows_used(plane: np.ndarray) -> int:
+    """1 + the last block row (natural order) holding a non-zero coefficient anywhere in the plane."""
+    nz = np.flatnonzero(np.asarray(plane).reshape(-1, 8, 8).any(axis=(0, 2)))
+    return int(nz[-1]) + 1 if nz.size else 1
 
 
 class GidCuda:
@@ -175,8 +182,9 @@ class GidCuda:
         return st.value, nb.value
 
     # -- one frame through the job API (host buffers, H2D + kernel + D2H) -----------
-    def reconstruct(self, desc: FrameDesc, planes: Sequence[np.ndarray]) -> np.ndarray:
-        """planes[c]: (by, bx, 64) int16.  Returns the pixel rows as (H, stride) uint8."""
+    def reconstruct(self, desc: FrameDesc, planes: Sequence[np.ndarray], hint_rows: bool = False) -> np.ndarray:
+        """planes[c]: (by, bx, 64) int16.  Returns the pixel rows as (H, stride) uint8.
+        hint_rows: tell the library which block rows are empty (gidcuda_job_hint_rows)."""
         job = ctypes.c_void_p()
         self._check(self.lib.gidcuda_job_begin(self.ctx, ctypes.byref(desc), ctypes.byref(job)), self.ctx)
         try:
@@ -190,6 +198,8 @@ class GidCuda:
                     raise ValueError(f"plane {c}: {src.size} coefficients, expected "
                                      f"{bx.value * by.value * 64}")
                 ctypes.memmove(p, src.ctypes.data, src.nbytes)
+                if hint_rows:
+                    self._check(self.lib.gidcuda_job_hint_rows(job, c, rows_used(src)), self.ctx)
             self._check(self.lib.gidcuda_job_submit(job), self.ctx)
             pix, stride = ctypes.c_void_p(), ctypes.c_size_t()
             self._check(self.lib.gidcuda_job_wait(job, ctypes.byref(pix), ctypes.byref(stride)), self.ctx)
@@ -199,9 +209,9 @@ class GidCuda:
             self._check(self.lib.gidcuda_job_release(job), self.ctx)
         return out
 
-    def reconstruct_rgb(self, desc: FrameDesc, planes: Sequence[np.ndarray]) -> np.ndarray:
+    def reconstruct_rgb(self, desc: FrameDesc, planes: Sequence[np.ndarray], hint_rows: bool = False) -> np.ndarray:
         """Same, cropped to (H, W, 3) -- (H, W, 4) for the RGBA format."""
-        rows = self.reconstruct(desc, planes)
+        rows = self.reconstruct(desc, planes, hint_rows)
         bpp = 4 if (desc.flags & 0xFF) == OUT_RGBA8 else 3
         return rows[:, :bpp * desc.width].reshape(desc.height, desc.width, bpp)
 

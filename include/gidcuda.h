@@ -112,6 +112,14 @@ int gidcuda_job_begin(gidcuda_ctx *ctx, const gidcuda_frame_desc *desc, gidcuda_
  * de-quantised.  The entropy decoder stores dc_predictor / value at
  * zig_zag(k) (:771, :785) or the progressive accumulators (:1339, :1615). */
 int16_t *gidcuda_job_plane(gidcuda_job *job, int comp, int32_t *blocks_x, int32_t *blocks_y);
+/* Optional promise from the entropy decoder: in EVERY block of plane comp the
+ * coefficients of rows >= rows_used (natural index >= 8 * rows_used) are zero.
+ * The library then does not move those rows over the host link (a frame's planes
+ * are 6 bytes per pixel as int16, twice its pixels; at ordinary qualities the lower
+ * half of every chroma block is empty).  rows_used = 1 .. 8; 8 (the state after
+ * gidcuda_job_begin) promises nothing.  Holds until changed or the job is released.
+ * A decoder tracks it for free: rows_used = 1 + (largest zig_zag(k) it stored) / 8. */
+int gidcuda_job_hint_rows(gidcuda_job *job, int comp, int rows_used);
 /* Asynchronous: host-to-device copies, reconstruction kernel, device-to-host
  * copy of the pixels, all on the job's own stream (two jobs in flight overlap
  * their transfers).  A job may be submitted again after gidcuda_job_wait. */

@@ -171,6 +171,37 @@ def test_plan_device_resident_batch(gpu, oracle, synth):
     gpu.plan_destroy(plan)
 
 
+@pytest.mark.parametrize("samp", ["444", "420", "grey", "440"])
+def test_row_hints(gpu, oracle, synth, samp):
+    """gidcuda_job_hint_rows: planes whose lower block rows are empty travel as pitched copies;
+    the result must not change, also when a recycled job switches between hinted and full
+    planes (the device copy of the skipped rows has to be zero, not stale)."""
+    from gid_b200 import capi
+    # planes of at least 8 MiB: smaller ones are always copied whole
+    W, H = (2304, 1296) if samp != "grey" else (3072, 3072)
+    if samp in ("420", "440"):
+        W, H = 4096, 2304
+    fr = synth.planes_only(pixels_for(synth, 70, W, H, samp), samp)
+    dense = synth.planes_only(pixels_for(synth, 71, W, H, samp), samp)
+    rng = np.random.default_rng(3)
+    dense.planes = [rng.integers(-40, 41, size=p.shape).astype(np.int16) for p in dense.planes]
+    sparse = synth.planes_only(pixels_for(synth, 72, W, H, samp), samp)
+    for p in sparse.planes:
+        p[:, :, 16:] = 0          # rows 2 .. 7 empty everywhere
+    assert all(capi.rows_used(p) <= 2 for p in sparse.planes)
+    for f in (fr, dense, sparse, fr, sparse, dense, sparse):
+        got = gpu.reconstruct_rgb(frame_desc(f), f.planes, hint_rows=True)
+        assert np.array_equal(got, oracle.reconstruct(f))
+    # a wrong component / row count is rejected
+    L = gpu.lib
+    job = ctypes.c_void_p()
+    d = frame_desc(fr)
+    assert L.gidcuda_job_begin(gpu.ctx, ctypes.byref(d), ctypes.byref(job)) == 0
+    assert L.gidcuda_job_hint_rows(job, 0, 0) == -1 and L.gidcuda_job_hint_rows(job, 3, 4) == -1
+    assert L.gidcuda_job_hint_rows(job, 0, 4) == 0
+    assert L.gidcuda_job_release(job) == 0
+
+
 def test_job_resubmission(gpu, oracle, synth):
     """A job submitted again after wait (what bench.py's e2e leg does) reconstructs again, also
     after its planes were rewritten in place."""

@@ -1,10 +1,10 @@
 #!/bin/bash
-# bench lines only (no tests): tools/bench_quick.sh tag [steps] [workloads...]
-tag=${1:-q}; steps=${2:-50}; shift; shift
+# bench lines only (no tests): tools/bench_quick.sh tag steps "extra bench args" [workloads...]
+tag=${1:-q}; steps=${2:-50}; extra=${3:-}; shift; shift; shift
 wl=${@:-cfg2 cfg3 cfg4 cfg5}
 mkdir -p gpurun_out; : > gpurun_out/${tag}_bench.jsonl
 for w in $wl; do
-  python bench.py --workload $w --steps $steps --warmup 5 --no-cpu >> gpurun_out/${tag}_bench.jsonl 2> gpurun_out/${tag}_bench_$w.err || tail -n 5 gpurun_out/${tag}_bench_$w.err
+  python bench.py --workload $w --steps $steps --warmup 5 --no-cpu $extra >> gpurun_out/${tag}_bench.jsonl 2> gpurun_out/${tag}_bench_$w.err || tail -n 5 gpurun_out/${tag}_bench_$w.err
 done
 python - <<PY
 import json
