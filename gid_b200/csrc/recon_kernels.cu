@@ -30,27 +30,34 @@ namespace {
 constexpr int kFrameWords = (int)(sizeof(FrameDev) / sizeof(uint32_t));
 static_assert(sizeof(FrameDev) % 16 == 0, "FrameDev is copied in 16-byte pieces");
 
-// Warps are assigned to the four SM sub-partitions round-robin inside a CTA, so
-// the warp count per CTA must spread evenly over them (5 warps per CTA put 6 of
-// 15 warps on one scheduler and cost 20 %: measured, profiles/r01c).
-#ifndef GIDK_WARPS_PER_CTA
-#define GIDK_WARPS_PER_CTA 15
-#define GIDK_CTAS_PER_SM 1
-#endif
-constexpr int kWarpsPerCta = GIDK_WARPS_PER_CTA;
-constexpr int kCtasPerSm = GIDK_CTAS_PER_SM;
-constexpr int kCtaThreads = kWarpsPerCta * 32;
+// CTA shapes.  Warps are assigned to the four SM sub-partitions round-robin inside
+// a CTA, so the warp count per CTA must spread evenly over them (5 warps per CTA
+// put 6 of 15 warps on one scheduler and cost 20 %: measured, profiles/r01c).
+//   Wide  : 1 CTA x 15 warps per SM -- the most warps shared memory allows; best for
+//           launches with many tiles per warp (batches).
+//   Narrow: 3 CTAs x 4 warps per SM -- SMs are handed to the next launch a CTA at a
+//           time, which shortens tail + ramp of short launches (one frame): +3 %.
+template <int WPC> struct Shape {
+  static_assert(WPC == 15 || WPC == 4, "supported CTA shapes");
+  static constexpr int kWarps = WPC;
+  static constexpr int kCtasPerSm = WPC == 15 ? 1 : 3;
+  static constexpr int kThreads = WPC * 32;
+};
 constexpr int kNumSlots = 2;
 constexpr int kSlotBytes = kTileMcus * 128;            // one block (64 x int16) per lane
 constexpr int kRingBytes = kNumSlots * kSlotBytes;
 constexpr int kScratchBytes = 3 * 8 * kTileMcus * 8;   // per warp: [3 planes][8 rows][32 lanes] x 8 bytes
 constexpr int kFrameBytes = (int)((sizeof(FrameDev) + 127) / 128 * 128);
-// dynamic shared memory of one CTA: rings (1024-byte aligned), scratches, frame caches, barriers
-constexpr int kOffScratch = kWarpsPerCta * kRingBytes;
-constexpr int kOffFrame = kOffScratch + kWarpsPerCta * kScratchBytes;
-constexpr int kOffBars = kOffFrame + kWarpsPerCta * kFrameBytes;
 constexpr int kBarBytes = kNumSlots * 8 + 64;  // per warp: the slot barriers + the ring of claimed tiles (4 x uint4)
-constexpr int kDynSmem = kOffBars + kWarpsPerCta * kBarBytes + 1024;  // + slack for the alignment
+// dynamic shared memory of one CTA: rings (1024-byte aligned), scratches, frame caches, barriers
+template <int WPC> struct SmemLayout {
+  static constexpr int kOffScratch = WPC * kRingBytes;
+  static constexpr int kOffFrame = kOffScratch + WPC * kScratchBytes;
+  static constexpr int kOffBars = kOffFrame + WPC * kFrameBytes;
+  static constexpr int kBytes = kOffBars + WPC * kBarBytes + 1024;  // + slack for the alignment
+};
+// launches with fewer tiles than this per resident warp use the narrow shape
+constexpr uint32_t kNarrowBelowTilesPerWarp = 6;
 static_assert(kTileMcus == 32, "one tile per warp");
 
 template <int LAYOUT> struct LayoutInfo;
@@ -288,14 +295,16 @@ __device__ __forceinline__ void cache_frame(uint8_t *dst, const FrameDev *src, u
   __syncwarp();
 }
 
-template <int LAYOUT, bool Q8, bool RGBA>
-__global__ void __launch_bounds__(kCtaThreads, kCtasPerSm)
+template <int LAYOUT, bool Q8, bool RGBA, int WPC>
+__global__ void __launch_bounds__(Shape<WPC>::kThreads, Shape<WPC>::kCtasPerSm)
 recon_tma_kernel(const __grid_constant__ CUtensorMap map2, const __grid_constant__ CUtensorMap map3,
                  const FrameDev *__restrict__ frames, const TileDesc *__restrict__ tiles, uint32_t ntiles,
                  uint32_t *__restrict__ counters) {
   extern __shared__ uint8_t dyn_smem[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t nwarps = gridDim.x * kWarpsPerCta;
+  constexpr int kOffScratch = SmemLayout<WPC>::kOffScratch, kOffFrame = SmemLayout<WPC>::kOffFrame,
+                kOffBars = SmemLayout<WPC>::kOffBars;
+  const uint32_t nwarps = gridDim.x * WPC;
 
   const uint32_t base = (smem_u32(dyn_smem) + 1023u) & ~1023u;
   uint8_t *gen = dyn_smem + (base - smem_u32(dyn_smem));
@@ -310,7 +319,7 @@ recon_tma_kernel(const __grid_constant__ CUtensorMap map2, const __grid_constant
   src.ntiles = ntiles;
   src.claims.counters = counters;
   src.claims.pending = 0;
-  src.claims.gw = blockIdx.x * kWarpsPerCta + warp;
+  src.claims.gw = blockIdx.x * WPC + warp;
   src.claims.nwarps = nwarps;
   src.claims.taken = 0;
   if (lane == 0) {
@@ -437,20 +446,29 @@ generic_color_kernel(const FrameDev *__restrict__ frame, int ncomp, int hmax, in
   if (rgba) dst[3] = 255;
 }
 
+template <int LAYOUT, bool Q8, bool RGBA, int WPC>
+cudaError_t launch_shape(const CUtensorMap *map2, const CUtensorMap *map3, const FrameDev *d_frames,
+                         const TileDesc *d_tiles, uint32_t ntiles, uint32_t *d_counters, int num_sms,
+                         cudaStream_t stream) {
+  uint32_t grid = (uint32_t)(num_sms * Shape<WPC>::kCtasPerSm);
+  const uint32_t need = (ntiles + WPC - 1) / WPC;
+  if (grid > need) grid = need;
+  recon_tma_kernel<LAYOUT, Q8, RGBA, WPC><<<grid, Shape<WPC>::kThreads, SmemLayout<WPC>::kBytes, stream>>>(
+      *map2, *map3, d_frames, d_tiles, ntiles, d_counters);
+  return cudaGetLastError();
+}
+
 template <int LAYOUT, bool Q8, bool RGBA>
 cudaError_t launch_one(bool use_tma, const CUtensorMap *map2, const CUtensorMap *map3, const FrameDev *d_frames,
                        const TileDesc *d_tiles, uint32_t ntiles, uint32_t *d_counters, int num_sms,
                        cudaStream_t stream) {
   if (use_tma) {
-    uint32_t grid = (uint32_t)(num_sms * kCtasPerSm);
-    const uint32_t need = (ntiles + kWarpsPerCta - 1) / kWarpsPerCta;
-    if (grid > need) grid = need;
-    recon_tma_kernel<LAYOUT, Q8, RGBA><<<grid, kCtaThreads, kDynSmem, stream>>>(*map2, *map3, d_frames, d_tiles,
-                                                                                ntiles, d_counters);
-  } else {
-    recon_ldg_kernel<LAYOUT, Q8, RGBA><<<(ntiles + kLdgWarps - 1) / kLdgWarps, kLdgWarps * 32, 0, stream>>>(
-        d_frames, d_tiles, ntiles);
+    const bool narrow = ntiles < (uint32_t)num_sms * 15u * kNarrowBelowTilesPerWarp;
+    return narrow ? launch_shape<LAYOUT, Q8, RGBA, 4>(map2, map3, d_frames, d_tiles, ntiles, d_counters, num_sms, stream)
+                  : launch_shape<LAYOUT, Q8, RGBA, 15>(map2, map3, d_frames, d_tiles, ntiles, d_counters, num_sms, stream);
   }
+  recon_ldg_kernel<LAYOUT, Q8, RGBA><<<(ntiles + kLdgWarps - 1) / kLdgWarps, kLdgWarps * 32, 0, stream>>>(
+      d_frames, d_tiles, ntiles);
   return cudaGetLastError();
 }
 
@@ -466,8 +484,11 @@ cudaError_t launch_q(bool q8, bool rgba, bool use_tma, const CUtensorMap *map2, 
 
 template <int LAYOUT, bool Q8, bool RGBA>
 cudaError_t set_attr() {
-  return cudaFuncSetAttribute(recon_tma_kernel<LAYOUT, Q8, RGBA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              kDynSmem);
+  cudaError_t e = cudaFuncSetAttribute(recon_tma_kernel<LAYOUT, Q8, RGBA, 15>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<15>::kBytes);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(recon_tma_kernel<LAYOUT, Q8, RGBA, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              SmemLayout<4>::kBytes);
 }
 template <int LAYOUT>
 cudaError_t set_attr_all() {
