@@ -311,18 +311,32 @@ def run_ours(args) -> None:
 
     # ---- end to end through the job API: host planes -> host pixels -----------------------
     L = ctx.lib
-    depth = 2
+    depth = max(2, args.e2e_depth)
     jobs = []
+    h2d_frame = 0  # bytes that cross the link per frame
     for k in range(depth):
         job = ctypes.c_void_p()
         fr = frames[k % distinct]
         d = descs_one[k % distinct]
         ctx._check(L.gidcuda_job_begin(ctx.ctx, ctypes.byref(d), ctypes.byref(job)), ctx.ctx)
+        moved = 0
         for c in range(fr.ncomp):
+            if args.e2e_input == "records":
+                # what the entropy decoder emits: one record per non-zero coefficient
+                try:
+                    moved += ctx.job_fill_records(job, d, c, fr.planes[c])
+                    continue
+                except OverflowError:
+                    pass  # too dense for the record buffer: this component travels as a plane
             p = L.gidcuda_job_plane(job, c, None, None)
             ctypes.memmove(p, fr.planes[c].ctypes.data, fr.planes[c].nbytes)
             # what the entropy decoder knows for free: the last block row it stored into
             ctx._check(L.gidcuda_job_hint_rows(job, c, capi.rows_used(fr.planes[c])), ctx.ctx)
+            # hinted planes move the upper half of every block
+            pl = fr.planes[c]
+            moved += pl.nbytes // 2 if capi.rows_used(pl) <= 4 and pl.nbytes >= (8 << 20) else pl.nbytes
+        if k == 0:
+            h2d_frame = moved
         jobs.append(job)
     e2e_frames = max(1, min(per_step, 8))  # frames per e2e step (bounded: host-link limited)
     pix, st = ctypes.c_void_p(), ctypes.c_size_t()
@@ -331,11 +345,11 @@ def run_ours(args) -> None:
     def e2e_steps(n: int) -> None:
         nonlocal checksum
         total = n * e2e_frames
-        for i in range(total + 1):
+        for i in range(total + depth - 1):
             if i < total:
                 ctx._check(L.gidcuda_job_submit(jobs[i % depth]), ctx.ctx)
-            if i >= 1:
-                ctx._check(L.gidcuda_job_wait(jobs[(i - 1) % depth], ctypes.byref(pix), ctypes.byref(st)), ctx.ctx)
+            if i >= depth - 1:
+                ctx._check(L.gidcuda_job_wait(jobs[(i - (depth - 1)) % depth], ctypes.byref(pix), ctypes.byref(st)), ctx.ctx)
                 # device->host read of the step's result: first and last byte of the host pixel buffer
                 row = (ctypes.c_uint8 * 1).from_address(pix.value)
                 checksum += row[0]
@@ -348,9 +362,7 @@ def run_ours(args) -> None:
     e2e_s = time.perf_counter() - t0
     e2e_value = sharding.whole_job_rate((w * h * e2e_frames / 1e6) * args.steps, world,
                                         sharding.max_over_ranks(e2e_s, dev))
-    # bytes that actually cross the link per frame: hinted planes move the upper half of every block
-    coef_bytes = sum(p.nbytes // 2 if capi.rows_used(p) <= 4 and p.nbytes >= (8 << 20) else p.nbytes
-                     for p in frames[0].planes)
+    coef_bytes = h2d_frame
     for job in jobs:
         L.gidcuda_job_release(job)
 
@@ -375,8 +387,12 @@ def run_ours(args) -> None:
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": coef_bytes * e2e_frames,
                     "d2h_bytes_per_step": nbytes * e2e_frames, "frames_per_step": e2e_frames,
-                    "api": "gidcuda_job_submit/wait, pinned host planes -> pinned host pixels, 2 jobs in flight; "
-                           "planes with empty block rows 4..7 (gidcuda_job_hint_rows) travel as pitched copies"},
+                    "input": args.e2e_input,
+                    "api": ("gidcuda_job_submit/wait, pinned host coefficient records (one per non-zero coefficient, "
+                            "gidcuda_job_records) -> expand + reconstruction kernels -> pinned host pixels, %d jobs in flight" % depth
+                            if args.e2e_input == "records" else
+                            "gidcuda_job_submit/wait, pinned host planes -> pinned host pixels, 2 jobs in flight; "
+                            "planes with empty block rows 4..7 (gidcuda_job_hint_rows) travel as pitched copies")},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(args.workload), "peak_source": peak_src,
@@ -399,6 +415,10 @@ def main() -> None:
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg2")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--e2e-input", choices=["records", "planes"], default="records",
+                    help="host-side form of the coefficients in the end-to-end leg: sparse records (what an entropy "
+                         "decoder emits) or dense int16 planes")
+    ap.add_argument("--e2e-depth", type=int, default=3, help="jobs in flight in the end-to-end leg")
     ap.add_argument("--streams", type=int, default=2, choices=[1, 2],
                     help="launch streams for the device-resident leg (2: consecutive frames overlap tail and ramp)")
     args = ap.parse_args()

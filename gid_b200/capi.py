@@ -28,7 +28,7 @@ FLAG_PACKED_ROWS = 0x100
 EXPORTS = [
     "gidcuda_abi_version", "gidcuda_device_count", "gidcuda_last_error", "gidcuda_set_option", "gidcuda_create",
     "gidcuda_destroy", "gidcuda_plane_geometry", "gidcuda_output_geometry", "gidcuda_job_begin",
-    "gidcuda_job_plane", "gidcuda_job_hint_rows", "gidcuda_job_submit", "gidcuda_job_wait", "gidcuda_job_release",
+    "gidcuda_job_plane", "gidcuda_job_hint_rows", "gidcuda_job_records", "gidcuda_job_records_commit", "gidcuda_job_submit", "gidcuda_job_wait", "gidcuda_job_release",
     "gidcuda_plan_create", "gidcuda_plan_launch", "gidcuda_plan_launch_count", "gidcuda_plan_uses_tma",
     "gidcuda_plan_destroy", "gidcuda_synchronize", "gidcuda_batch_create", "gidcuda_batch_run",
     "gidcuda_batch_destroy", "gidcuda_host_alloc", "gidcuda_host_free",
@@ -107,6 +107,9 @@ def load_library() -> ctypes.CDLL:
     L.gidcuda_job_plane.restype = vp
     L.gidcuda_job_plane.argtypes = [vp, ctypes.c_int, i32p, i32p]
     L.gidcuda_job_hint_rows.argtypes = [vp, ctypes.c_int, ctypes.c_int]
+    L.gidcuda_job_records.argtypes = [vp, ctypes.c_int, ctypes.POINTER(vp), ctypes.POINTER(vp),
+                                      ctypes.POINTER(ctypes.c_size_t), i32p]
+    L.gidcuda_job_records_commit.argtypes = [vp, ctypes.c_int, ctypes.c_size_t]
     L.gidcuda_job_submit.argtypes = [vp]
     L.gidcuda_job_wait.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t)]
     L.gidcuda_job_release.argtypes = [vp]
@@ -141,6 +144,25 @@ def rows_used(plane: np.ndarray) -> int:
     """1 + the last block row (natural order) holding a non-zero coefficient anywhere in the plane."""
     nz = np.flatnonzero(np.asarray(plane).reshape(-1, 8, 8).any(axis=(0, 2)))
     return int(nz[-1]) + 1 if nz.size else 1
+
+
+def records_from_plane(plane: np.ndarray, samp_h: int, samp_v: int) -> tuple[np.ndarray, np.ndarray]:
+    """Dense plane (by, bx, 64) int16 -> (first, records) of the sparse input form
+    (include/gidcuda.h): blocks in the order an interleaved scan visits them (MCUs in
+    raster order, inside an MCU the component's blocks row by row); one uint32 record per
+    non-zero coefficient = (uint16)value << 16 | natural index; first[seq] = index of block
+    seq's first record, first[nblocks] = number of records.  What an entropy decoder
+    emits directly; here derived from planes for tests and the bench."""
+    p = np.asarray(plane, dtype=np.int16)
+    by, bx = p.shape[0], p.shape[1]
+    seq = (p.reshape(by // samp_v, samp_v, bx // samp_h, samp_h, 64)
+            .transpose(0, 2, 1, 3, 4).reshape(-1, 64))
+    mask = seq != 0
+    first = np.zeros(seq.shape[0] + 1, dtype=np.uint32)
+    np.cumsum(mask.sum(axis=1), out=first[1:])
+    blk, k = np.nonzero(mask)
+    records = (seq[blk, k].astype(np.uint16).astype(np.uint32) << 16) | k.astype(np.uint32)
+    return first, records
 
 
 class GidCuda:
@@ -182,13 +204,43 @@ class GidCuda:
         return st.value, nb.value
 
     # -- one frame through the job API (host buffers, H2D + kernel + D2H) -----------
-    def reconstruct(self, desc: FrameDesc, planes: Sequence[np.ndarray], hint_rows: bool = False) -> np.ndarray:
+    def job_fill_records(self, job, desc: FrameDesc, comp: int, plane: np.ndarray) -> int:
+        """Supply component `comp` of a begun job in the sparse form; returns the bytes that will
+        cross the host link for it.  Raises OverflowError when the plane is too dense for the
+        record buffer (the caller then supplies the dense plane)."""
+        first, records = records_from_plane(plane, desc.samp_h[comp], desc.samp_v[comp])
+        pf, pr, cap, nb = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_size_t(), ctypes.c_int32()
+        self._check(self.lib.gidcuda_job_records(job, comp, ctypes.byref(pf), ctypes.byref(pr),
+                                                 ctypes.byref(cap), ctypes.byref(nb)), self.ctx)
+        if nb.value + 1 != first.size:
+            raise ValueError(f"plane {comp}: {first.size - 1} blocks, expected {nb.value}")
+        if records.size > cap.value:
+            raise OverflowError(f"plane {comp}: {records.size} records exceed the capacity {cap.value}")
+        ctypes.memmove(pf, first.ctypes.data, first.nbytes)
+        if records.size:
+            ctypes.memmove(pr, records.ctypes.data, records.nbytes)
+        self._check(self.lib.gidcuda_job_records_commit(job, comp, records.size), self.ctx)
+        return first.nbytes + records.nbytes
+
+    def reconstruct(self, desc: FrameDesc, planes: Sequence[np.ndarray], hint_rows: bool = False,
+                    sparse: Sequence[bool] | bool | str = False) -> np.ndarray:
         """planes[c]: (by, bx, 64) int16.  Returns the pixel rows as (H, stride) uint8.
-        hint_rows: tell the library which block rows are empty (gidcuda_job_hint_rows)."""
+        hint_rows: tell the library which block rows are empty (gidcuda_job_hint_rows).
+        sparse: supply the components (all, or per component) as coefficient records; "auto" = records
+        unless a component is too dense for the record buffer (what a decoder does on overflow)."""
         job = ctypes.c_void_p()
         self._check(self.lib.gidcuda_job_begin(self.ctx, ctypes.byref(desc), ctypes.byref(job)), self.ctx)
+        auto = isinstance(sparse, str) and sparse == "auto"
+        sp = [bool(sparse)] * desc.ncomp if isinstance(sparse, (bool, int, str)) else list(sparse)
         try:
             for c in range(desc.ncomp):
+                if sp[c]:
+                    try:
+                        self.job_fill_records(job, desc, c, np.asarray(planes[c]))
+                        continue
+                    except OverflowError:
+                        if not auto:
+                            raise
                 bx, by = ctypes.c_int32(), ctypes.c_int32()
                 p = self.lib.gidcuda_job_plane(job, c, ctypes.byref(bx), ctypes.byref(by))
                 if not p:
@@ -209,9 +261,10 @@ class GidCuda:
             self._check(self.lib.gidcuda_job_release(job), self.ctx)
         return out
 
-    def reconstruct_rgb(self, desc: FrameDesc, planes: Sequence[np.ndarray], hint_rows: bool = False) -> np.ndarray:
+    def reconstruct_rgb(self, desc: FrameDesc, planes: Sequence[np.ndarray], hint_rows: bool = False,
+                        sparse: Sequence[bool] | bool | str = False) -> np.ndarray:
         """Same, cropped to (H, W, 3) -- (H, W, 4) for the RGBA format."""
-        rows = self.reconstruct(desc, planes, hint_rows)
+        rows = self.reconstruct(desc, planes, hint_rows, sparse)
         bpp = 4 if (desc.flags & 0xFF) == OUT_RGBA8 else 3
         return rows[:, :bpp * desc.width].reshape(desc.height, desc.width, bpp)
 

@@ -156,8 +156,13 @@ struct gidcuda_job {
   gidcuda_frame_desc desc;
   Geometry geo;
   // capacities of the recycled buffers
-  size_t cap_coef = 0, cap_pixels = 0, cap_samples = 0;
-  uint8_t *h_coef = nullptr;    // pinned: planes, contiguous
+  size_t cap_coef = 0, cap_pixels = 0, cap_samples = 0, cap_hcoef = 0, cap_sparse = 0;
+  uint8_t *h_coef = nullptr;    // pinned: planes, contiguous; allocated at the first gidcuda_job_plane
+  bool h_coef_clean = false;    // zeroed since gidcuda_job_begin
+  // sparse input: per component [first: nblocks + 1 words][records: capacity words], pinned + device twin
+  uint8_t *h_sparse = nullptr, *d_sparse = nullptr;
+  size_t sparse_off[3] = {0, 0, 0}, sparse_cap[3] = {0, 0, 0}, sparse_count[3] = {0, 0, 0};
+  bool sparse[3] = {false, false, false};  // component committed as records
   uint8_t *h_pixels = nullptr;  // pinned
   uint8_t *d_coef = nullptr, *d_pixels = nullptr, *d_samples = nullptr;
   gidk::LaunchSet set;
@@ -170,6 +175,8 @@ struct gidcuda_job {
 
 static void job_free_buffers(gidcuda_job *j) {
   if (j->h_coef) cudaFreeHost(j->h_coef);
+  if (j->h_sparse) cudaFreeHost(j->h_sparse);
+  if (j->d_sparse) cudaFree(j->d_sparse);
   if (j->h_pixels) cudaFreeHost(j->h_pixels);
   if (j->d_coef) cudaFree(j->d_coef);
   if (j->d_pixels) cudaFree(j->d_pixels);
@@ -178,9 +185,53 @@ static void job_free_buffers(gidcuda_job *j) {
   if (j->stream) cudaStreamDestroy(j->stream);
   j->set.destroy();
   j->stream = nullptr;
-  j->h_coef = j->h_pixels = j->d_coef = j->d_pixels = j->d_samples = nullptr;
+  j->h_coef = j->h_pixels = j->d_coef = j->d_pixels = j->d_samples = j->h_sparse = j->d_sparse = nullptr;
   j->done = nullptr;
-  j->cap_coef = j->cap_pixels = j->cap_samples = 0;
+  j->cap_coef = j->cap_pixels = j->cap_samples = j->cap_hcoef = j->cap_sparse = 0;
+}
+
+// The pinned dense planes and the pinned + device record buffers are allocated on first use:
+// a decoder uses one input form or the other.
+static int job_reserve_planes(gidcuda_job *j) {
+  gidcuda_ctx *ctx = j->ctx;
+  const Geometry &g = j->geo;
+  if (j->cap_hcoef < g.coef_bytes) {
+    if (j->h_coef) cudaFreeHost(j->h_coef);
+    j->h_coef = nullptr;
+    j->cap_hcoef = 0;
+    CU_TRY(ctx, cudaHostAlloc((void **)&j->h_coef, g.coef_bytes, cudaHostAllocDefault));
+    j->cap_hcoef = g.coef_bytes;
+  }
+  if (!j->h_coef_clean) {
+    // planes must be zero before entropy decode (:771, :1876-1882)
+    memset(j->h_coef, 0, g.coef_bytes);
+    j->h_coef_clean = true;
+  }
+  return GIDCUDA_OK;
+}
+
+constexpr size_t kSparseRecordsPerBlock = 32;  // capacity: as many bytes as the dense plane
+
+static int job_reserve_sparse(gidcuda_job *j) {
+  gidcuda_ctx *ctx = j->ctx;
+  const Geometry &g = j->geo;
+  size_t off = 0;
+  for (int c = 0; c < g.ncomp; c++) {
+    const size_t nb = (size_t)g.bx[c] * g.by[c];
+    j->sparse_off[c] = off;
+    j->sparse_cap[c] = nb * kSparseRecordsPerBlock;
+    off += round_up((nb + 1 + j->sparse_cap[c]) * 4, 256);
+  }
+  if (j->cap_sparse < off) {
+    if (j->h_sparse) cudaFreeHost(j->h_sparse);
+    if (j->d_sparse) cudaFree(j->d_sparse);
+    j->h_sparse = j->d_sparse = nullptr;
+    j->cap_sparse = 0;
+    CU_TRY(ctx, cudaHostAlloc((void **)&j->h_sparse, off, cudaHostAllocDefault));
+    CU_TRY(ctx, cudaMalloc((void **)&j->d_sparse, off));
+    j->cap_sparse = off;
+  }
+  return GIDCUDA_OK;
 }
 
 static int job_reserve(gidcuda_job *j) {
@@ -189,11 +240,9 @@ static int job_reserve(gidcuda_job *j) {
   if (!j->done) CU_TRY(ctx, cudaEventCreateWithFlags(&j->done, cudaEventDisableTiming));
   if (!j->stream) CU_TRY(ctx, cudaStreamCreateWithFlags(&j->stream, cudaStreamNonBlocking));
   if (j->cap_coef < g.coef_bytes) {
-    if (j->h_coef) cudaFreeHost(j->h_coef);
     if (j->d_coef) cudaFree(j->d_coef);
-    j->h_coef = j->d_coef = nullptr;
+    j->d_coef = nullptr;
     j->cap_coef = 0;
-    CU_TRY(ctx, cudaHostAlloc((void **)&j->h_coef, g.coef_bytes, cudaHostAllocDefault));
     CU_TRY(ctx, cudaMalloc((void **)&j->d_coef, g.coef_bytes));
     j->cap_coef = g.coef_bytes;
     for (int c = 0; c < 3; c++) j->d_tail_zero[c] = false;
@@ -260,9 +309,12 @@ extern "C" int gidcuda_job_begin(gidcuda_ctx *ctx, const gidcuda_frame_desc *des
   it.pixels = j->d_pixels;
   it.samples = j->d_samples;
   j->set.build(std::vector<gidk::FrameItem>(1, it));
-  // planes must be zero before entropy decode (:771, :1876-1882)
-  memset(j->h_coef, 0, g.coef_bytes);
-  for (int c = 0; c < 3; c++) j->rows_hint[c] = 8;
+  j->h_coef_clean = false;  // zeroed when the decoder asks for the planes
+  for (int c = 0; c < 3; c++) {
+    j->rows_hint[c] = 8;
+    j->sparse[c] = false;
+    j->sparse_count[c] = 0;
+  }
   j->state = gidcuda_job::BEGUN;
   ctx->live_jobs++;
   *out = j;
@@ -274,9 +326,51 @@ extern "C" int16_t *gidcuda_job_plane(gidcuda_job *job, int comp, int32_t *block
     fail(job ? job->ctx : nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_job_plane: bad job or component");
     return nullptr;
   }
+  if (job_reserve_planes(job) != GIDCUDA_OK) return nullptr;
   if (blocks_x) *blocks_x = job->geo.bx[comp];
   if (blocks_y) *blocks_y = job->geo.by[comp];
   return reinterpret_cast<int16_t *>(job->h_coef + job->geo.plane_off[comp]);
+}
+
+extern "C" int gidcuda_job_records(gidcuda_job *job, int comp, uint32_t **first, uint32_t **records,
+                                   size_t *capacity, int32_t *nblocks) {
+  if (!job) return fail(nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "null job");
+  if (job->state == gidcuda_job::IDLE) return fail(job->ctx, GIDCUDA_ERR_STATE, "gidcuda_job_records: job was released");
+  if (comp < 0 || comp >= job->geo.ncomp || !first || !records)
+    return fail(job->ctx, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_job_records: bad component or null argument");
+  if (job->geo.layout == gidk::LAYOUT_GENERIC && job->geo.ncomp == 3 &&
+      (job->desc.samp_h[1] != 1 || job->desc.samp_v[1] != 1 || job->desc.samp_h[2] != 1 || job->desc.samp_v[2] != 1)) {
+    // (block sequence numbers are defined for every layout; nothing to reject -- kept for clarity)
+  }
+  const int rc = job_reserve_sparse(job);
+  if (rc != GIDCUDA_OK) return rc;
+  const size_t nb = (size_t)job->geo.bx[comp] * job->geo.by[comp];
+  uint32_t *base = reinterpret_cast<uint32_t *>(job->h_sparse + job->sparse_off[comp]);
+  *first = base;
+  *records = base + nb + 1;
+  if (capacity) *capacity = job->sparse_cap[comp];
+  if (nblocks) *nblocks = (int32_t)nb;
+  return GIDCUDA_OK;
+}
+
+extern "C" int gidcuda_job_records_commit(gidcuda_job *job, int comp, size_t count) {
+  if (!job) return fail(nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "null job");
+  if (job->state == gidcuda_job::IDLE)
+    return fail(job->ctx, GIDCUDA_ERR_STATE, "gidcuda_job_records_commit: job was released");
+  if (comp < 0 || comp >= job->geo.ncomp || !job->h_sparse)
+    return fail(job->ctx, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_job_records_commit: bad component, or gidcuda_job_records was not called");
+  if (count > job->sparse_cap[comp])
+    return fail(job->ctx, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_job_records_commit: %zu records exceed the capacity %zu", count,
+                job->sparse_cap[comp]);
+  const size_t nb = (size_t)job->geo.bx[comp] * job->geo.by[comp];
+  const uint32_t *first = reinterpret_cast<const uint32_t *>(job->h_sparse + job->sparse_off[comp]);
+  if (first[0] != 0 || first[nb] != count)
+    return fail(job->ctx, GIDCUDA_ERR_BAD_ARGUMENT,
+                "gidcuda_job_records_commit: first[0] = %u, first[nblocks] = %u do not frame %zu records", first[0], first[nb],
+                count);
+  job->sparse[comp] = true;
+  job->sparse_count[comp] = count;
+  return GIDCUDA_OK;
 }
 
 extern "C" int gidcuda_job_hint_rows(gidcuda_job *job, int comp, int rows_used) {
@@ -299,27 +393,32 @@ extern "C" int gidcuda_job_submit(gidcuda_job *job) {
   CU_TRY(ctx, cudaSetDevice(ctx->device));
   cudaStream_t s = job->stream;
   if (job->state == gidcuda_job::BEGUN) CU_TRY(ctx, job->set.upload(s));  // tables: once per begin
-  // Host -> device.  Without hints: one copy of the whole coefficient buffer.  A plane whose
-  // producer promised empty rows 4 .. 7 travels as a pitched copy of the upper 64 bytes of
-  // every block (measured 1.5x faster than the full plane on this link; narrower or wider
-  // partial rows are not faster than a full copy, so only this split is used).
-  bool any_hint = false;
-  // ... and only for large planes: below a few MiB the extra copy calls cost more than the bytes saved
-  // (measured on 1080p frames).
+  // Host -> device, per component:
+  //   records (gidcuda_job_records_commit): first[] + the records used, then the expand kernel;
+  //   dense plane: one copy -- or, when the producer promised empty rows 4 .. 7 and the plane is
+  //   large, a pitched copy of the upper 64 bytes of every block (measured 1.5x faster than the
+  //   full plane on this link; narrower or wider partial rows are not faster than a full copy,
+  //   and below a few MiB the extra calls cost more than the bytes saved: measured on 1080p).
   constexpr size_t kMinPitchedPlane = (size_t)8 << 20;
-  bool pitched[3] = {false, false, false};
+  bool any_sparse = false, all_dense_plain = true;
   for (int c = 0; c < g.ncomp; c++) {
-    pitched[c] = job->rows_hint[c] <= 4 && g.plane_bytes[c] >= kMinPitchedPlane;
-    any_hint = any_hint || pitched[c];
+    any_sparse = any_sparse || job->sparse[c];
+    if (job->sparse[c] || (job->rows_hint[c] <= 4 && g.plane_bytes[c] >= kMinPitchedPlane)) all_dense_plain = false;
   }
-  if (!any_hint) {
-    CU_TRY(ctx, cudaMemcpyAsync(job->d_coef, job->h_coef, g.coef_bytes, cudaMemcpyHostToDevice, s));
-    for (int c = 0; c < 3; c++) job->d_tail_zero[c] = false;
-  } else {
+  if (!all_dense_plain || any_sparse) {
     for (int c = 0; c < g.ncomp; c++) {
       uint8_t *dp = job->d_coef + g.plane_off[c];
+      if (job->sparse[c]) {
+        const size_t nb = (size_t)g.bx[c] * g.by[c];
+        CU_TRY(ctx, cudaMemcpyAsync(job->d_sparse + job->sparse_off[c], job->h_sparse + job->sparse_off[c],
+                                    (nb + 1 + job->sparse_count[c]) * 4, cudaMemcpyHostToDevice, s));
+        job->d_tail_zero[c] = false;
+        continue;
+      }
+      if (!job->h_coef || !job->h_coef_clean)
+        return fail(ctx, GIDCUDA_ERR_STATE, "gidcuda_job_submit: component %d has neither a plane nor records", c);
       const uint8_t *hp = job->h_coef + g.plane_off[c];
-      if (pitched[c]) {
+      if (job->rows_hint[c] <= 4 && g.plane_bytes[c] >= kMinPitchedPlane) {
         if (!job->d_tail_zero[c]) {
           CU_TRY(ctx, cudaMemsetAsync(dp, 0, g.plane_bytes[c], s));
           job->d_tail_zero[c] = true;
@@ -330,6 +429,28 @@ extern "C" int gidcuda_job_submit(gidcuda_job *job) {
         job->d_tail_zero[c] = false;
       }
     }
+  } else {
+    if (!job->h_coef || !job->h_coef_clean)
+      return fail(ctx, GIDCUDA_ERR_STATE, "gidcuda_job_submit: the frame has neither planes nor records");
+    CU_TRY(ctx, cudaMemcpyAsync(job->d_coef, job->h_coef, g.coef_bytes, cudaMemcpyHostToDevice, s));
+    for (int c = 0; c < 3; c++) job->d_tail_zero[c] = false;
+  }
+  if (any_sparse) {
+    gidk::ExpandArgs ea;
+    memset(&ea, 0, sizeof ea);
+    ea.mcux = (uint32_t)g.mcux;
+    for (int c = 0; c < g.ncomp; c++) {
+      const size_t nb = (size_t)g.bx[c] * g.by[c];
+      ea.h[c] = job->desc.samp_h[c];
+      ea.v[c] = job->desc.samp_v[c];
+      ea.bx[c] = (uint32_t)g.bx[c];
+      if (!job->sparse[c]) continue;  // nblocks stays 0: the component's plane came as a dense copy
+      ea.nblocks[c] = (uint32_t)nb;
+      ea.first[c] = reinterpret_cast<const uint32_t *>(job->d_sparse + job->sparse_off[c]);
+      ea.records[c] = ea.first[c] + nb + 1;
+      ea.plane[c] = reinterpret_cast<int16_t *>(job->d_coef + g.plane_off[c]);
+    }
+    CU_TRY(ctx, gidk::launch_expand(ea, g.ncomp, s));
   }
   CU_TRY(ctx, job->set.launch(ctx->num_sms, s));
   CU_TRY(ctx, cudaMemcpyAsync(job->h_pixels, job->d_pixels, g.pixel_bytes, cudaMemcpyDeviceToHost, s));

@@ -32,7 +32,7 @@ struct LaunchGroup {
   bool rgba;
   bool tma;
   uint32_t first_frame, nframes, first_tile, ntiles;
-  CUtensorMap map2, map3;
+  CUtensorMap map2;
 };
 
 typedef CUresult (*TensorMapEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -193,7 +193,7 @@ class LaunchSet {
     cudaError_t e;
     uint32_t gi = 0;
     for (const LaunchGroup &g : groups) {
-      if ((e = launch_fused(g.layout, g.q8, g.rgba, g.tma, &g.map2, &g.map3, d_frames_ + g.first_frame,
+      if ((e = launch_fused(g.layout, g.q8, g.rgba, g.tma, &g.map2, d_frames_ + g.first_frame,
                             d_tiles_ + g.first_tile, g.ntiles, d_counters_ + 2 * gi, num_sms, s)) != cudaSuccess)
         return e;
       gi++;
@@ -228,21 +228,10 @@ class LaunchSet {
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return false;
     }
-    {
-      const cuuint64_t dims[3] = {64, 2, rows / 2};
-      const cuuint64_t strides[2] = {128, 256};
-      const cuuint32_t box[3] = {64, 1, (cuuint32_t)kTileMcus};
-      const cuuint32_t estr[3] = {1, 1, 1};
-      if (enc(&g->map3, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, reinterpret_cast<void *>(base), dims, strides, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-        return false;
-    }
     return true;
   }
 
-  // Tiles of one frame.  coord[] = box row of each item relative to `base`:
-  // blocks for the 2-D map, block pairs for the 3-D (even/odd) luma map.
+  // Tiles of one frame.  coord[] = box row (block index relative to `base`) of each item.
   void append_tiles(const FrameItem &it, uint32_t frame_index, uintptr_t base) {
     const Geometry &g = it.geo;
     uint64_t row0[3] = {0, 0, 0};
@@ -273,9 +262,9 @@ class LaunchSet {
         t.coord[0] = (uint32_t)(row0[1] + m0);
         t.coord[1] = (uint32_t)(row0[2] + m0);
         for (int sy = 0; sy < V; sy++)
-          for (int sx = 0; sx < 2; sx++) {
+          for (int half = 0; half < 2; half++) {  // 32 consecutive luma blocks per item (mcu_item)
             const uint64_t blk = row0[0] + (uint64_t)(my * V + sy) * (uint64_t)g.bx[0] + 2u * (uint64_t)mx0;
-            t.coord[2 + sy * 2 + sx] = (uint32_t)(blk / 2);  // row0 and bx are even: exact
+            t.coord[2 + sy * 2 + half] = (uint32_t)(blk + 32u * (uint64_t)half);
           }
         tiles.push_back(t);
       }

@@ -95,13 +95,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
       ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2,
-                                            uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
-      : "memory");
-}
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -171,7 +164,7 @@ struct TmaSource {
   uint32_t lane_off;      // lane * 128 + ((lane & 7) << 4): row `lane`, chunk index pre-xored
   uint32_t slot, phase;   // consume cursor
   const TileDesc *tiles;
-  const CUtensorMap *map2, *map3;
+  const CUtensorMap *map2;
   uint32_t ntiles;
   TileClaims claims;
   volatile uint4 *claimed;  // shared: ring of claimed tiles {tile, frame, m0, -}
@@ -230,8 +223,7 @@ struct TmaSource {
     if ((threadIdx.x & 31) == 0) {
       const uint32_t bar = full + 8 * s, dst = slots + s * kSlotBytes;
       mbar_arrive_expect_tx(bar, kSlotBytes);
-      if (LI::H == 2 && f_item >= 2) tma_load_3d(dst, map3, 0, (int)((f_item - 2) & 1), (int)f_coord, bar);
-      else tma_load_2d(dst, map2, 0, (int)f_coord, bar);
+      tma_load_2d(dst, map2, 0, (int)f_coord, bar);
     }
     if (++f_item == (uint32_t)LI::NI) {
       f_item = 0;
@@ -266,9 +258,10 @@ __device__ __forceinline__ Scratch make_scratch(uint8_t *base, uint32_t lane) {
 }
 
 template <int LAYOUT, bool Q8, bool RGBA, class Src>
-__device__ __forceinline__ void run_mcu(bool active, const FrameDev &f, Src &src, const Scratch &sc, int mx, int my) {
+__device__ __forceinline__ void run_mcu(bool active, const FrameDev &f, Src &src, const Scratch &sc, int lane, int mx,
+                                        int my) {
   using LI = LayoutInfo<LAYOUT>;
-  mcu_run<LI::H, LI::V, LAYOUT == LAYOUT_GREY, Q8, RGBA>(active, f, &f.qw[0][0], src, sc, mx, my);
+  mcu_run<LI::H, LI::V, LAYOUT == LAYOUT_GREY, Q8, RGBA>(active, f, &f.qw[0][0], src, sc, lane, mx, my);
 }
 
 // MCU (mx, my) of lane t in a tile starting at m0, or false when the lane has
@@ -297,8 +290,7 @@ __device__ __forceinline__ void cache_frame(uint8_t *dst, const FrameDev *src, u
 
 template <int LAYOUT, bool Q8, bool RGBA, int WPC>
 __global__ void __launch_bounds__(Shape<WPC>::kThreads, Shape<WPC>::kCtasPerSm)
-recon_tma_kernel(const __grid_constant__ CUtensorMap map2, const __grid_constant__ CUtensorMap map3,
-                 const FrameDev *__restrict__ frames, const TileDesc *__restrict__ tiles, uint32_t ntiles,
+recon_tma_kernel(const __grid_constant__ CUtensorMap map2, const FrameDev *__restrict__ frames, const TileDesc *__restrict__ tiles, uint32_t ntiles,
                  uint32_t *__restrict__ counters) {
   extern __shared__ uint8_t dyn_smem[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -315,7 +307,6 @@ recon_tma_kernel(const __grid_constant__ CUtensorMap map2, const __grid_constant
   src.lane_off = lane * 128u + ((lane & 7u) << 4);
   src.tiles = tiles;
   src.map2 = &map2;
-  src.map3 = &map3;
   src.ntiles = ntiles;
   src.claims.counters = counters;
   src.claims.pending = 0;
@@ -343,7 +334,7 @@ recon_tma_kernel(const __grid_constant__ CUtensorMap map2, const __grid_constant
     }
     int mx, my;
     const bool active = tile_mcu<LAYOUT>(f, this_m0, lane, mx, my);
-    run_mcu<LAYOUT, Q8, RGBA>(active, f, src, scratch, mx, my);
+    run_mcu<LAYOUT, Q8, RGBA>(active, f, src, scratch, (int)lane, mx, my);
   }
   src.claims.finish();
 }
@@ -365,7 +356,7 @@ recon_ldg_kernel(const FrameDev *__restrict__ frames, const TileDesc *__restrict
   int mx, my;
   const bool active = tile_mcu<LAYOUT>(f, m0, lane, mx, my);
   LdgSource src{&f};
-  run_mcu<LAYOUT, Q8, RGBA>(active, f, src, make_scratch(s_scratch[warp], lane), mx, my);
+  run_mcu<LAYOUT, Q8, RGBA>(active, f, src, make_scratch(s_scratch[warp], lane), (int)lane, mx, my);
 }
 
 // ---- generic path -----------------------------------------------------------
@@ -447,25 +438,25 @@ generic_color_kernel(const FrameDev *__restrict__ frame, int ncomp, int hmax, in
 }
 
 template <int LAYOUT, bool Q8, bool RGBA, int WPC>
-cudaError_t launch_shape(const CUtensorMap *map2, const CUtensorMap *map3, const FrameDev *d_frames,
+cudaError_t launch_shape(const CUtensorMap *map2, const FrameDev *d_frames,
                          const TileDesc *d_tiles, uint32_t ntiles, uint32_t *d_counters, int num_sms,
                          cudaStream_t stream) {
   uint32_t grid = (uint32_t)(num_sms * Shape<WPC>::kCtasPerSm);
   const uint32_t need = (ntiles + WPC - 1) / WPC;
   if (grid > need) grid = need;
   recon_tma_kernel<LAYOUT, Q8, RGBA, WPC><<<grid, Shape<WPC>::kThreads, SmemLayout<WPC>::kBytes, stream>>>(
-      *map2, *map3, d_frames, d_tiles, ntiles, d_counters);
+      *map2, d_frames, d_tiles, ntiles, d_counters);
   return cudaGetLastError();
 }
 
 template <int LAYOUT, bool Q8, bool RGBA>
-cudaError_t launch_one(bool use_tma, const CUtensorMap *map2, const CUtensorMap *map3, const FrameDev *d_frames,
+cudaError_t launch_one(bool use_tma, const CUtensorMap *map2, const FrameDev *d_frames,
                        const TileDesc *d_tiles, uint32_t ntiles, uint32_t *d_counters, int num_sms,
                        cudaStream_t stream) {
   if (use_tma) {
     const bool narrow = ntiles < (uint32_t)num_sms * 15u * kNarrowBelowTilesPerWarp;
-    return narrow ? launch_shape<LAYOUT, Q8, RGBA, 4>(map2, map3, d_frames, d_tiles, ntiles, d_counters, num_sms, stream)
-                  : launch_shape<LAYOUT, Q8, RGBA, 15>(map2, map3, d_frames, d_tiles, ntiles, d_counters, num_sms, stream);
+    return narrow ? launch_shape<LAYOUT, Q8, RGBA, 4>(map2, d_frames, d_tiles, ntiles, d_counters, num_sms, stream)
+                  : launch_shape<LAYOUT, Q8, RGBA, 15>(map2, d_frames, d_tiles, ntiles, d_counters, num_sms, stream);
   }
   recon_ldg_kernel<LAYOUT, Q8, RGBA><<<(ntiles + kLdgWarps - 1) / kLdgWarps, kLdgWarps * 32, 0, stream>>>(
       d_frames, d_tiles, ntiles);
@@ -473,10 +464,10 @@ cudaError_t launch_one(bool use_tma, const CUtensorMap *map2, const CUtensorMap 
 }
 
 template <int LAYOUT>
-cudaError_t launch_q(bool q8, bool rgba, bool use_tma, const CUtensorMap *map2, const CUtensorMap *map3,
+cudaError_t launch_q(bool q8, bool rgba, bool use_tma, const CUtensorMap *map2,
                      const FrameDev *d_frames, const TileDesc *d_tiles, uint32_t ntiles, uint32_t *d_counters,
                      int num_sms, cudaStream_t stream) {
-#define GIDK_ARGS use_tma, map2, map3, d_frames, d_tiles, ntiles, d_counters, num_sms, stream
+#define GIDK_ARGS use_tma, map2, d_frames, d_tiles, ntiles, d_counters, num_sms, stream
   if (q8) return rgba ? launch_one<LAYOUT, true, true>(GIDK_ARGS) : launch_one<LAYOUT, true, false>(GIDK_ARGS);
   return rgba ? launch_one<LAYOUT, false, true>(GIDK_ARGS) : launch_one<LAYOUT, false, false>(GIDK_ARGS);
 #undef GIDK_ARGS
@@ -510,10 +501,10 @@ cudaError_t init_kernels() {
 }
 
 cudaError_t launch_fused(Layout layout, bool q8, bool rgba, bool use_tma, const CUtensorMap *map2,
-                         const CUtensorMap *map3, const FrameDev *d_frames, const TileDesc *d_tiles, uint32_t ntiles,
+                         const FrameDev *d_frames, const TileDesc *d_tiles, uint32_t ntiles,
                          uint32_t *d_counters, int num_sms, cudaStream_t stream) {
   if (ntiles == 0) return cudaSuccess;
-#define GIDK_ARGS q8, rgba, use_tma, map2, map3, d_frames, d_tiles, ntiles, d_counters, num_sms, stream
+#define GIDK_ARGS q8, rgba, use_tma, map2, d_frames, d_tiles, ntiles, d_counters, num_sms, stream
   switch (layout) {
     case LAYOUT_GREY: return launch_q<LAYOUT_GREY>(GIDK_ARGS);
     case LAYOUT_444: return launch_q<LAYOUT_444>(GIDK_ARGS);

@@ -17,7 +17,8 @@ constexpr int kTileMcus = 32;  // MCUs (= lanes of one warp) per tile of the fus
 // 4:4:4) use linear runs that may wrap over MCU rows; 4:2:2 / 4:2:0 tiles stay
 // inside one MCU row, so that every item of the tile is ONE box of the
 // coefficient tensor map.  coord[i] = row coordinate of item i for the TMA
-// kernel (items: grey {Y}; YCbCr {Cb, Cr, Y(sy, sx) in raster order}).
+// kernel (items: grey {Y}; 4:4:4 {Cb, Cr, Y}; 4:2:x {Cb, Cr, then per luma block
+// row sy the two halves of 32 consecutive luma blocks}, see mcu_item).
 struct TileDesc {
   uint32_t frame;
   uint32_t m0;
@@ -27,22 +28,36 @@ static_assert(sizeof(TileDesc) == 32, "TileDesc is 32 bytes");
 
 // Fused dequant + IDCT + upsample + colour over `ntiles` tiles of one layout.
 //   use_tma: coefficients are staged through a shared-memory ring by TMA
-//            (cp.async.bulk.tensor, 128-byte swizzle); needs map2/map3.
+//            (cp.async.bulk.tensor, 128-byte swizzle); needs map2.
 //            Otherwise every thread reads its blocks with 128-bit global loads.
 //   map2: [rows][64] int16 view of the coefficient arena, box 128 x 64
-//   map3: [rows/2][2][64] view (even/odd blocks) for the luma plane of 4:2:x
 //   d_counters: two zero-initialised words of device memory private to this launch
 //            group (dynamic tile claims; the kernel leaves them zero again), so one
 //            group must not run concurrently with itself.
 //   rgba:    4-byte pixels (a separate kernel instance: the 3-byte kernels do not carry its code)
 cudaError_t launch_fused(Layout layout, bool q8, bool rgba, bool use_tma, const CUtensorMap *map2,
-                         const CUtensorMap *map3, const FrameDev *d_frames, const TileDesc *d_tiles,
+                         const FrameDev *d_frames, const TileDesc *d_tiles,
                          uint32_t ntiles, uint32_t *d_counters, int num_sms, cudaStream_t stream);
 
 // Generic path for one frame (any integer up-factors): pass 1 writes 8-bit
 // sample planes (f.samples), pass 2 upsamples + colour-converts.  `h_frame` is
 // the host copy of d_frame[0] (for grid sizing).
 cudaError_t launch_generic(const FrameDev &h_frame, const FrameDev *d_frame, cudaStream_t stream);
+
+// Sparse coefficient input (expand_kernel.cu): per component, records[first[seq] .. first[seq + 1])
+// are the non-zero coefficients of the block with sequence number seq (scan order, see the kernel),
+// record = (uint16)value << 16 | natural index.  Writes every block of the dense planes.
+struct ExpandArgs {
+  const uint32_t *first[3];
+  const uint32_t *records[3];
+  int16_t *plane[3];
+  uint32_t nblocks[3];
+  uint32_t bx[3];
+  uint32_t mcux;
+  int32_t h[3], v[3];
+};
+cudaError_t launch_expand(const ExpandArgs &a, int ncomp, cudaStream_t stream);
+inline int launches_expand() { return 1; }
 
 // One-time kernel attribute set-up (dynamic shared memory opt-in).
 cudaError_t init_kernels();

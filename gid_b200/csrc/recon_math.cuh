@@ -60,70 +60,146 @@ GID_HD int tdiv(int x) {
 #endif
 }
 
-// Row_IDCT, gid-decoding_jpg.adb:799-845.
-// The "all AC zero" shortcut (:810-812) returns blk(0)*8 for the 8 outputs.
-// The general path with zero AC terms gives (blk(0)*2048 + 128) / 256, which
-// differs for negative blk(0) only through the rounding constant; so the
-// shortcut is reproduced by selecting the constant: 0 instead of 128.
-// (Exact while |blk(0)| < 2**20, which every 8-bit JPEG stream satisfies:
-// |DC| <= 2047 * 255.)
+// ---- byte permute and byte / half-word dot products (PRMT, IDP.4A, IDP.2A) -----------
+// The host versions restate the PTX semantics so that the CPU suite exercises
+// the same formulas.
+GID_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+#if defined(__CUDA_ARCH__)
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+#else
+  // selector nibble: bits 2..0 = source byte of {b, a}; bit 3 = replicate that byte's sign bit
+  const uint64_t src = ((uint64_t)b << 32) | a;
+  uint32_t d = 0;
+  for (int i = 0; i < 4; i++) {
+    const uint32_t n = (sel >> (4 * i)) & 0xF;
+    uint32_t byte = (uint32_t)((src >> (8 * (n & 7))) & 0xFF);
+    if (n & 8) byte = (byte & 0x80) ? 0xFFu : 0u;
+    d |= byte << (8 * i);
+  }
+  return d;
+#endif
+}
+GID_HD int dp4a_uu(uint32_t a, uint32_t b, int c) {  // unsigned bytes x unsigned bytes
+#if defined(__CUDA_ARCH__)
+  int d;
+  asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+#else
+  unsigned acc = (unsigned)c;
+  for (int i = 0; i < 4; i++) acc += ((a >> (8 * i)) & 0xFF) * ((b >> (8 * i)) & 0xFF);
+  return (int)acc;
+#endif
+}
+GID_HD int dp4a_us(uint32_t a, uint32_t b, int c) {  // unsigned bytes x signed bytes
+#if defined(__CUDA_ARCH__)
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+#else
+  unsigned acc = (unsigned)c;
+  for (int i = 0; i < 4; i++)
+    acc += (unsigned)((int)((a >> (8 * i)) & 0xFF) * (int)(int8_t)((b >> (8 * i)) & 0xFF));
+  return (int)acc;
+#endif
+}
+GID_HD int dp4a_ss(uint32_t a, uint32_t b, int c) {  // signed bytes x signed bytes
+#if defined(__CUDA_ARCH__)
+  int d;
+  asm("dp4a.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+#else
+  unsigned acc = (unsigned)c;
+  for (int i = 0; i < 4; i++)
+    acc += (unsigned)((int)(int8_t)((a >> (8 * i)) & 0xFF) * (int)(int8_t)((b >> (8 * i)) & 0xFF));
+  return (int)acc;
+#endif
+}
+// a = two unsigned 16-bit lanes, b = four unsigned bytes: .lo = a.lo*b0 + a.hi*b1 + c, .hi = a.lo*b2 + a.hi*b3 + c
+GID_HD int dp2a_lo_uu(uint32_t a, uint32_t b, int c) {
+#if defined(__CUDA_ARCH__)
+  int d;
+  asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+#else
+  return (int)((a & 0xFFFFu) * (b & 0xFFu) + (a >> 16) * ((b >> 8) & 0xFFu) + (unsigned)c);
+#endif
+}
+GID_HD int dp2a_hi_uu(uint32_t a, uint32_t b, int c) {
+#if defined(__CUDA_ARCH__)
+  int d;
+  asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+#else
+  return (int)((a & 0xFFFFu) * ((b >> 16) & 0xFFu) + (a >> 16) * (b >> 24) + (unsigned)c);
+#endif
+}
+
+// ---- truncating division, two values at a time ------------------------------------------
+// The fused kernels are bound by the ALU pipe (shifts, permutes, packs: 2 warp-
+// instructions / clock / SM), and tdiv spends two ALU instructions per value
+// (sign, final shift) -- 208 values per block.  Pairing halves the sign work:
+//   sp = PRMT(x1, x2, 0xFFBB): bytes 0,1 = 0xFF if x1 < 0 else 0, bytes 2,3 the same for x2
+//        (selector bit 3 replicates the sign bit of the selected byte) -- ONE ALU instruction;
+//   x + bias = a byte / half-word dot product of sp with a constant, accumulating
+//        into x (IDP.4A / IDP.2A, FMA pipe):
+//          K = 8 : bias 255   = u8 0xFF * 1
+//          K = 3 : bias 7     = s8 (-1) * (-7)
+//          K = 16: bias 65535 = u16 0xFFFF * 1
+//   and the final arithmetic shift (SHF, or LEA.HI.SX32 when an add follows).
+// Exact for every 32-bit x (the same wrap-around sum as tdiv).
+GID_HD uint32_t sign_pair(int x1, int x2) { return prmt((uint32_t)x1, (uint32_t)x2, 0xFFBBu); }
+template <int K> GID_HD int bias_first(uint32_t sp, int x) {
+  static_assert(K == 3 || K == 8 || K == 16, "supported divisors");
+  if (K == 8) return dp4a_uu(sp, 0x00000001u, x);
+  if (K == 3) return dp4a_ss(sp, 0x000000F9u, x);
+  return dp2a_lo_uu(sp, 0x00000001u, x);
+}
+template <int K> GID_HD int bias_second(uint32_t sp, int x) {
+  if (K == 8) return dp4a_uu(sp, 0x00010000u, x);
+  if (K == 3) return dp4a_ss(sp, 0x00F90000u, x);
+  return dp2a_hi_uu(sp, 0x01000000u, x);
+}
+// final shift: SHF on the ALU pipe, or (MH) mul.hi by 2**(32-K) = floor(t / 2**K) on the
+// FMA pipe (IMAD.HI, half rate) -- used where the ALU pipe is the busier one and the
+// result feeds multiplications, so that there is no add for the shift to fuse with.
+template <int K, bool MH> GID_HD int floor_shift(int t) {
+#if defined(__CUDA_ARCH__)
+  if (MH) {
+    int r;
+    asm("mul.hi.s32 %0, %1, %2;" : "=r"(r) : "r"(t), "r"((int)(1u << (32 - K))));
+    return r;
+  }
+#endif
+  return t >> K;
+}
+template <int K, bool MH = false>
+GID_HD void tdiv2(int x1, int x2, int &r1, int &r2) {
+  const uint32_t sp = sign_pair(x1, x2);
+  r1 = floor_shift<K, MH>(bias_first<K>(sp, x1));
+  r2 = floor_shift<K, MH>(bias_second<K>(sp, x2));
+}
+
+#if defined(GIDK_MULHI_ROWS)
+constexpr bool kRowOutMulHi = true;
+#else
+constexpr bool kRowOutMulHi = false;
+#endif
+
+// Row_IDCT, gid-decoding_jpg.adb:799-845, with the rounding constant supplied by
+// the caller: `rnd` = 128 when the row has a non-zero AC term, 0 when it has
+// none.  The "all AC zero" shortcut (:810-812) returns blk(0)*8 for the 8
+// outputs; the general path with zero AC terms gives (blk(0)*2048 + 128) / 256,
+// which differs for negative blk(0) only through the rounding constant, so the
+// shortcut is reproduced by selecting the constant.  (Exact while
+// |blk(0)| < 2**20, which every 8-bit JPEG stream satisfies: |DC| <= 2047 * 255.)
 //
 // Re-association (all exact modulo 2**32):
 //   x8 = W7*(x4+x5); x4' = x8 + (W1-W7)*x4 = W1*x4 + W7*x5;  x5' = x8 - (W1+W7)*x5 = W7*x4 - W1*x5
 //   x8 = W3*(x6+x7); x6' = x8 - (W3-W5)*x6 = W5*x6 + W3*x7;  x7' = x8 - (W3+W5)*x7 = W3*x6 - W5*x7
 //   x1 = W6*(x3+x2); x2' = x1 - (W2+W6)*x2 = W6*x3 - W2*x2;  x3' = x1 + (W2-W6)*x3 = W2*x3 + W6*x2
-//   181*(x4+x5)+128 = 181*x4 + (181*x5 + 128), and each output is one 3-input sum.
-GID_HD void row_idct(int &b0, int &b1, int &b2, int &b3, int &b4, int &b5, int &b6, int &b7) {
-  const int x1 = wmul(b4, 2048);
-  const int any_ac = x1 | b1 | b2 | b3 | b5 | b6 | b7;
-  const int x0 = wmad(b0, 2048, any_ac != 0 ? 128 : 0);
-  const int o4 = wmad(W1, b1, wmul(W7, b7)), o5 = wsub(wmul(W7, b1), wmul(W1, b7));
-  const int o6 = wmad(W5, b5, wmul(W3, b3)), o7 = wsub(wmul(W3, b5), wmul(W5, b3));
-  const int e2 = wsub(wmul(W6, b2), wmul(W2, b6)), e3 = wmad(W2, b2, wmul(W6, b6));
-  const int A = wadd(x0, x1), B = wsub(x0, x1);
-  const int p1 = wadd(o4, o6), q4 = wsub(o4, o6), p6 = wadd(o5, o7), q5 = wsub(o5, o7);
-  const int h = wmad(181, q4, 128);
-  const int x2 = tdiv<8>(wmad(181, q5, h));
-  const int x4 = tdiv<8>(wmad(-181, q5, h));
-  b0 = tdiv<8>(wadd3(A, e3, p1));
-  b7 = tdiv<8>(wadd3(A, e3, wneg(p1)));
-  b3 = tdiv<8>(wadd3(A, wneg(e3), p6));
-  b4 = tdiv<8>(wadd3(A, wneg(e3), wneg(p6)));
-  b1 = tdiv<8>(wadd3(B, e2, x2));
-  b6 = tdiv<8>(wadd3(B, e2, wneg(x2)));
-  b2 = tdiv<8>(wadd3(B, wneg(e2), x4));
-  b5 = tdiv<8>(wadd3(B, wneg(e2), wneg(x4)));
-}
-
-// Col_IDCT, gid-decoding_jpg.adb:847-895, general path only: the shortcut at
-// :858-862, Clip((b0+32)/64+128), equals the general path when x1..x7 = 0
-// ((b0*256+8192)/16384 is the same rational number).  Outputs are NOT clipped
-// here: v = s / 2**14 + 128; the caller saturates to 0..255 (Clip, :755-756).
-GID_HD void col_idct(int &b0, int &b1, int &b2, int &b3, int &b4, int &b5, int &b6, int &b7) {
-  const int x1 = wmul(b4, 256);
-  const int x0 = wmad(b0, 256, 8192);
-  const int o4 = tdiv<3>(wmad(W1, b1, wmad(W7, b7, 4))), o5 = tdiv<3>(wsub(wmad(W7, b1, 4), wmul(W1, b7)));
-  const int o6 = tdiv<3>(wmad(W5, b5, wmad(W3, b3, 4))), o7 = tdiv<3>(wsub(wmad(W3, b5, 4), wmul(W5, b3)));
-  const int e2 = tdiv<3>(wsub(wmad(W6, b2, 4), wmul(W2, b6))), e3 = tdiv<3>(wmad(W2, b2, wmad(W6, b6, 4)));
-  const int A = wadd(x0, x1), B = wsub(x0, x1);
-  const int p1 = wadd(o4, o6), q4 = wsub(o4, o6), p6 = wadd(o5, o7), q5 = wsub(o5, o7);
-  const int h = wmad(181, q4, 128);
-  const int x2 = tdiv<8>(wmad(181, q5, h));
-  const int x4 = tdiv<8>(wmad(-181, q5, h));
-  b0 = wadd(tdiv<14>(wadd3(A, e3, p1)), 128);
-  b7 = wadd(tdiv<14>(wadd3(A, e3, wneg(p1))), 128);
-  b3 = wadd(tdiv<14>(wadd3(A, wneg(e3), p6)), 128);
-  b4 = wadd(tdiv<14>(wadd3(A, wneg(e3), wneg(p6))), 128);
-  b1 = wadd(tdiv<14>(wadd3(B, e2, x2)), 128);
-  b6 = wadd(tdiv<14>(wadd3(B, e2, wneg(x2))), 128);
-  b2 = wadd(tdiv<14>(wadd3(B, wneg(e2), x4)), 128);
-  b5 = wadd(tdiv<14>(wadd3(B, wneg(e2), wneg(x4))), 128);
-}
-
-// Row_IDCT with the rounding constant supplied by the caller: `rnd` = 128 when
-// the row has a non-zero AC term, 0 when it has none (the shortcut of :810-812,
-// see row_idct above).  The caller already knows which (it classifies rows to
-// skip work warp-wide), so the 7-term OR is not repeated here.
+//   181*(x4+x5)+128 = 181*x4 + (181*x5 + 128)
 GID_HD void row_idct_rnd(int rnd, int &b0, int &b1, int &b2, int &b3, int &b4, int &b5, int &b6, int &b7) {
   const int x1 = wmul(b4, 2048);
   const int x0 = wmad(b0, 2048, rnd);
@@ -133,16 +209,49 @@ GID_HD void row_idct_rnd(int rnd, int &b0, int &b1, int &b2, int &b3, int &b4, i
   const int A = wadd(x0, x1), B = wsub(x0, x1);
   const int p1 = wadd(o4, o6), q4 = wsub(o4, o6), p6 = wadd(o5, o7), q5 = wsub(o5, o7);
   const int h = wmad(181, q4, 128);
-  const int x2 = tdiv<8>(wmad(181, q5, h));
-  const int x4 = tdiv<8>(wmad(-181, q5, h));
-  b0 = tdiv<8>(wadd3(A, e3, p1));
-  b7 = tdiv<8>(wadd3(A, e3, wneg(p1)));
-  b3 = tdiv<8>(wadd3(A, wneg(e3), p6));
-  b4 = tdiv<8>(wadd3(A, wneg(e3), wneg(p6)));
-  b1 = tdiv<8>(wadd3(B, e2, x2));
-  b6 = tdiv<8>(wadd3(B, e2, wneg(x2)));
-  b2 = tdiv<8>(wadd3(B, wneg(e2), x4));
-  b5 = tdiv<8>(wadd3(B, wneg(e2), wneg(x4)));
+  int x2, x4;
+  tdiv2<8>(wmad(181, q5, h), wmad(-181, q5, h), x2, x4);
+  const int P = wadd(A, e3), M = wsub(A, e3), Q = wadd(B, e2), N = wsub(B, e2);
+  tdiv2<8, kRowOutMulHi>(wadd(P, p1), wsub(P, p1), b0, b7);
+  tdiv2<8, kRowOutMulHi>(wadd(M, p6), wsub(M, p6), b3, b4);
+  tdiv2<8, kRowOutMulHi>(wadd(Q, x2), wsub(Q, x2), b1, b6);
+  tdiv2<8, kRowOutMulHi>(wadd(N, x4), wsub(N, x4), b2, b5);
+}
+GID_HD void row_idct(int &b0, int &b1, int &b2, int &b3, int &b4, int &b5, int &b6, int &b7) {
+  const int any_ac = b1 | b2 | b3 | b4 | b5 | b6 | b7;
+  row_idct_rnd(any_ac != 0 ? 128 : 0, b0, b1, b2, b3, b4, b5, b6, b7);
+}
+
+// Col_IDCT, gid-decoding_jpg.adb:847-895, general path only: the shortcut at
+// :858-862, Clip((b0+32)/64+128), equals the general path when x1..x7 = 0
+// ((b0*256+8192)/16384 is the same rational number).  Outputs are NOT clipped
+// here: v = s / 2**14 + 128; the caller saturates to 0..255 (Clip, :755-756).
+// K = 14 (the output stage) keeps the one-value form: its bias 16383 is not a byte or
+// half-word multiple, and scaling the sums by 4 to use the K = 16 form would change
+// the wrap-around behaviour of out-of-range streams.
+GID_HD void col_outputs(int A, int B, int e2, int e3, int p1, int p6, int x2, int x4, int &b0, int &b1, int &b2,
+                        int &b3, int &b4, int &b5, int &b6, int &b7) {
+  b0 = wadd(tdiv<14>(wadd3(A, e3, p1)), 128);
+  b7 = wadd(tdiv<14>(wadd3(A, e3, wneg(p1))), 128);
+  b3 = wadd(tdiv<14>(wadd3(A, wneg(e3), p6)), 128);
+  b4 = wadd(tdiv<14>(wadd3(A, wneg(e3), wneg(p6))), 128);
+  b1 = wadd(tdiv<14>(wadd3(B, e2, x2)), 128);
+  b6 = wadd(tdiv<14>(wadd3(B, e2, wneg(x2))), 128);
+  b2 = wadd(tdiv<14>(wadd3(B, wneg(e2), x4)), 128);
+  b5 = wadd(tdiv<14>(wadd3(B, wneg(e2), wneg(x4))), 128);
+}
+GID_HD void col_idct(int &b0, int &b1, int &b2, int &b3, int &b4, int &b5, int &b6, int &b7) {
+  const int x1 = wmul(b4, 256);
+  const int x0 = wmad(b0, 256, 8192);
+  int o4, o5, o6, o7, e2, e3, x2, x4;
+  tdiv2<3>(wmad(W1, b1, wmad(W7, b7, 4)), wsub(wmad(W7, b1, 4), wmul(W1, b7)), o4, o5);
+  tdiv2<3>(wmad(W5, b5, wmad(W3, b3, 4)), wsub(wmad(W3, b5, 4), wmul(W5, b3)), o6, o7);
+  tdiv2<3>(wsub(wmad(W6, b2, 4), wmul(W2, b6)), wmad(W2, b2, wmad(W6, b6, 4)), e2, e3);
+  const int A = wadd(x0, x1), B = wsub(x0, x1);
+  const int p1 = wadd(o4, o6), q4 = wsub(o4, o6), p6 = wadd(o5, o7), q5 = wsub(o5, o7);
+  const int h = wmad(181, q4, 128);
+  tdiv2<8>(wmad(181, q5, h), wmad(-181, q5, h), x2, x4);
+  col_outputs(A, B, e2, e3, p1, p6, x2, x4, b0, b1, b2, b3, b4, b5, b6, b7);
 }
 
 // Col_IDCT for a column whose inputs b3 .. b7 are zero (rows 3 .. 7 of the
@@ -152,20 +261,12 @@ GID_HD void row_idct_rnd(int rnd, int &b0, int &b1, int &b2, int &b3, int &b4, i
 // Writes all 8 outputs (un-clipped samples).
 GID_HD void col_idct_lo3(int &b0, int &b1, int &b2, int &b3, int &b4, int &b5, int &b6, int &b7) {
   const int x0 = wmad(b0, 256, 8192);
-  const int o4 = tdiv<3>(wmad(W1, b1, 4)), o5 = tdiv<3>(wmad(W7, b1, 4));
-  const int e2 = tdiv<3>(wmad(W6, b2, 4)), e3 = tdiv<3>(wmad(W2, b2, 4));
+  int o4, o5, e2, e3, x2, x4;
+  tdiv2<3>(wmad(W1, b1, 4), wmad(W7, b1, 4), o4, o5);
+  tdiv2<3>(wmad(W6, b2, 4), wmad(W2, b2, 4), e2, e3);
   const int h = wmad(181, o4, 128);
-  const int x2 = tdiv<8>(wmad(181, o5, h));
-  const int x4 = tdiv<8>(wmad(-181, o5, h));
-  const int Ap = wadd(x0, e3), Am = wsub(x0, e3), Bp = wadd(x0, e2), Bm = wsub(x0, e2);
-  b0 = wadd(tdiv<14>(wadd(Ap, o4)), 128);
-  b7 = wadd(tdiv<14>(wsub(Ap, o4)), 128);
-  b3 = wadd(tdiv<14>(wadd(Am, o5)), 128);
-  b4 = wadd(tdiv<14>(wsub(Am, o5)), 128);
-  b1 = wadd(tdiv<14>(wadd(Bp, x2)), 128);
-  b6 = wadd(tdiv<14>(wsub(Bp, x2)), 128);
-  b2 = wadd(tdiv<14>(wadd(Bm, x4)), 128);
-  b5 = wadd(tdiv<14>(wsub(Bm, x4)), 128);
+  tdiv2<8>(wmad(181, o5, h), wmad(-181, o5, h), x2, x4);
+  col_outputs(x0, x0, e2, e3, o4, o5, x2, x4, b0, b1, b2, b3, b4, b5, b6, b7);
 }
 
 // Inverse_DCT_8x8_Block on 64 registers (natural order, index = 8*row + col).
@@ -220,43 +321,6 @@ GID_HD ChromaTerms chroma_terms(int cb, int cr) {
   t.g = (-88 * cb - 183 * cr + 34816) >> 8;   // -88*(cb-128) - 183*(cr-128) + 128
   t.b = (454 * cb - 57984) >> 8;              // 454*(cb-128) + 128
   return t;
-}
-
-// Byte permute and 4-way byte dot products (PRMT, IDP.4A); the host versions
-// restate the PTX semantics so that the CPU suite exercises the same formulas.
-GID_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
-#if defined(__CUDA_ARCH__)
-  uint32_t d;
-  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
-  return d;
-#else
-  const uint64_t src = ((uint64_t)b << 32) | a;
-  uint32_t d = 0;
-  for (int i = 0; i < 4; i++) d |= (uint32_t)((src >> (8 * ((sel >> (4 * i)) & 7))) & 0xFF) << (8 * i);
-  return d;
-#endif
-}
-GID_HD int dp4a_uu(uint32_t a, uint32_t b, int c) {  // unsigned bytes x unsigned bytes
-#if defined(__CUDA_ARCH__)
-  int d;
-  asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-  return d;
-#else
-  unsigned acc = (unsigned)c;
-  for (int i = 0; i < 4; i++) acc += ((a >> (8 * i)) & 0xFF) * ((b >> (8 * i)) & 0xFF);
-  return (int)acc;
-#endif
-}
-GID_HD int dp4a_us(uint32_t a, uint32_t b, int c) {  // unsigned bytes x signed bytes
-#if defined(__CUDA_ARCH__)
-  int d;
-  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-  return d;
-#else
-  int acc = c;
-  for (int i = 0; i < 4; i++) acc += (int)((a >> (8 * i)) & 0xFF) * (int)(int8_t)((b >> (8 * i)) & 0xFF);
-  return acc;
-#endif
 }
 
 // The same terms from packed sample words: sample K (0..3) of cbw / crw.

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define GIDCUDA_ABI_VERSION 1
+#define GIDCUDA_ABI_VERSION 2
 
 /* Status codes.  The Ada binding maps DATA -> GID.error_in_image_data,
  * UNSUPPORTED -> GID.unsupported_image_subformat, the others ->
@@ -120,6 +120,29 @@ int16_t *gidcuda_job_plane(gidcuda_job *job, int comp, int32_t *blocks_x, int32_
  * gidcuda_job_begin) promises nothing.  Holds until changed or the job is released.
  * A decoder tracks it for free: rows_used = 1 + (largest zig_zag(k) it stored) / 8. */
 int gidcuda_job_hint_rows(gidcuda_job *job, int comp, int rows_used);
+/* ---- sparse coefficient input (optional, per component) --------------------
+ * What an entropy decoder produces is sparse: Decode_8x8_Block reads (run, value)
+ * pairs until EOB (:774-786), a handful per block at ordinary qualities, while a
+ * dense plane costs 128 bytes per block on the host link (the link, not the GPU,
+ * bounds a frame's end-to-end time).  Instead of storing into the plane of
+ * gidcuda_job_plane, the decoder may hand a component over as RECORDS:
+ *     records[n] = (uint32_t)(uint16_t)value << 16 | natural_index     (index = zig_zag(k), 0 .. 63)
+ *     first[seq] = n of the first record of block `seq`, first[nblocks] = number of records
+ * with `seq` counting the component's blocks in the order an interleaved scan visits
+ * them (:1190-1206): MCUs in raster order, inside an MCU the component's blocks row by
+ * row -- the order Baseline_DCT_Decoding_Scan decodes them in.  A progressive decoder
+ * compacts its accumulators in the same order when the last scan is done (the loop of
+ * Finalize_Progressive_DCT_Decoding, :1764-1775, visits every coefficient anyway).
+ * Zero-valued records are allowed; a natural index may appear once per block.
+ * gidcuda_job_records lends the two pinned arrays of component comp (first: nblocks + 1
+ * entries; records: *capacity entries = 32 per block, the size of the dense plane);
+ * gidcuda_job_records_commit(job, comp, count) declares them complete.  A decoder that
+ * runs out of capacity does not commit and fills the dense plane instead.  Components may
+ * be mixed (some committed, some dense).  On submit the library moves first[] and the
+ * records used, and a kernel rebuilds the dense plane in device memory. */
+int gidcuda_job_records(gidcuda_job *job, int comp, uint32_t **first, uint32_t **records, size_t *capacity,
+                        int32_t *nblocks);
+int gidcuda_job_records_commit(gidcuda_job *job, int comp, size_t count);
 /* Asynchronous: host-to-device copies, reconstruction kernel, device-to-host
  * copy of the pixels, all on the job's own stream (two jobs in flight overlap
  * their transfers).  A job may be submitted again after gidcuda_job_wait. */

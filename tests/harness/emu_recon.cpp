@@ -67,30 +67,54 @@ extern "C" int emu_reconstruct(const gidcuda_frame_desc *desc, const int16_t *co
       }
     return 0;
   }
+  // Fused layouts: the tiles, items and lanes of recon_tma_kernel / recon_ldg_kernel, run
+  // item by item (the lanes of a warp run an item together; in 4:2:x the luma items read the
+  // chroma samples another lane left in the warp's scratch).
   LdgSource src{&f};
-  u32x2 s_cb[8], s_cr[8], s_y[8];
-  Scratch sc{s_cb, s_cr, s_y, 1};
-  for (uint32_t tile = 0; tile < g.ntiles; tile++)
-    for (int t = 0; t < kTileMcusSetup; t++) {
-      const uint32_t m = (tile - f.tile_base) * kTileMcusSetup + t;
-      if (m >= (uint32_t)(f.mcux * f.mcuy)) continue;
-      const int my = (int)(m / (uint32_t)f.mcux), mx = (int)(m - (uint32_t)my * f.mcux);
-      const bool rgba = f.out_format == OUT_RGBA8;
-#define EMU_RUN(H, V, GREY)                                                                      \
-  do {                                                                                           \
-    if (f.q8) { if (rgba) mcu_run<H, V, GREY, true, true>(true, f, qw, src, sc, mx, my);          \
-                else mcu_run<H, V, GREY, true, false>(true, f, qw, src, sc, mx, my); }            \
-    else { if (rgba) mcu_run<H, V, GREY, false, true>(true, f, qw, src, sc, mx, my);              \
-           else mcu_run<H, V, GREY, false, false>(true, f, qw, src, sc, mx, my); }                \
+  u32x2 s_plane[3][8][kTileMcusSetup];
+  const bool linear = g.layout == LAYOUT_GREY || g.layout == LAYOUT_444;
+  const int ni = g.layout == LAYOUT_GREY ? 1 : (g.layout == LAYOUT_444 ? 3 : (g.layout == LAYOUT_422 ? 4 : 6));
+  const bool rgba = f.out_format == OUT_RGBA8;
+  const uint32_t nmcu = (uint32_t)(f.mcux * f.mcuy);
+  std::vector<uint32_t> tile_m0;
+  if (linear) {
+    for (uint32_t m0 = 0; m0 < nmcu; m0 += kTileMcusSetup) tile_m0.push_back(m0);
+  } else {
+    for (int my = 0; my < f.mcuy; my++)
+      for (int mx0 = 0; mx0 < f.mcux; mx0 += kTileMcusSetup) tile_m0.push_back((uint32_t)(my * f.mcux + mx0));
+  }
+  if (tile_m0.size() != g.ntiles && linear) return GIDCUDA_ERR_BAD_ARGUMENT;
+  for (uint32_t m0 : tile_m0)
+    for (int it = 0; it < ni; it++)
+      for (int t = 0; t < kTileMcusSetup; t++) {
+        int mx, my;
+        bool active;
+        if (linear) {  // tile_mcu of recon_kernels.cu
+          const uint32_t m = m0 + (uint32_t)t;
+          my = (int)(m / (uint32_t)f.mcux);
+          mx = (int)(m - (uint32_t)my * (uint32_t)f.mcux);
+          active = m < nmcu;
+        } else {
+          my = (int)(m0 / (uint32_t)f.mcux);
+          mx = (int)(m0 - (uint32_t)my * (uint32_t)f.mcux) + t;
+          active = mx < f.mcux;
+        }
+        Scratch sc{&s_plane[0][0][t], &s_plane[1][0][t], &s_plane[2][0][t], kTileMcusSetup};
+#define EMU_RUN(H, V, GREY)                                                                          \
+  do {                                                                                               \
+    if (f.q8) { if (rgba) mcu_item<H, V, GREY, true, true>(it, active, f, qw, src, sc, t, mx, my);    \
+                else mcu_item<H, V, GREY, true, false>(it, active, f, qw, src, sc, t, mx, my); }      \
+    else { if (rgba) mcu_item<H, V, GREY, false, true>(it, active, f, qw, src, sc, t, mx, my);        \
+           else mcu_item<H, V, GREY, false, false>(it, active, f, qw, src, sc, t, mx, my); }          \
   } while (0)
-      switch (g.layout) {
-        case LAYOUT_GREY: EMU_RUN(1, 1, true); break;
-        case LAYOUT_444: EMU_RUN(1, 1, false); break;
-        case LAYOUT_422: EMU_RUN(2, 1, false); break;
-        default: EMU_RUN(2, 2, false); break;
-      }
+        switch (g.layout) {
+          case LAYOUT_GREY: EMU_RUN(1, 1, true); break;
+          case LAYOUT_444: EMU_RUN(1, 1, false); break;
+          case LAYOUT_422: EMU_RUN(2, 1, false); break;
+          default: EMU_RUN(2, 2, false); break;
+        }
 #undef EMU_RUN
-    }
+      }
   return 0;
 }
 

@@ -24,7 +24,7 @@ def test_every_declared_symbol_is_exported(gidcuda_lib):
     for s in syms:
         assert hasattr(gidcuda_lib, s), s
     assert sorted(capi.EXPORTS) == syms
-    assert gidcuda_lib.gidcuda_abi_version() == 1
+    assert gidcuda_lib.gidcuda_abi_version() == 2
 
 
 def test_geometry_matches_gid(gidcuda_lib, synth):
@@ -96,3 +96,26 @@ def test_product_does_not_touch_the_oracle():
                 if re.search(r"gidref|oracle/|tests[./]harness|libemurecon", text):
                     bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_records_from_plane_scan_order():
+    """records_from_plane: blocks in interleaved-scan order, one record per non-zero coefficient."""
+    import numpy as np
+    from gid_b200 import capi
+    rng = np.random.default_rng(4)
+    by, bx, sh, sv = 4, 6, 2, 2
+    p = np.zeros((by, bx, 64), dtype=np.int16)
+    m = rng.random(p.shape) < 0.1
+    p[m] = rng.integers(-300, 300, size=int(m.sum()))
+    first, rec = capi.records_from_plane(p, sh, sv)
+    assert first[0] == 0 and first[-1] == rec.size == np.count_nonzero(p)
+    back = np.zeros_like(p)
+    seq = 0
+    for my in range(by // sv):
+        for mx in range(bx // sh):
+            for sy in range(sv):
+                for sx in range(sh):
+                    for w in rec[first[seq]:first[seq + 1]]:
+                        back[my * sv + sy, mx * sh + sx, int(w) & 63] = np.int16(np.uint16(int(w) >> 16))
+                    seq += 1
+    assert np.array_equal(back, p)

@@ -309,3 +309,70 @@ def test_batch_properties_full_size(oracle, synth, gidcuda_lib):
         for k, o in zip(order, outs):
             got = o.reshape(h, stride)[:, :3 * w].reshape(h, w, 3)
             assert np.array_equal(got, refs[k])
+
+
+# ---- sparse coefficient input (gidcuda_job_records) -----------------------------------
+
+
+@pytest.mark.parametrize("w,h,samp", GEOMETRIES)
+def test_sparse_records_match_oracle(gpu, oracle, synth, w, h, samp):
+    """The same frames supplied as coefficient records instead of dense planes."""
+    fr = synth.planes_only(pixels_for(synth, 13, w, h, samp), samp)
+    ref = oracle.reconstruct(fr)
+    # "auto": a component denser than 32 records per block (tiny noisy frames) goes as a plane
+    got = gpu.reconstruct_rgb(frame_desc(fr), fr.planes, sparse="auto")
+    assert np.array_equal(got, ref)
+
+
+def test_sparse_records_mixed_and_resubmitted(gpu, oracle, synth):
+    """Components may be mixed (records / dense plane / hinted dense plane); a job can be
+    filled again after a wait with different data in the other form."""
+    fr = synth.planes_only(pixels_for(synth, 17, 333, 217, "420"), "420")
+    ref = oracle.reconstruct(fr)
+    d = frame_desc(fr)
+    for sp in ([True, False, False], [False, True, True], [True, True, False]):
+        got = gpu.reconstruct_rgb(d, fr.planes, sparse=sp, hint_rows=True)
+        assert np.array_equal(got, ref), sp
+    # same job object recycled: dense after sparse and sparse after dense give the same pixels
+    assert np.array_equal(gpu.reconstruct_rgb(d, fr.planes), ref)
+    assert np.array_equal(gpu.reconstruct_rgb(d, fr.planes, sparse=True), ref)
+
+
+def test_sparse_records_random_and_limits(gpu, oracle, synth):
+    from gid_b200 import GidCudaError
+    from tests.harness import Frame, SAMPLING
+    rng = np.random.default_rng(21)
+    for samp in ("grey", "444", "422", "420", "411"):
+        w, h = 200, 136
+        bx, by = synth.grid(w, h, samp)
+        sh, sv = SAMPLING[samp]
+        qt = rng.integers(1, 256, size=(len(sh), 64)).astype(np.uint16)
+        fr = Frame(w, h, len(sh), list(sh), list(sv), bx, by, qt)
+        fr.planes = random_planes(rng, bx, by, "sparse")
+        ref = oracle.reconstruct(fr)
+        assert np.array_equal(gpu.reconstruct_rgb(frame_desc(fr), fr.planes, sparse=True), ref), samp
+    # exactly at capacity (32 records per block on average) is accepted ...
+    bx, by = synth.grid(64, 64, "grey")
+    fr = Frame(64, 64, 1, [1], [1], bx, by, np.full((1, 64), 3, dtype=np.uint16))
+    p = np.zeros((by[0], bx[0], 64), dtype=np.int16)
+    p[:, :, :32] = rng.integers(1, 50, size=(by[0], bx[0], 32))
+    fr.planes = [p]
+    assert np.array_equal(gpu.reconstruct_rgb(frame_desc(fr), fr.planes, sparse=True), oracle.reconstruct(fr))
+    # ... one more is refused by the binding (the decoder then uses the dense plane)
+    p[0, 0, 40] = 7
+    with pytest.raises(OverflowError):
+        gpu.reconstruct_rgb(frame_desc(fr), fr.planes, sparse=True)
+    # a commit whose first[] does not frame the records is rejected
+    L = gpu.lib
+    job = ctypes.c_void_p()
+    d = frame_desc(fr)
+    assert L.gidcuda_job_begin(gpu.ctx, ctypes.byref(d), ctypes.byref(job)) == 0
+    pf, pr, cap, nb = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_size_t(), ctypes.c_int32()
+    assert L.gidcuda_job_records(job, 0, ctypes.byref(pf), ctypes.byref(pr), ctypes.byref(cap), ctypes.byref(nb)) == 0
+    assert nb.value == bx[0] * by[0] and cap.value == 32 * nb.value
+    ctypes.memset(pf, 0, 4 * (nb.value + 1))
+    assert L.gidcuda_job_records_commit(job, 0, 5) == -1
+    assert L.gidcuda_job_submit(job) == -6      # neither planes nor records
+    assert L.gidcuda_job_release(job) == 0
+    with pytest.raises(GidCudaError):
+        gpu.reconstruct_rgb(frame_desc(fr), [p[:1]], sparse=True)
