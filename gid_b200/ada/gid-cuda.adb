@@ -87,6 +87,27 @@ package body GID.CUDA is
     Check (gidcuda_job_hint_rows (j, C.int (comp), C.int (rows_used)), Null_Context);
   end Hint_Rows;
 
+  procedure Records
+    (j : Job; comp : Natural;
+     first, records : out System.Address; capacity, nblocks : out Natural)
+  is
+    f, r : aliased System.Address := System.Null_Address;
+    cap  : aliased C.size_t := 0;
+    nb   : aliased Interfaces.Integer_32 := 0;
+  begin
+    Check (gidcuda_job_records (j, C.int (comp), f'Access, r'Access, cap'Access, nb'Access),
+           Null_Context);
+    first    := f;
+    records  := r;
+    capacity := Natural (cap);
+    nblocks  := Natural (nb);
+  end Records;
+
+  procedure Records_Commit (j : Job; comp : Natural; count : Natural) is
+  begin
+    Check (gidcuda_job_records_commit (j, C.int (comp), C.size_t (count)), Null_Context);
+  end Records_Commit;
+
   procedure Submit (j : Job) is
   begin
     Check (gidcuda_job_submit (j), Null_Context);

@@ -74,7 +74,19 @@ private package GID.CUDA is
   --  Promise that rows >= rows_used of every block of the plane are zero (1 .. 8).
   procedure Hint_Rows (j : Job; comp : Natural; rows_used : Positive);
 
-  procedure Submit (j : Job);   --  asynchronous: H2D, kernel, D2H
+  --  Sparse alternative to Plane (include/gidcuda.h, "sparse coefficient input"):
+  --  one 32-bit record per NON-ZERO coefficient,
+  --     record = Shift_Left (Unsigned_32 (Unsigned_16'Mod (value)), 16) or natural_index,
+  --  and first (seq) = index of the first record of block seq, blocks counted in the
+  --  order Baseline_DCT_Decoding_Scan visits them (:1190-1206); first (nblocks) = count.
+  --  capacity = 32 records per block; a decoder that runs out does not commit and
+  --  fills the dense plane instead.
+  procedure Records
+    (j : Job; comp : Natural;
+     first, records : out System.Address; capacity, nblocks : out Natural);
+  procedure Records_Commit (j : Job; comp : Natural; count : Natural);
+
+  procedure Submit (j : Job);   --  asynchronous: H2D, kernel(s), D2H
   procedure Wait   (j : Job; pixels : out System.Address; stride : out Natural);
   procedure Release (j : in out Job);
 
@@ -110,6 +122,14 @@ private
 
   function gidcuda_job_hint_rows (j : Job; comp, rows_used : C.int) return C.int;
   pragma Import (C, gidcuda_job_hint_rows, "gidcuda_job_hint_rows");
+
+  function gidcuda_job_records
+    (j : Job; comp : C.int; first, records : access System.Address;
+     capacity : access C.size_t; nblocks : access Interfaces.Integer_32) return C.int;
+  pragma Import (C, gidcuda_job_records, "gidcuda_job_records");
+
+  function gidcuda_job_records_commit (j : Job; comp : C.int; count : C.size_t) return C.int;
+  pragma Import (C, gidcuda_job_records_commit, "gidcuda_job_records_commit");
 
   function gidcuda_job_submit (j : Job) return C.int;
   pragma Import (C, gidcuda_job_submit, "gidcuda_job_submit");

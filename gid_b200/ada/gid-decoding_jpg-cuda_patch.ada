@@ -110,6 +110,59 @@
     end Decode_8x8_Block;
 
     ------------------------------------------------------------------
+    --  Sparse variant of the above (the one the C++ host mirror uses by default):
+    --  instead of storing into the dense plane, append one record per non-zero
+    --  value; 128 bytes per block on the host link become 4 bytes per non-zero
+    --  coefficient + 4 per block.  State per component, set up in
+    --  Begin_Device_Frame with GID.CUDA.Records:
+    --     rec_first (c), rec_data (c) : System.Address;  rec_cap (c), rec_n (c), rec_seq (c) : Natural
+    --  If rec_n (c) + 64 > rec_cap (c) at the start of a block the component switches
+    --  to its dense plane for good: the records emitted so far are replayed into the
+    --  plane (block of sequence number s = the s-th block this loop visited) and
+    --  Decode_8x8_Block above takes over.  After the scan:
+    --     first (nblocks) := rec_n (c);  GID.CUDA.Records_Commit (cuda_job, comp_index (c), rec_n (c));
+    --  Progressive files keep accumulating in (ordinary, not pinned) int16 planes and
+    --  compact them the same way in Finalize_Progressive_DCT_Decoding.
+    ------------------------------------------------------------------
+    procedure Decode_8x8_Block_Sparse (c : Component) is
+      value, coef : Integer;
+      code : U8;
+      procedure Emit (nat : Natural; v : Integer) is
+        type Record_Array is array (Natural) of Interfaces.Unsigned_32;
+        data : Record_Array;
+        for data'Address use rec_data (c);
+        pragma Import (Ada, data);
+        use Interfaces;
+      begin
+        if v /= 0 then
+          data (rec_n (c)) :=
+            Shift_Left (Unsigned_32 (Unsigned_16'Mod (v)), 16) or Unsigned_32 (nat);
+          rec_n (c) := rec_n (c) + 1;
+        end if;
+      end Emit;
+    begin
+      Set_First (c, rec_seq (c), rec_n (c));   --  first (seq) := n
+      rec_seq (c) := rec_seq (c) + 1;
+      Get_VLC (image.JPEG_stuff.vlc_defs (DC, info_B (c).ht_idx_DC).all, code, value);
+      info_B (c).dc_predictor := info_B (c).dc_predictor + value;
+      Emit (0, info_B (c).dc_predictor);
+      coef := 0;
+      loop
+        Get_VLC (image.JPEG_stuff.vlc_defs (AC, info_B (c).ht_idx_AC).all, code, value);
+        exit when code = 0;
+        if (code and 16#0F#) = 0 and code /= 16#F0# then
+          raise error_in_image_data with "JPEG: error in VLC AC code for de-quantization";
+        end if;
+        coef := coef + Integer (Shift_Right (code, 4)) + 1;
+        if coef > 63 then
+          raise error_in_image_data with "JPEG: coefficient for de-quantization is > 63";
+        end if;
+        Emit (zig_zag (coef), value);
+        exit when coef = 63;
+      end loop;
+    end Decode_8x8_Block_Sparse;
+
+    ------------------------------------------------------------------
     --  Steps 3-6 for the whole frame: replaces Inverse_DCT_8x8_Block (:1199),
     --  Upsampling_and_Output (:1206) and, for progressive files, the body of
     --  Finalize_Progressive_DCT_Decoding (:1789-1850).

@@ -88,6 +88,10 @@ struct Image_Descriptor {
   // the stream the header was read from (GID keeps it attached, gid.ads:345)
   Stream *stream = nullptr;
   int device = 0;  // CUDA device used by Load_Image_Contents (not in the reference)
+  // Coefficients reach the device as sparse records (gidcuda_job_records: one record per
+  // non-zero coefficient, the entropy decoder's natural output) unless this is false: then, or
+  // for a component too dense for the record buffer, as dense int16 planes.
+  bool sparse_input = true;
 };
 
 // gid.ads:64-67.  try_tga is accepted for signature compatibility and ignored.

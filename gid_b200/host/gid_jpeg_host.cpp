@@ -319,6 +319,17 @@ struct PlaneRef {
   int16_t *block(int bx, int by) const { return base + ((size_t)by * (size_t)blocks_x + (size_t)bx) * 64; }
 };
 
+// Sparse output of the entropy decoder for one component (include/gidcuda.h, "sparse
+// coefficient input"): first[seq] = index of the first record of block seq (blocks in the
+// order the interleaved scan visits them), record = (uint16)value << 16 | natural index.
+struct RecordSink {
+  uint32_t *first = nullptr, *rec = nullptr;
+  size_t cap = 0, n = 0;
+  uint32_t seq = 0, nblocks = 0;
+  bool on = false;
+  void put(int nat, int value) { rec[n++] = ((uint32_t)(uint16_t)(int16_t)value << 16) | (uint32_t)nat; }
+};
+
 struct Decoder {
   Image_Descriptor &im;
   Reader r;
@@ -327,6 +338,8 @@ struct Decoder {
   std::function<void()> begin_frame;  // called at the first SOS: tables and geometry are final (:1857)
   HuffTable huff[2][8];
   PlaneRef plane[3];
+  RecordSink sink[3];                 // baseline: components emitted as records while sink[c].on
+  std::function<void(int)> spill;     // sink[c] is nearly full: switch component c to its dense plane
   int dc_pred[3] = {0, 0, 0};
   int last_row[3] = {0, 0, 0};  // last block row (natural order) a coefficient was stored in, per component
   int ht_dc[3] = {0, 0, 0}, ht_ac[3] = {0, 0, 0};
@@ -374,11 +387,17 @@ struct Decoder {
   }
 
   // Decode_8x8_Block (:758-788) without the de-quantisation: values are stored as
-  // read, at their natural position; the multiplication by qt_local moves to the GPU.
-  void baseline_block(int c, int16_t *blk) {
+  // read, at their natural position -- as records (one per non-zero value) or into the
+  // dense plane; the multiplication by qt_local moves to the GPU.
+  void baseline_block(int c, int bx, int by) {
+    RecordSink &k = sink[c];
+    if (k.on && k.n + 64 > k.cap) spill(c);
+    int16_t *blk = k.on ? nullptr : plane[c].block(bx, by);
+    if (k.on) k.first[k.seq++] = (uint32_t)k.n;
     const int s = bits.symbol(table(0, ht_dc[c]));
     dc_pred[c] += bits.receive_extend(s & 15);
-    blk[0] = (int16_t)dc_pred[c];
+    if (blk) blk[0] = (int16_t)dc_pred[c];
+    else if ((int16_t)dc_pred[c] != 0) k.put(0, dc_pred[c]);
     const HuffTable &ac = table(1, ht_ac[c]);
     int coef = 0;
     for (;;) {
@@ -389,8 +408,13 @@ struct Decoder {
       coef += (code >> 4) + 1;
       if (coef > 63) throw error_in_image_data("JPEG: coefficient for de-quantization is > 63");
       const int nat = kZigZag[coef];
-      blk[nat] = (int16_t)bits.receive_extend(code & 15);
-      if ((nat >> 3) > last_row[c]) last_row[c] = nat >> 3;
+      const int value = bits.receive_extend(code & 15);
+      if (blk) {
+        blk[nat] = (int16_t)value;
+        if ((nat >> 3) > last_row[c]) last_row[c] = nat >> 3;
+      } else if ((int16_t)value != 0) {
+        k.put(nat, value);
+      }
       if (coef == 63) break;
     }
   }
@@ -406,7 +430,7 @@ struct Decoder {
           const Component_Info &ci = im.info[c];
           for (int sy = 0; sy < ci.samples_ver; sy++)
             for (int sx = 0; sx < ci.samples_hor; sx++)
-              baseline_block(c, plane[c].block(mx * ci.samples_hor + sx, my * ci.samples_ver + sy));
+              baseline_block(c, mx * ci.samples_hor + sx, my * ci.samples_ver + sy);
         }
         if (!(my == mv - 1 && mx == mh - 1)) check_restart(true);
       }
@@ -708,6 +732,37 @@ void decode_planes(Image_Descriptor &image, gidcuda_frame_desc *desc, int16_t *p
   if (!dec.plane[0].base) throw error_in_image_data("JPEG: no scan in the image");
 }
 
+// Block (bx, by) with sequence number seq: MCUs in raster order, inside an MCU the
+// component's h x v blocks row by row (the visiting order of :1190-1206).
+static void seq_to_block(uint32_t seq, int h, int v, int mcux, int *bx, int *by) {
+  const uint32_t hv = (uint32_t)(h * v), mcu = seq / hv, r = seq - mcu * hv;
+  const uint32_t sy = r / (uint32_t)h, sx = r - sy * (uint32_t)h;
+  *bx = (int)(mcu % (uint32_t)mcux) * h + (int)sx;
+  *by = (int)(mcu / (uint32_t)mcux) * v + (int)sy;
+}
+
+// Progressive frames accumulate in dense planes over the scans; when the last scan is done the
+// non-zero coefficients are compacted into records (the loop of Finalize_Progressive_DCT_Decoding,
+// :1764-1775, visits every coefficient anyway).  False when they do not fit.
+static bool compact_plane(const PlaneRef &pl, int h, int v, uint32_t *first, uint32_t *rec, size_t cap,
+                          size_t *count) {
+  const int mcux = pl.blocks_x / h;
+  const uint32_t nb = (uint32_t)pl.blocks_x * (uint32_t)pl.blocks_y;
+  size_t n = 0;
+  for (uint32_t seq = 0; seq < nb; seq++) {
+    int bx, by;
+    seq_to_block(seq, h, v, mcux, &bx, &by);
+    const int16_t *blk = pl.block(bx, by);
+    first[seq] = (uint32_t)n;
+    if (n + 64 > cap) return false;
+    for (int i = 0; i < 64; i++)
+      if (blk[i] != 0) rec[n++] = ((uint32_t)(uint16_t)blk[i] << 16) | (uint32_t)i;
+  }
+  first[nb] = (uint32_t)n;
+  *count = n;
+  return true;
+}
+
 Reconstruction decode_and_reconstruct(Image_Descriptor &image, const std::function<void(int)> &feedback) {
   if (!image.stream) throw constraint_error("Load_Image_Contents: no header was loaded");
   gidcuda_frame_desc desc;
@@ -718,30 +773,97 @@ Reconstruction decode_and_reconstruct(Image_Descriptor &image, const std::functi
   int rc = gidcuda_create(image.device, &ctx);
   if (rc != GIDCUDA_OK) raise_from_status(rc, nullptr);
   gidcuda_job *job = nullptr;
+  // progressive + sparse input: the scans accumulate in ordinary host memory
+  std::vector<std::vector<int16_t>> accum(3);
+  const bool sparse = image.sparse_input;
   // The job is begun at the first SOS, like Begin_Device_Frame of the Ada patch:
   // every DQT has been read by then (GID accepts none after entropy-coded data).
   Decoder dec(image, feedback);
+  auto use_job_plane = [&](int c) {
+    int32_t bx = 0, by = 0;
+    dec.plane[c].base = gidcuda_job_plane(job, comp_of[c], &bx, &by);
+    dec.plane[c].blocks_x = bx;
+    dec.plane[c].blocks_y = by;
+    if (!dec.plane[c].base) raise_from_status(GIDCUDA_ERR_STATE, ctx);
+  };
   try {
     dec.begin_frame = [&]() {
       fill_tables(image, &desc, comp_of);
       int st = gidcuda_job_begin(ctx, &desc, &job);
       if (st != GIDCUDA_OK) raise_from_status(st, ctx);
-      for (int c = 0; c < 3; c++)
-        if (image.info[c].present) {
+      for (int c = 0; c < 3; c++) {
+        if (!image.info[c].present) continue;
+        if (!sparse) {
+          use_job_plane(c);
+        } else if (image.progressive) {
           int32_t bx = 0, by = 0;
-          dec.plane[c].base = gidcuda_job_plane(job, comp_of[c], &bx, &by);
+          st = gidcuda_plane_geometry(&desc, comp_of[c], &bx, &by);
+          if (st != GIDCUDA_OK) raise_from_status(st, ctx);
+          accum[c].assign((size_t)bx * (size_t)by * 64, 0);
+          dec.plane[c].base = accum[c].data();
           dec.plane[c].blocks_x = bx;
           dec.plane[c].blocks_y = by;
-          if (!dec.plane[c].base) raise_from_status(GIDCUDA_ERR_STATE, ctx);
+        } else {
+          RecordSink &k = dec.sink[c];
+          int32_t nb = 0;
+          st = gidcuda_job_records(job, comp_of[c], &k.first, &k.rec, &k.cap, &nb);
+          if (st != GIDCUDA_OK) raise_from_status(st, ctx);
+          k.nblocks = (uint32_t)nb;
+          k.n = 0;
+          k.seq = 0;
+          k.on = true;
         }
+      }
+    };
+    // A baseline component outgrew its record buffer (more than 32 non-zero coefficients per
+    // block on average): replay its records into the dense plane and carry on there.
+    dec.spill = [&](int c) {
+      RecordSink &k = dec.sink[c];
+      use_job_plane(c);
+      const Component_Info &ci = image.info[c];
+      const int mcux = dec.plane[c].blocks_x / ci.samples_hor;
+      for (uint32_t seq = 0; seq < k.seq; seq++) {
+        int bx, by;
+        seq_to_block(seq, ci.samples_hor, ci.samples_ver, mcux, &bx, &by);
+        int16_t *blk = dec.plane[c].block(bx, by);
+        const uint32_t end = seq + 1 < k.seq ? k.first[seq + 1] : (uint32_t)k.n;
+        for (uint32_t i = k.first[seq]; i < end; i++) {
+          const int nat = (int)(k.rec[i] & 63u);
+          blk[nat] = (int16_t)(k.rec[i] >> 16);
+          if ((nat >> 3) > dec.last_row[c]) dec.last_row[c] = nat >> 3;
+        }
+      }
+      k.on = false;
     };
     dec.run();
     if (!job) throw error_in_image_data("JPEG: no scan in the image");
-    for (int c = 0; c < 3; c++)
-      if (image.info[c].present) {
-        rc = gidcuda_job_hint_rows(job, comp_of[c], dec.last_row[c] + 1);
+    for (int c = 0; c < 3; c++) {
+      if (!image.info[c].present) continue;
+      RecordSink &k = dec.sink[c];
+      if (sparse && image.progressive) {
+        uint32_t *first = nullptr, *rec = nullptr;
+        size_t cap = 0, count = 0;
+        rc = gidcuda_job_records(job, comp_of[c], &first, &rec, &cap, nullptr);
         if (rc != GIDCUDA_OK) raise_from_status(rc, ctx);
+        const Component_Info &ci = image.info[c];
+        if (compact_plane(dec.plane[c], ci.samples_hor, ci.samples_ver, first, rec, cap, &count)) {
+          rc = gidcuda_job_records_commit(job, comp_of[c], count);
+          if (rc != GIDCUDA_OK) raise_from_status(rc, ctx);
+          continue;
+        }
+        const PlaneRef acc = dec.plane[c];
+        use_job_plane(c);
+        memcpy(dec.plane[c].base, acc.base, accum[c].size() * sizeof(int16_t));
+      } else if (k.on) {
+        if (k.seq != k.nblocks) throw error_in_image_data("JPEG: scan ended before the last block");
+        k.first[k.nblocks] = (uint32_t)k.n;
+        rc = gidcuda_job_records_commit(job, comp_of[c], k.n);
+        if (rc != GIDCUDA_OK) raise_from_status(rc, ctx);
+        continue;
       }
+      rc = gidcuda_job_hint_rows(job, comp_of[c], dec.last_row[c] + 1);
+      if (rc != GIDCUDA_OK) raise_from_status(rc, ctx);
+    }
     rc = gidcuda_job_submit(job);
     if (rc != GIDCUDA_OK) raise_from_status(rc, ctx);
     Reconstruction rec;
@@ -824,6 +946,17 @@ int gidhost_probe(const uint8_t *data, size_t len, int32_t *width, int32_t *heig
 // (top-down packed RGB8, idx = 3 * (x + W * (H - 1 - y))).  modulus = 256 or 65536
 // selects the Primary_Color_Range instance (16-bit values are stored as their high
 // byte, = value / 257); anything else raises invalid_primary_color_range.
+// Process-wide options of the flat entry points: "sparse_input" 1 (default) = coefficients reach
+// the device as records, 0 = as dense planes (Image_Descriptor::sparse_input).
+static int g_sparse_input = 1;
+int gidhost_set_option(const char *name, int value) {
+  if (name && strcmp(name, "sparse_input") == 0) {
+    g_sparse_input = value != 0;
+    return GIDHOST_OK;
+  }
+  return GIDHOST_BAD_ARGUMENT;
+}
+
 int gidhost_decode_rgb(const uint8_t *data, size_t len, int device, uint32_t modulus, uint8_t *rgb,
                        size_t rgb_capacity, int32_t *feedback_log, int32_t feedback_cap, int32_t *feedback_n,
                        char *err, size_t errlen) {
@@ -832,6 +965,7 @@ int gidhost_decode_rgb(const uint8_t *data, size_t len, int device, uint32_t mod
     gid::Image_Descriptor im;
     gid::Load_Image_Header(im, st);
     im.device = device;
+    im.sparse_input = g_sparse_input != 0;
     const int W = gid::Pixel_Width(im), H = gid::Pixel_Height(im);
     if ((size_t)3 * (size_t)W * (size_t)H > rgb_capacity) {
       if (err && errlen) snprintf(err, errlen, "output buffer too small");

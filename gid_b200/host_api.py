@@ -59,6 +59,8 @@ def load_library() -> ctypes.CDLL:
     L.gidhost_decode_planes.argtypes = [vp, ctypes.c_size_t, ctypes.POINTER(capi.FrameDesc),
                                         ctypes.POINTER(vp), i32p, i32p, ctypes.c_char_p, ctypes.c_size_t]
     L.gidhost_free.argtypes = [vp]
+    L.gidhost_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int]
+    L.gidhost_set_option.restype = ctypes.c_int
     L.gidhost_free.restype = None
     for n in EXPORTS[:3]:
         getattr(L, n).restype = ctypes.c_int
@@ -88,6 +90,13 @@ def probe(data: bytes) -> Header:
     if rc != 0:
         raise GidHostError(rc, err.value.decode(errors="replace"))
     return Header(v[0].value, v[1].value, v[2].value, bool(v[3].value), v[4].value)
+
+
+def set_option(name: str, value: int) -> None:
+    """"sparse_input": 1 (default) = coefficients reach the device as records, 0 = as dense planes."""
+    rc = load_library().gidhost_set_option(name.encode(), value)
+    if rc != 0:
+        raise GidHostError(rc, f"unknown option {name}")
 
 
 def decode_rgb(data: bytes, device: int = 0, modulus: int = 256):

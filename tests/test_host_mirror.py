@@ -134,9 +134,17 @@ def test_exif_orientation(host, synth):
 # --------------------------------------------------------------------------- GPU
 
 
+@pytest.fixture(params=["records", "planes"])
+def coef_form(request, host):
+    """Both forms in which the entropy decoder hands coefficients to the device."""
+    host.set_option("sparse_input", 1 if request.param == "records" else 0)
+    yield request.param
+    host.set_option("sparse_input", 1)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("cfg", CONFIG_SMALL, ids=[c["name"] for c in CONFIG_SMALL])
-def test_load_image_contents_matches_gid(host, oracle, synth, gpu, cfg):
+def test_load_image_contents_matches_gid(host, oracle, synth, gpu, coef_form, cfg):
     """.jpg -> gid::Load_Image_Header + gid::Load_Image_Contents (entropy decode on the host,
     reconstruction on the B200, pixels replayed through Set_X_Y / Put_Pixel) == GID's decode."""
     jpg, _ = synth.encode(pixels_for(synth, 5, cfg["w"], cfg["h"], cfg["samp"]), cfg["samp"],
@@ -148,8 +156,23 @@ def test_load_image_contents_matches_gid(host, oracle, synth, gpu, cfg):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("prog", [False, True], ids=["baseline", "progressive"])
+def test_dense_frames_outgrow_the_record_buffer(host, oracle, synth, gpu, prog):
+    """Quality 100 on noise: more than 32 non-zero coefficients per block on average, so the
+    decoder runs out of record capacity part-way and carries on in the dense plane
+    (baseline: replaying the records it had; progressive: at compaction time)."""
+    rng = np.random.default_rng(8)
+    pix = rng.integers(0, 256, size=(96, 160, 3), dtype=np.uint8)
+    jpg, enc = synth.encode(pix, "420", quality=100, progressive=prog)
+    assert sum(int(np.count_nonzero(p)) for p in enc.planes) > 32 * sum(p.shape[0] * p.shape[1] for p in enc.planes)
+    _, ref, _ = oracle.decode(jpg)
+    rgb, _ = host.decode_rgb(jpg)
+    assert np.array_equal(rgb, ref)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("name,ent", _golden_files(), ids=[n for n, _ in _golden_files()])
-def test_golden_files_through_host_mirror(host, gpu, name, ent):
+def test_golden_files_through_host_mirror(host, gpu, coef_form, name, ent):
     data = open(os.path.join(GOLDEN, name), "rb").read()
     rgb, _ = host.decode_rgb(data)
     assert hashlib.sha256(rgb.tobytes()).hexdigest() == ent["rgb_sha256"]
