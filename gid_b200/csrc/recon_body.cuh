@@ -90,6 +90,9 @@ inline int dp2a_hi_su(uint32_t a, uint32_t b, int c) {
 // and the host build).
 struct LdgSource {
   const FrameDev *f;
+  // where the packed samples of the luma block being emitted go; nothing to hand back
+  GID_HD u32x2 *luma_scratch(u32x2 *own) const { return own; }
+  GID_HD void release() const {}
   GID_HD void load(bool active, int comp, int bx, int by, u32x4 (&raw)[8]) const {
     if (!active) {  // lane without an MCU: nothing to read, contributes zeros
 #pragma unroll
@@ -457,9 +460,24 @@ GID_HD void mcu_item(int it, bool active, const FrameDev &f, const uint32_t *qw,
   }
   u32x4 raw[8];
   src.load(active, comp, bxi, byi, raw);
-  u32x2 *dst = comp == 0 ? sc.y : (comp == 1 ? sc.cb : sc.cr);
+  // Chroma samples stay in the scratch for the whole tile.  The luma samples only live from
+  // here to the end of the emit: the TMA source lends the ring slot the raw block just came
+  // out of for them (no luma scratch of its own: 2 KiB less shared memory per warp, which is
+  // what lets a 16th warp onto the SM) and gets it back -- re-armed for the item two steps
+  // ahead -- when the pixels are out.  Chroma items hand their slot back at once.
+  u32x2 *dst;
+  if (comp == 0) {
+    dst = src.luma_scratch(sc.y);
+    se.y = dst;
+  } else {
+    dst = comp == 1 ? sc.cb : sc.cr;
+    src.release();
+  }
   dequant_idct_sparse<Q8, H * V == 1>(active, raw, qw + 32 * comp, dst, sc.stride);
-  if (comp == 0 && active) emit_block_rows<H, V, GREY, RGBA>(f, se, bxi * 8, byi * 8, sx, sy);
+  if (comp == 0) {
+    if (active) emit_block_rows<H, V, GREY, RGBA>(f, se, bxi * 8, byi * 8, sx, sy);
+    src.release();
+  }
 }
 
 template <int H, int V, bool GREY, bool Q8, bool RGBA, class Src>

@@ -37,16 +37,22 @@ static_assert(sizeof(FrameDev) % 16 == 0, "FrameDev is copied in 16-byte pieces"
 //           launches with many tiles per warp (batches).
 //   Narrow: 3 CTAs x 4 warps per SM -- SMs are handed to the next launch a CTA at a
 //           time, which shortens tail + ramp of short launches (one frame): +3 %.
+// 16 warps per SM = 4 per scheduler, the most 128 registers per thread allow.  Shared memory
+// per warp: the 8 KiB ring, 4 KiB of chroma scratch, the frame copy and the barriers (the luma
+// samples borrow the ring slot of their own item, see mcu_item).  (Dropping the per-warp copy of
+// the frame descriptor instead and reading it from global memory was measured: -6 % on 4:2:0
+// batches, -13 % on grey.)
+constexpr int kWideWarps = 16;
 template <int WPC> struct Shape {
-  static_assert(WPC == 15 || WPC == 4, "supported CTA shapes");
-  static constexpr int kWarps = WPC;
-  static constexpr int kCtasPerSm = WPC == 15 ? 1 : 3;
+  static_assert(WPC == kWideWarps || WPC == 4, "supported CTA shapes");
+  static constexpr int kCtasPerSm = WPC == kWideWarps ? 1 : 4;
   static constexpr int kThreads = WPC * 32;
 };
 constexpr int kNumSlots = 2;
 constexpr int kSlotBytes = kTileMcus * 128;            // one block (64 x int16) per lane
 constexpr int kRingBytes = kNumSlots * kSlotBytes;
-constexpr int kScratchBytes = 3 * 8 * kTileMcus * 8;   // per warp: [3 planes][8 rows][32 lanes] x 8 bytes
+constexpr int kScratchBytes = 2 * 8 * kTileMcus * 8;   // per warp: [Cb, Cr][8 rows][32 lanes] x 8 bytes
+constexpr int kLdgScratchBytes = 3 * 8 * kTileMcus * 8;  // plain-load kernel: + a luma plane
 constexpr int kFrameBytes = (int)((sizeof(FrameDev) + 127) / 128 * 128);
 constexpr int kBarBytes = kNumSlots * 8 + 64;  // per warp: the slot barriers + the ring of claimed tiles (4 x uint4)
 // dynamic shared memory of one CTA: rings (1024-byte aligned), scratches, frame caches, barriers
@@ -161,6 +167,7 @@ template <int LAYOUT>
 struct TmaSource {
   using LI = LayoutInfo<LAYOUT>;
   uint32_t slots, full;   // shared-window addresses (this warp)
+  uint8_t *slots_gen;     // the ring again, as a generic pointer
   uint32_t lane_off;      // lane * 128 + ((lane & 7) << 4): row `lane`, chunk index pre-xored
   uint32_t slot, phase;   // consume cursor
   const TileDesc *tiles;
@@ -238,7 +245,15 @@ struct TmaSource {
     const uint32_t base = slots + slot * kSlotBytes + lane_off;
 #pragma unroll
     for (int j = 0; j < 8; j++) raw[j] = lds128(base ^ (uint32_t)(j << 4));
-    // every lane has its block in registers: hand the slot back to the async proxy
+    __syncwarp();  // every lane has its block in registers: the slot's bytes are free
+  }
+  // The slot just read, as [8 rows][32 lanes] x 8 bytes for the packed luma samples (same layout
+  // as the chroma scratch; the first 2 KiB of the 4 KiB slot).
+  __device__ __forceinline__ u32x2 *luma_scratch(u32x2 *) const {
+    return reinterpret_cast<u32x2 *>(slots_gen + slot * kSlotBytes) + (threadIdx.x & 31);
+  }
+  // hand the slot back to the async proxy, re-armed with the item under the fetch cursor
+  __device__ __forceinline__ void release() {
     __syncwarp();
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     refill(slot);
@@ -247,12 +262,12 @@ struct TmaSource {
   }
 };
 
-__device__ __forceinline__ Scratch make_scratch(uint8_t *base, uint32_t lane) {
+__device__ __forceinline__ Scratch make_scratch(uint8_t *base, uint32_t lane, bool with_luma) {
   Scratch sc;
   u32x2 *p = reinterpret_cast<u32x2 *>(base) + lane;
   sc.cb = p;
   sc.cr = p + 8 * kTileMcus;
-  sc.y = p + 16 * kTileMcus;
+  sc.y = with_luma ? p + 16 * kTileMcus : nullptr;
   sc.stride = kTileMcus;
   return sc;
 }
@@ -302,6 +317,7 @@ recon_tma_kernel(const __grid_constant__ CUtensorMap map2, const FrameDev *__res
   uint8_t *gen = dyn_smem + (base - smem_u32(dyn_smem));
   TmaSource<LAYOUT> src;
   src.slots = base + warp * kRingBytes;
+  src.slots_gen = gen + warp * kRingBytes;
   src.full = base + kOffBars + warp * kBarBytes;
   src.claimed = reinterpret_cast<volatile uint4 *>(gen + kOffBars + warp * kBarBytes + kNumSlots * 8);
   src.lane_off = lane * 128u + ((lane & 7u) << 4);
@@ -321,7 +337,7 @@ recon_tma_kernel(const __grid_constant__ CUtensorMap map2, const FrameDev *__res
   __syncwarp();
   src.start();
 
-  const Scratch scratch = make_scratch(gen + kOffScratch + warp * kScratchBytes, lane);
+  const Scratch scratch = make_scratch(gen + kOffScratch + warp * kScratchBytes, lane, false);
   uint8_t *frame_cache = gen + kOffFrame + warp * kFrameBytes;
   const FrameDev &f = *reinterpret_cast<const FrameDev *>(frame_cache);
   uint32_t cur_frame = 0xFFFFFFFFu;
@@ -345,7 +361,7 @@ template <int LAYOUT, bool Q8, bool RGBA>
 __global__ void __launch_bounds__(kLdgWarps * 32)
 recon_ldg_kernel(const FrameDev *__restrict__ frames, const TileDesc *__restrict__ tiles, uint32_t ntiles) {
   __shared__ __align__(16) uint8_t s_frame[kLdgWarps][kFrameBytes];
-  __shared__ __align__(16) uint8_t s_scratch[kLdgWarps][kScratchBytes];
+  __shared__ __align__(16) uint8_t s_scratch[kLdgWarps][kLdgScratchBytes];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t tile = blockIdx.x * kLdgWarps + warp;
   if (tile >= ntiles) return;
@@ -356,7 +372,7 @@ recon_ldg_kernel(const FrameDev *__restrict__ frames, const TileDesc *__restrict
   int mx, my;
   const bool active = tile_mcu<LAYOUT>(f, m0, lane, mx, my);
   LdgSource src{&f};
-  run_mcu<LAYOUT, Q8, RGBA>(active, f, src, make_scratch(s_scratch[warp], lane), (int)lane, mx, my);
+  run_mcu<LAYOUT, Q8, RGBA>(active, f, src, make_scratch(s_scratch[warp], lane, true), (int)lane, mx, my);
 }
 
 // ---- generic path -----------------------------------------------------------
@@ -454,9 +470,9 @@ cudaError_t launch_one(bool use_tma, const CUtensorMap *map2, const FrameDev *d_
                        const TileDesc *d_tiles, uint32_t ntiles, uint32_t *d_counters, int num_sms,
                        cudaStream_t stream) {
   if (use_tma) {
-    const bool narrow = ntiles < (uint32_t)num_sms * 15u * kNarrowBelowTilesPerWarp;
+    const bool narrow = ntiles < (uint32_t)num_sms * (uint32_t)kWideWarps * kNarrowBelowTilesPerWarp;
     return narrow ? launch_shape<LAYOUT, Q8, RGBA, 4>(map2, d_frames, d_tiles, ntiles, d_counters, num_sms, stream)
-                  : launch_shape<LAYOUT, Q8, RGBA, 15>(map2, d_frames, d_tiles, ntiles, d_counters, num_sms, stream);
+                  : launch_shape<LAYOUT, Q8, RGBA, kWideWarps>(map2, d_frames, d_tiles, ntiles, d_counters, num_sms, stream);
   }
   recon_ldg_kernel<LAYOUT, Q8, RGBA><<<(ntiles + kLdgWarps - 1) / kLdgWarps, kLdgWarps * 32, 0, stream>>>(
       d_frames, d_tiles, ntiles);
@@ -475,8 +491,8 @@ cudaError_t launch_q(bool q8, bool rgba, bool use_tma, const CUtensorMap *map2,
 
 template <int LAYOUT, bool Q8, bool RGBA>
 cudaError_t set_attr() {
-  cudaError_t e = cudaFuncSetAttribute(recon_tma_kernel<LAYOUT, Q8, RGBA, 15>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<15>::kBytes);
+  cudaError_t e = cudaFuncSetAttribute(recon_tma_kernel<LAYOUT, Q8, RGBA, kWideWarps>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<kWideWarps>::kBytes);
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(recon_tma_kernel<LAYOUT, Q8, RGBA, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               SmemLayout<4>::kBytes);

@@ -6,5 +6,5 @@ name=$1; shift
 mkdir -p build/alt
 cd gid_b200/csrc
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared "$@" \
-  recon_kernels.cu gidcuda.cu -o ../../build/alt/libgidcuda_$name.so
+  *.cu -o ../../build/alt/libgidcuda_$name.so
 echo build/alt/libgidcuda_$name.so
