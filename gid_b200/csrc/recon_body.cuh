@@ -316,9 +316,10 @@ GID_HD int byte_of(uint32_t w) { return (int)prmt(w, 0u, 0x4440u + K); }
 // The destination pointer walks down the image one row per step (up for the
 // bottom-up format); rows below the image (:1023) are skipped by count.
 //   RGBA   4 bytes per pixel (a separate instance, so that the 3-byte loop stays lean)
-template <int H, int V, bool GREY, bool RGBA>
-GID_HD void emit_block_rows(const FrameDev &f, const Scratch &sc, int x0, int y0, int sx, int sy) {
-  if (x0 >= f.width) return;
+//   FAST   the whole block lies inside the image (8 pixels x 8 rows) and its rows are aligned:
+//          no per-row bounds checks, no call to the byte-wise store in the loop
+template <int H, int V, bool GREY, bool RGBA, bool FAST>
+GID_HD void emit_rows(const FrameDev &f, const Scratch &sc, int x0, int y0, int sx, int sy) {
   constexpr bool rgba = RGBA;
 #if defined(GIDK_EXTRACT_ADD_ALL)
   constexpr bool kExtractAdd = true;
@@ -330,18 +331,23 @@ GID_HD void emit_block_rows(const FrameDev &f, const Scratch &sc, int x0, int y0
   int npix = f.width - x0;
   if (npix > 8) npix = 8;
   const int nbytes = npix * 3;
-  const bool fast = (f.flags & (rgba ? FRAME_ALIGNED16 : FRAME_ALIGNED8)) != 0 && npix == 8;
+  // !FAST: rows that are whole and aligned still leave as 8-byte stores
+  const bool fast = FAST || ((f.flags & (rgba ? FRAME_ALIGNED16 : FRAME_ALIGNED8)) != 0 && npix == 8);
   const bool bottom_up = f.out_format == OUT_BGR8_BOTTOM_UP;
   const ColourOrder co = colour_order(bottom_up);
   uint8_t *dst = row_ptr(f, x0, y0);
   const long long step = bottom_up ? -(long long)f.stride : (long long)f.stride;
-  const int rows_left = f.height - y0;  // >= 1
-  const int crow0 = sy * (8 / V);       // first row inside the chroma block
+  const int rows_left = FAST ? 8 : f.height - y0;  // >= 1
+  const int crow0 = sy * (8 / V);                   // first row inside the chroma block
+  // (The byte selectors of the extract-add are literals: the compiler re-materialises them into
+  // uniform registers on every trip, 9 UMOV, but holding them in registers instead was measured
+  // slower on 4:2:0, -1.6 %.)
+  const uint32_t pick[4] = {0x1u, 0x100u, 0x10000u, 0x1000000u};
   // colour kernels: rolled (their hot loop is at the edge of the 32 KiB instruction cache; measured +3 %);
   // grey: two rows per trip
 #pragma unroll(GREY ? 2 : 1)
   for (int i = 0; i < 8 / V; i++) {
-    if (i * V >= rows_left) break;
+    if (!FAST && i * V >= rows_left) break;
     u32x2 cbc, crc;
     ChromaTerms t[8 / H];
     if (!GREY) {
@@ -361,7 +367,7 @@ GID_HD void emit_block_rows(const FrameDev &f, const Scratch &sc, int x0, int y0
     }
 #pragma unroll
     for (int ry = 0; ry < V; ry++) {
-      if (V > 1 && i * V + ry >= rows_left) break;
+      if (!FAST && V > 1 && i * V + ry >= rows_left) break;
       const u32x2 yv = sc.y[(i * V + ry) * sc.stride];
       if (GREY && rgba) {
         store_row8_rgba(dst, fast, npix, prmt(yv.x, 255u, 0x4000u), prmt(yv.x, 255u, 0x4111u), prmt(yv.x, 255u, 0x4222u),
@@ -380,10 +386,10 @@ GID_HD void emit_block_rows(const FrameDev &f, const Scratch &sc, int x0, int y0
 #pragma unroll
           for (int c = 0; c < 8; c++) {
             const ChromaTerms &tt = t[c / H];
-            const uint32_t yw = c < 4 ? yv.x : yv.y, pick = 1u << (8 * (c & 3));
-            c0[c] = dp4a_uu(yw, pick, tt.r);
-            c1[c] = dp4a_uu(yw, pick, tt.g);
-            c2[c] = dp4a_uu(yw, pick, tt.b);
+            const uint32_t yw = c < 4 ? yv.x : yv.y;
+            c0[c] = dp4a_uu(yw, pick[c & 3], tt.r);
+            c1[c] = dp4a_uu(yw, pick[c & 3], tt.g);
+            c2[c] = dp4a_uu(yw, pick[c & 3], tt.b);
           }
         } else {
           const int ys[8] = {byte_of<0>(yv.x), byte_of<1>(yv.x), byte_of<2>(yv.x), byte_of<3>(yv.x),
@@ -408,6 +414,40 @@ GID_HD void emit_block_rows(const FrameDev &f, const Scratch &sc, int x0, int y0
       }
       dst += step;
     }
+  }
+}
+
+// Blocks cut by the right or bottom edge of the image (:1023, :1026) and frames whose rows are
+// not aligned: the same loop with its bounds checks and byte-wise stores, kept out of line so
+// that the hot loop above carries none of it.
+template <int H, int V, bool GREY, bool RGBA>
+#if defined(__CUDACC__)
+static __host__ __device__ __noinline__
+#else
+inline
+#endif
+void emit_rows_edge(const FrameDev *f, u32x2 *cb, u32x2 *cr, u32x2 *y, int stride, int x0, int y0, int sx, int sy) {
+  // (scalars by value: a reference to the caller's Scratch would force it into local memory
+  // on the hot path too)
+  Scratch sc;
+  sc.cb = cb; sc.cr = cr; sc.y = y; sc.stride = stride;
+  emit_rows<H, V, GREY, RGBA, false>(*f, sc, x0, y0, sx, sy);
+}
+
+template <int H, int V, bool GREY, bool RGBA>
+GID_HD void emit_block_rows(const FrameDev &f, const Scratch &sc, int x0, int y0, int sx, int sy) {
+  if (x0 >= f.width) return;
+  // The split pays where registers are plentiful (grey: +1.7 %).  The colour kernels sit at the
+  // 128-register limit: there the call made two values of the tile loop spill and the second
+  // copy of the loop cost instruction-cache misses (-5 % on 4:2:0, profiles/r01s), so they keep
+  // the one loop with its checks.
+  if (GREY) {
+    const bool whole = f.width - x0 >= 8 && f.height - y0 >= 8 &&
+                       (f.flags & (RGBA ? FRAME_ALIGNED16 : FRAME_ALIGNED8)) != 0;
+    if (whole) emit_rows<H, V, GREY, RGBA, true>(f, sc, x0, y0, sx, sy);
+    else emit_rows_edge<H, V, GREY, RGBA>(&f, sc.cb, sc.cr, sc.y, sc.stride, x0, y0, sx, sy);
+  } else {
+    emit_rows<H, V, GREY, RGBA, false>(f, sc, x0, y0, sx, sy);
   }
 }
 
