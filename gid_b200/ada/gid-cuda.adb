@@ -108,6 +108,18 @@ package body GID.CUDA is
     Check (gidcuda_job_records_commit (j, C.int (comp), C.size_t (count)), Null_Context);
   end Records_Commit;
 
+  procedure Records_Commit_Runs (j : Job; comp : Natural; runs : Run_Array) is
+    b, n : Size_Array (0 .. runs'Length - 1);
+  begin
+    for i in runs'Range loop
+      b (i - runs'First) := C.size_t (runs (i).first_record);
+      n (i - runs'First) := C.size_t (runs (i).count);
+    end loop;
+    Check (gidcuda_job_records_commit_runs
+             (j, C.int (comp), Interfaces.Integer_32 (runs'Length), b (0)'Access, n (0)'Access),
+           Null_Context);
+  end Records_Commit_Runs;
+
   procedure Submit (j : Job) is
   begin
     Check (gidcuda_job_submit (j), Null_Context);

@@ -85,6 +85,12 @@ private package GID.CUDA is
     (j : Job; comp : Natural;
      first, records : out System.Address; capacity, nblocks : out Natural);
   procedure Records_Commit (j : Job; comp : Natural; count : Natural);
+  --  The same for records produced by several tasks (one run per task; runs ascending, disjoint)
+  type Run is record
+    first_record, count : Natural;
+  end record;
+  type Run_Array is array (Positive range <>) of Run;
+  procedure Records_Commit_Runs (j : Job; comp : Natural; runs : Run_Array);
 
   procedure Submit (j : Job);   --  asynchronous: H2D, kernel(s), D2H
   procedure Wait   (j : Job; pixels : out System.Address; stride : out Natural);
@@ -130,6 +136,15 @@ private
 
   function gidcuda_job_records_commit (j : Job; comp : C.int; count : C.size_t) return C.int;
   pragma Import (C, gidcuda_job_records_commit, "gidcuda_job_records_commit");
+
+  --  Records produced by several tasks, each decoding its own group of restart
+  --  intervals into its own slice of the lent array (include/gidcuda.h)
+  type Size_Array is array (Natural range <>) of aliased C.size_t;
+  pragma Convention (C, Size_Array);
+  function gidcuda_job_records_commit_runs
+    (j : Job; comp : C.int; nruns : Interfaces.Integer_32;
+     run_begin, run_count : access constant C.size_t) return C.int;
+  pragma Import (C, gidcuda_job_records_commit_runs, "gidcuda_job_records_commit_runs");
 
   function gidcuda_job_submit (j : Job) return C.int;
   pragma Import (C, gidcuda_job_submit, "gidcuda_job_submit");

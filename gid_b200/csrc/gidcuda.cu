@@ -163,6 +163,9 @@ struct gidcuda_job {
   uint8_t *h_sparse = nullptr, *d_sparse = nullptr;
   size_t sparse_off[3] = {0, 0, 0}, sparse_cap[3] = {0, 0, 0}, sparse_count[3] = {0, 0, 0};
   bool sparse[3] = {false, false, false};  // component committed as records
+  // gidcuda_job_records_commit_runs: (begin, count) of each run inside the lent record array;
+  // empty = one run starting at 0 (gidcuda_job_records_commit)
+  std::vector<std::pair<size_t, size_t>> sparse_runs[3];
   uint8_t *h_pixels = nullptr;  // pinned
   uint8_t *d_coef = nullptr, *d_pixels = nullptr, *d_samples = nullptr;
   gidk::LaunchSet set;
@@ -314,6 +317,7 @@ extern "C" int gidcuda_job_begin(gidcuda_ctx *ctx, const gidcuda_frame_desc *des
     j->rows_hint[c] = 8;
     j->sparse[c] = false;
     j->sparse_count[c] = 0;
+    j->sparse_runs[c].clear();
   }
   j->state = gidcuda_job::BEGUN;
   ctx->live_jobs++;
@@ -370,6 +374,39 @@ extern "C" int gidcuda_job_records_commit(gidcuda_job *job, int comp, size_t cou
                 count);
   job->sparse[comp] = true;
   job->sparse_count[comp] = count;
+  job->sparse_runs[comp].clear();
+  return GIDCUDA_OK;
+}
+
+extern "C" int gidcuda_job_records_commit_runs(gidcuda_job *job, int comp, int32_t nruns, const size_t *run_begin,
+                                               const size_t *run_count) {
+  if (!job) return fail(nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "null job");
+  if (job->state == gidcuda_job::IDLE)
+    return fail(job->ctx, GIDCUDA_ERR_STATE, "gidcuda_job_records_commit_runs: job was released");
+  if (comp < 0 || comp >= job->geo.ncomp || !job->h_sparse || nruns < 1 || !run_begin || !run_count)
+    return fail(job->ctx, GIDCUDA_ERR_BAD_ARGUMENT,
+                "gidcuda_job_records_commit_runs: bad component or runs, or gidcuda_job_records was not called");
+  const size_t cap = job->sparse_cap[comp];
+  size_t total = 0, floor_ = 0;
+  for (int32_t r = 0; r < nruns; r++) {
+    // runs are ascending and disjoint, so that the compacted copy never outgrows the device twin
+    if (run_begin[r] < floor_ || run_count[r] > cap || run_begin[r] > cap - run_count[r])
+      return fail(job->ctx, GIDCUDA_ERR_BAD_ARGUMENT,
+                  "gidcuda_job_records_commit_runs: run %d (begin %zu, count %zu) overlaps its predecessor or exceeds the capacity %zu",
+                  (int)r, run_begin[r], run_count[r], cap);
+    floor_ = run_begin[r] + run_count[r];
+    total += run_count[r];
+  }
+  const size_t nb = (size_t)job->geo.bx[comp] * job->geo.by[comp];
+  const uint32_t *first = reinterpret_cast<const uint32_t *>(job->h_sparse + job->sparse_off[comp]);
+  if (first[0] != 0 || first[nb] != total)
+    return fail(job->ctx, GIDCUDA_ERR_BAD_ARGUMENT,
+                "gidcuda_job_records_commit_runs: first[0] = %u, first[nblocks] = %u do not frame %zu records", first[0],
+                first[nb], total);
+  job->sparse[comp] = true;
+  job->sparse_count[comp] = total;
+  job->sparse_runs[comp].clear();
+  for (int32_t r = 0; r < nruns; r++) job->sparse_runs[comp].emplace_back(run_begin[r], run_count[r]);
   return GIDCUDA_OK;
 }
 
@@ -410,8 +447,22 @@ extern "C" int gidcuda_job_submit(gidcuda_job *job) {
       uint8_t *dp = job->d_coef + g.plane_off[c];
       if (job->sparse[c]) {
         const size_t nb = (size_t)g.bx[c] * g.by[c];
-        CU_TRY(ctx, cudaMemcpyAsync(job->d_sparse + job->sparse_off[c], job->h_sparse + job->sparse_off[c],
-                                    (nb + 1 + job->sparse_count[c]) * 4, cudaMemcpyHostToDevice, s));
+        uint8_t *dsp = job->d_sparse + job->sparse_off[c];
+        const uint8_t *hsp = job->h_sparse + job->sparse_off[c];
+        if (job->sparse_runs[c].empty()) {
+          CU_TRY(ctx, cudaMemcpyAsync(dsp, hsp, (nb + 1 + job->sparse_count[c]) * 4, cudaMemcpyHostToDevice, s));
+        } else {
+          // first[] as it is, then every run to its place in the concatenation: the copy engine
+          // does the compaction that several producer threads could not do in place
+          CU_TRY(ctx, cudaMemcpyAsync(dsp, hsp, (nb + 1) * 4, cudaMemcpyHostToDevice, s));
+          size_t at = nb + 1;
+          for (const auto &run : job->sparse_runs[c]) {
+            if (run.second)
+              CU_TRY(ctx, cudaMemcpyAsync(dsp + at * 4, hsp + (nb + 1 + run.first) * 4, run.second * 4,
+                                          cudaMemcpyHostToDevice, s));
+            at += run.second;
+          }
+        }
         job->d_tail_zero[c] = false;
         continue;
       }

@@ -26,6 +26,7 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <atomic>
 #include <functional>
 #include <stdexcept>
 #include <string>
@@ -92,6 +93,11 @@ struct Image_Descriptor {
   // non-zero coefficient, the entropy decoder's natural output) unless this is false: then, or
   // for a component too dense for the record buffer, as dense int16 planes.
   bool sparse_input = true;
+  // Host threads for the entropy decode of ONE image (not in the reference, which is serial): a
+  // baseline scan with restart intervals (DRI) is decoded interval-parallel when > 1
+  // (0 = one per hardware thread).  Scans without restart markers, and progressive scans,
+  // stay serial.  The decoded coefficients are the same either way.
+  int entropy_threads = 1;
 };
 
 // gid.ads:64-67.  try_tga is accepted for signature compatibility and ignored.
@@ -113,6 +119,10 @@ inline bool Expect_Transparency(const Image_Descriptor &) { return false; }
 
 namespace detail {
 
+// How many baseline scans were decoded restart-interval-parallel / fell back to the serial loop
+// after the parallel attempt met something unusual (process-wide; tests and statistics).
+extern std::atomic<long> parallel_scans, parallel_fallbacks;
+
 // Result of the device reconstruction: top-down RGB8 rows in pinned host memory
 // owned by the library until release().
 struct Reconstruction {
@@ -125,6 +135,11 @@ struct Reconstruction {
 // submits the job and waits.  feedback receives 0 .. 50 during the entropy pass.
 Reconstruction decode_and_reconstruct(Image_Descriptor &image, const std::function<void(int)> &feedback);
 void release(Reconstruction &r);
+
+// The two halves of the above for callers that keep several frames in flight on one context
+// (gid_batch.cpp): entropy-decode into a job of `ctx` and submit it (asynchronous; returns the
+// gidcuda_job), later gidcuda_job_wait / gidcuda_job_release.
+void *decode_and_submit(Image_Descriptor &image, void *ctx, const std::function<void(int)> &feedback);
 
 // Entropy decode only, into calloc'd planes (see gidhost_decode_planes).
 void decode_planes(Image_Descriptor &image, struct ::gidcuda_frame_desc *desc, int16_t *planes[3], int32_t blocks_x[3],

@@ -1,0 +1,954 @@
+// jpeg_entropy.hpp -- internal header of the C++ host mirror: segment readers and the
+// entropy decoder (baseline and progressive) that emits frame-wide int16 coefficient
+// planes / coefficient records.  Included by gid_jpeg_host.cpp (GID's API above the C
+// ABI) and gid_batch.cpp (many files on many host threads); everything lives in an
+// anonymous namespace, so each translation unit gets its own copy.
+//
+// References are to the GID 013 tree:
+//   segment reader            gid-decoding_jpg.adb:122-181
+//   Read_SOF                  :184-318      Read_DHT :320-391     Read_DQT :393-422
+//   Read_DRI                  :424-434      Read_EXIF :436-543
+//   bit buffer / Get_VLC      :594-753
+//   Check_Restart             :1133-1177
+//   baseline scan             :1179-1220    progressive scans :1243-1747
+//   Read_SOS + geometry       :1855-2034    segment loop :2043-2118
+//
+// Product code: independent of the test-only CPU restatement.
+#pragma once
+
+#include "gid.hpp"
+
+#include <algorithm>
+#include <array>
+#include <atomic>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+
+#include "../../include/gidcuda.h"
+
+namespace gid {
+
+namespace {
+
+std::string fmt(const char *f, ...) {
+  char buf[256];
+  va_list ap;
+  va_start(ap, f);
+  vsnprintf(buf, sizeof buf, f, ap);
+  va_end(ap);
+  return buf;
+}
+
+// zig-zag index -> natural index (gid-decoding_jpg.adb:570-578)
+const uint8_t kZigZag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                             41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                             30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+enum Marker : uint8_t {
+  M_SOF0 = 0xC0, M_SOF2 = 0xC2, M_DHT = 0xC4, M_RST0 = 0xD0, M_RST7 = 0xD7, M_SOI = 0xD8, M_EOI = 0xD9,
+  M_SOS = 0xDA, M_DQT = 0xDB, M_DRI = 0xDD, M_APP1 = 0xE1, M_COM = 0xFE
+};
+
+// Markers GID knows (marker_id table, gid-decoding_jpg.ads:41-87): SOF0-15
+// (C0..CF incl. DHT C4, JPG C8, DAC CC), RST0-7, SOI, EOI, SOS, DQT, DNL, DRI,
+// DHP, EXP, APP0-15, JPG0-13, COM.  Anything else raises "unknown marker".
+bool known_marker(uint8_t b) { return b >= 0xC0 && b <= 0xFE; }
+
+struct Reader {
+  Stream &s;
+  explicit Reader(Stream &st) : s(st) {}
+  uint8_t byte() {  // GID.Buffering.Get_Byte: End_Error at EOF (gid-buffering.adb:95-105)
+    if (s.pos >= s.size) throw error_in_image_data("JPEG: unexpected end of data (End_Error)");
+    return s.data[s.pos++];
+  }
+  unsigned be16() {
+    const unsigned h = byte();
+    return (h << 8) | byte();
+  }
+  void skip(int n) {
+    for (int i = 0; i < n; i++) (void)byte();
+  }
+};
+
+struct Segment {
+  uint8_t marker;
+  int length;  // of the contents, without the marker and the length field
+};
+
+Segment read_segment(Reader &r, bool have_marker, uint8_t buffered) {  // :122-167
+  uint8_t b = buffered;
+  if (!have_marker) {
+    if (r.byte() != 0xFF) throw error_in_image_data("JPEG: expected marker prefix (16#FF#) here");
+    b = r.byte();
+  }
+  if (!known_marker(b)) throw error_in_image_data(fmt("JPEG: unknown marker here: 16#FF#, then 16#%02X#", b));
+  Segment sg{b, 0};
+  if (b != M_EOI) sg.length = (int)r.be16() - 2;
+  return sg;
+}
+
+void read_dht(Image_Descriptor &im, Reader &r, int length) {  // :320-391
+  int remaining = length;
+  while (remaining > 0) {
+    const uint8_t b = r.byte();
+    remaining--;
+    const int kind = b >= 8 ? 1 : 0;  // GID: ">= 8" means AC
+    const int idx = b & 7;
+    std::vector<uint8_t> counts(16);
+    int total = 0;
+    for (int i = 0; i < 16; i++) {
+      counts[i] = r.byte();
+      remaining--;
+      total += counts[i];
+    }
+    // the code space must not be over-subscribed ("DHT data too short [2]")
+    long space = 65536, spread = 65536;
+    for (int len = 0; len < 16; len++) {
+      spread /= 2;
+      if (counts[len] > 0) {
+        if (remaining < counts[len]) throw error_in_image_data("JPEG: DHT data too short [1]");
+        space -= (long)counts[len] * spread;
+        if (space < 0) throw error_in_image_data("JPEG: DHT data too short [2]");
+      }
+    }
+    std::vector<uint8_t> vals((size_t)total);
+    for (int i = 0; i < total; i++) vals[(size_t)i] = r.byte();
+    remaining -= total;
+    im.huff_bits[kind][idx] = counts;
+    im.huff_vals[kind][idx] = vals;
+  }
+}
+
+void read_dqt(Image_Descriptor &im, Reader &r, int length) {  // :393-422
+  int remaining = length;
+  while (remaining > 0) {
+    const uint8_t b = r.byte();
+    remaining--;
+    const bool high = b >= 8;
+    Quantization_Table &t = im.qt_list[b & 7];
+    for (int i = 0; i < 64; i++) {
+      if (high) { t.q[i] = (uint16_t)r.be16(); remaining -= 2; }
+      else { t.q[i] = r.byte(); remaining -= 1; }
+    }
+    t.defined = true;
+  }
+}
+
+void read_exif(Image_Descriptor &im, Reader &r, int length) {  // :436-543
+  if (length < 6) { r.skip(length); return; }
+  char sig[6];
+  for (char &c : sig) c = (char)r.byte();
+  if (memcmp(sig, "Exif\0\0", 6) != 0) { r.skip(length - 6); return; }
+  const char endian = (char)r.byte();
+  r.skip(7);
+  (void)r.byte();  // IFD0 entry count (unused by the scan below, as in the reference)
+  (void)r.byte();
+  int x = 17;
+  while (x <= length - 12) {
+    const unsigned b0 = r.byte(), b1 = r.byte();
+    const unsigned tag = endian == 'I' ? (b0 | (b1 << 8)) : (b1 | (b0 << 8));
+    r.skip(6);
+    uint8_t value;
+    if (endian == 'I') { value = r.byte(); r.skip(3); }
+    else { (void)r.byte(); value = r.byte(); r.skip(2); }
+    x += 12;
+    if (tag == 0x112) {
+      switch (value) {
+        case 8: im.display_orientation = Orientation::Rotation_90; break;
+        case 3: im.display_orientation = Orientation::Rotation_180; break;
+        case 6: im.display_orientation = Orientation::Rotation_270; break;
+        default: im.display_orientation = Orientation::Unchanged; break;
+      }
+      break;
+    }
+  }
+  for (int i = x; i <= length; i++) (void)r.byte();
+}
+
+void read_sof(Image_Descriptor &im, Reader &r, const Segment &sg) {  // :184-318
+  if (sg.marker == M_SOF0) im.detailed_format = "JPEG, Baseline DCT (SOF_0)";
+  else if (sg.marker == M_SOF2) { im.detailed_format = "JPEG, Progressive DCT (SOF_2)"; im.progressive = true; }
+  else throw unsupported_image_subformat(fmt("JPEG: image type not yet supported: SOF_%d", sg.marker - 0xC0));
+  const int bits = r.byte();
+  if (bits != 8) throw unsupported_image_subformat(fmt("JPEG: bits per primary color= %d (not supported)", bits));
+  im.bits_per_pixel = 3 * bits;
+  const int h = (int)r.be16(), w = (int)r.be16();
+  if (w == 0) throw error_in_image_data("JPEG: zero image width");
+  if (h == 0) throw error_in_image_data("JPEG: zero image height");
+  im.width = w;
+  im.height = h;
+  im.subformat_id = r.byte();
+  im.max_samples_hor = im.max_samples_ver = 0;
+  int id_base = 1;
+  bool seen[5] = {false, false, false, false, false};  // Y, Cb, Cr, I, Q
+  for (int i = 0; i < im.subformat_id; i++) {
+    int b = r.byte();
+    if (b == 0) id_base = 0;  // encoders that number the components 0, 1, 2 (:226-233)
+    if (b - id_base > 4 || b - id_base < 0) throw error_in_image_data(fmt("JPEG: SOF: invalid component ID: %d", b));
+    const int c = b - id_base;
+    seen[c] = true;
+    const int sampling = r.byte(), tq = r.byte();
+    if (c < 3) {
+      Component_Info &ci = im.info[c];
+      ci.present = true;
+      ci.samples_hor = sampling / 16;
+      ci.samples_ver = sampling % 16;
+      ci.qt_assoc = tq;
+      if (ci.samples_hor > im.max_samples_hor) im.max_samples_hor = ci.samples_hor;
+      if (ci.samples_ver > im.max_samples_ver) im.max_samples_ver = ci.samples_ver;
+    }
+  }
+  if (sg.length < 6 + 3 * im.subformat_id) throw error_in_image_data("JPEG: SOF segment too short");
+  const bool ycbcr = seen[0] && seen[1] && seen[2] && !seen[3] && !seen[4];
+  const bool grey = seen[0] && !seen[1] && !seen[2] && !seen[3] && !seen[4];
+  if (!ycbcr && !grey) {
+    if (seen[0] && seen[1] && seen[2] && seen[3] && !seen[4])
+      throw unsupported_image_subformat("JPEG: CMYK color space is currently not properly decoded");
+    throw unsupported_image_subformat("JPEG: only YCbCr, Y_Grey and CMYK color spaces are currently defined");
+  }
+  im.greyscale = grey;
+  im.detailed_format += grey ? ", Y_GREY" : ", YCBCR";
+  for (Component_Info &ci : im.info)
+    if (ci.present) {
+      if (ci.samples_hor == 0 || ci.samples_ver == 0)
+        throw constraint_error("JPEG: zero sampling factor (division by zero in Read_SOF)");
+      ci.up_factor_x = im.max_samples_hor / ci.samples_hor;
+      ci.up_factor_y = im.max_samples_ver / ci.samples_ver;
+    }
+}
+
+// ---- entropy decoding --------------------------------------------------------------
+
+// Canonical Huffman table with an 8-bit fast path (the reference uses one 65 536
+// entry direct table per Huffman table, gid.ads:316; the decoded symbols are the same).
+struct HuffTable {
+  bool defined = false;
+  uint8_t fast_len[256], fast_sym[256];
+  // 10-bit direct table of the wide reader: len << 8 | symbol, 0 = code longer than 10 bits
+  static constexpr int kLutBits = 10;
+  uint16_t lut[1 << kLutBits];
+  int maxcode[18], valptr[17], mincode[17];
+  std::vector<uint8_t> vals;
+  void build(const std::vector<uint8_t> &counts, const std::vector<uint8_t> &v) {
+    defined = !counts.empty();
+    if (!defined) return;
+    vals = v;
+    memset(fast_len, 0, sizeof fast_len);
+    memset(lut, 0, sizeof lut);
+    int code = 0, k = 0;
+    for (int len = 1; len <= 16; len++) {
+      valptr[len] = k;
+      mincode[len] = code;
+      for (int i = 0; i < counts[(size_t)len - 1]; i++, k++, code++) {
+        if (len <= 8) {
+          const int first = code << (8 - len), n = 1 << (8 - len);
+          for (int j = 0; j < n; j++) { fast_len[first + j] = (uint8_t)len; fast_sym[first + j] = vals[(size_t)k]; }
+        }
+        if (len <= kLutBits && code < (1 << len)) {
+          const int first = code << (kLutBits - len), n = 1 << (kLutBits - len);
+          for (int j = 0; j < n; j++) lut[first + j] = (uint16_t)((len << 8) | vals[(size_t)k]);
+        }
+      }
+      maxcode[len] = counts[(size_t)len - 1] ? code - 1 : -1;
+      code <<= 1;
+    }
+    maxcode[17] = 0x7FFFFFFF;
+  }
+};
+
+struct BitReader {  // :594-690
+  Reader &r;
+  uint32_t buf = 0;
+  int len = 0;
+  uint8_t memo_marker = 0;  // a marker met while filling (it WILL appear at the end of the scan)
+  explicit BitReader(Reader &rd) : r(rd) {}
+  void reset() { buf = 0; len = 0; memo_marker = 0; }
+  void fill(int bits) {
+    while (len < bits) {
+      uint8_t b;
+      if (memo_marker != 0 || r.s.pos >= r.s.size) {
+        b = 0xFF;  // past a marker / end of data: pad (the reference pads with FF at End_Error, :665-670)
+      } else {
+        b = r.s.data[r.s.pos++];
+        if (b == 0xFF) {
+          const uint8_t m = r.s.pos < r.s.size ? r.s.data[r.s.pos++] : 0xD9;
+          if (m != 0) {  // byte stuffing FF 00 -> FF; anything else is a marker
+            const bool ok = m == M_EOI || m == M_COM || m == M_DHT || m == M_DRI || m == M_SOS ||
+                            (m >= M_RST0 && m <= M_RST7);
+            if (!ok) throw error_in_image_data(fmt("JPEG: Invalid marker within filling of bit buffer: 16#%02X#", m));
+            memo_marker = m;
+          }
+        }
+      }
+      buf = (buf << 8) | b;
+      len += 8;
+    }
+  }
+  int show(int bits) {
+    if (bits == 0) return 0;
+    fill(bits);
+    return (int)((buf >> (len - bits)) & ((1u << bits) - 1u));
+  }
+  void skip(int bits) {
+    if (len < bits) fill(bits);
+    len -= bits;
+  }
+  int get(int bits) {
+    const int v = show(bits);
+    skip(bits);
+    return v;
+  }
+  int symbol(const HuffTable &t) {  // Next_Huffval, :738-746
+    const int look = show(16);
+    int l = t.fast_len[look >> 8];
+    if (l != 0) {
+      skip(l);
+      return t.fast_sym[look >> 8];
+    }
+    for (l = 9; l <= 16; l++) {
+      const int code = look >> (16 - l);
+      if (code <= t.maxcode[l]) {
+        skip(l);
+        return t.vals[(size_t)(t.valptr[l] + code - t.mincode[l])];
+      }
+    }
+    throw error_in_image_data("JPEG: VLC table: bits = 0");
+  }
+  static int extend(int v, int bits) {  // Bin_Twos_Complement, :748-753
+    return v < (1 << (bits - 1)) ? v + 1 - (1 << bits) : v;
+  }
+  int receive_extend(int bits) { return bits ? extend(get(bits), bits) : 0; }
+};
+
+// The bit buffer again, 64 bits wide, for the baseline scan loop (the progressive scans keep
+// BitReader).  Same observable behaviour as BitReader / the reference's byte-wise buffer:
+//   * FF 00 is a stuffed FF; the first marker met stops the loading for good (memo_marker), the
+//     buffer is then padded with FF bytes; so is the end of the data;
+//   * a marker that may not appear inside entropy-coded data raises -- but only when the decoder
+//     asks for bits beyond the last real one, which is when the byte-wise buffer would have
+//     loaded it (it loads a byte only while it holds fewer bits than requested).  The wide buffer
+//     meets the marker earlier, remembers it (`bad`) and raises at that same request: need().
+// The buffer is left-aligned: the next bit is bit 63; `len` bits are valid, the last `pad` of
+// them padding.
+struct WideBits {
+  const uint8_t *data;
+  size_t pos, size;
+  uint64_t buf = 0;
+  int len = 0, pad = 0;
+  uint8_t memo_marker = 0, bad = 0;
+  bool stopped = false;
+  WideBits(const uint8_t *d, size_t p, size_t n) : data(d), pos(p), size(n) {}
+  void reset() { buf = 0; len = 0; pad = 0; memo_marker = 0; bad = 0; stopped = false; }
+  int real() const { return len - pad; }
+  void refill() {
+    if (!stopped && len <= 32 && pos + 8 <= size) {  // eight bytes at once when none of them is FF
+      uint64_t v;
+      memcpy(&v, data + pos, 8);
+      v = __builtin_bswap64(v);
+      const uint64_t inv = ~v;  // a byte of v is FF <=> the same byte of inv is zero
+      if (((inv - 0x0101010101010101ull) & ~inv & 0x8080808080808080ull) == 0) {
+        const int nb = (64 - len) >> 3, spare = 64 - len - 8 * nb;
+        buf |= (v >> len) & ~((1ull << spare) - 1ull);
+        len += 8 * nb;
+        pos += (size_t)nb;
+        return;
+      }
+    }
+    while (len <= 56) {
+      uint64_t b = 0xFF;
+      if (stopped || pos >= size) {
+        stopped = true;  // past a marker / the end of the data: FF padding (:665-670)
+        pad += 8;
+      } else {
+        b = data[pos++];
+        if (b == 0xFF) {
+          const uint8_t m = pos < size ? data[pos++] : (uint8_t)M_EOI;
+          if (m != 0) {
+            const bool ok = m == M_EOI || m == M_COM || m == M_DHT || m == M_DRI || m == M_SOS ||
+                            (m >= M_RST0 && m <= M_RST7);
+            if (ok) memo_marker = m; else bad = m;
+            stopped = true;
+            pad += 8;
+          }
+        }
+      }
+      buf |= b << (56 - len);
+      len += 8;
+    }
+  }
+  // the decoder is about to look at n bits: raise what the byte-wise buffer would raise there
+  void need(int n) {
+    if (len < n) refill();
+    if (bad && n > real())
+      throw error_in_image_data(fmt("JPEG: Invalid marker within filling of bit buffer: 16#%02X#", bad));
+  }
+  int peek(int n) const { return (int)(buf >> (64 - n)); }  // 1 <= n <= 32
+  void drop(int n) {
+    buf <<= n;
+    len -= n;
+    if (pad > len) pad = len;
+  }
+  int get(int n) {  // n = 0 .. 16
+    if (n == 0) return 0;
+    need(n);
+    const int v = peek(n);
+    drop(n);
+    return v;
+  }
+  int symbol(const HuffTable &t) {  // Next_Huffval, :738-746: always looks at 16 bits
+    need(16);
+    const int look = peek(16);
+    const uint16_t e = t.lut[look >> (16 - HuffTable::kLutBits)];
+    if (e != 0) {
+      drop(e >> 8);
+      return e & 0xFF;
+    }
+    for (int l = HuffTable::kLutBits + 1; l <= 16; l++) {
+      const int code = look >> (16 - l);
+      if (code <= t.maxcode[l]) {
+        drop(l);
+        return t.vals[(size_t)(t.valptr[l] + code - t.mincode[l])];
+      }
+    }
+    throw error_in_image_data("JPEG: VLC table: bits = 0");
+  }
+  int receive_extend(int bits) { return bits ? BitReader::extend(get(bits), bits) : 0; }
+};
+
+struct PlaneRef {
+  int16_t *base = nullptr;
+  int blocks_x = 0, blocks_y = 0;
+  int16_t *block(int bx, int by) const { return base + ((size_t)by * (size_t)blocks_x + (size_t)bx) * 64; }
+};
+
+// Sparse output of the entropy decoder for one component (include/gidcuda.h, "sparse
+// coefficient input"): first[seq] = index of the first record of block seq (blocks in the
+// order the interleaved scan visits them), record = (uint16)value << 16 | natural index.
+struct RecordSink {
+  uint32_t *first = nullptr, *rec = nullptr;
+  size_t cap = 0, n = 0;
+  uint32_t seq = 0, nblocks = 0;
+  bool on = false;
+  void put(int nat, int value) { rec[n++] = ((uint32_t)(uint16_t)(int16_t)value << 16) | (uint32_t)nat; }
+};
+
+struct Decoder {
+  Image_Descriptor &im;
+  Reader r;
+  BitReader bits;
+  const std::function<void(int)> &feedback;
+  std::function<void()> begin_frame;  // called at the first SOS: tables and geometry are final (:1857)
+  HuffTable huff[2][8];
+  PlaneRef plane[3];
+  RecordSink sink[3];                 // baseline: components emitted as records while sink[c].on
+  std::function<void(int)> spill;     // sink[c] is nearly full: switch component c to its dense plane
+  int dc_pred[3] = {0, 0, 0};
+  int last_row[3] = {0, 0, 0};  // last block row (natural order) a coefficient was stored in, per component
+  int ht_dc[3] = {0, 0, 0}, ht_ac[3] = {0, 0, 0};
+  int mcu_count_image_v = 0, mcu_count_image_h = 0;
+  int rst_count = 0, next_rst = 0;
+  int eobrun = 0;
+  int scans = 0;
+  int last_feedback = 0;
+
+  Decoder(Image_Descriptor &image, const std::function<void(int)> &fb) : im(image), r(*image.stream), bits(r), feedback(fb) {}
+
+  void emit_feedback(int p) {
+    if (p < last_feedback) p = last_feedback;  // clients draw progress bars: never go back
+    last_feedback = p;
+    feedback(p);
+  }
+
+  void rebuild_tables() {
+    for (int k = 0; k < 2; k++)
+      for (int i = 0; i < 8; i++) huff[k][i].build(im.huff_bits[k][i], im.huff_vals[k][i]);
+  }
+
+  void check_restart(bool reset_predictors) {  // :1133-1177
+    if (im.restart_interval <= 0) return;
+    if (--rst_count != 0) return;
+    bits.len &= 0xF8;  // byte alignment
+    const int w = bits.get(16);
+    // the marker bytes themselves were not pushed into the buffer by this reader:
+    // it remembers the marker and pads; accept either view of the 16 bits
+    const int expected = 0xFFD0 + next_rst;
+    const bool seen = bits.memo_marker == (uint8_t)(0xD0 + next_rst);
+    if (!seen && w != expected)
+      throw error_in_image_data(fmt("JPEG: expected RST (restart) marker Nb %d; code found %04X; expected %04X",
+                                    next_rst, w, expected));
+    bits.reset();
+    next_rst = (next_rst + 1) & 7;
+    rst_count = im.restart_interval;
+    eobrun = 0;
+    if (reset_predictors) dc_pred[0] = dc_pred[1] = dc_pred[2] = 0;
+  }
+
+  const HuffTable &table(int kind, int idx) {
+    if (idx < 0 || idx > 7 || !huff[kind][idx].defined) throw constraint_error("JPEG: Huffman table not defined");
+    return huff[kind][idx];
+  }
+
+  // Decode_8x8_Block (:758-788) without the de-quantisation: values are stored as
+  // read, at their natural position -- as records (one per non-zero value) or into the
+  // dense plane; the multiplication by qt_local moves to the GPU.
+  // k = record sink (blk == nullptr) or nullptr (dense block blk).  Static: the restart-parallel
+  // scan runs it on several threads, each with its own bit buffer, predictor and sink.
+  static void baseline_block(WideBits &bits, const HuffTable &dc, const HuffTable &ac, int &dc_pred, RecordSink *k,
+                             int16_t *blk, int &last_row) {
+    if (k) k->first[k->seq++] = (uint32_t)k->n;
+    const int s = bits.symbol(dc);
+    dc_pred += bits.receive_extend(s & 15);
+    if (blk) blk[0] = (int16_t)dc_pred;
+    else if ((int16_t)dc_pred != 0) k->put(0, dc_pred);
+    int coef = 0;
+    for (;;) {
+      int code, value;
+      if (bits.len <= 32) bits.refill();
+      if (bits.real() >= 32) {
+        // symbol (<= 16 bits) and its value bits (<= 15) are all real bits: no checks needed
+        const int look = bits.peek(16);
+        const uint16_t e = ac.lut[look >> (16 - HuffTable::kLutBits)];
+        if (e != 0) {
+          bits.drop(e >> 8);
+          code = e & 0xFF;
+        } else {
+          code = bits.symbol(ac);
+        }
+        if (code == 0) break;  // EOB
+        const int n = code & 15;
+        if (n == 0 && code != 0xF0) throw error_in_image_data("JPEG: error in VLC AC code for de-quantization");
+        coef += (code >> 4) + 1;
+        if (coef > 63) throw error_in_image_data("JPEG: coefficient for de-quantization is > 63");
+        value = 0;
+        if (n) {
+          value = BitReader::extend(bits.peek(n), n);
+          bits.drop(n);
+        }
+      } else {
+        code = bits.symbol(ac);
+        if (code == 0) break;  // EOB
+        if ((code & 0x0F) == 0 && code != 0xF0)
+          throw error_in_image_data("JPEG: error in VLC AC code for de-quantization");
+        coef += (code >> 4) + 1;
+        if (coef > 63) throw error_in_image_data("JPEG: coefficient for de-quantization is > 63");
+        value = bits.receive_extend(code & 15);
+      }
+      const int nat = kZigZag[coef];
+      if (blk) {
+        blk[nat] = (int16_t)value;
+        if ((nat >> 3) > last_row) last_row = nat >> 3;
+      } else if ((int16_t)value != 0) {
+        k->put(nat, value);
+      }
+      if (coef == 63) break;
+    }
+  }
+
+  // Check_Restart (:1133-1177) on the wide buffer: byte-align, the next 16 bits must be the
+  // expected RSTn.  The byte-wise buffer "sees" the marker iff fewer than 16 real bits are
+  // left after the alignment (then its Get_Bits (16) runs into the marker and remembers it).
+  void check_restart_wide(WideBits &wb) {
+    if (im.restart_interval <= 0) return;
+    if (--rst_count != 0) return;
+    wb.drop(wb.len & 7);
+    wb.need(16);
+    const bool seen = wb.real() < 16 && wb.memo_marker == (uint8_t)(0xD0 + next_rst);
+    if (!seen)
+      throw error_in_image_data(fmt("JPEG: expected RST (restart) marker Nb %d; code found %04X; expected %04X",
+                                    next_rst, wb.peek(16), 0xFFD0 + next_rst));
+    wb.reset();
+    next_rst = (next_rst + 1) & 7;
+    rst_count = im.restart_interval;
+    dc_pred[0] = dc_pred[1] = dc_pred[2] = 0;
+  }
+
+  // ---- restart-interval-parallel baseline scan ----------------
+  // After RSTn the predictors are reset and the bit buffer is byte-aligned (:1133-1177), so the
+  // restart intervals of a scan decode independently.  The scan's bytes are searched for the
+  // markers first; `threads` workers then decode contiguous groups of intervals, each with its
+  // own bit buffer, into disjoint blocks of the dense planes or into its own slice of the record
+  // arrays (one RUN per worker, handed over with gidcuda_job_records_commit_runs).
+  // Anything unusual -- markers out of sequence or not as many as the geometry needs, an interval
+  // with bytes left over, a record slice that fills up, any exception in a worker -- makes the
+  // function return false with the output state rewound, and the serial loop decodes the scan:
+  // error behaviour and messages stay those of the serial decoder.
+  struct Run { size_t begin[3] = {0, 0, 0}, count[3] = {0, 0, 0}; };
+  std::vector<Run> runs;  // one per worker after a successful parallel scan, else empty
+  int parallel_threads = 1;
+
+  bool parallel_baseline_scan() {
+    const int ri = im.restart_interval;
+    const long nmcu = (long)mcu_count_image_h * mcu_count_image_v;
+    if (ri <= 0 || parallel_threads < 2 || nmcu < 2048) return false;
+    const long nseg = (nmcu + ri - 1) / ri;
+    const int T = (int)std::min<long>(parallel_threads, nseg / 4);
+    if (T < 2) return false;
+    // -- where the intervals begin and end
+    const uint8_t *d = r.s.data;
+    const size_t size = r.s.size;
+    std::vector<size_t> seg_begin((size_t)nseg), seg_end((size_t)nseg);
+    {
+      size_t i = r.s.pos;
+      long k = 0;
+      seg_begin[0] = i;
+      for (;;) {
+        const void *f = i < size ? memchr(d + i, 0xFF, size - i) : nullptr;
+        if (!f) { seg_end[(size_t)k] = size; break; }
+        i = (size_t)((const uint8_t *)f - d);
+        const uint8_t m = i + 1 < size ? d[i + 1] : (uint8_t)M_EOI;
+        if (m == 0) { i += 2; continue; }
+        seg_end[(size_t)k] = i;
+        if (m >= M_RST0 && m <= M_RST7) {
+          if (m != (uint8_t)(M_RST0 + (k & 7)) || k + 1 >= nseg) return false;
+          seg_begin[(size_t)++k] = i + 2;
+          i += 2;
+          continue;
+        }
+        break;  // the marker that ends the scan (or one the serial decoder will complain about)
+      }
+      if (k != nseg - 1) return false;
+    }
+    // -- workers
+    int ncomp_blocks[3] = {0, 0, 0};
+    const HuffTable *tdc[3] = {nullptr, nullptr, nullptr}, *tac[3] = {nullptr, nullptr, nullptr};
+    for (int c = 0; c < 3; c++)
+      if (im.info[c].present) {
+        ncomp_blocks[c] = im.info[c].samples_hor * im.info[c].samples_ver;
+        tdc[c] = &table(0, ht_dc[c]);
+        tac[c] = &table(1, ht_ac[c]);
+      }
+    std::vector<Run> out((size_t)T);
+    std::vector<std::array<int, 3>> rows((size_t)T, std::array<int, 3>{{0, 0, 0}});
+    std::atomic<bool> failed{false};
+    const int mh = mcu_count_image_h;
+    auto work = [&](int w) {
+      try {
+        const long s0 = nseg * w / T, s1 = nseg * (w + 1) / T;
+        RecordSink loc[3];
+        for (int c = 0; c < 3; c++)
+          if (im.info[c].present && sink[c].on) {
+            const uint64_t seq0 = (uint64_t)s0 * ri * ncomp_blocks[c];
+            const uint64_t seq1 = std::min<uint64_t>((uint64_t)s1 * ri, (uint64_t)nmcu) * ncomp_blocks[c];
+            // a slice of the record array in proportion to the blocks (32 records per block)
+            const size_t b0 = (size_t)(sink[c].cap / sink[c].nblocks * seq0);
+            const size_t b1 = (size_t)(sink[c].cap / sink[c].nblocks * seq1);
+            loc[c].first = sink[c].first;
+            loc[c].rec = sink[c].rec + b0;
+            loc[c].cap = b1 - b0;
+            loc[c].seq = (uint32_t)seq0;
+            loc[c].on = true;
+            out[(size_t)w].begin[c] = b0;
+          }
+        for (long sg = s0; sg < s1 && !failed.load(std::memory_order_relaxed); sg++) {
+          WideBits wb(d, seg_begin[(size_t)sg], seg_end[(size_t)sg]);
+          int pred[3] = {0, 0, 0};
+          const long m1 = std::min<long>((sg + 1) * ri, nmcu);
+          for (long m = sg * ri; m < m1; m++) {
+            const int mx = (int)(m % mh), my = (int)(m / mh);
+            for (int c = 0; c < 3; c++) {
+              if (!im.info[c].present) continue;
+              const Component_Info &ci = im.info[c];
+              RecordSink *k = loc[c].on ? &loc[c] : nullptr;
+              if (k && k->n + 64 * (size_t)ncomp_blocks[c] > k->cap) { failed = true; return; }
+              for (int sy = 0; sy < ci.samples_ver; sy++)
+                for (int sx = 0; sx < ci.samples_hor; sx++)
+                  baseline_block(wb, *tdc[c], *tac[c], pred[c], k,
+                                 k ? nullptr : plane[c].block(mx * ci.samples_hor + sx, my * ci.samples_ver + sy),
+                                 rows[(size_t)w][(size_t)c]);
+            }
+          }
+          // every interval but the last must end where its RSTn begins: all bytes loaded, less
+          // than a byte of real bits left (the serial check tolerates more; let it decide then)
+          if (sg != nseg - 1) {
+            wb.drop(wb.len & 7);
+            if (wb.pos < wb.size || wb.real() >= 8 || wb.bad) { failed = true; return; }
+          }
+        }
+        for (int c = 0; c < 3; c++) out[(size_t)w].count[c] = loc[c].n;
+      } catch (...) {
+        failed = true;
+      }
+    };
+    std::vector<std::thread> pool;
+    for (int w = 1; w < T; w++) pool.emplace_back(work, w);
+    work(0);
+    for (std::thread &t : pool) t.join();
+    (failed ? detail::parallel_fallbacks : detail::parallel_scans).fetch_add(1, std::memory_order_relaxed);
+    if (failed) {
+      for (int c = 0; c < 3; c++)  // rewind: the serial loop starts from clean planes
+        if (im.info[c].present && !sink[c].on && plane[c].base)
+          memset(plane[c].base, 0, (size_t)plane[c].blocks_x * (size_t)plane[c].blocks_y * 64 * sizeof(int16_t));
+      return false;
+    }
+    // -- stitch: first[] numbers the records of the concatenated runs
+    for (int c = 0; c < 3; c++) {
+      if (!im.info[c].present) continue;
+      if (!sink[c].on) {
+        for (int w = 0; w < T; w++) last_row[c] = std::max(last_row[c], rows[(size_t)w][(size_t)c]);
+        continue;
+      }
+      size_t base = 0;
+      for (int w = 0; w < T; w++) {
+        const long s0 = nseg * w / T, s1 = nseg * (w + 1) / T;
+        const uint64_t seq0 = (uint64_t)s0 * ri * ncomp_blocks[c];
+        const uint64_t seq1 = std::min<uint64_t>((uint64_t)s1 * ri, (uint64_t)nmcu) * ncomp_blocks[c];
+        if (base)
+          for (uint64_t q = seq0; q < seq1; q++) sink[c].first[q] += (uint32_t)base;
+        base += out[(size_t)w].count[c];
+      }
+      sink[c].n = base;
+      sink[c].seq = sink[c].nblocks;
+    }
+    runs = out;
+    emit_feedback(50);
+    return true;
+  }
+
+  void baseline_scan() {  // :1179-1220; loops over FRAME components like the reference (:1190-1191)
+    const int mh = mcu_count_image_h, mv = mcu_count_image_v;
+    if (parallel_baseline_scan()) return;
+    rst_count = im.restart_interval;
+    next_rst = 0;
+    WideBits wb(r.s.data, r.s.pos, r.s.size);
+    const HuffTable *tdc[3] = {nullptr, nullptr, nullptr}, *tac[3] = {nullptr, nullptr, nullptr};
+    for (int c = 0; c < 3; c++)
+      if (im.info[c].present) {
+        tdc[c] = &table(0, ht_dc[c]);
+        tac[c] = &table(1, ht_ac[c]);
+      }
+    for (int my = 0; my < mv; my++) {
+      for (int mx = 0; mx < mh; mx++) {
+        for (int c = 0; c < 3; c++) {
+          if (!im.info[c].present) continue;
+          const Component_Info &ci = im.info[c];
+          for (int sy = 0; sy < ci.samples_ver; sy++)
+            for (int sx = 0; sx < ci.samples_hor; sx++) {
+              RecordSink &k = sink[c];
+              if (k.on && k.n + 64 > k.cap) spill(c);
+              baseline_block(wb, *tdc[c], *tac[c], dc_pred[c], k.on ? &k : nullptr,
+                             k.on ? nullptr : plane[c].block(mx * ci.samples_hor + sx, my * ci.samples_ver + sy),
+                             last_row[c]);
+            }
+        }
+        if (!(my == mv - 1 && mx == mh - 1)) check_restart_wide(wb);
+      }
+      emit_feedback((50 * (my + 1)) / mv);
+    }
+    r.s.pos = wb.pos;
+    bits.memo_marker = wb.memo_marker;
+  }
+
+  // ---- progressive (:1243-1747; ITU T.81 annex G) ----
+
+  void dc_first(int c, int16_t *blk, int al) {
+    const int s = bits.symbol(table(0, ht_dc[c]));
+    dc_pred[c] += bits.receive_extend(s & 15);
+    blk[0] = (int16_t)(dc_pred[c] * (1 << al));
+  }
+  void dc_refine(int16_t *blk, int al) {
+    if (bits.get(1)) blk[0] = (int16_t)(blk[0] | (1 << al));
+  }
+  void ac_first(int c, int16_t *blk, int ss, int se, int al) {
+    if (eobrun > 0) { eobrun--; return; }
+    const HuffTable &ac = table(1, ht_ac[c]);
+    for (int k = ss; k <= se;) {
+      const int rs = bits.symbol(ac), rr = rs >> 4, s = rs & 15;
+      if (s == 0) {
+        if (rr < 15) {
+          eobrun = (1 << rr) - 1;
+          if (rr) eobrun += bits.get(rr);
+          break;
+        }
+        k += 16;
+      } else {
+        k += rr;
+        if (k > 63) throw error_in_image_data("JPEG: progressive: coefficient index > 63");
+        const int nat = kZigZag[k];
+        blk[nat] = (int16_t)(bits.receive_extend(s) * (1 << al));
+        if ((nat >> 3) > last_row[c]) last_row[c] = nat >> 3;
+        k++;
+      }
+    }
+  }
+  void ac_refine(int c, int16_t *blk, int ss, int se, int al) {
+    const int p1 = 1 << al, m1 = -(1 << al);
+    int k = ss;
+    if (eobrun <= 0) {
+      const HuffTable &ac = table(1, ht_ac[c]);
+      for (; k <= se; k++) {
+        const int rs = bits.symbol(ac);
+        int rr = rs >> 4;
+        const int s = rs & 15;
+        int value = 0;
+        if (s == 0) {
+          if (rr < 15) {
+            eobrun = 1 << rr;
+            if (rr) eobrun += bits.get(rr);
+            break;
+          }
+        } else {
+          if (s != 1) throw error_in_image_data("JPEG: progressive: AC refinement with a size other than 1");
+          value = bits.get(1) ? p1 : m1;
+        }
+        for (; k <= se; k++) {
+          int16_t &z = blk[kZigZag[k]];
+          if (z != 0) {
+            if (bits.get(1) && (z & p1) == 0) z = (int16_t)(z >= 0 ? z + p1 : z + m1);
+          } else {
+            if (rr == 0) {
+              if (value) {
+                z = (int16_t)value;
+                if ((kZigZag[k] >> 3) > last_row[c]) last_row[c] = kZigZag[k] >> 3;
+              }
+              break;
+            }
+            rr--;
+          }
+        }
+      }
+    }
+    if (eobrun > 0) {
+      for (; k <= se; k++) {
+        int16_t &z = blk[kZigZag[k]];
+        if (z != 0 && bits.get(1) && (z & p1) == 0) z = (int16_t)(z >= 0 ? z + p1 : z + m1);
+      }
+      eobrun--;
+    }
+  }
+
+  void progressive_scan(const int *comps, int ncomps, int ss, int se, int ah, int al) {
+    if (ss > se || se > 63) throw error_in_image_data("JPEG: progressive: bad spectral selection");
+    if (ss == 0 && se != 0) throw error_in_image_data("JPEG: progressive: DC and AC in the same scan");
+    if (ss > 0 && ncomps != 1) throw error_in_image_data("JPEG: progressive: AC scan with several components");
+    rst_count = im.restart_interval;
+    next_rst = 0;
+    eobrun = 0;
+    const bool first_scan = scans == 0;
+    if (ncomps > 1) {  // interleaved (DC only): MCU structure
+      for (int my = 0; my < mcu_count_image_v; my++) {
+        for (int mx = 0; mx < mcu_count_image_h; mx++) {
+          for (int i = 0; i < ncomps; i++) {
+            const int c = comps[i];
+            const Component_Info &ci = im.info[c];
+            for (int sy = 0; sy < ci.samples_ver; sy++)
+              for (int sx = 0; sx < ci.samples_hor; sx++) {
+                int16_t *blk = plane[c].block(mx * ci.samples_hor + sx, my * ci.samples_ver + sy);
+                if (ah == 0) dc_first(c, blk, al);
+                else dc_refine(blk, al);
+              }
+          }
+          if (!(my == mcu_count_image_v - 1 && mx == mcu_count_image_h - 1)) check_restart(true);
+        }
+        if (first_scan) emit_feedback((50 * (my + 1)) / mcu_count_image_v);
+      }
+      return;
+    }
+    // single component: 8x8 "MCUs" over the component's own size (:1952-1971)
+    const int c = comps[0];
+    const Component_Info &ci = im.info[c];
+    const int wc = (im.width * ci.samples_hor + im.max_samples_hor - 1) / im.max_samples_hor;
+    const int hc = (im.height * ci.samples_ver + im.max_samples_ver - 1) / im.max_samples_ver;
+    const int bw = (wc + 7) / 8, bh = (hc + 7) / 8;
+    for (int by = 0; by < bh; by++) {
+      for (int bx = 0; bx < bw; bx++) {
+        int16_t *blk = plane[c].block(bx, by);
+        if (ss == 0) {
+          if (ah == 0) dc_first(c, blk, al);
+          else dc_refine(blk, al);
+        } else if (ah == 0) {
+          ac_first(c, blk, ss, se, al);
+        } else {
+          ac_refine(c, blk, ss, se, al);
+        }
+        if (!(by == bh - 1 && bx == bw - 1)) check_restart(true);
+      }
+      if (first_scan) emit_feedback((50 * (by + 1)) / bh);
+    }
+  }
+
+  // Read_SOS (:1855-2034): scan header, then the scan's entropy-coded data.
+  void read_sos(const Segment &sg) {
+    const int n = r.byte();
+    int ncomp_image = 0;
+    for (const Component_Info &ci : im.info) ncomp_image += ci.present ? 1 : 0;
+    if (n > ncomp_image) throw error_in_image_data("JPEG: Scan segment has more color components than the image");
+    if (n < 1) throw error_in_image_data("JPEG: Scan segment without components");
+    if (sg.length != 4 + 2 * n) throw error_in_image_data("JPEG: Scan segment to be decoded: bad length");
+    int comps[3];
+    int id_base = 1;
+    for (int i = 0; i < n; i++) {
+      const int b = r.byte();
+      if (b == 0) id_base = 0;
+      const int c = b - id_base;
+      if (c < 0 || c > 2 || !im.info[c].present) throw error_in_image_data(fmt("JPEG: Scan: invalid ID: %d", b));
+      comps[i] = c;
+      const int t = r.byte();
+      ht_dc[c] = t >> 4;
+      ht_ac[c] = t & 15;
+    }
+    const int ss = r.byte(), se = r.byte(), approx = r.byte();
+    const int mw = 8 * im.max_samples_hor, mh = 8 * im.max_samples_ver;
+    mcu_count_image_h = (im.width + mw - 1) / mw;
+    mcu_count_image_v = (im.height + mh - 1) / mh;
+    // a subsampled component must be at least 3 samples wide / high (:2014-2019)
+    for (int i = 0; i < n; i++) {
+      const Component_Info &ci = im.info[comps[i]];
+      const int wc = (im.width * ci.samples_hor + im.max_samples_hor - 1) / im.max_samples_hor;
+      const int hc = (im.height * ci.samples_ver + im.max_samples_ver - 1) / im.max_samples_ver;
+      if ((wc < 3 && ci.samples_hor != im.max_samples_hor) || (hc < 3 && ci.samples_ver != im.max_samples_ver))
+        throw error_in_image_data("JPEG: component: sample dimension mismatch");
+    }
+    if (!plane[0].base) begin_frame();
+    rebuild_tables();
+    bits.reset();
+    dc_pred[0] = dc_pred[1] = dc_pred[2] = 0;
+    if (im.progressive) progressive_scan(comps, n, ss, se, approx >> 4, approx & 15);
+    else baseline_scan();
+    scans++;
+  }
+
+  // the segment loop of Load (:2043-2118)
+  void run() {
+    bool have_marker = false;
+    uint8_t buffered = 0;
+    for (;;) {
+      Segment sg = read_segment(r, have_marker, buffered);
+      have_marker = false;
+      switch (sg.marker) {
+        case M_DQT: read_dqt(im, r, sg.length); break;
+        case M_DHT: read_dht(im, r, sg.length); break;
+        case M_DRI: im.restart_interval = (int)r.be16(); break;
+        case M_EOI:
+          if (im.progressive && scans == 0) throw error_in_image_data("JPEG: progressive image without scans");
+          return;
+        case M_SOS:
+          read_sos(sg);
+          if (!im.progressive) return;  // baseline: the first scan is the image (:2077)
+          if (bits.memo_marker != 0) {  // the marker that ended the scan was swallowed by the bit reader
+            have_marker = true;
+            buffered = bits.memo_marker;
+          }
+          break;
+        default: r.skip(sg.length); break;
+      }
+    }
+  }
+};
+
+[[noreturn]] void raise_from_status(int rc, gidcuda_ctx *ctx) {
+  const char *m = gidcuda_last_error(ctx);
+  const std::string msg = std::string("JPEG (CUDA): ") + (m ? m : "");
+  switch (rc) {
+    case GIDCUDA_ERR_UNSUPPORTED: throw unsupported_image_subformat(msg);
+    case GIDCUDA_ERR_BAD_ARGUMENT: throw error_in_image_data(msg);
+    default: throw cuda_device_error(msg + fmt(" (status %d)", rc));
+  }
+}
+
+}  // namespace
+
+}  // namespace gid

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define GIDCUDA_ABI_VERSION 2
+#define GIDCUDA_ABI_VERSION 3
 
 /* Status codes.  The Ada binding maps DATA -> GID.error_in_image_data,
  * UNSUPPORTED -> GID.unsupported_image_subformat, the others ->
@@ -143,6 +143,15 @@ int gidcuda_job_hint_rows(gidcuda_job *job, int comp, int rows_used);
 int gidcuda_job_records(gidcuda_job *job, int comp, uint32_t **first, uint32_t **records, size_t *capacity,
                         int32_t *nblocks);
 int gidcuda_job_records_commit(gidcuda_job *job, int comp, size_t count);
+/* The same, for a component whose records were produced by SEVERAL host threads, each decoding
+ * its own group of restart intervals (Check_Restart, gid-decoding_jpg.adb:1133-1177: after RSTn the
+ * predictors are reset and the bit buffer is byte-aligned, so the intervals decode independently).
+ * Thread r stores into its own slice of the lent record array, records[run_begin[r] ..
+ * run_begin[r] + run_count[r]), the runs ascending and disjoint; first[] numbers the records of the
+ * CONCATENATION of the runs (first[0] = 0, first[nblocks] = sum of run_count).  On submit the
+ * library copies every run to its place in that concatenation: no host-side compaction pass. */
+int gidcuda_job_records_commit_runs(gidcuda_job *job, int comp, int32_t nruns, const size_t *run_begin,
+                                    const size_t *run_count);
 /* Asynchronous: host-to-device copies, reconstruction kernel, device-to-host
  * copy of the pixels, all on the job's own stream (two jobs in flight overlap
  * their transfers).  A job may be submitted again after gidcuda_job_wait. */

@@ -122,6 +122,91 @@ def test_error_classes_follow_gid(host, oracle, synth):
     assert e.value.name == "error_in_image_data"
 
 
+# --------------------------------------------------------------------------- restart-interval-parallel decode
+
+
+@pytest.fixture
+def entropy_threads(host):
+    def set_threads(n):
+        host.set_option("entropy_threads", n)
+    yield set_threads
+    host.set_option("entropy_threads", 1)
+
+
+def _outcome(host, data):
+    try:
+        _, planes = host.decode_planes(data)
+        return ("ok", hashlib.sha256(b"".join(p.tobytes() for p in planes)).hexdigest())
+    except host.GidHostError as e:
+        return ("err", e.name)
+
+
+@pytest.mark.parametrize("samp,w,h,ri,threads", [
+    ("grey", 1024, 512, 4, 4), ("420", 1024, 800, 3, 3), ("444", 640, 520, 16, 8), ("422", 1000, 600, 64, 5),
+    ("grey", 520, 8 * 300 + 3, 1, 7), ("420", 16 * 90 + 5, 16 * 30 + 9, 2700, 8),
+])
+def test_restart_parallel_scan_matches_serial_and_oracle(host, oracle, synth, entropy_threads, samp, w, h, ri, threads):
+    """the restart intervals of a baseline scan (Check_Restart,
+    gid-decoding_jpg.adb:1133-1177) decoded by several host threads give the planes of the
+    serial loop, = GID's front end (oracle), = what the encoder quantised."""
+    jpg, enc = synth.encode(pixels_for(synth, 4, w, h, samp), samp, restart_interval=ri)
+    fr, _, _ = oracle.decode(jpg)
+    entropy_threads(1)
+    before = host.counter("parallel_scans")
+    _, serial = host.decode_planes(jpg)
+    assert host.counter("parallel_scans") == before
+    entropy_threads(threads)
+    _, par = host.decode_planes(jpg)
+    # (the last case has a single restart interval: too few for the parallel path, decoded serially)
+    assert host.counter("parallel_scans") == before + (1 if ri < 2700 else 0)
+    for c in range(fr.ncomp):
+        assert np.array_equal(par[c], serial[c])
+        assert np.array_equal(par[c], fr.planes[c])
+        assert np.array_equal(par[c], enc.planes[c])
+
+
+def test_restart_parallel_scan_keeps_the_serial_error_behaviour(host, oracle, synth, entropy_threads):
+    """Damaged streams: whatever the serial decoder does with them (same planes GID's front end
+    produces, or the same exception class), the threaded decoder does too -- it hands anything
+    unusual back to the serial loop."""
+    rng = np.random.default_rng(11)
+    checked = 0
+    for samp, w, h, ri in (("grey", 1024, 512, 4), ("420", 1024, 800, 3), ("444", 640, 520, 16)):
+        jpg, _ = synth.encode(pixels_for(synth, 3, w, h, samp), samp, restart_interval=ri)
+        sos = jpg.index(b"\xff\xda")
+        for t in range(24):
+            bad = bytearray(jpg)
+            pos = int(rng.integers(sos + 14, len(bad) - 2))
+            kind = t % 4
+            if kind == 0:
+                bad[pos] = int(rng.integers(0, 256))
+            elif kind == 1:
+                del bad[pos]
+            elif kind == 2:
+                bad.insert(pos, int(rng.integers(0, 256)))
+            else:  # renumber (or, below, drop) the next restart marker
+                k = bad.find(b"\xff", pos)
+                while k > 0 and not 0xD0 <= bad[k + 1] <= 0xD7:
+                    k = bad.find(b"\xff", k + 2)
+                if k > 0 and t % 8 == 3:
+                    bad[k + 1] = 0xD0 + int(rng.integers(0, 8))
+                elif k > 0:
+                    del bad[k:k + 2]
+            bad = bytes(bad)
+            entropy_threads(1)
+            serial = _outcome(host, bad)
+            entropy_threads(4)
+            assert _outcome(host, bad) == serial, (samp, t)
+            try:
+                fr, _, _ = oracle.decode(bad)
+                ref = ("ok", hashlib.sha256(b"".join(np.asarray(p).tobytes() for p in fr.planes[:fr.ncomp])).hexdigest())
+            except Exception:
+                ref = ("err", None)
+            assert serial[0] == ref[0] and (serial[0] == "err" or serial[1] == ref[1]), (samp, t)
+            checked += 1
+    assert checked == 72
+
+
 def test_exif_orientation(host, synth):
     jpg, _ = synth.encode(pixels_for(synth, 1, 32, 32, "444"), "444")
     for value, want in ((1, 0), (8, 1), (3, 2), (6, 3), (2, 0)):
@@ -189,3 +274,58 @@ def test_primary_color_ranges(host, oracle, synth, gpu):
     with pytest.raises(host.GidHostError) as e:
         host.decode_rgb(jpg, modulus=1024)
     assert e.value.name == "invalid_primary_color_range"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("samp,w,h,ri,threads", [("grey", 1024, 520, 4, 6), ("420", 1030, 810, 3, 5), ("444", 640, 520, 16, 8)])
+def test_restart_parallel_scan_through_the_device(host, oracle, synth, gpu, coef_form, entropy_threads, samp, w, h, ri, threads):
+    """The threaded scan hands its records over as one run per worker
+    (gidcuda_job_records_commit_runs) or fills the dense planes; pixels == GID's decode."""
+    jpg, _ = synth.encode(pixels_for(synth, 6, w, h, samp), samp, restart_interval=ri)
+    _, ref, _ = oracle.decode(jpg)
+    entropy_threads(threads)
+    before = host.counter("parallel_scans")
+    rgb, fb = host.decode_rgb(jpg)
+    assert host.counter("parallel_scans") == before + 1
+    assert np.array_equal(rgb, ref)
+    assert fb == sorted(fb) and fb[-1] == 100
+
+
+@pytest.mark.gpu
+def test_file_batch_matches_gid(host, oracle, synth, gpu):
+    """gidhost_batch_decode: a mixed set of files on several host threads, two frames in flight per
+    thread; every image == GID's decode, a damaged file is reported with GID's exception class and
+    does not disturb the others; the contexts are recycled by a second call."""
+    specs = [("420", 640, 360, False, 0), ("444", 97, 61, False, 0), ("grey", 300, 200, False, 5), ("422", 320, 240, True, 0),
+             ("420", 161, 99, True, 0), ("440", 64, 80, False, 0), ("grey", 1024, 520, False, 4), ("420", 1919, 1079, False, 0)]
+    files = []
+    for k, (samp, w, h, prog, ri) in enumerate(specs * 2):
+        files.append(synth.encode(pixels_for(synth, 20 + k, w, h, samp), samp, progressive=prog, restart_interval=ri)[0])
+    bad = bytearray(files[0])
+    i = bad.index(b"\xff\xda")
+    bad[i] = 0x12                       # garbage where a marker should be -> error_in_image_data
+    files.insert(3, bytes(bad))
+    files.insert(9, b"GIF89a" + bytes(64))  # another format GID knows
+    refs = []
+    for f in files:
+        try:
+            refs.append(oracle.decode(f)[1])
+        except Exception:
+            refs.append(None)
+    with host.HostBatch(devices=(0,), threads=4) as hb:
+        for _ in range(2):
+            imgs, st, stats = hb.decode(files)
+            assert stats.images_failed == 2 and stats.threads == 4
+            assert host.ERRORS[st[3]] == "error_in_image_data" and host.ERRORS[st[9]] == "known_but_unsupported_image_format"
+            for k, (img, ref) in enumerate(zip(imgs, refs)):
+                if ref is None:
+                    assert img is None and st[k] != 0
+                else:
+                    assert st[k] == 0 and np.array_equal(img, ref), k
+            assert abs(stats.megapixels - sum(r.shape[0] * r.shape[1] for r in refs if r is not None) / 1e6) < 1e-6
+    # fewer files than threads: the spare threads go into the restart-interval-parallel scan
+    big = synth.encode(pixels_for(synth, 31, 2048, 1024, "grey"), "grey", restart_interval=64)[0]
+    before = host.counter("parallel_scans")
+    imgs, st, stats = host.decode_batch([big], threads=8)
+    assert st == [0] and stats.entropy_threads == 8 and host.counter("parallel_scans") == before + 1
+    assert np.array_equal(imgs[0], oracle.decode(big)[1])
