@@ -15,6 +15,8 @@ Printed JSON (one line, rank 0):
   roofline     algorithmic bytes / kernel time against the measured HBM peak
   cpu_baseline the oracle's reconstruction (GID restated in C; GNAT is not
                available, so the Ada benchmark cannot be built) on the host cores
+  files        (beside the path) the same metric from .jpg bytes: Huffman decode
+               on the host threads, reconstruction on the GPU, pixels back in host memory
 
 `--impl reference` times that CPU restatement alone, with all host threads, on
 the same workload definition, and prints the same line with "impl": "reference".
@@ -66,6 +68,96 @@ def make_frames(workload: str, count: int, seed0: int):
         pix = img[:, :, 1].copy() if samp == "grey" else img
         frames.append(S.planes_only(pix, samp))
     return frames
+
+
+# JPEG-file form of each workload: (progressive, restart interval, files per call)
+FILE_FORM = {"cfg1": (False, 0, 256), "cfg2": (False, 0, 8), "cfg3": (False, 0, 64), "cfg4": (False, 64, 4),
+             "cfg5": (True, 0, 32)}
+
+
+def make_files(workload: str, count: int, seed0: int) -> list[bytes]:
+    """`count` distinct synthetic .jpg files of the workload (in-run encoder of the test harness)."""
+    from tests.harness import Synth
+    w, h, samp, _, _ = WORKLOADS[workload]
+    prog, ri, _ = FILE_FORM[workload]
+    S = Synth()
+    out = []
+    for i in range(count):
+        img = S.image(seed0 + i, w, h)
+        pix = img[:, :, 1].copy() if samp == "grey" else img
+        out.append(S.encode(pix, samp, progressive=prog, restart_interval=ri)[0])
+    return out
+
+
+def files_leg_ours(workload: str, device: int, threads: int, reps: int, pinned: bool = True) -> dict:
+    """.jpg bytes in host memory -> RGB8 in host memory: entropy decode on `threads` host threads
+    (restart-interval-parallel inside a frame when there are fewer files than threads),
+    reconstruction on the B200, through gidhost_batch_decode."""
+    from gid_b200 import host_api
+    w, h, _, _, _ = WORKLOADS[workload]
+    prog, ri, per_call = FILE_FORM[workload]
+    distinct = make_files(workload, 2, 77)
+    files = [distinct[i % 2] for i in range(per_call)]
+    # the client's image buffers: pinned host memory (the pixels arrive straight from the device)
+    # or ordinary memory (one more copy per image on the host)
+    from gid_b200 import capi
+    addrs = []
+    if pinned:
+        out = []
+        for _ in range(per_call):
+            a, addr = capi.pinned_empty(3 * w * h)
+            addrs.append(addr)
+            out.append(a.reshape(h, w, 3))
+    else:
+        out = [np.empty((h, w, 3), dtype=np.uint8) for _ in range(per_call)]
+    with host_api.HostBatch(devices=(device,), threads=threads) as hb:
+        _, st, stats = hb.decode(files, out)  # warm-up: contexts, pinned buffers
+        assert not any(st), st
+        secs = 0.0
+        for _ in range(reps):
+            _, st, stats = hb.decode(files, out)
+            secs += stats.seconds
+    del out
+    for addr in addrs:
+        capi.pinned_free(addr)
+    return {"value": w * h * per_call * reps / 1e6 / secs, "unit": UNIT, "threads": int(stats.threads),
+            "entropy_threads_per_image": int(stats.entropy_threads), "images_per_call": per_call, "calls": reps,
+            "jpeg_bytes_per_image": len(distinct[0]), "progressive": prog, "restart_interval": ri,
+            "output": "pinned client buffers (no host copy)" if pinned else "pageable client buffers (one host copy)",
+            "api": "gidhost_batch_decode: .jpg bytes -> Huffman decode on host threads -> coefficient records -> "
+                   "B200 reconstruction -> top-down RGB8 in host memory, two frames in flight per thread"}
+
+
+def files_leg_reference(workload: str, threads: int, seconds_target: float) -> dict:
+    """The oracle's whole decode of the same files (segments, Huffman, reconstruction, per-pixel
+    Put_Pixel client: what test/benchmark.adb times) on `threads` host threads."""
+    from tests.harness import Oracle
+    w, h, _, _, _ = WORKLOADS[workload]
+    prog, ri, _ = FILE_FORM[workload]
+    files = make_files(workload, 2, 77)
+    O = Oracle()
+    t0 = time.perf_counter()
+    O.decode(files[0], want_planes=False)
+    one = time.perf_counter() - t0
+    reps = max(1, int(round(seconds_target / max(one, 1e-3))))
+    done = [0] * threads
+
+    def work(k: int) -> None:
+        for r in range(reps):
+            O.decode(files[(k + r) % 2], want_planes=False)
+            done[k] += 1
+
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(threads)]
+    t0 = time.perf_counter()
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    dt = time.perf_counter() - t0
+    return {"value": w * h * sum(done) / 1e6 / dt, "unit": UNIT, "threads": threads,
+            "sample": f"{reps} file(s) per thread on {threads} thread(s), {dt:.1f} s wall",
+            "jpeg_bytes_per_image": len(files[0]), "progressive": prog, "restart_interval": ri,
+            "api": "oracle/gidref.c gidref_decode: whole GID decode restated in C (GNAT unavailable)"}
 
 
 class ClockSampler:
@@ -197,6 +289,8 @@ def run_reference(args) -> None:
                                  "GNAT is not installed so test/benchmark.adb cannot be built"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if not args.no_files:
+        line["files"] = files_leg_reference(args.workload, cores, 3.0)
     print(json.dumps(line), flush=True)
 
 
@@ -366,6 +460,15 @@ def run_ours(args) -> None:
     for job in jobs:
         L.gidcuda_job_release(job)
 
+    # ---- from .jpg files: host entropy decode on this rank's share of the cores + the path above ----
+    files = None
+    if not args.no_files:
+        share = max(1, (os.cpu_count() or 1) // world)
+        files = files_leg_ours(args.workload, local, share, 3)
+        secs = w * h * files["images_per_call"] * files["calls"] / 1e6 / files["value"]
+        files["value"] = sharding.whole_job_rate(w * h * files["images_per_call"] * files["calls"] / 1e6, world,
+                                                 sharding.max_over_ranks(secs, dev))
+
     # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -399,6 +502,8 @@ def run_ours(args) -> None:
                          "algorithmic_bytes_per_launch": alg_bytes_frame * per_step},
             "cpu_baseline": cpu,
         }
+        if files is not None:
+            line["files"] = files
         print(json.dumps(line), flush=True)
     for p in plans:
         ctx.plan_destroy(p)
@@ -415,6 +520,7 @@ def main() -> None:
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg2")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-files", action="store_true", help="skip the .jpg-files leg (host entropy decode + the path)")
     ap.add_argument("--e2e-input", choices=["records", "planes"], default="records",
                     help="host-side form of the coefficients in the end-to-end leg: sparse records (what an entropy "
                          "decoder emits) or dense int16 planes")

@@ -29,7 +29,7 @@ EXPORTS = [
     "gidcuda_abi_version", "gidcuda_device_count", "gidcuda_last_error", "gidcuda_set_option", "gidcuda_create",
     "gidcuda_destroy", "gidcuda_plane_geometry", "gidcuda_output_geometry", "gidcuda_job_begin",
     "gidcuda_job_plane", "gidcuda_job_hint_rows", "gidcuda_job_records", "gidcuda_job_records_commit", "gidcuda_job_records_commit_runs",
-    "gidcuda_job_submit", "gidcuda_job_wait", "gidcuda_job_release",
+    "gidcuda_job_output", "gidcuda_host_is_pinned", "gidcuda_job_submit", "gidcuda_job_wait", "gidcuda_job_release",
     "gidcuda_plan_create", "gidcuda_plan_launch", "gidcuda_plan_launch_count", "gidcuda_plan_uses_tma",
     "gidcuda_plan_destroy", "gidcuda_synchronize", "gidcuda_batch_create", "gidcuda_batch_run",
     "gidcuda_batch_destroy", "gidcuda_host_alloc", "gidcuda_host_free",
@@ -113,6 +113,8 @@ def load_library() -> ctypes.CDLL:
     L.gidcuda_job_records_commit.argtypes = [vp, ctypes.c_int, ctypes.c_size_t]
     L.gidcuda_job_records_commit_runs.argtypes = [vp, ctypes.c_int, ctypes.c_int32, ctypes.POINTER(ctypes.c_size_t),
                                                   ctypes.POINTER(ctypes.c_size_t)]
+    L.gidcuda_job_output.argtypes = [vp, vp, ctypes.c_size_t]
+    L.gidcuda_host_is_pinned.argtypes = [vp]
     L.gidcuda_job_submit.argtypes = [vp]
     L.gidcuda_job_wait.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t)]
     L.gidcuda_job_release.argtypes = [vp]

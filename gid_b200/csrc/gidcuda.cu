@@ -167,6 +167,7 @@ struct gidcuda_job {
   // empty = one run starting at 0 (gidcuda_job_records_commit)
   std::vector<std::pair<size_t, size_t>> sparse_runs[3];
   uint8_t *h_pixels = nullptr;  // pinned
+  uint8_t *user_pixels = nullptr;  // gidcuda_job_output: the caller's own pinned buffer receives the pixels
   uint8_t *d_coef = nullptr, *d_pixels = nullptr, *d_samples = nullptr;
   gidk::LaunchSet set;
   cudaEvent_t done = nullptr;
@@ -313,6 +314,7 @@ extern "C" int gidcuda_job_begin(gidcuda_ctx *ctx, const gidcuda_frame_desc *des
   it.samples = j->d_samples;
   j->set.build(std::vector<gidk::FrameItem>(1, it));
   j->h_coef_clean = false;  // zeroed when the decoder asks for the planes
+  j->user_pixels = nullptr;
   for (int c = 0; c < 3; c++) {
     j->rows_hint[c] = 8;
     j->sparse[c] = false;
@@ -410,6 +412,35 @@ extern "C" int gidcuda_job_records_commit_runs(gidcuda_job *job, int comp, int32
   return GIDCUDA_OK;
 }
 
+static bool is_pinned_host(const void *p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
+}
+
+extern "C" int gidcuda_host_is_pinned(const void *ptr) { return ptr && is_pinned_host(ptr) ? 1 : 0; }
+
+extern "C" int gidcuda_job_output(gidcuda_job *job, uint8_t *host_pixels, size_t capacity) {
+  if (!job) return fail(nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "null job");
+  if (job->state != gidcuda_job::BEGUN)
+    return fail(job->ctx, GIDCUDA_ERR_STATE, "gidcuda_job_output: only between gidcuda_job_begin and gidcuda_job_submit");
+  if (!host_pixels) {
+    job->user_pixels = nullptr;
+    return GIDCUDA_OK;
+  }
+  if (capacity < job->geo.pixel_bytes)
+    return fail(job->ctx, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_job_output: %zu bytes, the frame needs %zu", capacity,
+                job->geo.pixel_bytes);
+  if (!is_pinned_host(host_pixels))
+    return fail(job->ctx, GIDCUDA_ERR_BAD_ARGUMENT,
+                "gidcuda_job_output: the buffer is not pinned host memory (gidcuda_host_alloc / cudaHostRegister)");
+  job->user_pixels = host_pixels;
+  return GIDCUDA_OK;
+}
+
 extern "C" int gidcuda_job_hint_rows(gidcuda_job *job, int comp, int rows_used) {
   if (!job) return fail(nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "null job");
   if (job->state == gidcuda_job::IDLE) return fail(job->ctx, GIDCUDA_ERR_STATE, "gidcuda_job_hint_rows: job was released");
@@ -504,7 +535,8 @@ extern "C" int gidcuda_job_submit(gidcuda_job *job) {
     CU_TRY(ctx, gidk::launch_expand(ea, g.ncomp, s));
   }
   CU_TRY(ctx, job->set.launch(ctx->num_sms, s));
-  CU_TRY(ctx, cudaMemcpyAsync(job->h_pixels, job->d_pixels, g.pixel_bytes, cudaMemcpyDeviceToHost, s));
+  CU_TRY(ctx, cudaMemcpyAsync(job->user_pixels ? job->user_pixels : job->h_pixels, job->d_pixels, g.pixel_bytes,
+                              cudaMemcpyDeviceToHost, s));
   CU_TRY(ctx, cudaEventRecord(job->done, s));
   job->state = gidcuda_job::SUBMITTED;
   return GIDCUDA_OK;
@@ -516,7 +548,7 @@ extern "C" int gidcuda_job_wait(gidcuda_job *job, const uint8_t **pixels, size_t
   if (job->state != gidcuda_job::SUBMITTED)
     return fail(ctx, GIDCUDA_ERR_STATE, "gidcuda_job_wait: job was not submitted");
   CU_TRY(ctx, cudaEventSynchronize(job->done));
-  if (pixels) *pixels = job->h_pixels;
+  if (pixels) *pixels = job->user_pixels ? job->user_pixels : job->h_pixels;
   if (stride) *stride = job->geo.stride;
   return GIDCUDA_OK;
 }

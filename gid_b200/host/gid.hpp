@@ -139,7 +139,10 @@ void release(Reconstruction &r);
 // The two halves of the above for callers that keep several frames in flight on one context
 // (gid_batch.cpp): entropy-decode into a job of `ctx` and submit it (asynchronous; returns the
 // gidcuda_job), later gidcuda_job_wait / gidcuda_job_release.
-void *decode_and_submit(Image_Descriptor &image, void *ctx, const std::function<void(int)> &feedback);
+// out (optional): the caller's top-down packed RGB8 buffer; when it is pinned host memory the
+// pixels land there directly (gidcuda_job_output) and gidcuda_job_wait returns that address.
+void *decode_and_submit(Image_Descriptor &image, void *ctx, const std::function<void(int)> &feedback,
+                        uint8_t *out = nullptr, size_t out_capacity = 0);
 
 // Entropy decode only, into calloc'd planes (see gidhost_decode_planes).
 void decode_planes(Image_Descriptor &image, struct ::gidcuda_frame_desc *desc, int16_t *planes[3], int32_t blocks_x[3],

@@ -9,9 +9,10 @@
 // it on their core (gid-decoding_jpg.adb:1179-1220 / :1243-1747) straight into the pinned
 // record arrays of a job, submit it, and -- while that frame crosses the link and is
 // reconstructed on the B200 -- start on their next file.  Two frames are in flight per
-// worker.  Finished pixels are copied to the caller's top-down RGB8 buffers (the buffer
-// test/benchmark.adb:67-81 fills through Put_Pixel).  No inter-GPU communication: images
-// carry no cross-GPU data.
+// worker.  Finished pixels go to the caller's top-down RGB8 buffers (the buffer
+// test/benchmark.adb:67-81 fills through Put_Pixel): straight from the device when a buffer
+// is pinned host memory (gidcuda_host_alloc), through a copy otherwise.  No inter-GPU
+// communication: images carry no cross-GPU data.
 //
 // A file that fails (any of GID's exceptions) is reported in status[] and skipped; the
 // others are unaffected.  When there are fewer files than threads (one big frame), the
@@ -116,7 +117,9 @@ int gidhost_batch_decode(gidhost_batch *b, int32_t n, const uint8_t *const *data
         if (st != GIDCUDA_OK) gid::raise_from_status(st, ctx);
         const size_t row = (size_t)3 * (size_t)f.w;
         uint8_t *out = rgb[f.index];
-        if (stride == row) memcpy(out, px, row * (size_t)f.h);
+        if (px == out) {
+          // the caller's buffer is pinned: the pixels arrived there straight from the device
+        } else if (stride == row) memcpy(out, px, row * (size_t)f.h);
         else
           for (int y = 0; y < f.h; y++) memcpy(out + (size_t)y * row, px + (size_t)y * stride, row);
         mp += (double)f.w * f.h / 1e6;
@@ -141,7 +144,7 @@ int gidhost_batch_decode(gidhost_batch *b, int32_t n, const uint8_t *const *data
         im.entropy_threads = per_image;
         if ((size_t)3 * (size_t)im.width * (size_t)im.height > rgb_capacity[i])
           throw gid::gid_error("output buffer too small");
-        cur.job = static_cast<gidcuda_job *>(gid::detail::decode_and_submit(im, ctx, no_feedback));
+        cur.job = static_cast<gidcuda_job *>(gid::detail::decode_and_submit(im, ctx, no_feedback, rgb[i], rgb_capacity[i]));
         cur.index = i;
         cur.w = im.width;
         cur.h = im.height;

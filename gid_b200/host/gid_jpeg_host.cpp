@@ -148,7 +148,8 @@ static int resolve_threads(int n) {
   return hw ? (int)hw : 1;
 }
 
-void *decode_and_submit(Image_Descriptor &image, void *ctx_, const std::function<void(int)> &feedback) {
+void *decode_and_submit(Image_Descriptor &image, void *ctx_, const std::function<void(int)> &feedback, uint8_t *out,
+                        size_t out_capacity) {
   if (!image.stream) throw constraint_error("Load_Image_Contents: no header was loaded");
   gidcuda_ctx *ctx = static_cast<gidcuda_ctx *>(ctx_);
   gidcuda_frame_desc desc;
@@ -252,6 +253,10 @@ void *decode_and_submit(Image_Descriptor &image, void *ctx_, const std::function
         continue;
       }
       rc = gidcuda_job_hint_rows(job, comp_of[c], dec.last_row[c] + 1);
+      if (rc != GIDCUDA_OK) raise_from_status(rc, ctx);
+    }
+    if (out && gidcuda_host_is_pinned(out)) {
+      rc = gidcuda_job_output(job, out, out_capacity);
       if (rc != GIDCUDA_OK) raise_from_status(rc, ctx);
     }
     rc = gidcuda_job_submit(job);

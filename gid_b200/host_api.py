@@ -179,7 +179,8 @@ class HostBatch:
 
     def decode(self, files, out=None):
         """Returns (list of (H, W, 3) uint8 arrays -- None where the file failed --, list of status
-        codes, HostBatchStats).  `out`: optional preallocated arrays to decode into."""
+        codes, HostBatchStats).  `out`: optional preallocated arrays to decode into; arrays in pinned
+        memory (capi.pinned_empty) receive their pixels straight from the device."""
         n = len(files)
         if out is None:
             out = []

@@ -152,6 +152,13 @@ int gidcuda_job_records_commit(gidcuda_job *job, int comp, size_t count);
  * library copies every run to its place in that concatenation: no host-side compaction pass. */
 int gidcuda_job_records_commit_runs(gidcuda_job *job, int comp, int32_t nruns, const size_t *run_begin,
                                     const size_t *run_count);
+/* Optional: let the pixels land in the CALLER's buffer instead of one owned by the job -- the
+ * image buffer a client fills through Put_Pixel (test/benchmark.adb:67-81) handed over whole, so
+ * that no copy follows the device-to-host transfer.  host_pixels must be pinned host memory
+ * (gidcuda_host_alloc, or registered with the CUDA runtime) of at least gidcuda_output_geometry
+ * bytes, and stay valid until gidcuda_job_wait returns; the layout is the job's (format, stride).
+ * Between gidcuda_job_begin and gidcuda_job_submit; NULL returns to the job's own buffer. */
+int gidcuda_job_output(gidcuda_job *job, uint8_t *host_pixels, size_t capacity);
 /* Asynchronous: host-to-device copies, reconstruction kernel, device-to-host
  * copy of the pixels, all on the job's own stream (two jobs in flight overlap
  * their transfers).  A job may be submitted again after gidcuda_job_wait. */
@@ -213,6 +220,8 @@ int gidcuda_batch_destroy(gidcuda_batch *batch);
 /* Pinned host memory for callers that want the fast copy path. */
 int gidcuda_host_alloc(size_t bytes, void **ptr);
 int gidcuda_host_free(void *ptr);
+/* 1 when ptr points into pinned (page-locked) host memory known to the CUDA runtime, else 0. */
+int gidcuda_host_is_pinned(const void *ptr);
 
 #ifdef __cplusplus
 }

@@ -329,3 +329,42 @@ def test_file_batch_matches_gid(host, oracle, synth, gpu):
     imgs, st, stats = host.decode_batch([big], threads=8)
     assert st == [0] and stats.entropy_threads == 8 and host.counter("parallel_scans") == before + 1
     assert np.array_equal(imgs[0], oracle.decode(big)[1])
+
+
+@pytest.mark.gpu
+def test_pixels_land_in_the_callers_pinned_buffer(host, oracle, synth, gpu):
+    """gidcuda_job_output: the client's own (pinned) image buffer receives the pixels straight from
+    the device; ordinary memory is refused there, and the batch driver copies instead."""
+    import ctypes
+    from gid_b200 import capi
+    from tests.harness import frame_desc
+    L = gpu.lib
+    jpg, enc = synth.encode(pixels_for(synth, 12, 333, 211, "420"), "420")
+    _, ref, _ = oracle.decode(jpg)
+    desc = frame_desc(enc, flags=capi.FLAG_PACKED_ROWS)
+    buf, addr = capi.pinned_empty(ref.nbytes)
+    try:
+        assert L.gidcuda_host_is_pinned(ctypes.c_void_p(addr)) == 1
+        plain = np.zeros(ref.nbytes, dtype=np.uint8)
+        assert L.gidcuda_host_is_pinned(ctypes.c_void_p(plain.ctypes.data)) == 0
+        job = ctypes.c_void_p()
+        assert L.gidcuda_job_begin(gpu.ctx, ctypes.byref(desc), ctypes.byref(job)) == 0
+        assert L.gidcuda_job_output(job, ctypes.c_void_p(plain.ctypes.data), plain.nbytes) == -1   # not pinned
+        assert L.gidcuda_job_output(job, ctypes.c_void_p(addr), ref.nbytes - 1) == -1                # too small
+        assert L.gidcuda_job_output(job, ctypes.c_void_p(addr), ref.nbytes) == 0
+        for c in range(enc.ncomp):
+            p = L.gidcuda_job_plane(job, c, None, None)
+            ctypes.memmove(p, enc.planes[c].ctypes.data, enc.planes[c].nbytes)
+        assert L.gidcuda_job_submit(job) == 0
+        assert L.gidcuda_job_output(job, None, 0) == -6                                                # state
+        pix, st = ctypes.c_void_p(), ctypes.c_size_t()
+        assert L.gidcuda_job_wait(job, ctypes.byref(pix), ctypes.byref(st)) == 0
+        assert pix.value == addr and st.value == 3 * 333
+        assert np.array_equal(buf.reshape(ref.shape), ref)
+        assert L.gidcuda_job_release(job) == 0
+        # the batch driver: pinned and ordinary client buffers side by side
+        buf[:] = 0
+        imgs, st, _ = host.HostBatch(devices=(0,), threads=2).decode([jpg, jpg], [buf.reshape(ref.shape), plain.reshape(ref.shape)])
+        assert st == [0, 0] and np.array_equal(imgs[0], ref) and np.array_equal(imgs[1], ref)
+    finally:
+        capi.pinned_free(addr)

@@ -10,5 +10,5 @@ python - <<PY
 import json
 for l in open("gpurun_out/${tag}_bench.jsonl"):
     d=json.loads(l)
-    print("${tag}", d["config"]["workload"][:4], "value %.0f MP/s" % d["value"], "ms/step %.4f" % d["ms_per_step"], "frac %.3f" % d["roofline"]["frac"], "e2e %.0f" % d["e2e"]["value"], d["clocks"]["sm_mhz"], d["clocks"]["reasons"])
+    print("${tag}", d["config"]["workload"][:4], "value %.0f MP/s" % d["value"], "ms/step %.4f" % d["ms_per_step"], "frac %.3f" % d["roofline"]["frac"], "e2e %.0f" % d["e2e"]["value"], "files %.0f (%d thr)" % (d["files"]["value"], d["files"]["threads"]) if d.get("files") else "", d["clocks"]["sm_mhz"], d["clocks"]["reasons"])
 PY
