@@ -18,6 +18,7 @@ GIDCUDA_OK = 0
 ERR_NAMES = {
     -1: "BAD_ARGUMENT", -2: "UNSUPPORTED", -3: "NO_DEVICE", -4: "CUDA", -5: "OUT_OF_MEMORY",
     -6: "STATE",
+    -7: "DATA",
 }
 OUT_RGB8 = 0
 OUT_BGR8_BOTTOM_UP = 1
@@ -29,7 +30,7 @@ EXPORTS = [
     "gidcuda_abi_version", "gidcuda_device_count", "gidcuda_last_error", "gidcuda_set_option", "gidcuda_create",
     "gidcuda_destroy", "gidcuda_plane_geometry", "gidcuda_output_geometry", "gidcuda_job_begin",
     "gidcuda_job_plane", "gidcuda_job_hint_rows", "gidcuda_job_records", "gidcuda_job_records_commit", "gidcuda_job_records_commit_runs",
-    "gidcuda_job_output", "gidcuda_host_is_pinned", "gidcuda_job_submit", "gidcuda_job_wait", "gidcuda_job_release",
+    "gidcuda_job_output", "gidcuda_job_scan", "gidcuda_host_is_pinned", "gidcuda_job_submit", "gidcuda_job_wait", "gidcuda_job_release",
     "gidcuda_plan_create", "gidcuda_plan_launch", "gidcuda_plan_launch_count", "gidcuda_plan_uses_tma",
     "gidcuda_plan_destroy", "gidcuda_synchronize", "gidcuda_batch_create", "gidcuda_batch_run",
     "gidcuda_batch_destroy", "gidcuda_host_alloc", "gidcuda_host_free",
@@ -56,6 +57,17 @@ class FrameDesc(ctypes.Structure):
             ctypes.memmove(d.qt[c], q[c].ctypes.data, 128)
         d.flags, d.out_stride = flags, out_stride
         return d
+
+
+class HuffmanTable(ctypes.Structure):
+    """struct gidcuda_huffman_table"""
+    _fields_ = [("counts", ctypes.c_uint8 * 16), ("symbols", ctypes.c_uint8 * 256)]
+
+
+class ScanDesc(ctypes.Structure):
+    """struct gidcuda_scan_desc"""
+    _fields_ = [("restart_interval", ctypes.c_int32), ("nintervals", ctypes.c_int32),
+                ("dc", HuffmanTable * 3), ("ac", HuffmanTable * 3)]
 
 
 class BatchStats(ctypes.Structure):
@@ -114,6 +126,8 @@ def load_library() -> ctypes.CDLL:
     L.gidcuda_job_records_commit_runs.argtypes = [vp, ctypes.c_int, ctypes.c_int32, ctypes.POINTER(ctypes.c_size_t),
                                                   ctypes.POINTER(ctypes.c_size_t)]
     L.gidcuda_job_output.argtypes = [vp, vp, ctypes.c_size_t]
+    L.gidcuda_job_scan.argtypes = [vp, ctypes.POINTER(ScanDesc), vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint32),
+                                   ctypes.POINTER(ctypes.c_uint32)]
     L.gidcuda_host_is_pinned.argtypes = [vp]
     L.gidcuda_job_submit.argtypes = [vp]
     L.gidcuda_job_wait.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t)]

@@ -167,6 +167,12 @@ struct gidcuda_job {
   // empty = one run starting at 0 (gidcuda_job_records_commit)
   std::vector<std::pair<size_t, size_t>> sparse_runs[3];
   uint8_t *h_pixels = nullptr;  // pinned
+  // gidcuda_job_scan: [6 HuffDev][begin][end][scan bytes] pinned + device twin, status words
+  uint8_t *h_scan = nullptr, *d_scan = nullptr;
+  size_t cap_scan = 0, scan_bytes = 0, scan_off_begin = 0, scan_off_end = 0, scan_off_data = 0;
+  uint32_t *h_status = nullptr, *d_status = nullptr;
+  bool scan_active = false;
+  int32_t scan_ri = 0, scan_nintervals = 0;
   uint8_t *user_pixels = nullptr;  // gidcuda_job_output: the caller's own pinned buffer receives the pixels
   uint8_t *d_coef = nullptr, *d_pixels = nullptr, *d_samples = nullptr;
   gidk::LaunchSet set;
@@ -182,6 +188,13 @@ static void job_free_buffers(gidcuda_job *j) {
   if (j->h_sparse) cudaFreeHost(j->h_sparse);
   if (j->d_sparse) cudaFree(j->d_sparse);
   if (j->h_pixels) cudaFreeHost(j->h_pixels);
+  if (j->h_scan) cudaFreeHost(j->h_scan);
+  if (j->d_scan) cudaFree(j->d_scan);
+  if (j->h_status) cudaFreeHost(j->h_status);
+  if (j->d_status) cudaFree(j->d_status);
+  j->h_scan = j->d_scan = nullptr;
+  j->h_status = j->d_status = nullptr;
+  j->cap_scan = 0;
   if (j->d_coef) cudaFree(j->d_coef);
   if (j->d_pixels) cudaFree(j->d_pixels);
   if (j->d_samples) cudaFree(j->d_samples);
@@ -315,6 +328,7 @@ extern "C" int gidcuda_job_begin(gidcuda_ctx *ctx, const gidcuda_frame_desc *des
   j->set.build(std::vector<gidk::FrameItem>(1, it));
   j->h_coef_clean = false;  // zeroed when the decoder asks for the planes
   j->user_pixels = nullptr;
+  j->scan_active = false;
   for (int c = 0; c < 3; c++) {
     j->rows_hint[c] = 8;
     j->sparse[c] = false;
@@ -412,6 +426,83 @@ extern "C" int gidcuda_job_records_commit_runs(gidcuda_job *job, int comp, int32
   return GIDCUDA_OK;
 }
 
+// Canonical code of a DHT table (Read_DHT, :320-391) in the form the device decoder reads.
+static bool build_huff_dev(const gidcuda_huffman_table &t, gidk::HuffDev *d) {
+  memset(d, 0, sizeof *d);
+  int code = 0, k = 0;
+  for (int len = 1; len <= 16; len++) {
+    d->valoff[len] = k - code;
+    for (int i = 0; i < t.counts[len - 1]; i++, k++, code++) {
+      if (k > 255 || code >= (1 << len)) return false;  // more symbols than a table holds / over-subscribed
+      d->vals[k] = t.symbols[k];
+      if (len <= 10) {
+        const int first = code << (10 - len), n = 1 << (10 - len);
+        for (int j = 0; j < n; j++) d->lut[first + j] = (uint16_t)((len << 8) | t.symbols[k]);
+      }
+    }
+    d->maxcode[len] = t.counts[len - 1] ? code - 1 : -1;
+    code <<= 1;
+  }
+  return true;
+}
+
+extern "C" int gidcuda_job_scan(gidcuda_job *job, const gidcuda_scan_desc *scan, const uint8_t *data, size_t len,
+                                const uint32_t *begin, const uint32_t *end) {
+  if (!job) return fail(nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "null job");
+  gidcuda_ctx *ctx = job->ctx;
+  if (job->state != gidcuda_job::BEGUN)
+    return fail(ctx, GIDCUDA_ERR_STATE, "gidcuda_job_scan: only between gidcuda_job_begin and gidcuda_job_submit");
+  if (!scan || !data || !begin || !end || len == 0 || len > 0xFFFFFFF0u)
+    return fail(ctx, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_job_scan: null argument or no data");
+  const Geometry &g = job->geo;
+  const int64_t nmcu = (int64_t)g.mcux * g.mcuy;
+  if (scan->restart_interval <= 0 || scan->nintervals <= 0 ||
+      (nmcu + scan->restart_interval - 1) / scan->restart_interval != scan->nintervals)
+    return fail(ctx, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_job_scan: %d intervals of %d MCUs do not cover %lld MCUs",
+                (int)scan->nintervals, (int)scan->restart_interval, (long long)nmcu);
+  const size_t nint = (size_t)scan->nintervals;
+  for (size_t i = 0; i < nint; i++)
+    if (begin[i] > end[i] || end[i] > len)
+      return fail(ctx, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_job_scan: interval %zu = [%u, %u) outside the %zu bytes", i,
+                  begin[i], end[i], len);
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t off_begin = round_up(6 * sizeof(gidk::HuffDev), 256);
+  const size_t off_end = off_begin + round_up(nint * 4, 256);
+  const size_t off_data = off_end + round_up(nint * 4, 256);
+  const size_t total = off_data + round_up(len, 256);
+  if (job->cap_scan < total) {
+    if (job->h_scan) cudaFreeHost(job->h_scan);
+    if (job->d_scan) cudaFree(job->d_scan);
+    job->h_scan = job->d_scan = nullptr;
+    job->cap_scan = 0;
+    const size_t cap = total + total / 4;  // the next frame of a batch is rarely the same size
+    CU_TRY(ctx, cudaHostAlloc((void **)&job->h_scan, cap, cudaHostAllocDefault));
+    CU_TRY(ctx, cudaMalloc((void **)&job->d_scan, cap));
+    job->cap_scan = cap;
+  }
+  if (!job->h_status) {
+    CU_TRY(ctx, cudaHostAlloc((void **)&job->h_status, 8, cudaHostAllocDefault));
+    CU_TRY(ctx, cudaMalloc((void **)&job->d_status, 8));
+  }
+  gidk::HuffDev *tabs = reinterpret_cast<gidk::HuffDev *>(job->h_scan);
+  for (int c = 0; c < 3; c++) {
+    const bool used = c < g.ncomp;
+    if (!build_huff_dev(scan->dc[used ? c : 0], &tabs[c]) || !build_huff_dev(scan->ac[used ? c : 0], &tabs[3 + c]))
+      return fail(ctx, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_job_scan: Huffman table of component %d is not a prefix code", c);
+  }
+  memcpy(job->h_scan + off_begin, begin, nint * 4);
+  memcpy(job->h_scan + off_end, end, nint * 4);
+  memcpy(job->h_scan + off_data, data, len);
+  job->scan_off_begin = off_begin;
+  job->scan_off_end = off_end;
+  job->scan_off_data = off_data;
+  job->scan_bytes = total;
+  job->scan_ri = scan->restart_interval;
+  job->scan_nintervals = scan->nintervals;
+  job->scan_active = true;
+  return GIDCUDA_OK;
+}
+
 static bool is_pinned_host(const void *p) {
   cudaPointerAttributes at;
   if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
@@ -467,13 +558,42 @@ extern "C" int gidcuda_job_submit(gidcuda_job *job) {
   //   large, a pitched copy of the upper 64 bytes of every block (measured 1.5x faster than the
   //   full plane on this link; narrower or wider partial rows are not faster than a full copy,
   //   and below a few MiB the extra calls cost more than the bytes saved: measured on 1080p).
+  if (job->scan_active) {
+    // compressed bytes -> device, planes zeroed, one thread per restart interval decodes
+    CU_TRY(ctx, cudaMemcpyAsync(job->d_scan, job->h_scan, job->scan_bytes, cudaMemcpyHostToDevice, s));
+    CU_TRY(ctx, cudaMemsetAsync(job->d_coef, 0, g.coef_bytes, s));
+    CU_TRY(ctx, cudaMemsetAsync(job->d_status, 0, 8, s));
+    gidk::ScanArgs sa;
+    memset(&sa, 0, sizeof sa);
+    sa.data = job->d_scan + job->scan_off_data;
+    sa.begin = reinterpret_cast<const uint32_t *>(job->d_scan + job->scan_off_begin);
+    sa.end = reinterpret_cast<const uint32_t *>(job->d_scan + job->scan_off_end);
+    sa.tables = reinterpret_cast<const gidk::HuffDev *>(job->d_scan);
+    for (int c = 0; c < g.ncomp; c++) {
+      sa.plane[c] = reinterpret_cast<int16_t *>(job->d_coef + g.plane_off[c]);
+      sa.bx[c] = (uint32_t)g.bx[c];
+      sa.h[c] = job->desc.samp_h[c];
+      sa.v[c] = job->desc.samp_v[c];
+      job->d_tail_zero[c] = false;
+    }
+    sa.ncomp = g.ncomp;
+    sa.mcux = (uint32_t)g.mcux;
+    sa.nmcu = (uint32_t)g.mcux * (uint32_t)g.mcuy;
+    sa.ri = (uint32_t)job->scan_ri;
+    sa.nintervals = (uint32_t)job->scan_nintervals;
+    sa.status = job->d_status;
+    CU_TRY(ctx, gidk::launch_huffman_intervals(sa, s));
+    CU_TRY(ctx, cudaMemcpyAsync(job->h_status, job->d_status, 8, cudaMemcpyDeviceToHost, s));
+  }
   constexpr size_t kMinPitchedPlane = (size_t)8 << 20;
   bool any_sparse = false, all_dense_plain = true;
   for (int c = 0; c < g.ncomp; c++) {
     any_sparse = any_sparse || job->sparse[c];
     if (job->sparse[c] || (job->rows_hint[c] <= 4 && g.plane_bytes[c] >= kMinPitchedPlane)) all_dense_plain = false;
   }
-  if (!all_dense_plain || any_sparse) {
+  if (job->scan_active) {
+    any_sparse = false;  // every plane comes from the device decoder
+  } else if (!all_dense_plain || any_sparse) {
     for (int c = 0; c < g.ncomp; c++) {
       uint8_t *dp = job->d_coef + g.plane_off[c];
       if (job->sparse[c]) {
@@ -548,6 +668,15 @@ extern "C" int gidcuda_job_wait(gidcuda_job *job, const uint8_t **pixels, size_t
   if (job->state != gidcuda_job::SUBMITTED)
     return fail(ctx, GIDCUDA_ERR_STATE, "gidcuda_job_wait: job was not submitted");
   CU_TRY(ctx, cudaEventSynchronize(job->done));
+  if (job->scan_active) {
+    job->scan_active = false;  // a re-submission after a host decode takes planes / records
+    if (job->h_status[0] != 0) {
+      job->state = gidcuda_job::BEGUN;
+      return fail(ctx, GIDCUDA_ERR_DATA,
+                  "device entropy decoder: %u restart interval(s) left to the host decoder (damaged or unusual stream)",
+                  job->h_status[1]);
+    }
+  }
   if (pixels) *pixels = job->user_pixels ? job->user_pixels : job->h_pixels;
   if (stride) *stride = job->geo.stride;
   return GIDCUDA_OK;

@@ -59,6 +59,27 @@ struct ExpandArgs {
 cudaError_t launch_expand(const ExpandArgs &a, int ncomp, cudaStream_t stream);
 inline int launches_expand() { return 1; }
 
+// Baseline Huffman decoding on the device (entropy_kernel.cu): one thread per restart interval.
+struct HuffDev {        // one Huffman table as the device decoder reads it
+  uint16_t lut[1024];   // 10-bit prefix -> length << 8 | symbol; 0 = the code is longer than 10 bits
+  int32_t maxcode[17];  // [1 .. 16]: largest code of that length, -1 = none
+  int32_t valoff[17];   // index of the first symbol of that length - its smallest code
+  uint8_t vals[256];
+};
+static_assert(sizeof(HuffDev) == 2440, "HuffDev layout");
+struct ScanArgs {
+  const uint8_t *data;          // the scan's entropy-coded bytes
+  const uint32_t *begin, *end;  // [nintervals] byte offsets into data: interval i = [begin[i], end[i])
+  const HuffDev *tables;        // [6]: DC tables of components 0 .. 2, then their AC tables
+  int16_t *plane[3];            // zeroed dense planes (block-major, natural order)
+  uint32_t bx[3];
+  int32_t h[3], v[3];
+  int32_t ncomp;
+  uint32_t mcux, nmcu, ri, nintervals;
+  uint32_t *status;             // [0] flags (1 = an interval was left to the host), [1] how many
+};
+cudaError_t launch_huffman_intervals(const ScanArgs &a, cudaStream_t stream);
+
 // One-time kernel attribute set-up (dynamic shared memory opt-in).
 cudaError_t init_kernels();
 

@@ -98,6 +98,12 @@ struct Image_Descriptor {
   // (0 = one per hardware thread).  Scans without restart markers, and progressive scans,
   // stay serial.  The decoded coefficients are the same either way.
   int entropy_threads = 1;
+  // Baseline scans with restart intervals (at least 64 of them) are entropy-decoded ON THE DEVICE,
+  // one thread per interval (gidcuda_job_scan): only the compressed bytes cross the host link.
+  // Streams the device decoder declines (damaged or unusual ones) are decoded on the host as
+  // before, so results and error behaviour do not depend on this switch.
+  bool device_entropy = true;
+  size_t stream_pos_after_header = 0;  // where Load_Image_Contents starts reading
 };
 
 // gid.ads:64-67.  try_tga is accepted for signature compatibility and ignored.
@@ -143,6 +149,14 @@ void release(Reconstruction &r);
 // pixels land there directly (gidcuda_job_output) and gidcuda_job_wait returns that address.
 void *decode_and_submit(Image_Descriptor &image, void *ctx, const std::function<void(int)> &feedback,
                         uint8_t *out = nullptr, size_t out_capacity = 0);
+// gidcuda_job_wait for a job of decode_and_submit.  When the device entropy decoder left the scan
+// to the host (GIDCUDA_ERR_DATA), the image is decoded again on the host cores into a new job
+// (*job is replaced) and that one is waited for.  Raises GID's exceptions.
+const uint8_t *wait_pixels(Image_Descriptor &image, void *ctx, void **job, size_t *stride, uint8_t *out = nullptr,
+                           size_t out_capacity = 0);
+
+// statistics (process-wide): scans decoded on the device / handed back to the host by it
+extern std::atomic<long> device_scans, device_scan_fallbacks;
 
 // Entropy decode only, into calloc'd planes (see gidhost_decode_planes).
 void decode_planes(Image_Descriptor &image, struct ::gidcuda_frame_desc *desc, int16_t *planes[3], int32_t blocks_x[3],

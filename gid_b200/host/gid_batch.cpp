@@ -19,6 +19,7 @@
 // spare threads go to the restart-interval-parallel scan of each file
 // (Image_Descriptor::entropy_threads).
 #include <chrono>
+#include <memory>
 #include <mutex>
 
 #pragma GCC diagnostic ignored "-Wunused-function"  // the header's readers that only gid_jpeg_host.cpp uses
@@ -37,6 +38,7 @@ typedef struct gidhost_batch_stats {
 } gidhost_batch_stats;
 
 int gidhost_status_of_current_exception(char *err, size_t errlen);  // gid_jpeg_host.cpp
+int gidhost_option_device_entropy(void);
 
 // The workers' device contexts outlive a call: their pinned and device buffers are recycled
 // from one batch to the next (gidcuda_job_release returns them to the context's pool).
@@ -100,7 +102,14 @@ int gidhost_batch_decode(gidhost_batch *b, int32_t n, const uint8_t *const *data
       }
       return;
     }
-    struct InFlight { gidcuda_job *job = nullptr; int32_t index = -1; int w = 0, h = 0; } pending;
+    // a frame in flight keeps its descriptor: should the device entropy decoder hand the scan
+    // back, the image is decoded again on this thread (wait_pixels)
+    struct InFlight {
+      void *job = nullptr;
+      int32_t index = -1;
+      std::unique_ptr<gid::Stream> st;
+      std::unique_ptr<gid::Image_Descriptor> im;
+    } pending;
     double mp = 0.0;
     auto fail = [&](int32_t i) {
       char msg[256];
@@ -111,24 +120,23 @@ int gidhost_batch_decode(gidhost_batch *b, int32_t n, const uint8_t *const *data
     auto finish = [&](InFlight &f) {
       if (!f.job) return;
       try {
-        const uint8_t *px = nullptr;
         size_t stride = 0;
-        const int st = gidcuda_job_wait(f.job, &px, &stride);
-        if (st != GIDCUDA_OK) gid::raise_from_status(st, ctx);
-        const size_t row = (size_t)3 * (size_t)f.w;
         uint8_t *out = rgb[f.index];
+        const uint8_t *px = gid::detail::wait_pixels(*f.im, ctx, &f.job, &stride, out, rgb_capacity[f.index]);
+        const int fw = f.im->width, fh = f.im->height;
+        const size_t row = (size_t)3 * (size_t)fw;
         if (px == out) {
           // the caller's buffer is pinned: the pixels arrived there straight from the device
-        } else if (stride == row) memcpy(out, px, row * (size_t)f.h);
+        } else if (stride == row) memcpy(out, px, row * (size_t)fh);
         else
-          for (int y = 0; y < f.h; y++) memcpy(out + (size_t)y * row, px + (size_t)y * stride, row);
-        mp += (double)f.w * f.h / 1e6;
+          for (int y = 0; y < fh; y++) memcpy(out + (size_t)y * row, px + (size_t)y * stride, row);
+        mp += (double)fw * fh / 1e6;
         bytes += (int64_t)len[f.index];
         if (status) status[f.index] = 0;
       } catch (...) {
         fail(f.index);
       }
-      gidcuda_job_release(f.job);
+      if (f.job) gidcuda_job_release(static_cast<gidcuda_job *>(f.job));
       f.job = nullptr;
     };
     const std::function<void(int)> no_feedback = [](int) {};
@@ -137,23 +145,23 @@ int gidhost_batch_decode(gidhost_batch *b, int32_t n, const uint8_t *const *data
       if (i >= n) break;
       InFlight cur;
       try {
-        gid::Stream st(data[i], len[i]);
-        gid::Image_Descriptor im;
-        gid::Load_Image_Header(im, st);
+        cur.st.reset(new gid::Stream(data[i], len[i]));
+        cur.im.reset(new gid::Image_Descriptor);
+        gid::Image_Descriptor &im = *cur.im;
+        gid::Load_Image_Header(im, *cur.st);
         im.device = dev;
         im.entropy_threads = per_image;
+        im.device_entropy = gidhost_option_device_entropy() != 0;
         if ((size_t)3 * (size_t)im.width * (size_t)im.height > rgb_capacity[i])
           throw gid::gid_error("output buffer too small");
-        cur.job = static_cast<gidcuda_job *>(gid::detail::decode_and_submit(im, ctx, no_feedback, rgb[i], rgb_capacity[i]));
         cur.index = i;
-        cur.w = im.width;
-        cur.h = im.height;
+        cur.job = gid::detail::decode_and_submit(im, ctx, no_feedback, rgb[i], rgb_capacity[i]);
       } catch (...) {
         fail(i);
         continue;
       }
       finish(pending);  // the frame before this one: done by now, or nearly
-      pending = cur;
+      pending = std::move(cur);
     }
     finish(pending);
     std::lock_guard<std::mutex> g(mu);

@@ -49,11 +49,12 @@ void Load_Image_Header(Image_Descriptor &image, Stream &from, bool /*try_tga*/) 
     else if (sg.marker == M_APP1) read_exif(image, r, sg.length);
     else r.skip(sg.length);
   }
+  image.stream_pos_after_header = from.pos;
 }
 
 namespace detail {
 
-std::atomic<long> parallel_scans{0}, parallel_fallbacks{0};
+std::atomic<long> parallel_scans{0}, parallel_fallbacks{0}, device_scans{0}, device_scan_fallbacks{0};
 
 // Frame descriptor from the header: geometry now, tables when the first scan starts.
 static void describe_frame(const Image_Descriptor &image, gidcuda_frame_desc *desc, int comp_of[3]) {
@@ -174,8 +175,11 @@ void *decode_and_submit(Image_Descriptor &image, void *ctx_, const std::function
   try {
     dec.begin_frame = [&]() {
       fill_tables(image, &desc, comp_of);
-      int st = gidcuda_job_begin(ctx, &desc, &job);
+      const int st = gidcuda_job_begin(ctx, &desc, &job);
       if (st != GIDCUDA_OK) raise_from_status(st, ctx);
+    };
+    dec.prepare_host_output = [&]() {
+      int st;
       for (int c = 0; c < 3; c++) {
         if (!image.info[c].present) continue;
         if (!sparse) {
@@ -200,6 +204,27 @@ void *decode_and_submit(Image_Descriptor &image, void *ctx_, const std::function
         }
       }
     };
+    if (image.device_entropy && !image.progressive)
+      dec.device_scan = [&](const Decoder::DeviceScan &ds) {
+        gidcuda_scan_desc sd;
+        memset(&sd, 0, sizeof sd);
+        sd.restart_interval = ds.restart_interval;
+        sd.nintervals = (int32_t)ds.begin.size();
+        for (int c = 0; c < 3; c++) {
+          if (!image.info[c].present) continue;
+          gidcuda_huffman_table *t[2] = {&sd.dc[comp_of[c]], &sd.ac[comp_of[c]]};
+          const std::vector<uint8_t> *bits[2] = {ds.dc_bits[c], ds.ac_bits[c]}, *vals[2] = {ds.dc_vals[c], ds.ac_vals[c]};
+          for (int k = 0; k < 2; k++) {
+            if (bits[k]->size() != 16 || vals[k]->size() > 256) return false;
+            memcpy(t[k]->counts, bits[k]->data(), 16);
+            memcpy(t[k]->symbols, vals[k]->data(), vals[k]->size());
+          }
+        }
+        // (a table the device cannot take, e.g. an over-subscribed one, is a case for the host loop)
+        if (gidcuda_job_scan(job, &sd, ds.data, ds.len, ds.begin.data(), ds.end.data()) != GIDCUDA_OK) return false;
+        device_scans++;
+        return true;
+      };
     // A baseline component outgrew its record buffer (more than 32 non-zero coefficients per
     // block on average): replay its records into the dense plane and carry on there.
     dec.spill = [&](int c) {
@@ -223,7 +248,7 @@ void *decode_and_submit(Image_Descriptor &image, void *ctx_, const std::function
     dec.run();
     if (!job) throw error_in_image_data("JPEG: no scan in the image");
     for (int c = 0; c < 3; c++) {
-      if (!image.info[c].present) continue;
+      if (!image.info[c].present || dec.device_scanned) continue;
       RecordSink &k = dec.sink[c];
       if (sparse && image.progressive) {
         uint32_t *first = nullptr, *rec = nullptr;
@@ -268,6 +293,34 @@ void *decode_and_submit(Image_Descriptor &image, void *ctx_, const std::function
   }
 }
 
+const uint8_t *wait_pixels(Image_Descriptor &image, void *ctx_, void **job, size_t *stride, uint8_t *out,
+                           size_t out_capacity) {
+  gidcuda_ctx *ctx = static_cast<gidcuda_ctx *>(ctx_);
+  const uint8_t *px = nullptr;
+  int rc = gidcuda_job_wait(static_cast<gidcuda_job *>(*job), &px, stride);
+  if (rc == GIDCUDA_ERR_DATA) {
+    // the device entropy decoder met something unusual: the host decoder takes the image, and
+    // with it the reference's behaviour on damaged streams
+    device_scan_fallbacks++;
+    gidcuda_job_release(static_cast<gidcuda_job *>(*job));
+    *job = nullptr;
+    image.stream->pos = image.stream_pos_after_header;
+    const bool keep = image.device_entropy;
+    image.device_entropy = false;
+    const std::function<void(int)> no_feedback = [](int) {};
+    try {
+      *job = decode_and_submit(image, ctx, no_feedback, out, out_capacity);
+    } catch (...) {
+      image.device_entropy = keep;
+      throw;
+    }
+    image.device_entropy = keep;
+    rc = gidcuda_job_wait(static_cast<gidcuda_job *>(*job), &px, stride);
+  }
+  if (rc != GIDCUDA_OK) raise_from_status(rc, ctx);
+  return px;
+}
+
 Reconstruction decode_and_reconstruct(Image_Descriptor &image, const std::function<void(int)> &feedback) {
   gidcuda_ctx *ctx = nullptr;
   int rc = gidcuda_create(image.device, &ctx);
@@ -276,8 +329,14 @@ Reconstruction decode_and_reconstruct(Image_Descriptor &image, const std::functi
   try {
     job = static_cast<gidcuda_job *>(decode_and_submit(image, ctx, feedback));
     Reconstruction rec;
-    rc = gidcuda_job_wait(job, &rec.pixels, &rec.stride);
-    if (rc != GIDCUDA_OK) raise_from_status(rc, ctx);
+    void *j = job;
+    try {
+      rec.pixels = wait_pixels(image, ctx, &j, &rec.stride);
+    } catch (...) {
+      job = static_cast<gidcuda_job *>(j);
+      throw;
+    }
+    job = static_cast<gidcuda_job *>(j);
     rec.job = job;
     rec.ctx = ctx;
     return rec;
@@ -359,11 +418,17 @@ int gidhost_probe(const uint8_t *data, size_t len, int32_t *width, int32_t *heig
 // the device as records, 0 = as dense planes (Image_Descriptor::sparse_input).
 //   "entropy_threads" host threads for the entropy decode of one image (Image_Descriptor::entropy_threads;
 //   default 1, 0 = one per hardware thread).
+//   "device_entropy" 1 (default) = baseline scans with restart intervals are entropy-decoded on the device
 static int g_sparse_input = 1;
 static int g_entropy_threads = 1;
+static int g_device_entropy = 1;
 int gidhost_set_option(const char *name, int value) {
   if (name && strcmp(name, "sparse_input") == 0) {
     g_sparse_input = value != 0;
+    return GIDHOST_OK;
+  }
+  if (name && strcmp(name, "device_entropy") == 0) {
+    g_device_entropy = value != 0;
     return GIDHOST_OK;
   }
   if (name && strcmp(name, "entropy_threads") == 0 && value >= 0) {
@@ -383,6 +448,7 @@ int gidhost_decode_rgb(const uint8_t *data, size_t len, int device, uint32_t mod
     im.device = device;
     im.sparse_input = g_sparse_input != 0;
     im.entropy_threads = g_entropy_threads;
+    im.device_entropy = g_device_entropy != 0;
     const int W = gid::Pixel_Width(im), H = gid::Pixel_Height(im);
     if ((size_t)3 * (size_t)W * (size_t)H > rgb_capacity) {
       if (err && errlen) snprintf(err, errlen, "output buffer too small");
@@ -440,12 +506,15 @@ void gidhost_free(void *p) { free(p); }
 
 // (for gid_batch.cpp) status code + message of the exception being handled
 int gidhost_status_of_current_exception(char *err, size_t errlen) { return status_of_exception(err, errlen); }
+int gidhost_option_device_entropy(void) { return g_device_entropy; }
 
 // Process-wide counters: "parallel_scans" (baseline scans decoded restart-interval-parallel),
 // "parallel_fallbacks" (parallel attempts that handed the scan back to the serial loop).
 long gidhost_counter(const char *name) {
   if (name && strcmp(name, "parallel_scans") == 0) return gid::detail::parallel_scans.load();
   if (name && strcmp(name, "parallel_fallbacks") == 0) return gid::detail::parallel_fallbacks.load();
+  if (name && strcmp(name, "device_scans") == 0) return gid::detail::device_scans.load();
+  if (name && strcmp(name, "device_scan_fallbacks") == 0) return gid::detail::device_scan_fallbacks.load();
   return -1;
 }
 

@@ -442,6 +442,15 @@ struct Decoder {
   BitReader bits;
   const std::function<void(int)> &feedback;
   std::function<void()> begin_frame;  // called at the first SOS: tables and geometry are final (:1857)
+  // called once before the first coefficient is stored on the HOST (planes / record sinks are set
+  // up here rather than in begin_frame, so that a scan decoded on the device never reserves them)
+  std::function<void()> prepare_host_output;
+  bool host_output_ready = false;
+  void ensure_host_output() {
+    if (host_output_ready) return;
+    host_output_ready = true;
+    if (prepare_host_output) prepare_host_output();
+  }
   HuffTable huff[2][8];
   PlaneRef plane[3];
   RecordSink sink[3];                 // baseline: components emitted as records while sink[c].on
@@ -580,6 +589,84 @@ struct Decoder {
   std::vector<Run> runs;  // one per worker after a successful parallel scan, else empty
   int parallel_threads = 1;
 
+  // Where the restart intervals of the scan at r.s.pos begin and end: interval k runs from the
+  // byte after RSTk-1 to the FF of RSTk (the last one to the marker that ends the scan, or to the
+  // end of the data).  False unless the markers are exactly the nseg - 1 the geometry needs,
+  // numbered in sequence.
+  bool find_intervals(long nseg, std::vector<size_t> &seg_begin, std::vector<size_t> &seg_end) const {
+    const uint8_t *d = r.s.data;
+    const size_t size = r.s.size;
+    seg_begin.assign((size_t)nseg, 0);
+    seg_end.assign((size_t)nseg, 0);
+    size_t i = r.s.pos;
+    long k = 0;
+    seg_begin[0] = i;
+    for (;;) {
+      const void *f = i < size ? memchr(d + i, 0xFF, size - i) : nullptr;
+      if (!f) { seg_end[(size_t)k] = size; break; }
+      i = (size_t)((const uint8_t *)f - d);
+      const uint8_t m = i + 1 < size ? d[i + 1] : (uint8_t)M_EOI;
+      if (m == 0) { i += 2; continue; }
+      seg_end[(size_t)k] = i;
+      if (m >= M_RST0 && m <= M_RST7) {
+        if (m != (uint8_t)(M_RST0 + (k & 7)) || k + 1 >= nseg) return false;
+        seg_begin[(size_t)++k] = i + 2;
+        i += 2;
+        continue;
+      }
+      break;  // the marker that ends the scan (or one the serial decoder will complain about)
+    }
+    return k == nseg - 1;
+  }
+
+  // ---- the scan handed to the device as compressed bytes (gidcuda_job_scan) -----------------------
+  // Set by the caller that owns the job; returns false when the device path does not apply.
+  struct DeviceScan {
+    const uint8_t *data;
+    size_t len;
+    std::vector<uint32_t> begin, end;  // relative to data
+    int restart_interval;
+    const std::vector<uint8_t> *dc_bits[3], *dc_vals[3], *ac_bits[3], *ac_vals[3];
+  };
+  std::function<bool(const DeviceScan &)> device_scan;
+  bool device_scanned = false;
+
+  bool device_baseline_scan() {
+    const int ri = im.restart_interval;
+    const long nmcu = (long)mcu_count_image_h * mcu_count_image_v;
+    if (!device_scan || ri <= 0) return false;
+    const long nseg = (nmcu + ri - 1) / ri;
+    if (nseg < 64) return false;  // too few independent streams to occupy a GPU
+    std::vector<size_t> seg_begin, seg_end;
+    if (!find_intervals(nseg, seg_begin, seg_end)) return false;
+    DeviceScan ds;
+    const size_t base = seg_begin[0];
+    ds.data = r.s.data + base;
+    ds.len = seg_end[(size_t)nseg - 1] - base;
+    if (ds.len == 0 || ds.len > 0xFFFFFFF0u) return false;
+    ds.begin.resize((size_t)nseg);
+    ds.end.resize((size_t)nseg);
+    for (long k = 0; k < nseg; k++) {
+      ds.begin[(size_t)k] = (uint32_t)(seg_begin[(size_t)k] - base);
+      ds.end[(size_t)k] = (uint32_t)(seg_end[(size_t)k] - base);
+    }
+    ds.restart_interval = ri;
+    for (int c = 0; c < 3; c++) {
+      ds.dc_bits[c] = ds.dc_vals[c] = ds.ac_bits[c] = ds.ac_vals[c] = nullptr;
+      if (!im.info[c].present) continue;
+      table(0, ht_dc[c]);  // raises like the serial loop when a table is missing
+      table(1, ht_ac[c]);
+      ds.dc_bits[c] = &im.huff_bits[0][ht_dc[c]];
+      ds.dc_vals[c] = &im.huff_vals[0][ht_dc[c]];
+      ds.ac_bits[c] = &im.huff_bits[1][ht_ac[c]];
+      ds.ac_vals[c] = &im.huff_vals[1][ht_ac[c]];
+    }
+    if (!device_scan(ds)) return false;
+    device_scanned = true;
+    emit_feedback(50);
+    return true;
+  }
+
   bool parallel_baseline_scan() {
     const int ri = im.restart_interval;
     const long nmcu = (long)mcu_count_image_h * mcu_count_image_v;
@@ -587,31 +674,9 @@ struct Decoder {
     const long nseg = (nmcu + ri - 1) / ri;
     const int T = (int)std::min<long>(parallel_threads, nseg / 4);
     if (T < 2) return false;
-    // -- where the intervals begin and end
+    std::vector<size_t> seg_begin, seg_end;
+    if (!find_intervals(nseg, seg_begin, seg_end)) return false;
     const uint8_t *d = r.s.data;
-    const size_t size = r.s.size;
-    std::vector<size_t> seg_begin((size_t)nseg), seg_end((size_t)nseg);
-    {
-      size_t i = r.s.pos;
-      long k = 0;
-      seg_begin[0] = i;
-      for (;;) {
-        const void *f = i < size ? memchr(d + i, 0xFF, size - i) : nullptr;
-        if (!f) { seg_end[(size_t)k] = size; break; }
-        i = (size_t)((const uint8_t *)f - d);
-        const uint8_t m = i + 1 < size ? d[i + 1] : (uint8_t)M_EOI;
-        if (m == 0) { i += 2; continue; }
-        seg_end[(size_t)k] = i;
-        if (m >= M_RST0 && m <= M_RST7) {
-          if (m != (uint8_t)(M_RST0 + (k & 7)) || k + 1 >= nseg) return false;
-          seg_begin[(size_t)++k] = i + 2;
-          i += 2;
-          continue;
-        }
-        break;  // the marker that ends the scan (or one the serial decoder will complain about)
-      }
-      if (k != nseg - 1) return false;
-    }
     // -- workers
     int ncomp_blocks[3] = {0, 0, 0};
     const HuffTable *tdc[3] = {nullptr, nullptr, nullptr}, *tac[3] = {nullptr, nullptr, nullptr};
@@ -710,6 +775,8 @@ struct Decoder {
 
   void baseline_scan() {  // :1179-1220; loops over FRAME components like the reference (:1190-1191)
     const int mh = mcu_count_image_h, mv = mcu_count_image_v;
+    if (device_baseline_scan()) return;
+    ensure_host_output();
     if (parallel_baseline_scan()) return;
     rst_count = im.restart_interval;
     next_rst = 0;
@@ -824,6 +891,7 @@ struct Decoder {
     if (ss > se || se > 63) throw error_in_image_data("JPEG: progressive: bad spectral selection");
     if (ss == 0 && se != 0) throw error_in_image_data("JPEG: progressive: DC and AC in the same scan");
     if (ss > 0 && ncomps != 1) throw error_in_image_data("JPEG: progressive: AC scan with several components");
+    ensure_host_output();
     rst_count = im.restart_interval;
     next_rst = 0;
     eobrun = 0;

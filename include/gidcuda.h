@@ -45,7 +45,9 @@ enum {
   GIDCUDA_ERR_NO_DEVICE = -3,
   GIDCUDA_ERR_CUDA = -4,        /* a CUDA runtime call failed */
   GIDCUDA_ERR_OUT_OF_MEMORY = -5,
-  GIDCUDA_ERR_STATE = -6        /* call sequence violated (e.g. wait before submit) */
+  GIDCUDA_ERR_STATE = -6,       /* call sequence violated (e.g. wait before submit) */
+  GIDCUDA_ERR_DATA = -7         /* gidcuda_job_scan: the device entropy decoder met something it leaves to the
+                                   host decoder (which then reproduces the reference's behaviour, error or not) */
 };
 
 /* Output pixel formats (flags, low byte).  RGB8 top-down is what
@@ -152,6 +154,37 @@ int gidcuda_job_records_commit(gidcuda_job *job, int comp, size_t count);
  * library copies every run to its place in that concatenation: no host-side compaction pass. */
 int gidcuda_job_records_commit_runs(gidcuda_job *job, int comp, int32_t nruns, const size_t *run_begin,
                                     const size_t *run_count);
+/* ---- entropy decoding on the device (optional; baseline scans with restart intervals) ------
+ * The step BEFORE the path.  After RSTn the predictors are reset and the bit buffer is
+ * byte-aligned (Check_Restart, gid-decoding_jpg.adb:1133-1177): the restart intervals of a baseline
+ * scan are independent bit streams.  Instead of decoding them (Decode_8x8_Block, :758-788) and
+ * handing over planes or records, the host may hand over the scan's COMPRESSED bytes and where
+ * each interval lies; one device thread per interval decodes them into the job's planes, and the
+ * reconstruction follows in the same submit.  Only a few hundredths of a byte per pixel cross the
+ * host link.
+ *   data, len          the entropy-coded bytes of the scan (copied by the call)
+ *   begin[i], end[i]   interval i = data[begin[i] .. end[i]): from the byte after RSTn-1 (or the
+ *                      first byte of the scan) to the FF of the next marker; inside an interval every
+ *                      FF is followed by 00 (byte stuffing, :640-662)
+ *   scan               restart interval in MCUs, and per component the Huffman tables of the scan
+ *                      (Read_DHT :320-391: 16 counts, then the symbols in code order)
+ * The MCU order, block order and predictor handling are those of Baseline_DCT_Decoding_Scan
+ * (:1179-1220).  The device decoder does not reproduce the reference's handling of damaged streams:
+ * when an interval holds a code that is in no table, a run past coefficient 63, too few or too many
+ * bytes, gidcuda_job_wait returns GIDCUDA_ERR_DATA and the pixels are undefined; the caller then
+ * decodes the scan on the host (planes or records) and submits the same job again. */
+typedef struct gidcuda_huffman_table {
+  uint8_t counts[16];   /* codes of length 1 .. 16 */
+  uint8_t symbols[256]; /* in code order */
+} gidcuda_huffman_table;
+typedef struct gidcuda_scan_desc {
+  int32_t restart_interval;        /* MCUs per interval (DRI, :424-434), > 0 */
+  int32_t nintervals;              /* ceil(MCUs of the frame / restart_interval) */
+  gidcuda_huffman_table dc[3], ac[3]; /* per component of the frame */
+} gidcuda_scan_desc;
+int gidcuda_job_scan(gidcuda_job *job, const gidcuda_scan_desc *scan, const uint8_t *data, size_t len,
+                     const uint32_t *begin, const uint32_t *end);
+
 /* Optional: let the pixels land in the CALLER's buffer instead of one owned by the job -- the
  * image buffer a client fills through Put_Pixel (test/benchmark.adb:67-81) handed over whole, so
  * that no copy follows the device-to-host transfer.  host_pixels must be pinned host memory

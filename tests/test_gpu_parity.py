@@ -375,3 +375,33 @@ def test_sparse_records_random_and_limits(gpu, oracle, synth):
     assert L.gidcuda_job_release(job) == 0
     with pytest.raises(ValueError):             # wrong number of blocks for the frame
         gpu.reconstruct_rgb(frame_desc(fr), [p[:1]], sparse=True)
+
+
+def test_job_scan_argument_checks(gpu, synth):
+    """gidcuda_job_scan validates its geometry, offsets and tables (no decode launched)."""
+    import ctypes
+    from gid_b200 import capi
+    L = gpu.lib
+    fr = synth.planes_only(synth.image(1, 64, 64)[:, :, 1].copy(), "grey")
+    desc = frame_desc(fr)
+    job = ctypes.c_void_p()
+    assert L.gidcuda_job_begin(gpu.ctx, ctypes.byref(desc), ctypes.byref(job)) == 0
+    scan = capi.ScanDesc()
+    scan.restart_interval, scan.nintervals = 8, 8   # 64 MCUs
+    data = (ctypes.c_uint8 * 16)()
+    b = (ctypes.c_uint32 * 8)(*range(8))
+    e = (ctypes.c_uint32 * 8)(*range(1, 9))
+    scan.nintervals = 7
+    assert L.gidcuda_job_scan(job, ctypes.byref(scan), data, 16, b, e) == -1      # intervals do not cover the frame
+    scan.nintervals = 8
+    e[3] = 99
+    assert L.gidcuda_job_scan(job, ctypes.byref(scan), data, 16, b, e) == -1      # offset outside the data
+    e[3] = 4
+    scan.dc[0].counts[0] = 3                                                      # three 1-bit codes: not a prefix code
+    assert L.gidcuda_job_scan(job, ctypes.byref(scan), data, 16, b, e) == -1
+    scan.dc[0].counts[0] = 0
+    assert L.gidcuda_job_scan(job, ctypes.byref(scan), data, 16, b, e) == 0       # empty tables are a valid (useless) code
+    assert L.gidcuda_job_submit(job) == 0
+    pix, st = ctypes.c_void_p(), ctypes.c_size_t()
+    assert L.gidcuda_job_wait(job, ctypes.byref(pix), ctypes.byref(st)) == -7     # no code matches: left to the host
+    assert L.gidcuda_job_release(job) == 0

@@ -284,8 +284,12 @@ def test_restart_parallel_scan_through_the_device(host, oracle, synth, gpu, coef
     jpg, _ = synth.encode(pixels_for(synth, 6, w, h, samp), samp, restart_interval=ri)
     _, ref, _ = oracle.decode(jpg)
     entropy_threads(threads)
+    host.set_option("device_entropy", 0)  # this test is about the HOST threads
     before = host.counter("parallel_scans")
-    rgb, fb = host.decode_rgb(jpg)
+    try:
+        rgb, fb = host.decode_rgb(jpg)
+    finally:
+        host.set_option("device_entropy", 1)
     assert host.counter("parallel_scans") == before + 1
     assert np.array_equal(rgb, ref)
     assert fb == sorted(fb) and fb[-1] == 100
@@ -325,10 +329,19 @@ def test_file_batch_matches_gid(host, oracle, synth, gpu):
             assert abs(stats.megapixels - sum(r.shape[0] * r.shape[1] for r in refs if r is not None) / 1e6) < 1e-6
     # fewer files than threads: the spare threads go into the restart-interval-parallel scan
     big = synth.encode(pixels_for(synth, 31, 2048, 1024, "grey"), "grey", restart_interval=64)[0]
-    before = host.counter("parallel_scans")
-    imgs, st, stats = host.decode_batch([big], threads=8)
+    host.set_option("device_entropy", 0)
+    try:
+        before = host.counter("parallel_scans")
+        imgs, st, stats = host.decode_batch([big], threads=8)
+    finally:
+        host.set_option("device_entropy", 1)
     assert st == [0] and stats.entropy_threads == 8 and host.counter("parallel_scans") == before + 1
     assert np.array_equal(imgs[0], oracle.decode(big)[1])
+    # ... or, by default, the scan is entropy-decoded on the device
+    before = host.counter("device_scans")
+    imgs, st, stats = host.decode_batch([big, big], threads=2)
+    assert st == [0, 0] and host.counter("device_scans") == before + 2
+    assert np.array_equal(imgs[0], oracle.decode(big)[1]) and np.array_equal(imgs[1], imgs[0])
 
 
 @pytest.mark.gpu
@@ -368,3 +381,79 @@ def test_pixels_land_in_the_callers_pinned_buffer(host, oracle, synth, gpu):
         assert st == [0, 0] and np.array_equal(imgs[0], ref) and np.array_equal(imgs[1], ref)
     finally:
         capi.pinned_free(addr)
+
+
+# --------------------------------------------------------------------------- entropy decode on the device
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("samp,w,h,ri", [
+    ("grey", 1024, 520, 4), ("420", 1030, 810, 3), ("444", 640, 520, 16), ("422", 1000, 600, 64), ("440", 333, 700, 2),
+    ("411", 1024, 256, 1), ("grey", 520, 8 * 300 + 3, 1), ("420", 16 * 90 + 5, 16 * 30 + 9, 11),
+])
+def test_device_entropy_decode_matches_gid(host, oracle, synth, gpu, samp, w, h, ri):
+    """SURVEY.md 8f rank 1, second half: the restart intervals of a baseline scan Huffman-decoded
+    by one device thread each (gidcuda_job_scan) -- only the compressed bytes cross the link --
+    then reconstructed: pixels == GID's decode of the file."""
+    jpg, _ = synth.encode(pixels_for(synth, 8, w, h, samp), samp, restart_interval=ri)
+    _, ref, _ = oracle.decode(jpg)
+    scans, back = host.counter("device_scans"), host.counter("device_scan_fallbacks")
+    rgb, fb = host.decode_rgb(jpg)
+    assert host.counter("device_scans") == scans + 1 and host.counter("device_scan_fallbacks") == back
+    assert np.array_equal(rgb, ref)
+    assert fb == sorted(fb) and fb[-1] == 100
+
+
+@pytest.mark.gpu
+def test_device_entropy_decode_optimised_tables_and_dense_data(host, oracle, synth, gpu):
+    """Per-image optimised Huffman tables (codes up to 16 bits: the canonical search behind the
+    10-bit table) and quality-100 noise (long runs of large values)."""
+    rng = np.random.default_rng(5)
+    pix = rng.integers(0, 256, size=(256, 512, 3), dtype=np.uint8)
+    for quality, optimize in ((100, True), (100, False), (30, True)):
+        jpg, _ = synth.encode(pix, "420", quality=quality, restart_interval=1, optimize=optimize)
+        scans = host.counter("device_scans")
+        rgb, _ = host.decode_rgb(jpg)
+        assert host.counter("device_scans") == scans + 1
+        assert np.array_equal(rgb, oracle.decode(jpg)[1])
+
+
+@pytest.mark.gpu
+def test_device_entropy_decode_leaves_damaged_streams_to_the_host(host, oracle, synth, gpu):
+    """Whatever the host decoder does with a damaged stream (GID's behaviour, checked against the
+    oracle on the CPU side), the device path does too: it declines and the host decodes."""
+    rng = np.random.default_rng(21)
+    declined = 0
+    for samp, w, h, ri in (("grey", 1024, 512, 4), ("420", 1024, 800, 3)):
+        jpg, _ = synth.encode(pixels_for(synth, 3, w, h, samp), samp, restart_interval=ri)
+        sos = jpg.index(b"\xff\xda")
+        for t in range(12):
+            bad = bytearray(jpg)
+            pos = int(rng.integers(sos + 14, len(bad) - 2))
+            if t % 3 == 0:
+                bad[pos] = int(rng.integers(0, 256))
+            elif t % 3 == 1:
+                del bad[pos]
+            else:
+                bad.insert(pos, int(rng.integers(1, 255)))
+            bad = bytes(bad)
+
+            def outcome():
+                try:
+                    return ("ok", hashlib.sha256(host.decode_rgb(bad)[0].tobytes()).hexdigest())
+                except host.GidHostError as e:
+                    return ("err", e.name)
+            host.set_option("device_entropy", 0)
+            try:
+                want = outcome()
+            finally:
+                host.set_option("device_entropy", 1)
+            back = host.counter("device_scan_fallbacks")
+            assert outcome() == want, (samp, t)
+            declined += host.counter("device_scan_fallbacks") - back
+            try:
+                ref = ("ok", hashlib.sha256(oracle.decode(bad)[1].tobytes()).hexdigest())
+            except Exception:
+                ref = ("err", None)
+            assert want[0] == ref[0] and (want[0] == "err" or want[1] == ref[1]), (samp, t)
+    assert declined > 0
