@@ -125,7 +125,7 @@ def files_leg_ours(workload: str, device: int, threads: int, reps: int, pinned: 
             "jpeg_bytes_per_image": len(distinct[0]), "progressive": prog, "restart_interval": ri,
             "output": "pinned client buffers (no host copy)" if pinned else "pageable client buffers (one host copy)",
             "api": "gidhost_batch_decode: .jpg bytes -> Huffman decode on host threads -> coefficient records -> "
-                   "B200 reconstruction -> top-down RGB8 in host memory, two frames in flight per thread"}
+                   "B200 reconstruction -> top-down RGB8 in host memory, three frames in flight per thread"}
 
 
 def files_leg_reference(workload: str, threads: int, seconds_target: float) -> dict:

@@ -124,14 +124,15 @@ __global__ void __launch_bounds__(128) huffman_intervals_kernel(ScanArgs a) {
   b.buf = 0;
   b.len = 0;
   b.pad = 0;
-  int pred[3] = {0, 0, 0};
+  int pred[3] = {0, 0, 0};  // (registers: only indexed by the unrolled component loop)
   const uint32_t m0 = it * a.ri;
   const uint32_t m1 = min(m0 + a.ri, a.nmcu);
   bool ok = true;
   for (uint32_t m = m0; m < m1 && ok; m++) {
     const uint32_t my = m / a.mcux, mx = m - my * a.mcux;
-    for (int c = 0; c < a.ncomp && ok; c++)
-      for (int sy = 0; sy < a.v[c] && ok; sy++)
+#pragma unroll
+    for (int c = 0; c < 3; c++)  // (unrolled: a run-time index into the kernel parameters would put them in local memory)
+      for (int sy = 0; c < a.ncomp && sy < a.v[c] && ok; sy++)
         for (int sx = 0; sx < a.h[c] && ok; sx++) {
           int16_t *blk = a.plane[c] + ((size_t)(my * a.v[c] + sy) * a.bx[c] + (mx * a.h[c] + sx)) * 64;
           ok = decode_block(b, tabs[c], tabs[3 + c], pred[c], blk, zz);
@@ -155,6 +156,328 @@ __global__ void __launch_bounds__(128) huffman_intervals_kernel(ScanArgs a) {
 cudaError_t launch_huffman_intervals(const ScanArgs &a, cudaStream_t stream) {
   if (a.nintervals == 0) return cudaSuccess;
   huffman_intervals_kernel<<<(a.nintervals + 127) / 128, 128, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+
+// =================================================================================================
+// Baseline scans WITHOUT restart markers: self-synchronising parallel Huffman decoding.
+//
+// A scan without RSTn is one long bit stream, but Huffman codes re-synchronise: a decoder started
+// at a wrong bit position or in a wrong state falls into step with the true code-word sequence
+// after a few code words.  (Klein & Wiseman 2003; Weissenberger & Schmidt, "Massively Parallel
+// Huffman Decoding on GPUs", ICPP 2018, and their JPEG follow-up.)  The stream, with the byte
+// stuffing removed by the host, is cut into SUBSEQUENCES of kSubBits bits, one thread each.
+//   state      = (bit position of the next code word, block index inside the MCU, position inside
+//                the block: 0 = the DC code comes next) -- everything Decode_8x8_Block (:758-788)
+//                and the MCU loop (:1187-1219) need to know besides the predictors;
+//   exit[i]    = the state in which the decoder leaves subsequence i (first code word that starts at
+//                or after bit (i + 1) * kSubBits), given the state entry[i] it entered with;
+//   1. sync    every thread decodes its subsequence from a guessed state, then, window by window
+//              (256 subsequences in shared memory), re-decodes from its predecessor's exit state
+//              until nothing changes; a second launch with the windows shifted by half repairs the
+//              window heads.  Subsequence 0 starts from the true state, so a chain that has
+//              stopped changing is the true one;
+//   2. scan    exclusive prefix sums of (blocks completed, sum of DC differences per component)
+//              give every subsequence its first block number and its DC predictors;
+//   3. output  every thread decodes once more, storing coefficients; it VERIFIES that it entered in
+//              its predecessor's exit state and leaves in its own recorded exit state.  By
+//              induction from subsequence 0 a verified chain is exactly the serial decode.  Any
+//              mismatch, any code the serial decoder would raise on, or a block count that does not
+//              reach the frame's: flag -> GIDCUDA_ERR_DATA -> the host decodes the scan.
+
+namespace {
+
+constexpr int kWindow = 256;
+
+struct RawBits {  // no stuffing, no end: the buffer is padded with FF bytes past the data
+  const uint32_t *w;  // next 32-bit word of the (4-byte aligned) stream
+  uint64_t buf;       // left-aligned: the next bit is bit 63
+  int len;
+  static __device__ __forceinline__ uint32_t be(uint32_t x) { return __byte_perm(x, 0u, 0x0123); }
+  __device__ __forceinline__ void start(const uint8_t *data, uint32_t bitpos) {
+    w = reinterpret_cast<const uint32_t *>(data) + (bitpos >> 5);
+    const uint64_t two = ((uint64_t)be(__ldg(w)) << 32) | be(__ldg(w + 1));
+    w += 2;
+    buf = two << (bitpos & 31u);
+    len = 64 - (int)(bitpos & 31u);
+  }
+  __device__ __forceinline__ void refill() {  // call when len <= 32
+    buf |= (uint64_t)be(__ldg(w++)) << (32 - len);
+    len += 32;
+  }
+  __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)(buf >> (64 - n)); }
+  __device__ __forceinline__ void drop(int n) {
+    buf <<= n;
+    len -= n;
+  }
+};
+
+__device__ __forceinline__ uint64_t pack_state(uint32_t pos, uint32_t c, uint32_t zpos) {
+  return (uint64_t)pos | ((uint64_t)c << 32) | ((uint64_t)zpos << 40);
+}
+
+// Decodes the code words of subsequence `i` that start before bit `limit`, from state `entry`.
+// FINAL = false: returns the exit state, counts completed blocks and sums DC differences (tup).
+// FINAL = true : also stores the coefficients; `b` = number of the first block (in scan order),
+//                pred = predictors on entry; stops at block `total`; *bad is set for anything
+//                the serial decoder would not decode silently.
+// Where the blocks of one MCU go (shared memory: indexing the kernel parameters with a run-time
+// index would make the compiler copy them to local memory).
+struct BlockSlot {
+  int16_t *plane;
+  uint32_t row_blocks;  // blocks per block row of the component's plane
+  uint32_t h, v, sx, sy, comp;
+};
+
+template <bool FINAL>
+__device__ __forceinline__ uint64_t run_subsequence(const WholeArgs &a, const HuffDev *tabs, const uint8_t *zz,
+                                                    const BlockSlot *slots,
+                                                    uint64_t entry, uint32_t limit, int4 &tup, uint32_t b, int pred0,
+                                                    int pred1, int pred2, bool *bad, uint32_t *done_blocks) {
+  uint32_t pos = (uint32_t)entry, c = (uint32_t)(entry >> 32) & 0xFFu, zpos = (uint32_t)(entry >> 40) & 0xFFu;
+  RawBits bits;
+  bits.start(a.data, pos);
+  int nb = 0, dcs0 = 0, dcs1 = 0, dcs2 = 0;  // (scalars: an indexed array would live in local memory)
+  int16_t *blk = nullptr;
+  auto block_ptr = [&](uint32_t blockno, uint32_t cc) -> int16_t * {
+    const uint32_t mcu = (blockno - cc) / a.bpm;
+    const uint32_t my = mcu / a.mcux, mx = mcu - my * a.mcux;
+    const BlockSlot &q = slots[cc];
+    return q.plane + ((size_t)(my * q.v + q.sy) * q.row_blocks + (mx * q.h + q.sx)) * 64;
+  };
+  if (FINAL) blk = block_ptr(b, c);
+  while (pos < limit) {
+    if (FINAL && b >= a.total_blocks) break;
+    if (bits.len <= 32) bits.refill();
+    const int k = (int)slots[c].comp;
+    const HuffDev &t = zpos == 0 ? tabs[k] : tabs[3 + k];
+    const uint32_t look = bits.peek(16);
+    const uint32_t e = t.lut[look >> 6];
+    int l = (int)(e >> 8), sym = (int)(e & 0xFFu);
+    if (e == 0) {
+      sym = -1;
+      for (l = 11; l <= 16; l++) {
+        const int code = (int)(look >> (16 - l));
+        if (code <= t.maxcode[l]) {
+          sym = t.vals[(t.valoff[l] + code) & 0xFF];
+          break;
+        }
+      }
+      if (sym < 0) {  // no such code: the serial decoder raises; a guessing decoder moves on one bit
+        if (FINAL) { *bad = true; break; }
+        bits.drop(1);
+        pos += 1;
+        continue;
+      }
+    }
+    bits.drop(l);
+    pos += (uint32_t)l;
+    const int n = sym & 15;
+    bool block_done = false;
+    if (zpos == 0) {
+      int v = 0;
+      if (n) {
+        v = extend(bits.peek(n), n);
+        bits.drop(n);
+        pos += (uint32_t)n;
+      }
+      if (FINAL) {
+        pred0 += k == 0 ? v : 0;
+        pred1 += k == 1 ? v : 0;
+        pred2 += k == 2 ? v : 0;
+        blk[0] = (int16_t)(k == 0 ? pred0 : (k == 1 ? pred1 : pred2));
+      } else {
+        dcs0 += k == 0 ? v : 0;
+        dcs1 += k == 1 ? v : 0;
+        dcs2 += k == 2 ? v : 0;
+      }
+      zpos = 1;
+    } else if (sym == 0) {
+      block_done = true;  // EOB
+    } else {
+      const uint32_t idx = zpos + (uint32_t)(sym >> 4);
+      if (FINAL && ((n == 0 && sym != 0xF0) || idx > 63)) { *bad = true; break; }
+      if (n) {
+        const int v = extend(bits.peek(n), n);
+        bits.drop(n);
+        pos += (uint32_t)n;
+        if (FINAL) blk[zz[idx & 63u]] = (int16_t)v;
+      }
+      if (idx >= 63) block_done = true;
+      else zpos = idx + 1;
+    }
+    if (block_done) {
+      zpos = 0;
+      c = c + 1 == a.bpm ? 0 : c + 1;
+      nb++;
+      if (FINAL) {
+        b++;
+        if (b < a.total_blocks) blk = block_ptr(b, c);
+      }
+    }
+  }
+  tup = make_int4(nb, dcs0, dcs1, dcs2);
+  if (FINAL) *done_blocks = (uint32_t)nb;
+  return pack_state(pos, c, zpos);
+}
+
+__device__ __forceinline__ void load_tables(const WholeArgs &a, HuffDev *tabs, uint8_t *zz, BlockSlot *slots) {
+  const uint32_t *src = reinterpret_cast<const uint32_t *>(a.tables);
+  uint32_t *dst = reinterpret_cast<uint32_t *>(tabs);
+  for (uint32_t i = threadIdx.x; i < 6 * sizeof(HuffDev) / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+  if (threadIdx.x < 64) zz[threadIdx.x] = c_zigzag[threadIdx.x];
+  if (threadIdx.x == 0) {
+    uint32_t cc = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++)  // static component index; the MCU's blocks in scan order (:1190-1206)
+      for (int sy = 0; sy < a.v[k]; sy++)
+        for (int sx = 0; sx < a.h[k]; sx++, cc++) {
+          BlockSlot q;
+          q.plane = a.plane[k];
+          q.row_blocks = a.bx[k];
+          q.h = (uint32_t)a.h[k];
+          q.v = (uint32_t)a.v[k];
+          q.sx = (uint32_t)sx;
+          q.sy = (uint32_t)sy;
+          q.comp = (uint32_t)k;
+          if (cc < 12) slots[cc] = q;
+        }
+  }
+}
+
+// Step 1.  Launch A: shift = 0, first = 1 (guessed entries).  Launch B: shift = kWindow / 2, first = 0.
+__global__ void __launch_bounds__(kWindow) huffman_sync_kernel(WholeArgs a, uint32_t shift, int first) {
+  __shared__ HuffDev tabs[6];
+  __shared__ uint8_t zz[64];
+  __shared__ uint64_t X[kWindow];
+  __shared__ BlockSlot slots[12];
+  load_tables(a, tabs, zz, slots);
+  const uint32_t t = threadIdx.x;
+  const uint32_t i = blockIdx.x * kWindow + t + shift;
+  const bool active = i < a.nsub;
+  const uint64_t true_start = pack_state(0u, 0u, 0u);
+  uint64_t entry = 0, exit_ = 0, head = 0;
+  int4 tup = make_int4(0, 0, 0, 0);
+  bool dirty = false;
+  __syncthreads();
+  const uint32_t limit = active ? min((i + 1) * a.sub_bits, a.nbits) : 0u;
+  if (active) {
+    if (first) {
+      entry = i == 0 ? true_start : pack_state(i * a.sub_bits, 0u, 0u);
+      exit_ = run_subsequence<false>(a, tabs, zz, slots, entry, limit, tup, 0u, 0, 0, 0, nullptr, nullptr);
+      dirty = true;
+    } else {
+      entry = a.entry[i];
+      exit_ = a.exit_[i];
+    }
+    if (t == 0) head = i == 0 ? true_start : (first ? entry : a.exit_[i - 1]);
+  }
+  X[t] = exit_;
+  for (int iter = 0; iter < kWindow; iter++) {
+    __syncthreads();
+    const uint64_t want = t == 0 ? head : X[t - 1];
+    const bool redo = active && want != entry;
+    uint64_t nx = exit_;
+    if (redo) {
+      entry = want;
+      nx = run_subsequence<false>(a, tabs, zz, slots, entry, limit, tup, 0u, 0, 0, 0, nullptr, nullptr);
+      dirty = true;
+    }
+    __syncthreads();  // every X[t - 1] has been read
+    const bool changed = redo && nx != exit_;
+    if (redo) {
+      exit_ = nx;
+      X[t] = nx;
+    }
+    if (!__syncthreads_or(changed ? 1 : 0)) break;
+  }
+  if (active && dirty) {
+    a.entry[i] = entry;
+    a.exit_[i] = exit_;
+    a.tuple[i] = tup;
+  }
+}
+
+// Step 2.  One CTA: exclusive prefix sums of the tuples, 1024 at a time.
+__global__ void __launch_bounds__(1024) huffman_scan_kernel(WholeArgs a) {
+  __shared__ int4 warp_tot[32];
+  __shared__ int4 carry_s;
+  const uint32_t t = threadIdx.x, lane = t & 31u, w = t >> 5;
+  if (t == 0) carry_s = make_int4(0, 0, 0, 0);
+  __syncthreads();
+  for (uint32_t base = 0; base < a.nsub; base += 1024) {
+    const uint32_t i = base + t;
+    int4 v = i < a.nsub ? a.tuple[i] : make_int4(0, 0, 0, 0);
+    int4 s = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int x = __shfl_up_sync(0xFFFFFFFFu, s.x, d), y = __shfl_up_sync(0xFFFFFFFFu, s.y, d);
+      const int z = __shfl_up_sync(0xFFFFFFFFu, s.z, d), q = __shfl_up_sync(0xFFFFFFFFu, s.w, d);
+      if (lane >= (uint32_t)d) { s.x += x; s.y += y; s.z += z; s.w += q; }
+    }
+    if (lane == 31) warp_tot[w] = s;
+    __syncthreads();
+    if (w == 0) {
+      int4 u = warp_tot[lane];
+      int4 r = u;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int x = __shfl_up_sync(0xFFFFFFFFu, r.x, d), y = __shfl_up_sync(0xFFFFFFFFu, r.y, d);
+        const int z = __shfl_up_sync(0xFFFFFFFFu, r.z, d), q = __shfl_up_sync(0xFFFFFFFFu, r.w, d);
+        if (lane >= (uint32_t)d) { r.x += x; r.y += y; r.z += z; r.w += q; }
+      }
+      warp_tot[lane] = make_int4(r.x - u.x, r.y - u.y, r.z - u.z, r.w - u.w);  // exclusive over the warps
+    }
+    __syncthreads();
+    const int4 wo = warp_tot[w], cy = carry_s;
+    // exclusive: everything before element i
+    const int4 ex = make_int4(cy.x + wo.x + s.x - v.x, cy.y + wo.y + s.y - v.y, cy.z + wo.z + s.z - v.z,
+                              cy.w + wo.w + s.w - v.w);
+    if (i < a.nsub) a.prefix[i] = ex;
+    __syncthreads();
+    if (t == 1023) carry_s = make_int4(ex.x + v.x, ex.y + v.y, ex.z + v.z, ex.w + v.w);
+    __syncthreads();
+  }
+}
+
+// Step 3.
+__global__ void __launch_bounds__(128) huffman_output_kernel(WholeArgs a) {
+  __shared__ HuffDev tabs[6];
+  __shared__ uint8_t zz[64];
+  __shared__ BlockSlot slots[12];
+  load_tables(a, tabs, zz, slots);
+  __syncthreads();
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.nsub) return;
+  const int4 pre = a.prefix[i];
+  const uint32_t b = (uint32_t)pre.x;
+  if (b >= a.total_blocks) return;  // padding after the last block
+  const uint64_t entry = i == 0 ? pack_state(0u, 0u, 0u) : a.exit_[i - 1];
+  bool bad = entry != a.entry[i];  // the tuples (and so the prefixes) belong to another chain
+  const uint32_t c = (uint32_t)(entry >> 32) & 0xFFu;
+  if (c >= a.bpm || b % a.bpm != c) bad = true;
+  uint32_t done = 0;
+  if (!bad) {
+    int4 tup;
+    const uint32_t limit = min((i + 1) * a.sub_bits, a.nbits);
+    const uint64_t out = run_subsequence<true>(a, tabs, zz, slots, entry, limit, tup, b, pre.y, pre.z, pre.w, &bad, &done);
+    // a subsequence that ends with the frame's last block stops early: nothing follows it
+    if (!bad && b + done < a.total_blocks && out != a.exit_[i]) bad = true;
+  }
+  if (bad) atomicOr(a.status, 2u);
+  if (done) atomicAdd(a.status + 2, done);
+}
+
+}  // namespace
+
+cudaError_t launch_huffman_whole(const WholeArgs &a, cudaStream_t stream) {
+  if (a.nsub == 0) return cudaSuccess;
+  huffman_sync_kernel<<<(a.nsub + kWindow - 1) / kWindow, kWindow, 0, stream>>>(a, 0u, 1);
+  if (a.nsub > kWindow / 2)
+    huffman_sync_kernel<<<(a.nsub - kWindow / 2 + kWindow - 1) / kWindow, kWindow, 0, stream>>>(a, kWindow / 2, 0);
+  huffman_scan_kernel<<<1, 1024, 0, stream>>>(a);
+  huffman_output_kernel<<<(a.nsub + 127) / 128, 128, 0, stream>>>(a);
   return cudaGetLastError();
 }
 

@@ -151,6 +151,10 @@ extern "C" int gidcuda_host_free(void *ptr) {
 // ---------------------------------------------------------------------------
 // jobs
 
+// gidcuda_set_option("blocking_wait"): jobs created from now on sleep in gidcuda_job_wait instead
+// of spinning -- for callers that run about as many host threads as there are cores.
+static int g_blocking_wait = 0;
+
 struct gidcuda_job {
   gidcuda_ctx *ctx = nullptr;
   gidcuda_frame_desc desc;
@@ -173,6 +177,10 @@ struct gidcuda_job {
   uint32_t *h_status = nullptr, *d_status = nullptr;
   bool scan_active = false;
   int32_t scan_ri = 0, scan_nintervals = 0;
+  // ... scans without restart markers (scan_ri == 0): the self-synchronising decoder's arrays
+  uint8_t *d_sync = nullptr;
+  size_t cap_sync = 0, scan_len = 0;
+  uint32_t scan_nsub = 0;
   uint8_t *user_pixels = nullptr;  // gidcuda_job_output: the caller's own pinned buffer receives the pixels
   uint8_t *d_coef = nullptr, *d_pixels = nullptr, *d_samples = nullptr;
   gidk::LaunchSet set;
@@ -192,6 +200,9 @@ static void job_free_buffers(gidcuda_job *j) {
   if (j->d_scan) cudaFree(j->d_scan);
   if (j->h_status) cudaFreeHost(j->h_status);
   if (j->d_status) cudaFree(j->d_status);
+  if (j->d_sync) cudaFree(j->d_sync);
+  j->d_sync = nullptr;
+  j->cap_sync = 0;
   j->h_scan = j->d_scan = nullptr;
   j->h_status = j->d_status = nullptr;
   j->cap_scan = 0;
@@ -254,7 +265,8 @@ static int job_reserve_sparse(gidcuda_job *j) {
 static int job_reserve(gidcuda_job *j) {
   gidcuda_ctx *ctx = j->ctx;
   const Geometry &g = j->geo;
-  if (!j->done) CU_TRY(ctx, cudaEventCreateWithFlags(&j->done, cudaEventDisableTiming));
+  if (!j->done)
+    CU_TRY(ctx, cudaEventCreateWithFlags(&j->done, cudaEventDisableTiming | (g_blocking_wait ? cudaEventBlockingSync : 0)));
   if (!j->stream) CU_TRY(ctx, cudaStreamCreateWithFlags(&j->stream, cudaStreamNonBlocking));
   if (j->cap_coef < g.coef_bytes) {
     if (j->d_coef) cudaFree(j->d_coef);
@@ -269,7 +281,7 @@ static int job_reserve(gidcuda_job *j) {
     if (j->d_pixels) cudaFree(j->d_pixels);
     j->h_pixels = j->d_pixels = nullptr;
     j->cap_pixels = 0;
-    CU_TRY(ctx, cudaHostAlloc((void **)&j->h_pixels, g.pixel_bytes, cudaHostAllocDefault));
+    // (the pinned host twin is allocated at submit, unless the caller supplies its own: gidcuda_job_output)
     CU_TRY(ctx, cudaMalloc((void **)&j->d_pixels, g.pixel_bytes));
     j->cap_pixels = g.pixel_bytes;
   }
@@ -446,16 +458,71 @@ static bool build_huff_dev(const gidcuda_huffman_table &t, gidk::HuffDev *d) {
   return true;
 }
 
+constexpr uint32_t kSubsequenceBits = 256;  // one device thread per this many bits of a scan without restart markers
+
+// gidcuda_job_scan with restart_interval == 0: the whole scan, byte stuffing removed by the caller.
+static int job_scan_whole(gidcuda_job *job, const gidcuda_scan_desc *scan, const uint8_t *data, size_t len) {
+  gidcuda_ctx *ctx = job->ctx;
+  const Geometry &g = job->geo;
+  int bpm = 0;
+  for (int c = 0; c < g.ncomp; c++) bpm += job->desc.samp_h[c] * job->desc.samp_v[c];
+  if (bpm > 12) return fail(ctx, GIDCUDA_ERR_UNSUPPORTED, "gidcuda_job_scan: %d blocks per MCU", bpm);
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t off_data = round_up(6 * sizeof(gidk::HuffDev), 256);
+  const size_t total = off_data + round_up(len + 64, 256);  // FF padding: the decoder looks a few bytes ahead
+  if (job->cap_scan < total) {
+    if (job->h_scan) cudaFreeHost(job->h_scan);
+    if (job->d_scan) cudaFree(job->d_scan);
+    job->h_scan = job->d_scan = nullptr;
+    job->cap_scan = 0;
+    const size_t cap = total + total / 4;
+    CU_TRY(ctx, cudaHostAlloc((void **)&job->h_scan, cap, cudaHostAllocDefault));
+    CU_TRY(ctx, cudaMalloc((void **)&job->d_scan, cap));
+    job->cap_scan = cap;
+  }
+  if (!job->h_status) {
+    CU_TRY(ctx, cudaHostAlloc((void **)&job->h_status, 16, cudaHostAllocDefault));
+    CU_TRY(ctx, cudaMalloc((void **)&job->d_status, 16));
+  }
+  const uint32_t nsub = (uint32_t)((len * 8 + kSubsequenceBits - 1) / kSubsequenceBits);
+  const size_t sync_bytes = (size_t)nsub * (8 + 8 + 16 + 16) + 1024;
+  if (job->cap_sync < sync_bytes) {
+    if (job->d_sync) cudaFree(job->d_sync);
+    job->d_sync = nullptr;
+    job->cap_sync = 0;
+    const size_t cap = sync_bytes + sync_bytes / 4;
+    CU_TRY(ctx, cudaMalloc((void **)&job->d_sync, cap));
+    job->cap_sync = cap;
+  }
+  gidk::HuffDev *tabs = reinterpret_cast<gidk::HuffDev *>(job->h_scan);
+  for (int c = 0; c < 3; c++) {
+    const bool used = c < g.ncomp;
+    if (!build_huff_dev(scan->dc[used ? c : 0], &tabs[c]) || !build_huff_dev(scan->ac[used ? c : 0], &tabs[3 + c]))
+      return fail(ctx, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_job_scan: Huffman table of component %d is not a prefix code", c);
+  }
+  memcpy(job->h_scan + off_data, data, len);
+  memset(job->h_scan + off_data + len, 0xFF, total - off_data - len);
+  job->scan_off_data = off_data;
+  job->scan_bytes = total;
+  job->scan_len = len;
+  job->scan_nsub = nsub;
+  job->scan_ri = 0;
+  job->scan_nintervals = 0;
+  job->scan_active = true;
+  return GIDCUDA_OK;
+}
+
 extern "C" int gidcuda_job_scan(gidcuda_job *job, const gidcuda_scan_desc *scan, const uint8_t *data, size_t len,
                                 const uint32_t *begin, const uint32_t *end) {
   if (!job) return fail(nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "null job");
   gidcuda_ctx *ctx = job->ctx;
   if (job->state != gidcuda_job::BEGUN)
     return fail(ctx, GIDCUDA_ERR_STATE, "gidcuda_job_scan: only between gidcuda_job_begin and gidcuda_job_submit");
-  if (!scan || !data || !begin || !end || len == 0 || len > 0xFFFFFFF0u)
-    return fail(ctx, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_job_scan: null argument or no data");
+  if (!scan || !data || len == 0 || len >= ((size_t)1 << 28) || (scan->restart_interval != 0 && (!begin || !end)))
+    return fail(ctx, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_job_scan: null argument, no data or more than 256 MiB of it");
   const Geometry &g = job->geo;
   const int64_t nmcu = (int64_t)g.mcux * g.mcuy;
+  if (scan->restart_interval == 0) return job_scan_whole(job, scan, data, len);
   if (scan->restart_interval <= 0 || scan->nintervals <= 0 ||
       (nmcu + scan->restart_interval - 1) / scan->restart_interval != scan->nintervals)
     return fail(ctx, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_job_scan: %d intervals of %d MCUs do not cover %lld MCUs",
@@ -481,8 +548,8 @@ extern "C" int gidcuda_job_scan(gidcuda_job *job, const gidcuda_scan_desc *scan,
     job->cap_scan = cap;
   }
   if (!job->h_status) {
-    CU_TRY(ctx, cudaHostAlloc((void **)&job->h_status, 8, cudaHostAllocDefault));
-    CU_TRY(ctx, cudaMalloc((void **)&job->d_status, 8));
+    CU_TRY(ctx, cudaHostAlloc((void **)&job->h_status, 16, cudaHostAllocDefault));
+    CU_TRY(ctx, cudaMalloc((void **)&job->d_status, 16));
   }
   gidk::HuffDev *tabs = reinterpret_cast<gidk::HuffDev *>(job->h_scan);
   for (int c = 0; c < 3; c++) {
@@ -562,28 +629,58 @@ extern "C" int gidcuda_job_submit(gidcuda_job *job) {
     // compressed bytes -> device, planes zeroed, one thread per restart interval decodes
     CU_TRY(ctx, cudaMemcpyAsync(job->d_scan, job->h_scan, job->scan_bytes, cudaMemcpyHostToDevice, s));
     CU_TRY(ctx, cudaMemsetAsync(job->d_coef, 0, g.coef_bytes, s));
-    CU_TRY(ctx, cudaMemsetAsync(job->d_status, 0, 8, s));
-    gidk::ScanArgs sa;
-    memset(&sa, 0, sizeof sa);
-    sa.data = job->d_scan + job->scan_off_data;
-    sa.begin = reinterpret_cast<const uint32_t *>(job->d_scan + job->scan_off_begin);
-    sa.end = reinterpret_cast<const uint32_t *>(job->d_scan + job->scan_off_end);
-    sa.tables = reinterpret_cast<const gidk::HuffDev *>(job->d_scan);
-    for (int c = 0; c < g.ncomp; c++) {
-      sa.plane[c] = reinterpret_cast<int16_t *>(job->d_coef + g.plane_off[c]);
-      sa.bx[c] = (uint32_t)g.bx[c];
-      sa.h[c] = job->desc.samp_h[c];
-      sa.v[c] = job->desc.samp_v[c];
-      job->d_tail_zero[c] = false;
+    CU_TRY(ctx, cudaMemsetAsync(job->d_status, 0, 16, s));
+    if (job->scan_ri == 0) {
+      gidk::WholeArgs wa;
+      memset(&wa, 0, sizeof wa);
+      wa.data = job->d_scan + job->scan_off_data;
+      wa.tables = reinterpret_cast<const gidk::HuffDev *>(job->d_scan);
+      const size_t n = job->scan_nsub;
+      wa.entry = reinterpret_cast<uint64_t *>(job->d_sync);
+      wa.exit_ = wa.entry + n;
+      wa.tuple = reinterpret_cast<int4 *>(job->d_sync + round_up(16 * n, 256));
+      wa.prefix = wa.tuple + n;
+      uint32_t k = 0, blocks = 0;
+      for (int c = 0; c < g.ncomp; c++) {
+        wa.plane[c] = reinterpret_cast<int16_t *>(job->d_coef + g.plane_off[c]);
+        wa.bx[c] = (uint32_t)g.bx[c];
+        wa.h[c] = job->desc.samp_h[c];
+        wa.v[c] = job->desc.samp_v[c];
+        blocks += (uint32_t)g.bx[c] * (uint32_t)g.by[c];
+        k += (uint32_t)(wa.h[c] * wa.v[c]);
+        job->d_tail_zero[c] = false;
+      }
+      wa.bpm = k;
+      wa.mcux = (uint32_t)g.mcux;
+      wa.total_blocks = blocks;
+      wa.nbits = (uint32_t)(job->scan_len * 8);
+      wa.sub_bits = kSubsequenceBits;
+      wa.nsub = job->scan_nsub;
+      wa.status = job->d_status;
+      CU_TRY(ctx, gidk::launch_huffman_whole(wa, s));
+    } else {
+      gidk::ScanArgs sa;
+      memset(&sa, 0, sizeof sa);
+      sa.data = job->d_scan + job->scan_off_data;
+      sa.begin = reinterpret_cast<const uint32_t *>(job->d_scan + job->scan_off_begin);
+      sa.end = reinterpret_cast<const uint32_t *>(job->d_scan + job->scan_off_end);
+      sa.tables = reinterpret_cast<const gidk::HuffDev *>(job->d_scan);
+      for (int c = 0; c < g.ncomp; c++) {
+        sa.plane[c] = reinterpret_cast<int16_t *>(job->d_coef + g.plane_off[c]);
+        sa.bx[c] = (uint32_t)g.bx[c];
+        sa.h[c] = job->desc.samp_h[c];
+        sa.v[c] = job->desc.samp_v[c];
+        job->d_tail_zero[c] = false;
+      }
+      sa.ncomp = g.ncomp;
+      sa.mcux = (uint32_t)g.mcux;
+      sa.nmcu = (uint32_t)g.mcux * (uint32_t)g.mcuy;
+      sa.ri = (uint32_t)job->scan_ri;
+      sa.nintervals = (uint32_t)job->scan_nintervals;
+      sa.status = job->d_status;
+      CU_TRY(ctx, gidk::launch_huffman_intervals(sa, s));
     }
-    sa.ncomp = g.ncomp;
-    sa.mcux = (uint32_t)g.mcux;
-    sa.nmcu = (uint32_t)g.mcux * (uint32_t)g.mcuy;
-    sa.ri = (uint32_t)job->scan_ri;
-    sa.nintervals = (uint32_t)job->scan_nintervals;
-    sa.status = job->d_status;
-    CU_TRY(ctx, gidk::launch_huffman_intervals(sa, s));
-    CU_TRY(ctx, cudaMemcpyAsync(job->h_status, job->d_status, 8, cudaMemcpyDeviceToHost, s));
+    CU_TRY(ctx, cudaMemcpyAsync(job->h_status, job->d_status, 16, cudaMemcpyDeviceToHost, s));
   }
   constexpr size_t kMinPitchedPlane = (size_t)8 << 20;
   bool any_sparse = false, all_dense_plain = true;
@@ -655,6 +752,8 @@ extern "C" int gidcuda_job_submit(gidcuda_job *job) {
     CU_TRY(ctx, gidk::launch_expand(ea, g.ncomp, s));
   }
   CU_TRY(ctx, job->set.launch(ctx->num_sms, s));
+  if (!job->user_pixels && !job->h_pixels)
+    CU_TRY(ctx, cudaHostAlloc((void **)&job->h_pixels, job->cap_pixels, cudaHostAllocDefault));
   CU_TRY(ctx, cudaMemcpyAsync(job->user_pixels ? job->user_pixels : job->h_pixels, job->d_pixels, g.pixel_bytes,
                               cudaMemcpyDeviceToHost, s));
   CU_TRY(ctx, cudaEventRecord(job->done, s));
@@ -670,6 +769,15 @@ extern "C" int gidcuda_job_wait(gidcuda_job *job, const uint8_t **pixels, size_t
   CU_TRY(ctx, cudaEventSynchronize(job->done));
   if (job->scan_active) {
     job->scan_active = false;  // a re-submission after a host decode takes planes / records
+    uint32_t blocks = 0;
+    for (int c = 0; c < job->geo.ncomp; c++) blocks += (uint32_t)job->geo.bx[c] * (uint32_t)job->geo.by[c];
+    if (job->scan_ri == 0 && job->h_status[0] == 0 && job->h_status[2] != blocks) job->h_status[0] = 4;
+    if (job->scan_ri == 0 && job->h_status[0] != 0) {
+      job->state = gidcuda_job::BEGUN;
+      return fail(ctx, GIDCUDA_ERR_DATA,
+                  "device entropy decoder: scan left to the host decoder (flags %u, %u of %u blocks)", job->h_status[0],
+                  job->h_status[2], blocks);
+    }
     if (job->h_status[0] != 0) {
       job->state = gidcuda_job::BEGUN;
       return fail(ctx, GIDCUDA_ERR_DATA,
@@ -796,6 +904,10 @@ extern "C" int gidcuda_plan_launch_count(const gidcuda_plan *plan) { return plan
 
 extern "C" int gidcuda_set_option(const char *name, int value) {
   if (!name) return fail(nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "null option name");
+  if (strcmp(name, "blocking_wait") == 0) {
+    g_blocking_wait = value ? 1 : 0;
+    return GIDCUDA_OK;
+  }
   if (strcmp(name, "tma") == 0) {
     gidk::tma_option() = value ? 1 : 0;
     return GIDCUDA_OK;

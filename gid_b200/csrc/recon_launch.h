@@ -80,6 +80,23 @@ struct ScanArgs {
 };
 cudaError_t launch_huffman_intervals(const ScanArgs &a, cudaStream_t stream);
 
+// ... and for scans without restart markers: self-synchronising parallel decoding (entropy_kernel.cu)
+struct WholeArgs {
+  const uint8_t *data;     // the scan's bytes with the stuffing removed, padded with FF
+  const HuffDev *tables;   // [6]
+  uint64_t *entry, *exit_; // [nsub] decoder state on entering / leaving each subsequence
+  int4 *tuple, *prefix;    // [nsub] (blocks completed, DC difference sums) and their exclusive prefix sums
+  int16_t *plane[3];
+  uint32_t bx[3];
+  int32_t h[3], v[3];
+  uint32_t bpm;            // blocks per MCU (<= 12)
+  uint32_t mcux, total_blocks;
+  uint32_t nbits, sub_bits, nsub;
+  uint32_t *status;        // [0] flags (2 = chain not verified / undecodable), [2] blocks stored
+};
+cudaError_t launch_huffman_whole(const WholeArgs &a, cudaStream_t stream);
+inline int launches_huffman_whole() { return 4; }
+
 // One-time kernel attribute set-up (dynamic shared memory opt-in).
 cudaError_t init_kernels();
 

@@ -8,7 +8,7 @@
 // device devices[w mod ndevices], take the next file from a shared counter, entropy-decode
 // it on their core (gid-decoding_jpg.adb:1179-1220 / :1243-1747) straight into the pinned
 // record arrays of a job, submit it, and -- while that frame crosses the link and is
-// reconstructed on the B200 -- start on their next file.  Two frames are in flight per
+// reconstructed on the B200 -- start on their next file.  Three frames are in flight per
 // worker.  Finished pixels go to the caller's top-down RGB8 buffers (the buffer
 // test/benchmark.adb:67-81 fills through Put_Pixel): straight from the device when a buffer
 // is pinned host memory (gidcuda_host_alloc), through a copy otherwise.  No inter-GPU
@@ -19,6 +19,7 @@
 // spare threads go to the restart-interval-parallel scan of each file
 // (Image_Descriptor::entropy_threads).
 #include <chrono>
+#include <deque>
 #include <memory>
 #include <mutex>
 
@@ -40,6 +41,11 @@ typedef struct gidhost_batch_stats {
 int gidhost_status_of_current_exception(char *err, size_t errlen);  // gid_jpeg_host.cpp
 int gidhost_option_device_entropy(void);
 
+// Frames a worker keeps in flight: while it prepares frame k (header, entropy decode or -- when the
+// device decodes the scan -- just finding the scan's end), frames k - 1 and k - 2 cross the link and
+// are decoded / reconstructed.  Small frames are latency-bound (a dozen stream operations each).
+constexpr int kFramesInFlight = 3;
+
 // The workers' device contexts outlive a call: their pinned and device buffers are recycled
 // from one batch to the next (gidcuda_job_release returns them to the context's pool).
 struct gidhost_batch {
@@ -55,6 +61,10 @@ int gidhost_batch_create(const int32_t *devices, int32_t ndevices, int32_t threa
   for (int32_t i = 0; i < ndevices; i++) b->devices.push_back(devices[i]);
   b->threads = threads > 0 ? threads : (int)std::max(1u, std::thread::hardware_concurrency());
   b->ctx.assign((size_t)b->threads, nullptr);
+  // many workers: a waiting one sleeps instead of spinning on a core another worker needs
+  const char *env = getenv("GIDHOST_BLOCKING_WAIT");
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  gidcuda_set_option("blocking_wait", env ? atoi(env) : ((unsigned)b->threads * 2 > hw ? 1 : 0));
   *batch = b;
   return 0;
 }
@@ -109,7 +119,8 @@ int gidhost_batch_decode(gidhost_batch *b, int32_t n, const uint8_t *const *data
       int32_t index = -1;
       std::unique_ptr<gid::Stream> st;
       std::unique_ptr<gid::Image_Descriptor> im;
-    } pending;
+    };
+    std::deque<InFlight> inflight;  // oldest first; kFramesInFlight - 1 of them while the next one is decoded
     double mp = 0.0;
     auto fail = [&](int32_t i) {
       char msg[256];
@@ -160,10 +171,13 @@ int gidhost_batch_decode(gidhost_batch *b, int32_t n, const uint8_t *const *data
         fail(i);
         continue;
       }
-      finish(pending);  // the frame before this one: done by now, or nearly
-      pending = std::move(cur);
+      inflight.push_back(std::move(cur));
+      if ((int)inflight.size() >= kFramesInFlight) {  // the oldest frame: done by now, or nearly
+        finish(inflight.front());
+        inflight.pop_front();
+      }
     }
-    finish(pending);
+    for (InFlight &f : inflight) finish(f);
     std::lock_guard<std::mutex> g(mu);
     megapixels += mp;
   };

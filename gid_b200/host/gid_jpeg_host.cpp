@@ -221,7 +221,9 @@ void *decode_and_submit(Image_Descriptor &image, void *ctx_, const std::function
           }
         }
         // (a table the device cannot take, e.g. an over-subscribed one, is a case for the host loop)
-        if (gidcuda_job_scan(job, &sd, ds.data, ds.len, ds.begin.data(), ds.end.data()) != GIDCUDA_OK) return false;
+        if (gidcuda_job_scan(job, &sd, ds.data, ds.len, ds.restart_interval ? ds.begin.data() : nullptr,
+                             ds.restart_interval ? ds.end.data() : nullptr) != GIDCUDA_OK)
+          return false;
         device_scans++;
         return true;
       };

@@ -625,11 +625,59 @@ struct Decoder {
     const uint8_t *data;
     size_t len;
     std::vector<uint32_t> begin, end;  // relative to data
-    int restart_interval;
+    int restart_interval;              // 0: a scan without restart markers; data = `unstuffed`
+    std::vector<uint8_t> unstuffed;
     const std::vector<uint8_t> *dc_bits[3], *dc_vals[3], *ac_bits[3], *ac_vals[3];
   };
   std::function<bool(const DeviceScan &)> device_scan;
   bool device_scanned = false;
+
+  void device_scan_tables(DeviceScan &ds) {
+    for (int c = 0; c < 3; c++) {
+      ds.dc_bits[c] = ds.dc_vals[c] = ds.ac_bits[c] = ds.ac_vals[c] = nullptr;
+      if (!im.info[c].present) continue;
+      table(0, ht_dc[c]);  // raises like the serial loop when a table is missing
+      table(1, ht_ac[c]);
+      ds.dc_bits[c] = &im.huff_bits[0][ht_dc[c]];
+      ds.dc_vals[c] = &im.huff_vals[0][ht_dc[c]];
+      ds.ac_bits[c] = &im.huff_bits[1][ht_ac[c]];
+      ds.ac_vals[c] = &im.huff_vals[1][ht_ac[c]];
+    }
+  }
+
+  // A scan without restart markers: the bytes up to the marker that ends it, stuffing removed
+  // (FF 00 -> FF, :640-662), go to the device's self-synchronising decoder.
+  bool device_whole_scan() {
+    if (!device_scan || im.restart_interval > 0) return false;
+    const uint8_t *d = r.s.data;
+    const size_t size = r.s.size;
+    DeviceScan ds;
+    ds.restart_interval = 0;
+    size_t i = r.s.pos;
+    if (size - i < 4096) return false;  // a small scan is decoded on the host before the extra launches are queued
+    ds.unstuffed.reserve(size - i);
+    for (;;) {
+      const void *f = i < size ? memchr(d + i, 0xFF, size - i) : nullptr;
+      const size_t j = f ? (size_t)((const uint8_t *)f - d) : size;
+      ds.unstuffed.insert(ds.unstuffed.end(), d + i, d + j);
+      if (!f) break;
+      const uint8_t m = j + 1 < size ? d[j + 1] : (uint8_t)M_EOI;
+      if (m != 0) {
+        if (m >= M_RST0 && m <= M_RST7) return false;  // restart markers without DRI: the serial loop's case
+        break;
+      }
+      ds.unstuffed.push_back(0xFF);
+      i = j + 2;
+    }
+    if (ds.unstuffed.empty()) return false;
+    ds.data = ds.unstuffed.data();
+    ds.len = ds.unstuffed.size();
+    device_scan_tables(ds);
+    if (!device_scan(ds)) return false;
+    device_scanned = true;
+    emit_feedback(50);
+    return true;
+  }
 
   bool device_baseline_scan() {
     const int ri = im.restart_interval;
@@ -651,16 +699,7 @@ struct Decoder {
       ds.end[(size_t)k] = (uint32_t)(seg_end[(size_t)k] - base);
     }
     ds.restart_interval = ri;
-    for (int c = 0; c < 3; c++) {
-      ds.dc_bits[c] = ds.dc_vals[c] = ds.ac_bits[c] = ds.ac_vals[c] = nullptr;
-      if (!im.info[c].present) continue;
-      table(0, ht_dc[c]);  // raises like the serial loop when a table is missing
-      table(1, ht_ac[c]);
-      ds.dc_bits[c] = &im.huff_bits[0][ht_dc[c]];
-      ds.dc_vals[c] = &im.huff_vals[0][ht_dc[c]];
-      ds.ac_bits[c] = &im.huff_bits[1][ht_ac[c]];
-      ds.ac_vals[c] = &im.huff_vals[1][ht_ac[c]];
-    }
+    device_scan_tables(ds);
     if (!device_scan(ds)) return false;
     device_scanned = true;
     emit_feedback(50);
@@ -775,7 +814,7 @@ struct Decoder {
 
   void baseline_scan() {  // :1179-1220; loops over FRAME components like the reference (:1190-1191)
     const int mh = mcu_count_image_h, mv = mcu_count_image_v;
-    if (device_baseline_scan()) return;
+    if (device_baseline_scan() || device_whole_scan()) return;
     ensure_host_output();
     if (parallel_baseline_scan()) return;
     rst_count = im.restart_interval;

@@ -166,7 +166,7 @@ def decode_planes(data: bytes):
 
 class HostBatch:
     """Many .jpg files -> top-down RGB8 arrays (gid_b200/host/gid_batch.cpp): `threads` host threads
-    (0 = all) entropy-decode, the B200(s) reconstruct, two frames in flight per thread.  The
+    (0 = all) entropy-decode, the B200(s) reconstruct, three frames in flight per thread.  The
     workers' device contexts (pinned + device buffers) persist from one decode() to the next."""
 
     def __init__(self, devices=(0,), threads: int = 0):

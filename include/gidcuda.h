@@ -89,7 +89,9 @@ int gidcuda_device_count(void);
 const char *gidcuda_last_error(const gidcuda_ctx *ctx);
 
 /* Library options (process-wide; set before creating jobs / plans):
- *   "tma"  1 (default) = stage coefficients through TMA, 0 = plain 128-bit loads. */
+ *   "tma"  1 (default) = stage coefficients through TMA, 0 = plain 128-bit loads.
+ *   "blocking_wait"  0 (default) = gidcuda_job_wait spins (lowest latency); 1 = it sleeps until the
+ *          frame is done (for callers with about as many host threads as cores). */
 int gidcuda_set_option(const char *name, int value);
 
 /* One context per host thread / Ada task.  Owns a device, streams and a pool
@@ -168,6 +170,14 @@ int gidcuda_job_records_commit_runs(gidcuda_job *job, int comp, int32_t nruns, c
  *                      FF is followed by 00 (byte stuffing, :640-662)
  *   scan               restart interval in MCUs, and per component the Huffman tables of the scan
  *                      (Read_DHT :320-391: 16 counts, then the symbols in code order)
+ * A scan WITHOUT restart markers (restart_interval = 0, nintervals = 0, begin = end = NULL) is taken
+ * too: data = the scan's bytes up to the marker that ends it, with the byte stuffing REMOVED
+ * (FF 00 -> FF).  The device cuts the bit stream into subsequences of 256 bits, one thread each,
+ * and relies on Huffman codes re-synchronising: every thread decodes from a guessed state, then from
+ * its predecessor's exit state until the chain of states stops changing; prefix sums give every
+ * subsequence its first block and its DC predictors; a last pass stores the coefficients and
+ * VERIFIES the chain (by induction from the first subsequence a verified chain is the serial
+ * decode).  A chain that does not verify is reported like a damaged stream.
  * The MCU order, block order and predictor handling are those of Baseline_DCT_Decoding_Scan
  * (:1179-1220).  The device decoder does not reproduce the reference's handling of damaged streams:
  * when an interval holds a code that is in no table, a run past coefficient 63, too few or too many
@@ -178,8 +188,8 @@ typedef struct gidcuda_huffman_table {
   uint8_t symbols[256]; /* in code order */
 } gidcuda_huffman_table;
 typedef struct gidcuda_scan_desc {
-  int32_t restart_interval;        /* MCUs per interval (DRI, :424-434), > 0 */
-  int32_t nintervals;              /* ceil(MCUs of the frame / restart_interval) */
+  int32_t restart_interval;        /* MCUs per interval (DRI, :424-434); 0 = the scan has no restart markers */
+  int32_t nintervals;              /* ceil(MCUs of the frame / restart_interval); 0 with restart_interval = 0 */
   gidcuda_huffman_table dc[3], ac[3]; /* per component of the frame */
 } gidcuda_scan_desc;
 int gidcuda_job_scan(gidcuda_job *job, const gidcuda_scan_desc *scan, const uint8_t *data, size_t len,

@@ -457,3 +457,60 @@ def test_device_entropy_decode_leaves_damaged_streams_to_the_host(host, oracle, 
                 ref = ("err", None)
             assert want[0] == ref[0] and (want[0] == "err" or want[1] == ref[1]), (samp, t)
     assert declined > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("samp,w,h,quality,optimize", [
+    ("420", 1920, 1080, 75, False), ("444", 1024, 768, 75, False), ("grey", 2048, 1024, 75, False),
+    ("422", 1280, 720, 90, True), ("440", 640, 800, 50, False), ("411", 1024, 512, 75, True),
+    ("420", 2999, 2001, 95, False), ("444", 333, 211, 100, True),
+])
+def test_device_entropy_decode_without_restart_markers(host, oracle, synth, gpu, samp, w, h, quality, optimize):
+    """A baseline scan without RSTn is one bit stream: the device cuts it into 1024-bit
+    subsequences and lets the Huffman code re-synchronise (entropy_kernel.cu, second half).
+    The verified chain is the serial decode: pixels == GID's decode, nothing left to the host."""
+    jpg, _ = synth.encode(pixels_for(synth, 14, w, h, samp), samp, quality=quality, optimize=optimize)
+    _, ref, _ = oracle.decode(jpg)
+    scans, back = host.counter("device_scans"), host.counter("device_scan_fallbacks")
+    rgb, fb = host.decode_rgb(jpg)
+    assert np.array_equal(rgb, ref)
+    assert host.counter("device_scans") == scans + 1 and host.counter("device_scan_fallbacks") == back
+    assert fb == sorted(fb) and fb[-1] == 100
+
+
+@pytest.mark.gpu
+def test_device_entropy_decode_noise_and_damage_without_restart_markers(host, oracle, synth, gpu):
+    """Quality-100 noise (16-bit codes, 63-coefficient blocks), then damaged streams: the outcome is
+    the host decoder's (pixels or exception class), which the CPU suite pins to the oracle."""
+    rng = np.random.default_rng(9)
+    pix = rng.integers(0, 256, size=(512, 768, 3), dtype=np.uint8)
+    for samp in ("420", "444"):
+        jpg, _ = synth.encode(pix, samp, quality=100)
+        scans = host.counter("device_scans")
+        rgb, _ = host.decode_rgb(jpg)
+        assert host.counter("device_scans") == scans + 1
+        assert np.array_equal(rgb, oracle.decode(jpg)[1])
+    jpg, _ = synth.encode(pixels_for(synth, 3, 1024, 800, "420"), "420")
+    sos = jpg.index(b"\xff\xda")
+    for t in range(12):
+        bad = bytearray(jpg)
+        pos = int(rng.integers(sos + 14, len(bad) - 2))
+        if t % 3 == 0:
+            bad[pos] = int(rng.integers(0, 255))
+        elif t % 3 == 1:
+            del bad[pos]
+        else:
+            del bad[pos:pos + 1000]
+        bad = bytes(bad)
+
+        def outcome():
+            try:
+                return ("ok", hashlib.sha256(host.decode_rgb(bad)[0].tobytes()).hexdigest())
+            except host.GidHostError as e:
+                return ("err", e.name)
+        host.set_option("device_entropy", 0)
+        try:
+            want = outcome()
+        finally:
+            host.set_option("device_entropy", 1)
+        assert outcome() == want, t

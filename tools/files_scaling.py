@@ -25,8 +25,11 @@ for wl in (sys.argv[1:] or ["cfg3"]):
     while True:
         with host_api.HostBatch(devices=(0,), threads=T) as hb:
             hb.decode(files, out)
+            c0 = [host_api.counter(k) for k in ("device_scans", "device_scan_fallbacks")]
             _, st, stats = hb.decode(files, out)
-        print(f"{wl}: threads {stats.threads:3d} (x{stats.entropy_threads} inside an image)  {w*h*per_call/1e6/stats.seconds:8.0f} MP/s  {1e3*stats.seconds/per_call*stats.threads:7.2f} ms per image per thread", flush=True)
+            c1 = [host_api.counter(k) for k in ("device_scans", "device_scan_fallbacks")]
+        print(f"{wl}: threads {stats.threads:3d} (x{stats.entropy_threads} inside an image)  {w*h*per_call/1e6/stats.seconds:8.0f} MP/s  {1e3*stats.seconds/per_call*stats.threads:7.2f} ms per image per thread"
+              f"   device scans {c1[0]-c0[0]}, left to the host {c1[1]-c0[1]}", flush=True)
         if T >= ncpu:
             break
         T = min(ncpu, T * 2)
