@@ -463,7 +463,12 @@ def run_ours(args) -> None:
     # ---- from .jpg files: host entropy decode on this rank's share of the cores + the path above ----
     files = None
     if not args.no_files:
+        # this rank's share of the cores; at most 8 workers where the device decodes the scans (baseline files):
+        # 2-4 of them saturate the device-to-host link, and past ~12 the workers' CUDA calls contend
+        # (profiles/r01f_files_thread_scaling.txt).  Progressive files are Huffman-decoded on the host cores.
         share = max(1, (os.cpu_count() or 1) // world)
+        if not FILE_FORM[args.workload][0]:
+            share = min(share, 8)
         files = files_leg_ours(args.workload, local, share, 3)
         secs = w * h * files["images_per_call"] * files["calls"] / 1e6 / files["value"]
         files["value"] = sharding.whole_job_rate(w * h * files["images_per_call"] * files["calls"] / 1e6, world,

@@ -399,44 +399,47 @@ __global__ void __launch_bounds__(kWindow) huffman_sync_kernel(WholeArgs a, uint
   }
 }
 
-// Step 2.  One CTA: exclusive prefix sums of the tuples, 1024 at a time.
+// Step 2.  One CTA: exclusive prefix sums of the tuples, 4096 at a time (four per thread).
+__device__ __forceinline__ int4 add4(int4 a, int4 b) { return make_int4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ int4 sub4(int4 a, int4 b) { return make_int4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+__device__ __forceinline__ int4 warp_inclusive(int4 s, uint32_t lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int x = __shfl_up_sync(0xFFFFFFFFu, s.x, d), y = __shfl_up_sync(0xFFFFFFFFu, s.y, d);
+    const int z = __shfl_up_sync(0xFFFFFFFFu, s.z, d), q = __shfl_up_sync(0xFFFFFFFFu, s.w, d);
+    if (lane >= (uint32_t)d) { s.x += x; s.y += y; s.z += z; s.w += q; }
+  }
+  return s;
+}
 __global__ void __launch_bounds__(1024) huffman_scan_kernel(WholeArgs a) {
   __shared__ int4 warp_tot[32];
   __shared__ int4 carry_s;
   const uint32_t t = threadIdx.x, lane = t & 31u, w = t >> 5;
-  if (t == 0) carry_s = make_int4(0, 0, 0, 0);
+  const int4 zero = make_int4(0, 0, 0, 0);
+  if (t == 0) carry_s = zero;
   __syncthreads();
-  for (uint32_t base = 0; base < a.nsub; base += 1024) {
-    const uint32_t i = base + t;
-    int4 v = i < a.nsub ? a.tuple[i] : make_int4(0, 0, 0, 0);
-    int4 s = v;
+  for (uint32_t base = 0; base < a.nsub; base += 4096) {
+    const uint32_t i0 = base + 4 * t;
+    int4 v[4];
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int x = __shfl_up_sync(0xFFFFFFFFu, s.x, d), y = __shfl_up_sync(0xFFFFFFFFu, s.y, d);
-      const int z = __shfl_up_sync(0xFFFFFFFFu, s.z, d), q = __shfl_up_sync(0xFFFFFFFFu, s.w, d);
-      if (lane >= (uint32_t)d) { s.x += x; s.y += y; s.z += z; s.w += q; }
-    }
+    for (int k = 0; k < 4; k++) v[k] = i0 + k < a.nsub ? a.tuple[i0 + k] : zero;
+    const int4 mine = add4(add4(v[0], v[1]), add4(v[2], v[3]));
+    const int4 s = warp_inclusive(mine, lane);
     if (lane == 31) warp_tot[w] = s;
     __syncthreads();
     if (w == 0) {
-      int4 u = warp_tot[lane];
-      int4 r = u;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int x = __shfl_up_sync(0xFFFFFFFFu, r.x, d), y = __shfl_up_sync(0xFFFFFFFFu, r.y, d);
-        const int z = __shfl_up_sync(0xFFFFFFFFu, r.z, d), q = __shfl_up_sync(0xFFFFFFFFu, r.w, d);
-        if (lane >= (uint32_t)d) { r.x += x; r.y += y; r.z += z; r.w += q; }
-      }
-      warp_tot[lane] = make_int4(r.x - u.x, r.y - u.y, r.z - u.z, r.w - u.w);  // exclusive over the warps
+      const int4 u = warp_tot[lane];
+      warp_tot[lane] = sub4(warp_inclusive(u, lane), u);  // exclusive over the warps
     }
     __syncthreads();
-    const int4 wo = warp_tot[w], cy = carry_s;
-    // exclusive: everything before element i
-    const int4 ex = make_int4(cy.x + wo.x + s.x - v.x, cy.y + wo.y + s.y - v.y, cy.z + wo.z + s.z - v.z,
-                              cy.w + wo.w + s.w - v.w);
-    if (i < a.nsub) a.prefix[i] = ex;
+    int4 ex = add4(add4(carry_s, warp_tot[w]), sub4(s, mine));  // everything before element i0
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (i0 + k < a.nsub) a.prefix[i0 + k] = ex;
+      ex = add4(ex, v[k]);
+    }
     __syncthreads();
-    if (t == 1023) carry_s = make_int4(ex.x + v.x, ex.y + v.y, ex.z + v.z, ex.w + v.w);
+    if (t == 1023) carry_s = ex;
     __syncthreads();
   }
 }
