@@ -111,7 +111,8 @@ def files_leg_ours(workload: str, device: int, threads: int, reps: int, pinned: 
     else:
         out = [np.empty((h, w, 3), dtype=np.uint8) for _ in range(per_call)]
     with host_api.HostBatch(devices=(device,), threads=threads) as hb:
-        _, st, stats = hb.decode(files, out)  # warm-up: contexts, pinned buffers
+        for _ in range(3):  # warm-up: every worker creates its contexts and its three jobs (pinned + device buffers)
+            _, st, stats = hb.decode(files, out)
         assert not any(st), st
         secs = 0.0
         for _ in range(reps):
@@ -290,7 +291,7 @@ def run_reference(args) -> None:
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     if not args.no_files:
-        line["files"] = files_leg_reference(args.workload, cores, 3.0)
+        line["files"] = files_leg_reference(args.workload, cores, float(os.environ.get("GIDBENCH_REFERENCE_SECONDS", 3.0)))
     print(json.dumps(line), flush=True)
 
 
@@ -463,12 +464,9 @@ def run_ours(args) -> None:
     # ---- from .jpg files: host entropy decode on this rank's share of the cores + the path above ----
     files = None
     if not args.no_files:
-        # this rank's share of the cores; at most 8 workers where the device decodes the scans (baseline files):
-        # 2-4 of them saturate the device-to-host link, and past ~12 the workers' CUDA calls contend
-        # (profiles/r01f_files_thread_scaling.txt).  Progressive files are Huffman-decoded on the host cores.
+        # this rank's share of the cores (where the device decodes the scans, 2-4 workers already saturate
+        # the device-to-host link: profiles/r01f_files_thread_scaling.txt)
         share = max(1, (os.cpu_count() or 1) // world)
-        if not FILE_FORM[args.workload][0]:
-            share = min(share, 8)
         files = files_leg_ours(args.workload, local, share, 3)
         secs = w * h * files["images_per_call"] * files["calls"] / 1e6 / files["value"]
         files["value"] = sharding.whole_job_rate(w * h * files["images_per_call"] * files["calls"] / 1e6, world,

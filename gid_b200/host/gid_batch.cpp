@@ -61,10 +61,9 @@ int gidhost_batch_create(const int32_t *devices, int32_t ndevices, int32_t threa
   for (int32_t i = 0; i < ndevices; i++) b->devices.push_back(devices[i]);
   b->threads = threads > 0 ? threads : (int)std::max(1u, std::thread::hardware_concurrency());
   b->ctx.assign((size_t)b->threads, nullptr);
-  // many workers: a waiting one sleeps instead of spinning on a core another worker needs
-  const char *env = getenv("GIDHOST_BLOCKING_WAIT");
-  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-  gidcuda_set_option("blocking_wait", env ? atoi(env) : ((unsigned)b->threads * 2 > hw ? 1 : 0));
+  // GIDHOST_BLOCKING_WAIT=1: a waiting worker sleeps instead of spinning.  (Measured on 16 cores with 16
+  // workers: spinning 16.2 GP/s, sleeping 14.4 GP/s on 1080p files -- so spinning stays the default.)
+  if (const char *env = getenv("GIDHOST_BLOCKING_WAIT")) gidcuda_set_option("blocking_wait", atoi(env));
   *batch = b;
   return 0;
 }

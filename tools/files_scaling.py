@@ -24,7 +24,8 @@ for wl in (sys.argv[1:] or ["cfg3"]):
     ncpu = os.cpu_count() or 1
     while True:
         with host_api.HostBatch(devices=(0,), threads=T) as hb:
-            hb.decode(files, out)
+            for _ in range(3):  # warm-up: contexts, three jobs per worker
+                hb.decode(files, out)
             c0 = [host_api.counter(k) for k in ("device_scans", "device_scan_fallbacks")]
             _, st, stats = hb.decode(files, out)
             c1 = [host_api.counter(k) for k in ("device_scans", "device_scan_fallbacks")]

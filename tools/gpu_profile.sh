@@ -17,4 +17,8 @@ for w in $wl; do
   ncu --set full --clock-control none --import-source on -k regex:recon -s 6 -c 1 -f -o $out/${tag}_full_$w \
       python bench.py --workload $w --steps 4 --warmup 3 --no-cpu --streams 1 > $out/${tag}_full_$w.log 2>&1 || tail -3 $out/${tag}_full_$w.log
 done
+# the .jpg-files leg: host-thread scaling, and one full capture of each device Huffman kernel
+python tools/files_scaling.py cfg3 cfg2 cfg4 cfg1 cfg5 2>&1 | grep -v "^$" > $out/${tag}_files_thread_scaling.txt; cat $out/${tag}_files_thread_scaling.txt
+ncu --set full --clock-control none --import-source on -k regex:huffman -c 4 -f -o $out/${tag}_full_huffman \
+    python tools/files_once.py cfg3 1 1 > $out/${tag}_full_huffman.log 2>&1 || tail -3 $out/${tag}_full_huffman.log
 ls -la $out | grep ${tag}_ | head -40
