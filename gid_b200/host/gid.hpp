@@ -103,6 +103,10 @@ struct Image_Descriptor {
   // Streams the device decoder declines (damaged or unusual ones) are decoded on the host as
   // before, so results and error behaviour do not depend on this switch.
   bool device_entropy = true;
+  // Progressive scans (without restart markers) are read through the 64-bit bit buffer; false =
+  // through the byte-wise one that mirrors the reference's.  Same planes, same stream position
+  // afterwards, same exceptions (tests compare the two on damaged files).
+  bool wide_bit_buffer = true;
   size_t stream_pos_after_header = 0;  // where Load_Image_Contents starts reading
 };
 

@@ -40,6 +40,7 @@ typedef struct gidhost_batch_stats {
 
 int gidhost_status_of_current_exception(char *err, size_t errlen);  // gid_jpeg_host.cpp
 int gidhost_option_device_entropy(void);
+int gidhost_option_sparse_input(void);
 
 // Frames a worker keeps in flight: while it prepares frame k (header, entropy decode or -- when the
 // device decodes the scan -- just finding the scan's end), frames k - 1 and k - 2 cross the link and
@@ -162,6 +163,7 @@ int gidhost_batch_decode(gidhost_batch *b, int32_t n, const uint8_t *const *data
         im.device = dev;
         im.entropy_threads = per_image;
         im.device_entropy = gidhost_option_device_entropy() != 0;
+        im.sparse_input = gidhost_option_sparse_input() != 0;
         if ((size_t)3 * (size_t)im.width * (size_t)im.height > rgb_capacity[i])
           throw gid::gid_error("output buffer too small");
         cur.index = i;

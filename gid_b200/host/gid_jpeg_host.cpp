@@ -90,6 +90,7 @@ void decode_planes(Image_Descriptor &image, gidcuda_frame_desc *desc, int16_t *p
   const std::function<void(int)> no_feedback = [](int) {};
   Decoder dec(image, no_feedback);
   dec.parallel_threads = image.entropy_threads > 0 ? image.entropy_threads : (int)std::max(1u, std::thread::hardware_concurrency());
+  dec.wide_progressive = image.wide_bit_buffer;
   dec.begin_frame = [&]() {
     fill_tables(image, desc, comp_of);
     for (int c = 0; c < 3; c++)
@@ -135,8 +136,13 @@ static bool compact_plane(const PlaneRef &pl, int h, int v, uint32_t *first, uin
     const int16_t *blk = pl.block(bx, by);
     first[seq] = (uint32_t)n;
     if (n + 64 > cap) return false;
-    for (int i = 0; i < 64; i++)
-      if (blk[i] != 0) rec[n++] = ((uint32_t)(uint16_t)blk[i] << 16) | (uint32_t)i;
+    for (int i = 0; i < 64; i += 4) {  // four coefficients at a time: most groups are empty
+      uint64_t four;
+      memcpy(&four, blk + i, 8);
+      if (four == 0) continue;
+      for (int k = i; k < i + 4; k++)
+        if (blk[k] != 0) rec[n++] = ((uint32_t)(uint16_t)blk[k] << 16) | (uint32_t)k;
+    }
   }
   first[nb] = (uint32_t)n;
   *count = n;
@@ -165,6 +171,7 @@ void *decode_and_submit(Image_Descriptor &image, void *ctx_, const std::function
   // every DQT has been read by then (GID accepts none after entropy-coded data).
   Decoder dec(image, feedback);
   dec.parallel_threads = resolve_threads(image.entropy_threads);
+  dec.wide_progressive = image.wide_bit_buffer;
   auto use_job_plane = [&](int c) {
     int32_t bx = 0, by = 0;
     dec.plane[c].base = gidcuda_job_plane(job, comp_of[c], &bx, &by);
@@ -424,9 +431,14 @@ int gidhost_probe(const uint8_t *data, size_t len, int32_t *width, int32_t *heig
 static int g_sparse_input = 1;
 static int g_entropy_threads = 1;
 static int g_device_entropy = 1;
+static int g_wide_bit_buffer = 1;  // "wide_bit_buffer": Image_Descriptor::wide_bit_buffer
 int gidhost_set_option(const char *name, int value) {
   if (name && strcmp(name, "sparse_input") == 0) {
     g_sparse_input = value != 0;
+    return GIDHOST_OK;
+  }
+  if (name && strcmp(name, "wide_bit_buffer") == 0) {
+    g_wide_bit_buffer = value != 0;
     return GIDHOST_OK;
   }
   if (name && strcmp(name, "device_entropy") == 0) {
@@ -451,6 +463,7 @@ int gidhost_decode_rgb(const uint8_t *data, size_t len, int device, uint32_t mod
     im.sparse_input = g_sparse_input != 0;
     im.entropy_threads = g_entropy_threads;
     im.device_entropy = g_device_entropy != 0;
+    im.wide_bit_buffer = g_wide_bit_buffer != 0;
     const int W = gid::Pixel_Width(im), H = gid::Pixel_Height(im);
     if ((size_t)3 * (size_t)W * (size_t)H > rgb_capacity) {
       if (err && errlen) snprintf(err, errlen, "output buffer too small");
@@ -496,6 +509,7 @@ int gidhost_decode_planes(const uint8_t *data, size_t len, gidcuda_frame_desc *d
     gid::Image_Descriptor im;
     gid::Load_Image_Header(im, st);
     im.entropy_threads = g_entropy_threads;
+    im.wide_bit_buffer = g_wide_bit_buffer != 0;
     gid::detail::decode_planes(im, desc, planes, blocks_x, blocks_y);
     return GIDHOST_OK;
   } catch (...) {
@@ -509,6 +523,7 @@ void gidhost_free(void *p) { free(p); }
 // (for gid_batch.cpp) status code + message of the exception being handled
 int gidhost_status_of_current_exception(char *err, size_t errlen) { return status_of_exception(err, errlen); }
 int gidhost_option_device_entropy(void) { return g_device_entropy; }
+int gidhost_option_sparse_input(void) { return g_sparse_input; }
 
 // Process-wide counters: "parallel_scans" (baseline scans decoded restart-interval-parallel),
 // "parallel_fallbacks" (parallel attempts that handed the scan back to the serial loop).

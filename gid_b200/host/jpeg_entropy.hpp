@@ -341,8 +341,15 @@ struct WideBits {
   int len = 0, pad = 0;
   uint8_t memo_marker = 0, bad = 0;
   bool stopped = false;
+  // Progressive scans: the segment loop carries on where the reference's byte-wise buffer stopped
+  // reading.  With `track` set the wide buffer follows that buffer's fill level (it loads a byte
+  // whenever it holds fewer bits than are asked for, :622-690) and counts the bytes it would
+  // have loaded; reference_position() turns the count into a stream position.
+  bool track = false;
+  int ref_len = 0;
+  size_t ref_loaded = 0;
   WideBits(const uint8_t *d, size_t p, size_t n) : data(d), pos(p), size(n) {}
-  void reset() { buf = 0; len = 0; pad = 0; memo_marker = 0; bad = 0; stopped = false; }
+  void reset() { buf = 0; len = 0; pad = 0; memo_marker = 0; bad = 0; stopped = false; ref_len = 0; ref_loaded = 0; }
   int real() const { return len - pad; }
   void refill() {
     if (!stopped && len <= 32 && pos + 8 <= size) {  // eight bytes at once when none of them is FF
@@ -382,6 +389,8 @@ struct WideBits {
   }
   // the decoder is about to look at n bits: raise what the byte-wise buffer would raise there
   void need(int n) {
+    if (track)
+      while (ref_len < n) { ref_len += 8; ref_loaded++; }
     if (len < n) refill();
     if (bad && n > real())
       throw error_in_image_data(fmt("JPEG: Invalid marker within filling of bit buffer: 16#%02X#", bad));
@@ -390,7 +399,24 @@ struct WideBits {
   void drop(int n) {
     buf <<= n;
     len -= n;
+    ref_len -= n;
     if (pad > len) pad = len;
+  }
+  // Where the byte-wise buffer would stand after the same requests, the scan having begun at
+  // `start`: the stream position after the ref_loaded-th data byte (FF 00 counts as one), or just
+  // past the first marker when it would have run into it (*marker = that marker, else 0).
+  size_t reference_position(size_t start, uint8_t *marker) const {
+    size_t i = start, count = 0;
+    *marker = 0;
+    while (count < ref_loaded && i < size) {
+      const uint8_t b = data[i++];
+      if (b == 0xFF) {
+        const uint8_t m = i < size ? data[i++] : (uint8_t)M_EOI;
+        if (m != 0) { *marker = m; break; }
+      }
+      count++;
+    }
+    return i;
   }
   int get(int n) {  // n = 0 .. 16
     if (n == 0) return 0;
@@ -588,6 +614,7 @@ struct Decoder {
   struct Run { size_t begin[3] = {0, 0, 0}, count[3] = {0, 0, 0}; };
   std::vector<Run> runs;  // one per worker after a successful parallel scan, else empty
   int parallel_threads = 1;
+  bool wide_progressive = true;  // false: progressive scans through the byte-wise buffer (tests compare the two)
 
   // Where the restart intervals of the scan at r.s.pos begin and end: interval k runs from the
   // byte after RSTk-1 to the FF of RSTk (the last one to the marker that ends the scan, or to the
@@ -850,15 +877,15 @@ struct Decoder {
 
   // ---- progressive (:1243-1747; ITU T.81 annex G) ----
 
-  void dc_first(int c, int16_t *blk, int al) {
+  template <class B> void dc_first(B &bits, int c, int16_t *blk, int al) {
     const int s = bits.symbol(table(0, ht_dc[c]));
     dc_pred[c] += bits.receive_extend(s & 15);
     blk[0] = (int16_t)(dc_pred[c] * (1 << al));
   }
-  void dc_refine(int16_t *blk, int al) {
+  template <class B> void dc_refine(B &bits, int16_t *blk, int al) {
     if (bits.get(1)) blk[0] = (int16_t)(blk[0] | (1 << al));
   }
-  void ac_first(int c, int16_t *blk, int ss, int se, int al) {
+  template <class B> void ac_first(B &bits, int c, int16_t *blk, int ss, int se, int al) {
     if (eobrun > 0) { eobrun--; return; }
     const HuffTable &ac = table(1, ht_ac[c]);
     for (int k = ss; k <= se;) {
@@ -880,7 +907,7 @@ struct Decoder {
       }
     }
   }
-  void ac_refine(int c, int16_t *blk, int ss, int se, int al) {
+  template <class B> void ac_refine(B &bits, int c, int16_t *blk, int ss, int se, int al) {
     const int p1 = 1 << al, m1 = -(1 << al);
     int k = ss;
     if (eobrun <= 0) {
@@ -927,6 +954,24 @@ struct Decoder {
   }
 
   void progressive_scan(const int *comps, int ncomps, int ss, int se, int ah, int al) {
+    // Without restart markers the scan is read through the 64-bit buffer; afterwards the stream
+    // position and the remembered marker are set to what the byte-wise buffer would have left
+    // behind, so that the segment loop (and its errors on damaged files) carry on identically.
+    if (wide_progressive && im.restart_interval == 0) {
+      const size_t start = r.s.pos;
+      WideBits wb(r.s.data, start, r.s.size);
+      wb.track = true;
+      progressive_scan_with(wb, comps, ncomps, ss, se, ah, al);
+      uint8_t marker = 0;
+      r.s.pos = wb.reference_position(start, &marker);
+      bits.memo_marker = marker;
+      return;
+    }
+    progressive_scan_with(bits, comps, ncomps, ss, se, ah, al);
+  }
+
+  template <class B>
+  void progressive_scan_with(B &bits, const int *comps, int ncomps, int ss, int se, int ah, int al) {
     if (ss > se || se > 63) throw error_in_image_data("JPEG: progressive: bad spectral selection");
     if (ss == 0 && se != 0) throw error_in_image_data("JPEG: progressive: DC and AC in the same scan");
     if (ss > 0 && ncomps != 1) throw error_in_image_data("JPEG: progressive: AC scan with several components");
@@ -944,8 +989,8 @@ struct Decoder {
             for (int sy = 0; sy < ci.samples_ver; sy++)
               for (int sx = 0; sx < ci.samples_hor; sx++) {
                 int16_t *blk = plane[c].block(mx * ci.samples_hor + sx, my * ci.samples_ver + sy);
-                if (ah == 0) dc_first(c, blk, al);
-                else dc_refine(blk, al);
+                if (ah == 0) dc_first(bits, c, blk, al);
+                else dc_refine(bits, blk, al);
               }
           }
           if (!(my == mcu_count_image_v - 1 && mx == mcu_count_image_h - 1)) check_restart(true);
@@ -964,12 +1009,12 @@ struct Decoder {
       for (int bx = 0; bx < bw; bx++) {
         int16_t *blk = plane[c].block(bx, by);
         if (ss == 0) {
-          if (ah == 0) dc_first(c, blk, al);
-          else dc_refine(blk, al);
+          if (ah == 0) dc_first(bits, c, blk, al);
+          else dc_refine(bits, blk, al);
         } else if (ah == 0) {
-          ac_first(c, blk, ss, se, al);
+          ac_first(bits, c, blk, ss, se, al);
         } else {
-          ac_refine(c, blk, ss, se, al);
+          ac_refine(bits, c, blk, ss, se, al);
         }
         if (!(by == bh - 1 && bx == bw - 1)) check_restart(true);
       }

@@ -514,3 +514,62 @@ def test_device_entropy_decode_noise_and_damage_without_restart_markers(host, or
         finally:
             host.set_option("device_entropy", 1)
         assert outcome() == want, t
+
+
+@pytest.mark.gpu
+def test_configs_full_size_from_files(host, oracle, synth, gpu):
+    """The five BASELINE.json configs at their full frame size as .jpg files through the file batch
+    driver: device Huffman decoding (self-synchronising for configs 1-3, restart-interval-parallel for
+    config 4), host Huffman decoding for the progressive config 5; every image == GID's decode."""
+    from tests.test_gpu_parity import FULL_SIZE
+    files, refs = [], []
+    for name, w, h, samp, prog, ri in FULL_SIZE:
+        jpg, _ = synth.encode(pixels_for(synth, 78, w, h, samp), samp, progressive=prog, restart_interval=ri)
+        files.append(jpg)
+        refs.append(oracle.decode(jpg)[1])
+    scans, back = host.counter("device_scans"), host.counter("device_scan_fallbacks")
+    imgs, st, stats = host.decode_batch(files, devices=(0,), threads=3)
+    assert st == [0] * 5 and stats.images_failed == 0
+    assert host.counter("device_scans") == scans + 4 and host.counter("device_scan_fallbacks") == back
+    for k, (img, ref) in enumerate(zip(imgs, refs)):
+        assert np.array_equal(img, ref), FULL_SIZE[k][0]
+
+
+def test_progressive_scans_through_the_wide_bit_buffer(host, oracle, synth):
+    """Progressive scans are read through the 64-bit buffer, which afterwards puts the stream where
+    the reference's byte-wise buffer would have stopped: on valid files the planes are GID's
+    (oracle); on damaged files the outcome -- planes or exception class -- is that of the byte-wise
+    reader, whatever the segment loop meets next."""
+    rng = np.random.default_rng(2)
+    same = 0
+    for samp, w, h in (("420", 161, 99), ("422", 256, 192), ("444", 120, 88), ("grey", 200, 150)):
+        jpg, enc = synth.encode(pixels_for(synth, 3, w, h, samp), samp, progressive=True)
+        _, planes = host.decode_planes(jpg)
+        fr, _, _ = oracle.decode(jpg)
+        for c in range(fr.ncomp):
+            assert np.array_equal(planes[c], fr.planes[c]) and np.array_equal(planes[c], enc.planes[c])
+        sos = jpg.index(b"\xff\xda")
+        for t in range(60):
+            bad = bytearray(jpg)
+            pos = int(rng.integers(sos + 10, len(bad) - 2))
+            kind = t % 5
+            if kind == 0:
+                bad[pos] = int(rng.integers(0, 256))
+            elif kind == 1:
+                del bad[pos]
+            elif kind == 2:
+                bad.insert(pos, int(rng.integers(0, 256)))
+            elif kind == 3:
+                del bad[pos:pos + int(rng.integers(2, 40))]
+            else:
+                for _ in range(3):
+                    bad.insert(pos, int(rng.integers(0, 255)))
+            bad = bytes(bad)
+            host.set_option("wide_bit_buffer", 0)
+            try:
+                want = _outcome(host, bad)
+            finally:
+                host.set_option("wide_bit_buffer", 1)
+            assert _outcome(host, bad) == want, (samp, t)
+            same += 1
+    assert same == 240

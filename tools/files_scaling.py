@@ -9,6 +9,8 @@ import numpy as np
 import bench
 from gid_b200 import host_api
 
+if os.environ.get("FILES_SPARSE_INPUT"):
+    host_api.set_option("sparse_input", int(os.environ["FILES_SPARSE_INPUT"]))
 for wl in (sys.argv[1:] or ["cfg3"]):
     w, h, _, _, _ = bench.WORKLOADS[wl]
     prog, ri, per_call = bench.FILE_FORM[wl]
