@@ -105,19 +105,21 @@ void read_dht(Image_Descriptor &im, Reader &r, int length) {  // :320-391
       remaining--;
       total += counts[i];
     }
-    // the code space must not be over-subscribed ("DHT data too short [2]")
+    // As the reference: per code length, check the bytes left in the segment ("[1]") and the code
+    // space ("[2]": over-subscribed), then read that length's symbols.
     long space = 65536, spread = 65536;
+    std::vector<uint8_t> vals;
+    vals.reserve((size_t)total);
     for (int len = 0; len < 16; len++) {
       spread /= 2;
       if (counts[len] > 0) {
         if (remaining < counts[len]) throw error_in_image_data("JPEG: DHT data too short [1]");
         space -= (long)counts[len] * spread;
         if (space < 0) throw error_in_image_data("JPEG: DHT data too short [2]");
+        for (int i = 0; i < counts[len]; i++) vals.push_back(r.byte());
+        remaining -= counts[len];
       }
     }
-    std::vector<uint8_t> vals((size_t)total);
-    for (int i = 0; i < total; i++) vals[(size_t)i] = r.byte();
-    remaining -= total;
     im.huff_bits[kind][idx] = counts;
     im.huff_vals[kind][idx] = vals;
   }
