@@ -573,3 +573,30 @@ def test_progressive_scans_through_the_wide_bit_buffer(host, oracle, synth):
             assert _outcome(host, bad) == want, (samp, t)
             same += 1
     assert same == 240
+
+
+@pytest.mark.gpu
+def test_flat_and_periodic_images_stay_exact(host, oracle, synth, gpu):
+    """Flat regions make the bit stream periodic, and a periodic stream need not re-synchronise a
+    decoder that started in the wrong phase: the device's chain of states then fails its verification
+    and the host decodes the scan.  Whichever way an image goes, the pixels are GID's."""
+    h, w = 540, 960
+    base = synth.image(3, w, h)
+    flat = np.full((h, w, 3), 128, np.uint8)
+    bars = base.copy()
+    bars[:135] = 0
+    bars[-135:] = 0
+    stripes = np.zeros((h, w, 3), np.uint8)
+    stripes[:, ::16] = 255
+    sky = base.copy()
+    sky[:200] = 255
+    cases = [("flat", flat, "420"), ("flat", flat[:, :, 0].copy(), "grey"), ("flat", flat, "444"),
+             ("black", np.zeros((h, w, 3), np.uint8), "420"), ("bars", bars, "420"), ("bars", bars, "444"),
+             ("stripes", stripes, "420"), ("sky", sky, "422")]
+    scans, back = host.counter("device_scans"), host.counter("device_scan_fallbacks")
+    for name, pix, samp in cases:
+        jpg, _ = synth.encode(pix, samp)
+        rgb, _ = host.decode_rgb(jpg)
+        assert np.array_equal(rgb, oracle.decode(jpg)[1]), (name, samp)
+    assert host.counter("device_scans") == scans + len(cases)          # every scan was offered to the device
+    assert host.counter("device_scan_fallbacks") - back <= len(cases)  # ... and some came back
