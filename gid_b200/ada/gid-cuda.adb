@@ -8,6 +8,7 @@ package body GID.CUDA is
   --  Status codes of include/gidcuda.h
   ERR_BAD_ARGUMENT  : constant := -1;
   ERR_UNSUPPORTED   : constant := -2;
+  ERR_DATA          : constant := -7;
   ERR_NO_DEVICE     : constant := -3;
   ERR_CUDA          : constant := -4;
   ERR_OUT_OF_MEMORY : constant := -5;
@@ -31,6 +32,9 @@ package body GID.CUDA is
         raise unsupported_image_subformat with "JPEG (CUDA): " & Message;
       when ERR_BAD_ARGUMENT =>
         raise error_in_image_data with "JPEG (CUDA): " & Message;
+      when ERR_DATA =>
+        --  gidcuda_job_scan: the device left the scan to the serial loop of GID.Decoding_JPG
+        raise Device_Declined with "JPEG (CUDA): " & Message;
       when others =>
         --  ERR_NO_DEVICE, ERR_CUDA, ERR_OUT_OF_MEMORY, ERR_STATE:
         --  there is deliberately no CPU fallback.
@@ -119,6 +123,62 @@ package body GID.CUDA is
              (j, C.int (comp), Interfaces.Integer_32 (runs'Length), b (0)'Access, n (0)'Access),
            Null_Context);
   end Records_Commit_Runs;
+
+  procedure Scan
+    (j : Job; desc : Scan_Desc; data : System.Address; length : Natural;
+     interval_begin, interval_end : Offset_Array)
+  is
+    d : aliased constant Scan_Desc := desc;
+  begin
+    if interval_begin'Length = 0 then
+      Check (gidcuda_job_scan (j, d'Access, data, C.size_t (length), null, null), Null_Context);
+    else
+      Check (gidcuda_job_scan
+               (j, d'Access, data, C.size_t (length),
+                interval_begin (interval_begin'First)'Access, interval_end (interval_end'First)'Access),
+             Null_Context);
+    end if;
+  end Scan;
+
+  procedure Output (j : Job; pixels : System.Address; capacity : Natural) is
+  begin
+    Check (gidcuda_job_output (j, pixels, C.size_t (capacity)), Null_Context);
+  end Output;
+
+  function Host_Alloc (bytes : Natural) return System.Address is
+    p : aliased System.Address := System.Null_Address;
+  begin
+    Check (gidcuda_host_alloc (C.size_t (bytes), p'Access), Null_Context);
+    return p;
+  end Host_Alloc;
+
+  procedure Host_Free (p : System.Address) is
+  begin
+    Check (gidcuda_host_free (p), Null_Context);
+  end Host_Free;
+
+  function Is_Pinned (p : System.Address) return Boolean is
+  begin
+    return gidcuda_host_is_pinned (p) /= 0;
+  end Is_Pinned;
+
+  procedure Plane_Geometry (desc : Frame_Desc; comp : Natural; blocks_x, blocks_y : out Natural) is
+    d : aliased constant Frame_Desc := desc;
+    bx, by : aliased Interfaces.Integer_32 := 0;
+  begin
+    Check (gidcuda_plane_geometry (d'Access, C.int (comp), bx'Access, by'Access), Null_Context);
+    blocks_x := Natural (bx);
+    blocks_y := Natural (by);
+  end Plane_Geometry;
+
+  procedure Output_Geometry (desc : Frame_Desc; stride, bytes : out Natural) is
+    d : aliased constant Frame_Desc := desc;
+    s, b : aliased C.size_t := 0;
+  begin
+    Check (gidcuda_output_geometry (d'Access, s'Access, b'Access), Null_Context);
+    stride := Natural (s);
+    bytes  := Natural (b);
+  end Output_Geometry;
 
   procedure Submit (j : Job) is
   begin

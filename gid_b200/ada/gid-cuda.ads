@@ -35,6 +35,8 @@ private package GID.CUDA is
   Null_Context : constant Context;
   Null_Job     : constant Job;
 
+  type Byte_Array is array (Natural range <>) of aliased Interfaces.Unsigned_8;
+  pragma Convention (C, Byte_Array);
   type Sampling_Array is array (0 .. 2) of aliased Interfaces.Integer_32;
   pragma Convention (C, Sampling_Array);
   type Natural_Order_Table is array (0 .. 63) of aliased Interfaces.Unsigned_16;
@@ -91,6 +93,45 @@ private package GID.CUDA is
   end record;
   type Run_Array is array (Positive range <>) of Run;
   procedure Records_Commit_Runs (j : Job; comp : Natural; runs : Run_Array);
+
+  --  Entropy decoding on the device (include/gidcuda.h, gidcuda_job_scan): instead of running
+  --  Decode_8x8_Block (:758-788) over a baseline scan, hand over its compressed bytes.
+  --    restart_interval > 0 : data = the scan's bytes as they are; interval_begin / interval_end =
+  --        where each restart interval lies (from the byte after RSTn-1 to the FF of RSTn);
+  --    restart_interval = 0 : data = the scan's bytes with the stuffing removed (FF 00 -> FF);
+  --        the two arrays are empty.
+  --  Wait then raises Device_Declined when the device met something it leaves to the serial
+  --  loop (a damaged or unusual stream): decode the scan the old way and Submit the job again.
+  Device_Declined : exception;
+  type Huffman_Table is record
+    counts  : Byte_Array (0 .. 15);    --  Read_DHT :320-391: codes of length 1 .. 16
+    symbols : Byte_Array (0 .. 255);   --  in code order
+  end record;
+  pragma Convention (C, Huffman_Table);
+  type Huffman_Table_Array is array (0 .. 2) of aliased Huffman_Table;
+  pragma Convention (C, Huffman_Table_Array);
+  type Scan_Desc is record
+    restart_interval : Interfaces.Integer_32;
+    nintervals       : Interfaces.Integer_32;
+    dc, ac           : Huffman_Table_Array;   --  per component of the frame
+  end record;
+  pragma Convention (C, Scan_Desc);
+  type Offset_Array is array (Natural range <>) of aliased Interfaces.Unsigned_32;
+  pragma Convention (C, Offset_Array);
+  procedure Scan
+    (j : Job; desc : Scan_Desc; data : System.Address; length : Natural;
+     interval_begin, interval_end : Offset_Array);
+
+  --  Let the pixels land in the client's own image buffer (pinned host memory: Host_Alloc):
+  --  no copy after the device-to-host transfer.  Between Job_Begin and Submit.
+  procedure Output (j : Job; pixels : System.Address; capacity : Natural);
+  function  Host_Alloc (bytes : Natural) return System.Address;
+  procedure Host_Free (p : System.Address);
+  function  Is_Pinned (p : System.Address) return Boolean;
+
+  --  MCU-padded block grid of a component / row stride and size of the pixel buffer
+  procedure Plane_Geometry (desc : Frame_Desc; comp : Natural; blocks_x, blocks_y : out Natural);
+  procedure Output_Geometry (desc : Frame_Desc; stride, bytes : out Natural);
 
   procedure Submit (j : Job);   --  asynchronous: H2D, kernel(s), D2H
   procedure Wait   (j : Job; pixels : out System.Address; stride : out Natural);
@@ -155,5 +196,38 @@ private
 
   function gidcuda_job_release (j : Job) return C.int;
   pragma Import (C, gidcuda_job_release, "gidcuda_job_release");
+
+  function gidcuda_job_scan
+    (j : Job; scan : access constant Scan_Desc; data : System.Address; len : C.size_t;
+     interval_begin, interval_end : access constant Interfaces.Unsigned_32) return C.int;
+  pragma Import (C, gidcuda_job_scan, "gidcuda_job_scan");
+
+  function gidcuda_job_output (j : Job; host_pixels : System.Address; capacity : C.size_t) return C.int;
+  pragma Import (C, gidcuda_job_output, "gidcuda_job_output");
+
+  function gidcuda_host_alloc (bytes : C.size_t; ptr : access System.Address) return C.int;
+  pragma Import (C, gidcuda_host_alloc, "gidcuda_host_alloc");
+  function gidcuda_host_free (ptr : System.Address) return C.int;
+  pragma Import (C, gidcuda_host_free, "gidcuda_host_free");
+  function gidcuda_host_is_pinned (ptr : System.Address) return C.int;
+  pragma Import (C, gidcuda_host_is_pinned, "gidcuda_host_is_pinned");
+
+  function gidcuda_plane_geometry
+    (desc : access constant Frame_Desc; comp : C.int;
+     blocks_x, blocks_y : access Interfaces.Integer_32) return C.int;
+  pragma Import (C, gidcuda_plane_geometry, "gidcuda_plane_geometry");
+  function gidcuda_output_geometry
+    (desc : access constant Frame_Desc; stride, bytes : access C.size_t) return C.int;
+  pragma Import (C, gidcuda_output_geometry, "gidcuda_output_geometry");
+
+  function gidcuda_abi_version return C.int;
+  pragma Import (C, gidcuda_abi_version, "gidcuda_abi_version");
+  function gidcuda_set_option (name : C.Strings.chars_ptr; value : C.int) return C.int;
+  pragma Import (C, gidcuda_set_option, "gidcuda_set_option");
+  function gidcuda_synchronize (ctx : Context) return C.int;
+  pragma Import (C, gidcuda_synchronize, "gidcuda_synchronize");
+
+  --  gidcuda_plan_* (planes already in device memory) and gidcuda_batch_* (many frames, all GPUs of
+  --  a box) serve callers other than GID.Decoding_JPG and are not bound here.
 
 end GID.CUDA;

@@ -236,6 +236,76 @@
     end Baseline_DCT_Decoding_Scan;
 
     ------------------------------------------------------------------
+    --  OPTIONAL: Huffman decoding on the device (GID.CUDA.Scan = gidcuda_job_scan).
+    --  Called first by Baseline_DCT_Decoding_Scan; when it returns False, or when the
+    --  later Wait raises GID.CUDA.Device_Declined, the MCU loop above runs as before
+    --  (the stream is rewound to scan_start; GID.Buffering needs a Set_Index for that,
+    --  or the scan's bytes are kept in scan_bytes and re-read from there).
+    --    * the scan's bytes are read up to the marker that ends it (Get_Byte; FF 00 is
+    --      data, FF D0 .. D7 an RSTn, any other FF xx the end);
+    --    * with restart intervals: interval k runs from the byte after RSTk-1 to the FF
+    --      of RSTk; the bytes go over as they are;
+    --    * without: the stuffing is removed (FF 00 -> FF) and the device's
+    --      self-synchronising decoder takes the whole scan.
+    ------------------------------------------------------------------
+    function Baseline_Scan_On_Device return Boolean is
+      scan_bytes : Byte_Vector;          --  (an unbounded array of U8 filled below)
+      first, last : Offset_Vector;       --  restart intervals, offsets into scan_bytes
+      desc : GID.CUDA.Scan_Desc;
+      b : U8;
+      ri : constant Natural := image.JPEG_stuff.restart_interval;
+    begin
+      if ri > 0 then
+        first.Append (0);
+      end if;
+      Read_Scan :
+      loop
+        Get_Byte (image.buffer, b);
+        if b = 16#FF# then
+          Get_Byte (image.buffer, b);
+          if b = 0 then
+            scan_bytes.Append (16#FF#);
+            if ri > 0 then
+              scan_bytes.Append (0);     --  intervals travel with their stuffing
+            end if;
+          elsif b in 16#D0# .. 16#D7# and then ri > 0 then
+            last.Append (scan_bytes.Length);
+            scan_bytes.Append (16#FF#);
+            scan_bytes.Append (b);
+            first.Append (scan_bytes.Length);
+          else
+            memo_marker := b;            --  the segment loop carries on from this marker (:2043-2118)
+            exit Read_Scan;
+          end if;
+        else
+          scan_bytes.Append (b);
+        end if;
+      end loop Read_Scan;
+      if ri > 0 then
+        last.Append (scan_bytes.Length);
+        if Natural (first.Length) /= (mcu_count_image_h * mcu_count_image_v + ri - 1) / ri
+          or else Natural (first.Length) < 64
+        then
+          return False;                  --  not what the geometry needs, or too few streams for a GPU
+        end if;
+      end if;
+      desc.restart_interval := Interfaces.Integer_32 (ri);
+      desc.nintervals := Interfaces.Integer_32 (first.Length);
+      for c in Component loop
+        if image.JPEG_stuff.compo_set (c) then
+          --  counts and symbols of the tables the scan header selected (Read_DHT keeps them
+          --  beside the 65 536-entry VLC tables it builds, :320-391)
+          desc.dc (Component'Pos (c)) := Raw_Table (DC, info_B (c).ht_idx_DC);
+          desc.ac (Component'Pos (c)) := Raw_Table (AC, info_B (c).ht_idx_AC);
+        end if;
+      end loop;
+      GID.CUDA.Scan
+        (cuda_job, desc, scan_bytes.Address, Natural (scan_bytes.Length),
+         To_Offset_Array (first), To_Offset_Array (last));
+      return True;
+    end Baseline_Scan_On_Device;
+
+    ------------------------------------------------------------------
     --  Progressive files: every image_array (x, y, c_idx) access in
     --  Progressive_DCT_Decoding_Scan (:1263-1690) becomes an access to the int16
     --  plane cell  Coefficient_Address (c, x / 8, y / 8, 8 * (y mod 8) + x mod 8)
