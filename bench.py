@@ -528,7 +528,7 @@ def main() -> None:
                     help="host-side form of the coefficients in the end-to-end leg: sparse records (what an entropy "
                          "decoder emits) or dense int16 planes")
     ap.add_argument("--e2e-depth", type=int, default=3, help="jobs in flight in the end-to-end leg")
-    ap.add_argument("--streams", type=int, default=2, choices=[1, 2],
+    ap.add_argument("--streams", type=int, default=2, choices=[1, 2, 4],
                     help="launch streams for the device-resident leg (2: consecutive frames overlap tail and ramp)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
