@@ -20,6 +20,15 @@
 // the error behaviour of the reference is reproduced exactly.
 #include "recon_launch.h"
 
+// -DGIDK_CHECKED: device-side assertions on every coefficient address and table index (a debug
+// build for the GPU test suite; compute-sanitizer is not available on the test pool).
+#if defined(GIDK_CHECKED)
+#include <cassert>
+#define GIDK_ASSERT(c) assert(c)
+#else
+#define GIDK_ASSERT(c) ((void)0)
+#endif
+
 namespace gidk {
 
 namespace {
@@ -98,6 +107,7 @@ __device__ __forceinline__ bool decode_block(Bits &b, const HuffDev &dc, const H
     coef += (code >> 4) + 1;
     if (coef > 63) return false;
     if (m) {
+      GIDK_ASSERT(coef >= 1 && coef <= 63 && zz[coef] < 64);
       blk[zz[coef]] = (int16_t)extend(b.peek(m), m);
       b.drop(m);
     }
@@ -134,7 +144,9 @@ __global__ void __launch_bounds__(128) huffman_intervals_kernel(ScanArgs a) {
     for (int c = 0; c < 3; c++)  // (unrolled: a run-time index into the kernel parameters would put them in local memory)
       for (int sy = 0; c < a.ncomp && sy < a.v[c] && ok; sy++)
         for (int sx = 0; sx < a.h[c] && ok; sx++) {
-          int16_t *blk = a.plane[c] + ((size_t)(my * a.v[c] + sy) * a.bx[c] + (mx * a.h[c] + sx)) * 64;
+          const size_t blockno = (size_t)(my * a.v[c] + sy) * a.bx[c] + (mx * a.h[c] + sx);
+          GIDK_ASSERT(blockno < (size_t)a.bx[c] * a.v[c] * ((a.nmcu + a.mcux - 1) / a.mcux));
+          int16_t *blk = a.plane[c] + blockno * 64;
           ok = decode_block(b, tabs[c], tabs[3 + c], pred[c], blk, zz);
         }
   }
@@ -203,6 +215,7 @@ struct RawBits {  // no stuffing, no end: the buffer is padded with FF bytes pas
     len = 64 - (int)(bitpos & 31u);
   }
   __device__ __forceinline__ void refill() {  // call when len <= 32
+    GIDK_ASSERT(len >= 0 && len <= 32);
     buf |= (uint64_t)be(__ldg(w++)) << (32 - len);
     len += 32;
   }
@@ -243,13 +256,17 @@ __device__ __forceinline__ uint64_t run_subsequence(const WholeArgs &a, const Hu
   auto block_ptr = [&](uint32_t blockno, uint32_t cc) -> int16_t * {
     const uint32_t mcu = (blockno - cc) / a.bpm;
     const uint32_t my = mcu / a.mcux, mx = mcu - my * a.mcux;
+    GIDK_ASSERT(cc < a.bpm && blockno >= cc && blockno < a.total_blocks);
     const BlockSlot &q = slots[cc];
-    return q.plane + ((size_t)(my * q.v + q.sy) * q.row_blocks + (mx * q.h + q.sx)) * 64;
+    const size_t at = (size_t)(my * q.v + q.sy) * q.row_blocks + (mx * q.h + q.sx);
+    GIDK_ASSERT(mx < a.mcux && at < (size_t)q.row_blocks * q.v * (a.total_blocks / a.bpm / a.mcux));
+    return q.plane + at * 64;
   };
   if (FINAL) blk = block_ptr(b, c);
   while (pos < limit) {
     if (FINAL && b >= a.total_blocks) break;
     if (bits.len <= 32) bits.refill();
+    GIDK_ASSERT(c < a.bpm && zpos < 64 && pos < a.nbits);
     const int k = (int)slots[c].comp;
     const HuffDev &t = zpos == 0 ? tabs[k] : tabs[3 + k];
     const uint32_t look = bits.peek(16);
@@ -302,6 +319,7 @@ __device__ __forceinline__ uint64_t run_subsequence(const WholeArgs &a, const Hu
         const int v = extend(bits.peek(n), n);
         bits.drop(n);
         pos += (uint32_t)n;
+        GIDK_ASSERT(!FINAL || (idx >= 1 && idx <= 63));
         if (FINAL) blk[zz[idx & 63u]] = (int16_t)v;
       }
       if (idx >= 63) block_done = true;
