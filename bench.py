@@ -364,14 +364,16 @@ def run_ours(args) -> None:
     extra = [torch.cuda.Stream(device=dev) for _ in range(nstreams - 1)]
     streams = [tstream] + extra
 
-    def launch_steps(n: int) -> None:
+    def launch_steps(n: int, use: int = 0) -> None:
+        """n steps over the first `use` launch streams (0 = all of them)."""
+        k = use or nstreams
         fork = torch.cuda.Event()
         fork.record(tstream)
-        for st in extra:
+        for st in extra[:k - 1]:
             st.wait_event(fork)
         for s_ in range(n):
-            ctx.plan_launch(plans[s_ % ring], streams[s_ % nstreams].cuda_stream)
-        for st in extra:
+            ctx.plan_launch(plans[s_ % ring], streams[s_ % k].cuda_stream)
+        for st in extra[:k - 1]:
             join = torch.cuda.Event()
             join.record(st)
             tstream.wait_event(join)
@@ -392,6 +394,16 @@ def run_ours(args) -> None:
     e1.record(tstream)
     barrier()
     ms = e0.elapsed_time(e1)
+    # the same steps strictly one after the other (one stream): the kernel's own launch duration,
+    # without the overlap of one launch's tail with the next one's ramp
+    launch_steps(min(args.warmup, 5), 1)
+    torch.cuda.synchronize()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record(tstream)
+    launch_steps(args.steps, 1)
+    s1.record(tstream)
+    torch.cuda.synchronize()
+    ms_single = sharding.max_over_ranks(s0.elapsed_time(s1), dev)
     # keep the clocks under observation for at least ~0.5 s of the same work
     t_end = time.perf_counter() + 0.5
     s = 0
@@ -502,7 +514,11 @@ def run_ours(args) -> None:
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(args.workload), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes_frame * per_step},
+                         "algorithmic_bytes_per_launch": alg_bytes_frame * per_step,
+                         "launches_overlapped_on_streams": nstreams,
+                         "single_stream": {"ms_per_launch": ms_single / args.steps,
+                                           "achieved": alg_bytes_frame * per_step * args.steps / (ms_single * 1e-3) / 1e9,
+                                           "frac": alg_bytes_frame * per_step * args.steps / (ms_single * 1e-3) / 1e9 / peak}},
             "cpu_baseline": cpu,
         }
         if files is not None:

@@ -24,6 +24,7 @@ OUT_RGB8 = 0
 OUT_BGR8_BOTTOM_UP = 1
 OUT_RGBA8 = 2
 FLAG_PACKED_ROWS = 0x100
+FLAG_ROTATE_90, FLAG_ROTATE_180, FLAG_ROTATE_270 = 0x200, 0x400, 0x600  # GID.Display_Orientation applied to the pixels
 
 # every symbol include/gidcuda.h declares
 EXPORTS = [
@@ -274,8 +275,9 @@ class GidCuda:
             self._check(self.lib.gidcuda_job_submit(job), self.ctx)
             pix, stride = ctypes.c_void_p(), ctypes.c_size_t()
             self._check(self.lib.gidcuda_job_wait(job, ctypes.byref(pix), ctypes.byref(stride)), self.ctx)
-            buf = (ctypes.c_uint8 * (stride.value * desc.height)).from_address(pix.value)
-            out = np.frombuffer(buf, dtype=np.uint8).reshape(desc.height, stride.value).copy()
+            rows = desc.width if desc.flags & 0x200 else desc.height  # FLAG_ROTATE_90 / _270 swap the sides
+            buf = (ctypes.c_uint8 * (stride.value * rows)).from_address(pix.value)
+            out = np.frombuffer(buf, dtype=np.uint8).reshape(rows, stride.value).copy()
         finally:
             self._check(self.lib.gidcuda_job_release(job), self.ctx)
         return out
@@ -285,7 +287,8 @@ class GidCuda:
         """Same, cropped to (H, W, 3) -- (H, W, 4) for the RGBA format."""
         rows = self.reconstruct(desc, planes, hint_rows, sparse)
         bpp = 4 if (desc.flags & 0xFF) == OUT_RGBA8 else 3
-        return rows[:, :bpp * desc.width].reshape(desc.height, desc.width, bpp)
+        w, h = (desc.height, desc.width) if desc.flags & 0x200 else (desc.width, desc.height)
+        return rows[:, :bpp * w].reshape(h, w, bpp)
 
     # -- device-resident plans ----------------------------------------------------
     def plan_create(self, descs: Sequence[FrameDesc], d_planes: Sequence[int],

@@ -38,6 +38,7 @@ struct Geometry {
   Layout layout = LAYOUT_GENERIC;
   bool q8 = true;
   int out_format = 0;
+  int rotate = 0;  // 0, 1 = Rotation_90, 2 = Rotation_180, 3 = Rotation_270 (GIDCUDA_FLAG_ROTATE_*)
   uint32_t ntiles = 0;
 };
 
@@ -93,7 +94,9 @@ inline int make_geometry(std::string *err, const gidcuda_frame_desc *d, Geometry
   if (g->out_format != (int)GIDCUDA_OUT_RGB8 && g->out_format != (int)GIDCUDA_OUT_BGR8_BOTTOM_UP &&
       g->out_format != (int)GIDCUDA_OUT_RGBA8)
     return geo_fail(err, GIDCUDA_ERR_BAD_ARGUMENT, "unknown output format %d", g->out_format);
-  const size_t packed = (size_t)(g->out_format == (int)GIDCUDA_OUT_RGBA8 ? 4 : 3) * d->width;
+  g->rotate = (int)((d->flags & GIDCUDA_FLAG_ROTATE_MASK) >> 9);
+  const int out_w = (g->rotate & 1) ? d->height : d->width, out_h = (g->rotate & 1) ? d->width : d->height;
+  const size_t packed = (size_t)(g->out_format == (int)GIDCUDA_OUT_RGBA8 ? 4 : 3) * out_w;
   if (d->out_stride != 0) {
     if ((size_t)d->out_stride < packed)
       return geo_fail(err, GIDCUDA_ERR_BAD_ARGUMENT, "out_stride %d is smaller than a packed row", d->out_stride);
@@ -105,8 +108,10 @@ inline int make_geometry(std::string *err, const gidcuda_frame_desc *d, Geometry
   } else {
     g->stride = round_up(packed, 16);
   }
-  g->pixel_bytes = g->stride * (size_t)d->height;
-  if (d->ncomp == 1) {
+  g->pixel_bytes = g->stride * (size_t)out_h;
+  if (g->rotate != 0) {
+    g->layout = LAYOUT_GENERIC;  // the per-pixel pass applies the orientation
+  } else if (d->ncomp == 1) {
     g->layout = LAYOUT_GREY;
   } else if (d->samp_h[1] == 1 && d->samp_v[1] == 1 && d->samp_h[2] == 1 && d->samp_v[2] == 1) {
     if (d->samp_h[0] == 1 && d->samp_v[0] == 1) g->layout = LAYOUT_444;
@@ -141,7 +146,7 @@ inline void fill_frame_dev(const gidcuda_frame_desc *d, const Geometry &g, const
   f->height = d->height;
   f->mcux = g.mcux;
   f->mcuy = g.mcuy;
-  f->out_format = g.out_format;
+  f->out_format = g.out_format | (g.rotate << 8);  // (rotated frames only reach the generic kernels)
   f->tile_base = tile_base;
   f->q8 = g.q8 ? 1 : 0;
   f->flags = 0;

@@ -440,13 +440,19 @@ generic_color_kernel(const FrameDev *__restrict__ frame, int ncomp, int hmax, in
   } else {
     r = g = b = s[0];
   }
-  int yy = y;
-  if (f.out_format == OUT_BGR8_BOTTOM_UP) {
-    yy = f.height - 1 - y;
+  const int fmt = f.out_format & 0xFF, rot = (f.out_format >> 8) & 3;
+  // display orientation (GIDCUDA_FLAG_ROTATE_*, = Set_X_Y of test/to_bmp.adb:104-122): column and
+  // top-down row of the pixel in the output image, whose height is out_h
+  int ox = x, oy = y, out_h = f.height;
+  if (rot == 1) { ox = y; oy = f.width - 1 - x; out_h = f.width; }
+  else if (rot == 2) { ox = f.width - 1 - x; oy = f.height - 1 - y; }
+  else if (rot == 3) { ox = f.height - 1 - y; oy = x; out_h = f.width; }
+  if (fmt == OUT_BGR8_BOTTOM_UP) {
+    oy = out_h - 1 - oy;
     const int t = r; r = b; b = t;
   }
-  const bool rgba = f.out_format == OUT_RGBA8;
-  uint8_t *dst = f.pixels + (size_t)yy * f.stride + (size_t)x * (rgba ? 4 : 3);
+  const bool rgba = fmt == OUT_RGBA8;
+  uint8_t *dst = f.pixels + (size_t)oy * f.stride + (size_t)ox * (rgba ? 4 : 3);
   dst[0] = (uint8_t)r;
   dst[1] = (uint8_t)g;
   dst[2] = (uint8_t)b;

@@ -107,6 +107,10 @@ struct Image_Descriptor {
   // through the byte-wise one that mirrors the reference's.  Same planes, same stream position
   // afterwards, same exceptions (tests compare the two on damaged files).
   bool wide_bit_buffer = true;
+  // The file batch driver only (Load_Image_Contents leaves the orientation to the client's Set_X_Y, as
+  // GID does): write the pixels turned as Display_Orientation says (GIDCUDA_FLAG_ROTATE_*), so that
+  // the caller's buffer holds the image as it is to be displayed -- H x W for Rotation_90 / _270.
+  bool apply_orientation = false;
   size_t stream_pos_after_header = 0;  // where Load_Image_Contents starts reading
 };
 

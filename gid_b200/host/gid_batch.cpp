@@ -41,6 +41,7 @@ typedef struct gidhost_batch_stats {
 int gidhost_status_of_current_exception(char *err, size_t errlen);  // gid_jpeg_host.cpp
 int gidhost_option_device_entropy(void);
 int gidhost_option_sparse_input(void);
+int gidhost_option_apply_orientation(void);
 
 // Frames a worker keeps in flight: while it prepares frame k (header, entropy decode or -- when the
 // device decodes the scan -- just finding the scan's end), frames k - 1 and k - 2 cross the link and
@@ -134,7 +135,9 @@ int gidhost_batch_decode(gidhost_batch *b, int32_t n, const uint8_t *const *data
         size_t stride = 0;
         uint8_t *out = rgb[f.index];
         const uint8_t *px = gid::detail::wait_pixels(*f.im, ctx, &f.job, &stride, out, rgb_capacity[f.index]);
-        const int fw = f.im->width, fh = f.im->height;
+        const bool turned = f.im->apply_orientation && (f.im->display_orientation == gid::Orientation::Rotation_90 ||
+                                                        f.im->display_orientation == gid::Orientation::Rotation_270);
+        const int fw = turned ? f.im->height : f.im->width, fh = turned ? f.im->width : f.im->height;
         const size_t row = (size_t)3 * (size_t)fw;
         if (px == out) {
           // the caller's buffer is pinned: the pixels arrived there straight from the device
@@ -164,6 +167,7 @@ int gidhost_batch_decode(gidhost_batch *b, int32_t n, const uint8_t *const *data
         im.entropy_threads = per_image;
         im.device_entropy = gidhost_option_device_entropy() != 0;
         im.sparse_input = gidhost_option_sparse_input() != 0;
+        im.apply_orientation = gidhost_option_apply_orientation() != 0;
         if ((size_t)3 * (size_t)im.width * (size_t)im.height > rgb_capacity[i])
           throw gid::gid_error("output buffer too small");
         cur.index = i;

@@ -70,6 +70,12 @@ static void describe_frame(const Image_Descriptor &image, gidcuda_frame_desc *de
     }
   desc->ncomp = idx;
   desc->flags = GIDCUDA_OUT_RGB8 | GIDCUDA_FLAG_PACKED_ROWS;
+  if (image.apply_orientation) switch (image.display_orientation) {
+      case Orientation::Rotation_90: desc->flags |= GIDCUDA_FLAG_ROTATE_90; break;
+      case Orientation::Rotation_180: desc->flags |= GIDCUDA_FLAG_ROTATE_180; break;
+      case Orientation::Rotation_270: desc->flags |= GIDCUDA_FLAG_ROTATE_270; break;
+      default: break;
+    }
 }
 
 // natural-order tables, as Finalize_Progressive_DCT_Decoding builds qt_zz (:1771-1775)
@@ -432,9 +438,14 @@ static int g_sparse_input = 1;
 static int g_entropy_threads = 1;
 static int g_device_entropy = 1;
 static int g_wide_bit_buffer = 1;  // "wide_bit_buffer": Image_Descriptor::wide_bit_buffer
+static int g_apply_orientation = 0;  // "apply_orientation": gidhost_batch_decode writes the pixels turned as the EXIF tag says
 int gidhost_set_option(const char *name, int value) {
   if (name && strcmp(name, "sparse_input") == 0) {
     g_sparse_input = value != 0;
+    return GIDHOST_OK;
+  }
+  if (name && strcmp(name, "apply_orientation") == 0) {
+    g_apply_orientation = value != 0;
     return GIDHOST_OK;
   }
   if (name && strcmp(name, "wide_bit_buffer") == 0) {
@@ -524,6 +535,7 @@ void gidhost_free(void *p) { free(p); }
 int gidhost_status_of_current_exception(char *err, size_t errlen) { return status_of_exception(err, errlen); }
 int gidhost_option_device_entropy(void) { return g_device_entropy; }
 int gidhost_option_sparse_input(void) { return g_sparse_input; }
+int gidhost_option_apply_orientation(void) { return g_apply_orientation; }
 
 // Process-wide counters: "parallel_scans" (baseline scans decoded restart-interval-parallel),
 // "parallel_fallbacks" (parallel attempts that handed the scan back to the serial loop).

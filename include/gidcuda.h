@@ -60,6 +60,20 @@ enum {
 /* Force stride = 3 * width (no row padding) for RGB8 even when that makes rows
  * unaligned; the default stride is the packed row (3 or 4 bytes per pixel) rounded up to 16 bytes. */
 #define GIDCUDA_FLAG_PACKED_ROWS 0x100u
+/* Apply the display orientation (EXIF tag 16#112#, Read_EXIF gid-decoding_jpg.adb:436-543, what
+ * GID.Display_Orientation reports) while writing the pixels, as the client of test/to_bmp.adb does in
+ * its Set_X_Y / Put_Pixel (:104-146).  With (x, r) the column and top-down row of a pixel of the
+ * W x H frame, the output image is
+ *     ROTATE_90  : H x W,  pixel -> column r,         row W - 1 - x   (counted from the top)
+ *     ROTATE_180 : W x H,  pixel -> column W - 1 - x, row H - 1 - r
+ *     ROTATE_270 : H x W,  pixel -> column H - 1 - r, row x
+ * in the row order and byte order of the chosen format (for GIDCUDA_OUT_BGR8_BOTTOM_UP that is exactly
+ * to_bmp's buffer).  Stride and size (gidcuda_output_geometry) are those of the rotated image.
+ * Rotated frames take the two-pass kernels (IDCT, then one thread per pixel). */
+#define GIDCUDA_FLAG_ROTATE_90 0x200u
+#define GIDCUDA_FLAG_ROTATE_180 0x400u
+#define GIDCUDA_FLAG_ROTATE_270 0x600u
+#define GIDCUDA_FLAG_ROTATE_MASK 0x600u
 
 /* One JPEG frame, as the entropy decoder knows it after SOF/DQT/SOS
  * (Read_SOF gid-decoding_jpg.adb:184-318, Read_DQT :393-422). */

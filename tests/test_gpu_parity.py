@@ -100,6 +100,44 @@ def test_output_formats_and_strides(gpu, oracle, synth, samp):
     _check(gpu, oracle, fr, flags=capi.OUT_RGBA8, out_stride=4 * 211 + 4)
 
 
+def _to_bmp_buffer(ref, orientation):
+    """The byte buffer test/to_bmp.adb builds from GID's callbacks (:94-146): Set_X_Y (x, y) with y
+    counted from the bottom picks idx per orientation, Put_Pixel stores (blue, green, red)."""
+    h, w = ref.shape[:2]
+    pls_x, pls_y = 4 * -(-(w * 3) // 4), 4 * -(-(h * 3) // 4)
+    out_h = w if orientation in (1, 3) else h
+    buf = np.zeros((pls_y if orientation in (1, 3) else pls_x) * out_h, dtype=np.uint8)
+    x = np.arange(w)[None, :].repeat(h, 0)
+    y = (h - 1 - np.arange(h))[:, None].repeat(w, 1)     # GID's y: 0 = bottom row
+    rev_x, rev_y = w - (x + 1), h - (y + 1)
+    idx = [3 * x + pls_x * y, 3 * rev_y + pls_y * x, 3 * rev_x + pls_x * rev_y, 3 * y + pls_y * rev_x][orientation]
+    for k in range(3):
+        buf[(idx + k).ravel()] = ref[:, :, 2 - k].ravel()
+    return buf
+
+
+@pytest.mark.parametrize("samp", ["grey", "444", "422", "420", "440"])
+def test_display_orientation_applied_to_the_pixels(gpu, oracle, synth, samp):
+    """GIDCUDA_FLAG_ROTATE_*: GID.Display_Orientation (EXIF) applied while the pixels are written, as
+    the client of test/to_bmp.adb does per pixel in Set_X_Y / Put_Pixel.  The bottom-up B, G, R
+    buffer must be byte for byte the one to_bmp's formulas fill; the top-down formats its mirror."""
+    from gid_b200 import capi
+    fr = synth.planes_only(pixels_for(synth, 6, 131, 67, samp), samp)
+    ref = oracle.reconstruct(fr)
+    turned = {1: np.rot90(ref, 1), 2: ref[::-1, ::-1], 3: np.rot90(ref, -1)}
+    for orientation, flag in ((1, capi.FLAG_ROTATE_90), (2, capi.FLAG_ROTATE_180), (3, capi.FLAG_ROTATE_270)):
+        want = turned[orientation]
+        got = gpu.reconstruct_rgb(frame_desc(fr, flag | capi.FLAG_PACKED_ROWS), fr.planes)
+        assert got.shape == want.shape and np.array_equal(got, want), (samp, orientation)
+        got = gpu.reconstruct_rgb(frame_desc(fr, flag | capi.OUT_RGBA8), fr.planes)
+        assert np.array_equal(got[:, :, :3], want) and (got[:, :, 3] == 255).all()
+        rows = gpu.reconstruct(frame_desc(fr, flag | capi.OUT_BGR8_BOTTOM_UP), fr.planes)
+        used = 3 * want.shape[1]  # (the bytes that pad a row to a multiple of 4 are nobody's)
+        assert np.array_equal(rows[:, :used], _to_bmp_buffer(ref, orientation).reshape(rows.shape)[:, :used]), (samp, orientation)
+    rows = gpu.reconstruct(frame_desc(fr, capi.OUT_BGR8_BOTTOM_UP), fr.planes)
+    assert np.array_equal(rows[:, :3 * 131], _to_bmp_buffer(ref, 0).reshape(rows.shape)[:, :3 * 131])
+
+
 def test_job_recycling_and_state_errors(gpu, oracle, synth):
     from gid_b200 import GidCudaError
     a = synth.planes_only(pixels_for(synth, 1, 320, 240, "420"), "420")

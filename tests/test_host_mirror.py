@@ -600,3 +600,28 @@ def test_flat_and_periodic_images_stay_exact(host, oracle, synth, gpu):
         assert np.array_equal(rgb, oracle.decode(jpg)[1]), (name, samp)
     assert host.counter("device_scans") == scans + len(cases)          # every scan was offered to the device
     assert host.counter("device_scan_fallbacks") - back <= len(cases)  # ... and some came back
+
+
+@pytest.mark.gpu
+def test_file_batch_applies_the_display_orientation(host, oracle, synth, gpu):
+    """"apply_orientation": the batch driver writes every image turned as its EXIF tag says
+    (GID.Display_Orientation), H x W for Rotation_90 / _270 -- what to_bmp's Set_X_Y does per pixel."""
+    jpg, _ = synth.encode(pixels_for(synth, 2, 200, 120, "420"), "420")
+    ref = oracle.decode(jpg)[1]
+    files, want = [], []
+    for value, turn in ((1, ref), (8, np.rot90(ref, 1)), (3, ref[::-1, ::-1]), (6, np.rot90(ref, -1))):
+        tiff = b"II*\x00\x08\x00\x00\x00" + b"\x01\x00" + b"\x12\x01\x03\x00\x01\x00\x00\x00" + bytes([value, 0, 0, 0]) + bytes(4)
+        body = b"Exif\x00\x00" + tiff
+        files.append(jpg[:2] + b"\xff\xe1" + (len(body) + 2).to_bytes(2, "big") + body + jpg[2:])
+        want.append(turn)
+    host.set_option("apply_orientation", 1)
+    try:
+        out = [np.zeros(ref.nbytes, dtype=np.uint8) for _ in files]
+        imgs, st, _ = host.HostBatch(devices=(0,), threads=2).decode(files, [o.reshape(ref.shape) for o in out])
+    finally:
+        host.set_option("apply_orientation", 0)
+    assert st == [0, 0, 0, 0]
+    for o, w in zip(out, want):
+        assert np.array_equal(o.reshape(w.shape), w)
+    imgs, st, _ = host.decode_batch(files, threads=2)   # default: GID's behaviour, the orientation is the client's business
+    assert all(np.array_equal(i, ref) for i in imgs)
