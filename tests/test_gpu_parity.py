@@ -100,6 +100,23 @@ def test_output_formats_and_strides(gpu, oracle, synth, samp):
     _check(gpu, oracle, fr, flags=capi.OUT_RGBA8, out_stride=4 * 211 + 4)
 
 
+@pytest.mark.parametrize("w,h,samp", [(65535, 9, "grey"), (9, 65535, "420"), (65535, 17, "422"), (33, 65535, "444")])
+def test_maximum_dimensions(gpu, oracle, synth, w, h, samp):
+    """The largest width / height a JPEG frame header can carry (16 bits, :206-215), with partial
+    MCUs on the far edge; dense and record input."""
+    rng = np.random.default_rng(w ^ h)
+    gx, gy = synth.grid(w, h, samp)
+    from tests.harness import Frame
+    ref_frame = synth.planes_only(pixels_for(synth, 1, 64, 64, samp), samp)   # for the tables
+    planes = random_planes(rng, gx, gy, "sparse")
+    n = ref_frame.ncomp
+    fr = Frame(width=w, height=h, ncomp=n, samp_h=ref_frame.samp_h, samp_v=ref_frame.samp_v,
+               blocks_x=list(gx[:n]), blocks_y=list(gy[:n]), qt=ref_frame.qt, planes=planes[:n])
+    ref = oracle.reconstruct(fr)
+    assert np.array_equal(gpu.reconstruct_rgb(frame_desc(fr), fr.planes), ref)
+    assert np.array_equal(gpu.reconstruct_rgb(frame_desc(fr), fr.planes, sparse="auto"), ref)
+
+
 def _to_bmp_buffer(ref, orientation):
     """The byte buffer test/to_bmp.adb builds from GID's callbacks (:94-146): Set_X_Y (x, y) with y
     counted from the bottom picks idx per orientation, Put_Pixel stores (blue, green, red)."""
