@@ -336,10 +336,42 @@ const uint8_t *wait_pixels(Image_Descriptor &image, void *ctx_, void **job, size
   return px;
 }
 
-Reconstruction decode_and_reconstruct(Image_Descriptor &image, const std::function<void(int)> &feedback) {
+// One device context per host thread, kept from one image to the next: its stream and the pinned
+// and device buffers of its recycled jobs are what makes the second Load_Image_Contents of a
+// thread cost a tenth of the first (GID is "task safe" with one descriptor per task; so is this:
+// nothing is shared between threads).  Destroyed when the thread ends.
+namespace {
+struct ThreadContext {
   gidcuda_ctx *ctx = nullptr;
-  int rc = gidcuda_create(image.device, &ctx);
-  if (rc != GIDCUDA_OK) raise_from_status(rc, nullptr);
+  int device = -1;
+  ~ThreadContext() {
+    if (ctx) gidcuda_destroy(ctx);
+  }
+  gidcuda_ctx *get(int dev) {
+    if (ctx && device != dev) {
+      if (gidcuda_destroy(ctx) != GIDCUDA_OK) return nullptr;  // (a job of another image is still out)
+      ctx = nullptr;
+    }
+    if (!ctx) {
+      const int rc = gidcuda_create(dev, &ctx);
+      if (rc != GIDCUDA_OK) raise_from_status(rc, nullptr);
+      device = dev;
+    }
+    return ctx;
+  }
+};
+thread_local ThreadContext t_context;
+}  // namespace
+
+Reconstruction decode_and_reconstruct(Image_Descriptor &image, const std::function<void(int)> &feedback) {
+  gidcuda_ctx *ctx = t_context.get(image.device);
+  bool own = false;  // a context of its own, when the thread's is busy on another device
+  int rc;
+  if (!ctx) {
+    rc = gidcuda_create(image.device, &ctx);
+    if (rc != GIDCUDA_OK) raise_from_status(rc, nullptr);
+    own = true;
+  }
   gidcuda_job *job = nullptr;
   try {
     job = static_cast<gidcuda_job *>(decode_and_submit(image, ctx, feedback));
@@ -353,11 +385,11 @@ Reconstruction decode_and_reconstruct(Image_Descriptor &image, const std::functi
     }
     job = static_cast<gidcuda_job *>(j);
     rec.job = job;
-    rec.ctx = ctx;
+    rec.ctx = own ? ctx : nullptr;  // release() destroys only a context of its own
     return rec;
   } catch (...) {
     if (job) gidcuda_job_release(job);
-    gidcuda_destroy(ctx);
+    if (own) gidcuda_destroy(ctx);
     throw;
   }
 }
