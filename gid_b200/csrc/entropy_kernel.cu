@@ -1,4 +1,7 @@
-// entropy_kernel.cu -- baseline Huffman decoding on the device, one thread per restart interval.
+// entropy_kernel.cu -- baseline Huffman decoding on the device (gidcuda_job_scan):
+//   part 1  scans with restart intervals: one thread per interval      (huffman_intervals_kernel)
+//   part 2  scans without restart markers: self-synchronising parallel decoding
+//           (huffman_sync_kernel x 2, huffman_scan_kernel, huffman_output_kernel)
 //
 // SURVEY.md section 8f, rank 1 (the step BEFORE the reconstruction path).  After RSTn the DC
 // predictors are reset and the bit buffer is byte-aligned (Check_Restart,
