@@ -119,3 +119,17 @@ def test_records_from_plane_scan_order():
                         back[my * sv + sy, mx * sh + sx, int(w) & 63] = np.int16(np.uint16(int(w) >> 16))
                     seq += 1
     assert np.array_equal(back, p)
+
+
+def test_output_geometry_of_turned_frames(gidcuda_lib):
+    """GIDCUDA_FLAG_ROTATE_90 / _270 swap the sides of the pixel buffer; _180 keeps them."""
+    from gid_b200 import FrameDesc, capi
+    q = np.ones((3, 64), dtype=np.uint16)
+    for flag, (ow, oh) in ((0, (131, 67)), (capi.FLAG_ROTATE_90, (67, 131)), (capi.FLAG_ROTATE_180, (131, 67)),
+                           (capi.FLAG_ROTATE_270, (67, 131))):
+        for fmt, bpp, align in ((capi.OUT_RGB8 | capi.FLAG_PACKED_ROWS, 3, 1), (capi.OUT_BGR8_BOTTOM_UP, 3, 4), (capi.OUT_RGBA8, 4, 16)):
+            d = FrameDesc.make(131, 67, [2, 1, 1], [2, 1, 1], q, flags=fmt | flag)
+            st, nb = ctypes.c_size_t(), ctypes.c_size_t()
+            assert gidcuda_lib.gidcuda_output_geometry(ctypes.byref(d), ctypes.byref(st), ctypes.byref(nb)) == 0
+            want = -(-(bpp * ow) // align) * align
+            assert (st.value, nb.value) == (want, want * oh), (flag, fmt)
