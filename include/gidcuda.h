@@ -196,7 +196,8 @@ int gidcuda_job_records_commit_runs(gidcuda_job *job, int comp, int32_t nruns, c
  * (:1179-1220).  The device decoder does not reproduce the reference's handling of damaged streams:
  * when an interval holds a code that is in no table, a run past coefficient 63, too few or too many
  * bytes, gidcuda_job_wait returns GIDCUDA_ERR_DATA and the pixels are undefined; the caller then
- * decodes the scan on the host (planes or records) and submits the same job again. */
+ * decodes the scan on the host (planes or records) and submits the same job again.  The scan is consumed
+ * by the submit that follows it: a job that is submitted again needs its input handed over again. */
 typedef struct gidcuda_huffman_table {
   uint8_t counts[16];   /* codes of length 1 .. 16 */
   uint8_t symbols[256]; /* in code order */
