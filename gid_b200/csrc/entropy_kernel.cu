@@ -204,6 +204,11 @@ cudaError_t launch_huffman_intervals(const ScanArgs &a, cudaStream_t stream) {
 namespace {
 
 constexpr int kWindow = 256;
+// Re-decoding rounds per window.  A chain normally settles in 2 - 5 rounds, but where blocks are full
+// (quality 100: 63 coefficients and no EOB, so a decoder that guessed the position inside the block
+// wrong stays wrong until an EOB turns up) it takes dozens: a cap of 48 sent a quality-100 test image
+// to the host.  A whole window's worth of rounds guarantees that truth crosses the window.
+constexpr int kMaxRounds = kWindow;
 
 struct RawBits {  // no stuffing, no end: the buffer is padded with FF bytes past the data
   const uint32_t *w;  // next 32-bit word of the (4-byte aligned) stream
@@ -395,7 +400,7 @@ __global__ void __launch_bounds__(kWindow) huffman_sync_kernel(WholeArgs a, uint
     if (t == 0) head = i == 0 ? true_start : (first ? entry : a.exit_[i - 1]);
   }
   X[t] = exit_;
-  for (int iter = 0; iter < kWindow; iter++) {
+  for (int iter = 0; iter < kMaxRounds; iter++) {
     __syncthreads();
     const uint64_t want = t == 0 ? head : X[t - 1];
     const bool redo = active && want != entry;
