@@ -180,7 +180,7 @@ struct gidcuda_job {
   // ... scans without restart markers (scan_ri == 0): the self-synchronising decoder's arrays
   uint8_t *d_sync = nullptr;
   size_t cap_sync = 0, scan_len = 0;
-  uint32_t scan_nsub = 0;
+  uint32_t scan_nsub = 0, scan_sub_bits = 0;
   uint8_t *user_pixels = nullptr;  // gidcuda_job_output: the caller's own pinned buffer receives the pixels
   uint8_t *d_coef = nullptr, *d_pixels = nullptr, *d_samples = nullptr;
   gidk::LaunchSet set;
@@ -458,7 +458,12 @@ static bool build_huff_dev(const gidcuda_huffman_table &t, gidk::HuffDev *d) {
   return true;
 }
 
-constexpr uint32_t kSubsequenceBits = 256;  // one device thread per this many bits of a scan without restart markers
+// One device thread per this many bits of a scan without restart markers.  Short subsequences mean
+// more threads and shorter rounds; but a decoder only re-synchronises at block boundaries, so where
+// blocks are long (high qualities: hundreds of bits each) short subsequences would need many rounds
+// to carry the true state across a window -- those scans get longer subsequences.
+constexpr uint32_t kSubsequenceBits = 256, kSubsequenceBitsDense = 1024;
+constexpr uint32_t kDenseBitsPerBlock = 96;
 
 // gidcuda_job_scan with restart_interval == 0: the whole scan, byte stuffing removed by the caller.
 static int job_scan_whole(gidcuda_job *job, const gidcuda_scan_desc *scan, const uint8_t *data, size_t len) {
@@ -484,7 +489,10 @@ static int job_scan_whole(gidcuda_job *job, const gidcuda_scan_desc *scan, const
     CU_TRY(ctx, cudaHostAlloc((void **)&job->h_status, 16, cudaHostAllocDefault));
     CU_TRY(ctx, cudaMalloc((void **)&job->d_status, 16));
   }
-  const uint32_t nsub = (uint32_t)((len * 8 + kSubsequenceBits - 1) / kSubsequenceBits);
+  uint64_t frame_blocks = 0;
+  for (int c = 0; c < g.ncomp; c++) frame_blocks += (uint64_t)g.bx[c] * g.by[c];
+  const uint32_t sub_bits = (uint64_t)len * 8 > frame_blocks * kDenseBitsPerBlock ? kSubsequenceBitsDense : kSubsequenceBits;
+  const uint32_t nsub = (uint32_t)((len * 8 + sub_bits - 1) / sub_bits);
   const size_t sync_bytes = (size_t)nsub * (8 + 8 + 16 + 16) + 1024;
   if (job->cap_sync < sync_bytes) {
     if (job->d_sync) cudaFree(job->d_sync);
@@ -506,6 +514,7 @@ static int job_scan_whole(gidcuda_job *job, const gidcuda_scan_desc *scan, const
   job->scan_bytes = total;
   job->scan_len = len;
   job->scan_nsub = nsub;
+  job->scan_sub_bits = sub_bits;
   job->scan_ri = 0;
   job->scan_nintervals = 0;
   job->scan_active = true;
@@ -654,7 +663,7 @@ extern "C" int gidcuda_job_submit(gidcuda_job *job) {
       wa.mcux = (uint32_t)g.mcux;
       wa.total_blocks = blocks;
       wa.nbits = (uint32_t)(job->scan_len * 8);
-      wa.sub_bits = kSubsequenceBits;
+      wa.sub_bits = job->scan_sub_bits;
       wa.nsub = job->scan_nsub;
       wa.status = job->d_status;
       CU_TRY(ctx, gidk::launch_huffman_whole(wa, s));

@@ -186,7 +186,7 @@ int gidcuda_job_records_commit_runs(gidcuda_job *job, int comp, int32_t nruns, c
  *                      (Read_DHT :320-391: 16 counts, then the symbols in code order)
  * A scan WITHOUT restart markers (restart_interval = 0, nintervals = 0, begin = end = NULL) is taken
  * too: data = the scan's bytes up to the marker that ends it, with the byte stuffing REMOVED
- * (FF 00 -> FF).  The device cuts the bit stream into subsequences of 256 bits, one thread each,
+ * (FF 00 -> FF).  The device cuts the bit stream into subsequences of 256 bits (1024 where blocks are long), one thread each,
  * and relies on Huffman codes re-synchronising: every thread decodes from a guessed state, then from
  * its predecessor's exit state until the chain of states stops changing; prefix sums give every
  * subsequence its first block and its DC predictors; a last pass stores the coefficients and

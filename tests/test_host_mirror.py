@@ -625,3 +625,18 @@ def test_file_batch_applies_the_display_orientation(host, oracle, synth, gpu):
         assert np.array_equal(o.reshape(w.shape), w)
     imgs, st, _ = host.decode_batch(files, threads=2)   # default: GID's behaviour, the orientation is the client's business
     assert all(np.array_equal(i, ref) for i in imgs)
+
+
+@pytest.mark.gpu
+def test_device_entropy_decode_dense_full_blocks(host, oracle, synth, gpu):
+    """Quality 100 on noise, a larger frame: nearly every block carries 63 coefficients and no EOB, the
+    hardest case for re-synchronisation (a wrong position inside a block only corrects at an EOB).
+    Exact either way; with the longer subsequences dense scans get, it stays on the device."""
+    rng = np.random.default_rng(17)
+    pix = rng.integers(0, 256, size=(768, 1024, 3), dtype=np.uint8)
+    for samp in ("444", "420", "grey"):
+        jpg, _ = synth.encode(pix[:, :, 0].copy() if samp == "grey" else pix, samp, quality=100)
+        scans, back = host.counter("device_scans"), host.counter("device_scan_fallbacks")
+        rgb, _ = host.decode_rgb(jpg)
+        assert np.array_equal(rgb, oracle.decode(jpg)[1]), samp
+        assert host.counter("device_scans") == scans + 1 and host.counter("device_scan_fallbacks") == back, samp
