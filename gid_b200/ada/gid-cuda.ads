@@ -224,6 +224,8 @@ private
   pragma Import (C, gidcuda_abi_version, "gidcuda_abi_version");
   function gidcuda_set_option (name : C.Strings.chars_ptr; value : C.int) return C.int;
   pragma Import (C, gidcuda_set_option, "gidcuda_set_option");
+  function gidcuda_counter (name : C.Strings.chars_ptr) return C.long;
+  pragma Import (C, gidcuda_counter, "gidcuda_counter");
   function gidcuda_synchronize (ctx : Context) return C.int;
   pragma Import (C, gidcuda_synchronize, "gidcuda_synchronize");
 

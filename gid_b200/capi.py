@@ -28,7 +28,7 @@ FLAG_ROTATE_90, FLAG_ROTATE_180, FLAG_ROTATE_270 = 0x200, 0x400, 0x600  # GID.Di
 
 # every symbol include/gidcuda.h declares
 EXPORTS = [
-    "gidcuda_abi_version", "gidcuda_device_count", "gidcuda_last_error", "gidcuda_set_option", "gidcuda_create",
+    "gidcuda_abi_version", "gidcuda_device_count", "gidcuda_last_error", "gidcuda_set_option", "gidcuda_counter", "gidcuda_create",
     "gidcuda_destroy", "gidcuda_plane_geometry", "gidcuda_output_geometry", "gidcuda_job_begin",
     "gidcuda_job_plane", "gidcuda_job_hint_rows", "gidcuda_job_records", "gidcuda_job_records_commit", "gidcuda_job_records_commit_runs",
     "gidcuda_job_output", "gidcuda_job_scan", "gidcuda_host_is_pinned", "gidcuda_job_submit", "gidcuda_job_wait", "gidcuda_job_release",
@@ -108,6 +108,8 @@ def load_library() -> ctypes.CDLL:
     L = ctypes.CDLL(path)
     vp, i32p = ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32)
     L.gidcuda_abi_version.restype = ctypes.c_int
+    L.gidcuda_counter.argtypes = [ctypes.c_char_p]
+    L.gidcuda_counter.restype = ctypes.c_long
     L.gidcuda_device_count.restype = ctypes.c_int
     L.gidcuda_last_error.restype = ctypes.c_char_p
     L.gidcuda_last_error.argtypes = [vp]
@@ -345,6 +347,11 @@ class Batch:
         if self.h:
             self.lib.gidcuda_batch_destroy(self.h)
             self.h = ctypes.c_void_p()
+
+
+def counter(name: str) -> int:
+    """"chain_repairs" / "chain_repair_subsequences" (gidcuda_counter)."""
+    return int(load_library().gidcuda_counter(name.encode()))
 
 
 def pinned_empty(nbytes: int) -> tuple[np.ndarray, int]:

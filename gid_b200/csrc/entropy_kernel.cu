@@ -204,11 +204,14 @@ cudaError_t launch_huffman_intervals(const ScanArgs &a, cudaStream_t stream) {
 namespace {
 
 constexpr int kWindow = 256;
-// Re-decoding rounds per window.  A chain normally settles in 2 - 5 rounds, but where blocks are full
-// (quality 100: 63 coefficients and no EOB, so a decoder that guessed the position inside the block
-// wrong stays wrong until an EOB turns up) it takes dozens: a cap of 48 sent a quality-100 test image
-// to the host.  A whole window's worth of rounds guarantees that truth crosses the window.
-constexpr int kMaxRounds = kWindow;
+// Re-decoding rounds per window.  A chain normally settles in 2 - 5 rounds.  Where it does not -- a
+// flat region (periodic bit stream: a decoder in the wrong phase stays there), or full blocks without
+// EOB at quality 100 (a wrong position inside the block survives until an EOB turns up) -- truth only
+// advances one subsequence per round, which is a serial walk, and a host core does that an order of
+// magnitude faster than a GPU thread: after this many rounds the window gives up and leaves the
+// stretch to the chain repair in gidcuda_job_wait (measured: 256 rounds cost 3 ms per launch on a
+// black frame, for nothing).
+constexpr int kMaxRounds = 32;
 
 struct RawBits {  // no stuffing, no end: the buffer is padded with FF bytes past the data
   const uint32_t *w;  // next 32-bit word of the (4-byte aligned) stream
@@ -483,18 +486,22 @@ __global__ void __launch_bounds__(128) huffman_output_kernel(WholeArgs a) {
   const uint32_t b = (uint32_t)pre.x;
   if (b >= a.total_blocks) return;  // padding after the last block
   const uint64_t entry = i == 0 ? pack_state(0u, 0u, 0u) : a.exit_[i - 1];
-  bool bad = entry != a.entry[i];  // the tuples (and so the prefixes) belong to another chain
+  bool chain_bad = entry != a.entry[i];  // the tuples (and so the prefixes) belong to another chain
   const uint32_t c = (uint32_t)(entry >> 32) & 0xFFu;
-  if (c >= a.bpm || b % a.bpm != c) bad = true;
+  if (c >= a.bpm || b % a.bpm != c) chain_bad = true;
+  bool code_bad = false;
   uint32_t done = 0;
-  if (!bad) {
+  if (!chain_bad) {
     int4 tup;
     const uint32_t limit = min((i + 1) * a.sub_bits, a.nbits);
-    const uint64_t out = run_subsequence<true>(a, tabs, zz, slots, entry, limit, tup, b, pre.y, pre.z, pre.w, &bad, &done);
+    const uint64_t out = run_subsequence<true>(a, tabs, zz, slots, entry, limit, tup, b, pre.y, pre.z, pre.w, &code_bad, &done);
     // a subsequence that ends with the frame's last block stops early: nothing follows it
-    if (!bad && b + done < a.total_blocks && out != a.exit_[i]) bad = true;
+    if (!code_bad && b + done < a.total_blocks && out != a.exit_[i]) chain_bad = true;
   }
-  if (bad) atomicOr(a.status, 2u);
+  // 2: the chain of states does not hold here (not settled: the host can repair it, see
+  // gidcuda_job_wait); 8: something the serial decoder would raise on
+  if (chain_bad) atomicOr(a.status, 2u);
+  if (code_bad) atomicOr(a.status, 8u);
   if (done) atomicAdd(a.status + 2, done);
 }
 
@@ -505,6 +512,13 @@ cudaError_t launch_huffman_whole(const WholeArgs &a, cudaStream_t stream) {
   huffman_sync_kernel<<<(a.nsub + kWindow - 1) / kWindow, kWindow, 0, stream>>>(a, 0u, 1);
   if (a.nsub > kWindow / 2)
     huffman_sync_kernel<<<(a.nsub - kWindow / 2 + kWindow - 1) / kWindow, kWindow, 0, stream>>>(a, kWindow / 2, 0);
+  return launch_huffman_finish(a, stream);
+}
+
+// Steps 2 and 3 alone: prefix sums and the verified output pass over the chain as it stands
+// (after the sync launches, or after the host has repaired it).
+cudaError_t launch_huffman_finish(const WholeArgs &a, cudaStream_t stream) {
+  if (a.nsub == 0) return cudaSuccess;
   huffman_scan_kernel<<<1, 1024, 0, stream>>>(a);
   huffman_output_kernel<<<(a.nsub + 127) / 128, 128, 0, stream>>>(a);
   return cudaGetLastError();

@@ -154,6 +154,10 @@ extern "C" int gidcuda_host_free(void *ptr) {
 // gidcuda_set_option("blocking_wait"): jobs created from now on sleep in gidcuda_job_wait instead
 // of spinning -- for callers that run about as many host threads as there are cores.
 static int g_blocking_wait = 0;
+// gidcuda_set_option("chain_repair"): 1 (default) = an unsettled chain of the self-synchronising Huffman
+// decoder is repaired by the host (job_repair_chain); 0 = reported as GIDCUDA_ERR_DATA at once.
+static int g_chain_repair = 1;
+static std::atomic<long> g_chain_repairs{0}, g_chain_repair_subsequences{0};
 
 struct gidcuda_job {
   gidcuda_ctx *ctx = nullptr;
@@ -181,6 +185,7 @@ struct gidcuda_job {
   uint8_t *d_sync = nullptr;
   size_t cap_sync = 0, scan_len = 0;
   uint32_t scan_nsub = 0, scan_sub_bits = 0;
+  size_t repaired_subsequences = 0;  // subsequences the host walked in the last chain repair
   uint8_t *user_pixels = nullptr;  // gidcuda_job_output: the caller's own pinned buffer receives the pixels
   uint8_t *d_coef = nullptr, *d_pixels = nullptr, *d_samples = nullptr;
   gidk::LaunchSet set;
@@ -579,6 +584,163 @@ extern "C" int gidcuda_job_scan(gidcuda_job *job, const gidcuda_scan_desc *scan,
   return GIDCUDA_OK;
 }
 
+// The self-synchronising decoder's arguments for the scan a job holds (gidcuda_job_scan, restart_interval = 0).
+static void make_whole_args(gidcuda_job *job, gidk::WholeArgs *out) {
+  const Geometry &g = job->geo;
+  gidk::WholeArgs &wa = *out;
+  memset(&wa, 0, sizeof wa);
+  wa.data = job->d_scan + job->scan_off_data;
+  wa.tables = reinterpret_cast<const gidk::HuffDev *>(job->d_scan);
+  const size_t n = job->scan_nsub;
+  wa.entry = reinterpret_cast<uint64_t *>(job->d_sync);
+  wa.exit_ = wa.entry + n;
+  wa.tuple = reinterpret_cast<int4 *>(job->d_sync + round_up(16 * n, 256));
+  wa.prefix = wa.tuple + n;
+  uint32_t k = 0, blocks = 0;
+  for (int c = 0; c < g.ncomp; c++) {
+    wa.plane[c] = reinterpret_cast<int16_t *>(job->d_coef + g.plane_off[c]);
+    wa.bx[c] = (uint32_t)g.bx[c];
+    wa.h[c] = job->desc.samp_h[c];
+    wa.v[c] = job->desc.samp_v[c];
+    blocks += (uint32_t)g.bx[c] * (uint32_t)g.by[c];
+    k += (uint32_t)(wa.h[c] * wa.v[c]);
+    job->d_tail_zero[c] = false;
+  }
+  wa.bpm = k;
+  wa.mcux = (uint32_t)g.mcux;
+  wa.total_blocks = blocks;
+  wa.nbits = (uint32_t)(job->scan_len * 8);
+  wa.sub_bits = job->scan_sub_bits;
+  wa.nsub = job->scan_nsub;
+  wa.status = job->d_status;
+}
+
+// ---- chain repair on the host -------------------------------------------------------------------
+// A stretch of the scan that does not re-synchronise (a flat region: the same two code words over and
+// over, so a decoder in the wrong phase stays there) leaves the device's chain of states broken: truth
+// only advances one subsequence per round there.  Walking such a stretch is a SERIAL job, which one host
+// core does an order of magnitude faster than one GPU thread.  So when the output pass reports an
+// unsettled chain (and nothing undecodable), gidcuda_job_wait fetches the chain, walks it from the true
+// start state -- where a subsequence's recorded entry state is the true one its recorded exit and counts
+// are kept, where not the host decodes that subsequence (the mirror of run_subsequence<false> in
+// entropy_kernel.cu) -- sends it back and runs prefix sums, output pass and reconstruction again.  The
+// output pass verifies the repaired chain like any other.
+namespace {
+
+struct HostWalk {
+  const uint8_t *data;  // unstuffed scan bytes, FF-padded (the job's pinned staging copy)
+  const gidk::HuffDev *tabs;
+  uint32_t bpm;
+  uint8_t comp[12];
+};
+
+inline uint32_t host_peek(const uint8_t *d, uint32_t pos, int n) {  // n <= 16
+  const uint8_t *p = d + (pos >> 3);
+  const uint32_t w = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
+  return (w << (pos & 7u)) >> (32 - n);
+}
+
+inline int host_extend(uint32_t v, int n) { return v < (1u << (n - 1)) ? (int)v + 1 - (1 << n) : (int)v; }
+
+uint64_t host_run_subsequence(const HostWalk &w, uint64_t entry, uint32_t limit, int32_t tup[4]) {
+  uint32_t pos = (uint32_t)entry, c = (uint32_t)(entry >> 32) & 0xFFu, zpos = (uint32_t)(entry >> 40) & 0xFFu;
+  int nb = 0, dcs[3] = {0, 0, 0};
+  while (pos < limit) {
+    const int k = w.comp[c];
+    const gidk::HuffDev &t = zpos == 0 ? w.tabs[k] : w.tabs[3 + k];
+    const uint32_t look = host_peek(w.data, pos, 16);
+    const uint32_t e = t.lut[look >> 6];
+    int l = (int)(e >> 8), sym = (int)(e & 0xFFu);
+    if (e == 0) {
+      sym = -1;
+      for (l = 11; l <= 16; l++) {
+        const int code = (int)(look >> (16 - l));
+        if (code <= t.maxcode[l]) {
+          sym = t.vals[(t.valoff[l] + code) & 0xFF];
+          break;
+        }
+      }
+      if (sym < 0) {
+        pos += 1;
+        continue;
+      }
+    }
+    pos += (uint32_t)l;
+    const int n = sym & 15;
+    bool block_done = false;
+    if (zpos == 0) {
+      if (n) {
+        dcs[k] += host_extend(host_peek(w.data, pos, n), n);
+        pos += (uint32_t)n;
+      }
+      zpos = 1;
+    } else if (sym == 0) {
+      block_done = true;
+    } else {
+      const uint32_t idx = zpos + (uint32_t)(sym >> 4);
+      pos += (uint32_t)n;
+      if (idx >= 63) block_done = true;
+      else zpos = idx + 1;
+    }
+    if (block_done) {
+      zpos = 0;
+      c = c + 1 == w.bpm ? 0 : c + 1;
+      nb++;
+    }
+  }
+  tup[0] = nb; tup[1] = dcs[0]; tup[2] = dcs[1]; tup[3] = dcs[2];
+  return (uint64_t)pos | ((uint64_t)c << 32) | ((uint64_t)zpos << 40);
+}
+
+}  // namespace
+
+// Returns GIDCUDA_OK when the repaired chain has been re-submitted (the caller waits for job->done again).
+static int job_repair_chain(gidcuda_job *job) {
+  gidcuda_ctx *ctx = job->ctx;
+  const Geometry &g = job->geo;
+  cudaStream_t s = job->stream;
+  gidk::WholeArgs wa;
+  make_whole_args(job, &wa);
+  const size_t n = wa.nsub;
+  std::vector<uint64_t> st(2 * n);   // entry[], exit[]
+  std::vector<int32_t> tup(4 * n);
+  CU_TRY(ctx, cudaMemcpyAsync(st.data(), wa.entry, 16 * n, cudaMemcpyDeviceToHost, s));
+  CU_TRY(ctx, cudaMemcpyAsync(tup.data(), wa.tuple, 16 * n, cudaMemcpyDeviceToHost, s));
+  CU_TRY(ctx, cudaStreamSynchronize(s));
+  HostWalk w;
+  w.data = job->h_scan + job->scan_off_data;
+  w.tabs = reinterpret_cast<const gidk::HuffDev *>(job->h_scan);
+  w.bpm = wa.bpm;
+  uint32_t k = 0;
+  for (int c = 0; c < g.ncomp; c++)
+    for (int i = 0; i < job->desc.samp_h[c] * job->desc.samp_v[c]; i++) w.comp[k++] = (uint8_t)c;
+  uint64_t state = 0;  // the true start: bit 0, first block of the MCU, DC next
+  uint64_t blocks = 0;
+  size_t walked = 0;
+  for (size_t i = 0; i < n && blocks < wa.total_blocks; i++) {
+    if (st[i] != state) {
+      const uint32_t limit = std::min<uint64_t>((uint64_t)(i + 1) * wa.sub_bits, wa.nbits);
+      st[i] = state;
+      st[n + i] = host_run_subsequence(w, state, limit, &tup[4 * i]);
+      walked++;
+    }
+    state = st[n + i];
+    blocks += (uint64_t)tup[4 * i];
+  }
+  job->repaired_subsequences = walked;
+  CU_TRY(ctx, cudaMemcpyAsync(wa.entry, st.data(), 16 * n, cudaMemcpyHostToDevice, s));
+  CU_TRY(ctx, cudaMemcpyAsync(wa.tuple, tup.data(), 16 * n, cudaMemcpyHostToDevice, s));
+  CU_TRY(ctx, cudaMemsetAsync(job->d_coef, 0, g.coef_bytes, s));
+  CU_TRY(ctx, cudaMemsetAsync(job->d_status, 0, 16, s));
+  CU_TRY(ctx, gidk::launch_huffman_finish(wa, s));
+  CU_TRY(ctx, cudaMemcpyAsync(job->h_status, job->d_status, 16, cudaMemcpyDeviceToHost, s));
+  CU_TRY(ctx, job->set.launch(ctx->num_sms, s));
+  CU_TRY(ctx, cudaMemcpyAsync(job->user_pixels ? job->user_pixels : job->h_pixels, job->d_pixels, g.pixel_bytes,
+                              cudaMemcpyDeviceToHost, s));
+  CU_TRY(ctx, cudaStreamSynchronize(s));  // (st / tup are this function's: the copies must be done before they go)
+  return GIDCUDA_OK;
+}
+
 static bool is_pinned_host(const void *p) {
   cudaPointerAttributes at;
   if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
@@ -641,31 +803,7 @@ extern "C" int gidcuda_job_submit(gidcuda_job *job) {
     CU_TRY(ctx, cudaMemsetAsync(job->d_status, 0, 16, s));
     if (job->scan_ri == 0) {
       gidk::WholeArgs wa;
-      memset(&wa, 0, sizeof wa);
-      wa.data = job->d_scan + job->scan_off_data;
-      wa.tables = reinterpret_cast<const gidk::HuffDev *>(job->d_scan);
-      const size_t n = job->scan_nsub;
-      wa.entry = reinterpret_cast<uint64_t *>(job->d_sync);
-      wa.exit_ = wa.entry + n;
-      wa.tuple = reinterpret_cast<int4 *>(job->d_sync + round_up(16 * n, 256));
-      wa.prefix = wa.tuple + n;
-      uint32_t k = 0, blocks = 0;
-      for (int c = 0; c < g.ncomp; c++) {
-        wa.plane[c] = reinterpret_cast<int16_t *>(job->d_coef + g.plane_off[c]);
-        wa.bx[c] = (uint32_t)g.bx[c];
-        wa.h[c] = job->desc.samp_h[c];
-        wa.v[c] = job->desc.samp_v[c];
-        blocks += (uint32_t)g.bx[c] * (uint32_t)g.by[c];
-        k += (uint32_t)(wa.h[c] * wa.v[c]);
-        job->d_tail_zero[c] = false;
-      }
-      wa.bpm = k;
-      wa.mcux = (uint32_t)g.mcux;
-      wa.total_blocks = blocks;
-      wa.nbits = (uint32_t)(job->scan_len * 8);
-      wa.sub_bits = job->scan_sub_bits;
-      wa.nsub = job->scan_nsub;
-      wa.status = job->d_status;
+      make_whole_args(job, &wa);
       CU_TRY(ctx, gidk::launch_huffman_whole(wa, s));
     } else {
       gidk::ScanArgs sa;
@@ -780,6 +918,15 @@ extern "C" int gidcuda_job_wait(gidcuda_job *job, const uint8_t **pixels, size_t
     job->scan_active = false;  // a re-submission after a host decode takes planes / records
     uint32_t blocks = 0;
     for (int c = 0; c < job->geo.ncomp; c++) blocks += (uint32_t)job->geo.bx[c] * (uint32_t)job->geo.by[c];
+    if (job->scan_ri == 0 && (job->h_status[0] & 2u) && g_chain_repair) {
+      // an unsettled chain: the host walks the stretches that did not re-synchronise.  (Threads that
+      // decoded from a consistent but untrue state may have met undecodable codes, flag 8, as well:
+      // the output pass over the repaired chain tells whether the stream itself is damaged.)
+      const int rc = job_repair_chain(job);
+      if (rc != GIDCUDA_OK) return rc;
+      g_chain_repairs.fetch_add(1, std::memory_order_relaxed);
+      g_chain_repair_subsequences.fetch_add((long)job->repaired_subsequences, std::memory_order_relaxed);
+    }
     if (job->scan_ri == 0 && job->h_status[0] == 0 && job->h_status[2] != blocks) job->h_status[0] = 4;
     if (job->scan_ri == 0 && job->h_status[0] != 0) {
       job->state = gidcuda_job::BEGUN;
@@ -913,6 +1060,10 @@ extern "C" int gidcuda_plan_launch_count(const gidcuda_plan *plan) { return plan
 
 extern "C" int gidcuda_set_option(const char *name, int value) {
   if (!name) return fail(nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "null option name");
+  if (strcmp(name, "chain_repair") == 0) {
+    g_chain_repair = value ? 1 : 0;
+    return GIDCUDA_OK;
+  }
   if (strcmp(name, "blocking_wait") == 0) {
     g_blocking_wait = value ? 1 : 0;
     return GIDCUDA_OK;
@@ -922,6 +1073,12 @@ extern "C" int gidcuda_set_option(const char *name, int value) {
     return GIDCUDA_OK;
   }
   return fail(nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "unknown option '%s'", name);
+}
+
+extern "C" long gidcuda_counter(const char *name) {
+  if (name && strcmp(name, "chain_repairs") == 0) return g_chain_repairs.load();
+  if (name && strcmp(name, "chain_repair_subsequences") == 0) return g_chain_repair_subsequences.load();
+  return -1;
 }
 
 extern "C" int gidcuda_plan_uses_tma(const gidcuda_plan *plan) { return plan ? plan->set.tma_groups : 0; }

@@ -92,9 +92,10 @@ struct WholeArgs {
   uint32_t bpm;            // blocks per MCU (<= 12)
   uint32_t mcux, total_blocks;
   uint32_t nbits, sub_bits, nsub;
-  uint32_t *status;        // [0] flags (2 = chain not verified / undecodable), [2] blocks stored
+  uint32_t *status;        // [0] flags (2 = chain of states not settled, 8 = undecodable), [2] blocks stored
 };
 cudaError_t launch_huffman_whole(const WholeArgs &a, cudaStream_t stream);
+cudaError_t launch_huffman_finish(const WholeArgs &a, cudaStream_t stream);  // scan + output over the chain as it stands
 inline int launches_huffman_whole() { return 4; }
 
 // One-time kernel attribute set-up (dynamic shared memory opt-in).

@@ -104,9 +104,16 @@ const char *gidcuda_last_error(const gidcuda_ctx *ctx);
 
 /* Library options (process-wide; set before creating jobs / plans):
  *   "tma"  1 (default) = stage coefficients through TMA, 0 = plain 128-bit loads.
+ *   "chain_repair"  1 (default) = when the self-synchronising Huffman decoder (gidcuda_job_scan without restart
+ *          markers) is left with an unsettled chain of states -- a stretch of the scan that does not
+ *          re-synchronise, e.g. a large flat region -- gidcuda_job_wait lets the host walk those stretches
+ *          serially and runs the output pass again; 0 = report GIDCUDA_ERR_DATA at once.
  *   "blocking_wait"  0 (default) = gidcuda_job_wait spins (lowest latency); 1 = it sleeps until the
  *          frame is done (for callers with about as many host threads as cores). */
 int gidcuda_set_option(const char *name, int value);
+/* Process-wide statistics: "chain_repairs" (scans whose chain of states the host repaired),
+ * "chain_repair_subsequences" (subsequences it walked for that); -1 for an unknown name. */
+long gidcuda_counter(const char *name);
 
 /* One context per host thread / Ada task.  Owns a device, streams and a pool
  * of pinned host + device buffers that jobs recycle. */
@@ -191,7 +198,9 @@ int gidcuda_job_records_commit_runs(gidcuda_job *job, int comp, int32_t nruns, c
  * its predecessor's exit state until the chain of states stops changing; prefix sums give every
  * subsequence its first block and its DC predictors; a last pass stores the coefficients and
  * VERIFIES the chain (by induction from the first subsequence a verified chain is the serial
- * decode).  A chain that does not verify is reported like a damaged stream.
+ * decode).  A chain that has not settled (a stretch that does not re-synchronise: flat regions make the
+ * bit stream periodic) is repaired by the host, which walks those stretches serially, and verified
+ * again (option "chain_repair"); one that still does not verify is reported like a damaged stream.
  * The MCU order, block order and predictor handling are those of Baseline_DCT_Decoding_Scan
  * (:1179-1220).  The device decoder does not reproduce the reference's handling of damaged streams:
  * when an interval holds a code that is in no table, a run past coefficient 63, too few or too many

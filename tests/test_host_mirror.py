@@ -578,8 +578,9 @@ def test_progressive_scans_through_the_wide_bit_buffer(host, oracle, synth):
 @pytest.mark.gpu
 def test_flat_and_periodic_images_stay_exact(host, oracle, synth, gpu):
     """Flat regions make the bit stream periodic, and a periodic stream need not re-synchronise a
-    decoder that started in the wrong phase: the device's chain of states then fails its verification
-    and the host decodes the scan.  Whichever way an image goes, the pixels are GID's."""
+    decoder that started in the wrong phase: the device's chain of states is then left unsettled, the
+    host walks those stretches serially (gidcuda_job_wait, "chain_repair") and the output pass verifies
+    the repaired chain.  Whichever way an image goes, the pixels are GID's."""
     h, w = 540, 960
     base = synth.image(3, w, h)
     flat = np.full((h, w, 3), 128, np.uint8)
@@ -593,50 +594,23 @@ def test_flat_and_periodic_images_stay_exact(host, oracle, synth, gpu):
     cases = [("flat", flat, "420"), ("flat", flat[:, :, 0].copy(), "grey"), ("flat", flat, "444"),
              ("black", np.zeros((h, w, 3), np.uint8), "420"), ("bars", bars, "420"), ("bars", bars, "444"),
              ("stripes", stripes, "420"), ("sky", sky, "422")]
+    from gid_b200 import capi
     scans, back = host.counter("device_scans"), host.counter("device_scan_fallbacks")
+    repairs = capi.counter("chain_repairs")
     for name, pix, samp in cases:
         jpg, _ = synth.encode(pix, samp)
         rgb, _ = host.decode_rgb(jpg)
         assert np.array_equal(rgb, oracle.decode(jpg)[1]), (name, samp)
-    assert host.counter("device_scans") == scans + len(cases)          # every scan was offered to the device
-    assert host.counter("device_scan_fallbacks") - back <= len(cases)  # ... and some came back
-
-
-@pytest.mark.gpu
-def test_file_batch_applies_the_display_orientation(host, oracle, synth, gpu):
-    """"apply_orientation": the batch driver writes every image turned as its EXIF tag says
-    (GID.Display_Orientation), H x W for Rotation_90 / _270 -- what to_bmp's Set_X_Y does per pixel."""
-    jpg, _ = synth.encode(pixels_for(synth, 2, 200, 120, "420"), "420")
-    ref = oracle.decode(jpg)[1]
-    files, want = [], []
-    for value, turn in ((1, ref), (8, np.rot90(ref, 1)), (3, ref[::-1, ::-1]), (6, np.rot90(ref, -1))):
-        tiff = b"II*\x00\x08\x00\x00\x00" + b"\x01\x00" + b"\x12\x01\x03\x00\x01\x00\x00\x00" + bytes([value, 0, 0, 0]) + bytes(4)
-        body = b"Exif\x00\x00" + tiff
-        files.append(jpg[:2] + b"\xff\xe1" + (len(body) + 2).to_bytes(2, "big") + body + jpg[2:])
-        want.append(turn)
-    host.set_option("apply_orientation", 1)
+    assert host.counter("device_scans") == scans + len(cases)     # every scan went to the device ...
+    assert host.counter("device_scan_fallbacks") == back          # ... and none came back to the host decoder:
+    assert capi.counter("chain_repairs") > repairs                # the host repaired the unsettled chains
+    assert capi.counter("chain_repair_subsequences") > 0
+    # without the repair the same scans are handed back whole (and still come out exact)
+    capi.set_option("chain_repair", 0)
     try:
-        out = [np.zeros(ref.nbytes, dtype=np.uint8) for _ in files]
-        imgs, st, _ = host.HostBatch(devices=(0,), threads=2).decode(files, [o.reshape(ref.shape) for o in out])
+        for name, pix, samp in cases[:4]:
+            jpg, _ = synth.encode(pix, samp)
+            assert np.array_equal(host.decode_rgb(jpg)[0], oracle.decode(jpg)[1]), (name, samp)
     finally:
-        host.set_option("apply_orientation", 0)
-    assert st == [0, 0, 0, 0]
-    for o, w in zip(out, want):
-        assert np.array_equal(o.reshape(w.shape), w)
-    imgs, st, _ = host.decode_batch(files, threads=2)   # default: GID's behaviour, the orientation is the client's business
-    assert all(np.array_equal(i, ref) for i in imgs)
-
-
-@pytest.mark.gpu
-def test_device_entropy_decode_dense_full_blocks(host, oracle, synth, gpu):
-    """Quality 100 on noise, a larger frame: nearly every block carries 63 coefficients and no EOB, the
-    hardest case for re-synchronisation (a wrong position inside a block only corrects at an EOB).
-    Exact either way; with the longer subsequences dense scans get, it stays on the device."""
-    rng = np.random.default_rng(17)
-    pix = rng.integers(0, 256, size=(768, 1024, 3), dtype=np.uint8)
-    for samp in ("444", "420", "grey"):
-        jpg, _ = synth.encode(pix[:, :, 0].copy() if samp == "grey" else pix, samp, quality=100)
-        scans, back = host.counter("device_scans"), host.counter("device_scan_fallbacks")
-        rgb, _ = host.decode_rgb(jpg)
-        assert np.array_equal(rgb, oracle.decode(jpg)[1]), samp
-        assert host.counter("device_scans") == scans + 1 and host.counter("device_scan_fallbacks") == back, samp
+        capi.set_option("chain_repair", 1)
+    assert host.counter("device_scan_fallbacks") > back
