@@ -509,7 +509,7 @@ def run_ours(args) -> None:
                     "api": ("gidcuda_job_submit/wait, pinned host coefficient records (one per non-zero coefficient, "
                             "gidcuda_job_records) -> expand + reconstruction kernels -> pinned host pixels, %d jobs in flight" % depth
                             if args.e2e_input == "records" else
-                            "gidcuda_job_submit/wait, pinned host planes -> pinned host pixels, 2 jobs in flight; "
+                            "gidcuda_job_submit/wait, pinned host planes -> pinned host pixels, %d jobs in flight; " % depth +
                             "planes with empty block rows 4..7 (gidcuda_job_hint_rows) travel as pitched copies")},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -297,7 +297,7 @@ def test_restart_parallel_scan_through_the_device(host, oracle, synth, gpu, coef
 
 @pytest.mark.gpu
 def test_file_batch_matches_gid(host, oracle, synth, gpu):
-    """gidhost_batch_decode: a mixed set of files on several host threads, two frames in flight per
+    """gidhost_batch_decode: a mixed set of files on several host threads, three frames in flight per
     thread; every image == GID's decode, a damaged file is reported with GID's exception class and
     does not disturb the others; the contexts are recycled by a second call."""
     specs = [("420", 640, 360, False, 0), ("444", 97, 61, False, 0), ("grey", 300, 200, False, 5), ("422", 320, 240, True, 0),
