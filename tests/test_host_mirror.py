@@ -614,3 +614,61 @@ def test_flat_and_periodic_images_stay_exact(host, oracle, synth, gpu):
     finally:
         capi.set_option("chain_repair", 1)
     assert host.counter("device_scan_fallbacks") > back
+
+
+# --------------------------------------------------------------------------- files from another encoder (libjpeg via Pillow)
+
+
+def _pillow_files(synth):
+    """JPEG files written by libjpeg(-turbo) through Pillow: other Huffman tables (standard and
+    per-image optimised), JFIF / APPn segments, its progressive scan script, restart markers."""
+    Image = pytest.importorskip("PIL.Image")
+    import io
+    from PIL import ImageFile
+    ImageFile.MAXBLOCK = max(ImageFile.MAXBLOCK, 4 << 20)  # (libjpeg "suspension" with optimised / progressive output)
+    photo = synth.image(11, 640, 424)
+    rng = np.random.default_rng(3)
+    noisy = np.clip(photo.astype(np.int16) + rng.integers(-40, 41, size=photo.shape), 0, 255).astype(np.uint8)
+    out = []
+    for name, pix, kw in (
+            ("q85_420", photo, dict(quality=85)),
+            ("q85_420_optimised", photo, dict(quality=85, optimize=True)),
+            ("q92_444", noisy, dict(quality=92, subsampling=0)),
+            ("q75_422", photo, dict(quality=75, subsampling=1)),
+            ("q60_grey", photo[:, :, 1], dict(quality=60)),
+            ("q80_420_restart", noisy, dict(quality=80, restart_marker_blocks=3)),
+            ("q80_444_restart_rows", photo, dict(quality=80, subsampling=0, restart_marker_rows=1)),
+            ("q100_420", noisy, dict(quality=100)),
+            ("q30_420_progressive", photo, dict(quality=30, progressive=True)),
+            ("q90_444_progressive_optimised", noisy, dict(quality=90, subsampling=0, progressive=True, optimize=True))):
+        b = io.BytesIO()
+        Image.fromarray(pix).save(b, "JPEG", **kw)
+        out.append((name, b.getvalue()))
+    return out
+
+
+def test_libjpeg_files_entropy_decoder_matches_oracle(host, oracle, synth):
+    for name, jpg in _pillow_files(synth):
+        fr, _, _ = oracle.decode(jpg)
+        desc, planes = host.decode_planes(jpg)
+        assert (desc.width, desc.height, desc.ncomp) == (fr.width, fr.height, fr.ncomp), name
+        for c in range(fr.ncomp):
+            assert np.array_equal(planes[c], fr.planes[c]), (name, c)
+            assert list(desc.qt[c]) == fr.qt[c].tolist(), (name, c)
+
+
+@pytest.mark.gpu
+def test_libjpeg_files_through_the_device(host, oracle, synth, gpu):
+    """The same files end to end: baseline ones are Huffman-decoded on the device (with restart
+    markers only when there are at least 64 intervals, else by the self-synchronising decoder's
+    sibling on the host), progressive ones on the host; pixels == GID's decode of the file."""
+    scans, back = host.counter("device_scans"), host.counter("device_scan_fallbacks")
+    files = _pillow_files(synth)
+    for name, jpg in files:
+        rgb, _ = host.decode_rgb(jpg)
+        assert np.array_equal(rgb, oracle.decode(jpg)[1]), name
+    assert host.counter("device_scans") - scans >= 6 and host.counter("device_scan_fallbacks") == back
+    imgs, st, _ = host.decode_batch([f for _, f in files], threads=3)
+    assert st == [0] * len(files)
+    for (name, jpg), img in zip(files, imgs):
+        assert np.array_equal(img, oracle.decode(jpg)[1]), name
