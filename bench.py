@@ -23,6 +23,11 @@ the same workload definition, and prints the same line with "impl": "reference".
 """
 from __future__ import annotations
 
+import os as _os
+# read when the CUDA context is created (torch creates it before libgidcuda.so is loaded): as many hardware
+# work queues as the device has, so that frames in flight on different streams really run side by side
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import argparse
 import ctypes
 import json

@@ -389,6 +389,12 @@ __global__ void __launch_bounds__(kWindow) huffman_sync_kernel(WholeArgs a, uint
   uint64_t entry = 0, exit_ = 0, head = 0;
   int4 tup = make_int4(0, 0, 0, 0);
   bool dirty = false;
+  if (first) {
+    // the planes the output pass will store into, and the status words (both used only by later launches)
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (uint32_t k = blockIdx.x * kWindow + t; k < a.zero_count; k += gridDim.x * kWindow) a.zero_base[k] = z;
+    if (blockIdx.x == 0 && t < 4) a.status[t] = 0u;
+  }
   __syncthreads();
   const uint32_t limit = active ? min((i + 1) * a.sub_bits, a.nbits) : 0u;
   if (active) {

@@ -93,6 +93,8 @@ struct WholeArgs {
   uint32_t mcux, total_blocks;
   uint32_t nbits, sub_bits, nsub;
   uint32_t *status;        // [0] flags (2 = chain of states not settled, 8 = undecodable), [2] blocks stored
+  uint4 *zero_base;        // the job's coefficient planes, zeroed by the first sync launch together with
+  uint32_t zero_count;     // status[] (one stream operation each less per frame); count in 16-byte units
 };
 cudaError_t launch_huffman_whole(const WholeArgs &a, cudaStream_t stream);
 cudaError_t launch_huffman_finish(const WholeArgs &a, cudaStream_t stream);  // scan + output over the chain as it stands

@@ -8,7 +8,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import bench
 from gid_b200 import host_api
-
 if os.environ.get("FILES_SPARSE_INPUT"):
     host_api.set_option("sparse_input", int(os.environ["FILES_SPARSE_INPUT"]))
 for wl in (sys.argv[1:] or ["cfg3"]):
