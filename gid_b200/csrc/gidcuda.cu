@@ -1,44 +1,19 @@
-// gidcuda.cu -- C-ABI shim of the B200 reconstruction path (include/gidcuda.h).
+// gidcuda.cu -- C-ABI shim of the B200 reconstruction path (include/gidcuda.h): library and device,
+// jobs (one frame through pinned buffers), plans (frames already in device memory), options.
+// gidcuda_scan.cu holds the part for Huffman decoding on the device, gidcuda_batch.cu the multi-GPU
+// batch driver.
 //
 // Owns pinned host buffers, device buffers, streams and launches; the Ada
 // binding GID.CUDA and the C++ host mirror only see plain pointers and sizes.
 // No CPU fallback: every compute entry point needs a CUDA device.
-#include "../../include/gidcuda.h"
-
-#include <cuda_runtime.h>
-
-#include <atomic>
-#include <chrono>
-#include <condition_variable>
-#include <cstdarg>
-#include <cstdio>
-#include <cstring>
-#include <mutex>
-#include <new>
-#include <string>
-#include <thread>
-#include <vector>
-
-#include "launch_set.hpp"
-
-using gidk::FrameDev;
-using gidk::Layout;
+#include "gidcuda_internal.hpp"
 
 // ---------------------------------------------------------------------------
 // errors
 
 static thread_local std::string t_last_error;
 
-struct gidcuda_ctx {
-  int device = -1;
-  int num_sms = 148;
-  cudaStream_t stream = nullptr;
-  std::string last_error;
-  std::vector<gidcuda_job *> free_jobs;  // recycled jobs (buffers kept)
-  int live_jobs = 0;
-};
-
-static int fail(gidcuda_ctx *ctx, int code, const char *fmt, ...) {
+int fail(gidcuda_ctx *ctx, int code, const char *fmt, ...) {
   char buf[512];
   va_list ap;
   va_start(ap, fmt);
@@ -49,23 +24,10 @@ static int fail(gidcuda_ctx *ctx, int code, const char *fmt, ...) {
   return code;
 }
 
-#define CU_TRY(ctx, call)                                                                  \
-  do {                                                                                     \
-    cudaError_t e_ = (call);                                                               \
-    if (e_ != cudaSuccess)                                                                 \
-      return fail((ctx), e_ == cudaErrorMemoryAllocation ? GIDCUDA_ERR_OUT_OF_MEMORY       \
-                                                         : GIDCUDA_ERR_CUDA,               \
-                  "%s failed: %s", #call, cudaGetErrorString(e_));                         \
-  } while (0)
-
 // ---------------------------------------------------------------------------
 // geometry (frame_setup.hpp)
 
-using gidk::Geometry;
-using gidk::fill_frame_dev;
-using gidk::round_up;
-
-static int geometry_or_fail(gidcuda_ctx *ctx, const gidcuda_frame_desc *d, Geometry *g) {
+int geometry_or_fail(gidcuda_ctx *ctx, const gidcuda_frame_desc *d, Geometry *g) {
   std::string err;
   const int rc = gidk::make_geometry(&err, d, g);
   if (rc != GIDCUDA_OK) return fail(ctx, rc, "%s", err.c_str());
@@ -161,48 +123,12 @@ extern "C" int gidcuda_host_free(void *ptr) {
 
 // gidcuda_set_option("blocking_wait"): jobs created from now on sleep in gidcuda_job_wait instead
 // of spinning -- for callers that run about as many host threads as there are cores.
-static int g_blocking_wait = 0;
+int g_blocking_wait = 0;
 // gidcuda_set_option("chain_repair"): 1 (default) = an unsettled chain of the self-synchronising Huffman
 // decoder is repaired by the host (job_repair_chain); 0 = reported as GIDCUDA_ERR_DATA at once.
-static int g_chain_repair = 1;
-static std::atomic<long> g_chain_repairs{0}, g_chain_repair_subsequences{0};
+int g_chain_repair = 1;
+std::atomic<long> g_chain_repairs{0}, g_chain_repair_subsequences{0};
 
-struct gidcuda_job {
-  gidcuda_ctx *ctx = nullptr;
-  gidcuda_frame_desc desc;
-  Geometry geo;
-  // capacities of the recycled buffers
-  size_t cap_coef = 0, cap_pixels = 0, cap_samples = 0, cap_hcoef = 0, cap_sparse = 0;
-  uint8_t *h_coef = nullptr;    // pinned: planes, contiguous; allocated at the first gidcuda_job_plane
-  bool h_coef_clean = false;    // zeroed since gidcuda_job_begin
-  // sparse input: per component [first: nblocks + 1 words][records: capacity words], pinned + device twin
-  uint8_t *h_sparse = nullptr, *d_sparse = nullptr;
-  size_t sparse_off[3] = {0, 0, 0}, sparse_cap[3] = {0, 0, 0}, sparse_count[3] = {0, 0, 0};
-  bool sparse[3] = {false, false, false};  // component committed as records
-  // gidcuda_job_records_commit_runs: (begin, count) of each run inside the lent record array;
-  // empty = one run starting at 0 (gidcuda_job_records_commit)
-  std::vector<std::pair<size_t, size_t>> sparse_runs[3];
-  uint8_t *h_pixels = nullptr;  // pinned
-  // gidcuda_job_scan: [6 HuffDev][begin][end][scan bytes] pinned + device twin, status words
-  uint8_t *h_scan = nullptr, *d_scan = nullptr;
-  size_t cap_scan = 0, scan_bytes = 0, scan_off_begin = 0, scan_off_end = 0, scan_off_data = 0;
-  uint32_t *h_status = nullptr, *d_status = nullptr;
-  bool scan_active = false;
-  int32_t scan_ri = 0, scan_nintervals = 0;
-  // ... scans without restart markers (scan_ri == 0): the self-synchronising decoder's arrays
-  uint8_t *d_sync = nullptr;
-  size_t cap_sync = 0, scan_len = 0;
-  uint32_t scan_nsub = 0, scan_sub_bits = 0;
-  size_t repaired_subsequences = 0;  // subsequences the host walked in the last chain repair
-  uint8_t *user_pixels = nullptr;  // gidcuda_job_output: the caller's own pinned buffer receives the pixels
-  uint8_t *d_coef = nullptr, *d_pixels = nullptr, *d_samples = nullptr;
-  gidk::LaunchSet set;
-  cudaEvent_t done = nullptr;
-  cudaStream_t stream = nullptr;  // one stream per job: two jobs in flight overlap H2D and D2H
-  enum { IDLE, BEGUN, SUBMITTED } state = IDLE;
-  int rows_hint[3] = {8, 8, 8};          // gidcuda_job_hint_rows
-  bool d_tail_zero[3] = {false, false, false};  // rows 4..7 of every block of the device plane are zero
-};
 
 static void job_free_buffers(gidcuda_job *j) {
   if (j->h_coef) cudaFreeHost(j->h_coef);
@@ -451,306 +377,6 @@ extern "C" int gidcuda_job_records_commit_runs(gidcuda_job *job, int comp, int32
   return GIDCUDA_OK;
 }
 
-// Canonical code of a DHT table (Read_DHT, :320-391) in the form the device decoder reads.
-static bool build_huff_dev(const gidcuda_huffman_table &t, gidk::HuffDev *d) {
-  memset(d, 0, sizeof *d);
-  int code = 0, k = 0;
-  for (int len = 1; len <= 16; len++) {
-    d->valoff[len] = k - code;
-    for (int i = 0; i < t.counts[len - 1]; i++, k++, code++) {
-      if (k > 255 || code >= (1 << len)) return false;  // more symbols than a table holds / over-subscribed
-      d->vals[k] = t.symbols[k];
-      if (len <= 10) {
-        const int first = code << (10 - len), n = 1 << (10 - len);
-        for (int j = 0; j < n; j++) d->lut[first + j] = (uint16_t)((len << 8) | t.symbols[k]);
-      }
-    }
-    d->maxcode[len] = t.counts[len - 1] ? code - 1 : -1;
-    code <<= 1;
-  }
-  return true;
-}
-
-// One device thread per this many bits of a scan without restart markers.  Short subsequences mean
-// more threads and shorter rounds; but a decoder only re-synchronises at block boundaries, so where
-// blocks are long (high qualities: hundreds of bits each) short subsequences would need many rounds
-// to carry the true state across a window -- those scans get longer subsequences.
-constexpr uint32_t kSubsequenceBits = 256, kSubsequenceBitsDense = 1024;
-constexpr uint32_t kDenseBitsPerBlock = 96;
-
-// gidcuda_job_scan with restart_interval == 0: the whole scan, byte stuffing removed by the caller.
-static int job_scan_whole(gidcuda_job *job, const gidcuda_scan_desc *scan, const uint8_t *data, size_t len) {
-  gidcuda_ctx *ctx = job->ctx;
-  const Geometry &g = job->geo;
-  int bpm = 0;
-  for (int c = 0; c < g.ncomp; c++) bpm += job->desc.samp_h[c] * job->desc.samp_v[c];
-  if (bpm > 12) return fail(ctx, GIDCUDA_ERR_UNSUPPORTED, "gidcuda_job_scan: %d blocks per MCU", bpm);
-  CU_TRY(ctx, cudaSetDevice(ctx->device));
-  const size_t off_data = round_up(6 * sizeof(gidk::HuffDev), 256);
-  const size_t total = off_data + round_up(len + 64, 256);  // FF padding: the decoder looks a few bytes ahead
-  if (job->cap_scan < total) {
-    if (job->h_scan) cudaFreeHost(job->h_scan);
-    if (job->d_scan) cudaFree(job->d_scan);
-    job->h_scan = job->d_scan = nullptr;
-    job->cap_scan = 0;
-    const size_t cap = total + total / 4;
-    CU_TRY(ctx, cudaHostAlloc((void **)&job->h_scan, cap, cudaHostAllocDefault));
-    CU_TRY(ctx, cudaMalloc((void **)&job->d_scan, cap));
-    job->cap_scan = cap;
-  }
-  if (!job->h_status) {
-    CU_TRY(ctx, cudaHostAlloc((void **)&job->h_status, 16, cudaHostAllocDefault));
-    CU_TRY(ctx, cudaMalloc((void **)&job->d_status, 16));
-  }
-  uint64_t frame_blocks = 0;
-  for (int c = 0; c < g.ncomp; c++) frame_blocks += (uint64_t)g.bx[c] * g.by[c];
-  const uint32_t sub_bits = (uint64_t)len * 8 > frame_blocks * kDenseBitsPerBlock ? kSubsequenceBitsDense : kSubsequenceBits;
-  const uint32_t nsub = (uint32_t)((len * 8 + sub_bits - 1) / sub_bits);
-  const size_t sync_bytes = (size_t)nsub * (8 + 8 + 16 + 16) + 1024;
-  if (job->cap_sync < sync_bytes) {
-    if (job->d_sync) cudaFree(job->d_sync);
-    job->d_sync = nullptr;
-    job->cap_sync = 0;
-    const size_t cap = sync_bytes + sync_bytes / 4;
-    CU_TRY(ctx, cudaMalloc((void **)&job->d_sync, cap));
-    job->cap_sync = cap;
-  }
-  gidk::HuffDev *tabs = reinterpret_cast<gidk::HuffDev *>(job->h_scan);
-  for (int c = 0; c < 3; c++) {
-    const bool used = c < g.ncomp;
-    if (!build_huff_dev(scan->dc[used ? c : 0], &tabs[c]) || !build_huff_dev(scan->ac[used ? c : 0], &tabs[3 + c]))
-      return fail(ctx, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_job_scan: Huffman table of component %d is not a prefix code", c);
-  }
-  memcpy(job->h_scan + off_data, data, len);
-  memset(job->h_scan + off_data + len, 0xFF, total - off_data - len);
-  job->scan_off_data = off_data;
-  job->scan_bytes = total;
-  job->scan_len = len;
-  job->scan_nsub = nsub;
-  job->scan_sub_bits = sub_bits;
-  job->scan_ri = 0;
-  job->scan_nintervals = 0;
-  job->scan_active = true;
-  return GIDCUDA_OK;
-}
-
-extern "C" int gidcuda_job_scan(gidcuda_job *job, const gidcuda_scan_desc *scan, const uint8_t *data, size_t len,
-                                const uint32_t *begin, const uint32_t *end) {
-  if (!job) return fail(nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "null job");
-  gidcuda_ctx *ctx = job->ctx;
-  if (job->state != gidcuda_job::BEGUN)
-    return fail(ctx, GIDCUDA_ERR_STATE, "gidcuda_job_scan: only between gidcuda_job_begin and gidcuda_job_submit");
-  if (!scan || !data || len == 0 || len >= ((size_t)1 << 28) || (scan->restart_interval != 0 && (!begin || !end)))
-    return fail(ctx, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_job_scan: null argument, no data or more than 256 MiB of it");
-  const Geometry &g = job->geo;
-  const int64_t nmcu = (int64_t)g.mcux * g.mcuy;
-  if (scan->restart_interval == 0) return job_scan_whole(job, scan, data, len);
-  if (scan->restart_interval <= 0 || scan->nintervals <= 0 ||
-      (nmcu + scan->restart_interval - 1) / scan->restart_interval != scan->nintervals)
-    return fail(ctx, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_job_scan: %d intervals of %d MCUs do not cover %lld MCUs",
-                (int)scan->nintervals, (int)scan->restart_interval, (long long)nmcu);
-  const size_t nint = (size_t)scan->nintervals;
-  for (size_t i = 0; i < nint; i++)
-    if (begin[i] > end[i] || end[i] > len)
-      return fail(ctx, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_job_scan: interval %zu = [%u, %u) outside the %zu bytes", i,
-                  begin[i], end[i], len);
-  CU_TRY(ctx, cudaSetDevice(ctx->device));
-  const size_t off_begin = round_up(6 * sizeof(gidk::HuffDev), 256);
-  const size_t off_end = off_begin + round_up(nint * 4, 256);
-  const size_t off_data = off_end + round_up(nint * 4, 256);
-  const size_t total = off_data + round_up(len, 256);
-  if (job->cap_scan < total) {
-    if (job->h_scan) cudaFreeHost(job->h_scan);
-    if (job->d_scan) cudaFree(job->d_scan);
-    job->h_scan = job->d_scan = nullptr;
-    job->cap_scan = 0;
-    const size_t cap = total + total / 4;  // the next frame of a batch is rarely the same size
-    CU_TRY(ctx, cudaHostAlloc((void **)&job->h_scan, cap, cudaHostAllocDefault));
-    CU_TRY(ctx, cudaMalloc((void **)&job->d_scan, cap));
-    job->cap_scan = cap;
-  }
-  if (!job->h_status) {
-    CU_TRY(ctx, cudaHostAlloc((void **)&job->h_status, 16, cudaHostAllocDefault));
-    CU_TRY(ctx, cudaMalloc((void **)&job->d_status, 16));
-  }
-  gidk::HuffDev *tabs = reinterpret_cast<gidk::HuffDev *>(job->h_scan);
-  for (int c = 0; c < 3; c++) {
-    const bool used = c < g.ncomp;
-    if (!build_huff_dev(scan->dc[used ? c : 0], &tabs[c]) || !build_huff_dev(scan->ac[used ? c : 0], &tabs[3 + c]))
-      return fail(ctx, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_job_scan: Huffman table of component %d is not a prefix code", c);
-  }
-  memcpy(job->h_scan + off_begin, begin, nint * 4);
-  memcpy(job->h_scan + off_end, end, nint * 4);
-  memcpy(job->h_scan + off_data, data, len);
-  job->scan_off_begin = off_begin;
-  job->scan_off_end = off_end;
-  job->scan_off_data = off_data;
-  job->scan_bytes = total;
-  job->scan_ri = scan->restart_interval;
-  job->scan_nintervals = scan->nintervals;
-  job->scan_active = true;
-  return GIDCUDA_OK;
-}
-
-// The self-synchronising decoder's arguments for the scan a job holds (gidcuda_job_scan, restart_interval = 0).
-static void make_whole_args(gidcuda_job *job, gidk::WholeArgs *out) {
-  const Geometry &g = job->geo;
-  gidk::WholeArgs &wa = *out;
-  memset(&wa, 0, sizeof wa);
-  wa.data = job->d_scan + job->scan_off_data;
-  wa.tables = reinterpret_cast<const gidk::HuffDev *>(job->d_scan);
-  const size_t n = job->scan_nsub;
-  wa.entry = reinterpret_cast<uint64_t *>(job->d_sync);
-  wa.exit_ = wa.entry + n;
-  wa.tuple = reinterpret_cast<int4 *>(job->d_sync + round_up(16 * n, 256));
-  wa.prefix = wa.tuple + n;
-  uint32_t k = 0, blocks = 0;
-  for (int c = 0; c < g.ncomp; c++) {
-    wa.plane[c] = reinterpret_cast<int16_t *>(job->d_coef + g.plane_off[c]);
-    wa.bx[c] = (uint32_t)g.bx[c];
-    wa.h[c] = job->desc.samp_h[c];
-    wa.v[c] = job->desc.samp_v[c];
-    blocks += (uint32_t)g.bx[c] * (uint32_t)g.by[c];
-    k += (uint32_t)(wa.h[c] * wa.v[c]);
-    job->d_tail_zero[c] = false;
-  }
-  wa.bpm = k;
-  wa.mcux = (uint32_t)g.mcux;
-  wa.total_blocks = blocks;
-  wa.nbits = (uint32_t)(job->scan_len * 8);
-  wa.sub_bits = job->scan_sub_bits;
-  wa.nsub = job->scan_nsub;
-  wa.status = job->d_status;
-  wa.zero_base = reinterpret_cast<uint4 *>(job->d_coef);
-  wa.zero_count = (uint32_t)(g.coef_bytes / 16);
-}
-
-// ---- chain repair on the host -------------------------------------------------------------------
-// A stretch of the scan that does not re-synchronise (a flat region: the same two code words over and
-// over, so a decoder in the wrong phase stays there) leaves the device's chain of states broken: truth
-// only advances one subsequence per round there.  Walking such a stretch is a SERIAL job, which one host
-// core does an order of magnitude faster than one GPU thread.  So when the output pass reports an
-// unsettled chain (and nothing undecodable), gidcuda_job_wait fetches the chain, walks it from the true
-// start state -- where a subsequence's recorded entry state is the true one its recorded exit and counts
-// are kept, where not the host decodes that subsequence (the mirror of run_subsequence<false> in
-// entropy_kernel.cu) -- sends it back and runs prefix sums, output pass and reconstruction again.  The
-// output pass verifies the repaired chain like any other.
-namespace {
-
-struct HostWalk {
-  const uint8_t *data;  // unstuffed scan bytes, FF-padded (the job's pinned staging copy)
-  const gidk::HuffDev *tabs;
-  uint32_t bpm;
-  uint8_t comp[12];
-};
-
-inline uint32_t host_peek(const uint8_t *d, uint32_t pos, int n) {  // n <= 16
-  const uint8_t *p = d + (pos >> 3);
-  const uint32_t w = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
-  return (w << (pos & 7u)) >> (32 - n);
-}
-
-inline int host_extend(uint32_t v, int n) { return v < (1u << (n - 1)) ? (int)v + 1 - (1 << n) : (int)v; }
-
-uint64_t host_run_subsequence(const HostWalk &w, uint64_t entry, uint32_t limit, int32_t tup[4]) {
-  uint32_t pos = (uint32_t)entry, c = (uint32_t)(entry >> 32) & 0xFFu, zpos = (uint32_t)(entry >> 40) & 0xFFu;
-  int nb = 0, dcs[3] = {0, 0, 0};
-  while (pos < limit) {
-    const int k = w.comp[c];
-    const gidk::HuffDev &t = zpos == 0 ? w.tabs[k] : w.tabs[3 + k];
-    const uint32_t look = host_peek(w.data, pos, 16);
-    const uint32_t e = t.lut[look >> 6];
-    int l = (int)(e >> 8), sym = (int)(e & 0xFFu);
-    if (e == 0) {
-      sym = -1;
-      for (l = 11; l <= 16; l++) {
-        const int code = (int)(look >> (16 - l));
-        if (code <= t.maxcode[l]) {
-          sym = t.vals[(t.valoff[l] + code) & 0xFF];
-          break;
-        }
-      }
-      if (sym < 0) {
-        pos += 1;
-        continue;
-      }
-    }
-    pos += (uint32_t)l;
-    const int n = sym & 15;
-    bool block_done = false;
-    if (zpos == 0) {
-      if (n) {
-        dcs[k] += host_extend(host_peek(w.data, pos, n), n);
-        pos += (uint32_t)n;
-      }
-      zpos = 1;
-    } else if (sym == 0) {
-      block_done = true;
-    } else {
-      const uint32_t idx = zpos + (uint32_t)(sym >> 4);
-      pos += (uint32_t)n;
-      if (idx >= 63) block_done = true;
-      else zpos = idx + 1;
-    }
-    if (block_done) {
-      zpos = 0;
-      c = c + 1 == w.bpm ? 0 : c + 1;
-      nb++;
-    }
-  }
-  tup[0] = nb; tup[1] = dcs[0]; tup[2] = dcs[1]; tup[3] = dcs[2];
-  return (uint64_t)pos | ((uint64_t)c << 32) | ((uint64_t)zpos << 40);
-}
-
-}  // namespace
-
-// Returns GIDCUDA_OK when the repaired chain has been re-submitted (the caller waits for job->done again).
-static int job_repair_chain(gidcuda_job *job) {
-  gidcuda_ctx *ctx = job->ctx;
-  const Geometry &g = job->geo;
-  cudaStream_t s = job->stream;
-  gidk::WholeArgs wa;
-  make_whole_args(job, &wa);
-  const size_t n = wa.nsub;
-  std::vector<uint64_t> st(2 * n);   // entry[], exit[]
-  std::vector<int32_t> tup(4 * n);
-  CU_TRY(ctx, cudaMemcpyAsync(st.data(), wa.entry, 16 * n, cudaMemcpyDeviceToHost, s));
-  CU_TRY(ctx, cudaMemcpyAsync(tup.data(), wa.tuple, 16 * n, cudaMemcpyDeviceToHost, s));
-  CU_TRY(ctx, cudaStreamSynchronize(s));
-  HostWalk w;
-  w.data = job->h_scan + job->scan_off_data;
-  w.tabs = reinterpret_cast<const gidk::HuffDev *>(job->h_scan);
-  w.bpm = wa.bpm;
-  uint32_t k = 0;
-  for (int c = 0; c < g.ncomp; c++)
-    for (int i = 0; i < job->desc.samp_h[c] * job->desc.samp_v[c]; i++) w.comp[k++] = (uint8_t)c;
-  uint64_t state = 0;  // the true start: bit 0, first block of the MCU, DC next
-  uint64_t blocks = 0;
-  size_t walked = 0;
-  for (size_t i = 0; i < n && blocks < wa.total_blocks; i++) {
-    if (st[i] != state) {
-      const uint32_t limit = std::min<uint64_t>((uint64_t)(i + 1) * wa.sub_bits, wa.nbits);
-      st[i] = state;
-      st[n + i] = host_run_subsequence(w, state, limit, &tup[4 * i]);
-      walked++;
-    }
-    state = st[n + i];
-    blocks += (uint64_t)tup[4 * i];
-  }
-  job->repaired_subsequences = walked;
-  CU_TRY(ctx, cudaMemcpyAsync(wa.entry, st.data(), 16 * n, cudaMemcpyHostToDevice, s));
-  CU_TRY(ctx, cudaMemcpyAsync(wa.tuple, tup.data(), 16 * n, cudaMemcpyHostToDevice, s));
-  CU_TRY(ctx, cudaMemsetAsync(job->d_coef, 0, g.coef_bytes, s));
-  CU_TRY(ctx, cudaMemsetAsync(job->d_status, 0, 16, s));
-  CU_TRY(ctx, gidk::launch_huffman_finish(wa, s));
-  CU_TRY(ctx, cudaMemcpyAsync(job->h_status, job->d_status, 16, cudaMemcpyDeviceToHost, s));
-  CU_TRY(ctx, job->set.launch(ctx->num_sms, s));
-  CU_TRY(ctx, cudaMemcpyAsync(job->user_pixels ? job->user_pixels : job->h_pixels, job->d_pixels, g.pixel_bytes,
-                              cudaMemcpyDeviceToHost, s));
-  CU_TRY(ctx, cudaStreamSynchronize(s));  // (st / tup are this function's: the copies must be done before they go)
-  return GIDCUDA_OK;
-}
-
 static bool is_pinned_host(const void *p) {
   cudaPointerAttributes at;
   if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
@@ -806,40 +432,9 @@ extern "C" int gidcuda_job_submit(gidcuda_job *job) {
   //   large, a pitched copy of the upper 64 bytes of every block (measured 1.5x faster than the
   //   full plane on this link; narrower or wider partial rows are not faster than a full copy,
   //   and below a few MiB the extra calls cost more than the bytes saved: measured on 1080p).
-  if (job->scan_active) {
-    // compressed bytes -> device, planes zeroed, one thread per restart interval decodes
-    CU_TRY(ctx, cudaMemcpyAsync(job->d_scan, job->h_scan, job->scan_bytes, cudaMemcpyHostToDevice, s));
-    if (job->scan_ri != 0) {  // (the self-synchronising decoder's first launch zeroes both itself)
-      CU_TRY(ctx, cudaMemsetAsync(job->d_coef, 0, g.coef_bytes, s));
-      CU_TRY(ctx, cudaMemsetAsync(job->d_status, 0, 16, s));
-    }
-    if (job->scan_ri == 0) {
-      gidk::WholeArgs wa;
-      make_whole_args(job, &wa);
-      CU_TRY(ctx, gidk::launch_huffman_whole(wa, s));
-    } else {
-      gidk::ScanArgs sa;
-      memset(&sa, 0, sizeof sa);
-      sa.data = job->d_scan + job->scan_off_data;
-      sa.begin = reinterpret_cast<const uint32_t *>(job->d_scan + job->scan_off_begin);
-      sa.end = reinterpret_cast<const uint32_t *>(job->d_scan + job->scan_off_end);
-      sa.tables = reinterpret_cast<const gidk::HuffDev *>(job->d_scan);
-      for (int c = 0; c < g.ncomp; c++) {
-        sa.plane[c] = reinterpret_cast<int16_t *>(job->d_coef + g.plane_off[c]);
-        sa.bx[c] = (uint32_t)g.bx[c];
-        sa.h[c] = job->desc.samp_h[c];
-        sa.v[c] = job->desc.samp_v[c];
-        job->d_tail_zero[c] = false;
-      }
-      sa.ncomp = g.ncomp;
-      sa.mcux = (uint32_t)g.mcux;
-      sa.nmcu = (uint32_t)g.mcux * (uint32_t)g.mcuy;
-      sa.ri = (uint32_t)job->scan_ri;
-      sa.nintervals = (uint32_t)job->scan_nintervals;
-      sa.status = job->d_status;
-      CU_TRY(ctx, gidk::launch_huffman_intervals(sa, s));
-    }
-    CU_TRY(ctx, cudaMemcpyAsync(job->h_status, job->d_status, 16, cudaMemcpyDeviceToHost, s));
+  if (job->scan_active) {  // compressed bytes -> device, Huffman decoding there (gidcuda_scan.cu)
+    const int rc = job_submit_scan(job, s);
+    if (rc != GIDCUDA_OK) return rc;
   }
   constexpr size_t kMinPitchedPlane = (size_t)8 << 20;
   bool any_sparse = false, all_dense_plain = true;
@@ -926,32 +521,9 @@ extern "C" int gidcuda_job_wait(gidcuda_job *job, const uint8_t **pixels, size_t
   if (job->state != gidcuda_job::SUBMITTED)
     return fail(ctx, GIDCUDA_ERR_STATE, "gidcuda_job_wait: job was not submitted");
   CU_TRY(ctx, cudaEventSynchronize(job->done));
-  if (job->scan_active) {
-    job->scan_active = false;  // a re-submission after a host decode takes planes / records
-    uint32_t blocks = 0;
-    for (int c = 0; c < job->geo.ncomp; c++) blocks += (uint32_t)job->geo.bx[c] * (uint32_t)job->geo.by[c];
-    if (job->scan_ri == 0 && (job->h_status[0] & 2u) && g_chain_repair) {
-      // an unsettled chain: the host walks the stretches that did not re-synchronise.  (Threads that
-      // decoded from a consistent but untrue state may have met undecodable codes, flag 8, as well:
-      // the output pass over the repaired chain tells whether the stream itself is damaged.)
-      const int rc = job_repair_chain(job);
-      if (rc != GIDCUDA_OK) return rc;
-      g_chain_repairs.fetch_add(1, std::memory_order_relaxed);
-      g_chain_repair_subsequences.fetch_add((long)job->repaired_subsequences, std::memory_order_relaxed);
-    }
-    if (job->scan_ri == 0 && job->h_status[0] == 0 && job->h_status[2] != blocks) job->h_status[0] = 4;
-    if (job->scan_ri == 0 && job->h_status[0] != 0) {
-      job->state = gidcuda_job::BEGUN;
-      return fail(ctx, GIDCUDA_ERR_DATA,
-                  "device entropy decoder: scan left to the host decoder (flags %u, %u of %u blocks)", job->h_status[0],
-                  job->h_status[2], blocks);
-    }
-    if (job->h_status[0] != 0) {
-      job->state = gidcuda_job::BEGUN;
-      return fail(ctx, GIDCUDA_ERR_DATA,
-                  "device entropy decoder: %u restart interval(s) left to the host decoder (damaged or unusual stream)",
-                  job->h_status[1]);
-    }
+  if (job->scan_active) {  // what the device decoder made of the scan (the host's chain repair included)
+    const int rc = job_finish_scan(job);
+    if (rc != GIDCUDA_OK) return rc;
   }
   if (pixels) *pixels = job->user_pixels ? job->user_pixels : job->h_pixels;
   if (stride) *stride = job->geo.stride;
@@ -1095,294 +667,3 @@ extern "C" long gidcuda_counter(const char *name) {
 
 extern "C" int gidcuda_plan_uses_tma(const gidcuda_plan *plan) { return plan ? plan->set.tma_groups : 0; }
 
-// ---------------------------------------------------------------------------
-// batch driver: per-GPU worker thread + work queue + ring of in-flight chunks
-
-namespace {
-
-struct BatchRun {
-  int32_t n = 0;
-  const gidcuda_frame_desc *descs = nullptr;
-  const int16_t *const *planes = nullptr;
-  uint8_t *const *pixels = nullptr;
-  int32_t *status = nullptr;
-  std::atomic<int32_t> next{0};  // shared work queue: next image index (dynamic sharding)
-  std::atomic<int64_t> h2d{0}, d2h{0};
-  std::atomic<int32_t> launches{0}, failed{0};
-  int32_t per_device[16] = {0};
-};
-
-// A chunk in flight on one device: staging buffers + launch tables.
-struct ChunkSlot {
-  cudaStream_t stream = nullptr;
-  cudaEvent_t done = nullptr;
-  uint8_t *h_in = nullptr, *d_in = nullptr, *h_out = nullptr, *d_out = nullptr;
-  size_t cap_in = 0, cap_out = 0;
-  uint8_t *d_samples = nullptr;
-  size_t cap_samples = 0;
-  gidk::LaunchSet set;
-  // contents
-  std::vector<int32_t> images;
-  std::vector<Geometry> geos;
-  std::vector<size_t> out_off;
-  bool busy = false;
-};
-
-struct Worker {
-  int device = 0;
-  int index = 0;
-  int num_sms = 148;
-  std::thread thread;
-  std::vector<ChunkSlot> slots;
-};
-
-}  // namespace
-
-struct gidcuda_batch {
-  std::vector<Worker> workers;
-  int chunk_images = 8;
-  std::mutex mu;
-  std::condition_variable cv_start, cv_done;
-  BatchRun *run = nullptr;
-  uint64_t generation = 0;
-  int pending = 0;
-  bool quit = false;
-  std::string error;
-};
-
-namespace {
-
-bool cu_ok(gidcuda_batch *b, cudaError_t e, const char *what) {
-  if (e == cudaSuccess) return true;
-  std::lock_guard<std::mutex> lk(b->mu);
-  if (b->error.empty()) b->error = std::string(what) + ": " + cudaGetErrorString(e);
-  return false;
-}
-
-bool grow_pair(gidcuda_batch *b, uint8_t **h, uint8_t **d, size_t *cap, size_t need, bool host_too) {
-  if (*cap >= need) return true;
-  if (host_too && *h) cudaFreeHost(*h);
-  if (*d) cudaFree(*d);
-  if (host_too) *h = nullptr;
-  *d = nullptr;
-  *cap = 0;
-  need += need / 4;
-  if (host_too && !cu_ok(b, cudaHostAlloc((void **)h, need, cudaHostAllocDefault), "cudaHostAlloc")) return false;
-  if (!cu_ok(b, cudaMalloc((void **)d, need), "cudaMalloc")) return false;
-  *cap = need;
-  return true;
-}
-
-// Finish a slot: wait for its stream, copy pixels to the caller's buffers.
-void slot_finish(gidcuda_batch *b, BatchRun *run, ChunkSlot &s) {
-  if (!s.busy) return;
-  const bool ok = cu_ok(b, cudaEventSynchronize(s.done), "cudaEventSynchronize");
-  for (size_t k = 0; k < s.images.size(); k++) {
-    const int32_t i = s.images[k];
-    if (ok) {
-      memcpy(run->pixels[i], s.h_out + s.out_off[k], s.geos[k].pixel_bytes);
-      if (run->status) run->status[i] = GIDCUDA_OK;
-    } else {
-      if (run->status) run->status[i] = GIDCUDA_ERR_CUDA;
-      run->failed++;
-    }
-  }
-  s.busy = false;
-}
-
-// Fill a slot with up to chunk_images images from the shared queue and submit.
-// Returns false when the queue is empty.
-bool slot_submit(gidcuda_batch *b, BatchRun *run, Worker &w, ChunkSlot &s) {
-  s.images.clear();
-  s.geos.clear();
-  s.out_off.clear();
-  size_t in_bytes = 0, out_bytes = 0, samples = 0;
-  std::vector<size_t> in_off, sample_off;
-  bool drained = false;
-  while ((int)s.images.size() < b->chunk_images) {
-    const int32_t i = run->next.fetch_add(1);
-    if (i >= run->n) { drained = true; break; }
-    Geometry g;
-    const int rc = geometry_or_fail(nullptr, &run->descs[i], &g);
-    bool good = rc == GIDCUDA_OK && run->pixels[i] != nullptr;
-    for (int c = 0; good && c < g.ncomp; c++) good = run->planes[3 * i + c] != nullptr;
-    if (!good) {
-      // a failed image is reported and skipped; the others are unaffected
-      if (run->status) run->status[i] = rc != GIDCUDA_OK ? rc : GIDCUDA_ERR_BAD_ARGUMENT;
-      run->failed++;
-      continue;
-    }
-    s.images.push_back(i);
-    s.geos.push_back(g);
-    in_off.push_back(in_bytes);
-    s.out_off.push_back(out_bytes);
-    sample_off.push_back(samples);
-    in_bytes += g.coef_bytes;
-    out_bytes += round_up(g.pixel_bytes, 256);
-    if (g.layout == gidk::LAYOUT_GENERIC) samples += round_up(g.sample_bytes, 256);
-  }
-  if (s.images.empty()) return !drained;
-  const size_t nf = s.images.size();
-  uint8_t *none = nullptr;
-  if (!grow_pair(b, &s.h_in, &s.d_in, &s.cap_in, in_bytes, true)) return true;
-  if (!grow_pair(b, &s.h_out, &s.d_out, &s.cap_out, out_bytes, true)) return true;
-  if (samples && !grow_pair(b, &none, &s.d_samples, &s.cap_samples, samples, false)) return true;
-  // stage coefficients into pinned memory, then one H2D copy per chunk
-  std::vector<gidk::FrameItem> items(nf);
-  for (size_t k = 0; k < nf; k++) {
-    const int32_t i = s.images[k];
-    const Geometry &g = s.geos[k];
-    gidk::FrameItem &it = items[k];
-    it.desc = &run->descs[i];
-    it.geo = g;
-    for (int c = 0; c < 3; c++) {
-      it.planes[c] = nullptr;
-      if (c >= g.ncomp) continue;
-      memcpy(s.h_in + in_off[k] + g.plane_off[c], run->planes[3 * i + c], g.plane_bytes[c]);
-      it.planes[c] = reinterpret_cast<const int16_t *>(s.d_in + in_off[k] + g.plane_off[c]);
-    }
-    it.pixels = s.d_out + s.out_off[k];
-    it.samples = g.layout == gidk::LAYOUT_GENERIC ? s.d_samples + sample_off[k] : nullptr;
-  }
-  s.set.build(items);
-  cudaStream_t st = s.stream;
-  bool ok = cu_ok(b, cudaMemcpyAsync(s.d_in, s.h_in, in_bytes, cudaMemcpyHostToDevice, st), "H2D coefficients");
-  ok = ok && cu_ok(b, s.set.upload(st), "H2D launch tables");
-  ok = ok && cu_ok(b, s.set.launch(w.num_sms, st), "kernel launch");
-  ok = ok && cu_ok(b, cudaMemcpyAsync(s.h_out, s.d_out, out_bytes, cudaMemcpyDeviceToHost, st), "D2H pixels");
-  ok = ok && cu_ok(b, cudaEventRecord(s.done, st), "cudaEventRecord");
-  if (!ok) {
-    for (int32_t i : s.images) {
-      if (run->status) run->status[i] = GIDCUDA_ERR_CUDA;
-      run->failed++;
-    }
-    return !drained;  // keep draining the queue so that every image gets a status
-  }
-  run->h2d += (int64_t)(in_bytes + s.set.upload_bytes);
-  run->d2h += (int64_t)out_bytes;
-  run->launches += s.set.launch_count();
-  run->per_device[w.index] += (int32_t)nf;
-  s.busy = true;
-  return !drained;
-}
-
-void worker_main(gidcuda_batch *b, Worker *w) {
-  uint64_t seen = 0;
-  cu_ok(b, cudaSetDevice(w->device), "cudaSetDevice");
-  cu_ok(b, cudaDeviceGetAttribute(&w->num_sms, cudaDevAttrMultiProcessorCount, w->device), "device attribute");
-  cu_ok(b, gidk::init_kernels(), "kernel set-up");
-  for (ChunkSlot &s : w->slots) {
-    cu_ok(b, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), "cudaStreamCreate");
-    cu_ok(b, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming), "cudaEventCreate");
-  }
-  for (;;) {
-    BatchRun *run;
-    {
-      std::unique_lock<std::mutex> lk(b->mu);
-      b->cv_start.wait(lk, [&] { return b->quit || b->generation != seen; });
-      if (b->quit) break;
-      seen = b->generation;
-      run = b->run;
-    }
-    // ring of slots: finish the oldest slot, refill it, move on
-    size_t cur = 0;
-    bool more = true;
-    while (more) {
-      ChunkSlot &s = w->slots[cur];
-      slot_finish(b, run, s);
-      more = slot_submit(b, run, *w, s);
-      cur = (cur + 1) % w->slots.size();
-    }
-    for (size_t k = 0; k < w->slots.size(); k++) slot_finish(b, run, w->slots[(cur + k) % w->slots.size()]);
-    {
-      std::lock_guard<std::mutex> lk(b->mu);
-      if (--b->pending == 0) b->cv_done.notify_all();
-    }
-  }
-  for (ChunkSlot &s : w->slots) {
-    if (s.h_in) cudaFreeHost(s.h_in);
-    if (s.h_out) cudaFreeHost(s.h_out);
-    if (s.d_in) cudaFree(s.d_in);
-    if (s.d_out) cudaFree(s.d_out);
-    if (s.d_samples) cudaFree(s.d_samples);
-    s.set.destroy();
-    if (s.done) cudaEventDestroy(s.done);
-    if (s.stream) cudaStreamDestroy(s.stream);
-  }
-}
-
-}  // namespace
-
-extern "C" int gidcuda_batch_create(const int32_t *devices, int32_t ndevices, int32_t chunk_images,
-                                    gidcuda_batch **out) {
-  if (!out || ndevices < 1 || ndevices > 16 || !devices)
-    return fail(nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_batch_create: bad argument");
-  *out = nullptr;
-  const int n = gidcuda_device_count();
-  if (n == 0) return fail(nullptr, GIDCUDA_ERR_NO_DEVICE, "no CUDA device: no CPU fallback");
-  for (int i = 0; i < ndevices; i++)
-    if (devices[i] < 0 || devices[i] >= n)
-      return fail(nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "device %d out of range", devices[i]);
-  gidcuda_batch *b = new (std::nothrow) gidcuda_batch();
-  if (!b) return fail(nullptr, GIDCUDA_ERR_OUT_OF_MEMORY, "out of host memory");
-  b->chunk_images = chunk_images > 0 ? chunk_images : 8;
-  b->workers.resize((size_t)ndevices);
-  for (int i = 0; i < ndevices; i++) {
-    b->workers[(size_t)i].device = devices[i];
-    b->workers[(size_t)i].index = i;
-    b->workers[(size_t)i].slots.resize(3);
-  }
-  for (Worker &w : b->workers) w.thread = std::thread(worker_main, b, &w);
-  *out = b;
-  return GIDCUDA_OK;
-}
-
-extern "C" int gidcuda_batch_run(gidcuda_batch *b, int32_t n, const gidcuda_frame_desc *descs,
-                                 const int16_t *const *planes, uint8_t *const *pixels, int32_t *status,
-                                 gidcuda_batch_stats *stats) {
-  if (!b || n < 0 || (n > 0 && (!descs || !planes || !pixels)))
-    return fail(nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_batch_run: bad argument");
-  BatchRun run;
-  run.n = n;
-  run.descs = descs;
-  run.planes = planes;
-  run.pixels = pixels;
-  run.status = status;
-  const auto t0 = std::chrono::steady_clock::now();
-  {
-    std::unique_lock<std::mutex> lk(b->mu);
-    b->error.clear();
-    b->run = &run;
-    b->pending = (int)b->workers.size();
-    b->generation++;
-    b->cv_start.notify_all();
-    b->cv_done.wait(lk, [&] { return b->pending == 0; });
-    b->run = nullptr;
-  }
-  const auto t1 = std::chrono::steady_clock::now();
-  if (stats) {
-    memset(stats, 0, sizeof *stats);
-    stats->seconds = std::chrono::duration<double>(t1 - t0).count();
-    for (int32_t i = 0; i < n; i++) stats->megapixels += (double)descs[i].width * descs[i].height / 1e6;
-    stats->h2d_bytes = run.h2d;
-    stats->d2h_bytes = run.d2h;
-    stats->kernel_launches = run.launches;
-    stats->images_failed = run.failed;
-    for (int i = 0; i < 16; i++) stats->images_per_device[i] = run.per_device[i];
-  }
-  if (!b->error.empty()) return fail(nullptr, GIDCUDA_ERR_CUDA, "batch: %s", b->error.c_str());
-  return GIDCUDA_OK;
-}
-
-extern "C" int gidcuda_batch_destroy(gidcuda_batch *b) {
-  if (!b) return GIDCUDA_OK;
-  {
-    std::lock_guard<std::mutex> lk(b->mu);
-    b->quit = true;
-    b->cv_start.notify_all();
-  }
-  for (Worker &w : b->workers)
-    if (w.thread.joinable()) w.thread.join();
-  delete b;
-  return GIDCUDA_OK;
-}

@@ -1,0 +1,376 @@
+// gidcuda_scan.cu -- the C-ABI shim's part for Huffman decoding on the device (gidcuda_job_scan,
+// include/gidcuda.h): staging of the scan's bytes and code tables, the launches of entropy_kernel.cu,
+// and -- for the self-synchronising decoder -- the host's repair of a chain of decoder states that has
+// not settled.
+#include "gidcuda_internal.hpp"
+
+// Canonical code of a DHT table (Read_DHT, :320-391) in the form the device decoder reads.
+static bool build_huff_dev(const gidcuda_huffman_table &t, gidk::HuffDev *d) {
+  memset(d, 0, sizeof *d);
+  int code = 0, k = 0;
+  for (int len = 1; len <= 16; len++) {
+    d->valoff[len] = k - code;
+    for (int i = 0; i < t.counts[len - 1]; i++, k++, code++) {
+      if (k > 255 || code >= (1 << len)) return false;  // more symbols than a table holds / over-subscribed
+      d->vals[k] = t.symbols[k];
+      if (len <= 10) {
+        const int first = code << (10 - len), n = 1 << (10 - len);
+        for (int j = 0; j < n; j++) d->lut[first + j] = (uint16_t)((len << 8) | t.symbols[k]);
+      }
+    }
+    d->maxcode[len] = t.counts[len - 1] ? code - 1 : -1;
+    code <<= 1;
+  }
+  return true;
+}
+
+// One device thread per this many bits of a scan without restart markers.  Short subsequences mean
+// more threads and shorter rounds; but a decoder only re-synchronises at block boundaries, so where
+// blocks are long (high qualities: hundreds of bits each) short subsequences would need many rounds
+// to carry the true state across a window -- those scans get longer subsequences.
+constexpr uint32_t kSubsequenceBits = 256, kSubsequenceBitsDense = 1024;
+constexpr uint32_t kDenseBitsPerBlock = 96;
+
+// gidcuda_job_scan with restart_interval == 0: the whole scan, byte stuffing removed by the caller.
+static int job_scan_whole(gidcuda_job *job, const gidcuda_scan_desc *scan, const uint8_t *data, size_t len) {
+  gidcuda_ctx *ctx = job->ctx;
+  const Geometry &g = job->geo;
+  int bpm = 0;
+  for (int c = 0; c < g.ncomp; c++) bpm += job->desc.samp_h[c] * job->desc.samp_v[c];
+  if (bpm > 12) return fail(ctx, GIDCUDA_ERR_UNSUPPORTED, "gidcuda_job_scan: %d blocks per MCU", bpm);
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t off_data = round_up(6 * sizeof(gidk::HuffDev), 256);
+  const size_t total = off_data + round_up(len + 64, 256);  // FF padding: the decoder looks a few bytes ahead
+  if (job->cap_scan < total) {
+    if (job->h_scan) cudaFreeHost(job->h_scan);
+    if (job->d_scan) cudaFree(job->d_scan);
+    job->h_scan = job->d_scan = nullptr;
+    job->cap_scan = 0;
+    const size_t cap = total + total / 4;
+    CU_TRY(ctx, cudaHostAlloc((void **)&job->h_scan, cap, cudaHostAllocDefault));
+    CU_TRY(ctx, cudaMalloc((void **)&job->d_scan, cap));
+    job->cap_scan = cap;
+  }
+  if (!job->h_status) {
+    CU_TRY(ctx, cudaHostAlloc((void **)&job->h_status, 16, cudaHostAllocDefault));
+    CU_TRY(ctx, cudaMalloc((void **)&job->d_status, 16));
+  }
+  uint64_t frame_blocks = 0;
+  for (int c = 0; c < g.ncomp; c++) frame_blocks += (uint64_t)g.bx[c] * g.by[c];
+  const uint32_t sub_bits = (uint64_t)len * 8 > frame_blocks * kDenseBitsPerBlock ? kSubsequenceBitsDense : kSubsequenceBits;
+  const uint32_t nsub = (uint32_t)((len * 8 + sub_bits - 1) / sub_bits);
+  const size_t sync_bytes = (size_t)nsub * (8 + 8 + 16 + 16) + 1024;
+  if (job->cap_sync < sync_bytes) {
+    if (job->d_sync) cudaFree(job->d_sync);
+    job->d_sync = nullptr;
+    job->cap_sync = 0;
+    const size_t cap = sync_bytes + sync_bytes / 4;
+    CU_TRY(ctx, cudaMalloc((void **)&job->d_sync, cap));
+    job->cap_sync = cap;
+  }
+  gidk::HuffDev *tabs = reinterpret_cast<gidk::HuffDev *>(job->h_scan);
+  for (int c = 0; c < 3; c++) {
+    const bool used = c < g.ncomp;
+    if (!build_huff_dev(scan->dc[used ? c : 0], &tabs[c]) || !build_huff_dev(scan->ac[used ? c : 0], &tabs[3 + c]))
+      return fail(ctx, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_job_scan: Huffman table of component %d is not a prefix code", c);
+  }
+  memcpy(job->h_scan + off_data, data, len);
+  memset(job->h_scan + off_data + len, 0xFF, total - off_data - len);
+  job->scan_off_data = off_data;
+  job->scan_bytes = total;
+  job->scan_len = len;
+  job->scan_nsub = nsub;
+  job->scan_sub_bits = sub_bits;
+  job->scan_ri = 0;
+  job->scan_nintervals = 0;
+  job->scan_active = true;
+  return GIDCUDA_OK;
+}
+
+extern "C" int gidcuda_job_scan(gidcuda_job *job, const gidcuda_scan_desc *scan, const uint8_t *data, size_t len,
+                                const uint32_t *begin, const uint32_t *end) {
+  if (!job) return fail(nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "null job");
+  gidcuda_ctx *ctx = job->ctx;
+  if (job->state != gidcuda_job::BEGUN)
+    return fail(ctx, GIDCUDA_ERR_STATE, "gidcuda_job_scan: only between gidcuda_job_begin and gidcuda_job_submit");
+  if (!scan || !data || len == 0 || len >= ((size_t)1 << 28) || (scan->restart_interval != 0 && (!begin || !end)))
+    return fail(ctx, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_job_scan: null argument, no data or more than 256 MiB of it");
+  const Geometry &g = job->geo;
+  const int64_t nmcu = (int64_t)g.mcux * g.mcuy;
+  if (scan->restart_interval == 0) return job_scan_whole(job, scan, data, len);
+  if (scan->restart_interval <= 0 || scan->nintervals <= 0 ||
+      (nmcu + scan->restart_interval - 1) / scan->restart_interval != scan->nintervals)
+    return fail(ctx, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_job_scan: %d intervals of %d MCUs do not cover %lld MCUs",
+                (int)scan->nintervals, (int)scan->restart_interval, (long long)nmcu);
+  const size_t nint = (size_t)scan->nintervals;
+  for (size_t i = 0; i < nint; i++)
+    if (begin[i] > end[i] || end[i] > len)
+      return fail(ctx, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_job_scan: interval %zu = [%u, %u) outside the %zu bytes", i,
+                  begin[i], end[i], len);
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  const size_t off_begin = round_up(6 * sizeof(gidk::HuffDev), 256);
+  const size_t off_end = off_begin + round_up(nint * 4, 256);
+  const size_t off_data = off_end + round_up(nint * 4, 256);
+  const size_t total = off_data + round_up(len, 256);
+  if (job->cap_scan < total) {
+    if (job->h_scan) cudaFreeHost(job->h_scan);
+    if (job->d_scan) cudaFree(job->d_scan);
+    job->h_scan = job->d_scan = nullptr;
+    job->cap_scan = 0;
+    const size_t cap = total + total / 4;  // the next frame of a batch is rarely the same size
+    CU_TRY(ctx, cudaHostAlloc((void **)&job->h_scan, cap, cudaHostAllocDefault));
+    CU_TRY(ctx, cudaMalloc((void **)&job->d_scan, cap));
+    job->cap_scan = cap;
+  }
+  if (!job->h_status) {
+    CU_TRY(ctx, cudaHostAlloc((void **)&job->h_status, 16, cudaHostAllocDefault));
+    CU_TRY(ctx, cudaMalloc((void **)&job->d_status, 16));
+  }
+  gidk::HuffDev *tabs = reinterpret_cast<gidk::HuffDev *>(job->h_scan);
+  for (int c = 0; c < 3; c++) {
+    const bool used = c < g.ncomp;
+    if (!build_huff_dev(scan->dc[used ? c : 0], &tabs[c]) || !build_huff_dev(scan->ac[used ? c : 0], &tabs[3 + c]))
+      return fail(ctx, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_job_scan: Huffman table of component %d is not a prefix code", c);
+  }
+  memcpy(job->h_scan + off_begin, begin, nint * 4);
+  memcpy(job->h_scan + off_end, end, nint * 4);
+  memcpy(job->h_scan + off_data, data, len);
+  job->scan_off_begin = off_begin;
+  job->scan_off_end = off_end;
+  job->scan_off_data = off_data;
+  job->scan_bytes = total;
+  job->scan_ri = scan->restart_interval;
+  job->scan_nintervals = scan->nintervals;
+  job->scan_active = true;
+  return GIDCUDA_OK;
+}
+
+// The self-synchronising decoder's arguments for the scan a job holds (gidcuda_job_scan, restart_interval = 0).
+static void make_whole_args(gidcuda_job *job, gidk::WholeArgs *out) {
+  const Geometry &g = job->geo;
+  gidk::WholeArgs &wa = *out;
+  memset(&wa, 0, sizeof wa);
+  wa.data = job->d_scan + job->scan_off_data;
+  wa.tables = reinterpret_cast<const gidk::HuffDev *>(job->d_scan);
+  const size_t n = job->scan_nsub;
+  wa.entry = reinterpret_cast<uint64_t *>(job->d_sync);
+  wa.exit_ = wa.entry + n;
+  wa.tuple = reinterpret_cast<int4 *>(job->d_sync + round_up(16 * n, 256));
+  wa.prefix = wa.tuple + n;
+  uint32_t k = 0, blocks = 0;
+  for (int c = 0; c < g.ncomp; c++) {
+    wa.plane[c] = reinterpret_cast<int16_t *>(job->d_coef + g.plane_off[c]);
+    wa.bx[c] = (uint32_t)g.bx[c];
+    wa.h[c] = job->desc.samp_h[c];
+    wa.v[c] = job->desc.samp_v[c];
+    blocks += (uint32_t)g.bx[c] * (uint32_t)g.by[c];
+    k += (uint32_t)(wa.h[c] * wa.v[c]);
+    job->d_tail_zero[c] = false;
+  }
+  wa.bpm = k;
+  wa.mcux = (uint32_t)g.mcux;
+  wa.total_blocks = blocks;
+  wa.nbits = (uint32_t)(job->scan_len * 8);
+  wa.sub_bits = job->scan_sub_bits;
+  wa.nsub = job->scan_nsub;
+  wa.status = job->d_status;
+  wa.zero_base = reinterpret_cast<uint4 *>(job->d_coef);
+  wa.zero_count = (uint32_t)(g.coef_bytes / 16);
+}
+
+// ---- chain repair on the host -------------------------------------------------------------------
+// A stretch of the scan that does not re-synchronise (a flat region: the same two code words over and
+// over, so a decoder in the wrong phase stays there) leaves the device's chain of states broken: truth
+// only advances one subsequence per round there.  Walking such a stretch is a SERIAL job, which one host
+// core does an order of magnitude faster than one GPU thread.  So when the output pass reports an
+// unsettled chain (and nothing undecodable), gidcuda_job_wait fetches the chain, walks it from the true
+// start state -- where a subsequence's recorded entry state is the true one its recorded exit and counts
+// are kept, where not the host decodes that subsequence (the mirror of run_subsequence<false> in
+// entropy_kernel.cu) -- sends it back and runs prefix sums, output pass and reconstruction again.  The
+// output pass verifies the repaired chain like any other.
+namespace {
+
+struct HostWalk {
+  const uint8_t *data;  // unstuffed scan bytes, FF-padded (the job's pinned staging copy)
+  const gidk::HuffDev *tabs;
+  uint32_t bpm;
+  uint8_t comp[12];
+};
+
+inline uint32_t host_peek(const uint8_t *d, uint32_t pos, int n) {  // n <= 16
+  const uint8_t *p = d + (pos >> 3);
+  const uint32_t w = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
+  return (w << (pos & 7u)) >> (32 - n);
+}
+
+inline int host_extend(uint32_t v, int n) { return v < (1u << (n - 1)) ? (int)v + 1 - (1 << n) : (int)v; }
+
+uint64_t host_run_subsequence(const HostWalk &w, uint64_t entry, uint32_t limit, int32_t tup[4]) {
+  uint32_t pos = (uint32_t)entry, c = (uint32_t)(entry >> 32) & 0xFFu, zpos = (uint32_t)(entry >> 40) & 0xFFu;
+  int nb = 0, dcs[3] = {0, 0, 0};
+  while (pos < limit) {
+    const int k = w.comp[c];
+    const gidk::HuffDev &t = zpos == 0 ? w.tabs[k] : w.tabs[3 + k];
+    const uint32_t look = host_peek(w.data, pos, 16);
+    const uint32_t e = t.lut[look >> 6];
+    int l = (int)(e >> 8), sym = (int)(e & 0xFFu);
+    if (e == 0) {
+      sym = -1;
+      for (l = 11; l <= 16; l++) {
+        const int code = (int)(look >> (16 - l));
+        if (code <= t.maxcode[l]) {
+          sym = t.vals[(t.valoff[l] + code) & 0xFF];
+          break;
+        }
+      }
+      if (sym < 0) {
+        pos += 1;
+        continue;
+      }
+    }
+    pos += (uint32_t)l;
+    const int n = sym & 15;
+    bool block_done = false;
+    if (zpos == 0) {
+      if (n) {
+        dcs[k] += host_extend(host_peek(w.data, pos, n), n);
+        pos += (uint32_t)n;
+      }
+      zpos = 1;
+    } else if (sym == 0) {
+      block_done = true;
+    } else {
+      const uint32_t idx = zpos + (uint32_t)(sym >> 4);
+      pos += (uint32_t)n;
+      if (idx >= 63) block_done = true;
+      else zpos = idx + 1;
+    }
+    if (block_done) {
+      zpos = 0;
+      c = c + 1 == w.bpm ? 0 : c + 1;
+      nb++;
+    }
+  }
+  tup[0] = nb; tup[1] = dcs[0]; tup[2] = dcs[1]; tup[3] = dcs[2];
+  return (uint64_t)pos | ((uint64_t)c << 32) | ((uint64_t)zpos << 40);
+}
+
+}  // namespace
+
+// Returns GIDCUDA_OK when the repaired chain has been re-submitted (the caller waits for job->done again).
+static int job_repair_chain(gidcuda_job *job) {
+  gidcuda_ctx *ctx = job->ctx;
+  const Geometry &g = job->geo;
+  cudaStream_t s = job->stream;
+  gidk::WholeArgs wa;
+  make_whole_args(job, &wa);
+  const size_t n = wa.nsub;
+  std::vector<uint64_t> st(2 * n);   // entry[], exit[]
+  std::vector<int32_t> tup(4 * n);
+  CU_TRY(ctx, cudaMemcpyAsync(st.data(), wa.entry, 16 * n, cudaMemcpyDeviceToHost, s));
+  CU_TRY(ctx, cudaMemcpyAsync(tup.data(), wa.tuple, 16 * n, cudaMemcpyDeviceToHost, s));
+  CU_TRY(ctx, cudaStreamSynchronize(s));
+  HostWalk w;
+  w.data = job->h_scan + job->scan_off_data;
+  w.tabs = reinterpret_cast<const gidk::HuffDev *>(job->h_scan);
+  w.bpm = wa.bpm;
+  uint32_t k = 0;
+  for (int c = 0; c < g.ncomp; c++)
+    for (int i = 0; i < job->desc.samp_h[c] * job->desc.samp_v[c]; i++) w.comp[k++] = (uint8_t)c;
+  uint64_t state = 0;  // the true start: bit 0, first block of the MCU, DC next
+  uint64_t blocks = 0;
+  size_t walked = 0;
+  for (size_t i = 0; i < n && blocks < wa.total_blocks; i++) {
+    if (st[i] != state) {
+      const uint32_t limit = std::min<uint64_t>((uint64_t)(i + 1) * wa.sub_bits, wa.nbits);
+      st[i] = state;
+      st[n + i] = host_run_subsequence(w, state, limit, &tup[4 * i]);
+      walked++;
+    }
+    state = st[n + i];
+    blocks += (uint64_t)tup[4 * i];
+  }
+  job->repaired_subsequences = walked;
+  CU_TRY(ctx, cudaMemcpyAsync(wa.entry, st.data(), 16 * n, cudaMemcpyHostToDevice, s));
+  CU_TRY(ctx, cudaMemcpyAsync(wa.tuple, tup.data(), 16 * n, cudaMemcpyHostToDevice, s));
+  CU_TRY(ctx, cudaMemsetAsync(job->d_coef, 0, g.coef_bytes, s));
+  CU_TRY(ctx, cudaMemsetAsync(job->d_status, 0, 16, s));
+  CU_TRY(ctx, gidk::launch_huffman_finish(wa, s));
+  CU_TRY(ctx, cudaMemcpyAsync(job->h_status, job->d_status, 16, cudaMemcpyDeviceToHost, s));
+  CU_TRY(ctx, job->set.launch(ctx->num_sms, s));
+  CU_TRY(ctx, cudaMemcpyAsync(job->user_pixels ? job->user_pixels : job->h_pixels, job->d_pixels, g.pixel_bytes,
+                              cudaMemcpyDeviceToHost, s));
+  CU_TRY(ctx, cudaStreamSynchronize(s));  // (st / tup are this function's: the copies must be done before they go)
+  return GIDCUDA_OK;
+}
+
+// The scan's stream operations: compressed bytes to the device, planes zeroed, Huffman decoding (one
+// thread per restart interval, or the self-synchronising decoder), status words back.
+int job_submit_scan(gidcuda_job *job, cudaStream_t s) {
+  gidcuda_ctx *ctx = job->ctx;
+  const Geometry &g = job->geo;
+  CU_TRY(ctx, cudaMemcpyAsync(job->d_scan, job->h_scan, job->scan_bytes, cudaMemcpyHostToDevice, s));
+  if (job->scan_ri != 0) {  // (the self-synchronising decoder's first launch zeroes both itself)
+    CU_TRY(ctx, cudaMemsetAsync(job->d_coef, 0, g.coef_bytes, s));
+    CU_TRY(ctx, cudaMemsetAsync(job->d_status, 0, 16, s));
+  }
+  if (job->scan_ri == 0) {
+    gidk::WholeArgs wa;
+    make_whole_args(job, &wa);
+    CU_TRY(ctx, gidk::launch_huffman_whole(wa, s));
+  } else {
+    gidk::ScanArgs sa;
+    memset(&sa, 0, sizeof sa);
+    sa.data = job->d_scan + job->scan_off_data;
+    sa.begin = reinterpret_cast<const uint32_t *>(job->d_scan + job->scan_off_begin);
+    sa.end = reinterpret_cast<const uint32_t *>(job->d_scan + job->scan_off_end);
+    sa.tables = reinterpret_cast<const gidk::HuffDev *>(job->d_scan);
+    for (int c = 0; c < g.ncomp; c++) {
+      sa.plane[c] = reinterpret_cast<int16_t *>(job->d_coef + g.plane_off[c]);
+      sa.bx[c] = (uint32_t)g.bx[c];
+      sa.h[c] = job->desc.samp_h[c];
+      sa.v[c] = job->desc.samp_v[c];
+      job->d_tail_zero[c] = false;
+    }
+    sa.ncomp = g.ncomp;
+    sa.mcux = (uint32_t)g.mcux;
+    sa.nmcu = (uint32_t)g.mcux * (uint32_t)g.mcuy;
+    sa.ri = (uint32_t)job->scan_ri;
+    sa.nintervals = (uint32_t)job->scan_nintervals;
+    sa.status = job->d_status;
+    CU_TRY(ctx, gidk::launch_huffman_intervals(sa, s));
+  }
+  CU_TRY(ctx, cudaMemcpyAsync(job->h_status, job->d_status, 16, cudaMemcpyDeviceToHost, s));
+  return GIDCUDA_OK;
+}
+
+// After the job's work has finished: the device decoder's verdict on the scan.
+int job_finish_scan(gidcuda_job *job) {
+  gidcuda_ctx *ctx = job->ctx;
+  job->scan_active = false;  // a re-submission after a host decode takes planes / records
+  uint32_t blocks = 0;
+  for (int c = 0; c < job->geo.ncomp; c++) blocks += (uint32_t)job->geo.bx[c] * (uint32_t)job->geo.by[c];
+  if (job->scan_ri == 0 && (job->h_status[0] & 2u) && g_chain_repair) {
+    // an unsettled chain: the host walks the stretches that did not re-synchronise.  (Threads that
+    // decoded from a consistent but untrue state may have met undecodable codes, flag 8, as well:
+    // the output pass over the repaired chain tells whether the stream itself is damaged.)
+    const int rc = job_repair_chain(job);
+    if (rc != GIDCUDA_OK) return rc;
+    g_chain_repairs.fetch_add(1, std::memory_order_relaxed);
+    g_chain_repair_subsequences.fetch_add((long)job->repaired_subsequences, std::memory_order_relaxed);
+  }
+  if (job->scan_ri == 0 && job->h_status[0] == 0 && job->h_status[2] != blocks) job->h_status[0] = 4;
+  if (job->scan_ri == 0 && job->h_status[0] != 0) {
+    job->state = gidcuda_job::BEGUN;
+    return fail(ctx, GIDCUDA_ERR_DATA,
+                "device entropy decoder: scan left to the host decoder (flags %u, %u of %u blocks)", job->h_status[0],
+                job->h_status[2], blocks);
+  }
+  if (job->h_status[0] != 0) {
+    job->state = gidcuda_job::BEGUN;
+    return fail(ctx, GIDCUDA_ERR_DATA,
+                "device entropy decoder: %u restart interval(s) left to the host decoder (damaged or unusual stream)",
+                job->h_status[1]);
+  }
+  return GIDCUDA_OK;
+}
