@@ -241,11 +241,6 @@ __device__ __forceinline__ uint64_t pack_state(uint32_t pos, uint32_t c, uint32_
   return (uint64_t)pos | ((uint64_t)c << 32) | ((uint64_t)zpos << 40);
 }
 
-// Decodes the code words of subsequence `i` that start before bit `limit`, from state `entry`.
-// FINAL = false: returns the exit state, counts completed blocks and sums DC differences (tup).
-// FINAL = true : also stores the coefficients; `b` = number of the first block (in scan order),
-//                pred = predictors on entry; stops at block `total`; *bad is set for anything
-//                the serial decoder would not decode silently.
 // Where the blocks of one MCU go (shared memory: indexing the kernel parameters with a run-time
 // index would make the compiler copy them to local memory).
 struct BlockSlot {
@@ -254,6 +249,11 @@ struct BlockSlot {
   uint32_t h, v, sx, sy, comp;
 };
 
+// Decodes the code words of subsequence `i` that start before bit `limit`, from state `entry`.
+// FINAL = false: returns the exit state, counts completed blocks and sums DC differences (tup).
+// FINAL = true : also stores the coefficients; `b` = number of the first block (in scan order),
+//                pred = predictors on entry; stops at block `total`; *bad is set for anything
+//                the serial decoder would not decode silently.
 template <bool FINAL>
 __device__ __forceinline__ uint64_t run_subsequence(const WholeArgs &a, const HuffDev *tabs, const uint8_t *zz,
                                                     const BlockSlot *slots,
