@@ -133,3 +133,20 @@ def test_output_geometry_of_turned_frames(gidcuda_lib):
             assert gidcuda_lib.gidcuda_output_geometry(ctypes.byref(d), ctypes.byref(st), ctypes.byref(nb)) == 0
             want = -(-(bpp * ow) // align) * align
             assert (st.value, nb.value) == (want, want * oh), (flag, fmt)
+
+
+def test_job_entry_points_reject_null_jobs(gidcuda_lib):
+    """Without a device there are no jobs: every job entry point must answer a null handle with an
+    error code, never crash (the Ada binding turns the code into an exception)."""
+    L = gidcuda_lib
+    null = ctypes.c_void_p()
+    assert L.gidcuda_job_submit(null) == -1
+    assert L.gidcuda_job_wait(null, None, None) == -1
+    assert L.gidcuda_job_hint_rows(null, 0, 4) == -1
+    assert L.gidcuda_job_records_commit(null, 0, 0) == -1
+    assert L.gidcuda_job_records_commit_runs(null, 0, 1, None, None) == -1
+    assert L.gidcuda_job_output(null, None, 0) == -1
+    assert L.gidcuda_job_scan(null, None, None, 0, None, None) == -1
+    assert L.gidcuda_host_is_pinned(None) == 0
+    assert L.gidcuda_counter(b"chain_repairs") == 0 and L.gidcuda_counter(b"no such counter") == -1
+    assert L.gidcuda_set_option(b"chain_repair", 1) == 0 and L.gidcuda_set_option(b"no such option", 1) == -1
