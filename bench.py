@@ -303,6 +303,33 @@ def run_reference(args) -> None:
 # --------------------------------------------------------------------------- our arm
 
 
+def bind_to_gpu_numa_node(local: int) -> str:
+    """One rank per GPU: run this rank's host threads, and so first-touch its pinned buffers, on the
+    NUMA node the GPU hangs off (eight ranks streaming pixels into one host's memory are bound by the
+    host side; memory on the far socket halves what a link delivers).  Best effort: returns what was done."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:       # nvml prints an 8-digit PCI domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return "no NUMA information for the GPU"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return f"NUMA node {node} has none of this process's CPUs"
+        os.sched_setaffinity(0, cpus)
+        return f"bound to NUMA node {node} ({len(cpus)} CPUs)"
+    except Exception as e:  # no nvml, no sysfs entry, a container without the rights: carry on unbound
+        return f"not bound ({type(e).__name__})"
+
+
 def run_ours(args) -> None:
     import torch
     import torch.distributed as dist
@@ -311,10 +338,16 @@ def run_ours(args) -> None:
     from tests.harness import frame_desc
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    # stdout carries ONE line, the JSON: whatever libraries print there meanwhile (NCCL's version banner
+    # goes to stdout) is sent to stderr, until the line itself is printed
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the reconstruction path has no CPU fallback)")
     if not os.path.exists(capi.library_path()):
         build.build_cuda()
+    numa = bind_to_gpu_numa_node(local) if world > 1 else "single rank: not bound"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -505,7 +538,7 @@ def run_ours(args) -> None:
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}", "sampling": samp, "width": w, "height": h,
-                       "frames_per_step_per_gpu": per_step, "launch_streams": nstreams, "parallelism": f"images sharded over {world} GPU(s), no collective",
+                       "frames_per_step_per_gpu": per_step, "launch_streams": nstreams, "host_numa": numa, "parallelism": f"images sharded over {world} GPU(s), no collective",
                        "l2": f"inputs larger than L2: ring of {ring} step-batches of {alg_bytes_frame * per_step / 1e6:.0f} MB each"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": coef_bytes * e2e_frames,
@@ -528,7 +561,10 @@ def run_ours(args) -> None:
         }
         if files is not None:
             line["files"] = files
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     for p in plans:
         ctx.plan_destroy(p)
     ctx.close()
