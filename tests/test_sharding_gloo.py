@@ -77,3 +77,15 @@ def test_reference_arm_under_torchrun_rank0_only():
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_numa_binding_is_best_effort():
+    """bench.py binds each rank to its GPU's NUMA node when it can; without NVML / sysfs information
+    (as here) it says so and leaves the affinity alone."""
+    import bench
+    before = os.sched_getaffinity(0)
+    msg = bench.bind_to_gpu_numa_node(0)
+    assert isinstance(msg, str) and msg
+    if not msg.startswith("bound"):
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
