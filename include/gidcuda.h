@@ -102,7 +102,12 @@ int gidcuda_device_count(void);
 /* Message of the last error raised on this thread (ctx may be NULL). */
 const char *gidcuda_last_error(const gidcuda_ctx *ctx);
 
-/* Library options (process-wide; set before creating jobs / plans):
+/* Loading the library sets CUDA_DEVICE_MAX_CONNECTIONS=32 in the environment unless it is set already:
+ * frames in flight live on one stream each, and the device runs as many streams side by side as it has
+ * hardware work queues (8 by default).  The variable is read when the CUDA context is created; a
+ * process that creates its context before loading the library sets it itself.
+ *
+ * Library options (process-wide; set before creating jobs / plans):
  *   "tma"  1 (default) = stage coefficients through TMA, 0 = plain 128-bit loads.
  *   "chain_repair"  1 (default) = when the self-synchronising Huffman decoder (gidcuda_job_scan without restart
  *          markers) is left with an unsettled chain of states -- a stretch of the scan that does not
@@ -231,7 +236,8 @@ int gidcuda_job_output(gidcuda_job *job, uint8_t *host_pixels, size_t capacity);
  * their transfers).  A job may be submitted again after gidcuda_job_wait. */
 int gidcuda_job_submit(gidcuda_job *job);
 /* Block until the frame is done.  *pixels points to pinned host memory owned
- * by the job (valid until release): rows top-down, *stride bytes apart. */
+ * by the job (valid until release) -- or to the caller's buffer, after gidcuda_job_output --:
+ * rows in the order of the output format, *stride bytes apart.  GIDCUDA_ERR_DATA: see gidcuda_job_scan. */
 int gidcuda_job_wait(gidcuda_job *job, const uint8_t **pixels, size_t *stride);
 /* Return the job's buffers to the context pool. */
 int gidcuda_job_release(gidcuda_job *job);
