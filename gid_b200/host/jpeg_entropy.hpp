@@ -887,9 +887,18 @@ struct Decoder {
   template <class B> void dc_refine(B &bits, int16_t *blk, int al) {
     if (bits.get(1)) blk[0] = (int16_t)(blk[0] | (1 << al));
   }
+  // Which AC coefficients of a block are non-zero, bit k = zig-zag position k: kept beside the planes of
+  // a progressive frame so that the refinement scans -- which visit every position of the band in every
+  // block to ask "is it non-zero?" (:1560-1612, :1650-1677) -- read a register instead of walking the
+  // 128-byte block (the luma refinement scan was 10 of the 28 ms a 2048 x 2048 file took to decode).
+  // The bit is recomputed from the stored int16 at every store, so it always equals (coefficient != 0).
+  std::vector<uint64_t> nzmask[3];
+  uint64_t &mask_of(int c, const int16_t *blk) { return nzmask[c][(size_t)(blk - plane[c].base) >> 6]; }
+
   template <class B> void ac_first(B &bits, int c, int16_t *blk, int ss, int se, int al) {
     if (eobrun > 0) { eobrun--; return; }
     const HuffTable &ac = table(1, ht_ac[c]);
+    uint64_t &mask = mask_of(c, blk);
     for (int k = ss; k <= se;) {
       const int rs = bits.symbol(ac), rr = rs >> 4, s = rs & 15;
       if (s == 0) {
@@ -904,6 +913,7 @@ struct Decoder {
         if (k > 63) throw error_in_image_data("JPEG: progressive: coefficient index > 63");
         const int nat = kZigZag[k];
         blk[nat] = (int16_t)(bits.receive_extend(s) * (1 << al));
+        mask = blk[nat] != 0 ? mask | (1ull << k) : mask & ~(1ull << k);
         if ((nat >> 3) > last_row[c]) last_row[c] = nat >> 3;
         k++;
       }
@@ -912,6 +922,7 @@ struct Decoder {
   template <class B> void ac_refine(B &bits, int c, int16_t *blk, int ss, int se, int al) {
     const int p1 = 1 << al, m1 = -(1 << al);
     int k = ss;
+    uint64_t &mask = mask_of(c, blk);
     if (eobrun <= 0) {
       const HuffTable &ac = table(1, ht_ac[c]);
       for (; k <= se; k++) {
@@ -930,13 +941,15 @@ struct Decoder {
           value = bits.get(1) ? p1 : m1;
         }
         for (; k <= se; k++) {
-          int16_t &z = blk[kZigZag[k]];
-          if (z != 0) {
+          if ((mask >> k) & 1u) {
+            int16_t &z = blk[kZigZag[k]];
             if (bits.get(1) && (z & p1) == 0) z = (int16_t)(z >= 0 ? z + p1 : z + m1);
           } else {
             if (rr == 0) {
               if (value) {
+                int16_t &z = blk[kZigZag[k]];
                 z = (int16_t)value;
+                if (z != 0) mask |= 1ull << k;
                 if ((kZigZag[k] >> 3) > last_row[c]) last_row[c] = kZigZag[k] >> 3;
               }
               break;
@@ -947,9 +960,16 @@ struct Decoder {
       }
     }
     if (eobrun > 0) {
-      for (; k <= se; k++) {
-        int16_t &z = blk[kZigZag[k]];
-        if (z != 0 && bits.get(1) && (z & p1) == 0) z = (int16_t)(z >= 0 ? z + p1 : z + m1);
+      // the rest of the band: only the non-zero coefficients take a correction bit, in zig-zag order
+      if (k <= se) {
+        uint64_t m = mask & (~0ull << k) & (se >= 63 ? ~0ull : ((1ull << (se + 1)) - 1ull));
+        while (m) {
+          const int kk = __builtin_ctzll(m);
+          m &= m - 1;
+          int16_t &z = blk[kZigZag[kk]];
+          if (bits.get(1) && (z & p1) == 0) z = (int16_t)(z >= 0 ? z + p1 : z + m1);
+        }
+        k = se + 1;
       }
       eobrun--;
     }
@@ -978,6 +998,11 @@ struct Decoder {
     if (ss == 0 && se != 0) throw error_in_image_data("JPEG: progressive: DC and AC in the same scan");
     if (ss > 0 && ncomps != 1) throw error_in_image_data("JPEG: progressive: AC scan with several components");
     ensure_host_output();
+    for (int i = 0; i < ncomps; i++) {
+      const int c = comps[i];
+      const size_t nb = (size_t)plane[c].blocks_x * (size_t)plane[c].blocks_y;
+      if (nzmask[c].size() != nb) nzmask[c].assign(nb, 0);
+    }
     rst_count = im.restart_interval;
     next_rst = 0;
     eobrun = 0;
