@@ -170,8 +170,10 @@ void *decode_and_submit(Image_Descriptor &image, void *ctx_, const std::function
   describe_frame(image, &desc, comp_of);
   int rc;
   gidcuda_job *job = nullptr;
-  // progressive + sparse input: the scans accumulate in ordinary host memory
-  std::vector<std::vector<int16_t>> accum(3);
+  // progressive + sparse input: the scans accumulate in ordinary host memory -- this thread's, kept from
+  // one image to the next (a fresh 16 MB vector per image is thousands of page faults); it is only in
+  // use until the records have been made, i.e. inside this call
+  static thread_local std::vector<int16_t> accum[3];
   const bool sparse = image.sparse_input;
   // The job is begun at the first SOS, like Begin_Device_Frame of the Ada patch:
   // every DQT has been read by then (GID accepts none after entropy-coded data).
@@ -201,7 +203,9 @@ void *decode_and_submit(Image_Descriptor &image, void *ctx_, const std::function
           int32_t bx = 0, by = 0;
           st = gidcuda_plane_geometry(&desc, comp_of[c], &bx, &by);
           if (st != GIDCUDA_OK) raise_from_status(st, ctx);
-          accum[c].assign((size_t)bx * (size_t)by * 64, 0);
+          const size_t need = (size_t)bx * (size_t)by * 64;
+          if (accum[c].size() < need) accum[c].resize(need);
+          memset(accum[c].data(), 0, need * sizeof(int16_t));
           dec.plane[c].base = accum[c].data();
           dec.plane[c].blocks_x = bx;
           dec.plane[c].blocks_y = by;
@@ -278,7 +282,7 @@ void *decode_and_submit(Image_Descriptor &image, void *ctx_, const std::function
         }
         const PlaneRef acc = dec.plane[c];
         use_job_plane(c);
-        memcpy(dec.plane[c].base, acc.base, accum[c].size() * sizeof(int16_t));
+        memcpy(dec.plane[c].base, acc.base, (size_t)acc.blocks_x * (size_t)acc.blocks_y * 64 * sizeof(int16_t));
       } else if (k.on) {
         if (k.seq != k.nblocks) throw error_in_image_data("JPEG: scan ended before the last block");
         k.first[k.nblocks] = (uint32_t)k.n;
