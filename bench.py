@@ -356,6 +356,7 @@ def run_ours(args) -> None:
 
     w, h, samp, per_step, desc = WORKLOADS[args.workload]
     ctx = GidCuda(local)
+    capi.set_option("plan_pdl", args.pdl)
 
     # ---- synthetic inputs: a ring of distinct step-batches so that consecutive steps never
     # reuse L2-resident data (every step-batch is also larger than the 126 MB L2) ---------
@@ -587,6 +588,9 @@ def main() -> None:
     ap.add_argument("--e2e-depth", type=int, default=3, help="jobs in flight in the end-to-end leg")
     ap.add_argument("--streams", type=int, default=2, choices=[1, 2, 4],
                     help="launch streams for the device-resident leg (2: consecutive frames overlap tail and ramp)")
+    ap.add_argument("--pdl", type=int, default=1, choices=[0, 1],
+                    help="plan launches as programmatic dependent launches (library default 1); 0 = every launch "
+                         "waits for its predecessor to leave the device")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

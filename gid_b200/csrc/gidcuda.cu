@@ -127,6 +127,8 @@ int g_blocking_wait = 0;
 // gidcuda_set_option("chain_repair"): 1 (default) = an unsettled chain of the self-synchronising Huffman
 // decoder is repaired by the host (job_repair_chain); 0 = reported as GIDCUDA_ERR_DATA at once.
 int g_chain_repair = 1;
+// gidcuda_set_option("plan_pdl"): 1 (default) = plan launches are programmatic dependent launches
+int g_plan_pdl = 1;
 std::atomic<long> g_chain_repairs{0}, g_chain_repair_subsequences{0};
 
 
@@ -309,10 +311,6 @@ extern "C" int gidcuda_job_records(gidcuda_job *job, int comp, uint32_t **first,
   if (job->state == gidcuda_job::IDLE) return fail(job->ctx, GIDCUDA_ERR_STATE, "gidcuda_job_records: job was released");
   if (comp < 0 || comp >= job->geo.ncomp || !first || !records)
     return fail(job->ctx, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_job_records: bad component or null argument");
-  if (job->geo.layout == gidk::LAYOUT_GENERIC && job->geo.ncomp == 3 &&
-      (job->desc.samp_h[1] != 1 || job->desc.samp_v[1] != 1 || job->desc.samp_h[2] != 1 || job->desc.samp_v[2] != 1)) {
-    // (block sequence numbers are defined for every layout; nothing to reject -- kept for clarity)
-  }
   const int rc = job_reserve_sparse(job);
   if (rc != GIDCUDA_OK) return rc;
   const size_t nb = (size_t)job->geo.bx[comp] * job->geo.by[comp];
@@ -636,7 +634,7 @@ extern "C" int gidcuda_plan_launch(gidcuda_plan *plan, void *cuda_stream) {
   gidcuda_ctx *ctx = plan->ctx;
   cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
   CU_TRY(ctx, cudaSetDevice(ctx->device));
-  CU_TRY(ctx, plan->set.launch(ctx->num_sms, s));
+  CU_TRY(ctx, plan->set.launch(ctx->num_sms, s, g_plan_pdl != 0));
   return GIDCUDA_OK;
 }
 
@@ -650,6 +648,10 @@ extern "C" int gidcuda_set_option(const char *name, int value) {
   }
   if (strcmp(name, "blocking_wait") == 0) {
     g_blocking_wait = value ? 1 : 0;
+    return GIDCUDA_OK;
+  }
+  if (strcmp(name, "plan_pdl") == 0) {
+    g_plan_pdl = value ? 1 : 0;
     return GIDCUDA_OK;
   }
   if (strcmp(name, "tma") == 0) {

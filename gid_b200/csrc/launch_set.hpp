@@ -153,9 +153,9 @@ class LaunchSet {
   // Copies the tables to the device (asynchronously, from pinned staging).
   cudaError_t upload(cudaStream_t s) {
     cudaError_t e;
-    if (!d_counters_) {  // tile-claim counters, two words per possible launch group; kernels leave them zero
-      if ((e = cudaMalloc((void **)&d_counters_, kMaxGroups * 2 * sizeof(uint32_t))) != cudaSuccess) return e;
-      if ((e = cudaMemsetAsync(d_counters_, 0, kMaxGroups * 2 * sizeof(uint32_t), s)) != cudaSuccess) return e;
+    if (!d_counters_) {  // tile-claim counters: kCounterSlots pairs per possible launch group; kernels leave them zero
+      if ((e = cudaMalloc((void **)&d_counters_, kMaxGroups * kCounterSlots * 2 * sizeof(uint32_t))) != cudaSuccess) return e;
+      if ((e = cudaMemsetAsync(d_counters_, 0, kMaxGroups * kCounterSlots * 2 * sizeof(uint32_t), s)) != cudaSuccess) return e;
     }
     if (cap_frames_ < frames.size()) {
       if (d_frames_) cudaFree(d_frames_);
@@ -204,12 +204,19 @@ class LaunchSet {
     return cudaSuccess;
   }
 
-  cudaError_t launch(int num_sms, cudaStream_t s) const {
+  // pdl: programmatic dependent launches (recon_launch.h).  Two launches of the same set may then be
+  // on the device at once (the tail of one, the ramp of the next), so consecutive launches take turns
+  // on kCounterSlots pairs of claim counters; a third launch cannot start before the first has left the
+  // device (it needs every CTA of the second resident or gone, and a launch with dynamic claims fills
+  // the device).
+  cudaError_t launch(int num_sms, cudaStream_t s, bool pdl = false) {
     cudaError_t e;
     uint32_t gi = 0;
+    const uint32_t slot = launch_seq_++ % kCounterSlots;
     for (const LaunchGroup &g : groups) {
       if ((e = launch_fused(g.layout, g.q8, g.rgba, g.tma, &g.map2, d_frames_ + g.first_frame,
-                            d_tiles_ + g.first_tile, g.ntiles, d_counters_ + 2 * gi, num_sms, s)) != cudaSuccess)
+                            d_tiles_ + g.first_tile, g.ntiles, d_counters_ + 2 * (gi * kCounterSlots + slot), num_sms,
+                            pdl, s)) != cudaSuccess)
         return e;
       gi++;
     }
@@ -222,6 +229,8 @@ class LaunchSet {
 
  private:
   static constexpr int kMaxGroups = 16;  // 4 layouts x 2 table widths x 2 pixel sizes
+  static constexpr uint32_t kCounterSlots = 4;
+  uint32_t launch_seq_ = 0;
   uint32_t *d_counters_ = nullptr;
   FrameDev *d_frames_ = nullptr, *h_frames_ = nullptr;
   TileDesc *d_tiles_ = nullptr, *h_tiles_ = nullptr;

@@ -312,6 +312,11 @@ recon_tma_kernel(const __grid_constant__ CUtensorMap map2, const FrameDev *__res
   constexpr int kOffScratch = SmemLayout<WPC>::kOffScratch, kOffFrame = SmemLayout<WPC>::kOffFrame,
                 kOffBars = SmemLayout<WPC>::kOffBars;
   const uint32_t nwarps = gridDim.x * WPC;
+  // Programmatic dependent launch (plan launches, LaunchSet::launch(pdl = true)): frames of consecutive
+  // launches are independent, so the next launch of the stream may start filling SMs as soon as this
+  // one's CTAs leave them -- the tail of one launch runs under the ramp of the next, in ONE stream.
+  // A no-op when the launch does not carry the attribute.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const uint32_t base = (smem_u32(dyn_smem) + 1023u) & ~1023u;
   uint8_t *gen = dyn_smem + (base - smem_u32(dyn_smem));
@@ -353,6 +358,9 @@ recon_tma_kernel(const __grid_constant__ CUtensorMap map2, const FrameDev *__res
     run_mcu<LAYOUT, Q8, RGBA>(active, f, src, scratch, (int)lane, mx, my);
   }
   src.claims.finish();
+  // ... and this launch does not complete before its predecessor has (stream order as seen from
+  // outside: whatever follows in the stream finds both launches' pixels written)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 constexpr int kLdgWarps = 4;
@@ -462,23 +470,31 @@ generic_color_kernel(const FrameDev *__restrict__ frame, int ncomp, int hmax, in
 template <int LAYOUT, bool Q8, bool RGBA, int WPC>
 cudaError_t launch_shape(const CUtensorMap *map2, const FrameDev *d_frames,
                          const TileDesc *d_tiles, uint32_t ntiles, uint32_t *d_counters, int num_sms,
-                         cudaStream_t stream) {
+                         bool pdl, cudaStream_t stream) {
   uint32_t grid = (uint32_t)(num_sms * Shape<WPC>::kCtasPerSm);
   const uint32_t need = (ntiles + WPC - 1) / WPC;
   if (grid > need) grid = need;
-  recon_tma_kernel<LAYOUT, Q8, RGBA, WPC><<<grid, Shape<WPC>::kThreads, SmemLayout<WPC>::kBytes, stream>>>(
-      *map2, d_frames, d_tiles, ntiles, d_counters);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(Shape<WPC>::kThreads);
+  cfg.dynamicSmemBytes = SmemLayout<WPC>::kBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, recon_tma_kernel<LAYOUT, Q8, RGBA, WPC>, *map2, d_frames, d_tiles, ntiles, d_counters);
 }
 
 template <int LAYOUT, bool Q8, bool RGBA>
 cudaError_t launch_one(bool use_tma, const CUtensorMap *map2, const FrameDev *d_frames,
                        const TileDesc *d_tiles, uint32_t ntiles, uint32_t *d_counters, int num_sms,
-                       cudaStream_t stream) {
+                       bool pdl, cudaStream_t stream) {
   if (use_tma) {
     const bool narrow = ntiles < (uint32_t)num_sms * (uint32_t)kWideWarps * kNarrowBelowTilesPerWarp;
-    return narrow ? launch_shape<LAYOUT, Q8, RGBA, 4>(map2, d_frames, d_tiles, ntiles, d_counters, num_sms, stream)
-                  : launch_shape<LAYOUT, Q8, RGBA, kWideWarps>(map2, d_frames, d_tiles, ntiles, d_counters, num_sms, stream);
+    return narrow ? launch_shape<LAYOUT, Q8, RGBA, 4>(map2, d_frames, d_tiles, ntiles, d_counters, num_sms, pdl, stream)
+                  : launch_shape<LAYOUT, Q8, RGBA, kWideWarps>(map2, d_frames, d_tiles, ntiles, d_counters, num_sms, pdl, stream);
   }
   recon_ldg_kernel<LAYOUT, Q8, RGBA><<<(ntiles + kLdgWarps - 1) / kLdgWarps, kLdgWarps * 32, 0, stream>>>(
       d_frames, d_tiles, ntiles);
@@ -488,8 +504,8 @@ cudaError_t launch_one(bool use_tma, const CUtensorMap *map2, const FrameDev *d_
 template <int LAYOUT>
 cudaError_t launch_q(bool q8, bool rgba, bool use_tma, const CUtensorMap *map2,
                      const FrameDev *d_frames, const TileDesc *d_tiles, uint32_t ntiles, uint32_t *d_counters,
-                     int num_sms, cudaStream_t stream) {
-#define GIDK_ARGS use_tma, map2, d_frames, d_tiles, ntiles, d_counters, num_sms, stream
+                     int num_sms, bool pdl, cudaStream_t stream) {
+#define GIDK_ARGS use_tma, map2, d_frames, d_tiles, ntiles, d_counters, num_sms, pdl, stream
   if (q8) return rgba ? launch_one<LAYOUT, true, true>(GIDK_ARGS) : launch_one<LAYOUT, true, false>(GIDK_ARGS);
   return rgba ? launch_one<LAYOUT, false, true>(GIDK_ARGS) : launch_one<LAYOUT, false, false>(GIDK_ARGS);
 #undef GIDK_ARGS
@@ -524,9 +540,9 @@ cudaError_t init_kernels() {
 
 cudaError_t launch_fused(Layout layout, bool q8, bool rgba, bool use_tma, const CUtensorMap *map2,
                          const FrameDev *d_frames, const TileDesc *d_tiles, uint32_t ntiles,
-                         uint32_t *d_counters, int num_sms, cudaStream_t stream) {
+                         uint32_t *d_counters, int num_sms, bool pdl, cudaStream_t stream) {
   if (ntiles == 0) return cudaSuccess;
-#define GIDK_ARGS q8, rgba, use_tma, map2, d_frames, d_tiles, ntiles, d_counters, num_sms, stream
+#define GIDK_ARGS q8, rgba, use_tma, map2, d_frames, d_tiles, ntiles, d_counters, num_sms, pdl, stream
   switch (layout) {
     case LAYOUT_GREY: return launch_q<LAYOUT_GREY>(GIDK_ARGS);
     case LAYOUT_444: return launch_q<LAYOUT_444>(GIDK_ARGS);
