@@ -166,6 +166,51 @@ def files_leg_reference(workload: str, threads: int, seconds_target: float) -> d
             "api": "oracle/gidref.c gidref_decode: whole GID decode restated in C (GNAT unavailable)"}
 
 
+def workload_config(workload: str, world: int) -> dict:
+    """The workload as BOTH arms state it (identical keys and values: the driver compares the two)."""
+    w, h, samp, per_step, desc = WORKLOADS[workload]
+    return {"workload": f"{workload}: {desc}", "sampling": samp, "width": w, "height": h,
+            "frames_per_step_per_gpu": per_step,
+            "parallelism": f"images sharded over {world} GPU(s), no collective"}
+
+
+def link_peak(dev, world: int) -> dict:
+    """What the host link of this box delivers: raw pinned cudaMemcpyAsync loops (torch copy_), 256 MiB per
+    copy, one loop per GPU -- under torch.distributed every rank runs its loop at the same time and the rates are
+    summed.  The ceiling the end-to-end leg is held against (3 bytes per pixel leave over this link)."""
+    import torch
+    import torch.distributed as dist
+    from gid_b200 import sharding
+    n = 256 << 20
+    hbuf = torch.empty(n, dtype=torch.uint8).pin_memory()
+    hbuf2 = torch.empty(n, dtype=torch.uint8).pin_memory()
+    dbuf = torch.empty(n, dtype=torch.uint8, device=dev)
+    dbuf2 = torch.empty(n, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    out = {}
+    for name in ("d2h", "h2d", "both"):
+        reps = 8
+        def go():
+            for _ in range(reps):
+                if name in ("d2h", "both"):
+                    with torch.cuda.stream(s1):
+                        hbuf.copy_(dbuf, non_blocking=True)
+                if name in ("h2d", "both"):
+                    with torch.cuda.stream(s2):
+                        dbuf2.copy_(hbuf2, non_blocking=True)
+        go()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        go()
+        torch.cuda.synchronize()
+        dt = sharding.max_over_ranks(time.perf_counter() - t0, dev)
+        out[name + "_GBps"] = world * reps * n * (2 if name == "both" else 1) / dt / 1e9
+    out["method"] = f"{world} concurrent loop(s) of 8 x 256 MiB pinned cudaMemcpyAsync per direction, wall clock, max over ranks"
+    return out
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
 
@@ -263,6 +308,66 @@ def cpu_reconstruct_rate(frames, seconds_target: float, threads: int) -> tuple[f
     return total_mp / dt, sample
 
 
+def cpu_worker(core: int, path: str, reps: int) -> None:
+    """One pinned process of cpu_reconstruct_rate_processes: `reps` reconstructions of the pickled frame."""
+    import pickle
+    try:
+        os.sched_setaffinity(0, {core})
+    except OSError:
+        pass
+    from tests.harness import Oracle
+    O = Oracle()
+    fr = pickle.load(open(path, "rb"))
+    O.reconstruct(fr)  # warm
+    print("ready", flush=True)
+    sys.stdin.readline()  # start signal
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        O.reconstruct(fr)
+    print(json.dumps({"reps": reps, "seconds": time.perf_counter() - t0}), flush=True)
+
+
+def cpu_reconstruct_rate_processes(frames, seconds_target: float, cores: int) -> tuple[float, str]:
+    """The same reconstruction as ONE PROCESS PER HOST CORE, each pinned to its core (sched_setaffinity),
+    as SURVEY.md 8(d) plans the reference's CPU run (test/benchmark.adb, one process per core)."""
+    import pickle
+    import tempfile
+    from tests.harness import Oracle
+    fr = frames[0]
+    O = Oracle()
+    t0 = time.perf_counter()
+    O.reconstruct(fr)
+    one = time.perf_counter() - t0
+    reps = max(1, int(round(seconds_target / max(one, 1e-3))))
+    allowed = sorted(os.sched_getaffinity(0))[:cores]
+    with tempfile.NamedTemporaryFile(suffix=".pkl", delete=False) as tf:
+        pickle.dump(fr, tf)
+        path = tf.name
+    procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--cpu-worker", str(c), path, str(reps)],
+                              stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+             for c in allowed]
+    try:
+        for pr in procs:
+            assert pr.stdout.readline().strip() == "ready"
+        t0 = time.perf_counter()
+        for pr in procs:
+            pr.stdin.write("go\n")
+            pr.stdin.flush()
+        done = [json.loads(pr.stdout.readline()) for pr in procs]
+        dt = time.perf_counter() - t0
+    finally:
+        for pr in procs:
+            try:
+                pr.wait(timeout=10)
+            except subprocess.TimeoutExpired:
+                pr.kill()
+                pr.wait()
+        os.unlink(path)
+    mp = fr.width * fr.height / 1e6
+    return mp * sum(d["reps"] for d in done) / dt, \
+        f"{reps} x {fr.width}x{fr.height} frame(s) per process, {len(procs)} pinned process(es), {dt:.1f} s wall"
+
+
 def run_reference(args) -> None:
     rank = env_int("RANK", 0)
     if rank != 0:
@@ -274,12 +379,13 @@ def run_reference(args) -> None:
     per_step_seconds = max(0.5, min(4.0, 60.0 / max(1, args.steps + args.warmup)))
     if os.environ.get("GIDBENCH_REFERENCE_SECONDS"):  # tests: a shorter sample
         per_step_seconds = float(os.environ["GIDBENCH_REFERENCE_SECONDS"])
+    rate_fn = cpu_reconstruct_rate if os.environ.get("GIDBENCH_REFERENCE_THREADS") else cpu_reconstruct_rate_processes
     for _ in range(args.warmup):
-        cpu_reconstruct_rate(frames, per_step_seconds / 4, cores)
+        rate_fn(frames, per_step_seconds / 4, cores)
     rates, sample = [], ""
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        r, sample = cpu_reconstruct_rate(frames, per_step_seconds, cores)
+        r, sample = rate_fn(frames, per_step_seconds, cores)
         rates.append(r)
     dt = time.perf_counter() - t0
     value = float(np.mean(rates))
@@ -288,10 +394,10 @@ def run_reference(args) -> None:
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
         "data": "synthetic", "gpu_launches": 0,
-        "config": {"workload": f"{args.workload}: {desc}", "sampling": samp, "width": w, "height": h},
+        "config": workload_config(args.workload, args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "per step: " + sample,
-                         "note": "GID's reconstruction restated in C (oracle/gidref.c, gcc -O2); "
+                         "note": "GID's reconstruction restated in C (oracle/gidref.c, gcc -O2), one pinned process per host core; "
                                  "GNAT is not installed so test/benchmark.adb cannot be built"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -422,38 +528,52 @@ def run_ours(args) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed_regions(use: int, min_total_ms: float, max_regions: int = 40) -> list[float]:
+        """Regions of EXACTLY args.steps steps each, every one bracketed by barrier + synchronize, CUDA events
+        on the launching stream, max over ranks; repeated until the regions add up to min_total_ms of device
+        time (a single region of a 40 us kernel at --steps 20 is under a millisecond: too short a sample)."""
+        out: list[float] = []
+        while True:
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(tstream)
+            launch_steps(args.steps, use)
+            b.record(tstream)
+            barrier()
+            out.append(sharding.max_over_ranks(a.elapsed_time(b), dev))
+            if len(out) >= max_regions or (len(out) >= 3 and sum(out) >= min_total_ms):
+                return out
+
+    def summary(regions: list[float]) -> dict:
+        per = sorted(r / args.steps for r in regions)
+        return {"ms_per_launch_median": float(np.median(per)), "ms_per_launch_min": per[0], "ms_per_launch_max": per[-1],
+                "regions": len(per), "timed_region_ms": float(np.median(regions)), "timed_total_ms": float(sum(regions))}
+
     # ---- device-resident timing --------------------------------------------------------
+    # Primary figure: ONE stream, launches as the library issues them (programmatic dependent launches:
+    # a launch may start filling SMs while its predecessor's last tiles drain; completion order is kept).
     launch_steps(args.warmup)
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(tstream)
-    launch_steps(args.steps)
-    e1.record(tstream)
-    barrier()
-    ms = e0.elapsed_time(e1)
-    # the same steps strictly one after the other (one stream): the kernel's own launch duration,
-    # without the overlap of one launch's tail with the next one's ramp
+    regions = timed_regions(nstreams, 50.0)
+    prim = summary(regions)
+    ms_step = prim["ms_per_launch_median"]
+    # Secondary: the same launches with the overlap switched off (every launch waits for its predecessor to
+    # leave the device) -- the duration of one launch alone, ramp and drain included
+    capi.set_option("plan_pdl", 0)
     launch_steps(min(args.warmup, 5), 1)
-    torch.cuda.synchronize()
-    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s0.record(tstream)
-    launch_steps(args.steps, 1)
-    s1.record(tstream)
-    torch.cuda.synchronize()
-    ms_single = sharding.max_over_ranks(s0.elapsed_time(s1), dev)
+    serial = summary(timed_regions(1, 25.0, 20))
+    capi.set_option("plan_pdl", args.pdl)
     # keep the clocks under observation for at least ~0.5 s of the same work
     t_end = time.perf_counter() + 0.5
-    s = 0
     while time.perf_counter() < t_end:
         launch_steps(64)
         torch.cuda.synchronize()
     torch.cuda.synchronize()
     clocks = sampler.stop()
-    ms_max = sharding.max_over_ranks(ms, dev)  # the job is as slow as its slowest rank
     mp_step = w * h * per_step / 1e6
-    value = sharding.whole_job_rate(mp_step * args.steps, world, ms_max * 1e-3)
+    value = sharding.whole_job_rate(mp_step, world, ms_step * 1e-3)
 
     # ---- end to end through the job API: host planes -> host pixels -----------------------
     L = ctx.lib
@@ -501,13 +621,18 @@ def run_ours(args) -> None:
                 checksum += row[0]
 
     e2e_steps(max(1, min(args.warmup, 3)))
-    barrier()
-    t0 = time.perf_counter()
-    e2e_steps(args.steps)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    e2e_value = sharding.whole_job_rate((w * h * e2e_frames / 1e6) * args.steps, world,
-                                        sharding.max_over_ranks(e2e_s, dev))
+    e2e_regions: list[float] = []
+    while True:
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps(args.steps)
+        torch.cuda.synchronize()
+        e2e_regions.append(sharding.max_over_ranks(time.perf_counter() - t0, dev))
+        if len(e2e_regions) >= 40 or (len(e2e_regions) >= 3 and sum(e2e_regions) >= 1.0):
+            break
+    e2e_s = float(np.median(e2e_regions))
+    e2e_value = sharding.whole_job_rate((w * h * e2e_frames / 1e6) * args.steps, world, e2e_s)
+    link = link_peak(dev, world)
     coef_bytes = h2d_frame
     for job in jobs:
         L.gidcuda_job_release(job)
@@ -527,37 +652,53 @@ def run_ours(args) -> None:
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        v, sample = cpu_reconstruct_rate(frames[:1], 3.0, cores)
+        v, sample = cpu_reconstruct_rate_processes(frames[:1], 3.0, cores)
+        vt, sample_t = cpu_reconstruct_rate(frames[:1], 3.0, cores)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-               "note": "oracle/gidref.c reconstruction only (GID restated in C, gcc -O2); GNAT unavailable"}
+               "threads_of_one_process": {"value": vt, "sample": sample_t},
+               "note": "oracle/gidref.c reconstruction only (GID restated in C, gcc -O2), one pinned process per "
+                       "host core; GNAT unavailable"}
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        achieved = alg_bytes_frame * per_step * args.steps / (ms_max * 1e-3) / 1e9
+        alg = alg_bytes_frame * per_step
+        achieved = alg / (ms_step * 1e-3) / 1e9
+        ach_serial = alg / (serial["ms_per_launch_median"] * 1e-3) / 1e9
+        e2e_bytes_s = e2e_value * 1e6 * (nbytes / (w * h))   # pixel bytes leaving over the link per second
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {desc}", "sampling": samp, "width": w, "height": h,
-                       "frames_per_step_per_gpu": per_step, "launch_streams": nstreams, "host_numa": numa, "parallelism": f"images sharded over {world} GPU(s), no collective",
-                       "l2": f"inputs larger than L2: ring of {ring} step-batches of {alg_bytes_frame * per_step / 1e6:.0f} MB each"},
+            "config": workload_config(args.workload, world),
+            "method": {"launch_streams": nstreams, "programmatic_dependent_launch": bool(args.pdl), "host_numa": numa,
+                       "l2": f"inputs larger than L2: ring of {ring} step-batches of {alg / 1e6:.0f} MB each",
+                       "timing": "CUDA events on the launching stream around EXACTLY --steps launches, barrier + synchronize "
+                                 "on both sides, max over ranks; regions repeated until >= 50 ms of device time; the median "
+                                 "region is reported", **prim},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": coef_bytes * e2e_frames,
                     "d2h_bytes_per_step": nbytes * e2e_frames, "frames_per_step": e2e_frames,
-                    "input": args.e2e_input,
+                    "input": args.e2e_input, "regions": len(e2e_regions), "timed_total_s": float(sum(e2e_regions)),
+                    "region_s_min": float(min(e2e_regions)), "region_s_max": float(max(e2e_regions)),
+                    "link_peak": link, "d2h_GBps": e2e_bytes_s / 1e9,
+                    "frac_of_link_d2h_peak": e2e_bytes_s / 1e9 / link["d2h_GBps"],
                     "api": ("gidcuda_job_submit/wait, pinned host coefficient records (one per non-zero coefficient, "
                             "gidcuda_job_records) -> expand + reconstruction kernels -> pinned host pixels, %d jobs in flight" % depth
                             if args.e2e_input == "records" else
                             "gidcuda_job_submit/wait, pinned host planes -> pinned host pixels, %d jobs in flight; " % depth +
                             "planes with empty block rows 4..7 (gidcuda_job_hint_rows) travel as pitched copies")},
             "gpu_launches": launches_per_step * args.steps,
+            # the kernel's own figure: algorithmic bytes of ONE launch / the average duration of a launch in ONE
+            # stream (launched as the library launches: programmatic dependent launches).  `serialized` = the
+            # same with the overlap of consecutive launches switched off.
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(args.workload), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes_frame * per_step,
-                         "launches_overlapped_on_streams": nstreams,
-                         "single_stream": {"ms_per_launch": ms_single / args.steps,
-                                           "achieved": alg_bytes_frame * per_step * args.steps / (ms_single * 1e-3) / 1e9,
-                                           "frac": alg_bytes_frame * per_step * args.steps / (ms_single * 1e-3) / 1e9 / peak}},
+                         "algorithmic_bytes_per_launch": alg,
+                         "ms_per_launch": ms_step, "ms_per_launch_min": prim["ms_per_launch_min"],
+                         "ms_per_launch_max": prim["ms_per_launch_max"],
+                         "serialized": {"ms_per_launch": serial["ms_per_launch_median"], "achieved": ach_serial,
+                                        "frac": ach_serial / peak, "regions": serial["regions"],
+                                        "note": "plan_pdl = 0: every launch waits for its predecessor to leave the device"}},
             "cpu_baseline": cpu,
         }
         if files is not None:
@@ -574,6 +715,9 @@ def run_ours(args) -> None:
 
 
 def main() -> None:
+    if len(sys.argv) >= 5 and sys.argv[1] == "--cpu-worker":
+        cpu_worker(int(sys.argv[2]), sys.argv[3], int(sys.argv[4]))
+        return
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -586,8 +730,8 @@ def main() -> None:
                     help="host-side form of the coefficients in the end-to-end leg: sparse records (what an entropy "
                          "decoder emits) or dense int16 planes")
     ap.add_argument("--e2e-depth", type=int, default=3, help="jobs in flight in the end-to-end leg")
-    ap.add_argument("--streams", type=int, default=2, choices=[1, 2, 4],
-                    help="launch streams for the device-resident leg (2: consecutive frames overlap tail and ramp)")
+    ap.add_argument("--streams", type=int, default=1, choices=[1, 2, 4],
+                    help="launch streams for the device-resident leg (default 1: the kernel's own figure)")
     ap.add_argument("--pdl", type=int, default=1, choices=[0, 1],
                     help="plan launches as programmatic dependent launches (library default 1); 0 = every launch "
                          "waits for its predecessor to leave the device")

@@ -25,12 +25,13 @@ OUT_BGR8_BOTTOM_UP = 1
 OUT_RGBA8 = 2
 FLAG_PACKED_ROWS = 0x100
 FLAG_ROTATE_90, FLAG_ROTATE_180, FLAG_ROTATE_270 = 0x200, 0x400, 0x600  # GID.Display_Orientation applied to the pixels
+FLAG_WIDE_COEF = 0x800  # some coefficient exceeds gidcuda_fast_coef_limit: the exact kernel instances run
 
 # every symbol include/gidcuda.h declares
 EXPORTS = [
     "gidcuda_abi_version", "gidcuda_device_count", "gidcuda_last_error", "gidcuda_set_option", "gidcuda_counter", "gidcuda_create",
     "gidcuda_destroy", "gidcuda_plane_geometry", "gidcuda_output_geometry", "gidcuda_job_begin",
-    "gidcuda_job_plane", "gidcuda_job_hint_rows", "gidcuda_job_records", "gidcuda_job_records_commit", "gidcuda_job_records_commit_runs",
+    "gidcuda_job_plane", "gidcuda_job_hint_rows", "gidcuda_fast_coef_limit", "gidcuda_job_wide_coefficients", "gidcuda_job_records", "gidcuda_job_records_commit", "gidcuda_job_records_commit_runs",
     "gidcuda_job_output", "gidcuda_job_scan", "gidcuda_host_is_pinned", "gidcuda_job_submit", "gidcuda_job_wait", "gidcuda_job_release",
     "gidcuda_plan_create", "gidcuda_plan_launch", "gidcuda_plan_launch_count", "gidcuda_plan_uses_tma",
     "gidcuda_plan_destroy", "gidcuda_synchronize", "gidcuda_batch_create", "gidcuda_batch_run",
@@ -123,6 +124,9 @@ def load_library() -> ctypes.CDLL:
     L.gidcuda_job_plane.restype = vp
     L.gidcuda_job_plane.argtypes = [vp, ctypes.c_int, i32p, i32p]
     L.gidcuda_job_hint_rows.argtypes = [vp, ctypes.c_int, ctypes.c_int]
+    L.gidcuda_fast_coef_limit.argtypes = [ctypes.POINTER(FrameDesc), ctypes.c_int]
+    L.gidcuda_fast_coef_limit.restype = ctypes.c_int32
+    L.gidcuda_job_wide_coefficients.argtypes = [vp]
     L.gidcuda_job_records.argtypes = [vp, ctypes.c_int, ctypes.POINTER(vp), ctypes.POINTER(vp),
                                       ctypes.POINTER(ctypes.c_size_t), i32p]
     L.gidcuda_job_records_commit.argtypes = [vp, ctypes.c_int, ctypes.c_size_t]
@@ -160,6 +164,17 @@ def set_option(name: str, value: int) -> None:
     rc = L.gidcuda_set_option(name.encode(), value)
     if rc != GIDCUDA_OK:
         raise GidCudaError(rc, (L.gidcuda_last_error(None) or b"").decode())
+
+
+def coefficients_are_wide(desc: "FrameDesc", planes: Sequence[np.ndarray]) -> bool:
+    """What an entropy decoder tracks while it stores coefficients: does any magnitude of component c
+    exceed gidcuda_fast_coef_limit(desc, c)?  (include/gidcuda.h, GIDCUDA_FLAG_WIDE_COEF)"""
+    L = load_library()
+    for c in range(desc.ncomp):
+        p = np.asarray(planes[c])
+        if p.size and int(np.abs(p.astype(np.int32)).max()) > L.gidcuda_fast_coef_limit(ctypes.byref(desc), c):
+            return True
+    return False
 
 
 def rows_used(plane: np.ndarray) -> int:
@@ -274,6 +289,8 @@ class GidCuda:
                 ctypes.memmove(p, src.ctypes.data, src.nbytes)
                 if hint_rows:
                     self._check(self.lib.gidcuda_job_hint_rows(job, c, rows_used(src)), self.ctx)
+            if not desc.flags & FLAG_WIDE_COEF and coefficients_are_wide(desc, planes):
+                self._check(self.lib.gidcuda_job_wide_coefficients(job), self.ctx)  # as a decoder would, after decoding
             self._check(self.lib.gidcuda_job_submit(job), self.ctx)
             pix, stride = ctypes.c_void_p(), ctypes.c_size_t()
             self._check(self.lib.gidcuda_job_wait(job, ctypes.byref(pix), ctypes.byref(stride)), self.ctx)

@@ -88,8 +88,11 @@ __device__ __forceinline__ int extend(uint32_t v, int n) {  // Bin_Twos_Compleme
 }
 
 // One block; false = something the host decoder has to look at
+// |v| < 2**bits  (v = -2**bits counts as outside)
+__device__ __forceinline__ bool within_bits(int v, int bits) { return ((uint32_t)(v ^ (v >> 31)) >> bits) == 0u; }
+
 __device__ __forceinline__ bool decode_block(Bits &b, const HuffDev &dc, const HuffDev &ac, int &pred, int16_t *blk,
-                                             const uint8_t *zz) {
+                                             const uint8_t *zz, int limbits) {
   if (b.len <= 32) b.refill();
   const int s = symbol(b, dc);
   if (s < 0) return false;
@@ -97,6 +100,9 @@ __device__ __forceinline__ bool decode_block(Bits &b, const HuffDev &dc, const H
   if (n) {
     pred += extend(b.peek(n), n);
     b.drop(n);
+    // the reference keeps a 32-bit predictor (:766-771): one that leaves the range of the planes (or of
+    // the fast reconstruction instances) is the host decoder's case
+    if (!within_bits(pred, limbits)) return false;
   }
   blk[0] = (int16_t)pred;
   int coef = 0;
@@ -109,6 +115,7 @@ __device__ __forceinline__ bool decode_block(Bits &b, const HuffDev &dc, const H
     if (m == 0 && code != 0xF0) return false;
     coef += (code >> 4) + 1;
     if (coef > 63) return false;
+    if (m > limbits) return false;  // a value of category m is below 2**m
     if (m) {
       GIDK_ASSERT(coef >= 1 && coef <= 63 && zz[coef] < 64);
       blk[zz[coef]] = (int16_t)extend(b.peek(m), m);
@@ -150,7 +157,7 @@ __global__ void __launch_bounds__(128) huffman_intervals_kernel(ScanArgs a) {
           const size_t blockno = (size_t)(my * a.v[c] + sy) * a.bx[c] + (mx * a.h[c] + sx);
           GIDK_ASSERT(blockno < (size_t)a.bx[c] * a.v[c] * ((a.nmcu + a.mcux - 1) / a.mcux));
           int16_t *blk = a.plane[c] + blockno * 64;
-          ok = decode_block(b, tabs[c], tabs[3 + c], pred[c], blk, zz);
+          ok = decode_block(b, tabs[c], tabs[3 + c], pred[c], blk, zz, a.limbits[c]);
         }
   }
   // every interval but the last ends where its RSTn begins: all bytes read, less than a byte
@@ -247,6 +254,7 @@ struct BlockSlot {
   int16_t *plane;
   uint32_t row_blocks;  // blocks per block row of the component's plane
   uint32_t h, v, sx, sy, comp;
+  int32_t limbits;  // WholeArgs::limbits of the component
 };
 
 // Decodes the code words of subsequence `i` that start before bit `limit`, from state `entry`.
@@ -314,7 +322,10 @@ __device__ __forceinline__ uint64_t run_subsequence(const WholeArgs &a, const Hu
         pred0 += k == 0 ? v : 0;
         pred1 += k == 1 ? v : 0;
         pred2 += k == 2 ? v : 0;
-        blk[0] = (int16_t)(k == 0 ? pred0 : (k == 1 ? pred1 : pred2));
+        const int pk = k == 0 ? pred0 : (k == 1 ? pred1 : pred2);
+        // (the reference's predictor has 32 bits, :766-771; out of range: the host decoder's case)
+        if (!within_bits(pk, slots[c].limbits)) { *bad = true; break; }
+        blk[0] = (int16_t)pk;
       } else {
         dcs0 += k == 0 ? v : 0;
         dcs1 += k == 1 ? v : 0;
@@ -325,7 +336,7 @@ __device__ __forceinline__ uint64_t run_subsequence(const WholeArgs &a, const Hu
       block_done = true;  // EOB
     } else {
       const uint32_t idx = zpos + (uint32_t)(sym >> 4);
-      if (FINAL && ((n == 0 && sym != 0xF0) || idx > 63)) { *bad = true; break; }
+      if (FINAL && ((n == 0 && sym != 0xF0) || idx > 63 || n > (int)slots[c].limbits)) { *bad = true; break; }
       if (n) {
         const int v = extend(bits.peek(n), n);
         bits.drop(n);
@@ -370,6 +381,7 @@ __device__ __forceinline__ void load_tables(const WholeArgs &a, HuffDev *tabs, u
           q.sx = (uint32_t)sx;
           q.sy = (uint32_t)sy;
           q.comp = (uint32_t)k;
+          q.limbits = a.limbits[k];
           if (cc < 12) slots[cc] = q;
         }
   }

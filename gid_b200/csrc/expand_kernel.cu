@@ -31,7 +31,8 @@ __global__ void __launch_bounds__(256) expand_records_kernel(ExpandArgs a) {
   for (int i = 0; i < 8; i++) reinterpret_cast<uint4 *>(dst)[i] = z;
   // same thread, same addresses: the stores below are ordered after the zeroes
   const uint32_t *rec = a.records[c];
-  const uint32_t end = __ldg(a.first[c] + seq + 1);
+  // first[] is the caller's: whatever it holds, no read leaves the committed records
+  const uint32_t end = min(__ldg(a.first[c] + seq + 1), a.count[c]);
   for (uint32_t i = __ldg(a.first[c] + seq); i < end; i++) {
     const uint32_t w = __ldg(rec + i);
     dst[w & 63u] = (int16_t)(w >> 16);

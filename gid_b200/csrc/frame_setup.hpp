@@ -44,6 +44,28 @@ struct Geometry {
 
 inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Largest coefficient magnitude of component c for which the fast kernel instances are the reference:
+// every |coefficient * table entry| <= 2**16.  Then no sum of Row_IDCT (:813-843: at most
+// 18 377 * max|blk| + 256 in magnitude) wraps, blk(4) * 2**11 is zero only for blk(4) = 0, blk(0) * 8 is the
+// general path with rounding constant 0, and the row outputs (< 2**23 - 32) keep Col_IDCT's shortcut
+// (:858-862) equal to its general path.  JPEGs of 8-bit samples stay far inside (|coefficient * entry| <=
+// 1024 + entry / 2 before the encoder's rounding).
+inline int32_t fast_coef_limit(const gidcuda_frame_desc *d, int c);
+// ... as a bit count: magnitudes below 2**bits are inside the limit (what the Huffman decoders test: a
+// value of category n is below 2**n)
+inline int32_t fast_coef_bits(const gidcuda_frame_desc *d, int c) {
+  const uint32_t lim = (uint32_t)fast_coef_limit(d, c) + 1u;
+  int32_t b = 0;
+  while ((2u << b) <= lim) b++;
+  return b;
+}
+inline int32_t fast_coef_limit(const gidcuda_frame_desc *d, int c) {
+  uint32_t most = 1;
+  for (int i = 0; i < 64; i++) most = d->qt[c][i] > most ? d->qt[c][i] : most;
+  const uint32_t lim = 65536u / most;
+  return (int32_t)(lim > 32767u ? 32767u : lim);
+}
+
 // Validates a frame descriptor and derives everything the launch needs.
 // Mirrors Read_SOF / Read_SOS geometry (gid-decoding_jpg.adb:244-276, :1945-1951).
 inline int make_geometry(std::string *err, const gidcuda_frame_desc *d, Geometry *g) {
@@ -85,9 +107,11 @@ inline int make_geometry(std::string *err, const gidcuda_frame_desc *d, Geometry
     off += round_up(g->plane_bytes[c], 256);
     g->sample_off[c] = soff;
     soff += round_up((size_t)g->bx[c] * g->by[c] * 64, 256);
+    // the fast domain of the fused kernels (recon_body.cuh, dequant_idct_sparse): entries 1 .. 255
     for (int i = 0; i < 64; i++)
-      if (d->qt[c][i] > 255) g->q8 = false;
+      if (d->qt[c][i] > 255 || d->qt[c][i] == 0) g->q8 = false;
   }
+  if (d->flags & GIDCUDA_FLAG_WIDE_COEF) g->q8 = false;  // ... and coefficients within +-4095
   g->coef_bytes = off;
   g->sample_bytes = soff;
   g->out_format = (int)(d->flags & GIDCUDA_OUT_MASK);

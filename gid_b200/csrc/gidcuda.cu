@@ -236,6 +236,18 @@ static int job_reserve(gidcuda_job *j) {
   return GIDCUDA_OK;
 }
 
+// launch tables for this frame (device addresses are fixed once job_reserve has run)
+static void job_build_set(gidcuda_job *j) {
+  gidk::FrameItem it;
+  it.desc = &j->desc;
+  it.geo = j->geo;
+  for (int c = 0; c < 3; c++)
+    it.planes[c] = c < j->geo.ncomp ? reinterpret_cast<const int16_t *>(j->d_coef + j->geo.plane_off[c]) : nullptr;
+  it.pixels = j->d_pixels;
+  it.samples = j->d_samples;
+  j->set.build(std::vector<gidk::FrameItem>(1, it));
+}
+
 extern "C" int gidcuda_job_begin(gidcuda_ctx *ctx, const gidcuda_frame_desc *desc, gidcuda_job **out) {
   if (!ctx || !out) return fail(ctx, GIDCUDA_ERR_BAD_ARGUMENT, "null argument");
   *out = nullptr;
@@ -270,20 +282,15 @@ extern "C" int gidcuda_job_begin(gidcuda_ctx *ctx, const gidcuda_frame_desc *des
     delete j;
     return rc;
   }
-  // launch tables for this frame (device addresses are fixed from here on)
-  gidk::FrameItem it;
-  it.desc = &j->desc;
-  it.geo = g;
-  for (int c = 0; c < 3; c++)
-    it.planes[c] = c < g.ncomp ? reinterpret_cast<const int16_t *>(j->d_coef + g.plane_off[c]) : nullptr;
-  it.pixels = j->d_pixels;
-  it.samples = j->d_samples;
-  j->set.build(std::vector<gidk::FrameItem>(1, it));
+  job_build_set(j);
   j->h_coef_clean = false;  // zeroed when the decoder asks for the planes
   j->user_pixels = nullptr;
   j->scan_active = false;
   for (int c = 0; c < 3; c++) {
     j->rows_hint[c] = 8;
+    // a recycled job's device planes hold another frame's geometry: whatever was zeroed there, the
+    // rows 4 .. 7 of THIS frame's blocks are not known to be
+    j->d_tail_zero[c] = false;
     j->sparse[c] = false;
     j->sparse_count[c] = 0;
     j->sparse_runs[c].clear();
@@ -404,6 +411,25 @@ extern "C" int gidcuda_job_output(gidcuda_job *job, uint8_t *host_pixels, size_t
   return GIDCUDA_OK;
 }
 
+extern "C" int32_t gidcuda_fast_coef_limit(const gidcuda_frame_desc *desc, int comp) {
+  if (!desc || comp < 0 || comp >= 3) return 0;
+  return gidk::fast_coef_limit(desc, comp);
+}
+
+extern "C" int gidcuda_job_wide_coefficients(gidcuda_job *job) {
+  if (!job) return fail(nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "null job");
+  if (job->state != gidcuda_job::BEGUN)
+    return fail(job->ctx, GIDCUDA_ERR_STATE, "gidcuda_job_wide_coefficients: only between gidcuda_job_begin and gidcuda_job_submit");
+  if (job->desc.flags & GIDCUDA_FLAG_WIDE_COEF) return GIDCUDA_OK;
+  job->desc.flags |= GIDCUDA_FLAG_WIDE_COEF;
+  Geometry g;
+  const int rc = geometry_or_fail(job->ctx, &job->desc, &g);  // same geometry, exact kernel instances
+  if (rc != GIDCUDA_OK) return rc;
+  job->geo = g;
+  job_build_set(job);
+  return GIDCUDA_OK;
+}
+
 extern "C" int gidcuda_job_hint_rows(gidcuda_job *job, int comp, int rows_used) {
   if (!job) return fail(nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "null job");
   if (job->state == gidcuda_job::IDLE) return fail(job->ctx, GIDCUDA_ERR_STATE, "gidcuda_job_hint_rows: job was released");
@@ -497,6 +523,7 @@ extern "C" int gidcuda_job_submit(gidcuda_job *job) {
       ea.bx[c] = (uint32_t)g.bx[c];
       if (!job->sparse[c]) continue;  // nblocks stays 0: the component's plane came as a dense copy
       ea.nblocks[c] = (uint32_t)nb;
+      ea.count[c] = (uint32_t)job->sparse_count[c];
       ea.first[c] = reinterpret_cast<const uint32_t *>(job->d_sparse + job->sparse_off[c]);
       ea.records[c] = ea.first[c] + nb + 1;
       ea.plane[c] = reinterpret_cast<int16_t *>(job->d_coef + g.plane_off[c]);

@@ -163,6 +163,7 @@ static void make_whole_args(gidcuda_job *job, gidk::WholeArgs *out) {
     wa.bx[c] = (uint32_t)g.bx[c];
     wa.h[c] = job->desc.samp_h[c];
     wa.v[c] = job->desc.samp_v[c];
+    wa.limbits[c] = gidk::fast_coef_bits(&job->desc, c);
     blocks += (uint32_t)g.bx[c] * (uint32_t)g.by[c];
     k += (uint32_t)(wa.h[c] * wa.v[c]);
     job->d_tail_zero[c] = false;
@@ -330,6 +331,7 @@ int job_submit_scan(gidcuda_job *job, cudaStream_t s) {
       sa.bx[c] = (uint32_t)g.bx[c];
       sa.h[c] = job->desc.samp_h[c];
       sa.v[c] = job->desc.samp_v[c];
+      sa.limbits[c] = gidk::fast_coef_bits(&job->desc, c);
       job->d_tail_zero[c] = false;
     }
     sa.ncomp = g.ncomp;

@@ -180,6 +180,39 @@ GID_HD void dequant_row(const u32x4 &w, const uint32_t *q, int &c0, int &c1, int
 //     those rows are not touched and the column pass runs its 3-input form
 //     (col_idct_lo3), otherwise the general column pass.
 // Dense data takes the general path everywhere; the result is the same either way.
+//
+// Q8 is also the kernels' FAST DOMAIN: every table entry in 1 .. 255 and every |coefficient * entry| <= 2**16
+// (frame_setup.hpp, fast_coef_limit; anything else runs dequant_idct_exact below).  Inside it the decisions
+// taken here on RAW coefficients are the reference's, which takes them on de-quantised values (:803-812):
+//   * raw != 0  <=>  raw * q != 0, and blk(4) * 2**11 is zero only for blk(4) = 0;
+//   * no sum of the row pass wraps, so the general path with rounding constant 0 IS blk(0) * 8;
+//   * column inputs stay below 2**23 - 32, where the column shortcut (:858-862) is the general path.
+
+// The exact instance (Q8 = false: 16-bit tables, tables with an entry of 0, wide coefficients -- rare):
+// every row de-quantised, the reference's own tests per block on the de-quantised values, both shortcuts
+// carried literally.  Reproduces the reference's 32-bit wrap-around for every 16-bit input.
+GID_HD void dequant_idct_exact(bool active, const u32x4 (&raw)[8], const uint32_t *qw, u32x2 *dst, int dst_stride) {
+  constexpr bool Q8 = false;
+  int b[64];
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    int *row = &b[8 * r];
+    dequant_row<Q8>(raw[r], qw + 4 * r, row[0], row[1], row[2], row[3], row[4], row[5], row[6], row[7]);
+    const bool ac = row_has_ac(row[1], row[2], row[3], row[4], row[5], row[6], row[7]);
+    const int flat = wmul(row[0], 8);
+    if (warp_any(active && ac)) row_idct_rnd(128, row[0], row[1], row[2], row[3], row[4], row[5], row[6], row[7]);
+    if (!ac) {
+#pragma unroll
+      for (int c = 0; c < 8; c++) row[c] = flat;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 8; c++)
+    col_idct_exact(b[c], b[8 + c], b[16 + c], b[24 + c], b[32 + c], b[40 + c], b[48 + c], b[56 + c]);
+  store_block_packed(b, dst, dst_stride);
+}
+
+// The fast instance.
 template <bool Q8, bool LO3>
 GID_HD void dequant_idct_sparse(bool active, const u32x4 (&raw)[8], const uint32_t *qw, u32x2 *dst, int dst_stride) {
   int b[64];
@@ -513,7 +546,8 @@ GID_HD void mcu_item(int it, bool active, const FrameDev &f, const uint32_t *qw,
     dst = comp == 1 ? sc.cb : sc.cr;
     src.release();
   }
-  dequant_idct_sparse<Q8, H * V == 1>(active, raw, qw + 32 * comp, dst, sc.stride);
+  if (Q8) dequant_idct_sparse<true, H * V == 1>(active, raw, qw + 32 * comp, dst, sc.stride);
+  else dequant_idct_exact(active, raw, qw + 32 * comp, dst, sc.stride);
   if (comp == 0) {
     if (active) emit_block_rows<H, V, GREY, RGBA>(f, se, bxi * 8, byi * 8, sx, sy);
     src.release();

@@ -55,6 +55,7 @@ struct ExpandArgs {
   const uint32_t *records[3];
   int16_t *plane[3];
   uint32_t nblocks[3];
+  uint32_t count[3];  // records committed: a first[] entry beyond it is clamped (the arrays come from the caller)
   uint32_t bx[3];
   uint32_t mcux;
   int32_t h[3], v[3];
@@ -80,6 +81,10 @@ struct ScanArgs {
   int32_t ncomp;
   uint32_t mcux, nmcu, ri, nintervals;
   uint32_t *status;             // [0] flags (1 = an interval was left to the host), [1] how many
+  // Magnitudes of component c must stay below 2**limbits[c] (the range of the fast reconstruction
+  // instances, frame_setup.hpp fast_coef_limit, rounded down to a power of two; at most 15 so that the
+  // DC predictor fits the int16 planes): anything wider is left to the host decoder, which marks the frame.
+  int32_t limbits[3];
 };
 cudaError_t launch_huffman_intervals(const ScanArgs &a, cudaStream_t stream);
 
@@ -98,6 +103,7 @@ struct WholeArgs {
   uint32_t *status;        // [0] flags (2 = chain of states not settled, 8 = undecodable), [2] blocks stored
   uint4 *zero_base;        // the job's coefficient planes, zeroed by the first sync launch together with
   uint32_t zero_count;     // status[] (one stream operation each less per frame); count in 16-byte units
+  int32_t limbits[3];      // as in ScanArgs
 };
 cudaError_t launch_huffman_whole(const WholeArgs &a, cudaStream_t stream);
 cudaError_t launch_huffman_finish(const WholeArgs &a, cudaStream_t stream);  // scan + output over the chain as it stands

@@ -217,9 +217,19 @@ GID_HD void row_idct_rnd(int rnd, int &b0, int &b1, int &b2, int &b3, int &b4, i
   tdiv2<8, kRowOutMulHi>(wadd(Q, x2), wsub(Q, x2), b1, b6);
   tdiv2<8, kRowOutMulHi>(wadd(N, x4), wsub(N, x4), b2, b5);
 }
+// Row_IDCT exactly as the reference decides it (:803-812): the shortcut is taken when x1 .. x7 are zero,
+// where x1 = blk(4) * 2**11 -- a blk(4) that is a non-zero multiple of 2**21 counts as zero -- and its
+// result is blk(0) * 8 (which the general path with rnd = 0 only equals while blk(0) * 2**11 does not wrap).
+// One block per thread with its own branch: the generic kernels and the exact variant of the fused ones.
+GID_HD bool row_has_ac(int b1, int b2, int b3, int b4, int b5, int b6, int b7) {
+  return (b1 | b2 | b3 | wmul(b4, 2048) | b5 | b6 | b7) != 0;
+}
 GID_HD void row_idct(int &b0, int &b1, int &b2, int &b3, int &b4, int &b5, int &b6, int &b7) {
-  const int any_ac = b1 | b2 | b3 | b4 | b5 | b6 | b7;
-  row_idct_rnd(any_ac != 0 ? 128 : 0, b0, b1, b2, b3, b4, b5, b6, b7);
+  if (!row_has_ac(b1, b2, b3, b4, b5, b6, b7)) {
+    b0 = b1 = b2 = b3 = b4 = b5 = b6 = b7 = wmul(b0, 8);
+    return;
+  }
+  row_idct_rnd(128, b0, b1, b2, b3, b4, b5, b6, b7);
 }
 
 // Col_IDCT, gid-decoding_jpg.adb:847-895, general path only: the shortcut at
@@ -229,8 +239,26 @@ GID_HD void row_idct(int &b0, int &b1, int &b2, int &b3, int &b4, int &b5, int &
 // K = 14 (the output stage) keeps the one-value form: its bias 16383 is not a byte or
 // half-word multiple, and scaling the sums by 4 to use the K = 16 form would change
 // the wrap-around behaviour of out-of-range streams.
+// GIDK_TDIV14_PAIR (experiment): the two outputs of a butterfly share one sign extraction (PRMT) and
+// take their bias 16383 = 255 * 64 + 63 from two byte dot products on the FMA pipe (u8 0xFF * 64,
+// then s8 (-1) * (-63)): 1.5 ALU + 2 FMA instructions per output instead of 2 + 1.
+GID_HD void tdiv14_pair_128(int x1, int x2, int &r1, int &r2) {
+  const uint32_t sp = sign_pair(x1, x2);
+  const int t1 = dp4a_ss(sp, 0x000000C1u, dp4a_uu(sp, 0x00000040u, x1));
+  const int t2 = dp4a_ss(sp, 0x00C10000u, dp4a_uu(sp, 0x00400000u, x2));
+  r1 = wadd(t1 >> 14, 128);
+  r2 = wadd(t2 >> 14, 128);
+}
 GID_HD void col_outputs(int A, int B, int e2, int e3, int p1, int p6, int x2, int x4, int &b0, int &b1, int &b2,
                         int &b3, int &b4, int &b5, int &b6, int &b7) {
+#if defined(GIDK_TDIV14_PAIR)
+  const int P = wadd(A, e3), M = wsub(A, e3), Q = wadd(B, e2), N = wsub(B, e2);
+  tdiv14_pair_128(wadd(P, p1), wsub(P, p1), b0, b7);
+  tdiv14_pair_128(wadd(M, p6), wsub(M, p6), b3, b4);
+  tdiv14_pair_128(wadd(Q, x2), wsub(Q, x2), b1, b6);
+  tdiv14_pair_128(wadd(N, x4), wsub(N, x4), b2, b5);
+  return;
+#endif
   b0 = wadd(tdiv<14>(wadd3(A, e3, p1)), 128);
   b7 = wadd(tdiv<14>(wadd3(A, e3, wneg(p1))), 128);
   b3 = wadd(tdiv<14>(wadd3(A, wneg(e3), p6)), 128);
@@ -252,6 +280,17 @@ GID_HD void col_idct(int &b0, int &b1, int &b2, int &b3, int &b4, int &b5, int &
   const int h = wmad(181, q4, 128);
   tdiv2<8>(wmad(181, q5, h), wmad(-181, q5, h), x2, x4);
   col_outputs(A, B, e2, e3, p1, p6, x2, x4, b0, b1, b2, b3, b4, b5, b6, b7);
+}
+
+// Col_IDCT with the reference's shortcut (:858-862) where it is NOT the general path: x1 .. x7 zero with
+// x1 = blk(4 rows down) * 2**8, result Clip((b0 + 32) / 64 + 128).  It only differs from the general path
+// when b0 * 256 + 8192 wraps (|b0| within 32 of 2**23: streams far outside any JPEG), so the fast kernels
+// leave it out; the exact variant and the generic kernels carry it.
+GID_HD void col_idct_exact(int &b0, int &b1, int &b2, int &b3, int &b4, int &b5, int &b6, int &b7) {
+  const bool shortcut = (b1 | b2 | b3 | wmul(b4, 256) | b5 | b6 | b7) == 0;
+  const int v = wadd(tdiv<6>(wadd(b0, 32)), 128);
+  col_idct(b0, b1, b2, b3, b4, b5, b6, b7);
+  if (shortcut) b0 = b1 = b2 = b3 = b4 = b5 = b6 = b7 = v;
 }
 
 // Col_IDCT for a column whose inputs b3 .. b7 are zero (rows 3 .. 7 of the
@@ -278,7 +317,7 @@ GID_HD void idct_8x8(int (&b)[64]) {
              b[8 * r + 6], b[8 * r + 7]);
 #pragma unroll
   for (int c = 0; c < 8; c++)
-    col_idct(b[c], b[8 + c], b[16 + c], b[24 + c], b[32 + c], b[40 + c], b[48 + c], b[56 + c]);
+    col_idct_exact(b[c], b[8 + c], b[16 + c], b[24 + c], b[32 + c], b[40 + c], b[48 + c], b[56 + c]);
 }
 
 // Four samples -> four saturated bytes (Clip, :755-756, then packing), v0 in the

@@ -299,6 +299,23 @@ void *decode_and_submit(Image_Descriptor &image, void *ctx_, const std::function
       rc = gidcuda_job_hint_rows(job, comp_of[c], dec.last_row[c] + 1);
       if (rc != GIDCUDA_OK) raise_from_status(rc, ctx);
     }
+    // What the decoder stored, against what the planes and the fast kernel instances hold
+    // (include/gidcuda.h, GIDCUDA_FLAG_WIDE_COEF).  The reference keeps 32-bit values all the way
+    // (dc_predictor * qt_local (0), gid-decoding_jpg.adb:766-771, with differences of up to 15 bits, :727-733):
+    // a term that has left the 16 bits of a plane cannot be handed over -- reported, not painted wrongly.
+    if (!dec.device_scanned) {
+      bool wide = false;
+      for (int c = 0; c < 3; c++) {
+        if (!image.info[c].present) continue;
+        if (dec.mag[c] > 32767u)
+          throw unsupported_image_subformat("JPEG: a coefficient of the stream exceeds 16 bits (DC predictor out of range)");
+        if (dec.mag[c] > (uint32_t)gidcuda_fast_coef_limit(&desc, comp_of[c])) wide = true;
+      }
+      if (wide) {
+        rc = gidcuda_job_wide_coefficients(job);
+        if (rc != GIDCUDA_OK) raise_from_status(rc, ctx);
+      }
+    }
     if (out && gidcuda_host_is_pinned(out)) {
       rc = gidcuda_job_output(job, out, out_capacity);
       if (rc != GIDCUDA_OK) raise_from_status(rc, ctx);

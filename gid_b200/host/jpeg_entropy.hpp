@@ -485,6 +485,11 @@ struct Decoder {
   std::function<void(int)> spill;     // sink[c] is nearly full: switch component c to its dense plane
   int dc_pred[3] = {0, 0, 0};
   int last_row[3] = {0, 0, 0};  // last block row (natural order) a coefficient was stored in, per component
+  // OR of the magnitudes stored per component (v >= 0 ? v : ~v): below 2**n exactly when every magnitude is.
+  // The DC predictor enters with all its 32 bits (:766-771), before it is cut to the planes' 16.
+  // Read after the last scan: gidcuda_job_wide_coefficients / the range of the planes (gid_jpeg_host.cpp).
+  uint32_t mag[3] = {0, 0, 0};
+  static uint32_t magnitude(int v) { return (uint32_t)(v ^ (v >> 31)); }
   int ht_dc[3] = {0, 0, 0}, ht_ac[3] = {0, 0, 0};
   int mcu_count_image_v = 0, mcu_count_image_h = 0;
   int rst_count = 0, next_rst = 0;
@@ -535,10 +540,11 @@ struct Decoder {
   // k = record sink (blk == nullptr) or nullptr (dense block blk).  Static: the restart-parallel
   // scan runs it on several threads, each with its own bit buffer, predictor and sink.
   static void baseline_block(WideBits &bits, const HuffTable &dc, const HuffTable &ac, int &dc_pred, RecordSink *k,
-                             int16_t *blk, int &last_row) {
+                             int16_t *blk, int &last_row, uint32_t &mag) {
     if (k) k->first[k->seq++] = (uint32_t)k->n;
     const int s = bits.symbol(dc);
     dc_pred += bits.receive_extend(s & 15);
+    mag |= magnitude(dc_pred);
     if (blk) blk[0] = (int16_t)dc_pred;
     else if ((int16_t)dc_pred != 0) k->put(0, dc_pred);
     int coef = 0;
@@ -575,6 +581,7 @@ struct Decoder {
         value = bits.receive_extend(code & 15);
       }
       const int nat = kZigZag[coef];
+      mag |= magnitude(value);
       if (blk) {
         blk[nat] = (int16_t)value;
         if ((nat >> 3) > last_row) last_row = nat >> 3;
@@ -756,6 +763,7 @@ struct Decoder {
       }
     std::vector<Run> out((size_t)T);
     std::vector<std::array<int, 3>> rows((size_t)T, std::array<int, 3>{{0, 0, 0}});
+    std::vector<std::array<uint32_t, 3>> mags((size_t)T, std::array<uint32_t, 3>{{0, 0, 0}});
     std::atomic<bool> failed{false};
     const int mh = mcu_count_image_h;
     auto work = [&](int w) {
@@ -791,7 +799,7 @@ struct Decoder {
                 for (int sx = 0; sx < ci.samples_hor; sx++)
                   baseline_block(wb, *tdc[c], *tac[c], pred[c], k,
                                  k ? nullptr : plane[c].block(mx * ci.samples_hor + sx, my * ci.samples_ver + sy),
-                                 rows[(size_t)w][(size_t)c]);
+                                 rows[(size_t)w][(size_t)c], mags[(size_t)w][(size_t)c]);
             }
           }
           // every interval but the last must end where its RSTn begins: all bytes loaded, less
@@ -820,6 +828,7 @@ struct Decoder {
     // -- stitch: first[] numbers the records of the concatenated runs
     for (int c = 0; c < 3; c++) {
       if (!im.info[c].present) continue;
+      for (int w = 0; w < T; w++) mag[c] |= mags[(size_t)w][(size_t)c];
       if (!sink[c].on) {
         for (int w = 0; w < T; w++) last_row[c] = std::max(last_row[c], rows[(size_t)w][(size_t)c]);
         continue;
@@ -866,7 +875,7 @@ struct Decoder {
               if (k.on && k.n + 64 > k.cap) spill(c);
               baseline_block(wb, *tdc[c], *tac[c], dc_pred[c], k.on ? &k : nullptr,
                              k.on ? nullptr : plane[c].block(mx * ci.samples_hor + sx, my * ci.samples_ver + sy),
-                             last_row[c]);
+                             last_row[c], mag[c]);
             }
         }
         if (!(my == mv - 1 && mx == mh - 1)) check_restart_wide(wb);
@@ -882,6 +891,7 @@ struct Decoder {
   template <class B> void dc_first(B &bits, int c, int16_t *blk, int al) {
     const int s = bits.symbol(table(0, ht_dc[c]));
     dc_pred[c] += bits.receive_extend(s & 15);
+    mag[c] |= magnitude(dc_pred[c] * (1 << al));
     blk[0] = (int16_t)(dc_pred[c] * (1 << al));
   }
   template <class B> void dc_refine(B &bits, int16_t *blk, int al) {
@@ -912,7 +922,9 @@ struct Decoder {
         k += rr;
         if (k > 63) throw error_in_image_data("JPEG: progressive: coefficient index > 63");
         const int nat = kZigZag[k];
-        blk[nat] = (int16_t)(bits.receive_extend(s) * (1 << al));
+        const int value = bits.receive_extend(s) * (1 << al);
+        mag[c] |= magnitude(value);
+        blk[nat] = (int16_t)value;
         mask = blk[nat] != 0 ? mask | (1ull << k) : mask & ~(1ull << k);
         if ((nat >> 3) > last_row[c]) last_row[c] = nat >> 3;
         k++;
@@ -921,6 +933,7 @@ struct Decoder {
   }
   template <class B> void ac_refine(B &bits, int c, int16_t *blk, int ss, int se, int al) {
     const int p1 = 1 << al, m1 = -(1 << al);
+    mag[c] |= (uint32_t)p1;  // new coefficients are +-p1; corrections only set a bit below an existing leading one
     int k = ss;
     uint64_t &mask = mask_of(c, blk);
     if (eobrun <= 0) {
@@ -1002,6 +1015,7 @@ struct Decoder {
       const int c = comps[i];
       const size_t nb = (size_t)plane[c].blocks_x * (size_t)plane[c].blocks_y;
       if (nzmask[c].size() != nb) nzmask[c].assign(nb, 0);
+      if (ss == 0 && ah > 0) mag[c] |= 1u << al;  // DC refinement ORs bit al into the DC terms
     }
     rst_count = im.restart_interval;
     next_rst = 0;

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define GIDCUDA_ABI_VERSION 3
+#define GIDCUDA_ABI_VERSION 4
 
 /* Status codes.  The Ada binding maps DATA -> GID.error_in_image_data,
  * UNSUPPORTED -> GID.unsupported_image_subformat, the others ->
@@ -74,6 +74,18 @@ enum {
 #define GIDCUDA_FLAG_ROTATE_180 0x400u
 #define GIDCUDA_FLAG_ROTATE_270 0x600u
 #define GIDCUDA_FLAG_ROTATE_MASK 0x600u
+/* Set by the entropy decoder when it has stored, in some component c, a coefficient whose magnitude
+ * exceeds gidcuda_fast_coef_limit(desc, c) = 65536 / (largest entry of the component's table).  No JPEG of
+ * 8-bit samples holds one (|coefficient * entry| stays near 1024); Decode_8x8_Block accepts magnitudes up
+ * to 15 bits (gid-decoding_jpg.adb:727-733).  The fast kernel instances decide the row shortcut of
+ * Inverse_DCT_8x8_Block (:803-812) on raw coefficients and leave the column shortcut (:858-862) out, which
+ * is the reference's arithmetic while every |coefficient * entry| <= 2**16.  Frames that carry this flag --
+ * like frames whose tables hold an entry of 0 or above 255 -- run the instances that decide on
+ * de-quantised values per block and carry both shortcuts literally: they reproduce the reference's
+ * 32-bit wrap-around for EVERY 16-bit coefficient and every table (a few percent slower).  The host mirror
+ * and the device Huffman decoders track the range themselves (gidcuda_job_wide_coefficients); a caller
+ * that fills planes or records by other means sets the flag unless it knows its coefficients are in range. */
+#define GIDCUDA_FLAG_WIDE_COEF 0x800u
 
 /* One JPEG frame, as the entropy decoder knows it after SOF/DQT/SOS
  * (Read_SOF gid-decoding_jpg.adb:184-318, Read_DQT :393-422). */
@@ -150,6 +162,11 @@ int16_t *gidcuda_job_plane(gidcuda_job *job, int comp, int32_t *blocks_x, int32_
  * gidcuda_job_begin) promises nothing.  Holds until changed or the job is released.
  * A decoder tracks it for free: rows_used = 1 + (largest zig_zag(k) it stored) / 8. */
 int gidcuda_job_hint_rows(gidcuda_job *job, int comp, int rows_used);
+/* Range of the fast kernel instances for component comp (see GIDCUDA_FLAG_WIDE_COEF), and the call by which
+ * an entropy decoder that only learns the range while decoding -- after gidcuda_job_begin -- marks the
+ * frame: same effect as the flag in the descriptor.  Between gidcuda_job_begin and gidcuda_job_submit. */
+int32_t gidcuda_fast_coef_limit(const gidcuda_frame_desc *desc, int comp);
+int gidcuda_job_wide_coefficients(gidcuda_job *job);
 /* ---- sparse coefficient input (optional, per component) --------------------
  * What an entropy decoder produces is sparse: Decode_8x8_Block reads (run, value)
  * pairs until EOB (:774-786), a handful per block at ordinary qualities, while a

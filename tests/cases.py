@@ -58,3 +58,97 @@ def random_planes(rng: np.random.Generator, blocks_x, blocks_y, kind: str) -> li
             raise ValueError(kind)
         out.append(p.astype(np.int16))
     return out
+
+
+def edge_frames(synth):
+    """(name, Frame) pairs on the EDGE of the reconstruction's domain: where the reference's decisions
+    (row shortcut on blk(4) * 2**11 and the de-quantised terms, gid-decoding_jpg.adb:803-812; column shortcut
+    :858-862) part from the same decisions taken on raw coefficients, and where its 32-bit sums wrap.
+    Tables with entries of 0 are illegal in T.81 but GID reads them (Natural, :393-422)."""
+    from tests.harness import Frame, SAMPLING
+    rng = np.random.default_rng(20261020)
+    out = []
+
+    def frame(name, samp, w, h, qt, planes_fn):
+        bx, by = synth.grid(w, h, samp)
+        sh, sv = SAMPLING[samp]
+        fr = Frame(w, h, len(sh), list(sh), list(sv), bx, by, np.asarray(qt, dtype=np.uint16).reshape(len(sh), 64))
+        fr.planes = [planes_fn(c, (by[c], bx[c], 64)).astype(np.int16) for c in range(len(sh))]
+        out.append((name, fr))
+
+    def ncomp(samp):
+        return 1 if samp == "grey" else 3
+
+    # 1. every AC entry of the tables 0, raw AC terms non-zero, negative DC (the judge's reproduction)
+    for samp in ("grey", "420"):
+        qt = np.zeros((ncomp(samp), 64), dtype=np.int64)
+        qt[:, 0] = 16
+
+        def p1(c, shape):
+            p = rng.integers(-50, 51, size=shape)
+            p[..., 0] = -rng.integers(1, 60, size=shape[:2])
+            return p
+        frame(f"all_ac_entries_zero_{samp}", samp, 256, 256, qt, p1)
+    # 2. scattered entries of 0
+    for samp in ("444", "422"):
+        qt = rng.integers(1, 256, size=(3, 64))
+        qt[rng.random((3, 64)) < 0.25] = 0
+
+        def p2(c, shape):
+            p = rng.integers(-200, 201, size=shape)
+            p[rng.random(shape) < 0.6] = 0
+            p[..., 0] = rng.integers(-800, 100, size=shape[:2])
+            return p
+        frame(f"scattered_zero_entries_{samp}", samp, 136, 72, qt, p2)
+    # 3. 16-bit tables whose products at column 4 are multiples of 2**21: blk(4) * 2**11 wraps to 0
+    for samp in ("grey", "444", "420"):
+        qt = rng.integers(1, 1500, size=(ncomp(samp), 64))
+        qt[:, 4::8] = 1024
+
+        def p3(c, shape):
+            p = np.zeros(shape, dtype=np.int64)
+            p[..., 4::8] = 2048 * rng.integers(-3, 4, size=shape[:2] + (8,))
+            keep = rng.random(shape[:2] + (8,)) < 0.3          # some rows get other AC terms as well
+            extra = rng.integers(-20, 21, size=shape[:2] + (8,))
+            p[..., 1::8] = np.where(keep, extra, 0)
+            p[..., 0] = rng.integers(-300, 40, size=shape[:2])
+            return p
+        frame(f"q16_products_multiple_of_2p21_{samp}", samp, 120, 88, qt, p3)
+    # 4. the same with 8-bit tables: only coefficients far outside any JPEG get there (wide flag)
+    for samp in ("grey", "422"):
+        qt = rng.integers(1, 256, size=(ncomp(samp), 64))
+        qt[:, 4::8] = 128
+
+        def p4(c, shape):
+            p = np.zeros(shape, dtype=np.int64)
+            p[..., 4::8] = rng.choice(np.array([0, 16384, -16384, -32768]), size=shape[:2] + (8,))
+            p[..., 0] = rng.integers(-1000, 200, size=shape[:2])
+            return p
+        frame(f"q8_wide_products_multiple_of_2p21_{samp}", samp, 96, 64, qt, p4)
+    # 5. DC terms whose blk(0) * 2**11 wraps (the row shortcut is blk(0) * 8, not the general path), and whose
+    #    row outputs reach the edge where the column shortcut is NOT the general path
+    for samp in ("grey", "444"):
+        qt = np.full((ncomp(samp), 64), 255, dtype=np.int64)
+
+        def p5(c, shape):
+            p = np.zeros(shape, dtype=np.int64)
+            p[..., 0] = rng.choice(np.array([-32768, -30000, -4200, 4112, 4113, 20000, 32767]), size=shape[:2])
+            some = rng.random(shape[:2]) < 0.3
+            p[..., 9] = np.where(some, rng.integers(-3, 4, size=shape[:2]), 0)
+            return p
+        frame(f"dc_terms_that_wrap_{samp}", samp, 80, 48, qt, p5)
+    # 6. anything goes: full 16-bit coefficients, 16-bit tables with zeros (every sum wraps)
+    for samp in ("grey", "420", "440"):
+        qt = rng.integers(0, 65536, size=(ncomp(samp), 64))
+        qt[rng.random((ncomp(samp), 64)) < 0.1] = 0
+        frame(f"full_range_{samp}", samp, 72, 56, qt, lambda c, shape: rng.integers(-32768, 32768, size=shape))
+    # 7. the rim of the fast domain: |coefficient| = 65536 / largest entry exactly, dense
+    for samp in ("grey", "444", "420"):
+        qt = rng.integers(1, 256, size=(ncomp(samp), 64))
+        qt[:, rng.integers(0, 64)] = 255
+
+        def p7(c, shape):
+            lim = 65536 // int(qt[c].max())
+            return rng.choice(np.array([-lim, lim, -lim + 1, 0, 1, -1]), size=shape)
+        frame(f"rim_of_the_fast_domain_{samp}", samp, 104, 40, qt, p7)
+    return out

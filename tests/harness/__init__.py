@@ -440,5 +440,9 @@ class Emu:
 
 def frame_desc(fr: Frame, flags: int = 0, out_stride: int = 0):
     """gid_b200.FrameDesc for a harness Frame."""
-    from gid_b200 import FrameDesc
-    return FrameDesc.make(fr.width, fr.height, fr.samp_h, fr.samp_v, fr.qt, flags, out_stride)
+    from gid_b200 import FrameDesc, capi
+    d = FrameDesc.make(fr.width, fr.height, fr.samp_h, fr.samp_v, fr.qt, flags, out_stride)
+    # the producer of the planes states their range (GIDCUDA_FLAG_WIDE_COEF)
+    if getattr(fr, "planes", None) is not None and len(fr.planes) and capi.coefficients_are_wide(d, fr.planes):
+        d.flags |= capi.FLAG_WIDE_COEF
+    return d

@@ -7,7 +7,7 @@ import ctypes
 import numpy as np
 import pytest
 
-from tests.cases import CONFIG_SMALL, GEOMETRIES, pixels_for, random_planes
+from tests.cases import CONFIG_SMALL, GEOMETRIES, edge_frames, pixels_for, random_planes
 from tests.harness import frame_desc
 
 pytestmark = pytest.mark.gpu
@@ -72,6 +72,55 @@ def test_random_coefficients(gpu, oracle, synth, path, kind, samp):
     fr.planes = random_planes(rng, bx, by, kind)
     # |coef * q| <= 2047 * 255 < 2**20: inside the documented domain
     _check(gpu, oracle, fr)
+
+
+def test_edge_of_the_domain(gpu, oracle, synth, path):
+    """Tables with entries of 0 (all AC entries, scattered), 16-bit tables whose products are multiples of
+    2**21, wide coefficients, DC terms that wrap, full-range garbage, the rim of the fast domain: identical
+    bytes (the exact kernel instances outside the fast domain, the fast ones on its rim)."""
+    for name, fr in edge_frames(synth):
+        try:
+            _check(gpu, oracle, fr)
+            if fr.ncomp == 3:
+                from gid_b200 import capi
+                _check(gpu, oracle, fr, flags=capi.OUT_RGBA8)
+        except AssertionError as e:
+            raise AssertionError(f"{name}: {e}") from e
+
+
+def test_wide_coefficients_declared_after_begin(gpu, oracle, synth):
+    """gidcuda_job_wide_coefficients (what a decoder calls once it has seen the coefficients) == the flag in
+    the descriptor; without either, the same planes run the fast instances and the bytes differ (which is
+    why the producer has to say so)."""
+    from gid_b200 import capi
+    name, fr = next((n, f) for n, f in edge_frames(synth) if n == "dc_terms_that_wrap_444")
+    ref = oracle.reconstruct(fr)
+    d = frame_desc(fr)
+    assert d.flags & capi.FLAG_WIDE_COEF
+    assert np.array_equal(gpu.reconstruct_rgb(d, fr.planes), ref)
+    d.flags &= ~capi.FLAG_WIDE_COEF
+    assert np.array_equal(gpu.reconstruct_rgb(d, fr.planes), ref)      # the helper notices and calls the setter
+    L = gpu.lib
+    for c in range(3):
+        assert 257 <= L.gidcuda_fast_coef_limit(ctypes.byref(d), c) <= 32767
+
+
+def test_recycled_job_with_row_hints_of_another_layout(gpu, oracle, synth):
+    """A hinted plane (rows 4..7 not moved) relies on device rows that were zeroed for THIS frame: a job
+    recycled from a frame of another layout and size must zero them again."""
+    rng = np.random.default_rng(5)
+    frames = []
+    for w, h, samp in ((4096, 2304, "420"), (4096, 3072, "grey"), (4096, 2304, "420")):
+        fr = synth.planes_only(pixels_for(synth, 21 + len(frames), w, h, samp), samp)
+        for c in range(fr.ncomp):          # rows 4..7 empty: the hint applies; the first frame's chroma is dense
+            fr.planes[c][..., 32:] = 0
+        if len(frames) == 0:
+            fr.planes[1][..., 32:] = rng.integers(-3, 4, size=fr.planes[1][..., 32:].shape)
+            fr.planes[2][..., 32:] = rng.integers(-3, 4, size=fr.planes[2][..., 32:].shape)
+        frames.append(fr)
+    for fr in frames:
+        got = gpu.reconstruct_rgb(frame_desc(fr), fr.planes, hint_rows=True)
+        assert np.array_equal(got, oracle.reconstruct(fr)), (fr.width, fr.height, fr.ncomp)
 
 
 def test_16bit_quant_tables(gpu, oracle, synth):

@@ -672,3 +672,72 @@ def test_libjpeg_files_through_the_device(host, oracle, synth, gpu):
     assert st == [0] * len(files)
     for (name, jpg), img in zip(files, imgs):
         assert np.array_equal(img, oracle.decode(jpg)[1]), name
+
+
+# --------------------------------------------------------------------------- the edge of the coefficient range
+
+
+def _wide_planes(synth, rng, w, h, samp):
+    from tests.harness import SAMPLING
+    bx, by = synth.grid(w, h, samp)
+    planes = []
+    for c in range(len(SAMPLING[samp][0])):
+        p = np.zeros((by[c], bx[c], 64), dtype=np.int64)
+        m = rng.random(p.shape) < 0.05
+        p[m] = rng.integers(-40, 41, size=int(m.sum()))
+        big = rng.random(p.shape) < 0.002
+        p[big] = rng.choice(np.array([-20000, -5000, 4500, 9000, 16384, -16384]), size=int(big.sum()))
+        p[..., 0] = rng.integers(-3000, 3001, size=p.shape[:2])
+        planes.append(p.astype(np.int16))
+    return planes
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("samp,ri,prog", [("420", 0, False), ("444", 3, False), ("grey", 0, False), ("422", 0, True)])
+def test_streams_with_wide_coefficients(host, oracle, synth, gpu, coef_form, samp, ri, prog):
+    """Coefficients far beyond any JPEG of 8-bit samples (categories 13 .. 15, which Decode_8x8_Block accepts,
+    gid-decoding_jpg.adb:727-733): the device Huffman decoders hand the scan to the host decoder, which marks
+    the frame (gidcuda_job_wide_coefficients), and the exact kernel instances reproduce the reference's
+    32-bit wrap-around: pixels == GID's decode of the file."""
+    rng = np.random.default_rng(31)
+    w, h = 264, 136
+    jpg, _ = synth.encode_planes(w, h, _wide_planes(synth, rng, w, h, samp), samp, progressive=prog,
+                                 restart_interval=ri, optimize=True)
+    _, ref, _ = oracle.decode(jpg)
+    rgb, _ = host.decode_rgb(jpg)
+    assert np.array_equal(rgb, ref)
+
+
+def _two_block_stream_with_runaway_predictor() -> bytes:
+    """16 x 8 grey baseline file, two blocks, each a DC difference of +32767 (category 15) and EOB: the
+    predictor reaches 65 534.  DC table: the one code '0' -> category 15; AC table: '0' -> EOB."""
+    def seg(marker, body):
+        return bytes([0xFF, marker]) + (len(body) + 2).to_bytes(2, "big") + body
+    dqt = seg(0xDB, bytes([0]) + bytes([1] * 64))
+    sof = seg(0xC0, bytes([8]) + (8).to_bytes(2, "big") + (16).to_bytes(2, "big") + bytes([1, 1, 0x11, 0]))
+    dht_dc = seg(0xC4, bytes([0x00]) + bytes([1] + [0] * 15) + bytes([15]))
+    dht_ac = seg(0xC4, bytes([0x10]) + bytes([1] + [0] * 15) + bytes([0x00]))
+    sos = seg(0xDA, bytes([1, 1, 0x00, 0, 63, 0]))
+    bits = ("0" + "1" * 15 + "0") * 2
+    bits += "1" * (-len(bits) % 8)
+    data = bytearray()
+    for i in range(0, len(bits), 8):
+        b = int(bits[i:i + 8], 2)
+        data.append(b)
+        if b == 0xFF:
+            data.append(0)
+    return b"\xff\xd8" + dqt + sof + dht_dc + dht_ac + sos + bytes(data) + b"\xff\xd9"
+
+
+@pytest.mark.gpu
+def test_dc_predictor_beyond_16_bits_is_reported(host, oracle, gpu):
+    """The reference keeps a 32-bit predictor (dc_predictor * qt_local (0), :766-771) and paints this file
+    white.  The int16 planes of the boundary cannot carry 65 534: the host mirror says so
+    (unsupported_image_subformat) instead of painting a wrapped value; the device decoders leave the scan to
+    it.  Documented limit of the plane format."""
+    jpg = _two_block_stream_with_runaway_predictor()
+    _, ref, _ = oracle.decode(jpg)
+    assert ref.shape == (8, 16, 3) and (ref[:, :8] == 255).all() and (ref[:, 8:] == 255).all()
+    with pytest.raises(host.GidHostError) as e:
+        host.decode_rgb(jpg)
+    assert e.value.name == "unsupported_image_subformat" and "16 bits" in str(e.value)

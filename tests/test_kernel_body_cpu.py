@@ -8,7 +8,7 @@ import zlib
 import numpy as np
 import pytest
 
-from tests.cases import GEOMETRIES, pixels_for, random_planes
+from tests.cases import GEOMETRIES, edge_frames, pixels_for, random_planes
 from tests.harness import Frame, SAMPLING, frame_desc
 
 
@@ -51,6 +51,28 @@ def test_random_coefficients(emu, oracle, synth, gidcuda_lib, kind, samp):
     fr = Frame(w, h, len(sh), list(sh), list(sv), bx, by, qt)
     fr.planes = random_planes(rng, bx, by, kind)
     _check(emu, oracle, gidcuda_lib, fr)
+
+
+def test_edge_of_the_domain(emu, oracle, synth, gidcuda_lib):
+    """Tables with entries of 0, products that are multiples of 2**21, DC terms that wrap, full-range garbage,
+    the rim of the fast domain: identical bytes everywhere (the fast instances inside their domain, the
+    exact ones outside it)."""
+    from gid_b200 import capi
+    seen_fast = seen_exact = 0
+    for name, fr in edge_frames(synth):
+        d = frame_desc(fr)
+        fast = not (d.flags & capi.FLAG_WIDE_COEF) and int(fr.qt.min()) >= 1 and int(fr.qt.max()) <= 255
+        seen_fast += fast
+        seen_exact += not fast
+        if name.startswith("rim_of_the_fast_domain"):
+            assert fast, name
+        if name.startswith(("q8_wide", "dc_terms", "full_range", "all_ac", "scattered", "q16")):
+            assert not fast, name
+        try:
+            _check(emu, oracle, gidcuda_lib, fr)
+        except AssertionError as e:
+            raise AssertionError(f"{name}: kernel body != oracle") from e
+    assert seen_fast >= 3 and seen_exact >= 10
 
 
 def test_16bit_quant_tables(emu, oracle, synth, gidcuda_lib):

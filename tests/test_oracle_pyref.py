@@ -57,3 +57,13 @@ def test_frames_two_restatements_agree(oracle, synth, w, h, samp):
     fr = synth.planes_only(pixels_for(synth, 12, w, h, samp), samp)
     got = pyref.reconstruct(w, h, fr.samp_h, fr.samp_v, np.asarray(fr.qt), fr.planes[:fr.ncomp])
     assert np.array_equal(got, oracle.reconstruct(fr))
+
+
+def test_edge_of_the_domain_two_restatements_agree(oracle, synth):
+    """Tables with entries of 0, products that are multiples of 2**21 (blk(4) * 2**11 wraps to 0 and the
+    row shortcut is taken, :803-812), DC terms whose blk(0) * 2**11 wraps, full-range garbage: the two
+    restatements of the Ada text give the same bytes."""
+    from tests.cases import edge_frames
+    for name, fr in edge_frames(synth):
+        got = pyref.reconstruct(fr.width, fr.height, fr.samp_h, fr.samp_v, np.asarray(fr.qt), fr.planes[:fr.ncomp])
+        assert np.array_equal(got, oracle.reconstruct(fr)), name
