@@ -34,7 +34,7 @@ EXPORTS = [
     "gidcuda_job_plane", "gidcuda_job_hint_rows", "gidcuda_fast_coef_limit", "gidcuda_job_wide_coefficients", "gidcuda_job_records", "gidcuda_job_records_commit", "gidcuda_job_records_commit_runs",
     "gidcuda_job_output", "gidcuda_job_scan", "gidcuda_host_is_pinned", "gidcuda_job_submit", "gidcuda_job_wait", "gidcuda_job_release",
     "gidcuda_plan_create", "gidcuda_plan_launch", "gidcuda_plan_launch_count", "gidcuda_plan_uses_tma",
-    "gidcuda_plan_destroy", "gidcuda_synchronize", "gidcuda_batch_create", "gidcuda_batch_run",
+    "gidcuda_plan_destroy", "gidcuda_synchronize", "gidcuda_batch_create", "gidcuda_batch_run", "gidcuda_batch_run_records",
     "gidcuda_batch_destroy", "gidcuda_host_alloc", "gidcuda_host_free",
 ]
 
@@ -149,6 +149,9 @@ def load_library() -> ctypes.CDLL:
     L.gidcuda_batch_create.argtypes = [i32p, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(vp)]
     L.gidcuda_batch_run.argtypes = [vp, ctypes.c_int32, ctypes.POINTER(FrameDesc), ctypes.POINTER(vp),
                                     ctypes.POINTER(vp), i32p, ctypes.POINTER(BatchStats)]
+    L.gidcuda_batch_run_records.argtypes = [vp, ctypes.c_int32, ctypes.POINTER(FrameDesc), ctypes.POINTER(vp),
+                                            ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(vp),
+                                            i32p, ctypes.POINTER(BatchStats)]
     L.gidcuda_batch_destroy.argtypes = [vp]
     L.gidcuda_host_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp)]
     L.gidcuda_host_free.argtypes = [vp]
@@ -356,6 +359,22 @@ class Batch:
         status = (ctypes.c_int32 * n)()
         stats = BatchStats()
         rc = self.lib.gidcuda_batch_run(self.h, n, arr, pl, px, status, ctypes.byref(stats))
+        if rc != GIDCUDA_OK:
+            raise GidCudaError(rc, (self.lib.gidcuda_last_error(None) or b"").decode())
+        return list(status), stats
+
+    def run_records(self, descs: Sequence[FrameDesc], first: Sequence[int], records: Sequence[int],
+                    counts: Sequence[int], pixels: Sequence[int]):
+        """first / records: 3*n host addresses (0 for absent), counts: 3*n record counts, pixels: n host addresses."""
+        n = len(descs)
+        arr = (FrameDesc * n)(*descs)
+        fa = (ctypes.c_void_p * (3 * n))(*[ctypes.c_void_p(int(p) if p else None) for p in first])
+        ra = (ctypes.c_void_p * (3 * n))(*[ctypes.c_void_p(int(p) if p else None) for p in records])
+        ca = (ctypes.c_size_t * (3 * n))(*[int(c) for c in counts])
+        px = (ctypes.c_void_p * n)(*[ctypes.c_void_p(int(p) if p else None) for p in pixels])
+        status = (ctypes.c_int32 * n)()
+        stats = BatchStats()
+        rc = self.lib.gidcuda_batch_run_records(self.h, n, arr, fa, ra, ca, px, status, ctypes.byref(stats))
         if rc != GIDCUDA_OK:
             raise GidCudaError(rc, (self.lib.gidcuda_last_error(None) or b"").decode())
         return list(status), stats

@@ -141,11 +141,15 @@ inline int make_geometry(std::string *err, const gidcuda_frame_desc *d, Geometry
     if (d->samp_h[0] == 1 && d->samp_v[0] == 1) g->layout = LAYOUT_444;
     else if (d->samp_h[0] == 2 && d->samp_v[0] == 1) g->layout = LAYOUT_422;
     else if (d->samp_h[0] == 2 && d->samp_v[0] == 2) g->layout = LAYOUT_420;
+    else if (d->samp_h[0] == 1 && d->samp_v[0] == 2) g->layout = LAYOUT_440;
+    else if (d->samp_h[0] == 4 && d->samp_v[0] == 1) g->layout = LAYOUT_411;
     else g->layout = LAYOUT_GENERIC;
   } else {
     g->layout = LAYOUT_GENERIC;
   }
-  g->ntiles = (uint32_t)(((size_t)g->mcux * g->mcuy + kTileMcusSetup - 1) / kTileMcusSetup);
+  g->ntiles = layout_linear(g->layout) || g->layout == LAYOUT_GENERIC
+                  ? (uint32_t)(((size_t)g->mcux * g->mcuy + kTileMcusSetup - 1) / kTileMcusSetup)
+                  : (uint32_t)((size_t)g->mcuy * ((g->mcux + kTileMcusSetup - 1) / kTileMcusSetup));
   return GIDCUDA_OK;
 }
 

@@ -98,7 +98,7 @@ class LaunchSet {
     tiles.clear();
     groups.clear();
     tma_groups = 0;
-    for (int lay = 0; lay < 4; lay++)
+    for (int lay = 0; lay < kFusedLayouts; lay++)
       for (int qa = 3; qa >= 0; qa--) {
         const int q = qa & 1;
         LaunchGroup g;
@@ -228,7 +228,7 @@ class LaunchSet {
   size_t upload_bytes = 0;
 
  private:
-  static constexpr int kMaxGroups = 16;  // 4 layouts x 2 table widths x 2 pixel sizes
+  static constexpr int kMaxGroups = 4 * kFusedLayouts;  // layouts x 2 table widths x 2 pixel sizes
   static constexpr uint32_t kCounterSlots = 4;
   uint32_t launch_seq_ = 0;
   uint32_t *d_counters_ = nullptr;
@@ -280,7 +280,7 @@ class LaunchSet {
       }
       return;
     }
-    const int V = g.layout == LAYOUT_420 ? 2 : 1;
+    const int H = layout_h(g.layout), V = layout_v(g.layout);
     for (int my = 0; my < g.mcuy; my++)
       for (int mx0 = 0; mx0 < g.mcux; mx0 += kTileMcus) {
         const uint32_t m0 = (uint32_t)my * (uint32_t)g.mcux + (uint32_t)mx0;
@@ -288,9 +288,9 @@ class LaunchSet {
         t.coord[0] = (uint32_t)(row0[1] + m0);
         t.coord[1] = (uint32_t)(row0[2] + m0);
         for (int sy = 0; sy < V; sy++)
-          for (int half = 0; half < 2; half++) {  // 32 consecutive luma blocks per item (mcu_item)
-            const uint64_t blk = row0[0] + (uint64_t)(my * V + sy) * (uint64_t)g.bx[0] + 2u * (uint64_t)mx0;
-            t.coord[2 + sy * 2 + half] = (uint32_t)(blk + 32u * (uint64_t)half);
+          for (int part = 0; part < H; part++) {  // 32 consecutive luma blocks per item (mcu_item)
+            const uint64_t blk = row0[0] + (uint64_t)(my * V + sy) * (uint64_t)g.bx[0] + (uint64_t)H * (uint64_t)mx0;
+            t.coord[2 + sy * H + part] = (uint32_t)(blk + 32u * (uint64_t)part);
           }
         tiles.push_back(t);
       }

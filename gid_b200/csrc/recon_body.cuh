@@ -21,10 +21,21 @@
 
 namespace gidk {
 
-// Sampling layouts with a dedicated fused kernel.  Anything else GID accepts
-// (integer up-factors, e.g. 4:4:0, 4:1:1) goes through the generic two-pass
+// Sampling layouts with a dedicated fused kernel: grey, and Y with 1x1 chroma for luma samplings
+// 1x1 (4:4:4), 2x1 (4:2:2), 2x2 (4:2:0), 1x2 (4:4:0) and 4x1 (4:1:1).  Anything else GID accepts
+// (integer up-factors, e.g. 4:1:0, or chroma that is not 1x1) goes through the generic two-pass
 // kernels in recon_kernels.cu.
-enum Layout : int { LAYOUT_GREY = 0, LAYOUT_444 = 1, LAYOUT_422 = 2, LAYOUT_420 = 3, LAYOUT_GENERIC = 4 };
+enum Layout : int {
+  LAYOUT_GREY = 0, LAYOUT_444 = 1, LAYOUT_422 = 2, LAYOUT_420 = 3, LAYOUT_440 = 4, LAYOUT_411 = 5,
+  LAYOUT_GENERIC = 6
+};
+constexpr int kFusedLayouts = 6;
+// luma sampling and items per tile (Cb, Cr, then H x V luma items; grey: one) of a fused layout
+GID_HD int layout_h(int layout) { return layout == LAYOUT_422 || layout == LAYOUT_420 ? 2 : (layout == LAYOUT_411 ? 4 : 1); }
+GID_HD int layout_v(int layout) { return layout == LAYOUT_420 || layout == LAYOUT_440 ? 2 : 1; }
+GID_HD int layout_items(int layout) { return layout == LAYOUT_GREY ? 1 : 2 + layout_h(layout) * layout_v(layout); }
+// grey and 4:4:4: one block per component per MCU, tiles are linear runs of MCUs that may wrap over MCU rows
+GID_HD bool layout_linear(int layout) { return layout == LAYOUT_GREY || layout == LAYOUT_444; }
 
 // Output pixel formats, = GIDCUDA_OUT_* of include/gidcuda.h
 enum OutFormat : int { OUT_RGB8 = 0, OUT_BGR8_BOTTOM_UP = 1, OUT_RGBA8 = 2 };
@@ -392,10 +403,18 @@ GID_HD void emit_rows(const FrameDev &f, const Scratch &sc, int x0, int y0, int 
         t[4 / H] = chroma_terms_packed<0>(co, cbc.y, crc.y); t[5 / H] = chroma_terms_packed<1>(co, cbc.y, crc.y);
         t[6 / H] = chroma_terms_packed<2>(co, cbc.y, crc.y); t[7 / H] = chroma_terms_packed<3>(co, cbc.y, crc.y);
       } else {
-        // block sx covers chroma columns 4*sx .. 4*sx+3, i.e. word sx of the row
-        const uint32_t wb = sx ? cbc.y : cbc.x, wr = sx ? crc.y : crc.x;
-        t[0] = chroma_terms_packed<0>(co, wb, wr); t[1] = chroma_terms_packed<1>(co, wb, wr);
-        t[2] = chroma_terms_packed<2>(co, wb, wr); t[3] = chroma_terms_packed<3>(co, wb, wr);
+        if (H == 2) {
+          // block sx covers chroma columns 4*sx .. 4*sx+3, i.e. word sx of the row
+          const uint32_t wb = sx ? cbc.y : cbc.x, wr = sx ? crc.y : crc.x;
+          t[0] = chroma_terms_packed<0>(co, wb, wr); t[1] = chroma_terms_packed<1>(co, wb, wr);
+          constexpr int k2 = H == 2 ? 2 : 0, k3 = H == 2 ? 3 : 0;  // (only H = 2 runs this; keeps the index in range elsewhere)
+          t[k2] = chroma_terms_packed<2>(co, wb, wr); t[k3] = chroma_terms_packed<3>(co, wb, wr);
+        } else {
+          // H = 4: block sx covers chroma columns 2*sx, 2*sx+1: half-word (sx & 1) of word (sx >> 1)
+          const uint32_t sh = (uint32_t)(sx & 1) * 16u;
+          const uint32_t wb = ((sx & 2) ? cbc.y : cbc.x) >> sh, wr = ((sx & 2) ? crc.y : crc.x) >> sh;
+          t[0] = chroma_terms_packed<0>(co, wb, wr); t[1] = chroma_terms_packed<1>(co, wb, wr);
+        }
       }
     }
 #pragma unroll
@@ -497,10 +516,11 @@ GID_HD void warp_sync() {
 //
 // Which block a lane owns:
 //   grey, 4:4:4 (one block per component per MCU): lane t <-> MCU t of the tile, all items.
-//   4:2:2 / 4:2:0: chroma items as above (lane t <-> MCU t = (mx, my)); the luma items walk the
-//   tile's luma block rows 32 CONSECUTIVE blocks at a time -- item 2 + 2*sy + half holds blocks
-//   32*half .. 32*half + 31 of block row sy -- so lane t owns luma block j = 32*half + t, which
-//   belongs to MCU j / 2 and is its left (j even) or right block.  Neighbouring lanes therefore
+//   4:4:0 (H = 1, V = 2): the same for every item; luma item 2 + sy is block row sy of the MCUs.
+//   4:2:2 / 4:2:0 / 4:1:1 (H = 2 or 4): chroma items as above (lane t <-> MCU t = (mx, my)); the luma items
+//   walk the tile's luma block rows 32 CONSECUTIVE blocks at a time -- item 2 + H*sy + part holds blocks
+//   32*part .. 32*part + 31 of block row sy -- so lane t owns luma block j = 32*part + t, which
+//   belongs to MCU j / H and is its block number j % H from the left.  Neighbouring lanes therefore
 //   write neighbouring 24-byte runs of the same pixel rows in the same store instructions, and
 //   every 32-byte sector of the output is completed at once.  (With lane <-> MCU for luma the two
 //   halves of each 48-byte run were written a whole block of arithmetic apart: partially written
@@ -519,15 +539,15 @@ GID_HD void mcu_item(int it, bool active, const FrameDev &f, const uint32_t *qw,
       sy = it - 2;
       byi = my * V + sy;
     } else {
-      const int half = (it - 2) & 1;
-      sy = (it - 2) >> 1;
-      const int j = 32 * half + lane;       // luma block of this lane inside the tile's block row
-      bxi = 2 * (mx - lane) + j;            // mx - lane = first MCU of the tile (tiles stay in one MCU row)
+      const int part = (it - 2) % H;        // which 32 of the block row's 32 * H luma blocks
+      sy = (it - 2) / H;
+      const int j = 32 * part + lane;       // luma block of this lane inside the tile's block row
+      bxi = H * (mx - lane) + j;            // mx - lane = first MCU of the tile (tiles stay in one MCU row)
       byi = my * V + sy;
       active = bxi < f.bx[0];
-      sx = lane & 1;
-      se.cb = sc.cb + ((j >> 1) - lane);    // scratch column of MCU j / 2
-      se.cr = sc.cr + ((j >> 1) - lane);
+      sx = lane & (H - 1);                  // = j % H (32 is a multiple of H)
+      se.cb = sc.cb + ((j / H) - lane);     // scratch column of MCU j / H
+      se.cr = sc.cr + ((j / H) - lane);
       if (it == 2) warp_sync();             // every lane's chroma samples are in the scratch
     }
   }

@@ -71,6 +71,8 @@ template <> struct LayoutInfo<LAYOUT_GREY> { static constexpr int H = 1, V = 1, 
 template <> struct LayoutInfo<LAYOUT_444> { static constexpr int H = 1, V = 1, NI = 3; static constexpr bool linear = true; };
 template <> struct LayoutInfo<LAYOUT_422> { static constexpr int H = 2, V = 1, NI = 4; static constexpr bool linear = false; };
 template <> struct LayoutInfo<LAYOUT_420> { static constexpr int H = 2, V = 2, NI = 6; static constexpr bool linear = false; };
+template <> struct LayoutInfo<LAYOUT_440> { static constexpr int H = 1, V = 2, NI = 4; static constexpr bool linear = false; };
+template <> struct LayoutInfo<LAYOUT_411> { static constexpr int H = 4, V = 1, NI = 6; static constexpr bool linear = false; };
 
 // ---- PTX wrappers -------------------------------------------------------------
 
@@ -535,7 +537,9 @@ cudaError_t init_kernels() {
   if ((e = set_attr_all<LAYOUT_GREY>()) != cudaSuccess) return e;
   if ((e = set_attr_all<LAYOUT_444>()) != cudaSuccess) return e;
   if ((e = set_attr_all<LAYOUT_422>()) != cudaSuccess) return e;
-  return set_attr_all<LAYOUT_420>();
+  if ((e = set_attr_all<LAYOUT_420>()) != cudaSuccess) return e;
+  if ((e = set_attr_all<LAYOUT_440>()) != cudaSuccess) return e;
+  return set_attr_all<LAYOUT_411>();
 }
 
 cudaError_t launch_fused(Layout layout, bool q8, bool rgba, bool use_tma, const CUtensorMap *map2,
@@ -548,6 +552,8 @@ cudaError_t launch_fused(Layout layout, bool q8, bool rgba, bool use_tma, const 
     case LAYOUT_444: return launch_q<LAYOUT_444>(GIDK_ARGS);
     case LAYOUT_422: return launch_q<LAYOUT_422>(GIDK_ARGS);
     case LAYOUT_420: return launch_q<LAYOUT_420>(GIDK_ARGS);
+    case LAYOUT_440: return launch_q<LAYOUT_440>(GIDK_ARGS);
+    case LAYOUT_411: return launch_q<LAYOUT_411>(GIDK_ARGS);
     default: return cudaErrorInvalidValue;
   }
 #undef GIDK_ARGS

@@ -298,13 +298,22 @@ typedef struct gidcuda_batch_stats {
  * no inter-GPU communication (images carry no cross-GPU data). */
 int gidcuda_batch_create(const int32_t *devices, int32_t ndevices, int32_t chunk_images,
                          gidcuda_batch **batch);
-/* planes[i*3 + c]: HOST pointer to plane c of image i (any memory; pinned is
- * faster); pixels[i]: HOST output buffer of gidcuda_output_geometry bytes.
- * status[i] (optional) receives the per-image status: a failed image is
- * reported and skipped, the others are unaffected. */
+/* planes[i*3 + c]: HOST pointer to plane c of image i; pixels[i]: HOST output buffer of
+ * gidcuda_output_geometry bytes.  Buffers in pinned memory (gidcuda_host_alloc, or registered with the
+ * CUDA runtime) are read and written by the copy engines directly -- no host-side copy at all; pageable
+ * buffers go through the worker's pinned staging buffers (one host copy each way).  Three chunks of
+ * chunk_images images are in flight per device.  status[i] (optional) receives the per-image status: a
+ * failed image is reported and skipped, the others are unaffected; every image gets a status. */
 int gidcuda_batch_run(gidcuda_batch *batch, int32_t n, const gidcuda_frame_desc *descs,
                       const int16_t *const *planes, uint8_t *const *pixels, int32_t *status,
                       gidcuda_batch_stats *stats);
+/* The same with the components handed over as RECORDS (see gidcuda_job_records: what an entropy decoder
+ * emits, a few bytes per block instead of 128): first[i*3 + c] = the component's nblocks + 1 offsets,
+ * records[i*3 + c] = its records, counts[i*3 + c] = how many (= first[nblocks]).  The link carries the
+ * records; a kernel rebuilds the planes on the device. */
+int gidcuda_batch_run_records(gidcuda_batch *batch, int32_t n, const gidcuda_frame_desc *descs,
+                              const uint32_t *const *first, const uint32_t *const *records, const size_t *counts,
+                              uint8_t *const *pixels, int32_t *status, gidcuda_batch_stats *stats);
 int gidcuda_batch_destroy(gidcuda_batch *batch);
 
 /* Pinned host memory for callers that want the fast copy path. */

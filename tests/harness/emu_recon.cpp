@@ -72,8 +72,8 @@ extern "C" int emu_reconstruct(const gidcuda_frame_desc *desc, const int16_t *co
   // chroma samples another lane left in the warp's scratch).
   LdgSource src{&f};
   u32x2 s_plane[3][8][kTileMcusSetup];
-  const bool linear = g.layout == LAYOUT_GREY || g.layout == LAYOUT_444;
-  const int ni = g.layout == LAYOUT_GREY ? 1 : (g.layout == LAYOUT_444 ? 3 : (g.layout == LAYOUT_422 ? 4 : 6));
+  const bool linear = layout_linear(g.layout);
+  const int ni = layout_items(g.layout);
   const bool rgba = f.out_format == OUT_RGBA8;
   const uint32_t nmcu = (uint32_t)(f.mcux * f.mcuy);
   std::vector<uint32_t> tile_m0;
@@ -83,7 +83,7 @@ extern "C" int emu_reconstruct(const gidcuda_frame_desc *desc, const int16_t *co
     for (int my = 0; my < f.mcuy; my++)
       for (int mx0 = 0; mx0 < f.mcux; mx0 += kTileMcusSetup) tile_m0.push_back((uint32_t)(my * f.mcux + mx0));
   }
-  if (tile_m0.size() != g.ntiles && linear) return GIDCUDA_ERR_BAD_ARGUMENT;
+  if (tile_m0.size() != g.ntiles) return GIDCUDA_ERR_BAD_ARGUMENT;
   for (uint32_t m0 : tile_m0)
     for (int it = 0; it < ni; it++)
       for (int t = 0; t < kTileMcusSetup; t++) {
@@ -111,6 +111,8 @@ extern "C" int emu_reconstruct(const gidcuda_frame_desc *desc, const int16_t *co
           case LAYOUT_GREY: EMU_RUN(1, 1, true); break;
           case LAYOUT_444: EMU_RUN(1, 1, false); break;
           case LAYOUT_422: EMU_RUN(2, 1, false); break;
+          case LAYOUT_440: EMU_RUN(1, 2, false); break;
+          case LAYOUT_411: EMU_RUN(4, 1, false); break;
           default: EMU_RUN(2, 2, false); break;
         }
 #undef EMU_RUN

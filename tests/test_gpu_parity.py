@@ -363,6 +363,79 @@ def test_batch_driver(oracle, synth, gidcuda_lib):
         assert np.array_equal(got, oracle.reconstruct(fr)), i
 
 
+def test_batch_driver_every_device_pinned_and_records(oracle, synth, gidcuda_lib):
+    """The in-process batch driver on EVERY visible device: per-GPU worker, work queue and three chunks in
+    flight; images_per_device is non-zero on each device.  Buffers in pinned memory are read and written by
+    the copy engines directly (no staging copy); the records variant moves what an entropy decoder emits."""
+    from gid_b200 import capi
+    n_dev = gidcuda_lib.gidcuda_device_count()
+    geos = [(640, 360, "420"), (512, 256, "444"), (400, 300, "grey"), (320, 200, "422")]
+    distinct = [synth.planes_only(pixels_for(synth, 60 + i, *g[:2], g[2]), g[2]) for i, g in enumerate(geos)]
+    refs = [oracle.reconstruct(fr) for fr in distinct]
+    n = 24 * n_dev
+    frames = [distinct[i % len(distinct)] for i in range(n)]
+    descs = [frame_desc(fr) for fr in frames]
+    ctx = capi.GidCuda(0)
+    geo = [ctx.output_geometry(d) for d in descs]
+    ctx.close()
+    allocs = []
+
+    def pinned_copy(a):
+        buf, addr = capi.pinned_empty(max(a.nbytes, 16))
+        allocs.append(addr)
+        buf[:a.nbytes] = np.frombuffer(a.tobytes(), dtype=np.uint8)
+        return addr
+
+    def check(outs, status, stats):
+        assert all(st == 0 for st in status) and stats.images_failed == 0
+        assert sum(stats.images_per_device[:n_dev]) == n
+        assert all(stats.images_per_device[k] > 0 for k in range(n_dev)), list(stats.images_per_device[:n_dev])
+        for i, fr in enumerate(frames):
+            stride = geo[i][0]
+            got = outs[i][:fr.height * stride].reshape(fr.height, stride)[:, :3 * fr.width].reshape(fr.height, fr.width, 3)
+            assert np.array_equal(got, refs[i % len(distinct)]), i
+
+    batch = capi.Batch(list(range(n_dev)), chunk_images=2)
+    try:
+        # dense planes, pinned in and out
+        src = [[pinned_copy(fr.planes[c]) for c in range(fr.ncomp)] for fr in distinct]
+        planes, pixels, outs = [], [], []
+        for i, fr in enumerate(frames):
+            planes += [src[i % len(distinct)][c] if c < fr.ncomp else 0 for c in range(3)]
+            o, addr = capi.pinned_empty(geo[i][1])
+            allocs.append(addr)
+            o[:] = 0
+            outs.append(o)
+            pixels.append(addr)
+        status, stats = batch.run(descs, planes, pixels)
+        check(outs, status, stats)
+        assert stats.d2h_bytes == sum(g[1] for g in geo)
+        # records, pageable in, pinned out
+        recs = []
+        for fr in distinct:
+            per = []
+            for c in range(fr.ncomp):
+                first, rec = capi.records_from_plane(fr.planes[c], fr.samp_h[c], fr.samp_v[c])
+                per.append((np.ascontiguousarray(first, dtype=np.uint32), np.ascontiguousarray(rec, dtype=np.uint32)))
+            recs.append(per)
+        fa, ra, ca = [], [], []
+        for i, fr in enumerate(frames):
+            per = recs[i % len(distinct)]
+            for c in range(3):
+                fa.append(per[c][0].ctypes.data if c < fr.ncomp else 0)
+                ra.append(per[c][1].ctypes.data if c < fr.ncomp else 0)
+                ca.append(len(per[c][1]) if c < fr.ncomp else 0)
+        for o in outs:
+            o[:] = 0
+        status, stats2 = batch.run_records(descs, fa, ra, ca, pixels)
+        check(outs, status, stats2)
+        assert stats2.h2d_bytes < stats.h2d_bytes / 2     # the link carries the records, not the planes
+    finally:
+        batch.close()
+        for addr in allocs:
+            capi.pinned_free(addr)
+
+
 FULL_SIZE = [
     ("cfg1", 512, 512, "420", False, 0),
     ("cfg2", 4096, 4096, "444", False, 0),
