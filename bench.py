@@ -528,7 +528,7 @@ def run_ours(args) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_regions(use: int, min_total_ms: float, max_regions: int = 40) -> list[float]:
+    def timed_regions(use: int, min_total_ms: float, max_regions: int = 400) -> list[float]:
         """Regions of EXACTLY args.steps steps each, every one bracketed by barrier + synchronize, CUDA events
         on the launching stream, max over ranks; repeated until the regions add up to min_total_ms of device
         time (a single region of a 40 us kernel at --steps 20 is under a millisecond: too short a sample)."""
@@ -628,7 +628,7 @@ def run_ours(args) -> None:
         e2e_steps(args.steps)
         torch.cuda.synchronize()
         e2e_regions.append(sharding.max_over_ranks(time.perf_counter() - t0, dev))
-        if len(e2e_regions) >= 40 or (len(e2e_regions) >= 3 and sum(e2e_regions) >= 1.0):
+        if len(e2e_regions) >= 400 or (len(e2e_regions) >= 3 and sum(e2e_regions) >= 1.0):
             break
     e2e_s = float(np.median(e2e_regions))
     e2e_value = sharding.whole_job_rate((w * h * e2e_frames / 1e6) * args.steps, world, e2e_s)

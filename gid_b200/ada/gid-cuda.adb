@@ -91,6 +91,17 @@ package body GID.CUDA is
     Check (gidcuda_job_hint_rows (j, C.int (comp), C.int (rows_used)), Null_Context);
   end Hint_Rows;
 
+  function Fast_Coef_Limit (desc : Frame_Desc; comp : Natural) return Natural is
+    d : aliased constant Frame_Desc := desc;
+  begin
+    return Natural (gidcuda_fast_coef_limit (d'Access, C.int (comp)));
+  end Fast_Coef_Limit;
+
+  procedure Wide_Coefficients (j : Job) is
+  begin
+    Check (gidcuda_job_wide_coefficients (j), Null_Context);
+  end Wide_Coefficients;
+
   procedure Records
     (j : Job; comp : Natural;
      first, records : out System.Address; capacity, nblocks : out Natural)

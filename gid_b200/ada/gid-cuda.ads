@@ -47,6 +47,7 @@ private package GID.CUDA is
   Out_RGB8           : constant := 0;
   Out_BGR8_Bottom_Up : constant := 1;
   Flag_Packed_Rows   : constant := 16#100#;
+  Flag_Wide_Coef     : constant := 16#800#;   --  see Fast_Coef_Limit
 
   --  = struct gidcuda_frame_desc
   type Frame_Desc is record
@@ -75,6 +76,15 @@ private package GID.CUDA is
 
   --  Promise that rows >= rows_used of every block of the plane are zero (1 .. 8).
   procedure Hint_Rows (j : Job; comp : Natural; rows_used : Positive);
+
+  --  Range of the fast kernel instances (include/gidcuda.h, GIDCUDA_FLAG_WIDE_COEF): the largest
+  --  coefficient magnitude of component comp for which the decisions the kernels take on raw
+  --  coefficients are those Inverse_DCT_8x8_Block takes on de-quantised ones (:803-812, :858-862).
+  --  An entropy decoder that has stored a larger one -- Get_VLC accepts up to 15 bits, :727-733; no
+  --  JPEG of 8-bit samples holds one -- calls Wide_Coefficients before Submit: the frame then runs the
+  --  instances that reproduce the reference for every 16-bit coefficient.
+  function  Fast_Coef_Limit (desc : Frame_Desc; comp : Natural) return Natural;
+  procedure Wide_Coefficients (j : Job);
 
   --  Sparse alternative to Plane (include/gidcuda.h, "sparse coefficient input"):
   --  one 32-bit record per NON-ZERO coefficient,
@@ -169,6 +179,12 @@ private
 
   function gidcuda_job_hint_rows (j : Job; comp, rows_used : C.int) return C.int;
   pragma Import (C, gidcuda_job_hint_rows, "gidcuda_job_hint_rows");
+
+  function gidcuda_fast_coef_limit
+    (desc : access constant Frame_Desc; comp : C.int) return Interfaces.Integer_32;
+  pragma Import (C, gidcuda_fast_coef_limit, "gidcuda_fast_coef_limit");
+  function gidcuda_job_wide_coefficients (j : Job) return C.int;
+  pragma Import (C, gidcuda_job_wide_coefficients, "gidcuda_job_wide_coefficients");
 
   function gidcuda_job_records
     (j : Job; comp : C.int; first, records : access System.Address;

@@ -28,6 +28,10 @@
     plane      : array (Component) of Plane_Info;
     comp_index : array (Component) of Natural := (others => 0);  --  Y -> 0, Cb -> 1, Cr -> 2
     last_row   : array (Component) of Natural := (others => 0);  --  last block row a coefficient was stored in
+    --  largest magnitude stored per component (the DC term with all the bits of dc_predictor, :766-771),
+    --  held against GID.CUDA.Fast_Coef_Limit before Submit (see Reconstruct_On_Device_And_Output)
+    max_mag    : array (Component) of Natural := (others => 0);
+    coef_limit : array (Component) of Natural := (others => 0);
 
     --  Called once from Read_SOS, after the MCU geometry is known (:1974) and before
     --  the first scan is decoded.  Replaces Create_Image_Array (:1857-1883) too: the
@@ -59,6 +63,7 @@
       GID.CUDA.Job_Begin (cuda_ctx, desc, cuda_job);
       for c in Component loop
         if image.JPEG_stuff.compo_set (c) then
+          coef_limit (c) := GID.CUDA.Fast_Coef_Limit (desc, comp_index (c));
           plane (c).base :=
             GID.CUDA.Plane (cuda_job, comp_index (c), plane (c).blocks_x, plane (c).blocks_y);
         end if;
@@ -86,6 +91,11 @@
         for cell'Address use Coefficient_Address (c, bx, by, nat);
         pragma Import (Ada, cell);
       begin
+        max_mag (c) := Natural'Max (max_mag (c), abs v);
+        if abs v > 32767 then
+          --  (a DC predictor driven out of 16 bits by a crafted stream: the int16 planes cannot carry it)
+          raise unsupported_image_subformat with "JPEG: a coefficient of the stream exceeds 16 bits";
+        end if;
         cell := Interfaces.Integer_16 (v);  --  planes were zeroed by Job_Begin
         last_row (c) := Natural'Max (last_row (c), nat / 8);
       end Store;
@@ -174,6 +184,10 @@
       for c in Component loop
         if image.JPEG_stuff.compo_set (c) then
           GID.CUDA.Hint_Rows (cuda_job, comp_index (c), last_row (c) + 1);
+          if max_mag (c) > coef_limit (c) then
+            --  outside the range of the fast kernel instances: the exact ones take the frame
+            GID.CUDA.Wide_Coefficients (cuda_job);
+          end if;
         end if;
       end loop;
       GID.CUDA.Submit (cuda_job);
