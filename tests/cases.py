@@ -3,14 +3,15 @@ from __future__ import annotations
 
 import numpy as np
 
-# (width, height, sampling) -- covers the four fused layouts, the generic path
-# (4:4:0 = h1v2, 4:1:1 = h4v1), partial MCUs on both edges and the tiny sizes
+# (width, height, sampling) -- covers the six fused layouts (4:4:0 = h1v2 and 4:1:1 = h4v1 among them),
+# the generic path (4:1:0 = h4v2), partial MCUs on both edges and the tiny sizes
 # GID accepts (subsampled components need >= 3 samples).
 GEOMETRIES = [
     (512, 512, "420"), (256, 256, "444"), (640, 480, "422"), (300, 200, "grey"),
     (17, 9, "420"), (239, 134, "422"), (1, 1, "444"), (7, 3, "grey"), (7, 3, "444"),
     (100, 60, "440"), (100, 60, "411"), (333, 217, "420"), (1919 // 4, 1079 // 4, "420"),
     (8, 8, "444"), (16, 16, "420"), (5, 5, "420"), (1030, 9, "grey"), (9, 1030, "444"),
+    (100, 60, "410"), (1100, 20, "411"), (40, 530, "440"), (1030, 40, "440"), (1290, 9, "411"),
 ]
 
 # scaled-down versions of the five BASELINE.json configs (the full sizes are

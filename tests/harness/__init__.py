@@ -294,6 +294,7 @@ SAMPLING = {
     "420": ([2, 1, 1], [2, 1, 1]),
     "440": ([1, 1, 1], [2, 1, 1]),   # h1v2
     "411": ([4, 1, 1], [1, 1, 1]),
+    "410": ([4, 1, 1], [2, 1, 1]),   # h4v2: no fused kernel, the generic two-pass path
     "grey": ([1], [1]),
 }
 

@@ -231,7 +231,7 @@ def test_plan_device_resident_batch(gpu, oracle, synth):
     frames = [synth.planes_only(pixels_for(synth, 20 + i, w, h, s), s)
               for i, (w, h, s) in enumerate([(320, 200, "420"), (97, 61, "420"), (128, 64, "444"),
                                              (200, 120, "grey"), (64, 64, "422"), (90, 50, "440"),
-                                             (640, 360, "420")])]
+                                             (640, 360, "420"), (130, 40, "411"), (96, 64, "410")])]
     dev = torch.device("cuda:0")
     descs, d_planes, d_pixels, keep = [], [], [], []
     for fr in frames:
@@ -250,8 +250,8 @@ def test_plan_device_resident_batch(gpu, oracle, synth):
         d_pixels.append(out.data_ptr())
     torch.cuda.synchronize()
     plan = gpu.plan_create(descs, d_planes, d_pixels)
-    assert gpu.plan_launch_count(plan) == 4 + 2  # grey, 444, 422, 420 fused + generic (2 passes)
-    assert gpu.plan_uses_tma(plan) == 4          # torch allocations are 512-byte aligned
+    assert gpu.plan_launch_count(plan) == 6 + 2  # grey, 444, 422, 420, 440, 411 fused + generic 4:1:0 (2 passes)
+    assert gpu.plan_uses_tma(plan) == 6          # torch allocations are 512-byte aligned
     refs = [oracle.reconstruct(fr) for fr in frames]
     # the same plan launched several times back to back: the kernels hand out tiles through
     # launch-wide counters that the last warp resets, so every launch must be complete
