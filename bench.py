@@ -471,7 +471,8 @@ def run_ours(args) -> None:
     alg_bytes_frame = frames[0].algorithmic_bytes()
     ring = max(2, min(4, int(2.5e9 // max(1, alg_bytes_frame * per_step))))
     ring -= ring % 2  # a multiple of the number of launch streams
-    descs_one = [frame_desc(f) for f in frames]
+    rot_flag = {0: 0, 90: capi.FLAG_ROTATE_90, 180: capi.FLAG_ROTATE_180, 270: capi.FLAG_ROTATE_270}[args.rotate]
+    descs_one = [frame_desc(f, rot_flag) for f in frames]
     stride, nbytes = ctx.output_geometry(descs_one[0])
     keep, plans = [], []
     for r in range(ring):
@@ -670,7 +671,7 @@ def run_ours(args) -> None:
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": workload_config(args.workload, world),
-            "method": {"launch_streams": nstreams, "programmatic_dependent_launch": bool(args.pdl), "host_numa": numa,
+            "method": {"rotate": args.rotate, "launch_streams": nstreams, "programmatic_dependent_launch": bool(args.pdl), "host_numa": numa,
                        "l2": f"inputs larger than L2: ring of {ring} step-batches of {alg / 1e6:.0f} MB each",
                        "timing": "CUDA events on the launching stream around EXACTLY --steps launches, barrier + synchronize "
                                  "on both sides, max over ranks; regions repeated until >= 50 ms of device time; the median "
@@ -732,6 +733,8 @@ def main() -> None:
     ap.add_argument("--e2e-depth", type=int, default=3, help="jobs in flight in the end-to-end leg")
     ap.add_argument("--streams", type=int, default=1, choices=[1, 2, 4],
                     help="launch streams for the device-resident leg (default 1: the kernel's own figure)")
+    ap.add_argument("--rotate", type=int, default=0, choices=[0, 90, 180, 270],
+                    help="apply a display orientation while writing the pixels (GIDCUDA_FLAG_ROTATE_*; not the default workload)")
     ap.add_argument("--pdl", type=int, default=1, choices=[0, 1],
                     help="plan launches as programmatic dependent launches (library default 1); 0 = every launch "
                          "waits for its predecessor to leave the device")

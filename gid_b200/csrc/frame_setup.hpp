@@ -133,8 +133,11 @@ inline int make_geometry(std::string *err, const gidcuda_frame_desc *d, Geometry
     g->stride = round_up(packed, 16);
   }
   g->pixel_bytes = g->stride * (size_t)out_h;
-  if (g->rotate != 0) {
-    g->layout = LAYOUT_GENERIC;  // the per-pixel pass applies the orientation
+  if (g->rotate == 1 || g->rotate == 3 || (g->rotate == 2 && !g->q8)) {
+    // quarter turns: the per-pixel pass applies the orientation (runs along a row of the rotated image come
+    // from blocks of DIFFERENT MCU rows, which the fused kernels' tiles -- 32 MCUs of one row -- do not hold);
+    // so do half turns outside the fast domain (the rotating instances exist for the fast kernels only)
+    g->layout = LAYOUT_GENERIC;
   } else if (d->ncomp == 1) {
     g->layout = LAYOUT_GREY;
   } else if (d->samp_h[1] == 1 && d->samp_v[1] == 1 && d->samp_h[2] == 1 && d->samp_v[2] == 1) {
@@ -174,12 +177,20 @@ inline void fill_frame_dev(const gidcuda_frame_desc *d, const Geometry &g, const
   f->height = d->height;
   f->mcux = g.mcux;
   f->mcuy = g.mcuy;
-  f->out_format = g.out_format | (g.rotate << 8);  // (rotated frames only reach the generic kernels)
+  const bool fused = g.layout != LAYOUT_GENERIC;
+  // quarter turns only reach the generic kernels, which read the rotation here; the fused kernels do the
+  // half turn themselves (FRAME_ROT180)
+  f->out_format = fused ? g.out_format : (g.out_format | (g.rotate << 8));
   f->tile_base = tile_base;
   f->q8 = g.q8 ? 1 : 0;
   f->flags = 0;
-  if (g.stride % 8 == 0 && (reinterpret_cast<uintptr_t>(pixels) & 7u) == 0) f->flags |= FRAME_ALIGNED8;
-  if (g.stride % 16 == 0 && (reinterpret_cast<uintptr_t>(pixels) & 15u) == 0) f->flags |= FRAME_ALIGNED16;
+  const bool rot180 = fused && g.rotate == 2;
+  if (rot180) f->flags |= FRAME_ROT180;
+  // (mirrored runs of whole blocks start at column W - x0 - 8: the same boundaries only when W % 8 == 0)
+  if (g.stride % 8 == 0 && (reinterpret_cast<uintptr_t>(pixels) & 7u) == 0 && (!rot180 || d->width % 8 == 0))
+    f->flags |= FRAME_ALIGNED8;
+  if (g.stride % 16 == 0 && (reinterpret_cast<uintptr_t>(pixels) & 15u) == 0 && (!rot180 || d->width % 4 == 0))
+    f->flags |= FRAME_ALIGNED16;
 }
 
 }  // namespace gidk

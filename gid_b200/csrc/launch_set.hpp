@@ -30,6 +30,7 @@ struct LaunchGroup {
   Layout layout;
   bool q8;
   bool rgba;
+  bool rot;   // FRAME_ROT180 frames: kernel instances of their own
   bool tma;
   uint32_t first_frame, nframes, first_tile, ntiles;
   CUtensorMap map2;
@@ -99,18 +100,19 @@ class LaunchSet {
     groups.clear();
     tma_groups = 0;
     for (int lay = 0; lay < kFusedLayouts; lay++)
-      for (int qa = 3; qa >= 0; qa--) {
+      for (int qa = 7; qa >= 0; qa--) {
         const int q = qa & 1;
         LaunchGroup g;
         memset(&g, 0, sizeof g);
         g.layout = (Layout)lay;
         g.q8 = q == 1;
         g.rgba = (qa & 2) == 0;
+        g.rot = (qa & 4) == 0;
         g.first_frame = (uint32_t)frames.size();
         g.first_tile = (uint32_t)tiles.size();
         uintptr_t lo = ~(uintptr_t)0, hi = 0;
         for (const FrameItem &it : items) {
-          if ((int)it.geo.layout != lay || it.geo.q8 != g.q8 || (it.geo.out_format == (int)OUT_RGBA8) != g.rgba) continue;
+          if ((int)it.geo.layout != lay || it.geo.q8 != g.q8 || (it.geo.out_format == (int)OUT_RGBA8) != g.rgba || (it.geo.rotate == 2) != g.rot) continue;
           for (int c = 0; c < it.geo.ncomp; c++) {
             const uintptr_t p = reinterpret_cast<uintptr_t>(it.planes[c]);
             if (p < lo) lo = p;
@@ -121,13 +123,13 @@ class LaunchSet {
         const uintptr_t base = lo & ~(uintptr_t)255;
         bool aligned = true;
         for (const FrameItem &it : items) {
-          if ((int)it.geo.layout != lay || it.geo.q8 != g.q8 || (it.geo.out_format == (int)OUT_RGBA8) != g.rgba) continue;
+          if ((int)it.geo.layout != lay || it.geo.q8 != g.q8 || (it.geo.out_format == (int)OUT_RGBA8) != g.rgba || (it.geo.rotate == 2) != g.rot) continue;
           for (int c = 0; c < it.geo.ncomp; c++)
             if ((reinterpret_cast<uintptr_t>(it.planes[c]) - base) % 256 != 0) aligned = false;
         }
         g.tma = aligned && !tma_disabled_by_env() && encode_maps(&g, base, hi);
         for (const FrameItem &it : items) {
-          if ((int)it.geo.layout != lay || it.geo.q8 != g.q8 || (it.geo.out_format == (int)OUT_RGBA8) != g.rgba) continue;
+          if ((int)it.geo.layout != lay || it.geo.q8 != g.q8 || (it.geo.out_format == (int)OUT_RGBA8) != g.rgba || (it.geo.rotate == 2) != g.rot) continue;
           FrameDev f;
           fill_frame_dev(it.desc, it.geo, it.planes, it.pixels, nullptr, 0, &f);
           const uint32_t fi = (uint32_t)frames.size() - g.first_frame;
@@ -214,7 +216,7 @@ class LaunchSet {
     uint32_t gi = 0;
     const uint32_t slot = launch_seq_++ % kCounterSlots;
     for (const LaunchGroup &g : groups) {
-      if ((e = launch_fused(g.layout, g.q8, g.rgba, g.tma, &g.map2, d_frames_ + g.first_frame,
+      if ((e = launch_fused(g.layout, g.q8, g.rgba, g.rot, g.tma, &g.map2, d_frames_ + g.first_frame,
                             d_tiles_ + g.first_tile, g.ntiles, d_counters_ + 2 * (gi * kCounterSlots + slot), num_sms,
                             pdl, s)) != cudaSuccess)
         return e;
@@ -228,7 +230,7 @@ class LaunchSet {
   size_t upload_bytes = 0;
 
  private:
-  static constexpr int kMaxGroups = 4 * kFusedLayouts;  // layouts x 2 table widths x 2 pixel sizes
+  static constexpr int kMaxGroups = 8 * kFusedLayouts;  // layouts x 2 table widths x 2 pixel sizes x rotated or not
   static constexpr uint32_t kCounterSlots = 4;
   uint32_t launch_seq_ = 0;
   uint32_t *d_counters_ = nullptr;

@@ -44,6 +44,10 @@ enum OutFormat : int { OUT_RGB8 = 0, OUT_BGR8_BOTTOM_UP = 1, OUT_RGBA8 = 2 };
 enum FrameFlags : uint32_t {
   FRAME_ALIGNED8 = 1u,   // pixel base and stride are multiples of 8: rows of a block go out as 3 x 8 bytes
   FRAME_ALIGNED16 = 2u,  // ... multiples of 16: RGBA rows of a block go out as 2 x 16 bytes
+  // GIDCUDA_FLAG_ROTATE_180 in the fused kernels: pixel (x, r) lands at column W - 1 - x, row H - 1 - r
+  // (test/to_bmp.adb:104-122).  The alignment flags above then also promise W % 8 == 0 (W % 4 for RGBA), so
+  // that the mirrored runs of whole blocks start on the same boundaries.
+  FRAME_ROT180 = 4u,
 };
 
 // Per-frame descriptor in device memory (one per image of a launch).
@@ -290,15 +294,16 @@ static __host__ __device__ __noinline__
 #else
 inline
 #endif
-void store_row8_bytes(uint8_t *dst, int n, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4,
+void store_row8_bytes(uint8_t *dst, int n, int skip, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4,
                       uint32_t w5) {
+  // bytes skip .. skip + n - 1 of the 24 (skip > 0: a mirrored row of a block cut by the image's edge)
   const uint32_t w[6] = {w0, w1, w2, w3, w4, w5};
-  for (int i = 0; i < n; i++) dst[i] = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
+  for (int i = 0; i < n; i++) dst[i] = (uint8_t)(w[(i + skip) >> 2] >> (8 * ((i + skip) & 3)));
 }
 
 // One row of 8 pixels (24 packed bytes in w0..w5) at dst.  nbytes == 24 and an
 // 8-byte aligned dst (`fast`): the row leaves as three 8-byte stores.
-GID_HD void store_row8(uint8_t *dst, bool fast, int nbytes, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3,
+GID_HD void store_row8(uint8_t *dst, bool fast, int nbytes, int skip, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3,
                        uint32_t w4, uint32_t w5) {
   if (fast) {
     u32x2 *d2 = reinterpret_cast<u32x2 *>(dst);
@@ -307,7 +312,7 @@ GID_HD void store_row8(uint8_t *dst, bool fast, int nbytes, uint32_t w0, uint32_
     v.x = w2; v.y = w3; d2[1] = v;
     v.x = w4; v.y = w5; d2[2] = v;
   } else {
-    store_row8_bytes(dst, nbytes, w0, w1, w2, w3, w4, w5);
+    store_row8_bytes(dst, nbytes, skip, w0, w1, w2, w3, w4, w5);
   }
 }
 
@@ -317,13 +322,13 @@ static __host__ __device__ __noinline__
 #else
 inline
 #endif
-void store_row8_rgba_words(uint8_t *dst, int npix, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4,
+void store_row8_rgba_words(uint8_t *dst, int npix, int skip, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4,
                            uint32_t w5, uint32_t w6, uint32_t w7) {
   const uint32_t w[8] = {w0, w1, w2, w3, w4, w5, w6, w7};
   for (int i = 0; i < npix; i++)
-    for (int k = 0; k < 4; k++) dst[4 * i + k] = (uint8_t)(w[i] >> (8 * k));
+    for (int k = 0; k < 4; k++) dst[4 * i + k] = (uint8_t)(w[i + skip] >> (8 * k));
 }
-GID_HD void store_row8_rgba(uint8_t *dst, bool fast, int npix, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3,
+GID_HD void store_row8_rgba(uint8_t *dst, bool fast, int npix, int skip, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3,
                             uint32_t w4, uint32_t w5, uint32_t w6, uint32_t w7) {
   if (fast) {
     u32x4 *d4 = reinterpret_cast<u32x4 *>(dst);
@@ -331,7 +336,7 @@ GID_HD void store_row8_rgba(uint8_t *dst, bool fast, int npix, uint32_t w0, uint
     v.x = w0; v.y = w1; v.z = w2; v.w = w3; d4[0] = v;
     v.x = w4; v.y = w5; v.z = w6; v.w = w7; d4[1] = v;
   } else {
-    store_row8_rgba_words(dst, npix, w0, w1, w2, w3, w4, w5, w6, w7);
+    store_row8_rgba_words(dst, npix, skip, w0, w1, w2, w3, w4, w5, w6, w7);
   }
 }
 
@@ -362,7 +367,12 @@ GID_HD int byte_of(uint32_t w) { return (int)prmt(w, 0u, 0x4440u + K); }
 //   RGBA   4 bytes per pixel (a separate instance, so that the 3-byte loop stays lean)
 //   FAST   the whole block lies inside the image (8 pixels x 8 rows) and its rows are aligned:
 //          no per-row bounds checks, no call to the byte-wise store in the loop
-template <int H, int V, bool GREY, bool RGBA, bool FAST>
+//   REV    FRAME_ROT180: the run of a block row is written mirrored (pixel x0 + k at column W - 1 - x0 - k),
+//          rows bottom to top.  The sample words are byte-reversed as they are read, so that the arithmetic
+//          and the packing below produce the mirrored run as it is; a separate instance, so that frames
+//          that are not rotated run the code they always ran.
+GID_HD uint32_t brev4(uint32_t w) { return prmt(w, 0u, 0x0123u); }
+template <int H, int V, bool GREY, bool RGBA, bool FAST, bool REV = false>
 GID_HD void emit_rows(const FrameDev &f, const Scratch &sc, int x0, int y0, int sx, int sy) {
   constexpr bool rgba = RGBA;
 #if defined(GIDK_EXTRACT_ADD_ALL)
@@ -379,8 +389,11 @@ GID_HD void emit_rows(const FrameDev &f, const Scratch &sc, int x0, int y0, int 
   const bool fast = FAST || ((f.flags & (rgba ? FRAME_ALIGNED16 : FRAME_ALIGNED8)) != 0 && npix == 8);
   const bool bottom_up = f.out_format == OUT_BGR8_BOTTOM_UP;
   const ColourOrder co = colour_order(bottom_up);
-  uint8_t *dst = row_ptr(f, x0, y0);
-  const long long step = bottom_up ? -(long long)f.stride : (long long)f.stride;
+  // REV: the run starts where its LAST pixel lands; of a mirrored run cut by the edge the leading
+  // 8 - npix pixels of the 8 computed are not written
+  const int skip_pix = REV ? 8 - npix : 0;
+  uint8_t *dst = REV ? row_ptr(f, f.width - x0 - npix, f.height - 1 - y0) : row_ptr(f, x0, y0);
+  const long long step = (bottom_up != REV) ? -(long long)f.stride : (long long)f.stride;
   const int rows_left = FAST ? 8 : f.height - y0;  // >= 1
   const int crow0 = sy * (8 / V);                   // first row inside the chroma block
   // (The byte selectors of the extract-add are literals: the compiler re-materialises them into
@@ -397,6 +410,12 @@ GID_HD void emit_rows(const FrameDev &f, const Scratch &sc, int x0, int y0, int 
     if (!GREY) {
       cbc = sc.cb[(crow0 + i) * sc.stride];
       crc = sc.cr[(crow0 + i) * sc.stride];
+      if (REV) {  // columns 7 .. 0: the block's word sx (H = 2) / half-word (H = 4) is found mirrored below
+        const u32x2 b = cbc, r = crc;
+        cbc.x = brev4(b.y); cbc.y = brev4(b.x);
+        crc.x = brev4(r.y); crc.y = brev4(r.x);
+      }
+      const int sxm = REV ? H - 1 - sx : sx;
       if (H == 1) {
         t[0] = chroma_terms_packed<0>(co, cbc.x, crc.x); t[1] = chroma_terms_packed<1>(co, cbc.x, crc.x);
         t[2] = chroma_terms_packed<2>(co, cbc.x, crc.x); t[3] = chroma_terms_packed<3>(co, cbc.x, crc.x);
@@ -405,14 +424,14 @@ GID_HD void emit_rows(const FrameDev &f, const Scratch &sc, int x0, int y0, int 
       } else {
         if (H == 2) {
           // block sx covers chroma columns 4*sx .. 4*sx+3, i.e. word sx of the row
-          const uint32_t wb = sx ? cbc.y : cbc.x, wr = sx ? crc.y : crc.x;
+          const uint32_t wb = sxm ? cbc.y : cbc.x, wr = sxm ? crc.y : crc.x;
           t[0] = chroma_terms_packed<0>(co, wb, wr); t[1] = chroma_terms_packed<1>(co, wb, wr);
           constexpr int k2 = H == 2 ? 2 : 0, k3 = H == 2 ? 3 : 0;  // (only H = 2 runs this; keeps the index in range elsewhere)
           t[k2] = chroma_terms_packed<2>(co, wb, wr); t[k3] = chroma_terms_packed<3>(co, wb, wr);
         } else {
           // H = 4: block sx covers chroma columns 2*sx, 2*sx+1: half-word (sx & 1) of word (sx >> 1)
-          const uint32_t sh = (uint32_t)(sx & 1) * 16u;
-          const uint32_t wb = ((sx & 2) ? cbc.y : cbc.x) >> sh, wr = ((sx & 2) ? crc.y : crc.x) >> sh;
+          const uint32_t sh = (uint32_t)(sxm & 1) * 16u;
+          const uint32_t wb = ((sxm & 2) ? cbc.y : cbc.x) >> sh, wr = ((sxm & 2) ? crc.y : crc.x) >> sh;
           t[0] = chroma_terms_packed<0>(co, wb, wr); t[1] = chroma_terms_packed<1>(co, wb, wr);
         }
       }
@@ -420,14 +439,18 @@ GID_HD void emit_rows(const FrameDev &f, const Scratch &sc, int x0, int y0, int 
 #pragma unroll
     for (int ry = 0; ry < V; ry++) {
       if (!FAST && V > 1 && i * V + ry >= rows_left) break;
-      const u32x2 yv = sc.y[(i * V + ry) * sc.stride];
+      u32x2 yv = sc.y[(i * V + ry) * sc.stride];
+      if (REV) {
+        const u32x2 y = yv;
+        yv.x = brev4(y.y); yv.y = brev4(y.x);
+      }
       if (GREY && rgba) {
-        store_row8_rgba(dst, fast, npix, prmt(yv.x, 255u, 0x4000u), prmt(yv.x, 255u, 0x4111u), prmt(yv.x, 255u, 0x4222u),
+        store_row8_rgba(dst, fast, npix, skip_pix, prmt(yv.x, 255u, 0x4000u), prmt(yv.x, 255u, 0x4111u), prmt(yv.x, 255u, 0x4222u),
                         prmt(yv.x, 255u, 0x4333u), prmt(yv.y, 255u, 0x4000u), prmt(yv.y, 255u, 0x4111u),
                         prmt(yv.y, 255u, 0x4222u), prmt(yv.y, 255u, 0x4333u));
       } else if (GREY) {
         // R = G = B = Y (:1036-1038)
-        store_row8(dst, fast, nbytes, prmt(yv.x, 0u, 0x1000u), prmt(yv.x, 0u, 0x2211u), prmt(yv.x, 0u, 0x3332u),
+        store_row8(dst, fast, nbytes, 3 * skip_pix, prmt(yv.x, 0u, 0x1000u), prmt(yv.x, 0u, 0x2211u), prmt(yv.x, 0u, 0x3332u),
                    prmt(yv.y, 0u, 0x1000u), prmt(yv.y, 0u, 0x2211u), prmt(yv.y, 0u, 0x3332u));
       } else {
         int c0[8], c1[8], c2[8];
@@ -455,12 +478,12 @@ GID_HD void emit_rows(const FrameDev &f, const Scratch &sc, int x0, int y0, int 
           }
         }
         if (rgba)
-          store_row8_rgba(dst, fast, npix, pack_sat4(c0[0], c1[0], c2[0], 255), pack_sat4(c0[1], c1[1], c2[1], 255),
+          store_row8_rgba(dst, fast, npix, skip_pix, pack_sat4(c0[0], c1[0], c2[0], 255), pack_sat4(c0[1], c1[1], c2[1], 255),
                           pack_sat4(c0[2], c1[2], c2[2], 255), pack_sat4(c0[3], c1[3], c2[3], 255),
                           pack_sat4(c0[4], c1[4], c2[4], 255), pack_sat4(c0[5], c1[5], c2[5], 255),
                           pack_sat4(c0[6], c1[6], c2[6], 255), pack_sat4(c0[7], c1[7], c2[7], 255));
         else
-          store_row8(dst, fast, nbytes, pack_sat4(c0[0], c1[0], c2[0], c0[1]), pack_sat4(c1[1], c2[1], c0[2], c1[2]),
+          store_row8(dst, fast, nbytes, 3 * skip_pix, pack_sat4(c0[0], c1[0], c2[0], c0[1]), pack_sat4(c1[1], c2[1], c0[2], c1[2]),
                      pack_sat4(c2[2], c0[3], c1[3], c2[3]), pack_sat4(c0[4], c1[4], c2[4], c0[5]),
                      pack_sat4(c1[5], c2[5], c0[6], c1[6]), pack_sat4(c2[6], c0[7], c1[7], c2[7]));
       }
@@ -486,9 +509,16 @@ void emit_rows_edge(const FrameDev *f, u32x2 *cb, u32x2 *cr, u32x2 *y, int strid
   emit_rows<H, V, GREY, RGBA, false>(*f, sc, x0, y0, sx, sy);
 }
 
-template <int H, int V, bool GREY, bool RGBA>
+template <int H, int V, bool GREY, bool RGBA, bool ROT>
 GID_HD void emit_block_rows(const FrameDev &f, const Scratch &sc, int x0, int y0, int sx, int sy) {
   if (x0 >= f.width) return;
+  if (ROT) {
+    // FRAME_ROT180 frames run kernel instances of their own: a second copy of the row emitter inside the
+    // ordinary instances cost frames that are not rotated 6 % (measured on 4:2:0; the kernels are bound by
+    // instruction fetch, tools/icache_bench.cu)
+    emit_rows<H, V, GREY, RGBA, false, true>(f, sc, x0, y0, sx, sy);
+    return;
+  }
   // The split pays where registers are plentiful (grey: +1.7 %).  The colour kernels sit at the
   // 128-register limit: there the call made two values of the tile loop spill and the second
   // copy of the loop cost instruction-cache misses (-5 % on 4:2:0, profiles/r01s), so they keep
@@ -526,7 +556,7 @@ GID_HD void warp_sync() {
 //   halves of each 48-byte run were written a whole block of arithmetic apart: partially written
 //   sectors were evicted and re-fetched, +38 % DRAM reads and +24 % writes on 4:2:0, ncu.)
 //   The chroma samples of MCU j / 2 were left in the scratch by lane j / 2.
-template <int H, int V, bool GREY, bool Q8, bool RGBA, class Src>
+template <int H, int V, bool GREY, bool Q8, bool RGBA, bool ROT, class Src>
 GID_HD void mcu_item(int it, bool active, const FrameDev &f, const uint32_t *qw, Src &src, const Scratch &sc,
                      int lane, int mx, int my) {
   int comp = 0, sx = 0, sy = 0;
@@ -574,17 +604,17 @@ GID_HD void mcu_item(int it, bool active, const FrameDev &f, const uint32_t *qw,
   if (Q8) dequant_idct_sparse<true, kLo3>(active, raw, qw + 32 * comp, dst, sc.stride);
   else dequant_idct_exact(active, raw, qw + 32 * comp, dst, sc.stride);
   if (comp == 0) {
-    if (active) emit_block_rows<H, V, GREY, RGBA>(f, se, bxi * 8, byi * 8, sx, sy);
+    if (active) emit_block_rows<H, V, GREY, RGBA, ROT>(f, se, bxi * 8, byi * 8, sx, sy);
     src.release();
   }
 }
 
-template <int H, int V, bool GREY, bool Q8, bool RGBA, class Src>
+template <int H, int V, bool GREY, bool Q8, bool RGBA, bool ROT, class Src>
 GID_HD void mcu_run(bool active, const FrameDev &f, const uint32_t *qw /* [3][32] */, Src &src,
                     const Scratch &sc, int lane, int mx, int my) {
   constexpr int NI = GREY ? 1 : 2 + H * V;
 #pragma unroll 1
-  for (int it = 0; it < NI; it++) mcu_item<H, V, GREY, Q8, RGBA>(it, active, f, qw, src, sc, lane, mx, my);
+  for (int it = 0; it < NI; it++) mcu_item<H, V, GREY, Q8, RGBA, ROT>(it, active, f, qw, src, sc, lane, mx, my);
 }
 
 }  // namespace gidk

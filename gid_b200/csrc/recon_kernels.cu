@@ -274,11 +274,11 @@ __device__ __forceinline__ Scratch make_scratch(uint8_t *base, uint32_t lane, bo
   return sc;
 }
 
-template <int LAYOUT, bool Q8, bool RGBA, class Src>
+template <int LAYOUT, bool Q8, bool RGBA, bool ROT, class Src>
 __device__ __forceinline__ void run_mcu(bool active, const FrameDev &f, Src &src, const Scratch &sc, int lane, int mx,
                                         int my) {
   using LI = LayoutInfo<LAYOUT>;
-  mcu_run<LI::H, LI::V, LAYOUT == LAYOUT_GREY, Q8, RGBA>(active, f, &f.qw[0][0], src, sc, lane, mx, my);
+  mcu_run<LI::H, LI::V, LAYOUT == LAYOUT_GREY, Q8, RGBA, ROT>(active, f, &f.qw[0][0], src, sc, lane, mx, my);
 }
 
 // MCU (mx, my) of lane t in a tile starting at m0, or false when the lane has
@@ -305,7 +305,7 @@ __device__ __forceinline__ void cache_frame(uint8_t *dst, const FrameDev *src, u
   __syncwarp();
 }
 
-template <int LAYOUT, bool Q8, bool RGBA, int WPC>
+template <int LAYOUT, bool Q8, bool RGBA, int WPC, bool ROT = false>
 __global__ void __launch_bounds__(Shape<WPC>::kThreads, Shape<WPC>::kCtasPerSm)
 recon_tma_kernel(const __grid_constant__ CUtensorMap map2, const FrameDev *__restrict__ frames, const TileDesc *__restrict__ tiles, uint32_t ntiles,
                  uint32_t *__restrict__ counters) {
@@ -357,7 +357,7 @@ recon_tma_kernel(const __grid_constant__ CUtensorMap map2, const FrameDev *__res
     }
     int mx, my;
     const bool active = tile_mcu<LAYOUT>(f, this_m0, lane, mx, my);
-    run_mcu<LAYOUT, Q8, RGBA>(active, f, src, scratch, (int)lane, mx, my);
+    run_mcu<LAYOUT, Q8, RGBA, ROT>(active, f, src, scratch, (int)lane, mx, my);
   }
   src.claims.finish();
   // ... and this launch does not complete before its predecessor has (stream order as seen from
@@ -367,7 +367,7 @@ recon_tma_kernel(const __grid_constant__ CUtensorMap map2, const FrameDev *__res
 
 constexpr int kLdgWarps = 4;
 
-template <int LAYOUT, bool Q8, bool RGBA>
+template <int LAYOUT, bool Q8, bool RGBA, bool ROT = false>
 __global__ void __launch_bounds__(kLdgWarps * 32)
 recon_ldg_kernel(const FrameDev *__restrict__ frames, const TileDesc *__restrict__ tiles, uint32_t ntiles) {
   __shared__ __align__(16) uint8_t s_frame[kLdgWarps][kFrameBytes];
@@ -382,7 +382,7 @@ recon_ldg_kernel(const FrameDev *__restrict__ frames, const TileDesc *__restrict
   int mx, my;
   const bool active = tile_mcu<LAYOUT>(f, m0, lane, mx, my);
   LdgSource src{&f};
-  run_mcu<LAYOUT, Q8, RGBA>(active, f, src, make_scratch(s_scratch[warp], lane, true), (int)lane, mx, my);
+  run_mcu<LAYOUT, Q8, RGBA, ROT>(active, f, src, make_scratch(s_scratch[warp], lane, true), (int)lane, mx, my);
 }
 
 // ---- generic path -----------------------------------------------------------
@@ -428,48 +428,72 @@ generic_idct_kernel(const FrameDev *__restrict__ frame, int ncomp) {
   }
 }
 
-// Pass 2: one thread per pixel.  Pixel (x, y) reads sample (x / ux_c, y / uy_c)
-// of component c (replication, gid-decoding_jpg.adb:974-1008).
-__global__ void __launch_bounds__(256)
+// Pass 2: one thread per pixel, 32 x 32 pixels per CTA.  Pixel (x, y) reads sample (x / ux_c, y / uy_c)
+// of component c (replication, gid-decoding_jpg.adb:974-1008).  Quarter turns: the tile is transposed
+// through shared memory, so that the threads of a warp write neighbouring pixels of a row of the ROTATED
+// image (a row of the frame is a column there: written as it is read, every pixel would be a store of
+// its own sector).
+__global__ void __launch_bounds__(1024)
 generic_color_kernel(const FrameDev *__restrict__ frame, int ncomp, int hmax, int vmax) {
+  __shared__ uint32_t tile[32][33];
   const FrameDev &f = *frame;
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y;
-  if (x >= f.width || y >= f.height) return;
-  int s[3] = {0, 0, 0};
-  for (int c = 0; c < ncomp; c++) {
-    const int ux = hmax / f.samp_h[c], uy = vmax / f.samp_v[c];
-    s[c] = f.samples[c][(size_t)(y / uy) * ((size_t)f.bx[c] * 8) + (size_t)(x / ux)];
-  }
-  int r, g, b;
-  if (ncomp == 3) {
-    const ChromaTerms t = chroma_terms(s[1], s[2]);
-    r = clip255(s[0] + t.r);
-    g = clip255(s[0] + t.g);
-    b = clip255(s[0] + t.b);
-  } else {
-    r = g = b = s[0];
-  }
   const int fmt = f.out_format & 0xFF, rot = (f.out_format >> 8) & 3;
+  const bool quarter = (rot & 1) != 0;
+  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+  int x = x0 + (int)threadIdx.x, y = y0 + (int)threadIdx.y;
+  uint32_t px = 0;
+  if (x < f.width && y < f.height) {
+    int s[3] = {0, 0, 0};
+    for (int c = 0; c < ncomp; c++) {
+      const int ux = hmax / f.samp_h[c], uy = vmax / f.samp_v[c];
+      s[c] = f.samples[c][(size_t)(y / uy) * ((size_t)f.bx[c] * 8) + (size_t)(x / ux)];
+    }
+    int r, g, b;
+    if (ncomp == 3) {
+      const ChromaTerms t = chroma_terms(s[1], s[2]);
+      r = clip255(s[0] + t.r);
+      g = clip255(s[0] + t.g);
+      b = clip255(s[0] + t.b);
+    } else {
+      r = g = b = s[0];
+    }
+    if (fmt == OUT_BGR8_BOTTOM_UP) { const int t = r; r = b; b = t; }
+    px = (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16) | 0xFF000000u;
+  }
+  if (quarter) {  // this thread now writes pixel (x0 + threadIdx.y, y0 + threadIdx.x)
+    tile[threadIdx.y][threadIdx.x] = px;
+    __syncthreads();
+    px = tile[threadIdx.x][threadIdx.y];
+    x = x0 + (int)threadIdx.y;
+    y = y0 + (int)threadIdx.x;
+  }
+  if (x >= f.width || y >= f.height) return;
   // display orientation (GIDCUDA_FLAG_ROTATE_*, = Set_X_Y of test/to_bmp.adb:104-122): column and
   // top-down row of the pixel in the output image, whose height is out_h
   int ox = x, oy = y, out_h = f.height;
   if (rot == 1) { ox = y; oy = f.width - 1 - x; out_h = f.width; }
   else if (rot == 2) { ox = f.width - 1 - x; oy = f.height - 1 - y; }
   else if (rot == 3) { ox = f.height - 1 - y; oy = x; out_h = f.width; }
-  if (fmt == OUT_BGR8_BOTTOM_UP) {
-    oy = out_h - 1 - oy;
-    const int t = r; r = b; b = t;
+  if (fmt == OUT_BGR8_BOTTOM_UP) oy = out_h - 1 - oy;
+  if (fmt == OUT_RGBA8) {
+    uint8_t *dst = f.pixels + (size_t)oy * f.stride + (size_t)ox * 4;
+    if ((reinterpret_cast<uintptr_t>(dst) & 3u) == 0) {
+      *reinterpret_cast<uint32_t *>(dst) = px;
+    } else {  // a caller-chosen stride that is not a multiple of 4
+      dst[0] = (uint8_t)px;
+      dst[1] = (uint8_t)(px >> 8);
+      dst[2] = (uint8_t)(px >> 16);
+      dst[3] = 255;
+    }
+  } else {
+    uint8_t *dst = f.pixels + (size_t)oy * f.stride + (size_t)ox * 3;
+    dst[0] = (uint8_t)px;
+    dst[1] = (uint8_t)(px >> 8);
+    dst[2] = (uint8_t)(px >> 16);
   }
-  const bool rgba = fmt == OUT_RGBA8;
-  uint8_t *dst = f.pixels + (size_t)oy * f.stride + (size_t)ox * (rgba ? 4 : 3);
-  dst[0] = (uint8_t)r;
-  dst[1] = (uint8_t)g;
-  dst[2] = (uint8_t)b;
-  if (rgba) dst[3] = 255;
 }
 
-template <int LAYOUT, bool Q8, bool RGBA, int WPC>
+template <int LAYOUT, bool Q8, bool RGBA, int WPC, bool ROT = false>
 cudaError_t launch_shape(const CUtensorMap *map2, const FrameDev *d_frames,
                          const TileDesc *d_tiles, uint32_t ntiles, uint32_t *d_counters, int num_sms,
                          bool pdl, cudaStream_t stream) {
@@ -486,7 +510,7 @@ cudaError_t launch_shape(const CUtensorMap *map2, const FrameDev *d_frames,
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, recon_tma_kernel<LAYOUT, Q8, RGBA, WPC>, *map2, d_frames, d_tiles, ntiles, d_counters);
+  return cudaLaunchKernelEx(&cfg, recon_tma_kernel<LAYOUT, Q8, RGBA, WPC, ROT>, *map2, d_frames, d_tiles, ntiles, d_counters);
 }
 
 template <int LAYOUT, bool Q8, bool RGBA>
@@ -503,11 +527,26 @@ cudaError_t launch_one(bool use_tma, const CUtensorMap *map2, const FrameDev *d_
   return cudaGetLastError();
 }
 
+// FRAME_ROT180 frames: instances of their own (fast domain, wide shape) -- see emit_block_rows
+template <int LAYOUT, bool RGBA>
+cudaError_t launch_rot(bool use_tma, const CUtensorMap *map2, const FrameDev *d_frames, const TileDesc *d_tiles,
+                       uint32_t ntiles, uint32_t *d_counters, int num_sms, bool pdl, cudaStream_t stream) {
+  if (use_tma)
+    return launch_shape<LAYOUT, true, RGBA, kWideWarps, true>(map2, d_frames, d_tiles, ntiles, d_counters, num_sms, pdl, stream);
+  recon_ldg_kernel<LAYOUT, true, RGBA, true><<<(ntiles + kLdgWarps - 1) / kLdgWarps, kLdgWarps * 32, 0, stream>>>(
+      d_frames, d_tiles, ntiles);
+  return cudaGetLastError();
+}
+
 template <int LAYOUT>
-cudaError_t launch_q(bool q8, bool rgba, bool use_tma, const CUtensorMap *map2,
+cudaError_t launch_q(bool q8, bool rgba, bool rot, bool use_tma, const CUtensorMap *map2,
                      const FrameDev *d_frames, const TileDesc *d_tiles, uint32_t ntiles, uint32_t *d_counters,
                      int num_sms, bool pdl, cudaStream_t stream) {
 #define GIDK_ARGS use_tma, map2, d_frames, d_tiles, ntiles, d_counters, num_sms, pdl, stream
+  if (rot) {
+    if (!q8) return cudaErrorInvalidValue;  // (frame_setup.hpp sends those frames to the generic kernels)
+    return rgba ? launch_rot<LAYOUT, true>(GIDK_ARGS) : launch_rot<LAYOUT, false>(GIDK_ARGS);
+  }
   if (q8) return rgba ? launch_one<LAYOUT, true, true>(GIDK_ARGS) : launch_one<LAYOUT, true, false>(GIDK_ARGS);
   return rgba ? launch_one<LAYOUT, false, true>(GIDK_ARGS) : launch_one<LAYOUT, false, false>(GIDK_ARGS);
 #undef GIDK_ARGS
@@ -518,6 +557,11 @@ cudaError_t set_attr() {
   cudaError_t e = cudaFuncSetAttribute(recon_tma_kernel<LAYOUT, Q8, RGBA, kWideWarps>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<kWideWarps>::kBytes);
   if (e != cudaSuccess) return e;
+  if (Q8) {
+    e = cudaFuncSetAttribute(recon_tma_kernel<LAYOUT, true, RGBA, kWideWarps, true>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<kWideWarps>::kBytes);
+    if (e != cudaSuccess) return e;
+  }
   return cudaFuncSetAttribute(recon_tma_kernel<LAYOUT, Q8, RGBA, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               SmemLayout<4>::kBytes);
 }
@@ -542,11 +586,11 @@ cudaError_t init_kernels() {
   return set_attr_all<LAYOUT_411>();
 }
 
-cudaError_t launch_fused(Layout layout, bool q8, bool rgba, bool use_tma, const CUtensorMap *map2,
+cudaError_t launch_fused(Layout layout, bool q8, bool rgba, bool rot180, bool use_tma, const CUtensorMap *map2,
                          const FrameDev *d_frames, const TileDesc *d_tiles, uint32_t ntiles,
                          uint32_t *d_counters, int num_sms, bool pdl, cudaStream_t stream) {
   if (ntiles == 0) return cudaSuccess;
-#define GIDK_ARGS q8, rgba, use_tma, map2, d_frames, d_tiles, ntiles, d_counters, num_sms, pdl, stream
+#define GIDK_ARGS q8, rgba, rot180, use_tma, map2, d_frames, d_tiles, ntiles, d_counters, num_sms, pdl, stream
   switch (layout) {
     case LAYOUT_GREY: return launch_q<LAYOUT_GREY>(GIDK_ARGS);
     case LAYOUT_444: return launch_q<LAYOUT_444>(GIDK_ARGS);
@@ -573,8 +617,8 @@ cudaError_t launch_generic(const FrameDev &h, const FrameDev *d_frame, cudaStrea
   else generic_idct_kernel<false><<<grid1, 128, 0, stream>>>(d_frame, ncomp);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  dim3 grid2((unsigned)((h.width + 255) / 256), (unsigned)h.height);
-  generic_color_kernel<<<grid2, 256, 0, stream>>>(d_frame, ncomp, hmax, vmax);
+  dim3 grid2((unsigned)((h.width + 31) / 32), (unsigned)((h.height + 31) / 32));
+  generic_color_kernel<<<grid2, dim3(32, 32), 0, stream>>>(d_frame, ncomp, hmax, vmax);
   return cudaGetLastError();
 }
 

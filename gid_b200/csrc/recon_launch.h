@@ -35,10 +35,11 @@ static_assert(sizeof(TileDesc) == 32, "TileDesc is 32 bytes");
 //            group (dynamic tile claims; the kernel leaves them zero again), so one
 //            group must not run concurrently with itself.
 //   rgba:    4-byte pixels (a separate kernel instance: the 3-byte kernels do not carry its code)
+//   rot180:  FRAME_ROT180 frames (instances of their own, fast domain only: q8 must be set)
 //   pdl:     launch with programmatic stream serialization: the launch may start while the kernel
 //            before it in the stream is still draining.  Only for launches whose inputs do not come
 //            from that kernel (plans: frames resident and independent); completion order is kept.
-cudaError_t launch_fused(Layout layout, bool q8, bool rgba, bool use_tma, const CUtensorMap *map2,
+cudaError_t launch_fused(Layout layout, bool q8, bool rgba, bool rot180, bool use_tma, const CUtensorMap *map2,
                          const FrameDev *d_frames, const TileDesc *d_tiles,
                          uint32_t ntiles, uint32_t *d_counters, int num_sms, bool pdl, cudaStream_t stream);
 

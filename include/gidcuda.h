@@ -69,7 +69,8 @@ enum {
  *     ROTATE_270 : H x W,  pixel -> column H - 1 - r, row x
  * in the row order and byte order of the chosen format (for GIDCUDA_OUT_BGR8_BOTTOM_UP that is exactly
  * to_bmp's buffer).  Stride and size (gidcuda_output_geometry) are those of the rotated image.
- * Rotated frames take the two-pass kernels (IDCT, then one thread per pixel). */
+ * The half turn is done by the fused kernels themselves (mirrored runs, rows bottom to top: the price of
+ * an unrotated frame); quarter turns take the two-pass kernels (IDCT, then the pixel pass writes rotated). */
 #define GIDCUDA_FLAG_ROTATE_90 0x200u
 #define GIDCUDA_FLAG_ROTATE_180 0x400u
 #define GIDCUDA_FLAG_ROTATE_270 0x600u

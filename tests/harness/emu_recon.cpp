@@ -100,12 +100,16 @@ extern "C" int emu_reconstruct(const gidcuda_frame_desc *desc, const int16_t *co
           active = mx < f.mcux;
         }
         Scratch sc{&s_plane[0][0][t], &s_plane[1][0][t], &s_plane[2][0][t], kTileMcusSetup};
+#define EMU_RUN2(H, V, GREY, ROT)                                                                          \
+  do {                                                                                                     \
+    if (f.q8) { if (rgba) mcu_item<H, V, GREY, true, true, ROT>(it, active, f, qw, src, sc, t, mx, my);    \
+                else mcu_item<H, V, GREY, true, false, ROT>(it, active, f, qw, src, sc, t, mx, my); }      \
+    else { if (rgba) mcu_item<H, V, GREY, false, true, ROT>(it, active, f, qw, src, sc, t, mx, my);        \
+           else mcu_item<H, V, GREY, false, false, ROT>(it, active, f, qw, src, sc, t, mx, my); }          \
+  } while (0)
 #define EMU_RUN(H, V, GREY)                                                                          \
   do {                                                                                               \
-    if (f.q8) { if (rgba) mcu_item<H, V, GREY, true, true>(it, active, f, qw, src, sc, t, mx, my);    \
-                else mcu_item<H, V, GREY, true, false>(it, active, f, qw, src, sc, t, mx, my); }      \
-    else { if (rgba) mcu_item<H, V, GREY, false, true>(it, active, f, qw, src, sc, t, mx, my);        \
-           else mcu_item<H, V, GREY, false, false>(it, active, f, qw, src, sc, t, mx, my); }          \
+    if (f.flags & FRAME_ROT180) EMU_RUN2(H, V, GREY, true); else EMU_RUN2(H, V, GREY, false);        \
   } while (0)
         switch (g.layout) {
           case LAYOUT_GREY: EMU_RUN(1, 1, true); break;
@@ -116,6 +120,7 @@ extern "C" int emu_reconstruct(const gidcuda_frame_desc *desc, const int16_t *co
           default: EMU_RUN(2, 2, false); break;
         }
 #undef EMU_RUN
+#undef EMU_RUN2
       }
   return 0;
 }

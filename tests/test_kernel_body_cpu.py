@@ -98,6 +98,26 @@ def test_output_formats_and_strides(emu, oracle, synth, gidcuda_lib, samp):
     _check(emu, oracle, gidcuda_lib, fr, flags=capi.OUT_RGBA8, out_stride=4 * 211 + 4)
 
 
+@pytest.mark.parametrize("samp", ["grey", "444", "422", "420", "440", "411"])
+@pytest.mark.parametrize("w,h", [(64, 48), (211, 77), (40, 9), (1056, 16)])
+def test_half_turn_in_the_fused_kernels(emu, oracle, synth, gidcuda_lib, samp, w, h):
+    """GIDCUDA_FLAG_ROTATE_180 (Display_Orientation = Rotation_180 applied as test/to_bmp.adb:104-122 does in its
+    Set_X_Y): pixel (x, r) lands at column W - 1 - x, row H - 1 - r -- done by the fused kernels themselves
+    (mirrored runs, rows bottom to top), for whole and cut blocks, aligned and unaligned widths, every format."""
+    from gid_b200 import capi
+    fr = synth.planes_only(pixels_for(synth, 17, w, h, samp), samp)
+    ref = oracle.reconstruct(fr)[::-1, ::-1]
+    for flags, stride in ((0, 0), (capi.FLAG_PACKED_ROWS, 0), (capi.OUT_BGR8_BOTTOM_UP, 0), (capi.OUT_RGBA8, 0),
+                          (capi.OUT_RGBA8, 4 * w + 4)):
+        d = frame_desc(fr, flags | capi.FLAG_ROTATE_180, stride)
+        rows = emu.reconstruct(d, fr.planes, _stride(gidcuda_lib, d), h)
+        bpp = 4 if (flags & 0xFF) == capi.OUT_RGBA8 else 3
+        got = rows[:, :bpp * w].reshape(h, w, bpp)[:, :, :3]
+        if (flags & 0xFF) == capi.OUT_BGR8_BOTTOM_UP:
+            got = got[::-1, :, ::-1]
+        assert np.array_equal(got, ref), (samp, w, h, flags, stride)
+
+
 def test_idct_blocks_match_oracle(emu, oracle):
     """Block-level: the kernel IDCT (shortcut folded into the rounding constant,
     column shortcut dropped, re-associated rotations) == GID's, on blocks built
