@@ -46,6 +46,17 @@ struct Bits {
   uint64_t buf;  // left-aligned: the next bit is bit 63
   int len, pad;  // valid bits; how many of them (at the tail) are padding past the interval's end
   __device__ __forceinline__ void refill() {
+    // four bytes at once where none of them is FF (byte stuffing, :640-662, makes the byte-wise loop below
+    // a chain of dependent loads: one load latency per byte; these four loads are independent)
+    if (len <= 32 && p + 4 <= e) {
+      const uint32_t b0 = __ldg(p), b1 = __ldg(p + 1), b2 = __ldg(p + 2), b3 = __ldg(p + 3);
+      if (b0 != 0xFFu && b1 != 0xFFu && b2 != 0xFFu && b3 != 0xFFu) {
+        buf |= (uint64_t)((b0 << 24) | (b1 << 16) | (b2 << 8) | b3) << (32 - len);
+        len += 32;
+        p += 4;
+        return;
+      }
+    }
     while (len <= 56) {
       uint32_t b = 0xFFu;
       if (p < e) {
@@ -126,9 +137,18 @@ __device__ __forceinline__ bool decode_block(Bits &b, const HuffDev &dc, const H
   return b.pad <= b.len;  // false: bits past the end of the interval were used
 }
 
+// Every thread assembles its block in shared memory and writes it out whole, eight 16-byte stores: the
+// planes need no zeroing beforehand (every block of the frame belongs to exactly one interval) and no
+// sector is written piecemeal (scattered int16 stores into zeroed planes cost a 134 MB memset and 85 MB of
+// read-modify-write DRAM traffic per 8192 x 8192 frame: profiles/r01f_ncu_summary.md).  A thread's buffer is
+// 144 bytes from the next one's: its 16-byte pieces fall on different banks for the 8 threads of a
+// quarter warp.
+constexpr int kStageStride = 72;  // int16 per thread (64 used)
+
 __global__ void __launch_bounds__(128) huffman_intervals_kernel(ScanArgs a) {
   __shared__ HuffDev tabs[6];
   __shared__ uint8_t zz[64];
+  __shared__ __align__(16) int16_t stage[128 * kStageStride];
   {
     const uint32_t *src = reinterpret_cast<const uint32_t *>(a.tables);
     uint32_t *dst = reinterpret_cast<uint32_t *>(tabs);
@@ -138,6 +158,7 @@ __global__ void __launch_bounds__(128) huffman_intervals_kernel(ScanArgs a) {
   __syncthreads();
   const uint32_t it = blockIdx.x * blockDim.x + threadIdx.x;
   if (it >= a.nintervals) return;
+  uint4 *mine = reinterpret_cast<uint4 *>(stage + threadIdx.x * kStageStride);
   Bits b;
   b.p = a.data + __ldg(a.begin + it);
   b.e = a.data + __ldg(a.end + it);
@@ -156,8 +177,13 @@ __global__ void __launch_bounds__(128) huffman_intervals_kernel(ScanArgs a) {
         for (int sx = 0; sx < a.h[c] && ok; sx++) {
           const size_t blockno = (size_t)(my * a.v[c] + sy) * a.bx[c] + (mx * a.h[c] + sx);
           GIDK_ASSERT(blockno < (size_t)a.bx[c] * a.v[c] * ((a.nmcu + a.mcux - 1) / a.mcux));
-          int16_t *blk = a.plane[c] + blockno * 64;
-          ok = decode_block(b, tabs[c], tabs[3 + c], pred[c], blk, zz, a.limbits[c]);
+          const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+          for (int j = 0; j < 8; j++) mine[j] = z;
+          ok = decode_block(b, tabs[c], tabs[3 + c], pred[c], reinterpret_cast<int16_t *>(mine), zz, a.limbits[c]);
+          uint4 *dst = reinterpret_cast<uint4 *>(a.plane[c] + blockno * 64);
+#pragma unroll
+          for (int j = 0; j < 8; j++) dst[j] = mine[j];
         }
   }
   // every interval but the last ends where its RSTn begins: all bytes read, less than a byte

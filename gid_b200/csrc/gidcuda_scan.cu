@@ -311,10 +311,9 @@ int job_submit_scan(gidcuda_job *job, cudaStream_t s) {
   gidcuda_ctx *ctx = job->ctx;
   const Geometry &g = job->geo;
   CU_TRY(ctx, cudaMemcpyAsync(job->d_scan, job->h_scan, job->scan_bytes, cudaMemcpyHostToDevice, s));
-  if (job->scan_ri != 0) {  // (the self-synchronising decoder's first launch zeroes both itself)
-    CU_TRY(ctx, cudaMemsetAsync(job->d_coef, 0, g.coef_bytes, s));
-    CU_TRY(ctx, cudaMemsetAsync(job->d_status, 0, 16, s));
-  }
+  // (status words: the self-synchronising decoder's first launch zeroes them itself, together with the
+  // planes; the interval decoder writes every block whole and needs no zeroed planes)
+  if (job->scan_ri != 0) CU_TRY(ctx, cudaMemsetAsync(job->d_status, 0, 16, s));
   if (job->scan_ri == 0) {
     gidk::WholeArgs wa;
     make_whole_args(job, &wa);

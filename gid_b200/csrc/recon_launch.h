@@ -76,7 +76,7 @@ struct ScanArgs {
   const uint8_t *data;          // the scan's entropy-coded bytes
   const uint32_t *begin, *end;  // [nintervals] byte offsets into data: interval i = [begin[i], end[i])
   const HuffDev *tables;        // [6]: DC tables of components 0 .. 2, then their AC tables
-  int16_t *plane[3];            // zeroed dense planes (block-major, natural order)
+  int16_t *plane[3];            // dense planes (block-major, natural order); every block is written whole
   uint32_t bx[3];
   int32_t h[3], v[3];
   int32_t ncomp;
