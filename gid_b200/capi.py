@@ -32,7 +32,8 @@ EXPORTS = [
     "gidcuda_abi_version", "gidcuda_device_count", "gidcuda_last_error", "gidcuda_set_option", "gidcuda_counter", "gidcuda_create",
     "gidcuda_destroy", "gidcuda_plane_geometry", "gidcuda_output_geometry", "gidcuda_job_begin",
     "gidcuda_job_plane", "gidcuda_job_hint_rows", "gidcuda_fast_coef_limit", "gidcuda_job_wide_coefficients", "gidcuda_job_records", "gidcuda_job_records_commit", "gidcuda_job_records_commit_runs",
-    "gidcuda_job_output", "gidcuda_job_scan", "gidcuda_host_is_pinned", "gidcuda_job_submit", "gidcuda_job_wait", "gidcuda_job_release",
+    "gidcuda_job_pscan_reserve", "gidcuda_job_pscan", "gidcuda_job_pscan_masks", "gidcuda_job_pscan_refine",
+    "gidcuda_job_pscan_refine_commit", "gidcuda_job_output", "gidcuda_job_scan", "gidcuda_host_is_pinned", "gidcuda_job_submit", "gidcuda_job_wait", "gidcuda_job_release",
     "gidcuda_plan_create", "gidcuda_plan_launch", "gidcuda_plan_launch_count", "gidcuda_plan_uses_tma",
     "gidcuda_plan_destroy", "gidcuda_synchronize", "gidcuda_batch_create", "gidcuda_batch_run", "gidcuda_batch_run_records",
     "gidcuda_batch_destroy", "gidcuda_host_alloc", "gidcuda_host_free",

@@ -549,6 +549,393 @@ __global__ void __launch_bounds__(128) huffman_output_kernel(WholeArgs a) {
   if (done) atomicAdd(a.status + 2, done);
 }
 
+
+// =================================================================================================
+// Progressive scans (ITU T.81 annex G; GID: gid-decoding_jpg.adb:1243-1747).
+//
+// FIRST scans are ordinary Huffman streams and take the self-synchronising decoder above with a
+// smaller state:
+//   DC first (Ss = 0, Ah = 0; :1263-1340): per block one DC code and its difference bits; state =
+//       (bit position, block of the MCU); value stored = predictor << Al; prefix sums of the
+//       differences give the predictors, as for baseline scans;
+//   AC first (Ss > 0, Ah = 0; :1381-1470): one component, band Ss .. Se; state = (bit position,
+//       position in the band).  EOBn (run < 15, size 0) ends the block and the next 2**n - 1 + bits
+//       blocks read nothing, so a run only advances the block count -- it is not part of the state
+//       at a code-word boundary.
+// DC REFINEMENT scans (:1341-1380) are one bit per block: no code words at all.
+// AC REFINEMENT scans (:1560-1690) are NOT decodable this way: inside an EOB run a block still reads one
+// correction bit per coefficient that is already non-zero, so the decoder's state includes the
+// absolute block number, which no guessed start can recover from the bits.  They stay on the host,
+// which only needs the non-zero history (pscan_masks_kernel) and sends back, per block, which
+// positions took a correction bit and which became +-(1 << Al) (pscan_apply_kernel).
+// Block order: interleaved scans walk the frame's MCUs (:1187-1219); a single-component scan walks
+// the component's OWN block grid, ceil(W_c / 8) x ceil(H_c / 8), row by row (:1952-1971).
+
+struct PSlot {  // one block of the MCU of an interleaved scan
+  int16_t *plane;
+  uint32_t row_blocks, h, v, sx, sy, comp;
+  int32_t limbits;
+};
+
+__device__ __forceinline__ void pscan_slots(const PscanArgs &a, PSlot *slots) {  // one thread
+  uint32_t cc = 0;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {  // static component index (see load_tables)
+    bool in_scan = false;
+    for (uint32_t j = 0; j < a.ncomp; j++) in_scan = in_scan || a.comps[j] == (uint32_t)k;
+    if (!in_scan) continue;
+    const int hh = a.ncomp > 1 ? a.h[k] : 1, vv = a.ncomp > 1 ? a.v[k] : 1;
+    for (int sy = 0; sy < vv; sy++)
+      for (int sx = 0; sx < hh; sx++, cc++) {
+        PSlot q;
+        q.plane = a.plane[k];
+        q.row_blocks = a.row_blocks[k];
+        q.h = (uint32_t)hh;
+        q.v = (uint32_t)vv;
+        q.sx = (uint32_t)sx;
+        q.sy = (uint32_t)sy;
+        q.comp = (uint32_t)k;
+        q.limbits = a.limbits[k];
+        if (cc < 12) slots[cc] = q;
+      }
+  }
+}
+__device__ __forceinline__ void pscan_load(const PscanArgs &a, HuffDev *tabs, uint8_t *zz, PSlot *slots) {
+  const uint32_t *src = reinterpret_cast<const uint32_t *>(a.tables);
+  uint32_t *dst = reinterpret_cast<uint32_t *>(tabs);
+  for (uint32_t i = threadIdx.x; i < 6 * sizeof(HuffDev) / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+  if (threadIdx.x < 64) zz[threadIdx.x] = c_zigzag[threadIdx.x];
+  if (threadIdx.x == 0) pscan_slots(a, slots);
+}
+
+// block number `b` of the scan (its block `c` of the MCU) -> the block in its plane
+__device__ __forceinline__ int16_t *pscan_block(const PscanArgs &a, const PSlot *slots, uint32_t b, uint32_t c) {
+  const PSlot &q = slots[c];
+  size_t at;
+  if (a.ncomp > 1) {
+    const uint32_t mcu = (b - c) / a.bpm;
+    const uint32_t my = mcu / a.mcux, mx = mcu - my * a.mcux;
+    at = (size_t)(my * q.v + q.sy) * q.row_blocks + (mx * q.h + q.sx);
+  } else {
+    const uint32_t by = b / a.nbx, bx = b - by * a.nbx;
+    at = (size_t)by * q.row_blocks + bx;
+  }
+  return q.plane + at * 64;
+}
+
+// One Huffman symbol at the head of `bits`; -1 = no such code.  Advances pos.
+__device__ __forceinline__ int pscan_symbol(RawBits &bits, const HuffDev &t, uint32_t &pos) {
+  const uint32_t look = bits.peek(16);
+  const uint32_t e = t.lut[look >> 6];
+  int l = (int)(e >> 8), sym = (int)(e & 0xFFu);
+  if (e == 0) {
+    sym = -1;
+    for (l = 11; l <= 16; l++) {
+      const int code = (int)(look >> (16 - l));
+      if (code <= t.maxcode[l]) {
+        sym = t.vals[(t.valoff[l] + code) & 0xFF];
+        break;
+      }
+    }
+    if (sym < 0) return -1;
+  }
+  bits.drop(l);
+  pos += (uint32_t)l;
+  return sym;
+}
+
+// The code words of a subsequence that start before bit `limit`, from state `entry` = (pos, c, k).
+// MODE 1: DC first, MODE 2: AC first.  FINAL as in run_subsequence.
+template <bool FINAL, int MODE>
+__device__ __forceinline__ uint64_t run_pscan(const PscanArgs &a, const HuffDev *tabs, const uint8_t *zz, const PSlot *slots,
+                                              uint64_t entry, uint32_t limit, int4 &tup, uint32_t b, int pred0, int pred1,
+                                              int pred2, bool *bad, uint32_t *done_blocks) {
+  uint32_t pos = (uint32_t)entry, c = (uint32_t)(entry >> 32) & 0xFFu, k = (uint32_t)(entry >> 40) & 0xFFu;
+  RawBits bits;
+  bits.start(a.data, pos);
+  int nb = 0, dcs0 = 0, dcs1 = 0, dcs2 = 0;
+  const uint32_t b0 = b;
+  while (pos < limit) {
+    if (FINAL && b >= a.total_blocks) break;
+    if (bits.len <= 32) bits.refill();
+    if (MODE == 1) {
+      const int kc = (int)slots[c].comp;
+      const int sym = pscan_symbol(bits, tabs[kc], pos);
+      if (sym < 0) {
+        if (FINAL) { *bad = true; break; }
+        bits.drop(1);
+        pos += 1;
+        continue;
+      }
+      const int n = sym & 15;
+      int v = 0;
+      if (n) {
+        v = extend(bits.peek(n), n);
+        bits.drop(n);
+        pos += (uint32_t)n;
+      }
+      if (FINAL) {
+        pred0 += kc == 0 ? v : 0;
+        pred1 += kc == 1 ? v : 0;
+        pred2 += kc == 2 ? v : 0;
+        const int pk = kc == 0 ? pred0 : (kc == 1 ? pred1 : pred2);
+        const int room = slots[c].limbits - (int)a.al;  // |pk << al| must stay inside the planes' range
+        if (room <= 0 || !within_bits(pk, room)) { *bad = true; break; }
+        pscan_block(a, slots, b, c)[0] = (int16_t)(pk * (1 << a.al));
+        b++;
+      } else {
+        dcs0 += kc == 0 ? v : 0;
+        dcs1 += kc == 1 ? v : 0;
+        dcs2 += kc == 2 ? v : 0;
+      }
+      c = c + 1 == a.bpm ? 0 : c + 1;
+      nb++;
+    } else {
+      const int kc = (int)a.comps[0];
+      const int sym = pscan_symbol(bits, tabs[3 + kc], pos);
+      if (sym < 0) {
+        if (FINAL) { *bad = true; break; }
+        bits.drop(1);
+        pos += 1;
+        continue;
+      }
+      const uint32_t r = (uint32_t)sym >> 4, sz = (uint32_t)sym & 15u;
+      uint32_t adv = 0;  // blocks completed by this code word
+      if (sz == 0) {
+        if (r < 15) {  // EOBn: this block and the next 2**r - 1 + bits blocks are done
+          uint32_t run = (1u << r) - 1u;
+          if (r) {
+            run += bits.peek((int)r);
+            bits.drop((int)r);
+            pos += r;
+          }
+          adv = 1u + run;
+        } else {  // ZRL
+          k += 16;
+          if (k > a.se) adv = 1;
+        }
+      } else {
+        k += r;
+        const bool outside = k > a.se;
+        if (FINAL && (outside || (int)(sz + a.al) > slots[0].limbits)) { *bad = true; break; }
+        const int v = extend(bits.peek((int)sz), (int)sz);
+        bits.drop((int)sz);
+        pos += sz;
+        if (FINAL) pscan_block(a, slots, b, 0)[zz[k & 63u]] = (int16_t)(v * (1 << a.al));
+        k++;
+        if (outside || k > a.se) adv = 1;
+      }
+      if (adv) {
+        k = a.ss;
+        nb += (int)adv;
+        if (FINAL) b += adv;
+      }
+    }
+  }
+  tup = make_int4(nb, dcs0, dcs1, dcs2);
+  if (FINAL) *done_blocks = min(b, a.total_blocks) - b0;
+  return pack_state(pos, c, k);
+}
+
+template <bool FINAL>
+__device__ __forceinline__ uint64_t run_pscan_mode(const PscanArgs &a, const HuffDev *tabs, const uint8_t *zz, const PSlot *slots,
+                                                   uint64_t entry, uint32_t limit, int4 &tup, uint32_t b, int p0, int p1, int p2,
+                                                   bool *bad, uint32_t *done) {
+  return a.mode == 1 ? run_pscan<FINAL, 1>(a, tabs, zz, slots, entry, limit, tup, b, p0, p1, p2, bad, done)
+                     : run_pscan<FINAL, 2>(a, tabs, zz, slots, entry, limit, tup, b, p0, p1, p2, bad, done);
+}
+
+// Step 1, as huffman_sync_kernel.  A block starts in state (pos, 0, k0): k0 = 0 for DC scans, Ss for AC scans.
+__global__ void __launch_bounds__(kWindow) pscan_sync_kernel(PscanArgs a, uint32_t shift, int first) {
+  __shared__ HuffDev tabs[6];
+  __shared__ uint8_t zz[64];
+  __shared__ uint64_t X[kWindow];
+  __shared__ PSlot slots[12];
+  pscan_load(a, tabs, zz, slots);
+  const uint32_t t = threadIdx.x;
+  const uint32_t i = blockIdx.x * kWindow + t + shift;
+  const bool active = i < a.nsub;
+  const uint32_t k0 = a.mode == 2 ? a.ss : 0u;
+  const uint64_t true_start = pack_state(0u, 0u, k0);
+  uint64_t entry = 0, exit_ = 0, head = 0;
+  int4 tup = make_int4(0, 0, 0, 0);
+  bool dirty = false;
+  __syncthreads();
+  const uint32_t limit = active ? min((i + 1) * a.sub_bits, a.nbits) : 0u;
+  if (active) {
+    if (first) {
+      entry = i == 0 ? true_start : pack_state(i * a.sub_bits, 0u, k0);
+      exit_ = run_pscan_mode<false>(a, tabs, zz, slots, entry, limit, tup, 0u, 0, 0, 0, nullptr, nullptr);
+      dirty = true;
+    } else {
+      entry = a.entry[i];
+      exit_ = a.exit_[i];
+    }
+    if (t == 0) head = i == 0 ? true_start : (first ? entry : a.exit_[i - 1]);
+  }
+  X[t] = exit_;
+  for (int iter = 0; iter < kMaxRounds; iter++) {
+    __syncthreads();
+    const uint64_t want = t == 0 ? head : X[t - 1];
+    const bool redo = active && want != entry;
+    uint64_t nx = exit_;
+    if (redo) {
+      entry = want;
+      nx = run_pscan_mode<false>(a, tabs, zz, slots, entry, limit, tup, 0u, 0, 0, 0, nullptr, nullptr);
+      dirty = true;
+    }
+    __syncthreads();
+    const bool changed = redo && nx != exit_;
+    if (redo) {
+      exit_ = nx;
+      X[t] = nx;
+    }
+    if (!__syncthreads_or(changed ? 1 : 0)) break;
+  }
+  if (active && dirty) {
+    a.entry[i] = entry;
+    a.exit_[i] = exit_;
+    a.tuple[i] = tup;
+  }
+}
+
+// Step 3, as huffman_output_kernel.
+__global__ void __launch_bounds__(128) pscan_output_kernel(PscanArgs a) {
+  __shared__ HuffDev tabs[6];
+  __shared__ uint8_t zz[64];
+  __shared__ PSlot slots[12];
+  pscan_load(a, tabs, zz, slots);
+  __syncthreads();
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.nsub) return;
+  const int4 pre = a.prefix[i];
+  const uint32_t b = (uint32_t)pre.x;
+  if (b >= a.total_blocks) return;  // padding after the last block
+  const uint32_t k0 = a.mode == 2 ? a.ss : 0u;
+  const uint64_t entry = i == 0 ? pack_state(0u, 0u, k0) : a.exit_[i - 1];
+  bool chain_bad = entry != a.entry[i];
+  const uint32_t c = (uint32_t)(entry >> 32) & 0xFFu;
+  if (c >= a.bpm || b % a.bpm != c) chain_bad = true;
+  bool code_bad = false;
+  uint32_t done = 0;
+  if (!chain_bad) {
+    int4 tup;
+    const uint32_t limit = min((i + 1) * a.sub_bits, a.nbits);
+    const uint64_t out = run_pscan_mode<true>(a, tabs, zz, slots, entry, limit, tup, b, pre.y, pre.z, pre.w, &code_bad, &done);
+    if (!code_bad && b + (uint32_t)tup.x < a.total_blocks && out != a.exit_[i]) chain_bad = true;
+    // the thread that stored the scan's last block says where the scan's code words ended: the host holds
+    // that against the scan's length (bytes left over, or bits taken from the padding, are a damaged
+    // stream: the serial decoder's case)
+    if (!code_bad && done != 0 && b + done == a.total_blocks) a.status[3] = (uint32_t)out + 1u;
+  }
+  if (chain_bad) atomicOr(a.status, 2u);
+  if (code_bad) atomicOr(a.status, 8u);
+  if (done) atomicAdd(a.status + 2, done);
+}
+
+// The prefix sums of step 2 over PscanArgs (same arrays as WholeArgs)
+__global__ void __launch_bounds__(1024) pscan_scan_kernel(PscanArgs a) {
+  __shared__ int4 warp_tot[32];
+  __shared__ int4 carry_s;
+  const uint32_t t = threadIdx.x, lane = t & 31u, w = t >> 5;
+  const int4 zero = make_int4(0, 0, 0, 0);
+  if (t == 0) carry_s = zero;
+  __syncthreads();
+  for (uint32_t base = 0; base < a.nsub; base += 4096) {
+    const uint32_t i0 = base + 4 * t;
+    int4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) v[k] = i0 + k < a.nsub ? a.tuple[i0 + k] : zero;
+    const int4 mine = add4(add4(v[0], v[1]), add4(v[2], v[3]));
+    const int4 s = warp_inclusive(mine, lane);
+    if (lane == 31) warp_tot[w] = s;
+    __syncthreads();
+    if (w == 0) {
+      const int4 u = warp_tot[lane];
+      warp_tot[lane] = sub4(warp_inclusive(u, lane), u);
+    }
+    __syncthreads();
+    int4 ex = add4(add4(carry_s, warp_tot[w]), sub4(s, mine));
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (i0 + k < a.nsub) a.prefix[i0 + k] = ex;
+      ex = add4(ex, v[k]);
+    }
+    __syncthreads();
+    if (t == 1023) carry_s = ex;
+    __syncthreads();
+  }
+}
+
+// DC refinement (:1341-1380): bit b of the scan belongs to block b; a 1 sets bit Al of the DC term.
+__global__ void __launch_bounds__(256) pscan_dc_refine_kernel(PscanArgs a) {
+  __shared__ PSlot slots[12];
+  if (threadIdx.x == 0) pscan_slots(a, slots);
+  __syncthreads();
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.total_blocks) return;
+  const uint32_t bit = (__ldg(a.data + (b >> 3)) >> (7u - (b & 7u))) & 1u;
+  if (!bit) return;
+  int16_t *blk = pscan_block(a, slots, b, b % a.bpm);
+  blk[0] = (int16_t)(blk[0] | (int16_t)(1 << a.al));
+}
+
+// Non-zero history of a plane for the host's AC refinement decoder: bit k of masks[b] = the coefficient at
+// zig-zag position k of block b is non-zero.
+__global__ void __launch_bounds__(128) pscan_masks_kernel(const int16_t *__restrict__ plane, uint32_t nblocks,
+                                                          uint64_t *__restrict__ masks) {
+  __shared__ uint8_t zz[64];
+  if (threadIdx.x < 64) zz[threadIdx.x] = c_zigzag[threadIdx.x];
+  __syncthreads();
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nblocks) return;
+  const uint4 *src = reinterpret_cast<const uint4 *>(plane + (size_t)b * 64);
+  uint64_t nat = 0;  // bit n = coefficient at natural position n is non-zero
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const uint4 w = __ldg(src + j);
+    const uint32_t q[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (q[i] & 0xFFFFu) nat |= 1ull << (8 * j + 2 * i);
+      if (q[i] >> 16) nat |= 1ull << (8 * j + 2 * i + 1);
+    }
+  }
+  uint64_t m = 0;
+  for (int k = 0; k < 64; k++) m |= ((nat >> zz[k]) & 1ull) << k;
+  masks[b] = m;
+}
+
+// The host's AC refinement verdict on the planes (:1600-1690 as the host mirror's ac_refine applies it):
+//   corr   the coefficient, non-zero before the scan, read a correction bit of 1: add 1 << al away from zero
+//          unless bit al of it is set already;
+//   newpos the coefficient was zero and becomes +(1 << al), or -(1 << al) where newneg is set as well.
+__global__ void __launch_bounds__(128) pscan_apply_kernel(int16_t *__restrict__ plane, uint32_t nblocks,
+                                                          const uint64_t *__restrict__ corr, const uint64_t *__restrict__ newpos,
+                                                          const uint64_t *__restrict__ newneg, uint32_t al) {
+  __shared__ uint8_t zz[64];
+  if (threadIdx.x < 64) zz[threadIdx.x] = c_zigzag[threadIdx.x];
+  __syncthreads();
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nblocks) return;
+  int16_t *blk = plane + (size_t)b * 64;
+  const int p1 = 1 << al, m1 = -(1 << al);
+  uint64_t m = __ldg(corr + b);
+  while (m) {
+    const int k = __ffsll((long long)m) - 1;
+    m &= m - 1;
+    const int z = blk[zz[k]];
+    if ((z & p1) == 0) blk[zz[k]] = (int16_t)(z >= 0 ? z + p1 : z + m1);
+  }
+  m = __ldg(newpos + b);
+  const uint64_t neg = __ldg(newneg + b);
+  while (m) {
+    const int k = __ffsll((long long)m) - 1;
+    m &= m - 1;
+    blk[zz[k]] = (int16_t)(((neg >> k) & 1ull) ? m1 : p1);
+  }
+}
+
 }  // namespace
 
 cudaError_t launch_huffman_whole(const WholeArgs &a, cudaStream_t stream) {
@@ -565,6 +952,35 @@ cudaError_t launch_huffman_finish(const WholeArgs &a, cudaStream_t stream) {
   if (a.nsub == 0) return cudaSuccess;
   huffman_scan_kernel<<<1, 1024, 0, stream>>>(a);
   huffman_output_kernel<<<(a.nsub + 127) / 128, 128, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pscan(const PscanArgs &a, cudaStream_t stream) {
+  if (a.nsub == 0) return cudaSuccess;
+  pscan_sync_kernel<<<(a.nsub + kWindow - 1) / kWindow, kWindow, 0, stream>>>(a, 0u, 1);
+  if (a.nsub > kWindow / 2)
+    pscan_sync_kernel<<<(a.nsub - kWindow / 2 + kWindow - 1) / kWindow, kWindow, 0, stream>>>(a, kWindow / 2, 0);
+  pscan_scan_kernel<<<1, 1024, 0, stream>>>(a);
+  pscan_output_kernel<<<(a.nsub + 127) / 128, 128, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pscan_dc_refine(const PscanArgs &a, cudaStream_t stream) {
+  if (a.total_blocks == 0) return cudaSuccess;
+  pscan_dc_refine_kernel<<<(a.total_blocks + 255) / 256, 256, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pscan_masks(const int16_t *plane, uint32_t nblocks, uint64_t *masks, cudaStream_t stream) {
+  if (nblocks == 0) return cudaSuccess;
+  pscan_masks_kernel<<<(nblocks + 127) / 128, 128, 0, stream>>>(plane, nblocks, masks);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pscan_apply(int16_t *plane, uint32_t nblocks, const uint64_t *corr, const uint64_t *newpos,
+                               const uint64_t *newneg, uint32_t al, cudaStream_t stream) {
+  if (nblocks == 0) return cudaSuccess;
+  pscan_apply_kernel<<<(nblocks + 127) / 128, 128, 0, stream>>>(plane, nblocks, corr, newpos, newneg, al);
   return cudaGetLastError();
 }
 

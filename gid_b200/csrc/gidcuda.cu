@@ -144,6 +144,7 @@ static void job_free_buffers(gidcuda_job *j) {
   if (j->d_sync) cudaFree(j->d_sync);
   j->d_sync = nullptr;
   j->cap_sync = 0;
+  job_free_pscan(j);
   j->h_scan = j->d_scan = nullptr;
   j->h_status = j->d_status = nullptr;
   j->cap_scan = 0;
@@ -286,6 +287,7 @@ extern "C" int gidcuda_job_begin(gidcuda_ctx *ctx, const gidcuda_frame_desc *des
   j->h_coef_clean = false;  // zeroed when the decoder asks for the planes
   j->user_pixels = nullptr;
   j->scan_active = false;
+  j->pscan_active = false;
   for (int c = 0; c < 3; c++) {
     j->rows_hint[c] = 8;
     // a recycled job's device planes hold another frame's geometry: whatever was zeroed there, the
@@ -460,13 +462,17 @@ extern "C" int gidcuda_job_submit(gidcuda_job *job) {
     const int rc = job_submit_scan(job, s);
     if (rc != GIDCUDA_OK) return rc;
   }
+  if (job->pscan_active) {  // a progressive frame whose scans were queued one by one: the planes are on the device
+    const int rc = job_submit_pscan(job, s);
+    if (rc != GIDCUDA_OK) return rc;
+  }
   constexpr size_t kMinPitchedPlane = (size_t)8 << 20;
   bool any_sparse = false, all_dense_plain = true;
   for (int c = 0; c < g.ncomp; c++) {
     any_sparse = any_sparse || job->sparse[c];
     if (job->sparse[c] || (job->rows_hint[c] <= 4 && g.plane_bytes[c] >= kMinPitchedPlane)) all_dense_plain = false;
   }
-  if (job->scan_active) {
+  if (job->scan_active || job->pscan_active) {
     any_sparse = false;  // every plane comes from the device decoder
   } else if (!all_dense_plain || any_sparse) {
     for (int c = 0; c < g.ncomp; c++) {
@@ -548,6 +554,10 @@ extern "C" int gidcuda_job_wait(gidcuda_job *job, const uint8_t **pixels, size_t
   CU_TRY(ctx, cudaEventSynchronize(job->done));
   if (job->scan_active) {  // what the device decoder made of the scan (the host's chain repair included)
     const int rc = job_finish_scan(job);
+    if (rc != GIDCUDA_OK) return rc;
+  }
+  if (job->pscan_active) {
+    const int rc = job_finish_pscan(job);
     if (rc != GIDCUDA_OK) return rc;
   }
   if (pixels) *pixels = job->user_pixels ? job->user_pixels : job->h_pixels;

@@ -7,6 +7,7 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -83,6 +84,27 @@ struct gidcuda_job {
   size_t cap_sync = 0, scan_len = 0;
   uint32_t scan_nsub = 0, scan_sub_bits = 0;
   size_t repaired_subsequences = 0;  // subsequences the host walked in the last chain repair
+  // gidcuda_job_pscan*: the entropy-coded bytes + code tables of every scan of a progressive frame (pinned +
+  // device twin, one slice per scan), four status words per scan, and per component the non-zero masks and
+  // the three arrays of an AC refinement (pinned + device twins)
+  bool pscan_active = false;
+  uint8_t *h_pscan = nullptr, *d_pscan = nullptr;
+  size_t cap_pscan = 0, pscan_used = 0;
+  uint32_t *h_pstatus = nullptr, *d_pstatus = nullptr;
+  uint32_t pscan_count = 0;
+  uint32_t pscan_nbits[64] = {0};      // bits of each decoded scan (0: not checked)
+  uint32_t pscan_expected[64] = {0};   // blocks a decoded scan must store (0: a DC refinement scan, not counted)
+  uint64_t *h_masks = nullptr, *d_masks = nullptr, *h_refine = nullptr, *d_refine = nullptr;
+  size_t cap_masks = 0;                // blocks the four arrays above hold (masks: x1, refine: x3)
+  cudaEvent_t refine_copied = nullptr; // the host may overwrite h_refine again
+  // scans staged by gidcuda_job_pscan and not yet on the stream: ONE host-to-device copy and their launches go
+  // out together (pscan_flush), at the next point the host needs the device's answer.  A copy per scan,
+  // interleaved with that scan's kernels, would queue behind the copies of other frames' streams in the copy
+  // engine's FIFO while those wait for their own kernels: the streams of concurrent frames serialise each other.
+  std::vector<gidk::PscanArgs> pscan_pending;
+  size_t pscan_flushed = 0;            // bytes of h_pscan already copied
+  cudaEvent_t masks_ready = nullptr;   // blocking: the thread sleeps until the device has the history ready
+  bool refine_pending = false;
   uint8_t *user_pixels = nullptr;  // gidcuda_job_output: the caller's own pinned buffer receives the pixels
   uint8_t *d_coef = nullptr, *d_pixels = nullptr, *d_samples = nullptr;
   gidk::LaunchSet set;
@@ -98,3 +120,7 @@ struct gidcuda_job {
 // the host's chain repair included.
 int job_submit_scan(gidcuda_job *job, cudaStream_t s);
 int job_finish_scan(gidcuda_job *job);
+// ... and the scans of a progressive frame (gidcuda_job_pscan*): status words back at submit, verdict at wait
+int job_submit_pscan(gidcuda_job *job, cudaStream_t s);
+int job_finish_pscan(gidcuda_job *job);
+void job_free_pscan(gidcuda_job *job);

@@ -375,3 +375,321 @@ int job_finish_scan(gidcuda_job *job) {
   }
   return GIDCUDA_OK;
 }
+
+
+// ---------------------------------------------------------------------------
+// progressive frames: gidcuda_job_pscan* (include/gidcuda.h)
+
+constexpr uint32_t kMaxPscans = 64;
+constexpr size_t kPscanTables = (6 * sizeof(gidk::HuffDev) + 255) / 256 * 256;
+
+void job_free_pscan(gidcuda_job *job) {
+  if (job->h_pscan) cudaFreeHost(job->h_pscan);
+  if (job->d_pscan) cudaFree(job->d_pscan);
+  if (job->h_pstatus) cudaFreeHost(job->h_pstatus);
+  if (job->d_pstatus) cudaFree(job->d_pstatus);
+  if (job->h_masks) cudaFreeHost(job->h_masks);
+  if (job->d_masks) cudaFree(job->d_masks);
+  if (job->h_refine) cudaFreeHost(job->h_refine);
+  if (job->d_refine) cudaFree(job->d_refine);
+  if (job->refine_copied) cudaEventDestroy(job->refine_copied);
+  if (job->masks_ready) cudaEventDestroy(job->masks_ready);
+  job->masks_ready = nullptr;
+  job->h_pscan = job->d_pscan = nullptr;
+  job->h_pstatus = job->d_pstatus = nullptr;
+  job->h_masks = job->d_masks = job->h_refine = job->d_refine = nullptr;
+  job->refine_copied = nullptr;
+  job->cap_pscan = job->cap_masks = 0;
+}
+
+extern "C" int gidcuda_job_pscan_reserve(gidcuda_job *job, size_t total_bytes) {
+  if (!job) return fail(nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "null job");
+  gidcuda_ctx *ctx = job->ctx;
+  if (job->state != gidcuda_job::BEGUN || job->pscan_active || job->scan_active)
+    return fail(ctx, GIDCUDA_ERR_STATE, "gidcuda_job_pscan_reserve: once, between gidcuda_job_begin and the first scan");
+  if (total_bytes == 0 || total_bytes >= ((size_t)1 << 30))
+    return fail(ctx, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_job_pscan_reserve: %zu bytes", total_bytes);
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  // every scan: its six code tables, its bytes, FF padding (the decoder looks a few bytes ahead)
+  const size_t need = round_up(total_bytes, 256) + kMaxPscans * (kPscanTables + 512);
+  if (job->cap_pscan < need) {
+    if (job->h_pscan) cudaFreeHost(job->h_pscan);
+    if (job->d_pscan) cudaFree(job->d_pscan);
+    job->h_pscan = job->d_pscan = nullptr;
+    job->cap_pscan = 0;
+    const size_t cap = need + need / 4;
+    CU_TRY(ctx, cudaHostAlloc((void **)&job->h_pscan, cap, cudaHostAllocDefault));
+    CU_TRY(ctx, cudaMalloc((void **)&job->d_pscan, cap));
+    job->cap_pscan = cap;
+  }
+  if (!job->h_pstatus) {
+    CU_TRY(ctx, cudaHostAlloc((void **)&job->h_pstatus, kMaxPscans * 16, cudaHostAllocDefault));
+    CU_TRY(ctx, cudaMalloc((void **)&job->d_pstatus, kMaxPscans * 16));
+  }
+  size_t most = 0;
+  const Geometry &g = job->geo;
+  for (int c = 0; c < g.ncomp; c++) most = std::max(most, (size_t)g.bx[c] * g.by[c]);
+  if (job->cap_masks < most) {
+    if (job->h_masks) cudaFreeHost(job->h_masks);
+    if (job->d_masks) cudaFree(job->d_masks);
+    if (job->h_refine) cudaFreeHost(job->h_refine);
+    if (job->d_refine) cudaFree(job->d_refine);
+    job->h_masks = job->d_masks = job->h_refine = job->d_refine = nullptr;
+    job->cap_masks = 0;
+    const size_t cap = most + most / 4;
+    CU_TRY(ctx, cudaHostAlloc((void **)&job->h_masks, cap * 8, cudaHostAllocDefault));
+    CU_TRY(ctx, cudaMalloc((void **)&job->d_masks, cap * 8));
+    CU_TRY(ctx, cudaHostAlloc((void **)&job->h_refine, cap * 24, cudaHostAllocDefault));
+    CU_TRY(ctx, cudaMalloc((void **)&job->d_refine, cap * 24));
+    job->cap_masks = cap;
+  }
+  if (!job->refine_copied) CU_TRY(ctx, cudaEventCreateWithFlags(&job->refine_copied, cudaEventDisableTiming));
+  if (!job->masks_ready) CU_TRY(ctx, cudaEventCreateWithFlags(&job->masks_ready, cudaEventDisableTiming | cudaEventBlockingSync));
+  job->pscan_used = 0;
+  job->pscan_flushed = 0;
+  job->pscan_pending.clear();
+  job->pscan_count = 0;
+  job->refine_pending = false;
+  job->pscan_active = true;
+  // the planes accumulate from scan to scan: zero them once (progressive zero-fills, :1876-1882)
+  cudaStream_t s = job->stream;
+  CU_TRY(ctx, cudaMemsetAsync(job->d_coef, 0, g.coef_bytes, s));
+  CU_TRY(ctx, cudaMemsetAsync(job->d_pstatus, 0, kMaxPscans * 16, s));
+  for (int c = 0; c < 3; c++) job->d_tail_zero[c] = false;
+  return GIDCUDA_OK;
+}
+
+extern "C" int gidcuda_job_pscan(gidcuda_job *job, const gidcuda_pscan_desc *scan, const uint8_t *data, size_t len) {
+  if (!job) return fail(nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "null job");
+  gidcuda_ctx *ctx = job->ctx;
+  if (job->state != gidcuda_job::BEGUN || !job->pscan_active)
+    return fail(ctx, GIDCUDA_ERR_STATE, "gidcuda_job_pscan: after gidcuda_job_pscan_reserve, before gidcuda_job_submit");
+  const Geometry &g = job->geo;
+  if (!scan || !data || len == 0 || scan->ss < 0 || scan->se > 63 || scan->ss > scan->se || scan->al < 0 || scan->al > 13 ||
+      scan->ah < 0 || scan->ah > 13)
+    return fail(ctx, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_job_pscan: null argument, no data, or a bad band / approximation");
+  const bool dc = scan->ss == 0;
+  if ((dc && scan->se != 0) || (!dc && scan->ncomp != 1) || (!dc && scan->ah != 0))
+    return fail(ctx, GIDCUDA_ERR_UNSUPPORTED,
+                "gidcuda_job_pscan: DC and AC terms in one scan, an AC scan with several components, or an AC refinement scan");
+  if (scan->ncomp != 1 && scan->ncomp != g.ncomp)
+    return fail(ctx, GIDCUDA_ERR_UNSUPPORTED, "gidcuda_job_pscan: a scan of %d of the frame's %d components", scan->ncomp, g.ncomp);
+  for (int i = 0; i < scan->ncomp; i++)
+    if (scan->comp[i] < 0 || scan->comp[i] >= g.ncomp || (scan->ncomp > 1 && scan->comp[i] != i))
+      return fail(ctx, GIDCUDA_ERR_UNSUPPORTED, "gidcuda_job_pscan: components out of order or out of range");
+  if (job->pscan_count >= kMaxPscans) return fail(ctx, GIDCUDA_ERR_UNSUPPORTED, "gidcuda_job_pscan: more than %u scans", kMaxPscans);
+  const size_t slice = kPscanTables + round_up(len + 64, 256);
+  if (job->pscan_used + slice > job->cap_pscan)
+    return fail(ctx, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_job_pscan: the scans exceed what gidcuda_job_pscan_reserve was told");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  uint8_t *h = job->h_pscan + job->pscan_used, *d = job->d_pscan + job->pscan_used;
+  gidk::PscanArgs a;
+  memset(&a, 0, sizeof a);
+  a.mode = dc ? (scan->ah == 0 ? 1u : 3u) : 2u;
+  gidk::HuffDev *tabs = reinterpret_cast<gidk::HuffDev *>(h);
+  memset(tabs, 0, 6 * sizeof(gidk::HuffDev));
+  if (a.mode != 3u)
+    for (int i = 0; i < scan->ncomp; i++) {
+      const int c = scan->comp[i];
+      if (!build_huff_dev(dc ? scan->dc[c] : scan->ac[c], &tabs[dc ? c : 3 + c]))
+        return fail(ctx, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_job_pscan: Huffman table of component %d is not a prefix code", c);
+    }
+  memcpy(h + kPscanTables, data, len);
+  memset(h + kPscanTables + len, 0xFF, slice - kPscanTables - len);
+  a.data = d + kPscanTables;
+  a.tables = reinterpret_cast<const gidk::HuffDev *>(d);
+  a.ncomp = (uint32_t)scan->ncomp;
+  uint32_t bpm = 0;
+  for (int c = 0; c < g.ncomp; c++) {
+    a.plane[c] = reinterpret_cast<int16_t *>(job->d_coef + g.plane_off[c]);
+    a.row_blocks[c] = (uint32_t)g.bx[c];
+    a.h[c] = job->desc.samp_h[c];
+    a.v[c] = job->desc.samp_v[c];
+    a.limbits[c] = gidk::fast_coef_bits(&job->desc, c);
+    bpm += (uint32_t)(a.h[c] * a.v[c]);
+  }
+  for (int i = 0; i < scan->ncomp; i++) a.comps[i] = (uint32_t)scan->comp[i];
+  if (scan->ncomp > 1) {
+    if (bpm > 12) return fail(ctx, GIDCUDA_ERR_UNSUPPORTED, "gidcuda_job_pscan: %u blocks per MCU", bpm);
+    a.bpm = bpm;
+    a.mcux = (uint32_t)g.mcux;
+    a.total_blocks = (uint32_t)g.mcux * (uint32_t)g.mcuy * bpm;
+  } else {
+    // a single-component scan walks the component's own block grid (8 x 8 MCUs, :1952-1971)
+    const int c = scan->comp[0];
+    const int wc = (job->desc.width * job->desc.samp_h[c] + g.hmax - 1) / g.hmax;
+    const int hc = (job->desc.height * job->desc.samp_v[c] + g.vmax - 1) / g.vmax;
+    a.bpm = 1;
+    a.nbx = (uint32_t)((wc + 7) / 8);
+    a.total_blocks = a.nbx * (uint32_t)((hc + 7) / 8);
+  }
+  a.ss = (uint32_t)scan->ss;
+  a.se = (uint32_t)scan->se;
+  a.al = (uint32_t)scan->al;
+  a.nbits = (uint32_t)(len * 8);
+  a.status = job->d_pstatus + 4 * job->pscan_count;
+  if (a.mode == 3u) {
+    if ((uint64_t)len * 8 < a.total_blocks)
+      return fail(ctx, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_job_pscan: a DC refinement scan of %zu bytes for %u blocks", len, a.total_blocks);
+    if ((uint64_t)len * 8 - a.total_blocks >= 8)  // whole bytes left over: the serial decoder's case
+      return fail(ctx, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_job_pscan: a DC refinement scan of %zu bytes for %u blocks", len, a.total_blocks);
+    job->pscan_expected[job->pscan_count] = 0;
+    job->pscan_nbits[job->pscan_count] = 0;
+  } else {
+    a.sub_bits = (uint64_t)len * 8 > (uint64_t)a.total_blocks * kDenseBitsPerBlock ? kSubsequenceBitsDense : kSubsequenceBits;
+    a.nsub = (uint32_t)((len * 8 + a.sub_bits - 1) / a.sub_bits);
+    job->pscan_expected[job->pscan_count] = a.total_blocks;
+    job->pscan_nbits[job->pscan_count] = a.nbits;
+  }
+  job->pscan_pending.push_back(a);  // on the stream at the next pscan_flush
+  job->pscan_used += slice;
+  job->pscan_count++;
+  return GIDCUDA_OK;
+}
+
+// The staged scans onto the stream: one copy, then every scan's launches in order.
+static int pscan_flush(gidcuda_job *job) {
+  gidcuda_ctx *ctx = job->ctx;
+  if (job->pscan_pending.empty()) return GIDCUDA_OK;
+  cudaStream_t s = job->stream;
+  size_t most = 0;
+  for (const gidk::PscanArgs &a : job->pscan_pending) most = std::max(most, (size_t)a.nsub);
+  const size_t sync_bytes = most * (8 + 8 + 16 + 16) + 1024;
+  if (job->cap_sync < sync_bytes) {
+    CU_TRY(ctx, cudaStreamSynchronize(s));  // (the arrays of an earlier scan may still be in use on the stream)
+    if (job->d_sync) cudaFree(job->d_sync);
+    job->d_sync = nullptr;
+    job->cap_sync = 0;
+    const size_t cap = sync_bytes + sync_bytes / 2;
+    CU_TRY(ctx, cudaMalloc((void **)&job->d_sync, cap));
+    job->cap_sync = cap;
+  }
+  CU_TRY(ctx, cudaMemcpyAsync(job->d_pscan + job->pscan_flushed, job->h_pscan + job->pscan_flushed,
+                              job->pscan_used - job->pscan_flushed, cudaMemcpyHostToDevice, s));
+  job->pscan_flushed = job->pscan_used;
+  for (gidk::PscanArgs &a : job->pscan_pending) {
+    if (a.mode == 3u) {
+      CU_TRY(ctx, gidk::launch_pscan_dc_refine(a, s));
+    } else {
+      const size_t n = a.nsub;
+      a.entry = reinterpret_cast<uint64_t *>(job->d_sync);
+      a.exit_ = a.entry + n;
+      a.tuple = reinterpret_cast<int4 *>(job->d_sync + round_up(16 * n, 256));
+      a.prefix = a.tuple + n;
+      CU_TRY(ctx, gidk::launch_pscan(a, s));
+    }
+  }
+  job->pscan_pending.clear();
+  return GIDCUDA_OK;
+}
+
+// flags and block counts of the scans whose status words are in h_pstatus
+static int pscan_verdict(gidcuda_job *job) {
+  for (uint32_t i = 0; i < job->pscan_count; i++) {
+    const uint32_t *st = job->h_pstatus + 4 * i;
+    // a valid scan ends within a byte of its last code word (1-bits pad it to the marker, :640-662): whole
+    // bytes left over, or code words fed from the padding, are what the serial decoder decides about
+    const bool ends_badly = job->pscan_nbits[i] != 0 &&
+                            (st[3] == 0 || st[3] - 1u > job->pscan_nbits[i] || job->pscan_nbits[i] - (st[3] - 1u) >= 8u);
+    if (st[0] != 0 || (job->pscan_expected[i] != 0 && st[2] != job->pscan_expected[i]) || ends_badly) {
+      job->state = gidcuda_job::BEGUN;
+      job->pscan_active = false;
+      return fail(job->ctx, GIDCUDA_ERR_DATA,
+                  "device entropy decoder: scan %u of the progressive frame left to the host decoder (flags %u, %u of %u blocks)",
+                  i, st[0], st[2], job->pscan_expected[i]);
+    }
+  }
+  return GIDCUDA_OK;
+}
+
+extern "C" int gidcuda_job_pscan_masks(gidcuda_job *job, int comp, const uint64_t **masks, int32_t *nblocks) {
+  if (!job) return fail(nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "null job");
+  gidcuda_ctx *ctx = job->ctx;
+  if (job->state != gidcuda_job::BEGUN || !job->pscan_active)
+    return fail(ctx, GIDCUDA_ERR_STATE, "gidcuda_job_pscan_masks: after gidcuda_job_pscan_reserve, before gidcuda_job_submit");
+  if (comp < 0 || comp >= job->geo.ncomp || !masks)
+    return fail(ctx, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_job_pscan_masks: bad component or null argument");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  const Geometry &g = job->geo;
+  cudaStream_t s = job->stream;
+  const uint32_t nb = (uint32_t)g.bx[comp] * (uint32_t)g.by[comp];
+  {
+    const int rcf = pscan_flush(job);
+    if (rcf != GIDCUDA_OK) return rcf;
+  }
+  CU_TRY(ctx, gidk::launch_pscan_masks(reinterpret_cast<const int16_t *>(job->d_coef + g.plane_off[comp]), nb, job->d_masks, s));
+  // The host thread has nothing to do for this frame until the device has caught up with its first scans
+  // (a millisecond or two): it SLEEPS on a blocking event rather than spin, so that a caller with more
+  // threads than cores keeps the cores busy with other frames meanwhile.  The copies back are only issued
+  // once the kernels are done: queued earlier they would sit at the head of the device-to-host engine's FIFO
+  // for that millisecond and hold up the pixels of every other frame behind them.
+  CU_TRY(ctx, cudaEventRecord(job->masks_ready, s));
+  CU_TRY(ctx, cudaEventSynchronize(job->masks_ready));
+  CU_TRY(ctx, cudaMemcpyAsync(job->h_masks, job->d_masks, (size_t)nb * 8, cudaMemcpyDeviceToHost, s));
+  CU_TRY(ctx, cudaMemcpyAsync(job->h_pstatus, job->d_pstatus, (size_t)job->pscan_count * 16, cudaMemcpyDeviceToHost, s));
+  CU_TRY(ctx, cudaStreamSynchronize(s));
+  const int rc = pscan_verdict(job);   // a history built on a scan the device gave up on is worthless
+  if (rc != GIDCUDA_OK) return rc;
+  *masks = job->h_masks;
+  if (nblocks) *nblocks = (int32_t)nb;
+  return GIDCUDA_OK;
+}
+
+extern "C" int gidcuda_job_pscan_refine(gidcuda_job *job, int comp, uint64_t **corr, uint64_t **newpos, uint64_t **newneg) {
+  if (!job) return fail(nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "null job");
+  gidcuda_ctx *ctx = job->ctx;
+  if (job->state != gidcuda_job::BEGUN || !job->pscan_active)
+    return fail(ctx, GIDCUDA_ERR_STATE, "gidcuda_job_pscan_refine: after gidcuda_job_pscan_reserve, before gidcuda_job_submit");
+  if (comp < 0 || comp >= job->geo.ncomp || !corr || !newpos || !newneg)
+    return fail(ctx, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_job_pscan_refine: bad component or null argument");
+  if (job->refine_pending) {  // the arrays of the previous refinement scan are still being copied
+    CU_TRY(ctx, cudaEventSynchronize(job->refine_copied));
+    job->refine_pending = false;
+  }
+  const size_t nb = (size_t)job->geo.bx[comp] * job->geo.by[comp];
+  memset(job->h_refine, 0, nb * 24);
+  *corr = job->h_refine;
+  *newpos = job->h_refine + nb;
+  *newneg = job->h_refine + 2 * nb;
+  return GIDCUDA_OK;
+}
+
+extern "C" int gidcuda_job_pscan_refine_commit(gidcuda_job *job, int comp, int al) {
+  if (!job) return fail(nullptr, GIDCUDA_ERR_BAD_ARGUMENT, "null job");
+  gidcuda_ctx *ctx = job->ctx;
+  if (job->state != gidcuda_job::BEGUN || !job->pscan_active)
+    return fail(ctx, GIDCUDA_ERR_STATE, "gidcuda_job_pscan_refine_commit: after gidcuda_job_pscan_refine");
+  if (comp < 0 || comp >= job->geo.ncomp || al < 0 || al > 13)
+    return fail(ctx, GIDCUDA_ERR_BAD_ARGUMENT, "gidcuda_job_pscan_refine_commit: bad component or approximation");
+  CU_TRY(ctx, cudaSetDevice(ctx->device));
+  const Geometry &g = job->geo;
+  cudaStream_t s = job->stream;
+  const size_t nb = (size_t)g.bx[comp] * g.by[comp];
+  {
+    const int rcf = pscan_flush(job);  // scans staged before this refinement run before it
+    if (rcf != GIDCUDA_OK) return rcf;
+  }
+  CU_TRY(ctx, cudaMemcpyAsync(job->d_refine, job->h_refine, nb * 24, cudaMemcpyHostToDevice, s));
+  CU_TRY(ctx, cudaEventRecord(job->refine_copied, s));
+  job->refine_pending = true;
+  CU_TRY(ctx, gidk::launch_pscan_apply(reinterpret_cast<int16_t *>(job->d_coef + g.plane_off[comp]), (uint32_t)nb, job->d_refine,
+                                       job->d_refine + nb, job->d_refine + 2 * nb, (uint32_t)al, s));
+  return GIDCUDA_OK;
+}
+
+int job_submit_pscan(gidcuda_job *job, cudaStream_t s) {
+  gidcuda_ctx *ctx = job->ctx;
+  if (job->pscan_count == 0) return fail(ctx, GIDCUDA_ERR_STATE, "gidcuda_job_submit: a progressive frame without scans");
+  {
+    const int rcf = pscan_flush(job);
+    if (rcf != GIDCUDA_OK) return rcf;
+  }
+  CU_TRY(ctx, cudaMemcpyAsync(job->h_pstatus, job->d_pstatus, (size_t)job->pscan_count * 16, cudaMemcpyDeviceToHost, s));
+  return GIDCUDA_OK;
+}
+
+int job_finish_pscan(gidcuda_job *job) {
+  const int rc = pscan_verdict(job);
+  job->pscan_active = false;  // a re-submission after a host decode takes planes / records
+  return rc;
+}

@@ -110,6 +110,39 @@ cudaError_t launch_huffman_whole(const WholeArgs &a, cudaStream_t stream);
 cudaError_t launch_huffman_finish(const WholeArgs &a, cudaStream_t stream);  // scan + output over the chain as it stands
 inline int launches_huffman_whole() { return 4; }
 
+// ... and the scans of PROGRESSIVE frames (entropy_kernel.cu, "progressive scans"): first scans (DC first,
+// AC first) through the same self-synchronising decoder, DC refinement (one bit per block), and -- for AC
+// refinement, which only the host can decode (see the kernel file) -- the non-zero history of a component for
+// the host and the host's verdict applied to the planes.
+struct PscanArgs {
+  const uint8_t *data;      // the scan's bytes, stuffing removed, padded with FF
+  const HuffDev *tables;    // [6]: DC tables of frame components 0 .. 2, then their AC tables
+  uint64_t *entry, *exit_;  // [nsub]
+  int4 *tuple, *prefix;     // [nsub]
+  int16_t *plane[3];        // the frame's planes (accumulating from scan to scan)
+  uint32_t row_blocks[3];   // blocks per block row of each plane (MCU-padded)
+  int32_t h[3], v[3];       // sampling of the frame's components
+  int32_t limbits[3];       // as in ScanArgs
+  uint32_t mode;            // 1 = DC first, 2 = AC first, 3 = DC refinement
+  uint32_t ncomp, comps[3]; // components of the scan (frame indices)
+  uint32_t bpm;             // blocks per MCU of an interleaved scan; 1 for a single-component scan
+  uint32_t mcux;            // interleaved: MCUs per row
+  uint32_t nbx;             // single component: blocks per row of its OWN grid (8x8 MCUs, :1952-1971)
+  uint32_t total_blocks;
+  uint32_t ss, se, al;
+  uint32_t nbits, sub_bits, nsub;
+  uint32_t *status;         // 4 words of this scan: [0] flags (2 chain, 8 undecodable), [2] blocks stored,
+                            // [3] 1 + the bit position after the last code word of the scan
+};
+cudaError_t launch_pscan(const PscanArgs &a, cudaStream_t stream);             // modes 1, 2: sync x2, scan, output
+cudaError_t launch_pscan_dc_refine(const PscanArgs &a, cudaStream_t stream);   // mode 3
+// masks[b], b = block index in the (padded) plane: bit k = coefficient at zig-zag position k is non-zero
+cudaError_t launch_pscan_masks(const int16_t *plane, uint32_t nblocks, uint64_t *masks, cudaStream_t stream);
+// AC refinement decoded by the host (Ah > 0, :1560-1690): corr = positions that received a correction bit of 1,
+// newpos / newneg = positions that became +-(1 << al); all three indexed like masks
+cudaError_t launch_pscan_apply(int16_t *plane, uint32_t nblocks, const uint64_t *corr, const uint64_t *newpos,
+                               const uint64_t *newneg, uint32_t al, cudaStream_t stream);
+
 // One-time kernel attribute set-up (dynamic shared memory opt-in).
 cudaError_t init_kernels();
 

@@ -103,6 +103,10 @@ struct Image_Descriptor {
   // Streams the device decoder declines (damaged or unusual ones) are decoded on the host as
   // before, so results and error behaviour do not depend on this switch.
   bool device_entropy = true;
+  // ... and so are the first scans and the DC refinement scans of PROGRESSIVE files of at least this many
+  // bytes (gidcuda_job_pscan*); their AC refinement scans are decoded on the host from the non-zero history
+  // the device hands back.  0 bytes: every progressive file; a negative value: none.
+  long device_progressive_min_bytes = 96 * 1024;
   // Progressive scans (without restart markers) are read through the 64-bit bit buffer; false =
   // through the byte-wise one that mirrors the reference's.  Same planes, same stream position
   // afterwards, same exceptions (tests compare the two on damaged files).
@@ -136,6 +140,9 @@ namespace detail {
 // How many baseline scans were decoded restart-interval-parallel / fell back to the serial loop
 // after the parallel attempt met something unusual (process-wide; tests and statistics).
 extern std::atomic<long> parallel_scans, parallel_fallbacks;
+// progressive frames on the device: host time (ns) spent waiting for the non-zero history / decoding AC
+// refinement scans / queueing first scans (gidhost_counter "ns_masks_wait", "ns_refine_host", "ns_pscan_queue")
+extern std::atomic<long> ns_masks_wait, ns_refine_host, ns_pscan_queue;
 
 // Result of the device reconstruction: top-down RGB8 rows in pinned host memory
 // owned by the library until release().

@@ -40,6 +40,7 @@ typedef struct gidhost_batch_stats {
 
 int gidhost_status_of_current_exception(char *err, size_t errlen);  // gid_jpeg_host.cpp
 int gidhost_option_device_entropy(void);
+long gidhost_option_device_progressive_min_bytes(void);
 int gidhost_option_sparse_input(void);
 int gidhost_option_apply_orientation(void);
 
@@ -170,6 +171,7 @@ int gidhost_batch_decode(gidhost_batch *b, int32_t n, const uint8_t *const *data
         im.device = dev;
         im.entropy_threads = per_image;
         im.device_entropy = gidhost_option_device_entropy() != 0;
+        im.device_progressive_min_bytes = gidhost_option_device_progressive_min_bytes();
         im.sparse_input = gidhost_option_sparse_input() != 0;
         im.apply_orientation = gidhost_option_apply_orientation() != 0;
         if ((size_t)3 * (size_t)im.width * (size_t)im.height > rgb_capacity[i])

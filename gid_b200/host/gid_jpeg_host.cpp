@@ -55,6 +55,7 @@ void Load_Image_Header(Image_Descriptor &image, Stream &from, bool /*try_tga*/) 
 namespace detail {
 
 std::atomic<long> parallel_scans{0}, parallel_fallbacks{0}, device_scans{0}, device_scan_fallbacks{0};
+std::atomic<long> ns_masks_wait{0}, ns_refine_host{0}, ns_pscan_queue{0};
 
 // Frame descriptor from the header: geometry now, tables when the first scan starts.
 static void describe_frame(const Image_Descriptor &image, gidcuda_frame_desc *desc, int comp_of[3]) {
@@ -244,6 +245,44 @@ void *decode_and_submit(Image_Descriptor &image, void *ctx_, const std::function
         device_scans++;
         return true;
       };
+    if (image.device_entropy && image.progressive && image.device_progressive_min_bytes >= 0) {
+      dec.device_pscan_min_bytes = (size_t)image.device_progressive_min_bytes;
+      dec.device_pscan_begin = [&](size_t bytes) { return gidcuda_job_pscan_reserve(job, bytes) == GIDCUDA_OK; };
+      dec.device_pscan = [&](const Decoder::DevicePscan &ds) {
+        gidcuda_pscan_desc pd;
+        memset(&pd, 0, sizeof pd);
+        pd.ncomp = ds.ncomps;
+        for (int k = 0; k < ds.ncomps; k++) pd.comp[k] = comp_of[ds.comps[k]];
+        pd.ss = ds.ss; pd.se = ds.se; pd.ah = ds.ah; pd.al = ds.al;
+        for (int c = 0; c < 3; c++) {
+          if (!image.info[c].present) continue;
+          gidcuda_huffman_table *t[2] = {&pd.dc[comp_of[c]], &pd.ac[comp_of[c]]};
+          const std::vector<uint8_t> *bits[2] = {ds.dc_bits[c], ds.ac_bits[c]}, *vals[2] = {ds.dc_vals[c], ds.ac_vals[c]};
+          for (int k = 0; k < 2; k++) {
+            if (!bits[k]) continue;
+            if (bits[k]->size() != 16 || vals[k]->size() > 256) return false;
+            memcpy(t[k]->counts, bits[k]->data(), 16);
+            memcpy(t[k]->symbols, vals[k]->data(), vals[k]->size());
+          }
+        }
+        // (a table the device cannot take, a scan it does not cover: the host decodes the frame)
+        return gidcuda_job_pscan(job, &pd, ds.data, ds.len) == GIDCUDA_OK;
+      };
+      dec.device_masks = [&](int c, int32_t *blocks_x, int32_t *nblocks) {
+        const uint64_t *m = nullptr;
+        int32_t by = 0;
+        if (gidcuda_plane_geometry(&desc, comp_of[c], blocks_x, &by) != GIDCUDA_OK ||
+            gidcuda_job_pscan_masks(job, comp_of[c], &m, nblocks) != GIDCUDA_OK)
+          throw Decoder::device_declined();
+        return m;
+      };
+      dec.device_refine_begin = [&](int c, uint64_t **corr, uint64_t **newpos, uint64_t **newneg) {
+        if (gidcuda_job_pscan_refine(job, comp_of[c], corr, newpos, newneg) != GIDCUDA_OK) throw Decoder::device_declined();
+      };
+      dec.device_refine_commit = [&](int c, int al) {
+        if (gidcuda_job_pscan_refine_commit(job, comp_of[c], al) != GIDCUDA_OK) throw Decoder::device_declined();
+      };
+    }
     // A baseline component outgrew its record buffer (more than 32 non-zero coefficients per
     // block on average): replay its records into the dense plane and carry on there.
     dec.spill = [&](int c) {
@@ -264,8 +303,29 @@ void *decode_and_submit(Image_Descriptor &image, void *ctx_, const std::function
       }
       k.on = false;
     };
-    dec.run();
+    try {
+      dec.run();
+    } catch (const Decoder::device_declined &) {
+      // a scan of the progressive frame does not fit the device path: the host decoder takes the whole frame
+      device_scan_fallbacks++;
+      if (job) gidcuda_job_release(job);
+      job = nullptr;
+      image.stream->pos = image.stream_pos_after_header;
+      const long keep = image.device_progressive_min_bytes;
+      image.device_progressive_min_bytes = -1;
+      const std::function<void(int)> no_feedback = [](int) {};
+      void *again = nullptr;
+      try {
+        again = decode_and_submit(image, ctx_, no_feedback, out, out_capacity);
+      } catch (...) {
+        image.device_progressive_min_bytes = keep;
+        throw;
+      }
+      image.device_progressive_min_bytes = keep;
+      return again;
+    }
     if (!job) throw error_in_image_data("JPEG: no scan in the image");
+    if (dec.device_progressive) device_scans++;
     for (int c = 0; c < 3; c++) {
       if (!image.info[c].present || dec.device_scanned) continue;
       RecordSink &k = dec.sink[c];
@@ -491,6 +551,7 @@ static int g_sparse_input = 1;
 static int g_entropy_threads = 1;
 static int g_device_entropy = 1;
 static int g_wide_bit_buffer = 1;  // "wide_bit_buffer": Image_Descriptor::wide_bit_buffer
+static long g_device_progressive_min_bytes = 96 * 1024;  // "device_progressive_min_bytes": Image_Descriptor::device_progressive_min_bytes
 static int g_apply_orientation = 0;  // "apply_orientation": gidhost_batch_decode writes the pixels turned as the EXIF tag says
 int gidhost_set_option(const char *name, int value) {
   if (name && strcmp(name, "sparse_input") == 0) {
@@ -507,6 +568,10 @@ int gidhost_set_option(const char *name, int value) {
   }
   if (name && strcmp(name, "device_entropy") == 0) {
     g_device_entropy = value != 0;
+    return GIDHOST_OK;
+  }
+  if (name && strcmp(name, "device_progressive_min_bytes") == 0) {
+    g_device_progressive_min_bytes = value;
     return GIDHOST_OK;
   }
   if (name && strcmp(name, "entropy_threads") == 0 && value >= 0) {
@@ -527,6 +592,7 @@ int gidhost_decode_rgb(const uint8_t *data, size_t len, int device, uint32_t mod
     im.sparse_input = g_sparse_input != 0;
     im.entropy_threads = g_entropy_threads;
     im.device_entropy = g_device_entropy != 0;
+    im.device_progressive_min_bytes = g_device_progressive_min_bytes;
     im.wide_bit_buffer = g_wide_bit_buffer != 0;
     const int W = gid::Pixel_Width(im), H = gid::Pixel_Height(im);
     if ((size_t)3 * (size_t)W * (size_t)H > rgb_capacity) {
@@ -587,6 +653,7 @@ void gidhost_free(void *p) { free(p); }
 // (for gid_batch.cpp) status code + message of the exception being handled
 int gidhost_status_of_current_exception(char *err, size_t errlen) { return status_of_exception(err, errlen); }
 int gidhost_option_device_entropy(void) { return g_device_entropy; }
+long gidhost_option_device_progressive_min_bytes(void) { return g_device_progressive_min_bytes; }
 int gidhost_option_sparse_input(void) { return g_sparse_input; }
 int gidhost_option_apply_orientation(void) { return g_apply_orientation; }
 
@@ -597,6 +664,9 @@ long gidhost_counter(const char *name) {
   if (name && strcmp(name, "parallel_fallbacks") == 0) return gid::detail::parallel_fallbacks.load();
   if (name && strcmp(name, "device_scans") == 0) return gid::detail::device_scans.load();
   if (name && strcmp(name, "device_scan_fallbacks") == 0) return gid::detail::device_scan_fallbacks.load();
+  if (name && strcmp(name, "ns_masks_wait") == 0) return gid::detail::ns_masks_wait.load();
+  if (name && strcmp(name, "ns_refine_host") == 0) return gid::detail::ns_refine_host.load();
+  if (name && strcmp(name, "ns_pscan_queue") == 0) return gid::detail::ns_pscan_queue.load();
   return -1;
 }
 

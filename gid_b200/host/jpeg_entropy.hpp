@@ -474,6 +474,7 @@ struct Decoder {
   // up here rather than in begin_frame, so that a scan decoded on the device never reserves them)
   std::function<void()> prepare_host_output;
   bool host_output_ready = false;
+  bool frame_begun = false;
   void ensure_host_output() {
     if (host_output_ready) return;
     host_output_ready = true;
@@ -988,7 +989,193 @@ struct Decoder {
     }
   }
 
+  // ---- the scans of a progressive frame handed to the device (gidcuda_job_pscan*, include/gidcuda.h) --------
+  // First scans and DC refinement scans go there as compressed bytes; AC refinement scans are decoded here
+  // from the non-zero history alone (no coefficient values are needed to know which bits a refinement scan
+  // reads, :1560-1690) and answered with three bit masks per block.  Decided at the frame's first scan; if a
+  // later scan does not fit the device path the whole frame is handed back (device_declined) and decoded here.
+  struct device_declined {};
+  struct DevicePscan {
+    int ncomps, comps[3], ss, se, ah, al;
+    const uint8_t *data;
+    size_t len;
+    const std::vector<uint8_t> *dc_bits[3], *dc_vals[3], *ac_bits[3], *ac_vals[3];
+  };
+  std::function<bool(size_t)> device_pscan_begin;                 // all entropy bytes of the frame fit in this many
+  std::function<bool(const DevicePscan &)> device_pscan;          // false: declined
+  std::function<const uint64_t *(int, int32_t *, int32_t *)> device_masks;  // (c, blocks_x, nblocks): waits; throws on error
+  std::function<void(int, uint64_t **, uint64_t **, uint64_t **)> device_refine_begin;
+  std::function<void(int, int)> device_refine_commit;             // (c, al)
+  size_t device_pscan_min_bytes = 96 * 1024;  // smaller files: the launches cost more than the host decoder
+  bool device_progressive = false;
+  std::vector<uint64_t> hist[3];              // non-zero history per component, indexed by block of the padded plane
+  int hist_bx[3] = {0, 0, 0};
+  bool hist_valid[3] = {false, false, false};
+  std::vector<uint8_t> unstuffed;
+
+  // AC refinement of one block from its non-zero history (the mirror's ac_refine with the coefficient values
+  // left out): which positions read a correction bit of 1, which became +-(1 << al).
+  template <class B> void ac_refine_history(B &bits, int c, uint64_t &mask, uint64_t &corr, uint64_t &newpos, uint64_t &newneg,
+                                            int ss, int se) {
+    int k = ss;
+    if (eobrun <= 0) {
+      const HuffTable &ac = table(1, ht_ac[c]);
+      for (; k <= se; k++) {
+        const int rs = bits.symbol(ac);
+        int rr = rs >> 4;
+        const int s = rs & 15;
+        int value = 0;
+        if (s == 0) {
+          if (rr < 15) {
+            eobrun = 1 << rr;
+            if (rr) eobrun += bits.get(rr);
+            break;
+          }
+        } else {
+          if (s != 1) throw error_in_image_data("JPEG: progressive: AC refinement with a size other than 1");
+          value = bits.get(1) ? 1 : -1;
+        }
+        for (; k <= se; k++) {
+          if ((mask >> k) & 1u) {
+            if (bits.get(1)) corr |= 1ull << k;
+          } else {
+            if (rr == 0) {
+              if (value) {
+                newpos |= 1ull << k;
+                if (value < 0) newneg |= 1ull << k;
+                mask |= 1ull << k;
+              }
+              break;
+            }
+            rr--;
+          }
+        }
+      }
+    }
+    if (eobrun > 0) {
+      if (k <= se) {
+        uint64_t m = mask & (~0ull << k) & (se >= 63 ? ~0ull : ((1ull << (se + 1)) - 1ull));
+        while (m) {
+          const int kk = __builtin_ctzll(m);
+          m &= m - 1;
+          if (bits.get(1)) corr |= 1ull << kk;
+        }
+      }
+      eobrun--;
+    }
+  }
+
+  void device_progressive_scan(const int *comps, int ncomps, int ss, int se, int ah, int al) {
+    if (im.restart_interval != 0) throw device_declined();
+    if (ss > se || se > 63) throw error_in_image_data("JPEG: progressive: bad spectral selection");
+    if (ss == 0 && se != 0) throw error_in_image_data("JPEG: progressive: DC and AC in the same scan");
+    if (ss > 0 && ncomps != 1) throw error_in_image_data("JPEG: progressive: AC scan with several components");
+    int ncomp_image = 0;
+    for (const Component_Info &ci : im.info) ncomp_image += ci.present ? 1 : 0;
+    if (ncomps != 1 && ncomps != ncomp_image) throw device_declined();
+    rst_count = 0;
+    next_rst = 0;
+    eobrun = 0;
+    const uint8_t *d = r.s.data;
+    const size_t size = r.s.size, start = r.s.pos;
+    if (ss > 0 && ah > 0) {
+      // AC refinement: decoded here from the history, through the wide bit buffer over the raw bytes
+      const int c = comps[0];
+      const auto t0 = std::chrono::steady_clock::now();
+      if (!hist_valid[c]) {
+        int32_t bx = 0, nb = 0;
+        const uint64_t *m = device_masks(c, &bx, &nb);
+        hist[c].assign(m, m + nb);
+        hist_bx[c] = bx;
+        hist_valid[c] = true;
+      }
+      const auto t1 = std::chrono::steady_clock::now();
+      detail::ns_masks_wait.fetch_add(std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count(), std::memory_order_relaxed);
+      uint64_t *corr = nullptr, *newpos = nullptr, *newneg = nullptr;
+      device_refine_begin(c, &corr, &newpos, &newneg);
+      const Component_Info &ci = im.info[c];
+      const int wc = (im.width * ci.samples_hor + im.max_samples_hor - 1) / im.max_samples_hor;
+      const int hc = (im.height * ci.samples_ver + im.max_samples_ver - 1) / im.max_samples_ver;
+      const int bw = (wc + 7) / 8, bh = (hc + 7) / 8;
+      WideBits wb(d, start, size);
+      wb.track = true;
+      for (int by = 0; by < bh; by++)
+        for (int bx = 0; bx < bw; bx++) {
+          const size_t pb = (size_t)by * (size_t)hist_bx[c] + (size_t)bx;
+          ac_refine_history(wb, c, hist[c][pb], corr[pb], newpos[pb], newneg[pb], ss, se);
+        }
+      device_refine_commit(c, al);
+      detail::ns_refine_host.fetch_add(
+          std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t1).count(), std::memory_order_relaxed);
+      uint8_t marker = 0;
+      r.s.pos = wb.reference_position(start, &marker);
+      bits.memo_marker = marker;
+      return;
+    }
+    // a first scan or a DC refinement scan: its bytes up to the marker that ends it, stuffing removed
+    const auto tq = std::chrono::steady_clock::now();
+    unstuffed.clear();
+    size_t i = start;
+    uint8_t m = 0;
+    for (;;) {
+      const void *f = i < size ? memchr(d + i, 0xFF, size - i) : nullptr;
+      if (!f) throw device_declined();  // no marker ends the scan: a truncated file is the host decoder's case
+      const size_t j = (size_t)((const uint8_t *)f - d);
+      unstuffed.insert(unstuffed.end(), d + i, d + j);
+      if (j + 1 >= size) throw device_declined();
+      m = d[j + 1];
+      if (m != 0) {
+        if (m >= M_RST0 && m <= M_RST7) throw device_declined();
+        i = j;
+        break;
+      }
+      unstuffed.push_back(0xFF);
+      i = j + 2;
+    }
+    if (unstuffed.empty()) throw device_declined();
+    const bool ok = m == M_EOI || m == M_COM || m == M_DHT || m == M_DRI || m == M_SOS;
+    if (!ok) throw device_declined();  // (the serial decoder raises on it: let it)
+    DevicePscan ds;
+    ds.ncomps = ncomps;
+    for (int k = 0; k < 3; k++) ds.comps[k] = k < ncomps ? comps[k] : 0;
+    ds.ss = ss; ds.se = se; ds.ah = ah; ds.al = al;
+    ds.data = unstuffed.data();
+    ds.len = unstuffed.size();
+    for (int c = 0; c < 3; c++) {
+      ds.dc_bits[c] = ds.dc_vals[c] = ds.ac_bits[c] = ds.ac_vals[c] = nullptr;
+      bool used = false;
+      for (int k = 0; k < ncomps; k++) used = used || comps[k] == c;
+      if (!used || !im.info[c].present) continue;
+      if (ss == 0 && ah == 0) {
+        table(0, ht_dc[c]);  // raises like the serial loop when the table is missing
+        ds.dc_bits[c] = &im.huff_bits[0][ht_dc[c]];
+        ds.dc_vals[c] = &im.huff_vals[0][ht_dc[c]];
+      } else if (ss > 0) {
+        table(1, ht_ac[c]);
+        ds.ac_bits[c] = &im.huff_bits[1][ht_ac[c]];
+        ds.ac_vals[c] = &im.huff_vals[1][ht_ac[c]];
+      }
+    }
+    if (!device_pscan(ds)) throw device_declined();
+    detail::ns_pscan_queue.fetch_add(
+        std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - tq).count(), std::memory_order_relaxed);
+    if (ss > 0) hist_valid[comps[0]] = false;  // new non-zero coefficients: the history of the component is the device's
+    r.s.pos = i + 2;                           // past the marker that ended the scan, which the segment loop takes up
+    bits.memo_marker = m;
+    device_scanned = true;
+    emit_feedback(std::min(49, 5 * (scans + 1)));
+  }
+
   void progressive_scan(const int *comps, int ncomps, int ss, int se, int ah, int al) {
+    if (scans == 0) {
+      // the whole frame on the device, or none of it: decided here, at its first scan
+      device_progressive = device_pscan && device_pscan_begin && im.restart_interval == 0 &&
+                           r.s.size >= device_pscan_min_bytes && device_pscan_begin(r.s.size - r.s.pos);
+    }
+    if (device_progressive) {
+      device_progressive_scan(comps, ncomps, ss, se, ah, al);
+      return;
+    }
     // Without restart markers the scan is read through the 64-bit buffer; afterwards the stream
     // position and the remembered marker are set to what the byte-wise buffer would have left
     // behind, so that the segment loop (and its errors on damaged files) carry on identically.
@@ -1095,7 +1282,10 @@ struct Decoder {
       if ((wc < 3 && ci.samples_hor != im.max_samples_hor) || (hc < 3 && ci.samples_ver != im.max_samples_ver))
         throw error_in_image_data("JPEG: component: sample dimension mismatch");
     }
-    if (!plane[0].base) begin_frame();
+    if (!frame_begun) {
+      begin_frame();
+      frame_begun = true;
+    }
     rebuild_tables();
     bits.reset();
     dc_pred[0] = dc_pred[1] = dc_pred[2] = 0;

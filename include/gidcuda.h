@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define GIDCUDA_ABI_VERSION 4
+#define GIDCUDA_ABI_VERSION 5
 
 /* Status codes.  The Ada binding maps DATA -> GID.error_in_image_data,
  * UNSUPPORTED -> GID.unsupported_image_subformat, the others ->
@@ -241,6 +241,46 @@ typedef struct gidcuda_scan_desc {
 } gidcuda_scan_desc;
 int gidcuda_job_scan(gidcuda_job *job, const gidcuda_scan_desc *scan, const uint8_t *data, size_t len,
                      const uint32_t *begin, const uint32_t *end);
+
+/* ---- the scans of a PROGRESSIVE frame on the device (optional) -------------------------------------
+ * Progressive_DCT_Decoding_Scan (gid-decoding_jpg.adb:1243-1747) is, like the baseline scan, the step BEFORE the
+ * path.  Its FIRST scans (Ah = 0: DC first :1263-1340, AC first :1381-1470) are ordinary Huffman streams and are
+ * decoded by the device's self-synchronising decoder straight into the job's planes, which accumulate from
+ * scan to scan in device memory; DC refinement scans (:1341-1380) are one bit per block and go there too.
+ * AC REFINEMENT scans (:1560-1690) cannot be decoded in parallel (inside an EOB run every block still reads one
+ * correction bit per coefficient that is already non-zero: the decoder's state includes the absolute block
+ * number) and stay on the host -- which needs no coefficient values for that, only which coefficients are
+ * non-zero: gidcuda_job_pscan_masks hands that history over (8 bytes per block), and the host answers with,
+ * per block, the positions that read a correction bit of 1 and the positions that became +-(1 << Al).
+ *   gidcuda_job_pscan_reserve   once per frame, before the first scan: an upper bound of the entropy-coded
+ *                               bytes of all its scans (the file size will do)
+ *   gidcuda_job_pscan           a first scan or a DC refinement scan: data = the scan's bytes up to the marker
+ *                               that ends it, stuffing removed (FF 00 -> FF); copied by the call, staged: the scans staged so
+ *                               far go to the device together (one copy, then their kernels) with the next
+ *                               _masks, _refine_commit or gidcuda_job_submit.
+ *                               Scans with restart markers are the host decoder's case.
+ *   gidcuda_job_pscan_masks     waits for the scans queued so far; masks[b], b = by * blocks_x + bx in the
+ *                               component's (MCU-padded) plane: bit k = the coefficient at zig-zag position k
+ *                               is non-zero.  GIDCUDA_ERR_DATA: see below.
+ *   gidcuda_job_pscan_refine    lends three zeroed arrays indexed like masks; _refine_commit(al) applies them:
+ *                               corr = read a correction bit of 1 (adds 1 << al away from zero unless bit al is
+ *                               set already, :1600-1612), newpos / newneg = became +(1 << al) / -(1 << al).
+ * After the last scan gidcuda_job_submit reconstructs from the device planes; no coefficient crosses the link.
+ * As with gidcuda_job_scan the device does not reproduce the reference's handling of damaged streams: a code
+ * in no table, a coefficient outside the band, a value outside the planes' range, a chain of states that does
+ * not settle, or a scan that does not fill its blocks make gidcuda_job_pscan_masks / gidcuda_job_wait return
+ * GIDCUDA_ERR_DATA; the caller then decodes the frame on the host and submits the job again. */
+typedef struct gidcuda_pscan_desc {
+  int32_t ncomp;                       /* components of the scan: 1, or all components of the frame */
+  int32_t comp[3];                     /* their indices in the frame */
+  int32_t ss, se, ah, al;              /* spectral selection, successive approximation (Read_SOS :1855-1944) */
+  gidcuda_huffman_table dc[3], ac[3];  /* per component of the FRAME; only those the scan uses are read */
+} gidcuda_pscan_desc;
+int gidcuda_job_pscan_reserve(gidcuda_job *job, size_t total_bytes);
+int gidcuda_job_pscan(gidcuda_job *job, const gidcuda_pscan_desc *scan, const uint8_t *data, size_t len);
+int gidcuda_job_pscan_masks(gidcuda_job *job, int comp, const uint64_t **masks, int32_t *nblocks);
+int gidcuda_job_pscan_refine(gidcuda_job *job, int comp, uint64_t **corr, uint64_t **newpos, uint64_t **newneg);
+int gidcuda_job_pscan_refine_commit(gidcuda_job *job, int comp, int al);
 
 /* Optional: let the pixels land in the CALLER's buffer instead of one owned by the job -- the
  * image buffer a client fills through Put_Pixel (test/benchmark.adb:67-81) handed over whole, so

@@ -24,7 +24,7 @@ def test_every_declared_symbol_is_exported(gidcuda_lib):
     for s in syms:
         assert hasattr(gidcuda_lib, s), s
     assert sorted(capi.EXPORTS) == syms
-    assert gidcuda_lib.gidcuda_abi_version() == 4
+    assert gidcuda_lib.gidcuda_abi_version() == 5
 
 
 def test_geometry_matches_gid(gidcuda_lib, synth):

@@ -520,7 +520,7 @@ def test_device_entropy_decode_noise_and_damage_without_restart_markers(host, or
 def test_configs_full_size_from_files(host, oracle, synth, gpu):
     """The five BASELINE.json configs at their full frame size as .jpg files through the file batch
     driver: device Huffman decoding (self-synchronising for configs 1-3, restart-interval-parallel for
-    config 4), host Huffman decoding for the progressive config 5; every image == GID's decode."""
+    config 4, first scans + DC refinement of the progressive config 5); every image == GID's decode."""
     from tests.test_gpu_parity import FULL_SIZE
     files, refs = [], []
     for name, w, h, samp, prog, ri in FULL_SIZE:
@@ -530,7 +530,7 @@ def test_configs_full_size_from_files(host, oracle, synth, gpu):
     scans, back = host.counter("device_scans"), host.counter("device_scan_fallbacks")
     imgs, st, stats = host.decode_batch(files, devices=(0,), threads=3)
     assert st == [0] * 5 and stats.images_failed == 0
-    assert host.counter("device_scans") == scans + 4 and host.counter("device_scan_fallbacks") == back
+    assert host.counter("device_scans") == scans + 5 and host.counter("device_scan_fallbacks") == back
     for k, (img, ref) in enumerate(zip(imgs, refs)):
         assert np.array_equal(img, ref), FULL_SIZE[k][0]
 
@@ -741,3 +741,127 @@ def test_dc_predictor_beyond_16_bits_is_reported(host, oracle, gpu):
     with pytest.raises(host.GidHostError) as e:
         host.decode_rgb(jpg)
     assert e.value.name == "unsupported_image_subformat" and "16 bits" in str(e.value)
+
+
+# --------------------------------------------------------------------------- progressive scans on the device
+
+
+@pytest.fixture
+def device_progressive(host):
+    """Every progressive file takes the device path, however small."""
+    host.set_option("device_progressive_min_bytes", 0)
+    yield
+    host.set_option("device_progressive_min_bytes", 96 * 1024)
+
+
+def _rgb_outcome(host, data):
+    try:
+        rgb, _ = host.decode_rgb(data)
+        return ("ok", hashlib.sha256(rgb.tobytes()).hexdigest())
+    except host.GidHostError as e:
+        return ("err", e.name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,ent", [(n, e) for n, e in _golden_files() if e["progressive"] or "libjpeg_script" in n],
+                         ids=[n for n, e in _golden_files() if e["progressive"] or "libjpeg_script" in n])
+def test_golden_progressive_files_on_the_device(host, oracle, gpu, device_progressive, name, ent):
+    """the first scans (DC first, AC first) and the DC refinement scans of a progressive file are
+    decoded by the device's self-synchronising decoder into planes that accumulate on the device; AC
+    refinement scans are decoded on the host from the non-zero history the device hands back and applied there.
+    No coefficient crosses the link; pixels == the committed hashes == GID's decode of the file."""
+    jpg = open(os.path.join(GOLDEN, ent["jpg"]), "rb").read()
+    scans, back = host.counter("device_scans"), host.counter("device_scan_fallbacks")
+    rgb, fb = host.decode_rgb(jpg)
+    assert host.counter("device_scans") == scans + 1 and host.counter("device_scan_fallbacks") == back, name
+    assert hashlib.sha256(rgb.tobytes()).hexdigest() == ent["rgb_sha256"], name
+    assert np.array_equal(rgb, oracle.decode(jpg)[1])
+    assert fb == sorted(fb) and fb[-1] == 100
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("samp,w,h,quality", [
+    ("420", 640, 480, 75), ("422", 512, 512, 75), ("444", 333, 217, 90), ("grey", 520, 300, 60), ("440", 200, 310, 75),
+    ("411", 1024, 256, 85), ("420", 1919, 1079, 75), ("422", 2048, 2048, 75), ("444", 17, 9, 75), ("420", 5, 5, 75),
+])
+def test_progressive_files_on_the_device_match_gid(host, oracle, synth, gpu, device_progressive, samp, w, h, quality):
+    """The default scan script (DC with Al = 1, AC 1-5, DC refinement, AC 6-63 with Al = 1, AC refinement) on
+    every sampling layout, partial MCUs (a single-component scan walks the component's own block grid,
+    :1952-1971), the full cfg5 frame."""
+    jpg, _ = synth.encode(pixels_for(synth, 13, w, h, samp), samp, quality=quality, progressive=True)
+    scans, back = host.counter("device_scans"), host.counter("device_scan_fallbacks")
+    rgb, _ = host.decode_rgb(jpg)
+    assert host.counter("device_scans") == scans + 1 and host.counter("device_scan_fallbacks") == back
+    assert np.array_equal(rgb, oracle.decode(jpg)[1])
+
+
+@pytest.mark.gpu
+def test_progressive_scan_scripts_on_the_device(host, oracle, synth, gpu, device_progressive):
+    """Other scripts: no successive approximation at all; narrow bands; two
+    refinement passes of the same band (libjpeg's default: Al = 2, then 1, then 0); a first scan of another
+    band AFTER a refinement of the same component (the host fetches the non-zero history again)."""
+    pix = pixels_for(synth, 14, 400, 304, "420")
+    Y, CB, CR = [0], [1], [2]
+    scripts = {
+        "no_approximation": [([0, 1, 2], 0, 0, 0, 0)] + [(c, 1, 63, 0, 0) for c in (Y, CB, CR)],
+        "libjpeg_default": [([0, 1, 2], 0, 0, 0, 1), (Y, 1, 5, 0, 2), (CR, 1, 63, 0, 1), (CB, 1, 63, 0, 1), (Y, 6, 63, 0, 2),
+                            (Y, 1, 63, 2, 1), ([0, 1, 2], 0, 0, 1, 0), (CR, 1, 63, 1, 0), (CB, 1, 63, 1, 0), (Y, 1, 63, 1, 0)],
+        "first_after_refinement": [([0, 1, 2], 0, 0, 0, 0), (Y, 1, 9, 0, 1), (Y, 1, 9, 1, 0), (Y, 10, 63, 0, 1), (Y, 10, 63, 1, 0),
+                                   (CB, 1, 63, 0, 0), (CR, 1, 63, 0, 0)],
+        "narrow_bands": [([0, 1, 2], 0, 0, 0, 0)] + [(c, a, b, 0, 0) for c in (Y, CB, CR) for a, b in ((1, 1), (2, 2), (3, 20), (21, 63))],
+    }
+    for name, sc in scripts.items():
+        jpg, _ = synth.encode(pix, "420", quality=85, progressive=True, scans=sc)
+        scans, back = host.counter("device_scans"), host.counter("device_scan_fallbacks")
+        rgb, _ = host.decode_rgb(jpg)
+        assert host.counter("device_scans") == scans + 1 and host.counter("device_scan_fallbacks") == back, name
+        assert np.array_equal(rgb, oracle.decode(jpg)[1]), name
+
+
+@pytest.mark.gpu
+def test_damaged_progressive_files_are_handed_back(host, oracle, synth, gpu, device_progressive):
+    """Anything the device decoders do not decode silently (a code in no table, a coefficient outside its
+    band, a scan that does not fill its blocks, a chain of states that does not settle, a truncated file)
+    hands the whole frame to the host decoder: the outcome -- pixels or exception class -- is the one the
+    host decoder alone gives."""
+    rng = np.random.default_rng(8)
+    jpg, _ = synth.encode(pixels_for(synth, 15, 320, 240, "420"), "420", progressive=True)
+    sos = jpg.index(b"\xff\xda")
+    same = handed_back = 0
+    for t in range(40):
+        bad = bytearray(jpg)
+        pos = int(rng.integers(sos + 10, len(bad) - 2))
+        kind = t % 4
+        if kind == 0:
+            bad[pos] = int(rng.integers(0, 255))
+        elif kind == 1:
+            del bad[pos]
+        elif kind == 2:
+            del bad[pos:pos + int(rng.integers(2, 40))]
+        else:
+            bad = bad[:pos]
+        bad = bytes(bad)
+        host.set_option("device_progressive_min_bytes", -1)
+        want = _rgb_outcome(host, bad)
+        host.set_option("device_progressive_min_bytes", 0)
+        back = host.counter("device_scan_fallbacks")
+        got = _rgb_outcome(host, bad)
+        handed_back += host.counter("device_scan_fallbacks") - back
+        assert got == want, (t, kind, got, want)
+        same += 1
+    assert same == 40 and handed_back >= 10
+
+
+@pytest.mark.gpu
+def test_progressive_files_in_the_file_batch_driver(host, oracle, synth, gpu):
+    """cfg5 through gidhost_batch_decode with the default threshold: the 2048 x 2048 files take the device
+    path, the small one the host decoder; pixels == GID's."""
+    big, _ = synth.encode(pixels_for(synth, 16, 2048, 2048, "422"), "422", progressive=True)
+    small, _ = synth.encode(pixels_for(synth, 17, 96, 64, "422"), "422", progressive=True)
+    files = [big, small, big, big]
+    scans = host.counter("device_scans")
+    imgs, st, _ = host.decode_batch(files, threads=3)
+    assert st == [0] * 4 and host.counter("device_scans") == scans + 3
+    ref_big, ref_small = oracle.decode(big)[1], oracle.decode(small)[1]
+    for f, img in zip(files, imgs):
+        assert np.array_equal(img, ref_big if f is big else ref_small)

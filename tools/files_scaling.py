@@ -8,6 +8,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import bench
 from gid_b200 import host_api
+if os.environ.get("FILES_BLOCKING_WAIT"):
+    from gid_b200 import capi as _capi
+    _capi.set_option("blocking_wait", int(os.environ["FILES_BLOCKING_WAIT"]))
 if os.environ.get("FILES_SPARSE_INPUT"):
     host_api.set_option("sparse_input", int(os.environ["FILES_SPARSE_INPUT"]))
 for wl in (sys.argv[1:] or ["cfg3"]):
@@ -32,6 +35,7 @@ for wl in (sys.argv[1:] or ["cfg3"]):
             c1 = [host_api.counter(k) for k in ("device_scans", "device_scan_fallbacks")]
         print(f"{wl}: threads {stats.threads:3d} (x{stats.entropy_threads} inside an image)  {w*h*per_call/1e6/stats.seconds:8.0f} MP/s  {1e3*stats.seconds/per_call*stats.threads:7.2f} ms per image per thread"
               f"   device scans {c1[0]-c0[0]}, left to the host {c1[1]-c0[1]}", flush=True)
-        if T >= ncpu:
+        tmax = int(os.environ.get("FILES_MAX_THREADS", ncpu))
+        if T >= tmax:
             break
-        T = min(ncpu, T * 2)
+        T = min(tmax, T * 2 if T < ncpu else T + ncpu // 2)
