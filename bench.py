@@ -77,7 +77,7 @@ def make_frames(workload: str, count: int, seed0: int):
 
 # JPEG-file form of each workload: (progressive, restart interval, files per call)
 FILE_FORM = {"cfg1": (False, 0, 256), "cfg2": (False, 0, 8), "cfg3": (False, 0, 64), "cfg4": (False, 64, 4),
-             "cfg5": (True, 0, 32)}
+             "cfg5": (True, 0, 128)}
 
 
 def make_files(workload: str, count: int, seed0: int) -> list[bytes]:

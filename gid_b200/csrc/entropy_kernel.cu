@@ -237,6 +237,7 @@ cudaError_t launch_huffman_intervals(const ScanArgs &a, cudaStream_t stream) {
 namespace {
 
 constexpr int kWindow = 256;
+static_assert(kWindow == (int)kPscanWindow, "the shim sizes the sync launches of progressive scans with kPscanWindow");
 // Re-decoding rounds per window.  A chain normally settles in 2 - 5 rounds.  Where it does not -- a
 // flat region (periodic bit stream: a decoder in the wrong phase stays there), or full blocks without
 // EOB at quality 100 (a wrong position inside the block survives until an EOB turns up) -- truth only
@@ -746,14 +747,32 @@ __device__ __forceinline__ uint64_t run_pscan_mode(const PscanArgs &a, const Huf
 }
 
 // Step 1, as huffman_sync_kernel.  A block starts in state (pos, 0, k0): k0 = 0 for DC scans, Ss for AC scans.
-__global__ void __launch_bounds__(kWindow) pscan_sync_kernel(PscanArgs a, uint32_t shift, int first) {
+// Which scan of the group a CTA works for, and which CTA of that scan it is: `first_cta[s]` = the launch's first
+// CTA of scan s (nscans + 1 entries).  The scan's arguments are copied to shared memory.
+__device__ __forceinline__ uint32_t pscan_pick(const PscanArgs *__restrict__ args, const uint32_t *__restrict__ first_cta,
+                                               uint32_t nscans, PscanArgs *sa) {
+  uint32_t sc = 0;
+  while (sc + 1 < nscans && blockIdx.x >= __ldg(first_cta + sc + 1)) sc++;
+  const uint32_t *src = reinterpret_cast<const uint32_t *>(args + sc);
+  uint32_t *dst = reinterpret_cast<uint32_t *>(sa);
+  for (uint32_t i = threadIdx.x; i < sizeof(PscanArgs) / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+  __syncthreads();
+  return blockIdx.x - __ldg(first_cta + sc);
+}
+
+__global__ void __launch_bounds__(kWindow) pscan_sync_kernel(const PscanArgs *__restrict__ args,
+                                                             const uint32_t *__restrict__ first_cta, uint32_t nscans,
+                                                             uint32_t shift, int first) {
   __shared__ HuffDev tabs[6];
   __shared__ uint8_t zz[64];
   __shared__ uint64_t X[kWindow];
   __shared__ PSlot slots[12];
+  __shared__ PscanArgs sa;
+  const uint32_t cta = pscan_pick(args, first_cta, nscans, &sa);
+  const PscanArgs &a = sa;
   pscan_load(a, tabs, zz, slots);
   const uint32_t t = threadIdx.x;
-  const uint32_t i = blockIdx.x * kWindow + t + shift;
+  const uint32_t i = cta * kWindow + t + shift;
   const bool active = i < a.nsub;
   const uint32_t k0 = a.mode == 2 ? a.ss : 0u;
   const uint64_t true_start = pack_state(0u, 0u, k0);
@@ -800,13 +819,17 @@ __global__ void __launch_bounds__(kWindow) pscan_sync_kernel(PscanArgs a, uint32
 }
 
 // Step 3, as huffman_output_kernel.
-__global__ void __launch_bounds__(128) pscan_output_kernel(PscanArgs a) {
+__global__ void __launch_bounds__(128) pscan_output_kernel(const PscanArgs *__restrict__ args,
+                                                           const uint32_t *__restrict__ first_cta, uint32_t nscans) {
   __shared__ HuffDev tabs[6];
   __shared__ uint8_t zz[64];
   __shared__ PSlot slots[12];
+  __shared__ PscanArgs sa;
+  const uint32_t cta = pscan_pick(args, first_cta, nscans, &sa);
+  const PscanArgs &a = sa;
   pscan_load(a, tabs, zz, slots);
   __syncthreads();
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t i = cta * blockDim.x + threadIdx.x;
   if (i >= a.nsub) return;
   const int4 pre = a.prefix[i];
   const uint32_t b = (uint32_t)pre.x;
@@ -834,9 +857,17 @@ __global__ void __launch_bounds__(128) pscan_output_kernel(PscanArgs a) {
 }
 
 // The prefix sums of step 2 over PscanArgs (same arrays as WholeArgs)
-__global__ void __launch_bounds__(1024) pscan_scan_kernel(PscanArgs a) {
+__global__ void __launch_bounds__(1024) pscan_scan_kernel(const PscanArgs *__restrict__ args) {
   __shared__ int4 warp_tot[32];
   __shared__ int4 carry_s;
+  __shared__ PscanArgs sa;
+  {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(args + blockIdx.x);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(&sa);
+    for (uint32_t i = threadIdx.x; i < sizeof(PscanArgs) / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  const PscanArgs &a = sa;
   const uint32_t t = threadIdx.x, lane = t & 31u, w = t >> 5;
   const int4 zero = make_int4(0, 0, 0, 0);
   if (t == 0) carry_s = zero;
@@ -955,13 +986,13 @@ cudaError_t launch_huffman_finish(const WholeArgs &a, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_pscan(const PscanArgs &a, cudaStream_t stream) {
-  if (a.nsub == 0) return cudaSuccess;
-  pscan_sync_kernel<<<(a.nsub + kWindow - 1) / kWindow, kWindow, 0, stream>>>(a, 0u, 1);
-  if (a.nsub > kWindow / 2)
-    pscan_sync_kernel<<<(a.nsub - kWindow / 2 + kWindow - 1) / kWindow, kWindow, 0, stream>>>(a, kWindow / 2, 0);
-  pscan_scan_kernel<<<1, 1024, 0, stream>>>(a);
-  pscan_output_kernel<<<(a.nsub + 127) / 128, 128, 0, stream>>>(a);
+cudaError_t launch_pscan_group(const PscanArgs *d_args, const uint32_t *d_tables, uint32_t nscans, uint32_t ctas_a,
+                               uint32_t ctas_b, uint32_t ctas_out, cudaStream_t stream) {
+  if (nscans == 0 || ctas_a == 0) return cudaSuccess;
+  pscan_sync_kernel<<<ctas_a, kWindow, 0, stream>>>(d_args, d_tables, nscans, 0u, 1);
+  if (ctas_b) pscan_sync_kernel<<<ctas_b, kWindow, 0, stream>>>(d_args, d_tables + (nscans + 1), nscans, kWindow / 2, 0);
+  pscan_scan_kernel<<<nscans, 1024, 0, stream>>>(d_args);
+  pscan_output_kernel<<<ctas_out, 128, 0, stream>>>(d_args, d_tables + 2 * (nscans + 1), nscans);
   return cudaGetLastError();
 }
 

@@ -102,6 +102,8 @@ struct gidcuda_job {
   // interleaved with that scan's kernels, would queue behind the copies of other frames' streams in the copy
   // engine's FIFO while those wait for their own kernels: the streams of concurrent frames serialise each other.
   std::vector<gidk::PscanArgs> pscan_pending;
+  uint8_t *h_pargs = nullptr, *d_pargs = nullptr;  // the arguments + CTA tables of the groups of a frame (pinned + device)
+  size_t pargs_used = 0;
   size_t pscan_flushed = 0;            // bytes of h_pscan already copied
   cudaEvent_t masks_ready = nullptr;   // blocking: the thread sleeps until the device has the history ready
   bool refine_pending = false;

@@ -382,12 +382,16 @@ int job_finish_scan(gidcuda_job *job) {
 
 constexpr uint32_t kMaxPscans = 64;
 constexpr size_t kPscanTables = (6 * sizeof(gidk::HuffDev) + 255) / 256 * 256;
+constexpr size_t kPargsBytes = kMaxPscans * (sizeof(gidk::PscanArgs) + 64) + 4096;
 
 void job_free_pscan(gidcuda_job *job) {
   if (job->h_pscan) cudaFreeHost(job->h_pscan);
   if (job->d_pscan) cudaFree(job->d_pscan);
   if (job->h_pstatus) cudaFreeHost(job->h_pstatus);
   if (job->d_pstatus) cudaFree(job->d_pstatus);
+  if (job->h_pargs) cudaFreeHost(job->h_pargs);
+  if (job->d_pargs) cudaFree(job->d_pargs);
+  job->h_pargs = job->d_pargs = nullptr;
   if (job->h_masks) cudaFreeHost(job->h_masks);
   if (job->d_masks) cudaFree(job->d_masks);
   if (job->h_refine) cudaFreeHost(job->h_refine);
@@ -426,6 +430,11 @@ extern "C" int gidcuda_job_pscan_reserve(gidcuda_job *job, size_t total_bytes) {
     CU_TRY(ctx, cudaHostAlloc((void **)&job->h_pstatus, kMaxPscans * 16, cudaHostAllocDefault));
     CU_TRY(ctx, cudaMalloc((void **)&job->d_pstatus, kMaxPscans * 16));
   }
+  if (!job->h_pargs) {
+    CU_TRY(ctx, cudaHostAlloc((void **)&job->h_pargs, kPargsBytes, cudaHostAllocDefault));
+    CU_TRY(ctx, cudaMalloc((void **)&job->d_pargs, kPargsBytes));
+  }
+  job->pargs_used = 0;
   size_t most = 0;
   const Geometry &g = job->geo;
   for (int c = 0; c < g.ncomp; c++) most = std::max(most, (size_t)g.bx[c] * g.by[c]);
@@ -547,16 +556,22 @@ extern "C" int gidcuda_job_pscan(gidcuda_job *job, const gidcuda_pscan_desc *sca
   return GIDCUDA_OK;
 }
 
-// The staged scans onto the stream: one copy, then every scan's launches in order.
+// The staged scans onto the stream: their bytes in one copy, the first scans (DC first, AC first) of the group
+// in four launches however many they are, then its DC refinement scans (which follow the DC first scan they
+// refine; the first scans of a group store into different components or bands and are independent).
 static int pscan_flush(gidcuda_job *job) {
   gidcuda_ctx *ctx = job->ctx;
   if (job->pscan_pending.empty()) return GIDCUDA_OK;
   cudaStream_t s = job->stream;
-  size_t most = 0;
-  for (const gidk::PscanArgs &a : job->pscan_pending) most = std::max(most, (size_t)a.nsub);
-  const size_t sync_bytes = most * (8 + 8 + 16 + 16) + 1024;
+  std::vector<gidk::PscanArgs *> decoded;
+  size_t sync_bytes = 0;
+  for (gidk::PscanArgs &a : job->pscan_pending)
+    if (a.mode != 3u) {
+      decoded.push_back(&a);
+      sync_bytes += round_up((size_t)a.nsub * (8 + 8 + 16 + 16), 256) + 512;
+    }
   if (job->cap_sync < sync_bytes) {
-    CU_TRY(ctx, cudaStreamSynchronize(s));  // (the arrays of an earlier scan may still be in use on the stream)
+    CU_TRY(ctx, cudaStreamSynchronize(s));  // (the arrays of an earlier group may still be in use on the stream)
     if (job->d_sync) cudaFree(job->d_sync);
     job->d_sync = nullptr;
     job->cap_sync = 0;
@@ -567,18 +582,42 @@ static int pscan_flush(gidcuda_job *job) {
   CU_TRY(ctx, cudaMemcpyAsync(job->d_pscan + job->pscan_flushed, job->h_pscan + job->pscan_flushed,
                               job->pscan_used - job->pscan_flushed, cudaMemcpyHostToDevice, s));
   job->pscan_flushed = job->pscan_used;
-  for (gidk::PscanArgs &a : job->pscan_pending) {
-    if (a.mode == 3u) {
-      CU_TRY(ctx, gidk::launch_pscan_dc_refine(a, s));
-    } else {
+  const uint32_t ns = (uint32_t)decoded.size();
+  if (ns) {
+    const size_t need = round_up(ns * sizeof(gidk::PscanArgs), 256) + round_up(3 * (ns + 1) * 4, 256);
+    if (job->pargs_used + need > kPargsBytes) return fail(ctx, GIDCUDA_ERR_UNSUPPORTED, "gidcuda_job_pscan: too many scans");
+    uint8_t *h = job->h_pargs + job->pargs_used, *d = job->d_pargs + job->pargs_used;
+    gidk::PscanArgs *ha = reinterpret_cast<gidk::PscanArgs *>(h);
+    uint32_t *ht = reinterpret_cast<uint32_t *>(h + round_up(ns * sizeof(gidk::PscanArgs), 256));
+    uint32_t ca = 0, cb = 0, co = 0;
+    size_t off = 0;
+    for (uint32_t k = 0; k < ns; k++) {
+      gidk::PscanArgs &a = *decoded[k];
       const size_t n = a.nsub;
-      a.entry = reinterpret_cast<uint64_t *>(job->d_sync);
+      a.entry = reinterpret_cast<uint64_t *>(job->d_sync + off);
       a.exit_ = a.entry + n;
-      a.tuple = reinterpret_cast<int4 *>(job->d_sync + round_up(16 * n, 256));
+      a.tuple = reinterpret_cast<int4 *>(job->d_sync + off + round_up(16 * n, 256));
       a.prefix = a.tuple + n;
-      CU_TRY(ctx, gidk::launch_pscan(a, s));
+      off += round_up(n * (8 + 8 + 16 + 16), 256) + 512;
+      ha[k] = a;
+      ht[k] = ca;
+      ht[(ns + 1) + k] = cb;
+      ht[2 * (ns + 1) + k] = co;
+      ca += (a.nsub + gidk::kPscanWindow - 1) / gidk::kPscanWindow;
+      cb += a.nsub > gidk::kPscanWindow / 2 ? (a.nsub - gidk::kPscanWindow / 2 + gidk::kPscanWindow - 1) / gidk::kPscanWindow : 0u;
+      co += (a.nsub + gidk::kPscanOutputThreads - 1) / gidk::kPscanOutputThreads;
     }
+    ht[ns] = ca;
+    ht[(ns + 1) + ns] = cb;
+    ht[2 * (ns + 1) + ns] = co;
+    CU_TRY(ctx, cudaMemcpyAsync(d, h, need, cudaMemcpyHostToDevice, s));
+    job->pargs_used += need;
+    CU_TRY(ctx, gidk::launch_pscan_group(reinterpret_cast<const gidk::PscanArgs *>(d),
+                                         reinterpret_cast<const uint32_t *>(d + round_up(ns * sizeof(gidk::PscanArgs), 256)), ns, ca,
+                                         cb, co, s));
   }
+  for (const gidk::PscanArgs &a : job->pscan_pending)
+    if (a.mode == 3u) CU_TRY(ctx, gidk::launch_pscan_dc_refine(a, s));
   job->pscan_pending.clear();
   return GIDCUDA_OK;
 }
@@ -619,12 +658,17 @@ extern "C" int gidcuda_job_pscan_masks(gidcuda_job *job, int comp, const uint64_
   }
   CU_TRY(ctx, gidk::launch_pscan_masks(reinterpret_cast<const int16_t *>(job->d_coef + g.plane_off[comp]), nb, job->d_masks, s));
   // The host thread has nothing to do for this frame until the device has caught up with its first scans
-  // (a millisecond or two): it SLEEPS on a blocking event rather than spin, so that a caller with more
-  // threads than cores keeps the cores busy with other frames meanwhile.  The copies back are only issued
-  // once the kernels are done: queued earlier they would sit at the head of the device-to-host engine's FIFO
-  // for that millisecond and hold up the pixels of every other frame behind them.
-  CU_TRY(ctx, cudaEventRecord(job->masks_ready, s));
-  CU_TRY(ctx, cudaEventSynchronize(job->masks_ready));
+  // (a quarter of a millisecond of kernels).  It spins, like gidcuda_job_wait -- measured: sleeping on a blocking
+  // event costs 2 - 6 ms per wake-up on these boxes, cfg5 from files 7.5 against 10.2 GP/s on 16 threads --
+  // unless the option "blocking_wait" says that the caller runs more threads than cores.
+  // The copies back are only issued once the kernels are done: queued earlier they would sit at the head of the
+  // device-to-host engine's FIFO meanwhile and hold up the pixels of every other frame behind them.
+  if (g_blocking_wait) {
+    CU_TRY(ctx, cudaEventRecord(job->masks_ready, s));
+    CU_TRY(ctx, cudaEventSynchronize(job->masks_ready));
+  } else {
+    CU_TRY(ctx, cudaStreamSynchronize(s));
+  }
   CU_TRY(ctx, cudaMemcpyAsync(job->h_masks, job->d_masks, (size_t)nb * 8, cudaMemcpyDeviceToHost, s));
   CU_TRY(ctx, cudaMemcpyAsync(job->h_pstatus, job->d_pstatus, (size_t)job->pscan_count * 16, cudaMemcpyDeviceToHost, s));
   CU_TRY(ctx, cudaStreamSynchronize(s));

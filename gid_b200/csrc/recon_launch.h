@@ -134,7 +134,13 @@ struct PscanArgs {
   uint32_t *status;         // 4 words of this scan: [0] flags (2 chain, 8 undecodable), [2] blocks stored,
                             // [3] 1 + the bit position after the last code word of the scan
 };
-cudaError_t launch_pscan(const PscanArgs &a, cudaStream_t stream);             // modes 1, 2: sync x2, scan, output
+constexpr uint32_t kPscanWindow = 256, kPscanOutputThreads = 128;  // CTA sizes of the sync and output launches
+// A GROUP of first scans (modes 1, 2) in four launches -- sync, sync (windows shifted), prefix sums, output --
+// however many scans it holds: d_args[nscans] in device memory, d_tables = three tables of nscans + 1 entries
+// each (first CTA of every scan in the first sync launch, in the second, in the output launch).  The scans of a
+// group store into different components or bands, so they are independent of each other.
+cudaError_t launch_pscan_group(const PscanArgs *d_args, const uint32_t *d_tables, uint32_t nscans, uint32_t ctas_a,
+                               uint32_t ctas_b, uint32_t ctas_out, cudaStream_t stream);
 cudaError_t launch_pscan_dc_refine(const PscanArgs &a, cudaStream_t stream);   // mode 3
 // masks[b], b = block index in the (padded) plane: bit k = coefficient at zig-zag position k is non-zero
 cudaError_t launch_pscan_masks(const int16_t *plane, uint32_t nblocks, uint64_t *masks, cudaStream_t stream);

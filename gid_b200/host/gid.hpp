@@ -142,7 +142,8 @@ namespace detail {
 extern std::atomic<long> parallel_scans, parallel_fallbacks;
 // progressive frames on the device: host time (ns) spent waiting for the non-zero history / decoding AC
 // refinement scans / queueing first scans (gidhost_counter "ns_masks_wait", "ns_refine_host", "ns_pscan_queue")
-extern std::atomic<long> ns_masks_wait, ns_refine_host, ns_pscan_queue;
+extern std::atomic<long> ns_masks_wait, ns_refine_host, ns_pscan_queue, selftest_refine_scans;
+extern int g_selftest_refine;
 
 // Result of the device reconstruction: top-down RGB8 rows in pinned host memory
 // owned by the library until release().

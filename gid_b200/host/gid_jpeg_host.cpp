@@ -55,7 +55,8 @@ void Load_Image_Header(Image_Descriptor &image, Stream &from, bool /*try_tga*/) 
 namespace detail {
 
 std::atomic<long> parallel_scans{0}, parallel_fallbacks{0}, device_scans{0}, device_scan_fallbacks{0};
-std::atomic<long> ns_masks_wait{0}, ns_refine_host{0}, ns_pscan_queue{0};
+std::atomic<long> ns_masks_wait{0}, ns_refine_host{0}, ns_pscan_queue{0}, selftest_refine_scans{0};
+int g_selftest_refine = 0;  // gidhost_set_option("selftest_refine"): 1 = on, 2 = on with the portable decoder
 
 // Frame descriptor from the header: geometry now, tables when the first scan starts.
 static void describe_frame(const Image_Descriptor &image, gidcuda_frame_desc *desc, int comp_of[3]) {
@@ -98,6 +99,8 @@ void decode_planes(Image_Descriptor &image, gidcuda_frame_desc *desc, int16_t *p
   Decoder dec(image, no_feedback);
   dec.parallel_threads = image.entropy_threads > 0 ? image.entropy_threads : (int)std::max(1u, std::thread::hardware_concurrency());
   dec.wide_progressive = image.wide_bit_buffer;
+  dec.selftest_refine = g_selftest_refine != 0;
+  dec.force_portable_refine = g_selftest_refine == 2;
   dec.begin_frame = [&]() {
     fill_tables(image, desc, comp_of);
     for (int c = 0; c < 3; c++)
@@ -118,6 +121,7 @@ void decode_planes(Image_Descriptor &image, gidcuda_frame_desc *desc, int16_t *p
   };
   dec.run();
   if (!dec.plane[0].base) throw error_in_image_data("JPEG: no scan in the image");
+  selftest_refine_scans += dec.selftest_scans;
 }
 
 // Block (bx, by) with sequence number seq: MCUs in raster order, inside an MCU the
@@ -570,6 +574,12 @@ int gidhost_set_option(const char *name, int value) {
     g_device_entropy = value != 0;
     return GIDHOST_OK;
   }
+  if (name && strcmp(name, "selftest_refine") == 0) {
+    // decode_planes checks every AC refinement scan against its decode from the non-zero history alone (the
+    // host half of the device path for progressive files; 2: with the portable form of that decoder)
+    gid::detail::g_selftest_refine = value;
+    return GIDHOST_OK;
+  }
   if (name && strcmp(name, "device_progressive_min_bytes") == 0) {
     g_device_progressive_min_bytes = value;
     return GIDHOST_OK;
@@ -664,6 +674,7 @@ long gidhost_counter(const char *name) {
   if (name && strcmp(name, "parallel_fallbacks") == 0) return gid::detail::parallel_fallbacks.load();
   if (name && strcmp(name, "device_scans") == 0) return gid::detail::device_scans.load();
   if (name && strcmp(name, "device_scan_fallbacks") == 0) return gid::detail::device_scan_fallbacks.load();
+  if (name && strcmp(name, "selftest_refine_scans") == 0) return gid::detail::selftest_refine_scans.load();
   if (name && strcmp(name, "ns_masks_wait") == 0) return gid::detail::ns_masks_wait.load();
   if (name && strcmp(name, "ns_refine_host") == 0) return gid::detail::ns_refine_host.load();
   if (name && strcmp(name, "ns_pscan_queue") == 0) return gid::detail::ns_pscan_queue.load();

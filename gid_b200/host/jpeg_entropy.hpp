@@ -427,6 +427,22 @@ struct WideBits {
     drop(n);
     return v;
   }
+  // n (1 .. 16) bits that the caller would otherwise ask for ONE AT A TIME (the correction bits of an AC
+  // refinement scan): the same bits, and the same bookkeeping of what the byte-wise buffer would have loaded
+  // by then (it loads a byte whenever it is empty), in one step
+  int get_serial(int n) {
+    if (track && n > ref_len) {
+      const int k = (n - ref_len + 7) >> 3;
+      ref_len += 8 * k;
+      ref_loaded += (size_t)k;
+    }
+    if (len < n) refill();
+    if (bad && n > real())
+      throw error_in_image_data(fmt("JPEG: Invalid marker within filling of bit buffer: 16#%02X#", bad));
+    const int v = peek(n);
+    drop(n);
+    return v;
+  }
   int symbol(const HuffTable &t) {  // Next_Huffval, :738-746: always looks at 16 bits
     need(16);
     const int look = peek(16);
@@ -1065,6 +1081,79 @@ struct Decoder {
     }
   }
 
+  // The same with the walks over the band done by bit arithmetic (x86 BMI2: pdep finds the n-th zero position,
+  // popcount counts the correction bits, which are then read together and dealt out by pdep).  Same bits read
+  // in the same order, same results (tests: gidhost_selftest_refine, and the device path against the oracle).
+#if defined(__x86_64__)
+  template <class B>
+  __attribute__((target("bmi2,popcnt"))) void read_corrections(B &bits, uint64_t m, uint64_t &corr) {
+    while (m) {
+      const uint64_t chunk = __builtin_ia32_pdep_di(0xFFFFull, m);  // its 16 lowest positions
+      const int n = __builtin_popcountll(chunk);
+      const uint32_t v = (uint32_t)bits.get_serial(n);             // first bit read = most significant
+      uint32_t rev = 0;                                             // ... = lowest position
+      for (uint32_t x = v, i = 0; i < (uint32_t)n; i++, x >>= 1) rev = (rev << 1) | (x & 1u);
+      corr |= __builtin_ia32_pdep_di((uint64_t)rev, chunk);
+      m &= ~chunk;
+    }
+  }
+  template <class B>
+  __attribute__((target("bmi2,popcnt"))) void ac_refine_history_bmi2(B &bits, int c, uint64_t &mask, uint64_t &corr,
+                                                                     uint64_t &newpos, uint64_t &newneg, int ss, int se) {
+    const uint64_t band = (se >= 63 ? ~0ull : ((1ull << (se + 1)) - 1ull)) & (~0ull << ss);
+    int k = ss;
+    if (eobrun <= 0) {
+      const HuffTable &ac = table(1, ht_ac[c]);
+      while (k <= se) {
+        const int rs = bits.symbol(ac);
+        const int rr = rs >> 4, s = rs & 15;
+        int value = 0;
+        if (s == 0) {
+          if (rr < 15) {
+            eobrun = 1 << rr;
+            if (rr) eobrun += bits.get(rr);
+            break;
+          }
+        } else {
+          if (s != 1) throw error_in_image_data("JPEG: progressive: AC refinement with a size other than 1");
+          value = bits.get(1) ? 1 : -1;
+        }
+        // pass rr zero positions and stop at the next one; every non-zero position on the way reads a bit
+        const uint64_t from = band & (~0ull << k);
+        const uint64_t target = __builtin_ia32_pdep_di(1ull << rr, ~mask & from);
+        const int kt = target ? __builtin_ctzll(target) : se + 1;
+        read_corrections(bits, mask & from & (kt > 63 ? ~0ull : ((1ull << kt) - 1ull)), corr);
+        if (target && value) {
+          newpos |= target;
+          if (value < 0) newneg |= target;
+          mask |= target;
+        }
+        k = kt + 1;
+      }
+    }
+    if (eobrun > 0) {
+      if (k <= se) read_corrections(bits, mask & band & (~0ull << k), corr);
+      eobrun--;
+    }
+  }
+#endif
+  template <class B> void ac_refine_history_auto(B &bits, int c, uint64_t &mask, uint64_t &corr, uint64_t &newpos,
+                                                 uint64_t &newneg, int ss, int se) {
+#if defined(__x86_64__)
+    static const bool fast = __builtin_cpu_supports("bmi2") && __builtin_cpu_supports("popcnt");
+    if (fast && !force_portable_refine) {
+      ac_refine_history_bmi2(bits, c, mask, corr, newpos, newneg, ss, se);
+      return;
+    }
+#endif
+    ac_refine_history(bits, c, mask, corr, newpos, newneg, ss, se);
+  }
+  bool force_portable_refine = false;
+  bool selftest_refine = false;   // see progressive_scan
+  size_t selftest_pos = 0;
+  uint8_t selftest_marker = 0;
+  int selftest_scans = 0;
+
   void device_progressive_scan(const int *comps, int ncomps, int ss, int se, int ah, int al) {
     if (im.restart_interval != 0) throw device_declined();
     if (ss > se || se > 63) throw error_in_image_data("JPEG: progressive: bad spectral selection");
@@ -1102,7 +1191,7 @@ struct Decoder {
       for (int by = 0; by < bh; by++)
         for (int bx = 0; bx < bw; bx++) {
           const size_t pb = (size_t)by * (size_t)hist_bx[c] + (size_t)bx;
-          ac_refine_history(wb, c, hist[c][pb], corr[pb], newpos[pb], newneg[pb], ss, se);
+          ac_refine_history_auto(wb, c, hist[c][pb], corr[pb], newpos[pb], newneg[pb], ss, se);
         }
       device_refine_commit(c, al);
       detail::ns_refine_host.fetch_add(
@@ -1181,9 +1270,55 @@ struct Decoder {
     // behind, so that the segment loop (and its errors on damaged files) carry on identically.
     if (wide_progressive && im.restart_interval == 0) {
       const size_t start = r.s.pos;
+      // Self-test of the device path's host half (no device needed): decode the AC refinement scan a first
+      // time from the non-zero history alone, apply its verdict to a copy of the plane the way
+      // pscan_apply_kernel does, and hold the copy against what the decoder proper makes of the scan.
+      std::vector<int16_t> shadow;
+      int shadow_c = -1;
+      if (selftest_refine && ss > 0 && ah > 0 && ncomps == 1 && plane[comps[0]].base) {
+        const int c = comps[0];
+        const Component_Info &ci = im.info[c];
+        const size_t nb = (size_t)plane[c].blocks_x * (size_t)plane[c].blocks_y;
+        if (nzmask[c].size() != nb) nzmask[c].assign(nb, 0);
+        shadow.assign(plane[c].base, plane[c].base + nb * 64);
+        std::vector<uint64_t> h(nzmask[c]), corr(nb, 0), np(nb, 0), nn(nb, 0);
+        const int wc = (im.width * ci.samples_hor + im.max_samples_hor - 1) / im.max_samples_hor;
+        const int hc = (im.height * ci.samples_ver + im.max_samples_ver - 1) / im.max_samples_ver;
+        const int bw = (wc + 7) / 8, bh = (hc + 7) / 8;
+        WideBits w2(r.s.data, start, r.s.size);
+        w2.track = true;
+        eobrun = 0;
+        for (int by = 0; by < bh; by++)
+          for (int bx = 0; bx < bw; bx++) {
+            const size_t pb = (size_t)by * (size_t)plane[c].blocks_x + (size_t)bx;
+            ac_refine_history_auto(w2, c, h[pb], corr[pb], np[pb], nn[pb], ss, se);
+          }
+        const int p1 = 1 << al, m1 = -(1 << al);
+        for (size_t b = 0; b < nb; b++) {
+          int16_t *blk = shadow.data() + b * 64;
+          for (uint64_t m = corr[b]; m; m &= m - 1) {
+            int16_t &z = blk[kZigZag[__builtin_ctzll(m)]];
+            if ((z & p1) == 0) z = (int16_t)(z >= 0 ? z + p1 : z + m1);
+          }
+          for (uint64_t m = np[b]; m; m &= m - 1) {
+            const int k = __builtin_ctzll(m);
+            blk[kZigZag[k]] = (int16_t)(((nn[b] >> k) & 1ull) ? m1 : p1);
+          }
+        }
+        selftest_pos = w2.reference_position(start, &selftest_marker);
+        shadow_c = c;
+      }
       WideBits wb(r.s.data, start, r.s.size);
       wb.track = true;
       progressive_scan_with(wb, comps, ncomps, ss, se, ah, al);
+      if (shadow_c >= 0) {
+        const size_t nb = (size_t)plane[shadow_c].blocks_x * (size_t)plane[shadow_c].blocks_y;
+        uint8_t mk = 0;
+        const size_t pos = wb.reference_position(start, &mk);
+        if (memcmp(shadow.data(), plane[shadow_c].base, nb * 64 * sizeof(int16_t)) != 0 || pos != selftest_pos || mk != selftest_marker)
+          throw constraint_error("self-test: the AC refinement scan decoded from the non-zero history differs from the decoder's");
+        selftest_scans++;
+      }
       uint8_t marker = 0;
       r.s.pos = wb.reference_position(start, &marker);
       bits.memo_marker = marker;

@@ -865,3 +865,54 @@ def test_progressive_files_in_the_file_batch_driver(host, oracle, synth, gpu):
     ref_big, ref_small = oracle.decode(big)[1], oracle.decode(small)[1]
     for f, img in zip(files, imgs):
         assert np.array_equal(img, ref_big if f is big else ref_small)
+
+
+def test_refinement_from_the_nonzero_history_selftest(host, oracle, synth):
+    """The host half of the device path for progressive files, checked WITHOUT a device: with the option
+    "selftest_refine" the host decoder decodes every AC refinement scan a first time from the non-zero history
+    alone (which positions read a correction bit of 1, which became +-(1 << Al): what it would send to
+    pscan_apply_kernel), applies that to a copy of the plane as the kernel does, and compares the copy -- and the
+    stream position the scan leaves behind -- with what the decoder proper makes of the scan.  Both forms of the
+    history decoder (bit arithmetic with BMI2, portable loops), valid and damaged files."""
+    files = []
+    for name, ent in _golden_files():
+        if ent["progressive"] or "libjpeg_script" in name:
+            files.append((name, open(os.path.join(GOLDEN, ent["jpg"]), "rb").read()))
+    for samp, w, h in (("420", 333, 217), ("422", 256, 192), ("444", 120, 88), ("grey", 200, 150), ("411", 160, 40)):
+        files.append((f"synth_{samp}", synth.encode(pixels_for(synth, 5, w, h, samp), samp, progressive=True, quality=85)[0]))
+    Y, CB, CR = [0], [1], [2]
+    libjpeg = [([0, 1, 2], 0, 0, 0, 1), (Y, 1, 5, 0, 2), (CR, 1, 63, 0, 1), (CB, 1, 63, 0, 1), (Y, 6, 63, 0, 2),
+               (Y, 1, 63, 2, 1), ([0, 1, 2], 0, 0, 1, 0), (CR, 1, 63, 1, 0), (CB, 1, 63, 1, 0), (Y, 1, 63, 1, 0)]
+    files.append(("libjpeg_script_q95", synth.encode(pixels_for(synth, 6, 400, 304, "420"), "420", progressive=True,
+                                                     quality=95, scans=libjpeg)[0]))
+    files += [(n, f) for n, f in _pillow_files(synth) if "progressive" in n]
+    rng = np.random.default_rng(12)
+    for mode in (1, 2):
+        host.set_option("selftest_refine", mode)
+        try:
+            before = host.counter("selftest_refine_scans")
+            for name, jpg in files:
+                fr, _, _ = oracle.decode(jpg)
+                _, planes = host.decode_planes(jpg)          # raises constraint_error on a self-test mismatch
+                for c in range(fr.ncomp):
+                    assert np.array_equal(planes[c], fr.planes[c]), (name, c)
+            assert host.counter("selftest_refine_scans") - before >= 2 * len(files)
+            # damaged files: whatever the decoder proper does (planes or exception), the history decode did the
+            # same up to the scan in which it happened -- a mismatch would surface as constraint_error
+            jpg = files[-1][1]
+            sos = jpg.index(b"\xff\xda")
+            for t in range(60):
+                bad = bytearray(jpg)
+                pos = int(rng.integers(sos + 10, len(bad) - 2))
+                if t % 3 == 0:
+                    bad[pos] = int(rng.integers(0, 256))
+                elif t % 3 == 1:
+                    del bad[pos]
+                else:
+                    del bad[pos:pos + int(rng.integers(2, 30))]
+                try:
+                    host.decode_planes(bytes(bad))
+                except host.GidHostError as e:
+                    assert "self-test" not in str(e), (mode, t, str(e))
+        finally:
+            host.set_option("selftest_refine", 0)

@@ -7,6 +7,8 @@ import bench
 from gid_b200 import capi, host_api
 w, h, _, _, _ = bench.WORKLOADS["cfg5"]
 distinct = bench.make_files("cfg5", 2, 77)
+if os.environ.get("BLOCKING_WAIT"):
+    capi.set_option("blocking_wait", int(os.environ["BLOCKING_WAIT"]))
 names = ("ns_pscan_queue", "ns_masks_wait", "ns_refine_host")
 for T in [int(a) for a in sys.argv[1:]] or [1, 16]:
     n = 8 * T
