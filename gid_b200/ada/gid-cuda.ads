@@ -218,6 +218,31 @@ private
      interval_begin, interval_end : access constant Interfaces.Unsigned_32) return C.int;
   pragma Import (C, gidcuda_job_scan, "gidcuda_job_scan");
 
+  --  Progressive frames on the device (include/gidcuda.h, gidcuda_job_pscan*): first scans and DC refinement
+  --  scans as compressed bytes, AC refinement decoded by the host from the non-zero history.  Raw imports; the
+  --  C++ host mirror (gid_b200/host/jpeg_entropy.hpp, device_progressive_scan) is the worked example of the
+  --  call sequence a patched Progressive_DCT_Decoding_Scan (:1243-1747) makes.
+  type Pscan_Desc is record
+    ncomp          : Interfaces.Integer_32;
+    comp           : Sampling_Array;
+    ss, se, ah, al : Interfaces.Integer_32;
+    dc, ac         : Huffman_Table_Array;
+  end record;
+  pragma Convention (C, Pscan_Desc);
+  function gidcuda_job_pscan_reserve (j : Job; total_bytes : C.size_t) return C.int;
+  pragma Import (C, gidcuda_job_pscan_reserve, "gidcuda_job_pscan_reserve");
+  function gidcuda_job_pscan
+    (j : Job; scan : access constant Pscan_Desc; data : System.Address; len : C.size_t) return C.int;
+  pragma Import (C, gidcuda_job_pscan, "gidcuda_job_pscan");
+  function gidcuda_job_pscan_masks
+    (j : Job; comp : C.int; masks : access System.Address; nblocks : access Interfaces.Integer_32) return C.int;
+  pragma Import (C, gidcuda_job_pscan_masks, "gidcuda_job_pscan_masks");
+  function gidcuda_job_pscan_refine
+    (j : Job; comp : C.int; corr, newpos, newneg : access System.Address) return C.int;
+  pragma Import (C, gidcuda_job_pscan_refine, "gidcuda_job_pscan_refine");
+  function gidcuda_job_pscan_refine_commit (j : Job; comp, al : C.int) return C.int;
+  pragma Import (C, gidcuda_job_pscan_refine_commit, "gidcuda_job_pscan_refine_commit");
+
   function gidcuda_job_output (j : Job; host_pixels : System.Address; capacity : C.size_t) return C.int;
   pragma Import (C, gidcuda_job_output, "gidcuda_job_output");
 
