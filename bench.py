@@ -76,7 +76,10 @@ def make_frames(workload: str, count: int, seed0: int):
 
 
 # JPEG-file form of each workload: (progressive, restart interval, files per call)
-FILE_FORM = {"cfg1": (False, 0, 256), "cfg2": (False, 0, 8), "cfg3": (False, 0, 64), "cfg4": (False, 64, 4),
+# Files per call: enough of them that the ramp of a call -- the first frame's way through header, Huffman kernels
+# and reconstruction before the device-to-host link has anything to carry, about 1.3 ms for a 4096 x 4096 file --
+# is a few per cent of it (cfg2 with 8 files per call: 16.5 GP/s, with 32: 18.1; profiles/r02_files_per_call.txt)
+FILE_FORM = {"cfg1": (False, 0, 1024), "cfg2": (False, 0, 32), "cfg3": (False, 0, 256), "cfg4": (False, 64, 12),
              "cfg5": (True, 0, 128)}
 
 
@@ -468,10 +471,12 @@ def run_ours(args) -> None:
     # reuse L2-resident data (every step-batch is also larger than the 126 MB L2) ---------
     distinct = 2 if per_step > 1 else 4          # distinct source frames
     frames = make_frames(args.workload, distinct, 1000 * rank)
-    alg_bytes_frame = frames[0].algorithmic_bytes()
+    alg_bytes_frame = frames[0].algorithmic_bytes() + (w * h if args.rgba else 0)  # (R,G,B,A: a byte more per pixel)
     ring = max(2, min(4, int(2.5e9 // max(1, alg_bytes_frame * per_step))))
     ring -= ring % 2  # a multiple of the number of launch streams
     rot_flag = {0: 0, 90: capi.FLAG_ROTATE_90, 180: capi.FLAG_ROTATE_180, 270: capi.FLAG_ROTATE_270}[args.rotate]
+    if args.rgba:
+        rot_flag |= capi.OUT_RGBA8
     descs_one = [frame_desc(f, rot_flag) for f in frames]
     stride, nbytes = ctx.output_geometry(descs_one[0])
     keep, plans = [], []
@@ -671,7 +676,7 @@ def run_ours(args) -> None:
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": workload_config(args.workload, world),
-            "method": {"rotate": args.rotate, "launch_streams": nstreams, "programmatic_dependent_launch": bool(args.pdl), "host_numa": numa,
+            "method": {"rotate": args.rotate, "rgba": bool(args.rgba), "launch_streams": nstreams, "programmatic_dependent_launch": bool(args.pdl), "host_numa": numa,
                        "l2": f"inputs larger than L2: ring of {ring} step-batches of {alg / 1e6:.0f} MB each",
                        "timing": "CUDA events on the launching stream around EXACTLY --steps launches, barrier + synchronize "
                                  "on both sides, max over ranks; regions repeated until >= 50 ms of device time; the median "
@@ -735,6 +740,7 @@ def main() -> None:
                     help="launch streams for the device-resident leg (default 1: the kernel's own figure)")
     ap.add_argument("--rotate", type=int, default=0, choices=[0, 90, 180, 270],
                     help="apply a display orientation while writing the pixels (GIDCUDA_FLAG_ROTATE_*; not the default workload)")
+    ap.add_argument("--rgba", action="store_true", help="R,G,B,A pixels (GIDCUDA_OUT_RGBA8) instead of the benchmark's R,G,B")
     ap.add_argument("--pdl", type=int, default=1, choices=[0, 1],
                     help="plan launches as programmatic dependent launches (library default 1); 0 = every launch "
                          "waits for its predecessor to leave the device")

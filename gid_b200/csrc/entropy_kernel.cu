@@ -45,15 +45,39 @@ struct Bits {
   const uint8_t *p, *e;
   uint64_t buf;  // left-aligned: the next bit is bit 63
   int len, pad;  // valid bits; how many of them (at the tail) are padding past the interval's end
+  // The four bytes at p, most significant first, fetched ONE REFILL AHEAD (valid when `have`): a refill
+  // consumes bytes whose loads were issued 32 bits of decoding earlier, so their latency is not on the
+  // decoder's dependent chain (it was 29 % of the kernel's stall samples, profiles/r02_ncu_summary.md).
+  // (kept as the four bytes the loads return: combined where they are used, so that nothing waits for them here)
+  uint32_t a0, a1, a2, a3;
+  bool have;
+  __device__ __forceinline__ void fetch() {
+    have = p + 4 <= e;
+    if (have) {
+      a0 = __ldg(p);
+      a1 = __ldg(p + 1);
+      a2 = __ldg(p + 2);
+      a3 = __ldg(p + 3);
+    }
+  }
+  __device__ __forceinline__ void start(const uint8_t *begin, const uint8_t *end) {
+    p = begin;
+    e = end;
+    buf = 0;
+    len = 0;
+    pad = 0;
+    fetch();
+  }
   __device__ __forceinline__ void refill() {
     // four bytes at once where none of them is FF (byte stuffing, :640-662, makes the byte-wise loop below
-    // a chain of dependent loads: one load latency per byte; these four loads are independent)
-    if (len <= 32 && p + 4 <= e) {
-      const uint32_t b0 = __ldg(p), b1 = __ldg(p + 1), b2 = __ldg(p + 2), b3 = __ldg(p + 3);
-      if (b0 != 0xFFu && b1 != 0xFFu && b2 != 0xFFu && b3 != 0xFFu) {
-        buf |= (uint64_t)((b0 << 24) | (b1 << 16) | (b2 << 8) | b3) << (32 - len);
+    // a chain of dependent loads: one load latency per byte)
+    if (len <= 32 && have) {
+      const uint32_t w = (a0 << 24) | (a1 << 16) | (a2 << 8) | a3, n = ~w;
+      if (((n - 0x01010101u) & w & 0x80808080u) == 0u) {  // no byte of n is zero: no FF among the four
+        buf |= (uint64_t)w << (32 - len);
         len += 32;
         p += 4;
+        fetch();
         return;
       }
     }
@@ -68,31 +92,13 @@ struct Bits {
       buf |= (uint64_t)b << (56 - len);
       len += 8;
     }
+    fetch();
   }
-  __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)(buf >> (64 - n)); }
   __device__ __forceinline__ void drop(int n) {
     buf <<= n;
     len -= n;
   }
 };
-
-// Next_Huffval: 10-bit direct table, then the canonical search for longer codes; -1 = no such code
-__device__ __forceinline__ int symbol(Bits &b, const HuffDev &t) {
-  const uint32_t look = b.peek(16);
-  const uint32_t e = t.lut[look >> 6];
-  if (e != 0) {
-    b.drop((int)(e >> 8));
-    return (int)(e & 0xFFu);
-  }
-  for (int l = 11; l <= 16; l++) {
-    const int code = (int)(look >> (16 - l));
-    if (code <= t.maxcode[l]) {
-      b.drop(l);
-      return t.vals[(t.valoff[l] + code) & 0xFF];
-    }
-  }
-  return -1;
-}
 
 __device__ __forceinline__ int extend(uint32_t v, int n) {  // Bin_Twos_Complement
   return v < (1u << (n - 1)) ? (int)v + 1 - (1 << n) : (int)v;
@@ -102,36 +108,83 @@ __device__ __forceinline__ int extend(uint32_t v, int n) {  // Bin_Twos_Compleme
 // |v| < 2**bits  (v = -2**bits counts as outside)
 __device__ __forceinline__ bool within_bits(int v, int bits) { return ((uint32_t)(v ^ (v >> 31)) >> bits) == 0u; }
 
-__device__ __forceinline__ bool decode_block(Bits &b, const HuffDev &dc, const HuffDev &ac, int &pred, int16_t *blk,
-                                             const uint8_t *zz, int limbits) {
+// The interval kernel reads its tables through addresses in the shared window (a reference to a table in
+// shared memory made the compiler re-derive the window's base -- S2R + LEA -- at every symbol).
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+  uint16_t v;
+  asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int lds_s32(uint32_t a) {
+  int v;
+  asm("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+  uint32_t v;
+  asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+constexpr uint32_t kOffMaxcode = 2048, kOffValoff = 2048 + 68, kOffVals = 2048 + 136;
+static_assert(sizeof(HuffDev) == kOffVals + 256, "HuffDev layout");
+
+// Next_Huffval on the top 32 bits of the bit buffer (`hi`): the symbol and the length of its code, -1 = no such code
+__device__ __forceinline__ int symbol_in(uint32_t hi, uint32_t tab, int &codelen) {
+  const uint32_t look = hi >> 16;
+  const uint32_t e = lds_u16(tab + 2u * (look >> 6));
+  if (e != 0) {
+    codelen = (int)(e >> 8);
+    return (int)(e & 0xFFu);
+  }
+  for (int l = 11; l <= 16; l++) {
+    const int code = (int)(look >> (16 - l));
+    if (code <= lds_s32(tab + kOffMaxcode + 4u * l)) {
+      codelen = l;
+      return (int)lds_u8(tab + kOffVals + (uint32_t)((lds_s32(tab + kOffValoff + 4u * l) + code) & 0xFF));
+    }
+  }
+  codelen = 0;
+  return -1;
+}
+
+// A code and the value bits behind it are at most 16 + 15 bits: both come out of one 32-bit window of the
+// buffer, which is then advanced once.  (dc, ac, zz: shared-window addresses; blk: the thread's staging block)
+__device__ __forceinline__ bool decode_block(Bits &b, uint32_t dc, uint32_t ac, int &pred, int16_t *blk, uint32_t zz,
+                                             int limbits) {
   if (b.len <= 32) b.refill();
-  const int s = symbol(b, dc);
+  uint32_t hi = (uint32_t)(b.buf >> 32);
+  int cl;
+  const int s = symbol_in(hi, dc, cl);
   if (s < 0) return false;
   const int n = s & 15;
   if (n) {
-    pred += extend(b.peek(n), n);
-    b.drop(n);
+    pred += extend((hi << cl) >> (32 - n), n);
     // the reference keeps a 32-bit predictor (:766-771): one that leaves the range of the planes (or of
     // the fast reconstruction instances) is the host decoder's case
     if (!within_bits(pred, limbits)) return false;
   }
+  b.drop(cl + n);
   blk[0] = (int16_t)pred;
   int coef = 0;
   for (;;) {
     if (b.len <= 32) b.refill();
-    const int code = symbol(b, ac);
+    hi = (uint32_t)(b.buf >> 32);
+    const int code = symbol_in(hi, ac, cl);
     if (code < 0) return false;
-    if (code == 0) break;  // EOB
+    if (code == 0) {  // EOB
+      b.drop(cl);
+      break;
+    }
     const int m = code & 15;
     if (m == 0 && code != 0xF0) return false;
     coef += (code >> 4) + 1;
     if (coef > 63) return false;
     if (m > limbits) return false;  // a value of category m is below 2**m
     if (m) {
-      GIDK_ASSERT(coef >= 1 && coef <= 63 && zz[coef] < 64);
-      blk[zz[coef]] = (int16_t)extend(b.peek(m), m);
-      b.drop(m);
+      GIDK_ASSERT(coef >= 1 && coef <= 63);
+      blk[lds_u8(zz + (uint32_t)coef)] = (int16_t)extend((hi << cl) >> (32 - m), m);
     }
+    b.drop(cl + m);
     if (coef == 63) break;
   }
   return b.pad <= b.len;  // false: bits past the end of the interval were used
@@ -145,6 +198,10 @@ __device__ __forceinline__ bool decode_block(Bits &b, const HuffDev &dc, const H
 // quarter warp.
 constexpr int kStageStride = 72;  // int16 per thread (64 used)
 
+// Intervals per warp (a.lanes, a power of two): a warp runs the union of its lanes' paths through the decoder
+// for as long as its longest interval, and a frame has far fewer intervals than the GPU has thread slots -- so
+// the intervals are spread over as many warps as the SMs hold (8 lanes per warp for the 16 384 intervals of an
+// 8192 x 8192 grey frame, one lane for a frame with an interval per MCU row) instead of filling few warps.
 __global__ void __launch_bounds__(128) huffman_intervals_kernel(ScanArgs a) {
   __shared__ HuffDev tabs[6];
   __shared__ uint8_t zz[64];
@@ -156,15 +213,13 @@ __global__ void __launch_bounds__(128) huffman_intervals_kernel(ScanArgs a) {
     if (threadIdx.x < 64) zz[threadIdx.x] = c_zigzag[threadIdx.x];
   }
   __syncthreads();
-  const uint32_t it = blockIdx.x * blockDim.x + threadIdx.x;
-  if (it >= a.nintervals) return;
+  const uint32_t lane = threadIdx.x & 31u, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t it = warp * a.lanes + lane;
+  if (lane >= a.lanes || it >= a.nintervals) return;
   uint4 *mine = reinterpret_cast<uint4 *>(stage + threadIdx.x * kStageStride);
+  const uint32_t tabs_s = (uint32_t)__cvta_generic_to_shared(tabs), zz_s = (uint32_t)__cvta_generic_to_shared(zz);
   Bits b;
-  b.p = a.data + __ldg(a.begin + it);
-  b.e = a.data + __ldg(a.end + it);
-  b.buf = 0;
-  b.len = 0;
-  b.pad = 0;
+  b.start(a.data + __ldg(a.begin + it), a.data + __ldg(a.end + it));
   int pred[3] = {0, 0, 0};  // (registers: only indexed by the unrolled component loop)
   const uint32_t m0 = it * a.ri;
   const uint32_t m1 = min(m0 + a.ri, a.nmcu);
@@ -180,7 +235,8 @@ __global__ void __launch_bounds__(128) huffman_intervals_kernel(ScanArgs a) {
           const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
           for (int j = 0; j < 8; j++) mine[j] = z;
-          ok = decode_block(b, tabs[c], tabs[3 + c], pred[c], reinterpret_cast<int16_t *>(mine), zz, a.limbits[c]);
+          ok = decode_block(b, tabs_s + (uint32_t)(c * sizeof(HuffDev)), tabs_s + (uint32_t)((3 + c) * sizeof(HuffDev)),
+                            pred[c], reinterpret_cast<int16_t *>(mine), zz_s, a.limbits[c]);
           uint4 *dst = reinterpret_cast<uint4 *>(a.plane[c] + blockno * 64);
 #pragma unroll
           for (int j = 0; j < 8; j++) dst[j] = mine[j];
@@ -201,9 +257,14 @@ __global__ void __launch_bounds__(128) huffman_intervals_kernel(ScanArgs a) {
 
 }  // namespace
 
-cudaError_t launch_huffman_intervals(const ScanArgs &a, cudaStream_t stream) {
-  if (a.nintervals == 0) return cudaSuccess;
-  huffman_intervals_kernel<<<(a.nintervals + 127) / 128, 128, 0, stream>>>(a);
+cudaError_t launch_huffman_intervals(const ScanArgs &args, int num_sms, cudaStream_t stream) {
+  if (args.nintervals == 0) return cudaSuccess;
+  ScanArgs a = args;
+  // as few lanes per warp as keep the warps within what the SMs hold at once (16 per SM)
+  a.lanes = 1;
+  while (a.lanes < 32u && (a.nintervals + a.lanes - 1) / a.lanes > (uint32_t)num_sms * 16u) a.lanes *= 2;
+  const uint32_t nwarps = (a.nintervals + a.lanes - 1) / a.lanes;
+  huffman_intervals_kernel<<<(nwarps + 3) / 4, 128, 0, stream>>>(a);
   return cudaGetLastError();
 }
 

@@ -133,10 +133,9 @@ inline int make_geometry(std::string *err, const gidcuda_frame_desc *d, Geometry
     g->stride = round_up(packed, 16);
   }
   g->pixel_bytes = g->stride * (size_t)out_h;
-  if (g->rotate == 1 || g->rotate == 3 || (g->rotate == 2 && !g->q8)) {
-    // quarter turns: the per-pixel pass applies the orientation (runs along a row of the rotated image come
-    // from blocks of DIFFERENT MCU rows, which the fused kernels' tiles -- 32 MCUs of one row -- do not hold);
-    // so do half turns outside the fast domain (the rotating instances exist for the fast kernels only)
+  if (g->rotate != 0 && !g->q8) {
+    // rotated frames outside the fast domain: the per-pixel pass applies the orientation (the rotating
+    // instances of the fused kernels exist for the fast kernels only)
     g->layout = LAYOUT_GENERIC;
   } else if (d->ncomp == 1) {
     g->layout = LAYOUT_GREY;
@@ -150,9 +149,12 @@ inline int make_geometry(std::string *err, const gidcuda_frame_desc *d, Geometry
   } else {
     g->layout = LAYOUT_GENERIC;
   }
-  g->ntiles = layout_linear(g->layout) || g->layout == LAYOUT_GENERIC
-                  ? (uint32_t)(((size_t)g->mcux * g->mcuy + kTileMcusSetup - 1) / kTileMcusSetup)
-                  : (uint32_t)((size_t)g->mcuy * ((g->mcux + kTileMcusSetup - 1) / kTileMcusSetup));
+  if (g->layout != LAYOUT_GENERIC && (g->rotate & 1))  // quarter turns: tiles run down the columns of MCUs
+    g->ntiles = (uint32_t)((size_t)g->mcux * ((g->mcuy + kTileMcusSetup - 1) / kTileMcusSetup));
+  else
+    g->ntiles = layout_linear(g->layout) || g->layout == LAYOUT_GENERIC
+                    ? (uint32_t)(((size_t)g->mcux * g->mcuy + kTileMcusSetup - 1) / kTileMcusSetup)
+                    : (uint32_t)((size_t)g->mcuy * ((g->mcux + kTileMcusSetup - 1) / kTileMcusSetup));
   return GIDCUDA_OK;
 }
 
@@ -178,18 +180,21 @@ inline void fill_frame_dev(const gidcuda_frame_desc *d, const Geometry &g, const
   f->mcux = g.mcux;
   f->mcuy = g.mcuy;
   const bool fused = g.layout != LAYOUT_GENERIC;
-  // quarter turns only reach the generic kernels, which read the rotation here; the fused kernels do the
-  // half turn themselves (FRAME_ROT180)
+  // the generic kernels read the rotation here; the fused kernels are instances per orientation
   f->out_format = fused ? g.out_format : (g.out_format | (g.rotate << 8));
   f->tile_base = tile_base;
   f->q8 = g.q8 ? 1 : 0;
   f->flags = 0;
-  const bool rot180 = fused && g.rotate == 2;
-  if (rot180) f->flags |= FRAME_ROT180;
-  // (mirrored runs of whole blocks start at column W - x0 - 8: the same boundaries only when W % 8 == 0)
-  if (g.stride % 8 == 0 && (reinterpret_cast<uintptr_t>(pixels) & 7u) == 0 && (!rot180 || d->width % 8 == 0))
+  const int turn = fused ? g.rotate : 0;
+  if (turn == 1) f->flags |= FRAME_ROT90;
+  if (turn == 2) f->flags |= FRAME_ROT180;
+  if (turn == 3) f->flags |= FRAME_ROT270;
+  // (mirrored runs of whole blocks start at column W' - x0 - 8, W' = the frame's width for the half turn,
+  // its height for FRAME_ROT270: the same boundaries only when W' % 8 == 0)
+  const int mirrored = turn == 2 ? d->width : (turn == 3 ? d->height : 0);
+  if (g.stride % 8 == 0 && (reinterpret_cast<uintptr_t>(pixels) & 7u) == 0 && mirrored % 8 == 0)
     f->flags |= FRAME_ALIGNED8;
-  if (g.stride % 16 == 0 && (reinterpret_cast<uintptr_t>(pixels) & 15u) == 0 && (!rot180 || d->width % 4 == 0))
+  if (g.stride % 16 == 0 && (reinterpret_cast<uintptr_t>(pixels) & 15u) == 0 && mirrored % 4 == 0)
     f->flags |= FRAME_ALIGNED16;
 }
 

@@ -537,6 +537,14 @@ extern "C" int gidcuda_job_submit(gidcuda_job *job) {
     CU_TRY(ctx, gidk::launch_expand(ea, g.ncomp, s));
   }
   CU_TRY(ctx, job->set.launch(ctx->num_sms, s));
+  if (job->scan_active) {
+    const int rc = job_submit_scan_status(job, s);
+    if (rc != GIDCUDA_OK) return rc;
+  }
+  if (job->pscan_active) {
+    const int rc = job_submit_pscan_status(job, s);
+    if (rc != GIDCUDA_OK) return rc;
+  }
   if (!job->user_pixels && !job->h_pixels)
     CU_TRY(ctx, cudaHostAlloc((void **)&job->h_pixels, job->cap_pixels, cudaHostAllocDefault));
   CU_TRY(ctx, cudaMemcpyAsync(job->user_pixels ? job->user_pixels : job->h_pixels, job->d_pixels, g.pixel_bytes,

@@ -121,8 +121,10 @@ struct gidcuda_job {
 // wait the verdict of the device decoder (0 = pixels valid; GIDCUDA_ERR_DATA = left to the host decoder),
 // the host's chain repair included.
 int job_submit_scan(gidcuda_job *job, cudaStream_t s);
+int job_submit_scan_status(gidcuda_job *job, cudaStream_t s);  // ... its status words, once the reconstruction is queued
 int job_finish_scan(gidcuda_job *job);
 // ... and the scans of a progressive frame (gidcuda_job_pscan*): status words back at submit, verdict at wait
 int job_submit_pscan(gidcuda_job *job, cudaStream_t s);
+int job_submit_pscan_status(gidcuda_job *job, cudaStream_t s);
 int job_finish_pscan(gidcuda_job *job);
 void job_free_pscan(gidcuda_job *job);

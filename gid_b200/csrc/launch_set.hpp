@@ -30,7 +30,7 @@ struct LaunchGroup {
   Layout layout;
   bool q8;
   bool rgba;
-  bool rot;   // FRAME_ROT180 frames: kernel instances of their own
+  int rot;    // Geometry::rotate of the group's frames (rotated frames: kernel instances of their own)
   bool tma;
   uint32_t first_frame, nframes, first_tile, ntiles;
   CUtensorMap map2;
@@ -100,19 +100,19 @@ class LaunchSet {
     groups.clear();
     tma_groups = 0;
     for (int lay = 0; lay < kFusedLayouts; lay++)
-      for (int qa = 7; qa >= 0; qa--) {
+      for (int qa = 15; qa >= 0; qa--) {
         const int q = qa & 1;
         LaunchGroup g;
         memset(&g, 0, sizeof g);
         g.layout = (Layout)lay;
         g.q8 = q == 1;
         g.rgba = (qa & 2) == 0;
-        g.rot = (qa & 4) == 0;
+        g.rot = 3 - (qa >> 2);   // frames that are not rotated first
         g.first_frame = (uint32_t)frames.size();
         g.first_tile = (uint32_t)tiles.size();
         uintptr_t lo = ~(uintptr_t)0, hi = 0;
         for (const FrameItem &it : items) {
-          if ((int)it.geo.layout != lay || it.geo.q8 != g.q8 || (it.geo.out_format == (int)OUT_RGBA8) != g.rgba || (it.geo.rotate == 2) != g.rot) continue;
+          if ((int)it.geo.layout != lay || it.geo.q8 != g.q8 || (it.geo.out_format == (int)OUT_RGBA8) != g.rgba || it.geo.rotate != g.rot) continue;
           for (int c = 0; c < it.geo.ncomp; c++) {
             const uintptr_t p = reinterpret_cast<uintptr_t>(it.planes[c]);
             if (p < lo) lo = p;
@@ -123,13 +123,13 @@ class LaunchSet {
         const uintptr_t base = lo & ~(uintptr_t)255;
         bool aligned = true;
         for (const FrameItem &it : items) {
-          if ((int)it.geo.layout != lay || it.geo.q8 != g.q8 || (it.geo.out_format == (int)OUT_RGBA8) != g.rgba || (it.geo.rotate == 2) != g.rot) continue;
+          if ((int)it.geo.layout != lay || it.geo.q8 != g.q8 || (it.geo.out_format == (int)OUT_RGBA8) != g.rgba || it.geo.rotate != g.rot) continue;
           for (int c = 0; c < it.geo.ncomp; c++)
             if ((reinterpret_cast<uintptr_t>(it.planes[c]) - base) % 256 != 0) aligned = false;
         }
-        g.tma = aligned && !tma_disabled_by_env() && encode_maps(&g, base, hi);
+        g.tma = aligned && !(g.rot & 1) && !tma_disabled_by_env() && encode_maps(&g, base, hi);  // (quarter turns: plain loads)
         for (const FrameItem &it : items) {
-          if ((int)it.geo.layout != lay || it.geo.q8 != g.q8 || (it.geo.out_format == (int)OUT_RGBA8) != g.rgba || (it.geo.rotate == 2) != g.rot) continue;
+          if ((int)it.geo.layout != lay || it.geo.q8 != g.q8 || (it.geo.out_format == (int)OUT_RGBA8) != g.rgba || it.geo.rotate != g.rot) continue;
           FrameDev f;
           fill_frame_dev(it.desc, it.geo, it.planes, it.pixels, nullptr, 0, &f);
           const uint32_t fi = (uint32_t)frames.size() - g.first_frame;
@@ -230,7 +230,7 @@ class LaunchSet {
   size_t upload_bytes = 0;
 
  private:
-  static constexpr int kMaxGroups = 8 * kFusedLayouts;  // layouts x 2 table widths x 2 pixel sizes x rotated or not
+  static constexpr int kMaxGroups = 16 * kFusedLayouts;  // layouts x 2 table widths x 2 pixel sizes x 4 orientations
   static constexpr uint32_t kCounterSlots = 4;
   uint32_t launch_seq_ = 0;
   uint32_t *d_counters_ = nullptr;
@@ -268,6 +268,17 @@ class LaunchSet {
     TileDesc t;
     memset(&t, 0, sizeof t);
     t.frame = frame_index;
+    if (g.rotate & 1) {
+      // quarter turns: 32 MCUs of one column of MCUs (mcu_item); the plain-load kernel finds its blocks from
+      // the frame descriptor, no coordinates.  Tiles of one column after each other: they fill the same rows
+      // of the turned image side by side.
+      for (int mx = 0; mx < g.mcux; mx++)
+        for (int my0 = 0; my0 < g.mcuy; my0 += kTileMcus) {
+          t.m0 = (uint32_t)my0 * (uint32_t)g.mcux + (uint32_t)mx;
+          tiles.push_back(t);
+        }
+      return;
+    }
     if (g.layout == LAYOUT_GREY || g.layout == LAYOUT_444) {
       for (uint32_t m0 = 0; m0 < nmcu; m0 += kTileMcus) {
         t.m0 = m0;

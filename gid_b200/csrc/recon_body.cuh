@@ -48,7 +48,15 @@ enum FrameFlags : uint32_t {
   // (test/to_bmp.adb:104-122).  The alignment flags above then also promise W % 8 == 0 (W % 4 for RGBA), so
   // that the mirrored runs of whole blocks start on the same boundaries.
   FRAME_ROT180 = 4u,
+  // GIDCUDA_FLAG_ROTATE_90 / _270 in the fused kernels: pixel (x, r) lands at column r, row W - 1 - x / at
+  // column H - 1 - r, row x of an image H wide and W tall.  FRAME_ROT270 mirrors the runs: the alignment flags
+  // then also promise H % 8 == 0 (H % 4 for RGBA).
+  FRAME_ROT90 = 8u,
+  FRAME_ROT270 = 16u,
 };
+
+// Display orientation a kernel instance applies (= Geometry::rotate, GIDCUDA_FLAG_ROTATE_* >> 9)
+enum Turn : int { TURN_NONE = 0, TURN_90 = 1, TURN_180 = 2, TURN_270 = 3 };
 
 // Per-frame descriptor in device memory (one per image of a launch).
 struct FrameDev {
@@ -155,12 +163,21 @@ GID_HD void dequant_idct(const u32x4 (&raw)[8], const uint32_t *qw, int (&b)[64]
 
 // Clip (:755-756) + pack the 64 samples of a block to bytes and store them as 8
 // rows of 8 bytes, `stride` u32x2 apart (the per-lane scratch plane).
+//   TR   the block is stored transposed (scratch row c = column c of the block): what the instances that
+//        turn the image by a quarter emit from.  The samples sit in registers: the transposition is the
+//        order in which they are packed, no instruction more.
+template <bool TR = false>
 GID_HD void store_block_packed(const int (&b)[64], u32x2 *dst, int stride) {
 #pragma unroll
   for (int r = 0; r < 8; r++) {
     u32x2 v;
-    v.x = pack_sat4(b[8 * r + 0], b[8 * r + 1], b[8 * r + 2], b[8 * r + 3]);
-    v.y = pack_sat4(b[8 * r + 4], b[8 * r + 5], b[8 * r + 6], b[8 * r + 7]);
+    if (TR) {
+      v.x = pack_sat4(b[r], b[8 + r], b[16 + r], b[24 + r]);
+      v.y = pack_sat4(b[32 + r], b[40 + r], b[48 + r], b[56 + r]);
+    } else {
+      v.x = pack_sat4(b[8 * r + 0], b[8 * r + 1], b[8 * r + 2], b[8 * r + 3]);
+      v.y = pack_sat4(b[8 * r + 4], b[8 * r + 5], b[8 * r + 6], b[8 * r + 7]);
+    }
     dst[r * stride] = v;
   }
 }
@@ -228,7 +245,7 @@ GID_HD void dequant_idct_exact(bool active, const u32x4 (&raw)[8], const uint32_
 }
 
 // The fast instance.
-template <bool Q8, bool LO3>
+template <bool Q8, bool LO3, bool TR = false>
 GID_HD void dequant_idct_sparse(bool active, const u32x4 (&raw)[8], const uint32_t *qw, u32x2 *dst, int dst_stride) {
   int b[64];
   uint32_t ac[8];
@@ -264,12 +281,12 @@ GID_HD void dequant_idct_sparse(bool active, const u32x4 (&raw)[8], const uint32
 #pragma unroll
     for (int c = 0; c < 8; c++)
       col_idct(b[c], b[8 + c], b[16 + c], b[24 + c], b[32 + c], b[40 + c], b[48 + c], b[56 + c]);
-    store_block_packed(b, dst, dst_stride);
+    store_block_packed<TR>(b, dst, dst_stride);
   } else {
 #pragma unroll
     for (int c = 0; c < 8; c++)
       col_idct_lo3(b[c], b[8 + c], b[16 + c], b[24 + c], b[32 + c], b[40 + c], b[48 + c], b[56 + c]);
-    store_block_packed(b, dst, dst_stride);
+    store_block_packed<TR>(b, dst, dst_stride);
   }
 }
 
@@ -282,6 +299,11 @@ GID_HD void pack_block(const int (&b)[64], uint32_t (&p)[16]) {
 // Destination of pixel (x0, y): rows are flipped for the bottom-up format.
 GID_HD uint8_t *row_ptr(const FrameDev &f, int x0, int y) {
   const int yy = f.out_format == OUT_BGR8_BOTTOM_UP ? f.height - 1 - y : y;
+  return f.pixels + (size_t)yy * f.stride + (size_t)x0 * (f.out_format == OUT_RGBA8 ? 4 : 3);
+}
+// ... of an output image `rows` high (quarter turns: the frame's width)
+GID_HD uint8_t *row_ptr(const FrameDev &f, int rows, int x0, int y) {
+  const int yy = f.out_format == OUT_BGR8_BOTTOM_UP ? rows - 1 - y : y;
   return f.pixels + (size_t)yy * f.stride + (size_t)x0 * (f.out_format == OUT_RGBA8 ? 4 : 3);
 }
 
@@ -367,13 +389,21 @@ GID_HD int byte_of(uint32_t w) { return (int)prmt(w, 0u, 0x4440u + K); }
 //   RGBA   4 bytes per pixel (a separate instance, so that the 3-byte loop stays lean)
 //   FAST   the whole block lies inside the image (8 pixels x 8 rows) and its rows are aligned:
 //          no per-row bounds checks, no call to the byte-wise store in the loop
-//   REV    FRAME_ROT180: the run of a block row is written mirrored (pixel x0 + k at column W - 1 - x0 - k),
-//          rows bottom to top.  The sample words are byte-reversed as they are read, so that the arithmetic
-//          and the packing below produce the mirrored run as it is; a separate instance, so that frames
-//          that are not rotated run the code they always ran.
+//   MIRROR the run of a block row is written mirrored (pixel x0 + k at column W - 1 - x0 - k).  The sample
+//          words are byte-reversed as they are read, so that the arithmetic and the packing below produce
+//          the mirrored run as it is.
+//   FLIP   the rows go out bottom to top (row y0 + k at row H - 1 - y0 - k)
+//   TURN   the scratch holds the blocks TRANSPOSED (store_block_packed<true>) and the caller passes the block's
+//          place in the transposed image -- (y0, x0), (sy, sx), with H and V swapped: the output image is
+//          f.height wide and f.width high.
+//          FRAME_ROT180 = MIRROR + FLIP, FRAME_ROT90 = TURN + FLIP, FRAME_ROT270 = TURN + MIRROR
+//          (test/to_bmp.adb:104-122); separate kernel instances, so that frames that are not rotated run the
+//          code they always ran.
 GID_HD uint32_t brev4(uint32_t w) { return prmt(w, 0u, 0x0123u); }
-template <int H, int V, bool GREY, bool RGBA, bool FAST, bool REV = false>
+template <int H, int V, bool GREY, bool RGBA, bool FAST, bool MIRROR = false, bool FLIP = false, bool TURN = false>
 GID_HD void emit_rows(const FrameDev &f, const Scratch &sc, int x0, int y0, int sx, int sy) {
+  constexpr bool REV = MIRROR;
+  const int fw = TURN ? f.height : f.width, fh = TURN ? f.width : f.height;
   constexpr bool rgba = RGBA;
 #if defined(GIDK_EXTRACT_ADD_ALL)
   constexpr bool kExtractAdd = true;
@@ -382,7 +412,7 @@ GID_HD void emit_rows(const FrameDev &f, const Scratch &sc, int x0, int y0, int 
 #else
   constexpr bool kExtractAdd = H * V > 1;  // a chroma term serves several pixels
 #endif
-  int npix = f.width - x0;
+  int npix = fw - x0;
   if (npix > 8) npix = 8;
   const int nbytes = npix * 3;
   // !FAST: rows that are whole and aligned still leave as 8-byte stores
@@ -392,9 +422,9 @@ GID_HD void emit_rows(const FrameDev &f, const Scratch &sc, int x0, int y0, int 
   // REV: the run starts where its LAST pixel lands; of a mirrored run cut by the edge the leading
   // 8 - npix pixels of the 8 computed are not written
   const int skip_pix = REV ? 8 - npix : 0;
-  uint8_t *dst = REV ? row_ptr(f, f.width - x0 - npix, f.height - 1 - y0) : row_ptr(f, x0, y0);
-  const long long step = (bottom_up != REV) ? -(long long)f.stride : (long long)f.stride;
-  const int rows_left = FAST ? 8 : f.height - y0;  // >= 1
+  uint8_t *dst = row_ptr(f, fh, MIRROR ? fw - x0 - npix : x0, FLIP ? fh - 1 - y0 : y0);
+  const long long step = (bottom_up != FLIP) ? -(long long)f.stride : (long long)f.stride;
+  const int rows_left = FAST ? 8 : fh - y0;  // >= 1
   const int crow0 = sy * (8 / V);                   // first row inside the chroma block
   // (The byte selectors of the extract-add are literals: the compiler re-materialises them into
   // uniform registers on every trip, 9 UMOV, but holding them in registers instead was measured
@@ -509,14 +539,20 @@ void emit_rows_edge(const FrameDev *f, u32x2 *cb, u32x2 *cr, u32x2 *y, int strid
   emit_rows<H, V, GREY, RGBA, false>(*f, sc, x0, y0, sx, sy);
 }
 
-template <int H, int V, bool GREY, bool RGBA, bool ROT>
+template <int H, int V, bool GREY, bool RGBA, int ROT>
 GID_HD void emit_block_rows(const FrameDev &f, const Scratch &sc, int x0, int y0, int sx, int sy) {
   if (x0 >= f.width) return;
-  if (ROT) {
-    // FRAME_ROT180 frames run kernel instances of their own: a second copy of the row emitter inside the
+  if (ROT != TURN_NONE) {
+    // Rotated frames run kernel instances of their own: a second copy of the row emitter inside the
     // ordinary instances cost frames that are not rotated 6 % (measured on 4:2:0; the kernels are bound by
     // instruction fetch, tools/icache_bench.cu)
-    emit_rows<H, V, GREY, RGBA, false, true>(f, sc, x0, y0, sx, sy);
+    if (ROT == TURN_180) {
+      emit_rows<H, V, GREY, RGBA, false, true, true>(f, sc, x0, y0, sx, sy);
+    } else {
+      // quarter turns: the block's rows are the image's columns -- the samples were stored transposed
+      if (y0 >= f.height) return;
+      emit_rows<V, H, GREY, RGBA, false, ROT == TURN_270, ROT == TURN_90, true>(f, sc, y0, x0, sy, sx);
+    }
     return;
   }
   // The split pays where registers are plentiful (grey: +1.7 %).  The colour kernels sit at the
@@ -556,15 +592,39 @@ GID_HD void warp_sync() {
 //   halves of each 48-byte run were written a whole block of arithmetic apart: partially written
 //   sectors were evicted and re-fetched, +38 % DRAM reads and +24 % writes on 4:2:0, ncu.)
 //   The chroma samples of MCU j / 2 were left in the scratch by lane j / 2.
-template <int H, int V, bool GREY, bool Q8, bool RGBA, bool ROT, class Src>
+//   Quarter turns (ROT = TURN_90 / TURN_270): a row of the turned image is a COLUMN of the frame, so the tile is
+//   32 MCUs of one column of MCUs and the luma items walk its block columns 32 consecutive blocks at a time
+//   (item 2 + V*sx + part: blocks 32*part .. 32*part + 31 of block column sx): the lanes of a warp then
+//   write neighbouring 24-byte runs of the same rows of the turned image, as above.  (With the tiles along the
+//   frame's rows every lane wrote its run into a row of its own, 8 rows apart: sectors written a third at a
+//   time by different warps were evicted from L2 before they were complete -- twice the DRAM traffic, 0.19 of
+//   the HBM roofline on 1080p 4:2:0 batches against 0.68 unrotated; ncu, profiles/r02_ncu_summary.md.)
+template <int H, int V, bool GREY, bool Q8, bool RGBA, int ROT, class Src>
 GID_HD void mcu_item(int it, bool active, const FrameDev &f, const uint32_t *qw, Src &src, const Scratch &sc,
                      int lane, int mx, int my) {
   int comp = 0, sx = 0, sy = 0;
   int bxi = mx, byi = my;
   Scratch se = sc;
+  // quarter turns: the tile is 32 MCUs of one COLUMN of MCUs (lane t <-> MCU (mx, my0 + t)), the mirror image of
+  // everything above -- see the end of this comment block
+  constexpr bool VERT = ROT == TURN_90 || ROT == TURN_270;
   if (!GREY) {
     if (it < 2) {
       comp = it + 1;
+    } else if (VERT && V == 1) {
+      sx = it - 2;
+      bxi = mx * H + sx;
+    } else if (VERT) {
+      const int part = (it - 2) % V;        // which 32 of the block column's 32 * V luma blocks
+      sx = (it - 2) / V;
+      const int j = 32 * part + lane;       // luma block of this lane inside the tile's block column
+      bxi = mx * H + sx;
+      byi = V * (my - lane) + j;            // my - lane = first MCU of the tile
+      active = byi < f.by[0];
+      sy = lane & (V - 1);                  // = j % V
+      se.cb = sc.cb + ((j / V) - lane);     // scratch column of MCU j / V
+      se.cr = sc.cr + ((j / V) - lane);
+      if (it == 2) warp_sync();
     } else if (H == 1) {
       sy = it - 2;
       byi = my * V + sy;
@@ -601,7 +661,8 @@ GID_HD void mcu_item(int it, bool active, const FrameDev &f, const uint32_t *qw,
 #else
   constexpr bool kLo3 = H * V == 1;
 #endif
-  if (Q8) dequant_idct_sparse<true, kLo3>(active, raw, qw + 32 * comp, dst, sc.stride);
+  constexpr bool kTransposed = ROT == TURN_90 || ROT == TURN_270;  // (fast instances only: frame_setup.hpp)
+  if (Q8) dequant_idct_sparse<true, kLo3, kTransposed>(active, raw, qw + 32 * comp, dst, sc.stride);
   else dequant_idct_exact(active, raw, qw + 32 * comp, dst, sc.stride);
   if (comp == 0) {
     if (active) emit_block_rows<H, V, GREY, RGBA, ROT>(f, se, bxi * 8, byi * 8, sx, sy);
@@ -609,7 +670,7 @@ GID_HD void mcu_item(int it, bool active, const FrameDev &f, const uint32_t *qw,
   }
 }
 
-template <int H, int V, bool GREY, bool Q8, bool RGBA, bool ROT, class Src>
+template <int H, int V, bool GREY, bool Q8, bool RGBA, int ROT, class Src>
 GID_HD void mcu_run(bool active, const FrameDev &f, const uint32_t *qw /* [3][32] */, Src &src,
                     const Scratch &sc, int lane, int mx, int my) {
   constexpr int NI = GREY ? 1 : 2 + H * V;

@@ -274,7 +274,7 @@ __device__ __forceinline__ Scratch make_scratch(uint8_t *base, uint32_t lane, bo
   return sc;
 }
 
-template <int LAYOUT, bool Q8, bool RGBA, bool ROT, class Src>
+template <int LAYOUT, bool Q8, bool RGBA, int ROT, class Src>
 __device__ __forceinline__ void run_mcu(bool active, const FrameDev &f, Src &src, const Scratch &sc, int lane, int mx,
                                         int my) {
   using LI = LayoutInfo<LAYOUT>;
@@ -283,8 +283,14 @@ __device__ __forceinline__ void run_mcu(bool active, const FrameDev &f, Src &src
 
 // MCU (mx, my) of lane t in a tile starting at m0, or false when the lane has
 // no MCU (tail of the frame / of the MCU row).
-template <int LAYOUT>
+template <int LAYOUT, bool VERT = false>
 __device__ __forceinline__ bool tile_mcu(const FrameDev &f, uint32_t m0, uint32_t t, int &mx, int &my) {
+  if (VERT) {  // quarter turns: 32 MCUs of one column of MCUs, from MCU m0 down
+    const uint32_t my0 = m0 / (uint32_t)f.mcux;
+    mx = (int)(m0 - my0 * (uint32_t)f.mcux);
+    my = (int)(my0 + t);
+    return my < f.mcuy;
+  }
   if (LayoutInfo<LAYOUT>::linear) {
     const uint32_t m = m0 + t;
     my = (int)(m / (uint32_t)f.mcux);
@@ -305,7 +311,7 @@ __device__ __forceinline__ void cache_frame(uint8_t *dst, const FrameDev *src, u
   __syncwarp();
 }
 
-template <int LAYOUT, bool Q8, bool RGBA, int WPC, bool ROT = false>
+template <int LAYOUT, bool Q8, bool RGBA, int WPC, int ROT = TURN_NONE>
 __global__ void __launch_bounds__(Shape<WPC>::kThreads, Shape<WPC>::kCtasPerSm)
 recon_tma_kernel(const __grid_constant__ CUtensorMap map2, const FrameDev *__restrict__ frames, const TileDesc *__restrict__ tiles, uint32_t ntiles,
                  uint32_t *__restrict__ counters) {
@@ -367,7 +373,7 @@ recon_tma_kernel(const __grid_constant__ CUtensorMap map2, const FrameDev *__res
 
 constexpr int kLdgWarps = 4;
 
-template <int LAYOUT, bool Q8, bool RGBA, bool ROT = false>
+template <int LAYOUT, bool Q8, bool RGBA, int ROT = TURN_NONE>
 __global__ void __launch_bounds__(kLdgWarps * 32)
 recon_ldg_kernel(const FrameDev *__restrict__ frames, const TileDesc *__restrict__ tiles, uint32_t ntiles) {
   __shared__ __align__(16) uint8_t s_frame[kLdgWarps][kFrameBytes];
@@ -380,7 +386,7 @@ recon_ldg_kernel(const FrameDev *__restrict__ frames, const TileDesc *__restrict
   cache_frame(s_frame[warp], frames + fi, lane);
   const FrameDev &f = *reinterpret_cast<const FrameDev *>(s_frame[warp]);
   int mx, my;
-  const bool active = tile_mcu<LAYOUT>(f, m0, lane, mx, my);
+  const bool active = tile_mcu<LAYOUT, ROT == TURN_90 || ROT == TURN_270>(f, m0, lane, mx, my);
   LdgSource src{&f};
   run_mcu<LAYOUT, Q8, RGBA, ROT>(active, f, src, make_scratch(s_scratch[warp], lane, true), (int)lane, mx, my);
 }
@@ -493,7 +499,7 @@ generic_color_kernel(const FrameDev *__restrict__ frame, int ncomp, int hmax, in
   }
 }
 
-template <int LAYOUT, bool Q8, bool RGBA, int WPC, bool ROT = false>
+template <int LAYOUT, bool Q8, bool RGBA, int WPC, int ROT = TURN_NONE>
 cudaError_t launch_shape(const CUtensorMap *map2, const FrameDev *d_frames,
                          const TileDesc *d_tiles, uint32_t ntiles, uint32_t *d_counters, int num_sms,
                          bool pdl, cudaStream_t stream) {
@@ -527,25 +533,34 @@ cudaError_t launch_one(bool use_tma, const CUtensorMap *map2, const FrameDev *d_
   return cudaGetLastError();
 }
 
-// FRAME_ROT180 frames: instances of their own (fast domain, wide shape) -- see emit_block_rows
-template <int LAYOUT, bool RGBA>
+// Rotated frames (FRAME_ROT90 / _ROT180 / _ROT270): instances of their own (fast domain, wide shape) -- see
+// emit_block_rows
+template <int LAYOUT, bool RGBA, int ROT>
 cudaError_t launch_rot(bool use_tma, const CUtensorMap *map2, const FrameDev *d_frames, const TileDesc *d_tiles,
                        uint32_t ntiles, uint32_t *d_counters, int num_sms, bool pdl, cudaStream_t stream) {
-  if (use_tma)
-    return launch_shape<LAYOUT, true, RGBA, kWideWarps, true>(map2, d_frames, d_tiles, ntiles, d_counters, num_sms, pdl, stream);
-  recon_ldg_kernel<LAYOUT, true, RGBA, true><<<(ntiles + kLdgWarps - 1) / kLdgWarps, kLdgWarps * 32, 0, stream>>>(
+  // Quarter turns: tiles of 32 MCUs down a column of MCUs (mcu_item).  Their blocks are bx * 128 bytes apart,
+  // not one box of the arena's tensor map: they run the plain-load kernel.
+  constexpr bool kVert = ROT == TURN_90 || ROT == TURN_270;
+  if (use_tma && !kVert)
+    return launch_shape<LAYOUT, true, RGBA, kWideWarps, kVert ? TURN_180 : ROT>(map2, d_frames, d_tiles, ntiles, d_counters, num_sms, pdl, stream);
+  recon_ldg_kernel<LAYOUT, true, RGBA, ROT><<<(ntiles + kLdgWarps - 1) / kLdgWarps, kLdgWarps * 32, 0, stream>>>(
       d_frames, d_tiles, ntiles);
   return cudaGetLastError();
 }
 
 template <int LAYOUT>
-cudaError_t launch_q(bool q8, bool rgba, bool rot, bool use_tma, const CUtensorMap *map2,
+cudaError_t launch_q(bool q8, bool rgba, int rot, bool use_tma, const CUtensorMap *map2,
                      const FrameDev *d_frames, const TileDesc *d_tiles, uint32_t ntiles, uint32_t *d_counters,
                      int num_sms, bool pdl, cudaStream_t stream) {
 #define GIDK_ARGS use_tma, map2, d_frames, d_tiles, ntiles, d_counters, num_sms, pdl, stream
-  if (rot) {
+  if (rot != TURN_NONE) {
     if (!q8) return cudaErrorInvalidValue;  // (frame_setup.hpp sends those frames to the generic kernels)
-    return rgba ? launch_rot<LAYOUT, true>(GIDK_ARGS) : launch_rot<LAYOUT, false>(GIDK_ARGS);
+    switch (rot) {
+      case TURN_90: return rgba ? launch_rot<LAYOUT, true, TURN_90>(GIDK_ARGS) : launch_rot<LAYOUT, false, TURN_90>(GIDK_ARGS);
+      case TURN_180: return rgba ? launch_rot<LAYOUT, true, TURN_180>(GIDK_ARGS) : launch_rot<LAYOUT, false, TURN_180>(GIDK_ARGS);
+      case TURN_270: return rgba ? launch_rot<LAYOUT, true, TURN_270>(GIDK_ARGS) : launch_rot<LAYOUT, false, TURN_270>(GIDK_ARGS);
+      default: return cudaErrorInvalidValue;
+    }
   }
   if (q8) return rgba ? launch_one<LAYOUT, true, true>(GIDK_ARGS) : launch_one<LAYOUT, true, false>(GIDK_ARGS);
   return rgba ? launch_one<LAYOUT, false, true>(GIDK_ARGS) : launch_one<LAYOUT, false, false>(GIDK_ARGS);
@@ -558,7 +573,7 @@ cudaError_t set_attr() {
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<kWideWarps>::kBytes);
   if (e != cudaSuccess) return e;
   if (Q8) {
-    e = cudaFuncSetAttribute(recon_tma_kernel<LAYOUT, true, RGBA, kWideWarps, true>,
+    e = cudaFuncSetAttribute(recon_tma_kernel<LAYOUT, true, RGBA, kWideWarps, TURN_180>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<kWideWarps>::kBytes);
     if (e != cudaSuccess) return e;
   }
@@ -586,11 +601,11 @@ cudaError_t init_kernels() {
   return set_attr_all<LAYOUT_411>();
 }
 
-cudaError_t launch_fused(Layout layout, bool q8, bool rgba, bool rot180, bool use_tma, const CUtensorMap *map2,
+cudaError_t launch_fused(Layout layout, bool q8, bool rgba, int rotate, bool use_tma, const CUtensorMap *map2,
                          const FrameDev *d_frames, const TileDesc *d_tiles, uint32_t ntiles,
                          uint32_t *d_counters, int num_sms, bool pdl, cudaStream_t stream) {
   if (ntiles == 0) return cudaSuccess;
-#define GIDK_ARGS q8, rgba, rot180, use_tma, map2, d_frames, d_tiles, ntiles, d_counters, num_sms, pdl, stream
+#define GIDK_ARGS q8, rgba, rotate, use_tma, map2, d_frames, d_tiles, ntiles, d_counters, num_sms, pdl, stream
   switch (layout) {
     case LAYOUT_GREY: return launch_q<LAYOUT_GREY>(GIDK_ARGS);
     case LAYOUT_444: return launch_q<LAYOUT_444>(GIDK_ARGS);

@@ -35,11 +35,12 @@ static_assert(sizeof(TileDesc) == 32, "TileDesc is 32 bytes");
 //            group (dynamic tile claims; the kernel leaves them zero again), so one
 //            group must not run concurrently with itself.
 //   rgba:    4-byte pixels (a separate kernel instance: the 3-byte kernels do not carry its code)
-//   rot180:  FRAME_ROT180 frames (instances of their own, fast domain only: q8 must be set)
+//   rotate:  Geometry::rotate of the frames; rotated frames run instances of their own (fast domain only:
+//            q8 must be set)
 //   pdl:     launch with programmatic stream serialization: the launch may start while the kernel
 //            before it in the stream is still draining.  Only for launches whose inputs do not come
 //            from that kernel (plans: frames resident and independent); completion order is kept.
-cudaError_t launch_fused(Layout layout, bool q8, bool rgba, bool rot180, bool use_tma, const CUtensorMap *map2,
+cudaError_t launch_fused(Layout layout, bool q8, bool rgba, int rotate, bool use_tma, const CUtensorMap *map2,
                          const FrameDev *d_frames, const TileDesc *d_tiles,
                          uint32_t ntiles, uint32_t *d_counters, int num_sms, bool pdl, cudaStream_t stream);
 
@@ -86,8 +87,9 @@ struct ScanArgs {
   // instances, frame_setup.hpp fast_coef_limit, rounded down to a power of two; at most 15 so that the
   // DC predictor fits the int16 planes): anything wider is left to the host decoder, which marks the frame.
   int32_t limbits[3];
+  uint32_t lanes;               // intervals per warp (set by launch_huffman_intervals)
 };
-cudaError_t launch_huffman_intervals(const ScanArgs &a, cudaStream_t stream);
+cudaError_t launch_huffman_intervals(const ScanArgs &a, int num_sms, cudaStream_t stream);
 
 // ... and for scans without restart markers: self-synchronising parallel decoding (entropy_kernel.cu)
 struct WholeArgs {

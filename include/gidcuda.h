@@ -69,8 +69,11 @@ enum {
  *     ROTATE_270 : H x W,  pixel -> column H - 1 - r, row x
  * in the row order and byte order of the chosen format (for GIDCUDA_OUT_BGR8_BOTTOM_UP that is exactly
  * to_bmp's buffer).  Stride and size (gidcuda_output_geometry) are those of the rotated image.
- * The half turn is done by the fused kernels themselves (mirrored runs, rows bottom to top: the price of
- * an unrotated frame); quarter turns take the two-pass kernels (IDCT, then the pixel pass writes rotated). */
+ * All three are done by the fused kernels themselves, in instances of their own: the half turn writes mirrored
+ * runs, rows bottom to top (the price of an unrotated frame); quarter turns store the samples of a block
+ * transposed and emit its columns as rows of the turned image (24-byte runs in rows 8 apart: 0.3 - 0.6 of the
+ * unrotated rate on the device, the same rate end to end).  Frames outside the fast domain (see
+ * GIDCUDA_FLAG_WIDE_COEF) and samplings without a fused kernel rotate in the two-pass kernels. */
 #define GIDCUDA_FLAG_ROTATE_90 0x200u
 #define GIDCUDA_FLAG_ROTATE_180 0x400u
 #define GIDCUDA_FLAG_ROTATE_270 0x600u

@@ -416,6 +416,10 @@ class Emu:
         self.lib = ctypes.CDLL(os.path.join(_HERE, "libemurecon.so"))
         self.lib.emu_reconstruct.restype = ctypes.c_int
 
+    def layout(self, desc) -> int:
+        """The kernel family a frame runs (recon_body.cuh, Layout; 6 = the generic two-pass kernels)."""
+        return int(self.lib.emu_layout(ctypes.byref(desc)))
+
     def reconstruct(self, desc, planes, stride: int, height: int) -> np.ndarray:
         """desc: gid_b200.FrameDesc; returns (H, stride) uint8 rows."""
         keep = [np.ascontiguousarray(p, dtype=np.int16) for p in planes]

@@ -13,6 +13,14 @@
 
 using namespace gidk;
 
+// the layout make_geometry chooses for a frame (LAYOUT_GENERIC = 6: the two-pass kernels), < 0: refused
+extern "C" int emu_layout(const gidcuda_frame_desc *desc) {
+  Geometry g;
+  std::string e;
+  const int rc = make_geometry(&e, desc, &g);
+  return rc != 0 ? rc : (int)g.layout;
+}
+
 extern "C" int emu_reconstruct(const gidcuda_frame_desc *desc, const int16_t *const planes[3],
                                uint8_t *pixels, char *err, size_t errlen) {
   Geometry g;
@@ -77,7 +85,11 @@ extern "C" int emu_reconstruct(const gidcuda_frame_desc *desc, const int16_t *co
   const bool rgba = f.out_format == OUT_RGBA8;
   const uint32_t nmcu = (uint32_t)(f.mcux * f.mcuy);
   std::vector<uint32_t> tile_m0;
-  if (linear) {
+  const bool vert = (f.flags & (FRAME_ROT90 | FRAME_ROT270)) != 0;  // quarter turns: tiles down the columns of MCUs
+  if (vert) {
+    for (int mx = 0; mx < f.mcux; mx++)
+      for (int my0 = 0; my0 < f.mcuy; my0 += kTileMcusSetup) tile_m0.push_back((uint32_t)(my0 * f.mcux + mx));
+  } else if (linear) {
     for (uint32_t m0 = 0; m0 < nmcu; m0 += kTileMcusSetup) tile_m0.push_back(m0);
   } else {
     for (int my = 0; my < f.mcuy; my++)
@@ -89,7 +101,11 @@ extern "C" int emu_reconstruct(const gidcuda_frame_desc *desc, const int16_t *co
       for (int t = 0; t < kTileMcusSetup; t++) {
         int mx, my;
         bool active;
-        if (linear) {  // tile_mcu of recon_kernels.cu
+        if (vert) {
+          mx = (int)(m0 % (uint32_t)f.mcux);
+          my = (int)(m0 / (uint32_t)f.mcux) + t;
+          active = my < f.mcuy;
+        } else if (linear) {  // tile_mcu of recon_kernels.cu
           const uint32_t m = m0 + (uint32_t)t;
           my = (int)(m / (uint32_t)f.mcux);
           mx = (int)(m - (uint32_t)my * (uint32_t)f.mcux);
@@ -109,7 +125,10 @@ extern "C" int emu_reconstruct(const gidcuda_frame_desc *desc, const int16_t *co
   } while (0)
 #define EMU_RUN(H, V, GREY)                                                                          \
   do {                                                                                               \
-    if (f.flags & FRAME_ROT180) EMU_RUN2(H, V, GREY, true); else EMU_RUN2(H, V, GREY, false);        \
+    if (f.flags & FRAME_ROT180) EMU_RUN2(H, V, GREY, TURN_180);                                      \
+    else if (f.flags & FRAME_ROT90) EMU_RUN2(H, V, GREY, TURN_90);                                   \
+    else if (f.flags & FRAME_ROT270) EMU_RUN2(H, V, GREY, TURN_270);                                 \
+    else EMU_RUN2(H, V, GREY, TURN_NONE);                                                            \
   } while (0)
         switch (g.layout) {
           case LAYOUT_GREY: EMU_RUN(1, 1, true); break;

@@ -40,7 +40,7 @@ def test_bench_line_contract():
     k = d["clocks"]
     assert k["sm_max_mhz"] and not set(k["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     f = d["files"]
-    assert f["value"] > 0 and f["threads"] >= 1 and f["images_per_call"] == 256
+    assert f["value"] > 0 and f["threads"] >= 1 and f["images_per_call"] == 1024
 
 
 def test_reference_arm_line_has_the_same_config_keys():

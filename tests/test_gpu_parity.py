@@ -182,6 +182,22 @@ def _to_bmp_buffer(ref, orientation):
     return buf
 
 
+@pytest.mark.parametrize("samp", ["grey", "444", "422", "420", "440", "411"])
+@pytest.mark.parametrize("w,h", [(512, 40), (1064, 56), (2080, 24)])
+def test_turned_frames_of_several_tile_columns(gpu, oracle, synth, samp, w, h):
+    """Quarter-turned frames list their tiles column by column (launch_set.hpp, append_tiles): frames wide enough
+    for several tiles per MCU row, with and without a cut last tile, MCU counts that are and are not multiples
+    of 32 (grey / 4:4:4: the linear runs then wrap and keep their order)."""
+    from gid_b200 import capi
+    fr = synth.planes_only(pixels_for(synth, 31, w, h, samp), samp)
+    ref = oracle.reconstruct(fr)
+    for k, flag in ((1, capi.FLAG_ROTATE_90), (-1, capi.FLAG_ROTATE_270)):
+        got = gpu.reconstruct_rgb(frame_desc(fr, flag), fr.planes)
+        assert np.array_equal(got, np.rot90(ref, k)), (samp, w, h, k)
+    got = gpu.reconstruct_rgb(frame_desc(fr, capi.FLAG_ROTATE_180 | capi.OUT_RGBA8), fr.planes)
+    assert np.array_equal(got[:, :, :3], ref[::-1, ::-1])
+
+
 @pytest.mark.parametrize("samp", ["grey", "444", "422", "420", "440"])
 def test_display_orientation_applied_to_the_pixels(gpu, oracle, synth, samp):
     """GIDCUDA_FLAG_ROTATE_*: GID.Display_Orientation (EXIF) applied while the pixels are written, as
@@ -272,6 +288,49 @@ def test_plan_device_resident_batch(gpu, oracle, synth):
             k += 1
             got = rows[:, :3 * fr.width].reshape(fr.height, fr.width, 3)
             assert np.array_equal(got, ref), rep
+    gpu.plan_destroy(plan)
+
+
+def test_plan_with_turned_frames(gpu, oracle, synth):
+    """A plan over frames of every orientation: one launch per (layout, orientation) group, every frame where
+    to_bmp's Set_X_Y would put it."""
+    import torch
+    from gid_b200 import capi
+    flags = [0, capi.FLAG_ROTATE_90, capi.FLAG_ROTATE_180, capi.FLAG_ROTATE_270]
+    spec = [(320, 200, "420"), (1064, 72, "420"), (256, 64, "444"), (200, 120, "grey")]
+    frames, descs, d_planes, d_pixels, outs, keep = [], [], [], [], [], []
+    dev = torch.device("cuda:0")
+    for i, (w, h, s) in enumerate(spec):
+        for flag in flags:
+            fr = synth.planes_only(pixels_for(synth, 40 + i, w, h, s), s)
+            d = frame_desc(fr, flag)
+            _, nbytes = gpu.output_geometry(d)
+            frames.append((fr, flag))
+            descs.append(d)
+            for c in range(3):
+                if c < fr.ncomp:
+                    t = torch.from_numpy(fr.planes[c].reshape(-1)).to(dev)
+                    keep.append(t)
+                    d_planes.append(t.data_ptr())
+                else:
+                    d_planes.append(0)
+            out = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+            outs.append(out)
+            d_pixels.append(out.data_ptr())
+    torch.cuda.synchronize()
+    plan = gpu.plan_create(descs, d_planes, d_pixels)
+    assert gpu.plan_launch_count(plan) == 3 * 4  # three layouts x four orientations
+    for rep in range(2):
+        gpu.plan_launch(plan, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    for (fr, flag), d, out in zip(frames, descs, outs):
+        ref = oracle.reconstruct(fr)
+        want = {0: ref, capi.FLAG_ROTATE_90: np.rot90(ref, 1), capi.FLAG_ROTATE_180: ref[::-1, ::-1],
+                capi.FLAG_ROTATE_270: np.rot90(ref, -1)}[flag]
+        stride, _ = gpu.output_geometry(d)
+        oh, ow = want.shape[:2]
+        got = out.cpu().numpy().reshape(oh, stride)[:, :3 * ow].reshape(oh, ow, 3)
+        assert np.array_equal(got, want), (fr.width, fr.height, flag)
     gpu.plan_destroy(plan)
 
 

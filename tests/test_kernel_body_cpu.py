@@ -106,16 +106,39 @@ def test_half_turn_in_the_fused_kernels(emu, oracle, synth, gidcuda_lib, samp, w
     (mirrored runs, rows bottom to top), for whole and cut blocks, aligned and unaligned widths, every format."""
     from gid_b200 import capi
     fr = synth.planes_only(pixels_for(synth, 17, w, h, samp), samp)
-    ref = oracle.reconstruct(fr)[::-1, ::-1]
+    _check_turned(emu, gidcuda_lib, fr, capi.FLAG_ROTATE_180, oracle.reconstruct(fr)[::-1, ::-1], samp)
+
+
+def _check_turned(emu, gidcuda_lib, fr, flag, ref, samp):
+    from gid_b200 import capi
+    oh, ow = ref.shape[:2]
     for flags, stride in ((0, 0), (capi.FLAG_PACKED_ROWS, 0), (capi.OUT_BGR8_BOTTOM_UP, 0), (capi.OUT_RGBA8, 0),
-                          (capi.OUT_RGBA8, 4 * w + 4)):
-        d = frame_desc(fr, flags | capi.FLAG_ROTATE_180, stride)
-        rows = emu.reconstruct(d, fr.planes, _stride(gidcuda_lib, d), h)
+                          (capi.OUT_RGBA8, 4 * ow + 4), (0, 3 * ow + 5)):
+        d = frame_desc(fr, flags | flag, stride)
+        assert emu.layout(d) != 6, "the frame must run a fused kernel body"
+        rows = emu.reconstruct(d, fr.planes, _stride(gidcuda_lib, d), oh)
         bpp = 4 if (flags & 0xFF) == capi.OUT_RGBA8 else 3
-        got = rows[:, :bpp * w].reshape(h, w, bpp)[:, :, :3]
+        got = rows[:, :bpp * ow].reshape(oh, ow, bpp)[:, :, :3]
         if (flags & 0xFF) == capi.OUT_BGR8_BOTTOM_UP:
             got = got[::-1, :, ::-1]
-        assert np.array_equal(got, ref), (samp, w, h, flags, stride)
+        assert np.array_equal(got, ref), (samp, fr.width, fr.height, flags, stride)
+        if bpp == 4:
+            assert (rows[:, :4 * ow].reshape(oh, ow, 4)[:, :, 3] == 255).all()
+        assert not rows[:, bpp * ow:].any(), "bytes beyond a row's pixels were written"
+
+
+@pytest.mark.parametrize("samp", ["grey", "444", "422", "420", "440", "411"])
+@pytest.mark.parametrize("w,h", [(64, 48), (211, 77), (40, 9), (9, 40), (1056, 16), (24, 1064)])
+def test_quarter_turns_in_the_fused_kernels(emu, oracle, synth, gidcuda_lib, samp, w, h):
+    """GIDCUDA_FLAG_ROTATE_90 / _270 (test/to_bmp.adb:104-122, Set_X_Y): pixel (x, r) lands at column r, row
+    W - 1 - x / at column H - 1 - r, row x of an image H wide and W high.  The fused kernels store the samples of
+    a block transposed and emit its columns as the rows of the turned image: whole and cut blocks, heights that
+    are and are not multiples of 8 (the mirrored runs of _270), every format."""
+    from gid_b200 import capi
+    fr = synth.planes_only(pixels_for(synth, 23, w, h, samp), samp)
+    ref = oracle.reconstruct(fr)
+    _check_turned(emu, gidcuda_lib, fr, capi.FLAG_ROTATE_90, np.rot90(ref, 1), samp)
+    _check_turned(emu, gidcuda_lib, fr, capi.FLAG_ROTATE_270, np.rot90(ref, -1), samp)
 
 
 def test_idct_blocks_match_oracle(emu, oracle):

@@ -16,6 +16,7 @@ if os.environ.get("FILES_SPARSE_INPUT"):
 for wl in (sys.argv[1:] or ["cfg3"]):
     w, h, _, _, _ = bench.WORKLOADS[wl]
     prog, ri, per_call = bench.FILE_FORM[wl]
+    per_call = int(os.environ.get("FILES_PER_CALL", per_call))   # (length of a call: its ramp and drain are inside the time)
     distinct = bench.make_files(wl, 2, 77)
     files = [distinct[i % 2] for i in range(per_call)]
     from gid_b200 import capi
@@ -24,7 +25,7 @@ for wl in (sys.argv[1:] or ["cfg3"]):
     # entropy decode alone (no device), one thread
     t0 = time.perf_counter(); host_api.decode_planes(distinct[0]); t1 = time.perf_counter()
     print(f"{wl}: decode_planes (1 thread, incl. allocation + copy to numpy) {w*h/1e6/(t1-t0):.0f} MP/s", flush=True)
-    T = 1
+    T = int(os.environ.get("FILES_MIN_THREADS", 1))
     ncpu = os.cpu_count() or 1
     while True:
         with host_api.HostBatch(devices=(0,), threads=T) as hb:

@@ -38,6 +38,25 @@ KEYS = [
     "launch__occupancy_limit_shared_mem",
     "launch__occupancy_limit_warps",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    # the store path (rotated frames: runs of 24 bytes in 32 different rows per store instruction)
+    "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum",
+    "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_global_op_st.sum",   # (not in every ncu version)
+    "l1tex__data_pipe_lsu_wavefronts.sum",
+    "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sectors_op_write.sum",
+    "lts__t_sectors_srcunit_tex_op_write.sum",
+    "lts__t_sectors.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_bytes.sum.per_second",
+    "l1tex__m_xbar2l1tex_read_bytes.sum.per_second",
+    "l1tex__m_l1tex2xbar_write_bytes.sum.per_second",
+    "l1tex__m_l1tex2xbar_write_bytes.sum.pct_of_peak_sustained_elapsed",
+    "lts__d_sectors_fill_sysmem.sum",
+    "lts__t_sectors_lookup_miss.sum",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed",
 ]
 
 
