@@ -269,25 +269,31 @@ struct BitReader {  // :594-690
   uint8_t memo_marker = 0;  // a marker met while filling (it WILL appear at the end of the scan)
   explicit BitReader(Reader &rd) : r(rd) {}
   void reset() { buf = 0; len = 0; memo_marker = 0; }
+  // Show_Bits' loop (:621-671) as it is: a marker's two bytes go into the buffer like any others, the marker is
+  // remembered, and the loading carries on behind it; past the end of the data every byte asked for is FF.
   void fill(int bits) {
     while (len < bits) {
-      uint8_t b;
-      if (memo_marker != 0 || r.s.pos >= r.s.size) {
-        b = 0xFF;  // past a marker / end of data: pad (the reference pads with FF at End_Error, :665-670)
-      } else {
-        b = r.s.data[r.s.pos++];
-        if (b == 0xFF) {
-          const uint8_t m = r.s.pos < r.s.size ? r.s.data[r.s.pos++] : 0xD9;
-          if (m != 0) {  // byte stuffing FF 00 -> FF; anything else is a marker
-            const bool ok = m == M_EOI || m == M_COM || m == M_DHT || m == M_DRI || m == M_SOS ||
-                            (m >= M_RST0 && m <= M_RST7);
-            if (!ok) throw error_in_image_data(fmt("JPEG: Invalid marker within filling of bit buffer: 16#%02X#", m));
-            memo_marker = m;
-          }
-        }
+      if (r.s.pos >= r.s.size) {  // End_Error
+        buf = (buf << 8) | 0xFFu;
+        len += 8;
+        continue;
       }
+      const uint8_t b = r.s.data[r.s.pos++];
       buf = (buf << 8) | b;
       len += 8;
+      if (b != 0xFF) continue;
+      if (r.s.pos >= r.s.size) {  // End_Error at the byte behind the FF: the handler puts one more FF in
+        buf = (buf << 8) | 0xFFu;
+        len += 8;
+        continue;
+      }
+      const uint8_t m = r.s.data[r.s.pos++];
+      if (m == 0) continue;       // byte stuffing: FF 00 is a data byte FF
+      buf = (buf << 8) | m;
+      len += 8;
+      memo_marker = m;
+      const bool ok = m == M_EOI || m == M_COM || m == M_DHT || m == M_DRI || m == M_SOS || (m >= M_RST0 && m <= M_RST7);
+      if (!ok) throw error_in_image_data(fmt("JPEG: Invalid marker within filling of bit buffer: 16#%02X#", m));
     }
   }
   int show(int bits) {
@@ -326,23 +332,29 @@ struct BitReader {  // :594-690
   int receive_extend(int bits) { return bits ? extend(get(bits), bits) : 0; }
 };
 
-// The bit buffer again, 64 bits wide, for the baseline scan loop (the progressive scans keep
-// BitReader).  Same observable behaviour as BitReader / the reference's byte-wise buffer:
-//   * FF 00 is a stuffed FF; the first marker met stops the loading for good (memo_marker), the
-//     buffer is then padded with FF bytes; so is the end of the data;
-//   * a marker that may not appear inside entropy-coded data raises -- but only when the decoder
-//     asks for bits beyond the last real one, which is when the byte-wise buffer would have
-//     loaded it (it loads a byte only while it holds fewer bits than requested).  The wide buffer
-//     meets the marker earlier, remembers it (`bad`) and raises at that same request: need().
-// The buffer is left-aligned: the next bit is bit 63; `len` bits are valid, the last `pad` of
-// them padding.
+// The bit buffer again, 64 bits wide.  Same observable behaviour as BitReader / the reference's byte-wise buffer
+// (Show_Bits, :609-677):
+//   * FF 00 is a stuffed FF; entropy-coded bytes are loaded ahead of the requests, eight at a time where none
+//     of them is FF -- which nobody can tell, they are the bytes the byte-wise buffer loads a little later;
+//   * at the first marker (FF followed by anything but 00) the loading ahead stops BEFORE it (`lazy`).  From
+//     there on bytes are loaded exactly when the byte-wise buffer loads them -- when a request finds fewer bits
+//     than it asks for (lazy_fill): the marker's two bytes go into the buffer, the marker is remembered
+//     (memo_marker) or raises if it may not appear inside entropy-coded data, and the loading carries on behind
+//     it, as the reference's does.  Both buffers hold the same bits at that point (the wide one never went
+//     beyond the marker), so they load the same bytes at the same requests from then on, and `pos` is the
+//     reference's stream position (`exact`);
+//   * past the end of the data every byte asked for is FF (End_Error, :665-670).
+// The buffer is left-aligned: the next bit is bit 63; `len` bits are valid, the last `pad` of them are not
+// entropy-coded data of the scan (marker bytes, what follows them, FF past the end).
 struct WideBits {
   const uint8_t *data;
   size_t pos, size;
   uint64_t buf = 0;
   int len = 0, pad = 0;
   uint8_t memo_marker = 0, bad = 0;
-  bool stopped = false;
+  bool stopped = false;  // past the end of the data
+  bool lazy = false;     // the next byte is the FF of a marker (or an FF that ends the data): no loading ahead
+  bool exact = false;    // bytes were loaded on request: pos and memo_marker are the reference's
   // Progressive scans: the segment loop carries on where the reference's byte-wise buffer stopped
   // reading.  With `track` set the wide buffer follows that buffer's fill level (it loads a byte
   // whenever it holds fewer bits than are asked for, :622-690) and counts the bytes it would
@@ -351,9 +363,13 @@ struct WideBits {
   int ref_len = 0;
   size_t ref_loaded = 0;
   WideBits(const uint8_t *d, size_t p, size_t n) : data(d), pos(p), size(n) {}
-  void reset() { buf = 0; len = 0; pad = 0; memo_marker = 0; bad = 0; stopped = false; ref_len = 0; ref_loaded = 0; }
+  void reset() {
+    buf = 0; len = 0; pad = 0; memo_marker = 0; bad = 0; stopped = false; lazy = false; exact = false;
+    ref_len = 0; ref_loaded = 0;
+  }
   int real() const { return len - pad; }
   void refill() {
+    if (lazy) return;
     if (!stopped && len <= 32 && pos + 8 <= size) {  // eight bytes at once when none of them is FF
       uint64_t v;
       memcpy(&v, data + pos, 8);
@@ -370,32 +386,55 @@ struct WideBits {
     while (len <= 56) {
       uint64_t b = 0xFF;
       if (stopped || pos >= size) {
-        stopped = true;  // past a marker / the end of the data: FF padding (:665-670)
+        stopped = true;  // the end of the data: FF padding (:665-670)
         pad += 8;
       } else {
-        b = data[pos++];
+        b = data[pos];
         if (b == 0xFF) {
-          const uint8_t m = pos < size ? data[pos++] : (uint8_t)M_EOI;
-          if (m != 0) {
-            const bool ok = m == M_EOI || m == M_COM || m == M_DHT || m == M_DRI || m == M_SOS ||
-                            (m >= M_RST0 && m <= M_RST7);
-            if (ok) memo_marker = m; else bad = m;
-            stopped = true;
-            pad += 8;
+          if (pos + 1 >= size || data[pos + 1] != 0) {  // a marker, or an FF that ends the data
+            lazy = true;
+            return;
           }
+          pos += 2;  // byte stuffing
+        } else {
+          pos++;
         }
       }
       buf |= b << (56 - len);
       len += 8;
     }
   }
-  // the decoder is about to look at n bits: raise what the byte-wise buffer would raise there
+  // Show_Bits' loop as it is (:621-671), from the marker on
+  void push_beyond(uint64_t b) {
+    buf |= b << (56 - len);
+    len += 8;
+    pad += 8;
+  }
+  void lazy_fill(int n) {
+    exact = true;
+    while (len < n) {
+      if (pos >= size) { push_beyond(0xFF); continue; }  // End_Error
+      const uint8_t b = data[pos++];
+      push_beyond(b);
+      if (b != 0xFF) continue;
+      if (pos >= size) { push_beyond(0xFF); continue; }  // End_Error at the byte behind the FF
+      const uint8_t m = data[pos++];
+      if (m == 0) continue;  // byte stuffing
+      push_beyond(m);
+      memo_marker = m;
+      const bool ok = m == M_EOI || m == M_COM || m == M_DHT || m == M_DRI || m == M_SOS || (m >= M_RST0 && m <= M_RST7);
+      if (!ok) throw error_in_image_data(fmt("JPEG: Invalid marker within filling of bit buffer: 16#%02X#", m));
+    }
+    ref_len = len;
+  }
+  // the decoder is about to look at n bits (n <= 32)
   void need(int n) {
-    if (track)
+    if (track && !exact)
       while (ref_len < n) { ref_len += 8; ref_loaded++; }
-    if (len < n) refill();
-    if (bad && n > real())
-      throw error_in_image_data(fmt("JPEG: Invalid marker within filling of bit buffer: 16#%02X#", bad));
+    if (len < n) {
+      refill();
+      if (len < n) lazy_fill(n);
+    }
   }
   int peek(int n) const { return (int)(buf >> (64 - n)); }  // 1 <= n <= 32
   void drop(int n) {
@@ -408,6 +447,10 @@ struct WideBits {
   // `start`: the stream position after the ref_loaded-th data byte (FF 00 counts as one), or just
   // past the first marker when it would have run into it (*marker = that marker, else 0).
   size_t reference_position(size_t start, uint8_t *marker) const {
+    if (exact) {  // bytes were loaded on request from the marker on: the position is the reference's own
+      *marker = memo_marker;
+      return pos;
+    }
     size_t i = start, count = 0;
     *marker = 0;
     while (count < ref_loaded && i < size) {
@@ -431,14 +474,15 @@ struct WideBits {
   // refinement scan): the same bits, and the same bookkeeping of what the byte-wise buffer would have loaded
   // by then (it loads a byte whenever it is empty), in one step
   int get_serial(int n) {
-    if (track && n > ref_len) {
+    if (track && !exact && n > ref_len) {
       const int k = (n - ref_len + 7) >> 3;
       ref_len += 8 * k;
       ref_loaded += (size_t)k;
     }
-    if (len < n) refill();
-    if (bad && n > real())
-      throw error_in_image_data(fmt("JPEG: Invalid marker within filling of bit buffer: 16#%02X#", bad));
+    if (len < n) {
+      refill();
+      if (len < n) lazy_fill(n);
+    }
     const int v = peek(n);
     drop(n);
     return v;
@@ -532,11 +576,8 @@ struct Decoder {
     if (--rst_count != 0) return;
     bits.len &= 0xF8;  // byte alignment
     const int w = bits.get(16);
-    // the marker bytes themselves were not pushed into the buffer by this reader:
-    // it remembers the marker and pads; accept either view of the 16 bits
     const int expected = 0xFFD0 + next_rst;
-    const bool seen = bits.memo_marker == (uint8_t)(0xD0 + next_rst);
-    if (!seen && w != expected)
+    if (w != expected)
       throw error_in_image_data(fmt("JPEG: expected RST (restart) marker Nb %d; code found %04X; expected %04X",
                                     next_rst, w, expected));
     bits.reset();
@@ -610,15 +651,13 @@ struct Decoder {
   }
 
   // Check_Restart (:1133-1177) on the wide buffer: byte-align, the next 16 bits must be the
-  // expected RSTn.  The byte-wise buffer "sees" the marker iff fewer than 16 real bits are
-  // left after the alignment (then its Get_Bits (16) runs into the marker and remembers it).
+  // expected RSTn -- the marker's own two bytes, loaded by this request (WideBits::lazy_fill).
   void check_restart_wide(WideBits &wb) {
     if (im.restart_interval <= 0) return;
     if (--rst_count != 0) return;
     wb.drop(wb.len & 7);
     wb.need(16);
-    const bool seen = wb.real() < 16 && wb.memo_marker == (uint8_t)(0xD0 + next_rst);
-    if (!seen)
+    if (wb.peek(16) != 0xFFD0 + next_rst)
       throw error_in_image_data(fmt("JPEG: expected RST (restart) marker Nb %d; code found %04X; expected %04X",
                                     next_rst, wb.peek(16), 0xFFD0 + next_rst));
     wb.reset();
@@ -911,8 +950,12 @@ struct Decoder {
     mag[c] |= magnitude(dc_pred[c] * (1 << al));
     blk[0] = (int16_t)(dc_pred[c] * (1 << al));
   }
-  template <class B> void dc_refine(B &bits, int16_t *blk, int al) {
-    if (bits.get(1)) blk[0] = (int16_t)(blk[0] | (1 << al));
+  template <class B> void dc_refine(B &bits, int c, int16_t *blk, int al) {
+    if (bits.get(1)) {  // (added, not OR-ed: :1320-1326)
+      const int v = blk[0] + (1 << al);
+      mag[c] |= magnitude(v);
+      blk[0] = (int16_t)v;
+    }
   }
   // Which AC coefficients of a block are non-zero, bit k = zig-zag position k: kept beside the planes of
   // a progressive frame so that the refinement scans -- which visit every position of the band in every
@@ -948,56 +991,74 @@ struct Decoder {
       }
     }
   }
+  // Progressive_AC_Scan, refining (:1515-1689), one block's share of it.  The reference's own control flow, so
+  // that streams no encoder writes come out as they do there:
+  //   * a new coefficient may have any size s (its value is Bin_Twos_Complement of s bits, times 2**al; :1580-1616);
+  //   * a zero run is walked without regard to the end of the band (:1561-1573): it may carry the index past
+  //     it, and raises Constraint_Error (zag_zig's range) past coefficient 63;
+  //   * a correction bit is ADDED to the magnitude of the coefficient, whatever its bits (:1433-1447);
+  //   * the coefficients an end-of-band run passes wait in a list of 2000 for their bits (Append, :1402-1415):
+  //     a longer run raises Constraint_Error.
+  // The order of the reads is the reference's: the walk reads nothing, then the bits of the new value, then one
+  // bit per coefficient passed.
+  int eob_points = 0;  // coefficients passed by the end-of-band run under way
   template <class B> void ac_refine(B &bits, int c, int16_t *blk, int ss, int se, int al) {
-    const int p1 = 1 << al, m1 = -(1 << al);
-    mag[c] |= (uint32_t)p1;  // new coefficients are +-p1; corrections only set a bit below an existing leading one
+    const int p1 = 1 << al;
     int k = ss;
     uint64_t &mask = mask_of(c, blk);
+    auto correct = [&](int kk) {  // Refine_Batch, one point
+      if (!bits.get(1)) return;
+      int16_t &z = blk[kZigZag[kk]];
+      const int v = z > 0 ? z + p1 : z - p1;
+      mag[c] |= magnitude(v);
+      z = (int16_t)v;
+      mask = z != 0 ? mask | (1ull << kk) : mask & ~(1ull << kk);
+    };
     if (eobrun <= 0) {
       const HuffTable &ac = table(1, ht_ac[c]);
-      for (; k <= se; k++) {
+      while (k <= se) {
         const int rs = bits.symbol(ac);
-        int rr = rs >> 4;
-        const int s = rs & 15;
-        int value = 0;
-        if (s == 0) {
-          if (rr < 15) {
-            eobrun = 1 << rr;
-            if (rr) eobrun += bits.get(rr);
-            break;
-          }
-        } else {
-          if (s != 1) throw error_in_image_data("JPEG: progressive: AC refinement with a size other than 1");
-          value = bits.get(1) ? p1 : m1;
+        const int rr = rs >> 4, s = rs & 15;
+        if (s == 0 && rr < 15) {
+          eobrun = 1 << rr;
+          if (rr) eobrun += bits.get(rr);
+          eob_points = 0;
+          break;
         }
-        for (; k <= se; k++) {
-          if ((mask >> k) & 1u) {
-            int16_t &z = blk[kZigZag[k]];
-            if (bits.get(1) && (z & p1) == 0) z = (int16_t)(z >= 0 ? z + p1 : z + m1);
-          } else {
-            if (rr == 0) {
-              if (value) {
-                int16_t &z = blk[kZigZag[k]];
-                z = (int16_t)value;
-                if (z != 0) mask |= 1ull << k;
-                if ((kZigZag[k] >> 3) > last_row[c]) last_row[c] = kZigZag[k] >> 3;
-              }
-              break;
-            }
-            rr--;
-          }
+        uint8_t passed[64];
+        int npassed = 0;
+        for (int zero_run = s == 0 ? 16 : rr; zero_run > 0; k++) {
+          if (k > 63) throw constraint_error("JPEG: progressive: zag_zig index out of range");
+          if ((mask >> k) & 1ull) passed[npassed++] = (uint8_t)k;
+          else zero_run--;
         }
+        if (s != 0) {
+          const int value = BitReader::extend(bits.get(s), s) * p1;
+          if (k > 63) throw constraint_error("JPEG: progressive: zag_zig index out of range");
+          while ((mask >> k) & 1ull) {
+            passed[npassed++] = (uint8_t)k;
+            if (++k > 63) throw error_in_image_data("JPEG, progressive: zig-zag index overflow");
+          }
+          mag[c] |= magnitude(value);
+          int16_t &z = blk[kZigZag[k]];
+          z = (int16_t)value;
+          if (z != 0) mask |= 1ull << k;
+          if ((kZigZag[k] >> 3) > last_row[c]) last_row[c] = kZigZag[k] >> 3;
+          k++;
+        }
+        for (int i = 0; i < npassed; i++) correct(passed[i]);
       }
     }
     if (eobrun > 0) {
       // the rest of the band: only the non-zero coefficients take a correction bit, in zig-zag order
       if (k <= se) {
         uint64_t m = mask & (~0ull << k) & (se >= 63 ? ~0ull : ((1ull << (se + 1)) - 1ull));
+        eob_points += __builtin_popcountll(m);
+        if (eob_points > 2000) throw constraint_error("Progressive JPEG: refining buffer capacity 2000 exceeded");
         while (m) {
           const int kk = __builtin_ctzll(m);
           m &= m - 1;
-          int16_t &z = blk[kZigZag[kk]];
-          if (bits.get(1) && (z & p1) == 0) z = (int16_t)(z >= 0 ? z + p1 : z + m1);
+          correct(kk);
         }
         k = se + 1;
       }
@@ -1045,10 +1106,13 @@ struct Decoder {
           if (rr < 15) {
             eobrun = 1 << rr;
             if (rr) eobrun += bits.get(rr);
+            eob_points = 0;
             break;
           }
         } else {
-          if (s != 1) throw error_in_image_data("JPEG: progressive: AC refinement with a size other than 1");
+          // (what no encoder writes -- a size other than 1, a run that leaves the band, an end-of-band run over
+          // more than 2000 coefficients -- is the host decoder's: it follows the reference's control flow there)
+          if (s != 1) throw device_declined();
           value = bits.get(1) ? 1 : -1;
         }
         for (; k <= se; k++) {
@@ -1066,11 +1130,14 @@ struct Decoder {
             rr--;
           }
         }
+        if (k > se) throw device_declined();  // the run went past the end of the band
       }
     }
     if (eobrun > 0) {
       if (k <= se) {
         uint64_t m = mask & (~0ull << k) & (se >= 63 ? ~0ull : ((1ull << (se + 1)) - 1ull));
+        eob_points += __builtin_popcountll(m);
+        if (eob_points > 2000) throw device_declined();
         while (m) {
           const int kk = __builtin_ctzll(m);
           m &= m - 1;
@@ -1112,15 +1179,17 @@ struct Decoder {
           if (rr < 15) {
             eobrun = 1 << rr;
             if (rr) eobrun += bits.get(rr);
+            eob_points = 0;
             break;
           }
         } else {
-          if (s != 1) throw error_in_image_data("JPEG: progressive: AC refinement with a size other than 1");
+          if (s != 1) throw device_declined();  // (see ac_refine_history)
           value = bits.get(1) ? 1 : -1;
         }
         // pass rr zero positions and stop at the next one; every non-zero position on the way reads a bit
         const uint64_t from = band & (~0ull << k);
         const uint64_t target = __builtin_ia32_pdep_di(1ull << rr, ~mask & from);
+        if (!target) throw device_declined();   // the run went past the end of the band
         const int kt = target ? __builtin_ctzll(target) : se + 1;
         read_corrections(bits, mask & from & (kt > 63 ? ~0ull : ((1ull << kt) - 1ull)), corr);
         if (target && value) {
@@ -1132,7 +1201,12 @@ struct Decoder {
       }
     }
     if (eobrun > 0) {
-      if (k <= se) read_corrections(bits, mask & band & (~0ull << k), corr);
+      if (k <= se) {
+        const uint64_t m = mask & band & (~0ull << k);
+        eob_points += __builtin_popcountll(m);
+        if (eob_points > 2000) throw device_declined();
+        read_corrections(bits, m, corr);
+      }
       eobrun--;
     }
   }
@@ -1149,6 +1223,7 @@ struct Decoder {
     ac_refine_history(bits, c, mask, corr, newpos, newneg, ss, se);
   }
   bool force_portable_refine = false;
+  int8_t coded_al[3][64] = {};    // device path: the bit down to which each coefficient of a component has been coded (-1: not yet), see device_progressive_scan
   bool selftest_refine = false;   // see progressive_scan
   size_t selftest_pos = 0;
   uint8_t selftest_marker = 0;
@@ -1158,6 +1233,8 @@ struct Decoder {
     if (im.restart_interval != 0) throw device_declined();
     if (ss > se || se > 63) throw error_in_image_data("JPEG: progressive: bad spectral selection");
     if (ss == 0 && se != 0) throw error_in_image_data("JPEG: progressive: DC and AC in the same scan");
+    if (ah != 0 && ah - al != 1)  // :1716-1727
+      throw error_in_image_data("JPEG, progressive: precision improvement has to be by one bit.");
     if (ss > 0 && ncomps != 1) throw error_in_image_data("JPEG: progressive: AC scan with several components");
     int ncomp_image = 0;
     for (const Component_Info &ci : im.info) ncomp_image += ci.present ? 1 : 0;
@@ -1165,6 +1242,15 @@ struct Decoder {
     rst_count = 0;
     next_rst = 0;
     eobrun = 0;
+    // The device refines by setting one bit (DC) and by the libjpeg rule (AC); the reference ADDS the bit
+    // (:1320-1326, :1433-1447).  The two agree when the bit is clear, which it is when every coefficient the
+    // scan touches was last coded down to bit al + 1 -- the successive approximation every encoder writes.
+    for (int i = 0; i < ncomps; i++)
+      for (int k = ss; k <= se; k++) {
+        int8_t &p = coded_al[comps[i]][k];
+        if (ah > 0 && (ah != al + 1 || p != ah)) throw device_declined();
+        p = (int8_t)al;
+      }
     const uint8_t *d = r.s.data;
     const size_t size = r.s.size, start = r.s.pos;
     if (ss > 0 && ah > 0) {
@@ -1188,11 +1274,16 @@ struct Decoder {
       const int bw = (wc + 7) / 8, bh = (hc + 7) / 8;
       WideBits wb(d, start, size);
       wb.track = true;
-      for (int by = 0; by < bh; by++)
-        for (int bx = 0; bx < bw; bx++) {
-          const size_t pb = (size_t)by * (size_t)hist_bx[c] + (size_t)bx;
-          ac_refine_history_auto(wb, c, hist[c][pb], corr[pb], newpos[pb], newneg[pb], ss, se);
-        }
+      try {
+        for (int by = 0; by < bh; by++)
+          for (int bx = 0; bx < bw; bx++) {
+            const size_t pb = (size_t)by * (size_t)hist_bx[c] + (size_t)bx;
+            ac_refine_history_auto(wb, c, hist[c][pb], corr[pb], newpos[pb], newneg[pb], ss, se);
+          }
+      } catch (const gid_error &) {
+        throw device_declined();  // whatever the stream raises, the host decoder raises it (or carries on as the reference does)
+      }
+      if (eobrun > 0) throw device_declined();  // an end-of-band run that reaches past the last block
       device_refine_commit(c, al);
       detail::ns_refine_host.fetch_add(
           std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t1).count(), std::memory_order_relaxed);
@@ -1257,6 +1348,7 @@ struct Decoder {
 
   void progressive_scan(const int *comps, int ncomps, int ss, int se, int ah, int al) {
     if (scans == 0) {
+      memset(coded_al, -1, sizeof coded_al);
       // the whole frame on the device, or none of it: decided here, at its first scan
       device_progressive = device_pscan && device_pscan_begin && im.restart_interval == 0 &&
                            r.s.size >= device_pscan_min_bytes && device_pscan_begin(r.s.size - r.s.pos);
@@ -1288,11 +1380,19 @@ struct Decoder {
         WideBits w2(r.s.data, start, r.s.size);
         w2.track = true;
         eobrun = 0;
-        for (int by = 0; by < bh; by++)
-          for (int bx = 0; bx < bw; bx++) {
-            const size_t pb = (size_t)by * (size_t)plane[c].blocks_x + (size_t)bx;
-            ac_refine_history_auto(w2, c, h[pb], corr[pb], np[pb], nn[pb], ss, se);
-          }
+        bool usual = ah == al + 1;
+        try {
+          for (int by = 0; by < bh && usual; by++)
+            for (int bx = 0; bx < bw; bx++) {
+              const size_t pb = (size_t)by * (size_t)plane[c].blocks_x + (size_t)bx;
+              ac_refine_history_auto(w2, c, h[pb], corr[pb], np[pb], nn[pb], ss, se);
+            }
+          if (eobrun > 0) usual = false;
+        } catch (const gid_error &) {
+          usual = false;   // (a damaged scan: the decoder proper below raises what there is to raise)
+        } catch (const device_declined &) {
+          usual = false;   // (a scan the device path hands to the host decoder)
+        }
         const int p1 = 1 << al, m1 = -(1 << al);
         for (size_t b = 0; b < nb; b++) {
           int16_t *blk = shadow.data() + b * 64;
@@ -1306,7 +1406,7 @@ struct Decoder {
           }
         }
         selftest_pos = w2.reference_position(start, &selftest_marker);
-        shadow_c = c;
+        shadow_c = usual ? c : -1;
       }
       WideBits wb(r.s.data, start, r.s.size);
       wb.track = true;
@@ -1331,6 +1431,8 @@ struct Decoder {
   void progressive_scan_with(B &bits, const int *comps, int ncomps, int ss, int se, int ah, int al) {
     if (ss > se || se > 63) throw error_in_image_data("JPEG: progressive: bad spectral selection");
     if (ss == 0 && se != 0) throw error_in_image_data("JPEG: progressive: DC and AC in the same scan");
+    if (ah != 0 && ah - al != 1)  // :1716-1727
+      throw error_in_image_data("JPEG, progressive: precision improvement has to be by one bit.");
     if (ss > 0 && ncomps != 1) throw error_in_image_data("JPEG: progressive: AC scan with several components");
     ensure_host_output();
     for (int i = 0; i < ncomps; i++) {
@@ -1353,7 +1455,7 @@ struct Decoder {
               for (int sx = 0; sx < ci.samples_hor; sx++) {
                 int16_t *blk = plane[c].block(mx * ci.samples_hor + sx, my * ci.samples_ver + sy);
                 if (ah == 0) dc_first(bits, c, blk, al);
-                else dc_refine(bits, blk, al);
+                else dc_refine(bits, c, blk, al);
               }
           }
           if (!(my == mcu_count_image_v - 1 && mx == mcu_count_image_h - 1)) check_restart(true);
@@ -1373,7 +1475,7 @@ struct Decoder {
         int16_t *blk = plane[c].block(bx, by);
         if (ss == 0) {
           if (ah == 0) dc_first(bits, c, blk, al);
-          else dc_refine(bits, blk, al);
+          else dc_refine(bits, c, blk, al);
         } else if (ah == 0) {
           ac_first(bits, c, blk, ss, se, al);
         } else {
@@ -1383,16 +1485,24 @@ struct Decoder {
       }
       if (first_scan) emit_feedback((50 * (by + 1)) / bh);
     }
+    // An end-of-band run of a refining scan walks on through the blocks it covers as soon as it is read
+    // (:1650-1675): past the component's last block that is rows of the image array no scan has written
+    // (8 * max_samples_ver * MCU rows high for every component, Create_Image_Array :1857-1883) -- nothing to
+    // refine there -- and past the array's last row Constraint_Error.
+    if (ss > 0 && ah > 0 && eobrun > 0) {
+      const long rows = (long)mcu_count_image_v * im.max_samples_ver;
+      if ((long)eobrun > (rows - bh) * (long)bw) throw constraint_error("JPEG: progressive: image_array index out of range");
+    }
   }
 
   // Read_SOS (:1855-2034): scan header, then the scan's entropy-coded data.
-  void read_sos(const Segment &sg) {
+  void read_sos(const Segment &) {
     const int n = r.byte();
     int ncomp_image = 0;
     for (const Component_Info &ci : im.info) ncomp_image += ci.present ? 1 : 0;
     if (n > ncomp_image) throw error_in_image_data("JPEG: Scan segment has more color components than the image");
     if (n < 1) throw error_in_image_data("JPEG: Scan segment without components");
-    if (sg.length != 4 + 2 * n) throw error_in_image_data("JPEG: Scan segment to be decoded: bad length");
+    // (the segment's length field is not looked at: Read_SOS reads what it needs, :1895-1940)
     int comps[3];
     int id_base = 1;
     for (int i = 0; i < n; i++) {

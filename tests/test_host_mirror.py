@@ -575,6 +575,66 @@ def test_progressive_scans_through_the_wide_bit_buffer(host, oracle, synth):
     assert same == 240
 
 
+def _scan_ends(jpg):
+    """Positions of the markers that end the entropy-coded segments of a file."""
+    out, j = [], jpg.index(b"\xff\xda") + 2
+    while j < len(jpg) - 1:
+        if jpg[j] == 0xFF and jpg[j + 1] != 0 and not 0xD0 <= jpg[j + 1] <= 0xD7:
+            out.append(j)
+        j += 1
+    return out
+
+
+def _damage_near(jpg, end, rng, t):
+    bad = bytearray(jpg)
+    k = int(rng.integers(1, 4))
+    bad[end - k] = int(rng.integers(0, 255))
+    if t % 3 == 0 and k > 1:
+        bad[end - k + 1] = int(rng.integers(0, 255))
+    return bytes(bad)
+
+
+@pytest.mark.parametrize("wide", [1, 0], ids=["wide_buffer", "bytewise_buffer"])
+def test_damage_at_the_end_of_a_scan_is_decoded_as_gid_does(host, oracle, synth, wide):
+    """The last bytes of a scan damaged: the decoder then reads INTO the marker that ends the scan, meets
+    refinement symbols of sizes other than 1, runs that leave their band or the image, end-of-band runs longer
+    than the scan.  GID decodes much of that silently, in its own way (Show_Bits :609-677 puts the marker's two
+    bytes into the bit buffer and carries on behind them; Progressive_AC_Scan :1515-1689 takes any size, walks
+    runs past the band, adds correction bits to the magnitude; Append :1402-1415 holds 2000 points): the host
+    mirror must give the oracle's planes, or raise where it raises.  (A frame whose coefficients leave 16 bits is
+    the documented exception: the oracle flags it, the product path reports it as unsupported.)"""
+    rng = np.random.default_rng(11)
+    host.set_option("wide_bit_buffer", wide)
+    ok = err = 0
+    try:
+        for prog in (False, True):
+            for samp, w, h in (("420", 96, 80), ("444", 64, 48), ("grey", 72, 40)):
+                jpg, _ = synth.encode(pixels_for(synth, 5, w, h, samp), samp, progressive=prog)
+                for end in _scan_ends(jpg)[-6:]:
+                    for t in range(40):
+                        bad = _damage_near(jpg, end, rng, t)
+                        try:
+                            fr, _, _ = oracle.decode(bad)
+                        except Exception:
+                            fr = None
+                        try:
+                            _, planes = host.decode_planes(bad)
+                        except host.GidHostError:
+                            planes = None
+                        if fr is not None and fr.coef_overflow:
+                            continue
+                        assert (fr is None) == (planes is None), (prog, samp, end, t)
+                        if fr is None:
+                            err += 1
+                            continue
+                        ok += 1
+                        for c in range(fr.ncomp):
+                            assert np.array_equal(planes[c], fr.planes[c]), (prog, samp, end, t, c)
+    finally:
+        host.set_option("wide_bit_buffer", 1)
+    assert ok > 300 and err > 300
+
+
 @pytest.mark.gpu
 def test_flat_and_periodic_images_stay_exact(host, oracle, synth, gpu):
     """Flat regions make the bit stream periodic, and a periodic stream need not re-synchronise a
@@ -850,6 +910,25 @@ def test_damaged_progressive_files_are_handed_back(host, oracle, synth, gpu, dev
         assert got == want, (t, kind, got, want)
         same += 1
     assert same == 40 and handed_back >= 10
+
+
+@pytest.mark.gpu
+def test_damage_at_the_end_of_a_scan_on_the_device_path(host, oracle, synth, gpu, device_progressive):
+    """... and with the scans of the progressive frame on the device: what is unusual is handed back, the outcome is
+    the host decoder's (which the CPU suite holds against the oracle)."""
+    rng = np.random.default_rng(12)
+    jpg, _ = synth.encode(pixels_for(synth, 15, 320, 240, "420"), "420", progressive=True)
+    same = 0
+    for end in _scan_ends(jpg)[-6:]:
+        for t in range(20):
+            bad = _damage_near(jpg, end, rng, t)
+            host.set_option("device_progressive_min_bytes", -1)
+            want = _rgb_outcome(host, bad)
+            host.set_option("device_progressive_min_bytes", 0)
+            got = _rgb_outcome(host, bad)
+            assert got == want, (end, t, got, want)
+            same += 1
+    assert same == 120
 
 
 @pytest.mark.gpu
