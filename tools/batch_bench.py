@@ -36,6 +36,8 @@ def main() -> None:
     L = capi.load_library()
     ndev = L.gidcuda_device_count()
     counts = sorted({n for n in (1, 2, 4, 8, ndev) if n <= ndev})
+    if os.environ.get("BATCH_DEVICES"):
+        counts = [int(x) for x in os.environ["BATCH_DEVICES"].split(",")]
     lines = []
     for wl in (sys.argv[1:] or ["cfg3", "cfg2"]):
         w, h, samp, _, desc_txt = bench.WORKLOADS[wl]
@@ -56,7 +58,7 @@ def main() -> None:
             src_recs.append(per)
         # enough images for ~0.5 s per device at the link's rate
         per_dev = max(6, int(9e9 / (w * h)))
-        chunk = 8 if w * h < 4e6 else 1
+        chunk = int(os.environ.get("BATCH_CHUNK", 8 if w * h < 4e6 else 1))   # images per launch
         for n_dev in counts:
             n = per_dev * n_dev
             outs = []
