@@ -113,6 +113,19 @@ inline int dp2a_hi_su(uint32_t a, uint32_t b, int c) {
 // and the host build).
 struct LdgSource {
   const FrameDev *f;
+  static constexpr bool kItemsCanBeSkipped = true;  // no ring of fetches in flight: an item nobody needs is not read
+  // The block of the NEXT item, asked for while this item is computed (the plain loads have no ring that runs
+  // ahead: without this every item starts with the latency of a trip to DRAM).
+  GID_HD void prefetch(bool active, int comp, int bx, int by) const {
+#if defined(__CUDA_ARCH__)
+    if (active) {
+      const int16_t *p = f->plane[comp] + ((size_t)by * (size_t)f->bx[comp] + (size_t)bx) * 64;
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+    }
+#else
+    (void)active; (void)comp; (void)bx; (void)by;
+#endif
+  }
   // where the packed samples of the luma block being emitted go; nothing to hand back
   GID_HD u32x2 *luma_scratch(u32x2 *own) const { return own; }
   GID_HD void release() const {}
@@ -599,12 +612,39 @@ GID_HD void warp_sync() {
 //   frame's rows every lane wrote its run into a row of its own, 8 rows apart: sectors written a third at a
 //   time by different warps were evicted from L2 before they were complete -- twice the DRAM traffic, 0.19 of
 //   the HBM roofline on 1080p 4:2:0 batches against 0.68 unrotated; ncu, profiles/r02_ncu_summary.md.)
+// Which block item `it` is for this lane (the mapping of mcu_item below, without its side effects): for the
+// sources that fetch ahead by hand
+template <int H, int V, bool GREY, bool VERT>
+GID_HD bool item_block(int it, bool active, const FrameDev &f, int lane, int mx, int my, int &comp, int &bxi, int &byi) {
+  comp = 0;
+  bxi = mx;
+  byi = my;
+  if (GREY) return active;
+  if (it < 2) {
+    comp = it + 1;
+  } else if (VERT && V == 1) {
+    bxi = mx * H + (it - 2);
+  } else if (VERT) {
+    bxi = mx * H + (it - 2) / V;
+    byi = V * (my - lane) + 32 * ((it - 2) % V) + lane;
+    active = byi < f.by[0];
+  } else if (H == 1) {
+    byi = my * V + (it - 2);
+  } else {
+    bxi = H * (mx - lane) + 32 * ((it - 2) % H) + lane;
+    byi = my * V + (it - 2) / H;
+    active = bxi < f.bx[0];
+  }
+  return active;
+}
+
 template <int H, int V, bool GREY, bool Q8, bool RGBA, int ROT, class Src>
 GID_HD void mcu_item(int it, bool active, const FrameDev &f, const uint32_t *qw, Src &src, const Scratch &sc,
                      int lane, int mx, int my) {
   int comp = 0, sx = 0, sy = 0;
   int bxi = mx, byi = my;
   Scratch se = sc;
+  const bool lane_has_mcu = active;
   // quarter turns: the tile is 32 MCUs of one COLUMN of MCUs (lane t <-> MCU (mx, my0 + t)), the mirror image of
   // everything above -- see the end of this comment block
   constexpr bool VERT = ROT == TURN_90 || ROT == TURN_270;
@@ -641,8 +681,16 @@ GID_HD void mcu_item(int it, bool active, const FrameDev &f, const uint32_t *qw,
       if (it == 2) warp_sync();             // every lane's chroma samples are in the scratch
     }
   }
+  // the last tile of a column of MCUs is rarely full (1080p 4:2:0: 68 MCU rows = 2 tiles and one of 4 lanes,
+  // whose second half of every block column holds no block at all)
+  if (VERT && Src::kItemsCanBeSkipped && !warp_any(active)) return;
   u32x4 raw[8];
   src.load(active, comp, bxi, byi, raw);
+  if (Src::kItemsCanBeSkipped && it + 1 < (GREY ? 1 : 2 + H * V)) {
+    int c2, bx2, by2;
+    const bool a2 = item_block<H, V, GREY, VERT>(it + 1, lane_has_mcu, f, lane, mx, my, c2, bx2, by2);
+    src.prefetch(a2, c2, bx2, by2);
+  }
   // Chroma samples stay in the scratch for the whole tile.  The luma samples only live from
   // here to the end of the emit: the TMA source lends the ring slot the raw block just came
   // out of for them (no luma scratch of its own: 2 KiB less shared memory per warp, which is

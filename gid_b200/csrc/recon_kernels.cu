@@ -168,6 +168,8 @@ struct TileClaims {
 template <int LAYOUT>
 struct TmaSource {
   using LI = LayoutInfo<LAYOUT>;
+  static constexpr bool kItemsCanBeSkipped = false;  // every item has a slot of the ring armed for it
+  __device__ __forceinline__ void prefetch(bool, int, int, int) const {}  // (the ring runs two items ahead)
   uint32_t slots, full;   // shared-window addresses (this warp)
   uint8_t *slots_gen;     // the ring again, as a generic pointer
   uint32_t lane_off;      // lane * 128 + ((lane & 7) << 4): row `lane`, chunk index pre-xored
