@@ -580,7 +580,6 @@ struct Decoder {
     if (w != expected)
       throw error_in_image_data(fmt("JPEG: expected RST (restart) marker Nb %d; code found %04X; expected %04X",
                                     next_rst, w, expected));
-    bits.reset();
     next_rst = (next_rst + 1) & 7;
     rst_count = im.restart_interval;
     eobrun = 0;
@@ -660,7 +659,10 @@ struct Decoder {
     if (wb.peek(16) != 0xFFD0 + next_rst)
       throw error_in_image_data(fmt("JPEG: expected RST (restart) marker Nb %d; code found %04X; expected %04X",
                                     next_rst, wb.peek(16), 0xFFD0 + next_rst));
-    wb.reset();
+    // The 16 bits are consumed and nothing else changes (:1141-1166): what the buffer holds behind them stays --
+    // 16 bits that merely LOOK like the marker (a stuffed FF followed by Dn) are followed by data already loaded.
+    wb.drop(16);
+    wb.lazy = false;  // past the marker: load ahead again
     next_rst = (next_rst + 1) & 7;
     rst_count = im.restart_interval;
     dc_pred[0] = dc_pred[1] = dc_pred[2] = 0;

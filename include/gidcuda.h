@@ -71,9 +71,9 @@ enum {
  * to_bmp's buffer).  Stride and size (gidcuda_output_geometry) are those of the rotated image.
  * All three are done by the fused kernels themselves, in instances of their own: the half turn writes mirrored
  * runs, rows bottom to top (the price of an unrotated frame); quarter turns store the samples of a block
- * transposed and emit its columns as rows of the turned image (24-byte runs in rows 8 apart: 0.3 - 0.6 of the
- * unrotated rate on the device, the same rate end to end).  Frames outside the fast domain (see
- * GIDCUDA_FLAG_WIDE_COEF) and samplings without a fused kernel rotate in the two-pass kernels. */
+ * transposed, emit its columns as rows of the turned image and work through the frame in tiles of 32 MCUs down
+ * a column (0.75 - 0.9 of the unrotated rate on the device, the same rate end to end).  Frames outside the fast
+ * domain (see GIDCUDA_FLAG_WIDE_COEF) and samplings without a fused kernel rotate in the two-pass kernels. */
 #define GIDCUDA_FLAG_ROTATE_90 0x200u
 #define GIDCUDA_FLAG_ROTATE_180 0x400u
 #define GIDCUDA_FLAG_ROTATE_270 0x600u

@@ -635,6 +635,56 @@ def test_damage_at_the_end_of_a_scan_is_decoded_as_gid_does(host, oracle, synth,
     assert ok > 300 and err > 300
 
 
+def test_damage_around_restart_markers_is_decoded_as_gid_does(host, oracle, synth):
+    """Baseline files with restart intervals, damaged in and around their RSTn markers (a byte changed, dropped,
+    inserted, a stretch cut out, an FF planted): Check_Restart (:1133-1177) consumes the 16 bits it compares and
+    leaves the rest of the bit buffer alone -- 16 bits that merely LOOK like the marker (a stuffed FF followed by
+    Dn) are followed by data the buffer has already loaded.  Outcome and planes must be the oracle's."""
+    rng = np.random.default_rng(5)
+    ok = err = 0
+    for samp, w, h, ri in (("420", 161, 99, 2), ("422", 256, 192, 5), ("444", 120, 88, 1), ("grey", 200, 150, 7)):
+        jpg, _ = synth.encode(pixels_for(synth, 3, w, h, samp), samp, restart_interval=ri)
+        sos = jpg.index(b"\xff\xda")
+        marks = [j for j in range(sos, len(jpg) - 1) if jpg[j] == 0xFF and jpg[j + 1] != 0]
+        for t in range(120):
+            bad = bytearray(jpg)
+            if t % 2:
+                pos = int(rng.integers(sos + 10, len(bad) - 2))
+            else:
+                e = marks[int(rng.integers(0, len(marks)))]
+                pos = max(sos + 10, min(len(bad) - 3, e + int(rng.integers(-3, 3))))
+            kind = t % 5
+            if kind == 0:
+                bad[pos] = int(rng.integers(0, 256))
+            elif kind == 1:
+                del bad[pos]
+            elif kind == 2:
+                bad.insert(pos, int(rng.integers(0, 256)))
+            elif kind == 3:
+                del bad[pos:pos + int(rng.integers(2, 40))]
+            else:
+                bad[pos] = 0xFF
+            bad = bytes(bad)
+            try:
+                fr, _, _ = oracle.decode(bad)
+            except Exception:
+                fr = None
+            try:
+                _, planes = host.decode_planes(bad)
+            except host.GidHostError:
+                planes = None
+            if fr is not None and fr.coef_overflow:
+                continue
+            assert (fr is None) == (planes is None), (samp, t, kind, pos)
+            if fr is None:
+                err += 1
+                continue
+            ok += 1
+            for c in range(fr.ncomp):
+                assert np.array_equal(planes[c], fr.planes[c]), (samp, t, kind, pos, c)
+    assert ok > 100 and err > 200
+
+
 @pytest.mark.gpu
 def test_flat_and_periodic_images_stay_exact(host, oracle, synth, gpu):
     """Flat regions make the bit stream periodic, and a periodic stream need not re-synchronise a
