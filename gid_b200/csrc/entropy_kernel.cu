@@ -603,6 +603,9 @@ __global__ void __launch_bounds__(128) huffman_output_kernel(WholeArgs a) {
     const uint64_t out = run_subsequence<true>(a, tabs, zz, slots, entry, limit, tup, b, pre.y, pre.z, pre.w, &code_bad, &done);
     // a subsequence that ends with the frame's last block stops early: nothing follows it
     if (!code_bad && b + done < a.total_blocks && out != a.exit_[i]) chain_bad = true;
+    // ... and tells where the scan's last code word ended (1 + bit position): past the scan's last bit it was
+    // fed from the padding, which is not what follows the scan in the file
+    if (!code_bad && done != 0 && b + done == a.total_blocks) a.status[3] = (uint32_t)out + 1u;
   }
   // 2: the chain of states does not hold here (not settled: the host can repair it, see
   // gidcuda_job_wait); 8: something the serial decoder would raise on

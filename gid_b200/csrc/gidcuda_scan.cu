@@ -370,6 +370,13 @@ int job_finish_scan(gidcuda_job *job) {
     g_chain_repair_subsequences.fetch_add((long)job->repaired_subsequences, std::memory_order_relaxed);
   }
   if (job->scan_ri == 0 && job->h_status[0] == 0 && job->h_status[2] != blocks) job->h_status[0] = 4;
+  if (job->scan_ri == 0 && job->h_status[0] == 0) {
+    // a valid scan ends within a byte of its last code word (1-bits pad it to the marker, :640-662): whole bytes
+    // left over, or code words fed from the padding (the reference reads the marker's own bytes there), are
+    // what the serial decoder decides about
+    const uint32_t nbits = (uint32_t)(job->scan_len * 8), end = job->h_status[3];
+    if (end == 0 || end - 1u > nbits || nbits - (end - 1u) >= 8u) job->h_status[0] = 16;
+  }
   if (job->scan_ri == 0 && job->h_status[0] != 0) {
     job->state = gidcuda_job::BEGUN;
     return fail(ctx, GIDCUDA_ERR_DATA,

@@ -351,10 +351,11 @@ struct WideBits {
   size_t pos, size;
   uint64_t buf = 0;
   int len = 0, pad = 0;
-  uint8_t memo_marker = 0, bad = 0;
+  uint8_t memo_marker = 0;
   bool stopped = false;  // past the end of the data
   bool lazy = false;     // the next byte is the FF of a marker (or an FF that ends the data): no loading ahead
   bool exact = false;    // bytes were loaded on request: pos and memo_marker are the reference's
+  bool overrun = false;  // bits that are not the scan's entropy-coded data have been consumed
   // Progressive scans: the segment loop carries on where the reference's byte-wise buffer stopped
   // reading.  With `track` set the wide buffer follows that buffer's fill level (it loads a byte
   // whenever it holds fewer bits than are asked for, :622-690) and counts the bytes it would
@@ -364,7 +365,7 @@ struct WideBits {
   size_t ref_loaded = 0;
   WideBits(const uint8_t *d, size_t p, size_t n) : data(d), pos(p), size(n) {}
   void reset() {
-    buf = 0; len = 0; pad = 0; memo_marker = 0; bad = 0; stopped = false; lazy = false; exact = false;
+    buf = 0; len = 0; pad = 0; memo_marker = 0; stopped = false; lazy = false; exact = false; overrun = false;
     ref_len = 0; ref_loaded = 0;
   }
   int real() const { return len - pad; }
@@ -441,7 +442,10 @@ struct WideBits {
     buf <<= n;
     len -= n;
     ref_len -= n;
-    if (pad > len) pad = len;
+    if (pad > len) {
+      pad = len;
+      overrun = true;
+    }
   }
   // Where the byte-wise buffer would stand after the same requests, the scan having begun at
   // `start`: the stream position after the ref_loaded-th data byte (FF 00 counts as one), or just
@@ -862,9 +866,11 @@ struct Decoder {
           }
           // every interval but the last must end where its RSTn begins: all bytes loaded, less
           // than a byte of real bits left (the serial check tolerates more; let it decide then)
+          // (an interval that needed more bits than it has was fed FF bytes here, not what follows it in the file)
+          if (wb.overrun) { failed = true; return; }
           if (sg != nseg - 1) {
             wb.drop(wb.len & 7);
-            if (wb.pos < wb.size || wb.real() >= 8 || wb.bad) { failed = true; return; }
+            if (wb.pos < wb.size || wb.real() >= 8) { failed = true; return; }  // (pos < size: bytes left over, or a marker inside the interval)
           }
         }
         for (int c = 0; c < 3; c++) out[(size_t)w].count[c] = loc[c].n;
