@@ -97,13 +97,16 @@ def make_files(workload: str, count: int, seed0: int) -> list[bytes]:
     return out
 
 
-def files_leg_ours(workload: str, device: int, threads: int, reps: int, pinned: bool = True) -> dict:
+def files_leg_ours(workload: str, device: int, threads: int, reps: int, pinned: bool = True, world: int = 1) -> dict:
     """.jpg bytes in host memory -> RGB8 in host memory: entropy decode on `threads` host threads
     (restart-interval-parallel inside a frame when there are fewer files than threads),
     reconstruction on the B200, through gidhost_batch_decode."""
     from gid_b200 import host_api
     w, h, _, _, _ = WORKLOADS[workload]
     prog, ri, per_call = FILE_FORM[workload]
+    # many ranks on one host share its memory and its link: from four ranks on, fewer files per call and rank (the
+    # pinned image buffers of all ranks together stay what two ranks' are; two ranks saturate the link anyway)
+    per_call = max(2, per_call // max(1, min(world, 8) // 2))
     distinct = make_files(workload, 2, 77)
     files = [distinct[i % 2] for i in range(per_call)]
     # the client's image buffers: pinned host memory (the pixels arrive straight from the device)
@@ -649,7 +652,7 @@ def run_ours(args) -> None:
         # this rank's share of the cores (where the device decodes the scans, 2-4 workers already saturate
         # the device-to-host link: profiles/r01f_files_thread_scaling.txt)
         share = max(1, (os.cpu_count() or 1) // world)
-        files = files_leg_ours(args.workload, local, share, 3)
+        files = files_leg_ours(args.workload, local, share, 3, world=world)
         secs = w * h * files["images_per_call"] * files["calls"] / 1e6 / files["value"]
         files["value"] = sharding.whole_job_rate(w * h * files["images_per_call"] * files["calls"] / 1e6, world,
                                                  sharding.max_over_ranks(secs, dev))
