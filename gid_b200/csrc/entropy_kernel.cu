@@ -125,6 +125,9 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
   asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
   return v;
 }
+__device__ __forceinline__ void sts_s16(uint32_t a, int v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((short)v) : "memory");
+}
 constexpr uint32_t kOffMaxcode = 2048, kOffValoff = 2048 + 68, kOffVals = 2048 + 136;
 static_assert(sizeof(HuffDev) == kOffVals + 256, "HuffDev layout");
 
@@ -148,8 +151,8 @@ __device__ __forceinline__ int symbol_in(uint32_t hi, uint32_t tab, int &codelen
 }
 
 // A code and the value bits behind it are at most 16 + 15 bits: both come out of one 32-bit window of the
-// buffer, which is then advanced once.  (dc, ac, zz: shared-window addresses; blk: the thread's staging block)
-__device__ __forceinline__ bool decode_block(Bits &b, uint32_t dc, uint32_t ac, int &pred, int16_t *blk, uint32_t zz,
+// buffer, which is then advanced once.  (dc, ac, zz, blk: shared-window addresses; blk = the thread's staging block)
+__device__ __forceinline__ bool decode_block(Bits &b, uint32_t dc, uint32_t ac, int &pred, uint32_t blk, uint32_t zz,
                                              int limbits) {
   if (b.len <= 32) b.refill();
   uint32_t hi = (uint32_t)(b.buf >> 32);
@@ -164,7 +167,7 @@ __device__ __forceinline__ bool decode_block(Bits &b, uint32_t dc, uint32_t ac, 
     if (!within_bits(pred, limbits)) return false;
   }
   b.drop(cl + n);
-  blk[0] = (int16_t)pred;
+  sts_s16(blk, pred);
   int coef = 0;
   for (;;) {
     if (b.len <= 32) b.refill();
@@ -182,7 +185,7 @@ __device__ __forceinline__ bool decode_block(Bits &b, uint32_t dc, uint32_t ac, 
     if (m > limbits) return false;  // a value of category m is below 2**m
     if (m) {
       GIDK_ASSERT(coef >= 1 && coef <= 63);
-      blk[lds_u8(zz + (uint32_t)coef)] = (int16_t)extend((hi << cl) >> (32 - m), m);
+      sts_s16(blk + 2u * lds_u8(zz + (uint32_t)coef), extend((hi << cl) >> (32 - m), m));
     }
     b.drop(cl + m);
     if (coef == 63) break;
@@ -217,7 +220,11 @@ __global__ void __launch_bounds__(128) huffman_intervals_kernel(ScanArgs a) {
   const uint32_t it = warp * a.lanes + lane;
   if (lane >= a.lanes || it >= a.nintervals) return;
   uint4 *mine = reinterpret_cast<uint4 *>(stage + threadIdx.x * kStageStride);
-  const uint32_t tabs_s = (uint32_t)__cvta_generic_to_shared(tabs), zz_s = (uint32_t)__cvta_generic_to_shared(zz);
+  uint32_t tabs_s = (uint32_t)__cvta_generic_to_shared(tabs), zz_s = (uint32_t)__cvta_generic_to_shared(zz);
+  uint32_t mine_s = (uint32_t)__cvta_generic_to_shared(mine);
+  // (made opaque: otherwise the compiler re-derives the shared window's base -- S2UR SR_CgaCtaId + LEA -- at every
+  // symbol instead of keeping three registers)
+  asm volatile("" : "+r"(tabs_s), "+r"(zz_s), "+r"(mine_s));
   Bits b;
   b.start(a.data + __ldg(a.begin + it), a.data + __ldg(a.end + it));
   int pred[3] = {0, 0, 0};  // (registers: only indexed by the unrolled component loop)
@@ -236,7 +243,7 @@ __global__ void __launch_bounds__(128) huffman_intervals_kernel(ScanArgs a) {
 #pragma unroll
           for (int j = 0; j < 8; j++) mine[j] = z;
           ok = decode_block(b, tabs_s + (uint32_t)(c * sizeof(HuffDev)), tabs_s + (uint32_t)((3 + c) * sizeof(HuffDev)),
-                            pred[c], reinterpret_cast<int16_t *>(mine), zz_s, a.limbits[c]);
+                            pred[c], mine_s, zz_s, a.limbits[c]);
           uint4 *dst = reinterpret_cast<uint4 *>(a.plane[c] + blockno * 64);
 #pragma unroll
           for (int j = 0; j < 8; j++) dst[j] = mine[j];
