@@ -45,8 +45,13 @@ private package GID.CUDA is
   pragma Convention (C, Table_Array);
 
   Out_RGB8           : constant := 0;
-  Out_BGR8_Bottom_Up : constant := 1;
+  Out_BGR8_Bottom_Up : constant := 1;         --  test/to_bmp.adb's buffer
+  Out_RGBA8          : constant := 2;
   Flag_Packed_Rows   : constant := 16#100#;
+  --  GID.Display_Orientation applied while the pixels are written (Set_X_Y of test/to_bmp.adb:104-122)
+  Flag_Rotate_90     : constant := 16#200#;
+  Flag_Rotate_180    : constant := 16#400#;
+  Flag_Rotate_270    : constant := 16#600#;
   Flag_Wide_Coef     : constant := 16#800#;   --  see Fast_Coef_Limit
 
   --  = struct gidcuda_frame_desc

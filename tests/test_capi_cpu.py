@@ -150,3 +150,21 @@ def test_job_entry_points_reject_null_jobs(gidcuda_lib):
     assert L.gidcuda_host_is_pinned(None) == 0
     assert L.gidcuda_counter(b"chain_repairs") == 0 and L.gidcuda_counter(b"no such counter") == -1
     assert L.gidcuda_set_option(b"chain_repair", 1) == 0 and L.gidcuda_set_option(b"no such option", 1) == -1
+
+
+def test_ada_binding_constants_match_the_header():
+    """gid_b200/ada/gid-cuda.ads (the binding a GID maintainer would add) names the same flag and
+    format values as include/gidcuda.h."""
+    import re
+    from gid_b200 import capi
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ads = open(os.path.join(root, "gid_b200", "ada", "gid-cuda.ads")).read()
+    hdr = open(os.path.join(root, "include", "gidcuda.h")).read()
+    ada = {m.group(1).upper(): int(m.group(2).replace("16#", "").replace("#", ""), 16 if "16#" in m.group(2) else 10)
+           for m in re.finditer(r"^\s*((?:Out|Flag)_\w+)\s*:\s*constant\s*:=\s*([0-9#A-Fa-f]+);", ads, re.M)}
+    c = {m.group(1): int(m.group(2).rstrip("u"), 0)
+         for m in re.finditer(r"#define GIDCUDA_((?:OUT|FLAG)_\w+) (0x[0-9A-Fa-f]+u?|[0-9]+u?)\b", hdr)}
+    assert len(ada) >= 8
+    for name, value in ada.items():
+        assert c[name] == value, name
+    assert capi.FLAG_ROTATE_270 == c["FLAG_ROTATE_270"] and capi.OUT_RGBA8 == c["OUT_RGBA8"]
