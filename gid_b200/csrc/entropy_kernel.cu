@@ -23,6 +23,8 @@
 // the error behaviour of the reference is reproduced exactly.
 #include "recon_launch.h"
 
+#include <cstdlib>
+
 // -DGIDK_CHECKED: device-side assertions on every coefficient address and table index (a debug
 // build for the GPU test suite; compute-sanitizer is not available on the test pool).
 #if defined(GIDK_CHECKED)
@@ -270,6 +272,8 @@ cudaError_t launch_huffman_intervals(const ScanArgs &args, int num_sms, cudaStre
   // as few lanes per warp as keep the warps within what the SMs hold at once (16 per SM)
   a.lanes = 1;
   while (a.lanes < 32u && (a.nintervals + a.lanes - 1) / a.lanes > (uint32_t)num_sms * 16u) a.lanes *= 2;
+  static const int forced = [] { const char *e = getenv("GIDCUDA_INTERVAL_LANES"); return e ? atoi(e) : 0; }();  // (tuning)
+  if (forced >= 1 && forced <= 32) a.lanes = (uint32_t)forced;
   const uint32_t nwarps = (a.nintervals + a.lanes - 1) / a.lanes;
   huffman_intervals_kernel<<<(nwarps + 3) / 4, 128, 0, stream>>>(a);
   return cudaGetLastError();
