@@ -635,6 +635,23 @@ def test_damage_at_the_end_of_a_scan_is_decoded_as_gid_does(host, oracle, synth,
     assert ok > 300 and err > 300
 
 
+def test_dc_scans_of_single_components_are_decoded_as_t81_says(host, oracle, synth):
+    """A KNOWN DIFFERENCE from GID: in a DC scan that carries some but not all components of
+    a colour frame, Progressive_DC_Scan numbers the layers of its image array by the scan's components
+    (gid-decoding_jpg.adb:1286, :1352), so the DC terms of a Cb-only scan land in the Y layer.  The mirror decodes
+    such scans as T.81 says: its chroma planes are the encoder's.  (Should GID ever change, the last assertion
+    says so.)"""
+    Y, CB, CR = [0], [1], [2]
+    sc = [(Y, 0, 0, 0, 1), (CB, 0, 0, 0, 1), (CR, 0, 0, 0, 1), (Y, 1, 63, 0, 0), (CB, 1, 63, 0, 0), (CR, 1, 63, 0, 0),
+          (Y, 0, 0, 1, 0), (CB, 0, 0, 1, 0), (CR, 0, 0, 1, 0)]
+    jpg, enc = synth.encode(pixels_for(synth, 14, 200, 120, "420"), "420", quality=85, progressive=True, scans=sc)
+    _, planes = host.decode_planes(jpg)
+    for c in (1, 2):
+        assert np.array_equal(planes[c], enc.planes[c])
+    fr, _, _ = oracle.decode(jpg)
+    assert not np.array_equal(fr.planes[1], enc.planes[1])
+
+
 def test_damage_around_restart_markers_is_decoded_as_gid_does(host, oracle, synth):
     """Baseline files with restart intervals, damaged in and around their RSTn markers (a byte changed, dropped,
     inserted, a stretch cut out, an FF planted): Check_Restart (:1133-1177) consumes the 16 bits it compares and
