@@ -469,6 +469,8 @@ def run_ours(args) -> None:
     w, h, samp, per_step, desc = WORKLOADS[args.workload]
     ctx = GidCuda(local)
     capi.set_option("plan_pdl", args.pdl)
+    if args.turn_tile_rows:
+        capi.set_option("turn_tile_rows", args.turn_tile_rows)   # (tuning: tile shape of frames turned by a quarter)
 
     # ---- synthetic inputs: a ring of distinct step-batches so that consecutive steps never
     # reuse L2-resident data (every step-batch is also larger than the 126 MB L2) ---------
@@ -743,6 +745,8 @@ def main() -> None:
                     help="launch streams for the device-resident leg (default 1: the kernel's own figure)")
     ap.add_argument("--rotate", type=int, default=0, choices=[0, 90, 180, 270],
                     help="apply a display orientation while writing the pixels (GIDCUDA_FLAG_ROTATE_*; not the default workload)")
+    ap.add_argument("--turn-tile-rows", type=int, default=0, choices=[0, 4, 8, 16, 32],
+                    help="tuning: MCU rows per tile of frames turned by a quarter (0 = the library chooses)")
     ap.add_argument("--rgba", action="store_true", help="R,G,B,A pixels (GIDCUDA_OUT_RGBA8) instead of the benchmark's R,G,B")
     ap.add_argument("--pdl", type=int, default=1, choices=[0, 1],
                     help="plan launches as programmatic dependent launches (library default 1); 0 = every launch "

@@ -46,7 +46,7 @@ def _sources(d: str, exts: tuple[str, ...]) -> list[str]:
 def build_cuda(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIB, exist_ok=True)
     out = os.path.join(LIB, "libgidcuda.so")
-    deps = _sources(CSRC, (".cu", ".cuh", ".h")) + [os.path.join(ROOT, "include", "gidcuda.h")]
+    deps = _sources(CSRC, (".cu", ".cuh", ".h", ".hpp")) + [os.path.join(ROOT, "include", "gidcuda.h")]
     if force or _stale(out, deps):
         srcs = _sources(CSRC, (".cu",))
         cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + srcs + ["-o", out]

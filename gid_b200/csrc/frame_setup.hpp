@@ -40,6 +40,7 @@ struct Geometry {
   int out_format = 0;
   int rotate = 0;  // 0, 1 = Rotation_90, 2 = Rotation_180, 3 = Rotation_270 (GIDCUDA_FLAG_ROTATE_*)
   uint32_t ntiles = 0;
+  int turn_tile_rows = 0;  // fused frames turned by a quarter: MCU rows per tile (32, 16, 8 or 4), see make_geometry
 };
 
 inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -68,6 +69,12 @@ inline int32_t fast_coef_limit(const gidcuda_frame_desc *d, int c) {
 
 // Validates a frame descriptor and derives everything the launch needs.
 // Mirrors Read_SOF / Read_SOS geometry (gid-decoding_jpg.adb:244-276, :1945-1951).
+// tuning / tests: 0 = choose (default), else force the rows per tile of frames turned by a quarter (32, 16, 8, 4)
+inline int &turn_tile_rows_option() {
+  static int rows = 0;
+  return rows;
+}
+
 inline int make_geometry(std::string *err, const gidcuda_frame_desc *d, Geometry *g) {
   if (!d) return geo_fail(err, GIDCUDA_ERR_BAD_ARGUMENT, "null frame descriptor");
   if (d->width < 1 || d->width > 65535 || d->height < 1 || d->height > 65535)
@@ -149,9 +156,29 @@ inline int make_geometry(std::string *err, const gidcuda_frame_desc *d, Geometry
   } else {
     g->layout = LAYOUT_GENERIC;
   }
-  if (g->layout != LAYOUT_GENERIC && (g->rotate & 1))  // quarter turns: tiles run down the columns of MCUs
-    g->ntiles = (uint32_t)((size_t)g->mcux * ((g->mcuy + kTileMcusSetup - 1) / kTileMcusSetup));
-  else
+  g->turn_tile_rows = 0;
+  if (g->layout != LAYOUT_GENERIC && (g->rotate & 1)) {
+    // Quarter turns: a tile is `rows` MCUs down times 32 / rows MCUs across (mcu_item).  The shape that costs
+    // least: the number of tiles, weighted by what a tile of that shape was measured to cost (its runs along a
+    // row of the turned image are rows x 24 bytes: on 1080p 4:2:0 batches a tile of 16 / 8 / 4 rows takes 1.06 /
+    // 1.12 / 1.29 times as long as one of 32; profiles/r02_rotations.jsonl).  A frame 32 k MCUs high keeps 32
+    // rows; a 1080p 4:2:0 frame is 68 MCUs high -- 32 + 32 + 4 would leave a third of its tiles an eighth full --
+    // and takes 8.
+    size_t best = 0, best_tiles = 0;
+    const int opt = turn_tile_rows_option();
+    const int forced = opt == 32 || opt == 16 || opt == 8 || opt == 4 ? opt : 0;
+    for (int rows = kTileMcusSetup; rows >= 4; rows /= 2) {
+      const int cols = kTileMcusSetup / rows;
+      const size_t n = (size_t)((g->mcux + cols - 1) / cols) * (size_t)((g->mcuy + rows - 1) / rows);
+      const size_t cost = n * (size_t)(rows == 32 ? 100 : (rows == 16 ? 106 : (rows == 8 ? 112 : 129)));
+      if (forced == rows || (forced == 0 && (best == 0 || cost < best))) {
+        best = cost;
+        best_tiles = n;
+        g->turn_tile_rows = rows;
+      }
+    }
+    g->ntiles = (uint32_t)best_tiles;
+  } else
     g->ntiles = layout_linear(g->layout) || g->layout == LAYOUT_GENERIC
                     ? (uint32_t)(((size_t)g->mcux * g->mcuy + kTileMcusSetup - 1) / kTileMcusSetup)
                     : (uint32_t)((size_t)g->mcuy * ((g->mcux + kTileMcusSetup - 1) / kTileMcusSetup));
@@ -182,7 +209,8 @@ inline void fill_frame_dev(const gidcuda_frame_desc *d, const Geometry &g, const
   const bool fused = g.layout != LAYOUT_GENERIC;
   // the generic kernels read the rotation here; the fused kernels are instances per orientation
   f->out_format = fused ? g.out_format : (g.out_format | (g.rotate << 8));
-  f->tile_base = tile_base;
+  (void)tile_base;
+  f->tile_rows = (uint32_t)g.turn_tile_rows;
   f->q8 = g.q8 ? 1 : 0;
   f->flags = 0;
   const int turn = fused ? g.rotate : 0;

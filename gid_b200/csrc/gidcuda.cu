@@ -691,6 +691,10 @@ extern "C" int gidcuda_set_option(const char *name, int value) {
     g_chain_repair = value ? 1 : 0;
     return GIDCUDA_OK;
   }
+  if (strcmp(name, "turn_tile_rows") == 0) {  // tuning: MCU rows per tile of frames turned by a quarter (0 = choose)
+    gidk::turn_tile_rows_option() = value;
+    return GIDCUDA_OK;
+  }
   if (strcmp(name, "blocking_wait") == 0) {
     g_blocking_wait = value ? 1 : 0;
     return GIDCUDA_OK;

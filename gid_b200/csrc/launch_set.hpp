@@ -269,12 +269,13 @@ class LaunchSet {
     memset(&t, 0, sizeof t);
     t.frame = frame_index;
     if (g.rotate & 1) {
-      // quarter turns: 32 MCUs of one column of MCUs (mcu_item); the plain-load kernel finds its blocks from
-      // the frame descriptor, no coordinates.  Tiles of one column after each other: they fill the same rows
-      // of the turned image side by side.
-      for (int mx = 0; mx < g.mcux; mx++)
-        for (int my0 = 0; my0 < g.mcuy; my0 += kTileMcus) {
-          t.m0 = (uint32_t)my0 * (uint32_t)g.mcux + (uint32_t)mx;
+      // quarter turns: turn_tile_rows MCUs down x 32 / turn_tile_rows across (mcu_item); the plain-load kernel
+      // finds its blocks from the frame descriptor, no coordinates.  Tiles of one column of tiles after each
+      // other: they fill the same rows of the turned image side by side.
+      const int rows = g.turn_tile_rows, cols = kTileMcus / rows;
+      for (int mx0 = 0; mx0 < g.mcux; mx0 += cols)
+        for (int my0 = 0; my0 < g.mcuy; my0 += rows) {
+          t.m0 = (uint32_t)my0 * (uint32_t)g.mcux + (uint32_t)mx0;
           tiles.push_back(t);
         }
       return;

@@ -68,7 +68,7 @@ struct FrameDev {
   int32_t bx[3], by[3];     // block grid per plane = mcu grid * sampling
   int32_t samp_h[3], samp_v[3];
   int32_t out_format;
-  uint32_t tile_base;       // index of this frame's first tile in the launch
+  uint32_t tile_rows;       // frames turned by a quarter: MCU rows per tile (32, 16, 8 or 4; 32 / tile_rows MCU columns)
   // Quantisation tables, natural order, two per 32-bit word:
   //   q8 == 1 (all entries <= 255): word k = q[2k] | q[2k+1] << 24   (dp2a operand)
   //   q8 == 0:                      word k = q[2k] | q[2k+1] << 16
@@ -605,10 +605,12 @@ GID_HD void warp_sync() {
 //   halves of each 48-byte run were written a whole block of arithmetic apart: partially written
 //   sectors were evicted and re-fetched, +38 % DRAM reads and +24 % writes on 4:2:0, ncu.)
 //   The chroma samples of MCU j / 2 were left in the scratch by lane j / 2.
-//   Quarter turns (ROT = TURN_90 / TURN_270): a row of the turned image is a COLUMN of the frame, so the tile is
-//   32 MCUs of one column of MCUs and the luma items walk its block columns 32 consecutive blocks at a time
-//   (item 2 + V*sx + part: blocks 32*part .. 32*part + 31 of block column sx): the lanes of a warp then
-//   write neighbouring 24-byte runs of the same rows of the turned image, as above.  (With the tiles along the
+//   Quarter turns (ROT = TURN_90 / TURN_270): a row of the turned image is a COLUMN of the frame, so the tile
+//   runs DOWN the frame -- th MCU rows x 32 / th MCU columns (FrameDev::tile_rows: 32 x 1 where the frame's
+//   height fills such tiles, flatter ones where it does not) -- and the luma items walk its block columns th
+//   consecutive blocks at a time (item 2 + V*sx + part: blocks th*part .. th*part + th - 1 of block column sx
+//   of every MCU column): the lanes of one MCU column then write neighbouring 24-byte runs of the same rows
+//   of the turned image, as above.  (With the tiles along the
 //   frame's rows every lane wrote its run into a row of its own, 8 rows apart: sectors written a third at a
 //   time by different warps were evicted from L2 before they were complete -- twice the DRAM traffic, 0.19 of
 //   the HBM roofline on 1080p 4:2:0 batches against 0.68 unrotated; ncu, profiles/r02_ncu_summary.md.)
@@ -625,9 +627,10 @@ GID_HD bool item_block(int it, bool active, const FrameDev &f, int lane, int mx,
   } else if (VERT && V == 1) {
     bxi = mx * H + (it - 2);
   } else if (VERT) {
+    const int th = (int)f.tile_rows, r = lane & (th - 1);
     bxi = mx * H + (it - 2) / V;
-    byi = V * (my - lane) + 32 * ((it - 2) % V) + lane;
-    active = byi < f.by[0];
+    byi = V * (my - r) + th * ((it - 2) % V) + r;
+    active = mx < f.mcux && byi < f.by[0];
   } else if (H == 1) {
     byi = my * V + (it - 2);
   } else {
@@ -655,15 +658,17 @@ GID_HD void mcu_item(int it, bool active, const FrameDev &f, const uint32_t *qw,
       sx = it - 2;
       bxi = mx * H + sx;
     } else if (VERT) {
-      const int part = (it - 2) % V;        // which 32 of the block column's 32 * V luma blocks
+      // the tile: th MCU rows x 32 / th MCU columns; lane = (column dx, row r) = (lane / th, lane % th)
+      const int th = (int)f.tile_rows, r = lane & (th - 1);
+      const int part = (it - 2) % V;        // which th of a block column's th * V luma blocks
       sx = (it - 2) / V;
-      const int j = 32 * part + lane;       // luma block of this lane inside the tile's block column
+      const int j = th * part + r;          // luma block of this lane inside its block column
       bxi = mx * H + sx;
-      byi = V * (my - lane) + j;            // my - lane = first MCU of the tile
-      active = byi < f.by[0];
-      sy = lane & (V - 1);                  // = j % V
-      se.cb = sc.cb + ((j / V) - lane);     // scratch column of MCU j / V
-      se.cr = sc.cr + ((j / V) - lane);
+      byi = V * (my - r) + j;               // my - r = first MCU row of the tile
+      active = mx < f.mcux && byi < f.by[0];
+      sy = r & (V - 1);                     // = j % V (th is a multiple of V)
+      se.cb = sc.cb + ((j / V) - r);        // scratch column of MCU j / V of the same MCU column
+      se.cr = sc.cr + ((j / V) - r);
       if (it == 2) warp_sync();
     } else if (H == 1) {
       sy = it - 2;

@@ -287,11 +287,11 @@ __device__ __forceinline__ void run_mcu(bool active, const FrameDev &f, Src &src
 // no MCU (tail of the frame / of the MCU row).
 template <int LAYOUT, bool VERT = false>
 __device__ __forceinline__ bool tile_mcu(const FrameDev &f, uint32_t m0, uint32_t t, int &mx, int &my) {
-  if (VERT) {  // quarter turns: 32 MCUs of one column of MCUs, from MCU m0 down
-    const uint32_t my0 = m0 / (uint32_t)f.mcux;
-    mx = (int)(m0 - my0 * (uint32_t)f.mcux);
-    my = (int)(my0 + t);
-    return my < f.mcuy;
+  if (VERT) {  // quarter turns: tile_rows MCUs down x 32 / tile_rows MCUs across, from MCU m0
+    const uint32_t my0 = m0 / (uint32_t)f.mcux, th = f.tile_rows;
+    mx = (int)(m0 - my0 * (uint32_t)f.mcux + t / th);
+    my = (int)(my0 + (t & (th - 1u)));
+    return mx < f.mcux && my < f.mcuy;
   }
   if (LayoutInfo<LAYOUT>::linear) {
     const uint32_t m = m0 + t;

@@ -416,6 +416,10 @@ class Emu:
         self.lib = ctypes.CDLL(os.path.join(_HERE, "libemurecon.so"))
         self.lib.emu_reconstruct.restype = ctypes.c_int
 
+    def set_turn_tile_rows(self, rows: int) -> None:
+        """Force the rows per tile of frames turned by a quarter (32, 16, 8, 4; 0 = make_geometry chooses)."""
+        self.lib.emu_set_turn_tile_rows(ctypes.c_int(rows))
+
     def layout(self, desc) -> int:
         """The kernel family a frame runs (recon_body.cuh, Layout; 6 = the generic two-pass kernels)."""
         return int(self.lib.emu_layout(ctypes.byref(desc)))

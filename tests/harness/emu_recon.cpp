@@ -21,6 +21,9 @@ extern "C" int emu_layout(const gidcuda_frame_desc *desc) {
   return rc != 0 ? rc : (int)g.layout;
 }
 
+// tests: force the rows per tile of frames turned by a quarter (0 = let make_geometry choose)
+extern "C" void emu_set_turn_tile_rows(int rows) { turn_tile_rows_option() = rows; }
+
 extern "C" int emu_reconstruct(const gidcuda_frame_desc *desc, const int16_t *const planes[3],
                                uint8_t *pixels, char *err, size_t errlen) {
   Geometry g;
@@ -87,8 +90,9 @@ extern "C" int emu_reconstruct(const gidcuda_frame_desc *desc, const int16_t *co
   std::vector<uint32_t> tile_m0;
   const bool vert = (f.flags & (FRAME_ROT90 | FRAME_ROT270)) != 0;  // quarter turns: tiles down the columns of MCUs
   if (vert) {
-    for (int mx = 0; mx < f.mcux; mx++)
-      for (int my0 = 0; my0 < f.mcuy; my0 += kTileMcusSetup) tile_m0.push_back((uint32_t)(my0 * f.mcux + mx));
+    const int rows = g.turn_tile_rows, cols = kTileMcusSetup / rows;
+    for (int mx0 = 0; mx0 < f.mcux; mx0 += cols)
+      for (int my0 = 0; my0 < f.mcuy; my0 += rows) tile_m0.push_back((uint32_t)(my0 * f.mcux + mx0));
   } else if (linear) {
     for (uint32_t m0 = 0; m0 < nmcu; m0 += kTileMcusSetup) tile_m0.push_back(m0);
   } else {
@@ -102,9 +106,10 @@ extern "C" int emu_reconstruct(const gidcuda_frame_desc *desc, const int16_t *co
         int mx, my;
         bool active;
         if (vert) {
-          mx = (int)(m0 % (uint32_t)f.mcux);
-          my = (int)(m0 / (uint32_t)f.mcux) + t;
-          active = my < f.mcuy;
+          const int th = (int)f.tile_rows;
+          mx = (int)(m0 % (uint32_t)f.mcux) + t / th;
+          my = (int)(m0 / (uint32_t)f.mcux) + (t & (th - 1));
+          active = mx < f.mcux && my < f.mcuy;
         } else if (linear) {  // tile_mcu of recon_kernels.cu
           const uint32_t m = m0 + (uint32_t)t;
           my = (int)(m / (uint32_t)f.mcux);

@@ -141,6 +141,26 @@ def test_quarter_turns_in_the_fused_kernels(emu, oracle, synth, gidcuda_lib, sam
     _check_turned(emu, gidcuda_lib, fr, capi.FLAG_ROTATE_270, np.rot90(ref, -1), samp)
 
 
+@pytest.mark.parametrize("rows", [32, 16, 8, 4])
+@pytest.mark.parametrize("samp", ["grey", "444", "422", "420", "440", "411"])
+def test_quarter_turn_tiles_of_every_shape(emu, oracle, synth, gidcuda_lib, samp, rows):
+    """Frames turned by a quarter are worked through in tiles of `rows` MCUs down x 32 / rows across (make_geometry
+    picks the shape that fills best; forced here): every shape, frames with cut tiles in both directions."""
+    from gid_b200 import capi
+    emu.set_turn_tile_rows(rows)
+    try:
+        for w, h in ((211, 77), (72, 1088), (600, 40)):
+            fr = synth.planes_only(pixels_for(synth, 29, w, h, samp), samp)
+            ref = oracle.reconstruct(fr)
+            for flag, want in ((capi.FLAG_ROTATE_90, np.rot90(ref, 1)), (capi.FLAG_ROTATE_270, np.rot90(ref, -1))):
+                d = frame_desc(fr, flag | capi.FLAG_PACKED_ROWS)
+                assert emu.layout(d) != 6
+                got = emu.reconstruct(d, fr.planes, 3 * h, w)[:, :3 * h].reshape(w, h, 3)
+                assert np.array_equal(got, want), (samp, rows, w, h, flag)
+    finally:
+        emu.set_turn_tile_rows(0)
+
+
 def test_idct_blocks_match_oracle(emu, oracle):
     """Block-level: the kernel IDCT (shortcut folded into the rounding constant,
     column shortcut dropped, re-associated rotations) == GID's, on blocks built
